@@ -1,0 +1,127 @@
+"""Loader and builder for libfnd_b200.so — the C-ABI library that holds every CUDA kernel of this package.
+
+The library is built in-tree with plain ``nvcc`` for sm_100a only (no torch headers, no JIT cache) and is
+bound with ``ctypes``: the Python side passes raw device pointers, sizes and the CUDA stream handle, exactly
+what a cgo/JNI/ctypes binding in any other host language would pass.
+
+There is deliberately no fallback: if the library is missing or a symbol declared in ``include/fnd_b200.h``
+is absent, loading raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import re
+import subprocess
+import sys
+from typing import Dict, List, Optional
+
+_PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+_REPO_DIR = os.path.dirname(_PKG_DIR)
+LIB_PATH = os.path.join(_PKG_DIR, "libfnd_b200.so")
+HEADER_PATH = os.path.join(_REPO_DIR, "include", "fnd_b200.h")
+CSRC_DIR = os.path.join(_PKG_DIR, "csrc")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-lineinfo", "-O3", "-std=c++17",
+    "--shared", "-Xcompiler", "-fPIC",
+    "-cudart", "static",
+]
+
+
+def _sources() -> List[str]:
+    return [os.path.join(CSRC_DIR, "fnd_api.cu")]
+
+
+def _deps() -> List[str]:
+    out = [HEADER_PATH]
+    for fn in sorted(os.listdir(CSRC_DIR)):
+        if fn.endswith((".cu", ".cuh", ".h")):
+            out.append(os.path.join(CSRC_DIR, fn))
+    return out
+
+
+def needs_build() -> bool:
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    return any(os.path.getmtime(p) > t for p in _deps())
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile libfnd_b200.so with nvcc for sm_100a (cross-compiles without a GPU)."""
+    if not force and not needs_build():
+        return LIB_PATH
+    nvcc = os.environ.get("NVCC", "nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + _sources()
+    proc = subprocess.run(cmd, cwd=_REPO_DIR, capture_output=True, text=True)
+    if proc.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + proc.stdout + proc.stderr)
+    if verbose:
+        sys.stderr.write(proc.stderr)
+    return LIB_PATH
+
+
+def declared_symbols() -> List[str]:
+    """Every function name declared in include/fnd_b200.h."""
+    with open(HEADER_PATH, "r", encoding="utf-8") as f:
+        src = f.read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    src = re.sub(r"//[^\n]*", "", src)
+    return sorted(set(re.findall(r"\b(fnd_[a-z0-9_]+)\s*\(", src)))
+
+
+_lib: Optional[ctypes.CDLL] = None
+
+_c_void_p = ctypes.c_void_p
+_c_int = ctypes.c_int
+_c_size_t = ctypes.c_size_t
+_c_float = ctypes.c_float
+_c_u64 = ctypes.c_uint64
+
+
+def _signatures() -> Dict[str, tuple]:
+    return {
+        "fnd_version": (_c_int, []),
+        "fnd_build_arch": (ctypes.c_char_p, []),
+        "fnd_gemm_scratch_bytes": (_c_size_t, [_c_int] * 4),
+        "fnd_gemm_bf16": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_void_p, _c_void_p, _c_int, _c_int,
+                                   _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,
+                                   _c_void_p, _c_size_t, _c_void_p]),
+    }
+
+
+def load() -> ctypes.CDLL:
+    """Load the library (building it first if the sources are newer) and bind every declared symbol."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if needs_build():
+        if os.environ.get("FND_NO_BUILD"):
+            raise RuntimeError(f"{LIB_PATH} is missing or stale and FND_NO_BUILD is set")
+        build()
+    lib = ctypes.CDLL(LIB_PATH)
+    sigs = _signatures()
+    for name in declared_symbols():
+        if not hasattr(lib, name):
+            raise RuntimeError(f"libfnd_b200.so does not export {name} declared in include/fnd_b200.h")
+        if name in sigs:
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = sigs[name]
+    _lib = lib
+    return lib
+
+
+class FndError(RuntimeError):
+    pass
+
+
+def check(status: int, what: str) -> None:
+    if status == 0:
+        return
+    if status <= -1000:
+        raise FndError(f"{what}: CUDA runtime error {-status - 1000}")
+    if status < 0:
+        raise FndError(f"{what}: invalid argument / host error {status}")
+    raise FndError(f"{what}: device-side error code {status}")

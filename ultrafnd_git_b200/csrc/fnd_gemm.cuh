@@ -1,0 +1,409 @@
+// fnd_gemm.cuh — grouped, warp-specialised tcgen05 GEMM for sm_100a.
+//
+//   C[M,N] = sum_k A[m,k] * B[n,k]      (bf16 operands, fp32 accumulation in TMEM)
+//
+// One launch runs a TABLE of independent problems (GemmProblem, in device memory); each CTA owns one
+// (tile_m, tile_n, k-split) work item of one problem.  Operands arrive by TMA (SWIZZLE_128B) into a
+// 3-stage shared-memory ring, a single elected thread issues tcgen05.mma (UMMA 128 x BN x 16), the
+// accumulator lives in TMEM and four epilogue warps read it back with tcgen05.ld.
+//
+// Either operand may be K-major (contraction index contiguous in memory: activations x weights of
+// nn.Linear) or MN-major (row index contiguous: what dgrad needs for W and wgrad needs for dY and X),
+// selected by template flags, so forward, dgrad and wgrad all read the SAME row-major tensors — no
+// transposed copies are ever materialised.
+//
+// Precision modes: ncombo == 1 is plain bf16; ncombo == 3 is "fp32x3": every operand is stored as a
+// bf16 (hi, lo) pair and the k-loop runs the three products Ah*Bh + Ah*Bl + Al*Bh, which reproduces
+// fp32 GEMM to ~2^-17 relative while staying on the tensor pipe.
+//
+// Split-K: each split writes its fp32 partial tile to a workspace, bumps a per-tile counter, and the
+// LAST arriving CTA sums the partials in split order (deterministic) and runs the epilogue.
+//
+// Replaces (reference, all via ATen addmm on CPU): nn.Linear forward/backward at
+//   src/models/fusion/cross_modal_transformer.py:96-102,122-129,147-150,186,197 and
+//   src/models/fusion/deep_truth_classifier.py:121-128,162.
+#pragma once
+#include "fnd_common.cuh"
+
+namespace fnd {
+
+constexpr int kGemmBM = 128;          // UMMA M (rows of A per tile)
+constexpr int kGemmBK = 64;           // contraction elements per stage (128 B of bf16)
+constexpr int kGemmStages = 3;
+constexpr int kGemmStageBytesA = kGemmBM * kGemmBK * 2;   // 16 KB
+constexpr int kGemmStageBytesB = 128 * kGemmBK * 2;       // 16 KB (BN <= 128)
+constexpr int kGemmStageBytes = kGemmStageBytesA + kGemmStageBytesB;
+constexpr int kGemmSmemBytes = kGemmStages * kGemmStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int kGemmThreads = 192;     // warp0 TMA, warp1 MMA+TMEM, warps2-5 epilogue
+constexpr int kGemmTmemCols = 128;
+
+// Everything the epilogue may do to an accumulator value v at (m, n), in this order.
+struct EpiParams {
+  const float* bias;                 // v += bias[n]
+  const float* aux;                  // rank-2 update: v += aux[m,0]*aux_w[n,0] + aux[m,1]*aux_w[n,1]
+  const float* aux_w;
+  int aux_w_pitch;
+  const float* add_in;               // v += add_in[m*add_pitch + n]
+  int add_pitch;
+  float* out_pre;                    // store v (pre-activation) for the backward pass
+  int pre_pitch;
+  int act;                           // 1: v = gelu_erf(v)
+  float drop_p;                      // >0: v *= dropout_mask(drop_stream, m*N+n) / (1-p)
+  int drop_stream;
+  const float* gate_z;               // backward gate: v *= gelu'(gate_z[m,n]) * dropout_mask(gate_stream)/(1-gate_p)
+  int gate_pitch;
+  float gate_p;
+  int gate_stream;
+  float* out_f32;                    // store v as fp32
+  int f32_pitch;
+  __nv_bfloat16* out_hi;             // store bf16(v) (and the residual in out_lo when non-null)
+  __nv_bfloat16* out_lo;
+  int bf_pitch;
+  float* sumsq_slots;                // per-CTA sum of v^2 (for the global gradient norm)
+};
+
+struct alignas(128) GemmProblem {
+  CUtensorMap tmA[2];                // [0] hi, [1] lo
+  CUtensorMap tmB[2];
+  int M, N, K;
+  int tiles_m, tiles_n, splits, kb_per_split, kb_total;
+  int cta_begin, cta_count;
+  int ncombo;                        // 1 bf16, 3 fp32x3
+  int bn;                            // tile width: 32/64/128 (MN-major B: 64/128)
+  unsigned long long hintA, hintB;   // L2 eviction hints for the two operand streams
+  float* splitk_ws;                  // [tiles][splits][128][bn] fp32
+  int* splitk_ctr;                   // [tiles], zero between launches
+  EpiParams epi;
+};
+
+struct RunCtx {
+  int* err;                          // device error flag
+  const uint32_t* rng;               // [0] seed lo, [1] seed hi, [2] step (dropout counter salt)
+};
+
+__device__ __forceinline__ void epi_named_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+template <bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+fnd_gemm_kernel(const GemmProblem* __restrict__ probs, int nprob, RunCtx ctx) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kGemmStages * kGemmStageBytes);
+  uint64_t* empty_bar = full_bar + kGemmStages;
+  uint64_t* accum_bar = empty_bar + kGemmStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+  volatile int* last_flag = reinterpret_cast<volatile int*>(tmem_slot + 1);
+  float* red_smem = reinterpret_cast<float*>(tmem_slot + 2);   // 4 floats
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // ---- locate this CTA's work item ----
+  int pi = 0;
+  while (pi + 1 < nprob && static_cast<int>(blockIdx.x) >= probs[pi + 1].cta_begin) ++pi;
+  const GemmProblem& P = probs[pi];
+  const int local = static_cast<int>(blockIdx.x) - P.cta_begin;
+  const int splits = P.splits;
+  const int split = local % splits;
+  const int tile = local / splits;
+  const int tm = tile % P.tiles_m;
+  const int tn = tile / P.tiles_m;
+  const int bn = P.bn;
+  const int ncombo = P.ncombo;
+  const int kb0 = split * P.kb_per_split;
+  const int kb1 = min(kb0 + P.kb_per_split, P.kb_total);
+  const int iters = (kb1 - kb0) * ncombo;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&P.tmA[0]);
+    tma_prefetch_desc(&P.tmB[0]);
+    if (ncombo > 1) {
+      tma_prefetch_desc(&P.tmA[1]);
+      tma_prefetch_desc(&P.tmB[1]);
+    }
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < kGemmStages; ++s) {
+        mbar_init(&full_bar[s], 1);
+        mbar_init(&empty_bar[s], 1);
+      }
+      mbar_init(accum_bar, 1);
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, kGemmTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      const uint32_t bytesB = static_cast<uint32_t>(bn) * kGemmBK * 2;
+      const uint32_t tx = kGemmStageBytesA + bytesB;
+      for (int it = 0; it < iters; ++it) {
+        const int s = it % kGemmStages;
+        const uint32_t ph = static_cast<uint32_t>(it / kGemmStages) & 1u;
+        if (!mbar_wait(&empty_bar[s], ph ^ 1u, ctx.err, FND_DEV_TIMEOUT_PRODUCER)) break;
+        const int kb = kb0 + it / ncombo;
+        const int c = it - (it / ncombo) * ncombo;
+        const void* mapA = &P.tmA[c == 2 ? 1 : 0];
+        const void* mapB = &P.tmB[c == 1 ? 1 : 0];
+        uint8_t* sA = smem + s * kGemmStageBytes;
+        uint8_t* sB = sA + kGemmStageBytesA;
+        mbar_arrive_expect_tx(&full_bar[s], tx);
+        if (!A_MN) {
+          tma_load_2d(sA, mapA, &full_bar[s], kb * kGemmBK, tm * kGemmBM, P.hintA);
+        } else {
+          tma_load_2d(sA, mapA, &full_bar[s], tm * kGemmBM, kb * kGemmBK, P.hintA);
+          tma_load_2d(sA + 8192, mapA, &full_bar[s], tm * kGemmBM + 64, kb * kGemmBK, P.hintA);
+        }
+        if (!B_MN) {
+          tma_load_2d(sB, mapB, &full_bar[s], kb * kGemmBK, tn * bn, P.hintB);
+        } else {
+          for (int ch = 0; ch < bn / 64; ++ch)
+            tma_load_2d(sB + ch * 8192, mapB, &full_bar[s], tn * bn + ch * 64, kb * kGemmBK, P.hintB);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(kGemmBM, bn, A_MN ? 1 : 0, B_MN ? 1 : 0);
+      bool ok = true;
+      for (int it = 0; it < iters && ok; ++it) {
+        const int s = it % kGemmStages;
+        const uint32_t ph = static_cast<uint32_t>(it / kGemmStages) & 1u;
+        ok = mbar_wait(&full_bar[s], ph, ctx.err, FND_DEV_TIMEOUT_MMA);
+        if (!ok) break;
+        tc_fence_after_sync();
+        const uint32_t aBase = smem_u32(smem + s * kGemmStageBytes);
+        const uint32_t bBase = aBase + kGemmStageBytesA;
+#pragma unroll
+        for (int k = 0; k < kGemmBK / 16; ++k) {
+          // K-major: 16 contraction elements = 32 B inside the 128-B swizzled row.
+          // MN-major: 16 contraction rows of 128 B = 2048 B (two 8-row swizzle atoms).
+          const uint64_t ad = A_MN ? make_smem_desc_sw128(aBase + k * 2048, 8192, 1024)
+                                   : make_smem_desc_sw128(aBase + k * 32, 16, 1024);
+          const uint64_t bd = B_MN ? make_smem_desc_sw128(bBase + k * 2048, 8192, 1024)
+                                   : make_smem_desc_sw128(bBase + k * 32, 16, 1024);
+          umma_f16(tmem_base, ad, bd, idesc, (it | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[s]);      // frees the smem stage once these MMAs retire
+      }
+      umma_commit(accum_bar);            // accumulator complete
+    }
+    __syncwarp();
+  } else {
+    // ================= epilogue (warps 2..5) =================
+    const EpiParams& E = P.epi;
+    const int lane_grp = warp & 3;                 // TMEM lane quarter this warp may access
+    const int row = lane_grp * 32 + lane;
+    const int m = tm * kGemmBM + row;
+    const bool row_ok = m < P.M;
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16);
+    const int nchunks = bn / 32;
+    const int epi_tid = threadIdx.x - 64;
+    bool proceed = mbar_wait(accum_bar, 0u, ctx.err, FND_DEV_TIMEOUT_EPILOGUE);
+    tc_fence_after_sync();
+
+    float* ws_tile = nullptr;
+    if (splits > 1) {
+      ws_tile = P.splitk_ws + static_cast<size_t>(tile) * splits * (kGemmBM * bn);
+      float* mine = ws_tile + static_cast<size_t>(split) * (kGemmBM * bn) + static_cast<size_t>(row) * bn;
+      for (int ch = 0; ch < nchunks; ++ch) {
+        uint32_t r[32];
+        tmem_ld_32x32(taddr + ch * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          __stcg(reinterpret_cast<float4*>(mine + ch * 32 + j),
+                 make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                             __uint_as_float(r[j + 3])));
+      }
+      __threadfence();
+      epi_named_barrier();
+      if (epi_tid == 0) {
+        const int old = atomicAdd(&P.splitk_ctr[tile], 1);
+        const int last = (old == splits - 1) ? 1 : 0;
+        if (last) P.splitk_ctr[tile] = 0;     // re-arm for the next launch (graph replay safe)
+        *last_flag = last;
+      }
+      epi_named_barrier();
+      proceed = proceed && (*last_flag != 0);
+      if (proceed) __threadfence();
+    }
+
+    if (proceed) {
+      const uint32_t seed_lo = ctx.rng ? ctx.rng[0] : 0u;
+      const uint32_t seed_hi = ctx.rng ? ctx.rng[1] : 0u;
+      const uint32_t rstep = ctx.rng ? ctx.rng[2] : 0u;
+      DropCfg dfw = make_dropcfg(E.drop_p, (static_cast<uint64_t>(seed_hi) << 32) | seed_lo);
+      DropCfg dbw = make_dropcfg(E.gate_p, (static_cast<uint64_t>(seed_hi) << 32) | seed_lo);
+      float a0 = 0.f, a1 = 0.f;
+      if (E.aux && row_ok) {
+        a0 = E.aux[static_cast<size_t>(m) * 2];
+        a1 = E.aux[static_cast<size_t>(m) * 2 + 1];
+      }
+      float ss = 0.f;
+      for (int ch = 0; ch < nchunks; ++ch) {
+        float v[32];
+        if (splits > 1) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = 0.f;
+          for (int s = 0; s < splits; ++s) {
+            const float* src = ws_tile + static_cast<size_t>(s) * (kGemmBM * bn) + static_cast<size_t>(row) * bn + ch * 32;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 t = ldcg_f4(src + j);
+              v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
+            }
+          }
+        } else {
+          uint32_t r[32];
+          tmem_ld_32x32(taddr + ch * 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        }
+        const int n0 = tn * bn + ch * 32;
+        if (!row_ok || n0 >= P.N) continue;
+        const bool full = (n0 + 32 <= P.N);
+
+        if (E.bias) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (full || n0 + j < P.N) v[j] += __ldg(E.bias + n0 + j);
+        }
+        if (E.aux) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (full || n0 + j < P.N) {
+              const float* w = E.aux_w + static_cast<size_t>(n0 + j) * E.aux_w_pitch;
+              v[j] += a0 * __ldg(w) + a1 * __ldg(w + 1);
+            }
+        }
+        if (E.add_in) {
+          const float* src = E.add_in + static_cast<size_t>(m) * E.add_pitch + n0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (full || n0 + j < P.N) v[j] += src[j];
+        }
+        if (E.out_pre) {
+          float* dst = E.out_pre + static_cast<size_t>(m) * E.pre_pitch + n0;
+          if (full && (E.pre_pitch & 3) == 0) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (n0 + j < P.N) dst[j] = v[j];
+          }
+        }
+        if (E.act == 1) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+        }
+        if (E.drop_p > 0.f) {
+          const uint64_t e0 = static_cast<uint64_t>(m) * static_cast<uint64_t>(P.N) + n0;   // multiple of 4
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float mm[4];
+            dropout_mult4(dfw, static_cast<uint32_t>(E.drop_stream) ^ (rstep << 8), (e0 + j) >> 2, mm);
+            v[j] *= mm[0]; v[j + 1] *= mm[1]; v[j + 2] *= mm[2]; v[j + 3] *= mm[3];
+          }
+        }
+        if (E.gate_z) {
+          const float* z = E.gate_z + static_cast<size_t>(m) * E.gate_pitch + n0;
+          const uint64_t e0 = static_cast<uint64_t>(m) * static_cast<uint64_t>(P.N) + n0;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float mm[4] = {1.f, 1.f, 1.f, 1.f};
+            if (E.gate_p > 0.f)
+              dropout_mult4(dbw, static_cast<uint32_t>(E.gate_stream) ^ (rstep << 8), (e0 + j) >> 2, mm);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              if (full || n0 + j + q < P.N) v[j + q] *= gelu_erf_grad(z[j + q]) * mm[q];
+          }
+        }
+        if (E.out_f32) {
+          float* dst = E.out_f32 + static_cast<size_t>(m) * E.f32_pitch + n0;
+          if (full && (E.f32_pitch & 3) == 0 && (reinterpret_cast<uintptr_t>(E.out_f32) & 15) == 0) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (n0 + j < P.N) dst[j] = v[j];
+          }
+        }
+        if (E.out_hi) {
+          __nv_bfloat16* dh = E.out_hi + static_cast<size_t>(m) * E.bf_pitch + n0;
+          const bool vec = full && (E.bf_pitch & 7) == 0;
+          if (vec) {
+            uint32_t ph[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) ph[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+#pragma unroll
+            for (int j = 0; j < 16; j += 4)
+              *reinterpret_cast<uint4*>(dh + 2 * j) = make_uint4(ph[j], ph[j + 1], ph[j + 2], ph[j + 3]);
+            if (E.out_lo) {
+              __nv_bfloat16* dl = E.out_lo + static_cast<size_t>(m) * E.bf_pitch + n0;
+              uint32_t pl[16];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&ph[j]);
+                pl[j] = pack_bf16x2(v[2 * j] - __low2float(h2), v[2 * j + 1] - __high2float(h2));
+              }
+#pragma unroll
+              for (int j = 0; j < 16; j += 4)
+                *reinterpret_cast<uint4*>(dl + 2 * j) = make_uint4(pl[j], pl[j + 1], pl[j + 2], pl[j + 3]);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (n0 + j < P.N) {
+                __nv_bfloat16 h, l;
+                split_bf16(v[j], h, l);
+                dh[j] = h;
+                if (E.out_lo) E.out_lo[static_cast<size_t>(m) * E.bf_pitch + n0 + j] = l;
+              }
+          }
+        }
+        if (E.sumsq_slots) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (full || n0 + j < P.N) ss += v[j] * v[j];
+        }
+      }
+      if (E.sumsq_slots) {
+        ss = warp_sum(ss);
+        if (lane == 0) red_smem[lane_grp] = ss;
+        epi_named_barrier();
+        if (epi_tid == 0) {
+          // fixed order => deterministic
+          E.sumsq_slots[local] = (red_smem[2] + red_smem[3]) + (red_smem[0] + red_smem[1]);
+        }
+      }
+    } else if (P.epi.sumsq_slots && splits > 1) {
+      // non-last split CTAs contribute zero to the norm
+      if (epi_tid == 0) P.epi.sumsq_slots[local] = 0.f;
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, kGemmTmemCols);
+  }
+}
+
+}  // namespace fnd

@@ -1,0 +1,97 @@
+// fnd_gemm_host.h — host-side construction of GemmProblem tables and the grouped launch.
+#pragma once
+#include "fnd_gemm.cuh"
+#include "fnd_tmap.h"
+#include <vector>
+
+namespace fnd {
+
+// A GEMM operand as it lies in memory. Logical shape is [rows = M or N, contraction = K].
+//   mn_major == false : memory is [rows][K]   (K contiguous)      e.g. activations / nn.Linear weights (fwd)
+//   mn_major == true  : memory is [K][rows]   (rows contiguous)   e.g. W for dgrad, dY and X for wgrad
+struct Operand {
+  const __nv_bfloat16* hi;
+  const __nv_bfloat16* lo;   // may be null when ncombo == 1
+  int pitch;                 // elements between consecutive memory rows
+  bool mn_major;
+};
+
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// Fills one problem; returns 0 or a negative error. `cta_begin` is assigned by the caller (finish_table).
+inline int fill_problem(GemmProblem& p, const Operand& A, const Operand& B, int M, int N, int K, int bn, int splits,
+                        int ncombo, unsigned long long hintA, unsigned long long hintB, float* ws, int* ctr,
+                        const EpiParams& epi) {
+  memset(&p, 0, sizeof(p));
+  if (bn != 32 && bn != 64 && bn != 128) return -10;
+  if (B.mn_major && bn < 64) return -11;
+  if (ncombo != 1 && ncombo != 3) return -12;
+  if (ncombo == 3 && (!A.lo || !B.lo)) return -13;
+  p.M = M; p.N = N; p.K = K;
+  p.bn = bn;
+  p.ncombo = ncombo;
+  p.tiles_m = ceil_div(M, kGemmBM);
+  p.tiles_n = ceil_div(N, bn);
+  p.kb_total = ceil_div(K, kGemmBK);
+  if (splits < 1) splits = 1;
+  if (splits > p.kb_total) splits = p.kb_total;
+  p.kb_per_split = ceil_div(p.kb_total, splits);
+  p.splits = ceil_div(p.kb_total, p.kb_per_split);   // every split non-empty
+  if (p.splits > 1 && (!ws || !ctr)) return -14;
+  p.cta_count = p.tiles_m * p.tiles_n * p.splits;
+  p.hintA = hintA; p.hintB = hintB;
+  p.splitk_ws = ws; p.splitk_ctr = ctr;
+  p.epi = epi;
+  for (int h = 0; h < (ncombo == 3 ? 2 : 1); ++h) {
+    const void* a = h ? static_cast<const void*>(A.lo) : static_cast<const void*>(A.hi);
+    const void* b = h ? static_cast<const void*>(B.lo) : static_cast<const void*>(B.hi);
+    int r;
+    if (!A.mn_major) r = encode_bf16_2d(&p.tmA[h], a, K, M, A.pitch, 64, kGemmBM);
+    else             r = encode_bf16_2d(&p.tmA[h], a, M, K, A.pitch, 64, kGemmBK);
+    if (r) return r;
+    if (!B.mn_major) r = encode_bf16_2d(&p.tmB[h], b, K, N, B.pitch, 64, bn);
+    else             r = encode_bf16_2d(&p.tmB[h], b, N, K, B.pitch, 64, kGemmBK);
+    if (r) return r;
+  }
+  if (ncombo == 1) { p.tmA[1] = p.tmA[0]; p.tmB[1] = p.tmB[0]; }
+  return 0;
+}
+
+inline size_t splitk_ws_floats(int M, int N, int bn, int splits) {
+  return static_cast<size_t>(ceil_div(M, kGemmBM)) * ceil_div(N, bn) * splits * kGemmBM * bn;
+}
+
+// Assigns cta_begin prefix sums; returns the grid size.
+inline int finish_table(GemmProblem* probs, int n) {
+  int c = 0;
+  for (int i = 0; i < n; ++i) { probs[i].cta_begin = c; c += probs[i].cta_count; }
+  return c;
+}
+
+template <bool A_MN, bool B_MN>
+inline cudaError_t launch_gemm_t(const GemmProblem* dev_table, int nprob, int grid, RunCtx ctx, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(fnd_gemm_kernel<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         kGemmSmemBytes);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  fnd_gemm_kernel<A_MN, B_MN><<<grid, kGemmThreads, kGemmSmemBytes, st>>>(dev_table, nprob, ctx);
+  return cudaGetLastError();
+}
+
+// kind: 0 = forward (A K-major, B K-major); 1 = dgrad (A K-major, B MN-major); 2 = wgrad (both MN-major)
+inline cudaError_t launch_gemm(int kind, const GemmProblem* dev_table, int nprob, int grid, RunCtx ctx,
+                               cudaStream_t st) {
+  if (grid <= 0) return cudaSuccess;
+  switch (kind) {
+    case 0: return launch_gemm_t<false, false>(dev_table, nprob, grid, ctx, st);
+    case 1: return launch_gemm_t<false, true>(dev_table, nprob, grid, ctx, st);
+    case 2: return launch_gemm_t<true, true>(dev_table, nprob, grid, ctx, st);
+    case 3: return launch_gemm_t<true, false>(dev_table, nprob, grid, ctx, st);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+}  // namespace fnd
