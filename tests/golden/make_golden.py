@@ -1,0 +1,142 @@
+#!/usr/bin/env python3
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (/root/reference) on CPU.
+
+Run in the build container only (the reference checkout does not exist on the GPU box):
+
+    HF_HUB_OFFLINE=1 PYTHONDONTWRITEBYTECODE=1 python tests/golden/make_golden.py
+
+Weights are NOT stored (51 MB): they are regenerated deterministically by ``oracle.fnd_oracle.init_params(seed)``
+and loaded into the reference modules with ``load_state_dict``; each fixture stores per-tensor checksums of the
+weights so RNG drift is detected. Inputs are stored in full (small batches). Outputs stored: fused, logits,
+probs, forensic scalars, loss, per-parameter gradient norms, strided gradient samples, and (train case) the
+loss trajectory and strided parameter samples after 3 steps of clip_grad_norm_(5.0) + torch.optim.AdamW.
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+REF = os.environ.get("FND_REFERENCE", "/root/reference")
+sys.path.insert(0, ROOT)
+sys.path.insert(0, REF)
+os.environ.setdefault("HF_HUB_OFFLINE", "1")
+os.environ.setdefault("PYTHONDONTWRITEBYTECODE", "1")
+os.chdir(REF)
+
+import torch  # noqa: E402
+import torch.nn as nn  # noqa: E402
+import torch.nn.functional as F  # noqa: E402
+
+from oracle import fnd_oracle as O  # noqa: E402
+from src.models.fusion.cross_modal_transformer import CrossModalTransformer  # noqa: E402
+from src.models.fusion.deep_truth_classifier import DeepTruthClassifier  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+STRIDE = 997
+
+
+def build_reference(seed, perturb):
+    fus_p, clf_p = O.init_params(seed)
+    if perturb:
+        O.perturb_node_head(clf_p)
+    fusion = CrossModalTransformer("configs/model_configs/fusion.yaml")
+    clf = DeepTruthClassifier("configs/model_configs/classifier.yaml")
+    missing = fusion.load_state_dict(fus_p, strict=True)
+    clf.load_state_dict(clf_p, strict=True)
+    assert not missing.missing_keys and not missing.unexpected_keys
+    return fusion, clf, fus_p, clf_p
+
+
+def set_dropout(mod, p):
+    for m in mod.modules():
+        if isinstance(m, nn.Dropout):
+            m.p = p
+
+
+def checksums(params):
+    return {k: np.array([float(v.double().sum()), float((v.double() ** 2).sum())]) for k, v in params.items()}
+
+
+def ref_forward(fusion, clf, batch):
+    feats = {k: batch[k] for k in O.FEAT_KEYS}
+    fo = fusion(feats)
+    co = clf(fo["fused"], batch["aux"])
+    loss = F.cross_entropy(co["logits"], batch["label"])
+    return fo, co, loss
+
+
+def save_case(name, seed, perturb, batch, dist, steps=0):
+    torch.manual_seed(0)
+    fusion, clf, fus_p, clf_p = build_reference(seed, perturb)
+    b = O.make_batch(batch, seed=1234, dist=dist)
+    rec = {"meta_seed": np.array(seed), "meta_perturb": np.array(int(perturb)), "meta_batch": np.array(batch),
+           "meta_steps": np.array(steps)}
+    for k, v in b.items():
+        rec["in." + k] = v.numpy()
+    for k, v in checksums(fus_p).items():
+        rec["wsum.fusion." + k] = v
+    for k, v in checksums(clf_p).items():
+        rec["wsum.clf." + k] = v
+
+    # ---- eval-mode forward ----
+    fusion.eval(); clf.eval()
+    with torch.no_grad():
+        fo, co, loss = ref_forward(fusion, clf, b)
+    rec["eval.fused"] = fo["fused"].numpy()
+    rec["eval.fusion_logits"] = fo["logits"].numpy()
+    for k, v in fo["forensic"].items():
+        rec["eval.forensic." + k] = v.numpy()
+    rec["eval.logits"] = co["logits"].numpy()
+    rec["eval.probs"] = co["probs"].numpy()
+    rec["eval.loss"] = np.array(float(loss))
+
+    # ---- train-mode (dropout forced to 0) gradients ----
+    fusion.train(); clf.train()
+    set_dropout(fusion, 0.0); set_dropout(clf, 0.0)
+    params = list(fusion.parameters()) + list(clf.parameters())
+    for p in params:
+        p.grad = None
+    fo, co, loss = ref_forward(fusion, clf, b)
+    loss.backward()
+    rec["train.loss"] = np.array(float(loss))
+    for prefix, mod in (("fusion", fusion), ("clf", clf)):
+        for k, p in mod.named_parameters():
+            if p.grad is None:
+                rec[f"gnone.{prefix}.{k}"] = np.array(1)
+                continue
+            g = p.grad.detach()
+            rec[f"gnorm.{prefix}.{k}"] = np.array(float(g.double().norm()))
+            flat = g.flatten()
+            rec[f"gsamp.{prefix}.{k}"] = (flat if flat.numel() <= 4096 else flat[::STRIDE]).numpy().copy()
+
+    # ---- k optimizer steps exactly as forensic_trainer.py:286-298 (dropout off) ----
+    if steps:
+        opt = torch.optim.AdamW(params, lr=2e-4, weight_decay=1e-4)
+        losses, norms = [], []
+        for s in range(steps):
+            bs = O.make_batch(batch, seed=2000 + s, dist=dist)
+            for k, v in bs.items():
+                rec[f"step{s}.in.{k}"] = v.numpy()
+            fo, co, loss = ref_forward(fusion, clf, bs)
+            opt.zero_grad(set_to_none=True)
+            loss.backward()
+            n = nn.utils.clip_grad_norm_(params, max_norm=5.0)
+            opt.step()
+            losses.append(float(loss)); norms.append(float(n))
+        rec["steps.loss"] = np.array(losses)
+        rec["steps.grad_norm"] = np.array(norms)
+        for prefix, mod in (("fusion", fusion), ("clf", clf)):
+            for k, p in mod.named_parameters():
+                flat = p.detach().flatten()
+                rec[f"psamp.{prefix}.{k}"] = (flat if flat.numel() <= 4096 else flat[::STRIDE]).numpy().copy()
+    path = os.path.join(OUT, name + ".npz")
+    np.savez_compressed(path, **rec)
+    print(f"wrote {path}: {os.path.getsize(path) / 1024:.1f} KiB, eval loss {float(rec['eval.loss']):.6f}")
+
+
+if __name__ == "__main__":
+    torch.set_num_threads(8)
+    save_case("eval_smoke_b4", seed=42, perturb=False, batch=4, dist="smoke")
+    save_case("trained_cache_b16", seed=42, perturb=True, batch=16, dist="cache")
+    save_case("train3_smoke_b8", seed=43, perturb=True, batch=8, dist="smoke", steps=3)
