@@ -1,11 +1,15 @@
 /* fnd_b200.h — C ABI of libfnd_b200.so, the B200 (sm_100a) fusion hot path of Ultrafnd.
  *
  * Plain C: raw device pointers, sizes and a cudaStream_t passed as void*. No torch types.
- * Every function returns 0 on success, a negative value for a host-side error (bad argument,
+ * Every int-returning function returns 0 on success, a negative value for a host-side error (bad argument;
  * CUDA runtime error = -1000 - cudaError_t) and a positive value for a device-side error code.
- * The caller owns every buffer; the library never allocates or frees device memory.
+ * The caller owns every DEVICE buffer (parameters, gradients, optimizer state, bf16 shadows, workspace);
+ * the library never allocates or frees device memory. A plan handle is a small host object.
+ * All hot-path entry points are stream-ordered, never synchronise and are CUDA-graph capturable.
  *
- * All citations are relative to the reference checkout (Nuralamsiddik16/Ultrafnd_git).
+ * Citations are relative to the reference checkout (Nuralamsiddik16/Ultrafnd_git); each entry point names the
+ * reference code it replaces. The reference has no native/FFI layer (it is pure Python on ATen), so these are
+ * the entry points a binding at the nn.Module.forward / trainer-step boundary needs.
  */
 #ifndef FND_B200_H_
 #define FND_B200_H_
@@ -22,10 +26,121 @@ int fnd_version(void);
 const char* fnd_build_arch(void);
 
 /* ---------------------------------------------------------------------------------------------
+ * Model dimensions. Mirrors configs/model_configs/fusion.yaml + classifier.yaml and the input widths
+ * hard-coded at cross_modal_transformer.py:96-99.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct fnd_dims {
+  int hidden;            /* H: 512 or 1024 (fusion hidden == classifier hidden == classifier input_dim) */
+  int d_text, d_audio, d_visual, d_temporal, d_gnn;   /* 768, 128, 512, 256, 128 (multiples of 64) */
+  int use_gnn;           /* 1: 16 slots in fused_cat, 0: 15 */
+  int aux_dim;           /* 2 or 0 */
+  int trees, depth;      /* NODE ensemble: trees*depth <= 32, depth <= 4 */
+  float fusion_dropout;  /* fusion.yaml:3 */
+  float clf_dropout;     /* classifier.yaml:4 */
+  float tree_dropout;    /* 0.3, deep_truth_classifier.py:134 */
+  float node_tau;        /* 10.0 */
+} fnd_dims;
+
+/* ---------------------------------------------------------------------------------------------
+ * Parameter arena. All parameters of CrossModalTransformer + DeepTruthClassifier live in one flat fp32
+ * buffer; entry i describes one state_dict tensor: its name prefixed "fusion." or "clf.", its element
+ * offset, its shape (ndim 0..2) and whether it is "hot" (receives a gradient in the reference training step,
+ * forensic_trainer.py:286-298). Hot tensors occupy [0, fnd_arena_hot_elems); GEMM weights come first and have
+ * bf16 shadows at the same element offsets in [0, fnd_arena_shadow_elems) (the shadow buffers must hold
+ * fnd_arena_shadow_buffer_elems elements: the tail is a re-pitched copy of pre.0.weight).
+ * ------------------------------------------------------------------------------------------- */
+int fnd_param_count(const fnd_dims* dims);
+int fnd_param_info(const fnd_dims* dims, int index, char* name, int name_cap, long long* offset, int* ndim,
+                   int* rows, int* cols, int* hot);
+long long fnd_arena_total_elems(const fnd_dims* dims);
+long long fnd_arena_hot_elems(const fnd_dims* dims);
+long long fnd_arena_shadow_elems(const fnd_dims* dims);
+long long fnd_arena_shadow_buffer_elems(const fnd_dims* dims);
+
+/* ---------------------------------------------------------------------------------------------
+ * Plans. A plan fixes (dims, batch, precision mode) and owns the TMA descriptors and kernel tables.
+ *   mode 0: bf16 operands, fp32 accumulate.   mode 1: "fp32x3" — bf16 hi/lo operand pairs, three tensor-core
+ *   products per GEMM, fp32-equivalent results (rel. err ~1e-5).
+ * fnd_plan_bind uploads the tables; it is the only plan call that issues copies and must not be captured.
+ * shadow_lo may be NULL in mode 0. m / v may be NULL for inference-only plans.
+ * ------------------------------------------------------------------------------------------- */
+int fnd_plan_create(const fnd_dims* dims, int batch, int mode, void** plan_out);
+void fnd_plan_destroy(void* plan);
+size_t fnd_plan_workspace_bytes(const void* plan);
+int fnd_plan_bind(void* plan, void* workspace, float* params, float* grads, float* adam_m, float* adam_v,
+                  void* shadow_hi, void* shadow_lo, void* stream);
+/* Byte offset / element count of a named workspace buffer ("fused", "fusion_logits", "rowstat", "logits",
+ * "probs", "loss_row", "dlogits", "dfused", "state", "fused_cat_hi", ...); returns -1 if unknown. */
+long long fnd_plan_buffer_offset(const void* plan, const char* name);
+long long fnd_plan_buffer_bytes(const void* plan, const char* name);
+
+/* Inputs of one batch. x[i]: fp32 [*, d_i] with row pitch pitch[i] (elements, multiple of 4), i = text, audio,
+ * visual, temporal, gnn. gather (optional): int64 row indices applied to x[*], aux and labels, so a whole
+ * feature cache can stay resident on the device (replaces CachedTensorDataset + default collate +
+ * gnn_Z[global_idx], forensic_trainer.py:60-83,238-263). aux: fp32 [*,2]; labels: int64. */
+typedef struct fnd_inputs {
+  const float* x[5];
+  int pitch[5];
+  const float* aux;
+  int aux_pitch;
+  const long long* labels;
+  const long long* gather;
+} fnd_inputs;
+
+/* ---- optimizer / RNG state (small stream-ordered writes; call outside graph capture) ---- */
+int fnd_set_hyper(void* plan, float lr, float beta1, float beta2, float eps, float weight_decay, float max_norm,
+                  void* stream);
+int fnd_set_lr(void* plan, float lr, void* stream);
+int fnd_set_seed(void* plan, unsigned long long seed, void* stream);
+int fnd_set_loss_scale(void* plan, float scale, void* stream);   /* d(mean loss)/d(row loss); default 1/batch */
+/* Rebuild the bf16 operand copies from the fp32 master parameters (after load_state_dict or an external
+ * optimizer step). fnd_clip_adamw_step keeps them current by itself. */
+int fnd_refresh_shadows(void* plan, void* stream);
+
+/* ---- module-level entry points (what a binding of the two nn.Modules calls) ----
+ * fnd_fusion_forward  : CrossModalTransformer.forward, cross_modal_transformer.py:134-210.
+ *                       Results in workspace buffers "fused" [B,H], "fusion_logits" [B,2], "rowstat" [B,16]
+ *                       (cols 0..2 = semantic_conflict, emotion_intensity, temporal_delay).
+ * fnd_classifier_forward : DeepTruthClassifier.forward, deep_truth_classifier.py:148-171. `fused` NULL = use
+ *                       the plan's own "fused"; aux NULL = aux already staged by fnd_fusion_forward's inputs.
+ *                       Results in "logits", "probs" [B,2].
+ * fnd_ce_loss_fwd_bwd : F.cross_entropy(logits, y) mean + its gradient, forensic_trainer.py:287.
+ *                       Results in "loss_row" [B], "dlogits" [B,2].
+ * fnd_classifier_backward / fnd_fusion_backward : autograd of the two forwards; parameter gradients land in
+ *                       the bound gradient arena, "dfused" [B,H] carries the gradient across the boundary.
+ *                       dlogits / dfused NULL = use the workspace buffers; dfusion_logits may be NULL.
+ * fnd_clip_adamw_step : clip_grad_norm_(max_norm) + AdamW.step, forensic_trainer.py:292-298. norm_from_slots
+ *                       = 1 reuses the norm folded into the fused step's wgrad epilogues; 0 recomputes it over
+ *                       the gradient arena (use after a gradient all-reduce or the module-level backward). */
+int fnd_fusion_forward(void* plan, const fnd_inputs* in, int training, void* stream);
+int fnd_classifier_forward(void* plan, const float* fused, const float* aux, int aux_pitch, int training,
+                           void* stream);
+int fnd_ce_loss_fwd_bwd(void* plan, const long long* labels, void* stream);
+int fnd_classifier_backward(void* plan, const float* dlogits, void* stream);
+int fnd_fusion_backward(void* plan, const float* dfused, const float* dfusion_logits, void* stream);
+int fnd_clip_adamw_step(void* plan, int norm_from_slots, void* stream);
+
+/* ---- fused trainer-step entry points (ForensicTrainer._epoch_loop body, forensic_trainer.py:285-298) ----
+ * fnd_train_fwd_bwd : forward + cross-entropy + full backward in one stream-ordered sequence; leaves the mean
+ *                     loss / gradient norm in "state" and all gradients in the arena.
+ * fnd_train_step    : fnd_train_fwd_bwd followed by fnd_clip_adamw_step(norm_from_slots = 1).
+ * fnd_eval_step     : forward of both modules (+ row losses when labels are given), no dropout, nothing saved. */
+int fnd_train_fwd_bwd(void* plan, const fnd_inputs* in, void* stream);
+int fnd_train_step(void* plan, const fnd_inputs* in, void* stream);
+int fnd_eval_step(void* plan, const fnd_inputs* in, void* stream);
+
+/* Number of kernel launches one call of the named entry point issues ("train_step", "eval_step", ...). */
+int fnd_launch_count(const void* plan, const char* entry);
+/* Dropout keep-multipliers (0 or 1/(1-p)) that the NEXT training forward will use for a layer
+ * (1 fuse0 [B,2H], 2 fuse1 [B,H], 3 pre0 [B,H], 4 pre1 [B,H], 5 tree [B,T,2]); test support. */
+int fnd_export_dropout_mask(void* plan, int layer, float* out, long long n, void* stream);
+/* Reads (and clears) the device error flag; synchronises the stream. */
+int fnd_check_error(void* plan, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Building block: C[M,N] (fp32) = A[M,K] * B[N,K]^T on the tcgen05 tensor cores.
- * Replaces ATen addmm as reached from nn.Linear (src/models/fusion/cross_modal_transformer.py:96-102,
- * 122-129; src/models/fusion/deep_truth_classifier.py:121-128). Exposed for tests and for callers that
- * want the raw GEMM; the fused entry points below are what the model uses.
+ * Replaces ATen addmm as reached from nn.Linear (cross_modal_transformer.py:96-102,122-129;
+ * deep_truth_classifier.py:121-128). Exposed for tests and for callers that want the raw GEMM.
  *   a_mn / b_mn : 0 = operand stored [rows][K] (K contiguous), 1 = stored [K][rows] (rows contiguous)
  *   *_lo        : residual bf16 planes, required when ncombo == 3 (fp32x3 mode), else may be NULL
  *   bn          : tile width (32, 64 or 128; MN-major B needs >= 64);  splits : split-K factor

@@ -1,0 +1,221 @@
+"""GPU parity of the B200 fusion hot path (through the C ABI) against the CPU oracle and the golden fixtures.
+
+Tolerances are BASELINE.json's: logits/loss rel-err <= 1e-3 in fp32 mode and <= 2e-2 in bf16 mode, argmax identical.
+"""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import fnd_oracle as O
+from ultrafnd_git_b200.fused import FusedStep
+from ultrafnd_git_b200.modules import CrossModalTransformer, DeepTruthClassifier, pair_modules
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+TOL = {"fp32": 1e-3, "bf16": 2e-2}
+STRIDE = 997
+
+
+def build_pair(seed=42, perturb=False, precision="fp32", dropout_off=False):
+    fus, clf = O.init_params(seed)
+    if perturb:
+        O.perturb_node_head(clf)
+    f = CrossModalTransformer(precision=precision)
+    c = DeepTruthClassifier(precision=precision)
+    f.load_state_dict(fus)
+    c.load_state_dict(clf)
+    if dropout_off:
+        for m in list(f.modules()) + list(c.modules()):
+            if isinstance(m, torch.nn.Dropout):
+                m.p = 0.0
+    return f, c, fus, clf
+
+
+def to_cuda(batch):
+    return {k: v.cuda() for k, v in batch.items()}
+
+
+def load_gold(name):
+    z = np.load(os.path.join(GOLD, name + ".npz"))
+    batch = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("in.")}
+    return z, batch
+
+
+def module_forward(f, c, batch):
+    fo = f({k: batch[k] for k in O.FEAT_KEYS})
+    co = c(fo["fused"], batch["aux"])
+    return fo, co
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("name", ["eval_smoke_b4", "trained_cache_b16", "train3_smoke_b8"])
+def test_eval_forward_matches_golden_and_oracle(name, precision):
+    z, batch = load_gold(name)
+    f, c, fus, clf = build_pair(int(z["meta_seed"]), bool(int(z["meta_perturb"])), precision)
+    f.eval(); c.eval()
+    with torch.no_grad():
+        fo, co = module_forward(f, c, to_cuda(batch))
+        ref = O.model_forward(fus, clf, batch)
+    tol = TOL[precision]
+    got = {"fused": fo["fused"], "fusion_logits": fo["logits"], "logits": co["logits"], "probs": co["probs"]}
+    for k, v in got.items():
+        e_or = O.rel_err(v.cpu(), ref[k])
+        e_gold = O.rel_err(v.cpu(), torch.from_numpy(z["eval." + k]))
+        print(f"[{name}/{precision}] {k}: rel-err vs oracle {e_or:.2e}, vs reference golden {e_gold:.2e}")
+        assert e_or < tol and e_gold < tol, k
+    for k, v in fo["forensic"].items():
+        assert O.rel_err(v.cpu(), torch.from_numpy(z["eval.forensic." + k])) < tol, k
+    assert torch.equal(co["logits"].argmax(-1).cpu(), torch.from_numpy(z["eval.logits"]).argmax(-1))
+    assert float(co["temperature"]) == 1.0
+    loss = torch.nn.functional.cross_entropy(co["logits"].cpu(), batch["label"])
+    assert abs(float(loss) - float(z["eval.loss"])) / float(z["eval.loss"]) < tol
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("name", ["trained_cache_b16", "train3_smoke_b8"])
+def test_module_autograd_gradients_match_reference(name, precision):
+    """model(batch) -> F.cross_entropy -> loss.backward(), exactly the reference trainer's calls, dropout forced off."""
+    z, batch = load_gold(name)
+    f, c, fus, clf = build_pair(int(z["meta_seed"]), bool(int(z["meta_perturb"])), precision, dropout_off=True)
+    f.train(); c.train()
+    cb = to_cuda(batch)
+    fo, co = module_forward(f, c, cb)
+    loss = torch.nn.functional.cross_entropy(co["logits"], cb["label"])
+    loss.backward()
+    tol = TOL[precision]
+    assert abs(float(loss) - float(z["train.loss"])) / float(z["train.loss"]) < tol
+    _, gf, gc = O.loss_and_grads(fus, clf, batch, dropout=0.0)
+    worst = 0.0
+    for prefix, mod, grads in (("fusion", f, gf), ("clf", c, gc)):
+        for k, p in mod.named_parameters():
+            if f"gnone.{prefix}.{k}" in z.files:
+                assert p.grad is None, f"{prefix}.{k} must stay grad=None like the reference"
+                continue
+            assert p.grad is not None, f"{prefix}.{k} got no gradient"
+            ref = grads[k]
+            rn = float(ref.norm())
+            if rn == 0.0:
+                assert float(p.grad.abs().max()) < 1e-12, k
+                continue
+            e = O.rel_err(p.grad.cpu(), ref)
+            worst = max(worst, e)
+            # golden (reference) strided samples as a second witness
+            flat = p.grad.flatten().cpu()
+            samp = flat if flat.numel() <= 4096 else flat[::STRIDE]
+            eg = O.rel_err(samp, torch.from_numpy(z[f"gsamp.{prefix}.{k}"]))
+            assert e < 5 * tol and eg < 5 * tol, (prefix, k, e, eg)
+    print(f"[{name}/{precision}] worst per-parameter gradient rel-err {worst:.2e}")
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_fused_train_steps_match_reference(precision):
+    """fnd_train_step x3 (fused fwd + CE + bwd + clip + AdamW, CUDA-graph replayed) vs the reference's 3 real steps."""
+    z, _ = load_gold("train3_smoke_b8")
+    f, c, fus, clf = build_pair(int(z["meta_seed"]), True, precision, dropout_off=True)
+    f.train(); c.train()
+    f._sync_dropout(); c._sync_dropout()
+    B = int(z["meta_batch"])
+    step = FusedStep(f, c, B, precision=precision, use_graph=True)
+    assert step.engine.dims.fusion_dropout == 0.0 and step.engine.dims.tree_dropout == 0.0
+    losses, norms = [], []
+    for s in range(int(z["meta_steps"])):
+        batch = {k.split(".in.")[1]: torch.from_numpy(z[k]) for k in z.files if k.startswith(f"step{s}.in.")}
+        step.load_batch(to_cuda(batch))
+        step.train_step()
+        st = step.plan.state()
+        losses.append(st["loss"]); norms.append(st["grad_norm"])
+        assert st["err"] == 0 and st["step"] == s + 1
+    step.plan.check_error()
+    tol = TOL[precision]
+    print(f"[train3/{precision}] losses {losses} vs {z['steps.loss']}; norms {norms} vs {z['steps.grad_norm']}")
+    np.testing.assert_allclose(losses, z["steps.loss"], rtol=tol)
+    np.testing.assert_allclose(norms, z["steps.grad_norm"], rtol=max(tol, 2e-3))
+    # parameters after 3 AdamW steps: every weight moved by ~3*lr, compare the values (update error << lr)
+    lr = 2e-4
+    for prefix, mod in (("fusion", f), ("clf", c)):
+        for k, p in mod.named_parameters():
+            key = f"psamp.{prefix}.{k}"
+            flat = p.detach().flatten().cpu()
+            samp = flat if flat.numel() <= 4096 else flat[::STRIDE]
+            ref = torch.from_numpy(z[key])
+            diff = (samp - ref).abs()
+            # Adam's first updates are ~lr*sign(g): elements whose gradient is ~eps (or flips sign in bf16) may differ
+            # by a sizeable fraction of the total move, the mean must not
+            max_bound = (0.3 if precision == "fp32" else 2.0) * 3 * lr
+            mean_bound = (0.01 if precision == "fp32" else 0.3) * 3 * lr
+            assert float(diff.max()) <= max_bound and float(diff.mean()) <= mean_bound, (prefix, k, float(diff.max()), float(diff.mean()))
+
+
+@pytest.mark.parametrize("precision", ["fp32"])
+def test_train_mode_with_dropout_matches_oracle_given_same_masks(precision):
+    """Dropout ON: export the Philox keep-masks the next forward will draw, replay them in the CPU oracle."""
+    f, c, fus, clf = build_pair(42, True, precision)
+    f.train(); c.train()
+    B = 16
+    batch = O.make_batch(B, seed=77)
+    step = FusedStep(f, c, B, precision=precision, use_graph=False)
+    masks = {k: v.cpu() for k, v in step.plan.dropout_masks().items()}
+    for k, p in (("fuse0", 0.1), ("fuse1", 0.1), ("pre0", 0.1), ("pre1", 0.1), ("tree", 0.3)):
+        keep = float((masks[k] > 0).float().mean())
+        assert set(torch.unique(masks[k]).tolist()) <= {0.0, pytest.approx(1.0 / (1.0 - p))}
+        assert abs(keep - (1.0 - p)) < (0.25 if k == "tree" else 0.05), (k, keep)
+    step.load_batch(to_cuda(batch))
+    step.train_fwd_bwd()
+    st = step.plan.state()
+    out, gf, gc = O.loss_and_grads(fus, clf, batch, dropout=0.1, masks=masks)
+    print(f"[dropout/{precision}] loss {st['loss']} vs oracle {float(out['loss'])}")
+    assert abs(st["loss"] - float(out["loss"])) / float(out["loss"]) < TOL[precision]
+    eng = step.engine
+    for prefix, grads in (("fusion", gf), ("clf", gc)):
+        for k, g in grads.items():
+            got = eng.grad_view(f"{prefix}.{k}").cpu()
+            if float(g.norm()) == 0:
+                continue
+            assert O.rel_err(got, g) < 5 * TOL[precision], (prefix, k, O.rel_err(got, g))
+    # a second forward draws different masks
+    m2 = step.plan.dropout_masks()
+    assert not torch.equal(m2["fuse0"].cpu(), masks["fuse0"])
+
+
+@pytest.mark.parametrize("B", [1, 4, 128, 1000])
+def test_batch_sizes_and_eval_step(B):
+    """fnd_eval_step at ragged and large batches (bf16): logits within tolerance of the oracle, argmax identical
+    wherever the oracle's margin exceeds the tolerance."""
+    f, c, fus, clf = build_pair(42, True, "bf16")
+    f.eval(); c.eval()
+    batch = O.make_batch(B, seed=5)
+    step = FusedStep(f, c, B, precision="bf16", use_graph=(B == 128))
+    step.load_batch(to_cuda(batch))
+    step.eval_step()
+    with torch.no_grad():
+        ref = O.model_forward(fus, clf, batch)
+    lg = step.logits().cpu()
+    assert O.rel_err(lg, ref["logits"]) < TOL["bf16"]
+    margin = (ref["logits"][:, 0] - ref["logits"][:, 1]).abs()
+    sure = margin > 2 * TOL["bf16"] * ref["logits"].abs().max()
+    assert torch.equal(lg.argmax(-1)[sure], ref["logits"].argmax(-1)[sure])
+    row_loss = torch.nn.functional.cross_entropy(ref["logits"], batch["label"], reduction="none")
+    assert O.rel_err(step.loss_rows().cpu(), row_loss) < TOL["bf16"]
+    step.plan.check_error()
+
+
+def test_missing_gnn_feat_raises_like_reference():
+    f = CrossModalTransformer()
+    x = {"text_features": torch.randn(2, 768), "audio_features": torch.randn(2, 128),
+         "visual_features": torch.randn(2, 512), "temporal_features": torch.randn(2, 256), "gnn_feat": None}
+    with pytest.raises(RuntimeError, match="shapes cannot be multiplied"):
+        f(x)
+
+
+def test_backward_after_overwritten_forward_raises():
+    f, c, _, _ = build_pair(42, False, "bf16")
+    f.train(); c.train()
+    b1, b2 = to_cuda(O.make_batch(4, seed=1)), to_cuda(O.make_batch(4, seed=2))
+    fo1, co1 = module_forward(f, c, b1)
+    module_forward(f, c, b2)
+    with pytest.raises(RuntimeError, match="overwritten"):
+        torch.nn.functional.cross_entropy(co1["logits"], b1["label"]).backward()

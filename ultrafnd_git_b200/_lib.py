@@ -81,10 +81,56 @@ _c_float = ctypes.c_float
 _c_u64 = ctypes.c_uint64
 
 
+class FndDims(ctypes.Structure):
+    """Mirror of ``fnd_dims`` (include/fnd_b200.h)."""
+    _fields_ = [("hidden", _c_int), ("d_text", _c_int), ("d_audio", _c_int), ("d_visual", _c_int),
+                ("d_temporal", _c_int), ("d_gnn", _c_int), ("use_gnn", _c_int), ("aux_dim", _c_int),
+                ("trees", _c_int), ("depth", _c_int), ("fusion_dropout", _c_float), ("clf_dropout", _c_float),
+                ("tree_dropout", _c_float), ("node_tau", _c_float)]
+
+
+class FndInputs(ctypes.Structure):
+    """Mirror of ``fnd_inputs`` (include/fnd_b200.h)."""
+    _fields_ = [("x", _c_void_p * 5), ("pitch", _c_int * 5), ("aux", _c_void_p), ("aux_pitch", _c_int),
+                ("labels", _c_void_p), ("gather", _c_void_p)]
+
+
 def _signatures() -> Dict[str, tuple]:
+    P = ctypes.POINTER
+    ll = ctypes.c_longlong
     return {
         "fnd_version": (_c_int, []),
         "fnd_build_arch": (ctypes.c_char_p, []),
+        "fnd_param_count": (_c_int, [P(FndDims)]),
+        "fnd_param_info": (_c_int, [P(FndDims), _c_int, ctypes.c_char_p, _c_int, P(ll), P(_c_int), P(_c_int),
+                                    P(_c_int), P(_c_int)]),
+        "fnd_arena_total_elems": (ll, [P(FndDims)]),
+        "fnd_arena_hot_elems": (ll, [P(FndDims)]),
+        "fnd_arena_shadow_elems": (ll, [P(FndDims)]),
+        "fnd_arena_shadow_buffer_elems": (ll, [P(FndDims)]),
+        "fnd_plan_create": (_c_int, [P(FndDims), _c_int, _c_int, P(_c_void_p)]),
+        "fnd_plan_destroy": (None, [_c_void_p]),
+        "fnd_plan_workspace_bytes": (_c_size_t, [_c_void_p]),
+        "fnd_plan_bind": (_c_int, [_c_void_p] * 9),
+        "fnd_plan_buffer_offset": (ll, [_c_void_p, ctypes.c_char_p]),
+        "fnd_plan_buffer_bytes": (ll, [_c_void_p, ctypes.c_char_p]),
+        "fnd_set_hyper": (_c_int, [_c_void_p, _c_float, _c_float, _c_float, _c_float, _c_float, _c_float, _c_void_p]),
+        "fnd_set_lr": (_c_int, [_c_void_p, _c_float, _c_void_p]),
+        "fnd_set_seed": (_c_int, [_c_void_p, ctypes.c_ulonglong, _c_void_p]),
+        "fnd_set_loss_scale": (_c_int, [_c_void_p, _c_float, _c_void_p]),
+        "fnd_refresh_shadows": (_c_int, [_c_void_p, _c_void_p]),
+        "fnd_fusion_forward": (_c_int, [_c_void_p, P(FndInputs), _c_int, _c_void_p]),
+        "fnd_classifier_forward": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_void_p]),
+        "fnd_ce_loss_fwd_bwd": (_c_int, [_c_void_p, _c_void_p, _c_void_p]),
+        "fnd_classifier_backward": (_c_int, [_c_void_p, _c_void_p, _c_void_p]),
+        "fnd_fusion_backward": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p]),
+        "fnd_clip_adamw_step": (_c_int, [_c_void_p, _c_int, _c_void_p]),
+        "fnd_train_fwd_bwd": (_c_int, [_c_void_p, P(FndInputs), _c_void_p]),
+        "fnd_train_step": (_c_int, [_c_void_p, P(FndInputs), _c_void_p]),
+        "fnd_eval_step": (_c_int, [_c_void_p, P(FndInputs), _c_void_p]),
+        "fnd_launch_count": (_c_int, [_c_void_p, ctypes.c_char_p]),
+        "fnd_export_dropout_mask": (_c_int, [_c_void_p, _c_int, _c_void_p, ll, _c_void_p]),
+        "fnd_check_error": (_c_int, [_c_void_p, _c_void_p]),
         "fnd_gemm_scratch_bytes": (_c_size_t, [_c_int] * 4),
         "fnd_gemm_bf16": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_void_p, _c_void_p, _c_int, _c_int,
                                    _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,
@@ -106,9 +152,10 @@ def load() -> ctypes.CDLL:
     for name in declared_symbols():
         if not hasattr(lib, name):
             raise RuntimeError(f"libfnd_b200.so does not export {name} declared in include/fnd_b200.h")
-        if name in sigs:
-            fn = getattr(lib, name)
-            fn.restype, fn.argtypes = sigs[name]
+        if name not in sigs:
+            raise RuntimeError(f"{name} is declared in include/fnd_b200.h but has no ctypes signature in _lib.py")
+        fn = getattr(lib, name)
+        fn.restype, fn.argtypes = sigs[name]
     _lib = lib
     return lib
 

@@ -1,26 +1,755 @@
 // fnd_api.cu — C-ABI of libfnd_b200.so (see include/fnd_b200.h for the contract of every entry point).
-#include "../../include/fnd_b200.h"
-#include "fnd_gemm_host.h"
+#include "fnd_engine.h"
+#include <new>
 
 using namespace fnd;
 
-#define FND_CUDA_OK(expr)                                   \
-  do {                                                      \
-    cudaError_t _e = (expr);                                \
-    if (_e != cudaSuccess) return -1000 - static_cast<int>(_e); \
+#define FND_CUDA_OK(expr)                                        \
+  do {                                                           \
+    cudaError_t _e = (expr);                                     \
+    if (_e != cudaSuccess) return -1000 - static_cast<int>(_e);  \
+  } while (0)
+#define FND_OK(expr)          \
+  do {                        \
+    int _r = (expr);          \
+    if (_r) return _r;        \
   } while (0)
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// "slots" workspace buffer (16384 floats): [0, 8192) fused-step norm slots (wgrad CTAs, then finalize CTAs);
+// [8192, 12288) sumsq_kernel slots; [12288, 16384) scratch for the module-level finalize launches.
+static const int kSlotSumsq = 8192;
+static const int kSlotScratch = 12288;
+
+// ---------------------------------------------------------------------------------------------------
+// table construction (runs once per plan at bind time)
+// ---------------------------------------------------------------------------------------------------
+static int build_tables(Plan& P) {
+  TableBuilder tb(P);
+  const int B = P.B, H = P.H;
+  const fnd_dims& d = P.d;
+  const char* pn[5] = {"text_proj", "audio_proj", "visual_proj", "temporal_proj", "gnn_proj"};
+  // Q layout: input column (in P) and stacked weight of each q/k/v group
+  struct QGroup { int in_col; int q_col; int n; const char* first; };
+  const QGroup qg[4] = {{0, 0, 2 * H, "fusion.attn_tv.q"}, {2 * H, 2 * H, 3 * H, "fusion.attn_tv.k"},
+                        {H, 5 * H, 2 * H, "fusion.attn_ta.k"}, {3 * H, 7 * H, 2 * H, "fusion.attn_vu.k"}};
+  const int catw = P.nslots * H;
+  const int p0w = H + d.aux_dim;
+
+  // ---------------- forward ----------------
+  P.fwd_proj.kind = 0;
+  for (int i = 0; i < P.nmod; ++i) {
+    EpiParams e = epi_zero();
+    const std::string key = std::string("fusion.") + pn[i];
+    e.bias = P.W(key + ".bias");
+    e.out_f32 = P.buf<float>("P") + i * H; e.f32_pitch = 5 * H;
+    if (i < 4) {
+      e.out_hi = P.buf<__nv_bfloat16>("pbf_hi") + i * H;
+      e.out_lo = P.buf<__nv_bfloat16>("pbf_lo") ? P.buf<__nv_bfloat16>("pbf_lo") + i * H : nullptr;
+      e.bf_pitch = 5 * H;
+    }
+    FND_OK(add_problem(P, P.fwd_proj, tb.act("xbf", P.xoff[i], P.dsum, false), tb.weight(key + ".weight", P.xdim[i], false),
+                       B, H, P.xdim[i], 64, 1, e, ""));
+  }
+  P.fwd_qkv.kind = 0;
+  for (int g = 0; g < 4; ++g) {
+    EpiParams e = epi_zero();
+    e.bias = P.W(std::string(qg[g].first) + ".bias");
+    e.out_f32 = P.buf<float>("Q") + qg[g].q_col; e.f32_pitch = 9 * H;
+    FND_OK(add_problem(P, P.fwd_qkv, tb.act("pbf", qg[g].in_col, 5 * H, false),
+                       tb.weight(std::string(qg[g].first) + ".weight", H, false), B, qg[g].n, H, 64, 1, e, ""));
+  }
+  {
+    P.fwd_f0.kind = 0;
+    EpiParams e = epi_zero();
+    e.bias = P.W("fusion.fuse_mlp.0.bias");
+    e.out_pre = P.buf<float>("z_f0"); e.pre_pitch = 2 * H;
+    e.act = 1; e.drop_p = d.fusion_dropout; e.drop_stream = kStreamFuse0;
+    e.out_hi = P.buf<__nv_bfloat16>("h1_hi"); e.out_lo = P.buf<__nv_bfloat16>("h1_lo"); e.bf_pitch = 2 * H;
+    FND_OK(add_problem(P, P.fwd_f0, tb.act("fused_cat", 0, catw, false), tb.weight("fusion.fuse_mlp.0.weight", catw, false),
+                       B, 2 * H, catw, 64, P.splits_f0, e, "f0"));
+  }
+  {
+    P.fwd_f1.kind = 0;
+    EpiParams e = epi_zero();
+    e.bias = P.W("fusion.fuse_mlp.3.bias");
+    e.out_pre = P.buf<float>("z_f1"); e.pre_pitch = H;
+    e.act = 1; e.drop_p = d.fusion_dropout; e.drop_stream = kStreamFuse1;
+    e.out_f32 = P.buf<float>("fused"); e.f32_pitch = H;
+    e.out_hi = P.buf<__nv_bfloat16>("fusedbf_hi"); e.out_lo = P.buf<__nv_bfloat16>("fusedbf_lo"); e.bf_pitch = H;
+    FND_OK(add_problem(P, P.fwd_f1, tb.act("h1", 0, 2 * H, false), tb.weight("fusion.fuse_mlp.3.weight", 2 * H, false),
+                       B, H, 2 * H, 64, P.splits_f1, e, "f1"));
+  }
+  {
+    P.fwd_p0.kind = 0;
+    EpiParams e = epi_zero();
+    e.bias = P.W("clf.pre.0.bias");
+    if (d.aux_dim) {
+      e.aux = P.buf<float>("aux");
+      e.aux_w = P.W("clf.pre.0.weight") + H; e.aux_w_pitch = p0w;
+    }
+    e.out_pre = P.buf<float>("z_p0"); e.pre_pitch = H;
+    e.act = 1; e.drop_p = d.clf_dropout; e.drop_stream = kStreamPre0;
+    e.out_hi = P.buf<__nv_bfloat16>("xp1_hi"); e.out_lo = P.buf<__nv_bfloat16>("xp1_lo"); e.bf_pitch = H;
+    FND_OK(add_problem(P, P.fwd_p0, tb.act("fusedbf", 0, H, false), tb.weight_rp(false), B, H, H, 64, 1, e, ""));
+  }
+  {
+    P.fwd_p1.kind = 0;
+    EpiParams e = epi_zero();
+    e.bias = P.W("clf.pre.3.bias");
+    e.out_pre = P.buf<float>("z_p1"); e.pre_pitch = H;
+    e.act = 1; e.drop_p = d.clf_dropout; e.drop_stream = kStreamPre1;
+    e.out_f32 = P.buf<float>("h"); e.f32_pitch = H;
+    e.out_hi = P.buf<__nv_bfloat16>("hbf_hi"); e.out_lo = P.buf<__nv_bfloat16>("hbf_lo"); e.bf_pitch = H;
+    FND_OK(add_problem(P, P.fwd_p1, tb.act("xp1", 0, H, false), tb.weight("clf.pre.3.weight", H, false), B, H, H, 64, 1, e, ""));
+  }
+
+  // ---------------- dgrad (A = dY K-major, B = W viewed MN-major) ----------------
+  {
+    P.dg_p1.kind = 1;
+    EpiParams e = epi_zero();
+    e.gate_z = P.buf<float>("z_p0"); e.gate_pitch = H; e.gate_p = d.clf_dropout; e.gate_stream = kStreamPre0;
+    e.out_hi = P.buf<__nv_bfloat16>("dz_p0_hi"); e.out_lo = P.buf<__nv_bfloat16>("dz_p0_lo"); e.bf_pitch = H;
+    FND_OK(add_problem(P, P.dg_p1, tb.act("dz_p1", 0, H, false), tb.weight("clf.pre.3.weight", H, true), B, H, H, 64, 1, e, ""));
+  }
+  for (int fusedpath = 0; fusedpath < 2; ++fusedpath) {
+    GemmTable& T = fusedpath ? P.dg_p0_fused : P.dg_p0_split;
+    T.kind = 1;
+    EpiParams e = epi_zero();
+    if (fusedpath) {
+      e.gate_z = P.buf<float>("z_f1"); e.gate_pitch = H; e.gate_p = d.fusion_dropout; e.gate_stream = kStreamFuse1;
+      e.out_hi = P.buf<__nv_bfloat16>("dz_f1_hi"); e.out_lo = P.buf<__nv_bfloat16>("dz_f1_lo"); e.bf_pitch = H;
+    } else {
+      e.out_f32 = P.buf<float>("dfused"); e.f32_pitch = H;
+    }
+    FND_OK(add_problem(P, T, tb.act("dz_p0", 0, H, false), tb.weight_rp(true), B, H, H, 64, 1, e, ""));
+  }
+  {
+    P.dg_f1.kind = 1;
+    EpiParams e = epi_zero();
+    e.gate_z = P.buf<float>("z_f0"); e.gate_pitch = 2 * H; e.gate_p = d.fusion_dropout; e.gate_stream = kStreamFuse0;
+    e.out_hi = P.buf<__nv_bfloat16>("dz_f0_hi"); e.out_lo = P.buf<__nv_bfloat16>("dz_f0_lo"); e.bf_pitch = 2 * H;
+    FND_OK(add_problem(P, P.dg_f1, tb.act("dz_f1", 0, H, false), tb.weight("fusion.fuse_mlp.3.weight", 2 * H, true),
+                       B, 2 * H, H, 64, 1, e, ""));
+  }
+  {
+    P.dg_f0.kind = 1;
+    EpiParams e = epi_zero();
+    e.out_f32 = P.buf<float>("dcat"); e.f32_pitch = catw;
+    FND_OK(add_problem(P, P.dg_f0, tb.act("dz_f0", 0, 2 * H, false), tb.weight("fusion.fuse_mlp.0.weight", catw, true),
+                       B, catw, 2 * H, 64, 1, e, ""));
+  }
+  P.dg_qkv.kind = 1;
+  for (int g = 0; g < 4; ++g) {
+    EpiParams e = epi_zero();
+    e.add_in = P.buf<float>("dPdirect") + qg[g].in_col; e.add_pitch = 5 * H;
+    e.out_hi = P.buf<__nv_bfloat16>("dP_hi") + qg[g].in_col;
+    e.out_lo = P.buf<__nv_bfloat16>("dP_lo") ? P.buf<__nv_bfloat16>("dP_lo") + qg[g].in_col : nullptr;
+    e.bf_pitch = 5 * H;
+    FND_OK(add_problem(P, P.dg_qkv, tb.act("dQ", qg[g].q_col, 9 * H, false),
+                       tb.weight(std::string(qg[g].first) + ".weight", H, true), B, H, qg[g].n, 64, 1, e, ""));
+  }
+
+  // ---------------- wgrad (dW[N_out, K_in] = dY^T X; both operands MN-major; contraction = batch) -------------
+  auto wg = [&](GemmTable& T, const Operand& dY, const Operand& X, int n_out, int k_in, float* dst, int pitch) -> int {
+    EpiParams e = epi_zero();
+    e.out_f32 = dst; e.f32_pitch = pitch;
+    return add_problem(P, T, dY, X, n_out, k_in, B, 128, 1, e, "");
+  };
+  auto build_wg = [&](GemmTable& T, bool clf, bool fus) -> int {
+    T.kind = 2;
+    if (clf) {
+      FND_OK(wg(T, tb.act("dz_p1", 0, H, true), tb.act("xp1", 0, H, true), H, H, P.G("clf.pre.3.weight"), H));
+      FND_OK(wg(T, tb.act("dz_p0", 0, H, true), tb.act("fusedbf", 0, H, true), H, H, P.G("clf.pre.0.weight"), p0w));
+      FND_OK(wg(T, tb.act("dFbf", 0, kDFCols, true), tb.act("hbf", 0, H, true), P.TD + 2, H, P.buf<float>("dAraw"), H));
+    }
+    if (fus) {
+      FND_OK(wg(T, tb.act("dz_f1", 0, H, true), tb.act("h1", 0, 2 * H, true), H, 2 * H, P.G("fusion.fuse_mlp.3.weight"), 2 * H));
+      FND_OK(wg(T, tb.act("dz_f0", 0, 2 * H, true), tb.act("fused_cat", 0, catw, true), 2 * H, catw,
+                P.G("fusion.fuse_mlp.0.weight"), catw));
+      for (int g = 0; g < 4; ++g)
+        FND_OK(wg(T, tb.act("dQ", qg[g].q_col, 9 * H, true), tb.act("pbf", qg[g].in_col, 5 * H, true), qg[g].n, H,
+                  P.G(std::string(qg[g].first) + ".weight"), H));
+      for (int i = 0; i < P.nmod; ++i)
+        FND_OK(wg(T, tb.act("dP", i * H, 5 * H, true), tb.act("xbf", P.xoff[i], P.dsum, true), H, P.xdim[i],
+                  P.G(std::string("fusion.") + pn[i] + ".weight"), P.xdim[i]));
+    }
+    return 0;
+  };
+  FND_OK(build_wg(P.wg_all, true, true));
+  FND_OK(build_wg(P.wg_clf, true, false));
+  FND_OK(build_wg(P.wg_fus, false, true));
+
+  // ---------------- finalize job tables ----------------
+  auto job = [&](FinTable& T, int type, int rows, int cols, int src_pitch, const float* f32, const __nv_bfloat16* hi,
+                 const __nv_bfloat16* lo, const float* aux, float* dst, int dst_pitch, float scale) {
+    FinJob j;
+    memset(&j, 0, sizeof(j));
+    j.type = type; j.rows = rows; j.cols = cols; j.src_pitch = src_pitch;
+    j.src_f32 = f32; j.src_hi = hi; j.src_lo = lo; j.aux = aux; j.dst = dst; j.dst_pitch = dst_pitch; j.scale = scale;
+    j.cta_count = (type == kJobSoftmaxBwd) ? rows : ceil_div(cols, 64);
+    j.want_norm = 1;
+    T.host.push_back(j);
+  };
+  auto bfj = [&](FinTable& T, const std::string& name, int col, int cols, int pitch, float* dst) {
+    const __nv_bfloat16* lo = P.buf<__nv_bfloat16>(name + "_lo");
+    job(T, kJobColsumBF16, B, cols, pitch, nullptr, P.buf<__nv_bfloat16>(name + "_hi") + col, lo ? lo + col : nullptr,
+        nullptr, dst, 0, 1.0f);
+  };
+  auto build_fin = [&](FinTable& T, bool clf, bool fus) {
+    if (clf) {
+      bfj(T, "dz_p1", 0, H, H, P.G("clf.pre.3.bias"));
+      bfj(T, "dz_p0", 0, H, H, P.G("clf.pre.0.bias"));
+      if (d.aux_dim) {
+        const __nv_bfloat16* lo = P.buf<__nv_bfloat16>("dz_p0_lo");
+        job(T, kJobColsumAux, B, H, H, nullptr, P.buf<__nv_bfloat16>("dz_p0_hi"), lo, P.buf<float>("aux"),
+            P.G("clf.pre.0.weight") + H, p0w, 1.0f);
+      }
+      job(T, kJobColsumF32, B, P.TD, kDFCols, P.buf<float>("dF"), nullptr, nullptr, nullptr, P.G("clf.node.trees.0.thresh.0"), 0, -1.0f);
+      job(T, kJobColsumF32, B, 2, kDFCols, P.buf<float>("dF") + P.TD, nullptr, nullptr, nullptr, P.G("clf.bypass.bias"), 0, 1.0f);
+      job(T, kJobColsumF32, B, d.trees * P.leaves * 2, d.trees * P.leaves * 2, P.buf<float>("leafc"), nullptr, nullptr, nullptr,
+          P.G("clf.node.trees.0.leaf_logits"), 0, 1.0f);
+      job(T, kJobColsumF32, 1, 2 * H, 2 * H, P.buf<float>("dAraw") + static_cast<size_t>(P.TD) * H, nullptr, nullptr, nullptr,
+          P.G("clf.bypass.weight"), 0, 1.0f);
+      job(T, kJobSoftmaxBwd, P.TD, H, H, P.buf<float>("dAraw"), nullptr, nullptr, P.buf<float>("alpha"),
+          P.G("clf.node.trees.0.gates.0"), H, 1.0f);
+    }
+    if (fus) {
+      bfj(T, "dP", 0, P.nmod * H, 5 * H, P.G("fusion.text_proj.bias"));
+      bfj(T, "dQ", 0, 9 * H, 9 * H, P.G("fusion.attn_tv.q.bias"));
+      bfj(T, "dz_f0", 0, 2 * H, 2 * H, P.G("fusion.fuse_mlp.0.bias"));
+      bfj(T, "dz_f1", 0, H, H, P.G("fusion.fuse_mlp.3.bias"));
+      job(T, kJobColsumF32, P.n_asm_ctas, 3 * P.L.evstride, 3 * P.L.evstride, P.buf<float>("ev_partial"), nullptr, nullptr,
+          nullptr, P.G("fusion.attn_tv.evidence_proj.0.weight"), 0, 1.0f);
+    }
+    int c = 0;
+    for (auto& j : T.host) { j.cta_begin = c; c += j.cta_count; }
+    T.grid = c;
+  };
+  build_fin(P.fin_all, true, true);
+  build_fin(P.fin_clf, true, false);
+  build_fin(P.fin_fus, false, true);
+
+  // ---------------- finish: CTA prefixes, slots, upload ----------------
+  GemmTable* all[] = {&P.fwd_proj, &P.fwd_qkv, &P.fwd_f0, &P.fwd_f1, &P.fwd_p0, &P.fwd_p1, &P.dg_p1, &P.dg_p0_fused,
+                      &P.dg_p0_split, &P.dg_f1, &P.dg_f0, &P.dg_qkv, &P.wg_all, &P.wg_clf, &P.wg_fus};
+  for (GemmTable* T : all) T->grid = finish_table(T->host.data(), static_cast<int>(T->host.size()));
+  // gradient-norm slots: fused-step wgrad CTAs first (the dAraw problem writes none: its slots stay 0)
+  float* slots = P.buf<float>("slots");
+  for (auto& g : P.wg_all.host)
+    if (g.epi.out_f32 != P.buf<float>("dAraw")) g.epi.sumsq_slots = slots + g.cta_begin;
+  P.total_slots = P.wg_all.grid + P.fin_all.grid;
+  if (P.total_slots > kSlotSumsq || P.fin_all.grid > 16384 - kSlotScratch) return -31;
+  return 0;
+}
+
+static int upload_tables(Plan& P, cudaStream_t st) {
+  uint8_t* base = P.buf<uint8_t>("tables");
+  size_t off = 0;
+  const size_t cap = static_cast<size_t>(P.bufs["tables"].bytes);
+  GemmTable* all[] = {&P.fwd_proj, &P.fwd_qkv, &P.fwd_f0, &P.fwd_f1, &P.fwd_p0, &P.fwd_p1, &P.dg_p1, &P.dg_p0_fused,
+                      &P.dg_p0_split, &P.dg_f1, &P.dg_f0, &P.dg_qkv, &P.wg_all, &P.wg_clf, &P.wg_fus};
+  for (GemmTable* T : all) {
+    const size_t bytes = T->host.size() * sizeof(GemmProblem);
+    if (off + bytes > cap) return -32;
+    T->dev = reinterpret_cast<GemmProblem*>(base + off);
+    FND_CUDA_OK(cudaMemcpyAsync(T->dev, T->host.data(), bytes, cudaMemcpyHostToDevice, st));
+    off = align_up(off + bytes, 256);
+  }
+  FinTable* fins[] = {&P.fin_all, &P.fin_clf, &P.fin_fus};
+  for (FinTable* T : fins) {
+    const size_t bytes = T->host.size() * sizeof(FinJob);
+    if (off + bytes > cap) return -32;
+    T->dev = reinterpret_cast<FinJob*>(base + off);
+    FND_CUDA_OK(cudaMemcpyAsync(T->dev, T->host.data(), bytes, cudaMemcpyHostToDevice, st));
+    off = align_up(off + bytes, 256);
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// launch helpers
+// ---------------------------------------------------------------------------------------------------
+static inline RunCtx make_ctx(const Plan& P, int training) {
+  DevState* S = P.state();
+  RunCtx c;
+  c.err = &S->err;
+  c.rng = S->rng;
+  c.training = training;
+  return c;
+}
+static int run_gemm(const Plan& P, const GemmTable& T, int training, cudaStream_t st) {
+  FND_CUDA_OK(launch_gemm(T.kind, T.dev, static_cast<int>(T.host.size()), T.grid, make_ctx(P, training), st));
+  return 0;
+}
+
+static int run_prep(Plan& P, const fnd_inputs* in, int training, bool bump_clf, cudaStream_t st) {
+  PrepParams pp;
+  memset(&pp, 0, sizeof(pp));
+  for (int i = 0; i < P.nmod; ++i) {
+    if (!in->x[i]) return -40;
+    if (in->pitch[i] % 4 || (reinterpret_cast<uintptr_t>(in->x[i]) & 15)) return -41;
+    pp.x[i] = in->x[i]; pp.xpitch[i] = in->pitch[i]; pp.xdim[i] = P.xdim[i]; pp.xoff[i] = P.xoff[i];
+  }
+  pp.nmod = P.nmod; pp.dsum = P.dsum; pp.gather = in->gather;
+  pp.aux_src = P.d.aux_dim ? in->aux : nullptr; pp.aux_pitch = in->aux_pitch;
+  pp.label_src = in->labels;
+  pp.aux_dst = P.buf<float>("aux"); pp.label_dst = P.buf<long long>("labels");
+  pp.out_hi = P.buf<__nv_bfloat16>("xbf_hi"); pp.out_lo = P.buf<__nv_bfloat16>("xbf_lo");
+  pp.B = P.B;
+  pp.gates = P.W("clf.node.trees.0.gates.0"); pp.alpha = P.buf<float>("alpha");
+  pp.TD = P.TD; pp.H = P.H;
+  pp.rng = P.state()->rng; pp.bump_fusion = training ? 1 : 0; pp.bump_clf = (training && bump_clf) ? 1 : 0;
+  prep_kernel<<<P.B + P.TD, kRowThreads, 0, st>>>(pp);
+  FND_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+static void fill_ev(const Plan& P, EvidenceParams (&ev)[3]) {
+  const char* an[3] = {"attn_tv", "attn_ta", "attn_vu"};
+  for (int k = 0; k < 3; ++k) {
+    const std::string b = std::string("fusion.") + an[k] + ".evidence_proj.";
+    ev[k].w1 = P.W(b + "0.weight"); ev[k].b1 = P.W(b + "0.bias");
+    ev[k].w2 = P.W(b + "2.weight"); ev[k].b2 = P.W(b + "2.bias");
+  }
+}
+
+static int run_assemble_fwd(Plan& P, cudaStream_t st) {
+  AssembleParams a;
+  memset(&a, 0, sizeof(a));
+  a.P = P.buf<float>("P"); a.Q = P.buf<float>("Q");
+  fill_ev(P, a.ev);
+  a.cat_hi = P.buf<__nv_bfloat16>("fused_cat_hi"); a.cat_lo = P.buf<__nv_bfloat16>("fused_cat_lo");
+  a.rowstat = P.buf<float>("rowstat");
+  a.B = P.B; a.H = P.H; a.use_gnn = P.d.use_gnn;
+  const int grid = P.B < 1184 ? P.B : 1184;
+  if (P.H == 512) assemble_fwd_kernel<1><<<grid, kRowThreads, 0, st>>>(a);
+  else assemble_fwd_kernel<2><<<grid, kRowThreads, 0, st>>>(a);
+  FND_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+static int run_assemble_bwd(Plan& P, cudaStream_t st) {
+  AssembleBwdParams a;
+  memset(&a, 0, sizeof(a));
+  a.P = P.buf<float>("P"); a.Q = P.buf<float>("Q"); a.dcat = P.buf<float>("dcat"); a.rowstat = P.buf<float>("rowstat");
+  fill_ev(P, a.ev);
+  a.dPdirect = P.buf<float>("dPdirect");
+  a.dQ_hi = P.buf<__nv_bfloat16>("dQ_hi"); a.dQ_lo = P.buf<__nv_bfloat16>("dQ_lo");
+  a.dP_hi = P.buf<__nv_bfloat16>("dP_hi"); a.dP_lo = P.buf<__nv_bfloat16>("dP_lo");
+  a.ev_partial = P.buf<float>("ev_partial"); a.evstride = P.L.evstride;
+  a.B = P.B; a.H = P.H; a.use_gnn = P.d.use_gnn;
+  if (P.H == 512) assemble_bwd_kernel<1><<<P.n_asm_ctas, kRowThreads, 0, st>>>(a);
+  else assemble_bwd_kernel<2><<<P.n_asm_ctas, kRowThreads, 0, st>>>(a);
+  FND_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+static HeadParams head_params(const Plan& P, int training) {
+  HeadParams h;
+  memset(&h, 0, sizeof(h));
+  h.h = P.buf<float>("h"); h.alpha = P.buf<float>("alpha");
+  h.thresh = P.W("clf.node.trees.0.thresh.0"); h.leaf = P.W("clf.node.trees.0.leaf_logits");
+  h.wb = P.W("clf.bypass.weight"); h.bb = P.W("clf.bypass.bias"); h.temperature = P.W("clf.temperature");
+  h.labels = P.buf<long long>("labels");
+  h.tau = P.d.node_tau; h.tree_drop_p = P.d.tree_dropout; h.training = training;
+  h.logits = P.buf<float>("logits"); h.probs = P.buf<float>("probs"); h.svals = P.buf<float>("svals");
+  h.loss_row = P.buf<float>("loss_row"); h.dlogits_out = P.buf<float>("dlogits");
+  h.dF = P.buf<float>("dF"); h.dF_hi = P.buf<__nv_bfloat16>("dFbf_hi"); h.dF_lo = P.buf<__nv_bfloat16>("dFbf_lo");
+  h.leafc = P.buf<float>("leafc");
+  h.z_pre1 = P.buf<float>("z_p1"); h.pre_drop_p = P.d.clf_dropout;
+  h.dz_hi = P.buf<__nv_bfloat16>("dz_p1_hi"); h.dz_lo = P.buf<__nv_bfloat16>("dz_p1_lo");
+  h.state = P.state();
+  h.B = P.B; h.H = P.H; h.T = P.d.trees; h.D = P.d.depth;
+  return h;
+}
+template <bool FWD, bool CE, bool BWD>
+static int run_head(const Plan& P, const HeadParams& h, cudaStream_t st) {
+  const int grid = ceil_div(P.B, 8);
+  if (P.H == 512) head_kernel<FWD, CE, BWD, 4><<<grid, 256, 0, st>>>(h);
+  else head_kernel<FWD, CE, BWD, 8><<<grid, 256, 0, st>>>(h);
+  FND_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+static int run_finalize(Plan& P, const FinTable& T, int slot_base, int total_slots, bool with_loss, int update_step,
+                        cudaStream_t st) {
+  FinParams f;
+  memset(&f, 0, sizeof(f));
+  f.jobs = T.dev; f.njobs = static_cast<int>(T.host.size());
+  f.slots = P.buf<float>("slots"); f.slot_base = slot_base; f.total_slots = total_slots;
+  f.loss_row = with_loss ? P.buf<float>("loss_row") : nullptr; f.B = P.B;
+  f.state = P.state(); f.update_step = update_step;
+  finalize_kernel<<<T.grid, 256, 0, st>>>(f);
+  FND_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+static AdamWParams adamw_params(const Plan& P) {
+  AdamWParams a;
+  memset(&a, 0, sizeof(a));
+  a.p = P.params; a.g = P.grads; a.m = P.m; a.v = P.v;
+  a.n = static_cast<size_t>(P.L.n_hot);
+  a.sh_hi = P.sh_hi; a.sh_lo = P.sh_lo; a.n_shadow = static_cast<size_t>(P.L.n_shadow);
+  if (P.d.aux_dim) {
+    a.rp_begin = static_cast<size_t>(P.L.at("clf.pre.0.weight"));
+    a.rp_end = a.rp_begin + static_cast<size_t>(P.H) * (P.H + P.d.aux_dim);
+    a.rp_cols = P.H + P.d.aux_dim; a.rp_pitch = P.L.rp_pitch;
+    a.rp_hi = P.sh_hi + P.L.n_shadow; a.rp_lo = P.sh_lo ? P.sh_lo + P.L.n_shadow : nullptr;
+  }
+  a.state = P.state();
+  return a;
+}
+
+static int fusion_forward_impl(Plan& P, const fnd_inputs* in, int training, bool bump_clf, cudaStream_t st) {
+  P.last_training = training;
+  FND_OK(run_prep(P, in, training, bump_clf, st));
+  FND_OK(run_gemm(P, P.fwd_proj, training, st));
+  FND_OK(run_gemm(P, P.fwd_qkv, training, st));
+  FND_OK(run_assemble_fwd(P, st));
+  FND_OK(run_gemm(P, P.fwd_f0, training, st));
+  FND_OK(run_gemm(P, P.fwd_f1, training, st));
+  return 0;
+}
+static int fusion_head_impl(Plan& P, cudaStream_t st) {   // fusion.classifier: returned for API parity only
+  rowlinear2_fwd_kernel<<<ceil_div(P.B, 8), 256, 0, st>>>(P.buf<float>("fused"), P.W("fusion.classifier.weight"),
+                                                          P.W("fusion.classifier.bias"), P.buf<float>("fusion_logits"),
+                                                          P.B, P.H);
+  FND_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+static int classifier_gemms_impl(Plan& P, int training, cudaStream_t st) {
+  FND_OK(run_gemm(P, P.fwd_p0, training, st));
+  FND_OK(run_gemm(P, P.fwd_p1, training, st));
+  return 0;
+}
+
+static Plan* as_plan(void* p) { return static_cast<Plan*>(p); }
+#define FND_PLAN(p)                      \
+  Plan* PP = as_plan(p);                 \
+  if (!PP) return -1;                    \
+  if (!PP->bound) return -5;             \
+  Plan& P = *PP;                         \
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream)
+
 extern "C" {
 
 int fnd_version(void) { return 100; }
-
 const char* fnd_build_arch(void) { return "sm_100a"; }
 
+// ------------------------------- arena -------------------------------
+int fnd_param_count(const fnd_dims* dims) {
+  if (!dims || !dims_ok(*dims)) return -1;
+  return static_cast<int>(make_layout(*dims).entries.size());
+}
+int fnd_param_info(const fnd_dims* dims, int index, char* name, int name_cap, long long* offset, int* ndim, int* rows,
+                   int* cols, int* hot) {
+  if (!dims || !dims_ok(*dims)) return -1;
+  const ArenaLayout L = make_layout(*dims);
+  if (index < 0 || index >= static_cast<int>(L.entries.size())) return -2;
+  const ParamEntry& e = L.entries[index];
+  if (name && name_cap > 0) {
+    strncpy(name, e.name.c_str(), name_cap - 1);
+    name[name_cap - 1] = 0;
+  }
+  if (offset) *offset = e.offset;
+  if (ndim) *ndim = e.ndim;
+  if (rows) *rows = e.rows;
+  if (cols) *cols = e.cols;
+  if (hot) *hot = e.hot;
+  return 0;
+}
+long long fnd_arena_total_elems(const fnd_dims* dims) { return (dims && dims_ok(*dims)) ? make_layout(*dims).n_total : -1; }
+long long fnd_arena_hot_elems(const fnd_dims* dims) { return (dims && dims_ok(*dims)) ? make_layout(*dims).n_hot : -1; }
+long long fnd_arena_shadow_elems(const fnd_dims* dims) { return (dims && dims_ok(*dims)) ? make_layout(*dims).n_shadow : -1; }
+long long fnd_arena_shadow_buffer_elems(const fnd_dims* dims) {
+  if (!dims || !dims_ok(*dims)) return -1;
+  const ArenaLayout L = make_layout(*dims);
+  return L.n_shadow + align64(L.rp_elems);
+}
+
+// ------------------------------- plan -------------------------------
+int fnd_plan_create(const fnd_dims* dims, int batch, int mode, void** plan_out) {
+  if (!dims || !plan_out || batch < 1 || (mode != 0 && mode != 1)) return -1;
+  if (!dims_ok(*dims)) return -2;
+  Plan* P = new (std::nothrow) Plan();
+  if (!P) return -3;
+  P->d = *dims;
+  P->L = make_layout(*dims);
+  P->B = batch; P->mode = mode; P->ncombo = mode ? 3 : 1;
+  P->H = dims->hidden; P->nmod = dims->use_gnn ? 5 : 4; P->nslots = dims->use_gnn ? 16 : 15;
+  P->TD = dims->trees * dims->depth; P->leaves = 1 << dims->depth;
+  const int pd[5] = {dims->d_text, dims->d_audio, dims->d_visual, dims->d_temporal, dims->d_gnn};
+  int o = 0;
+  for (int i = 0; i < P->nmod; ++i) { P->xoff[i] = o; P->xdim[i] = pd[i]; o += pd[i]; }
+  P->dsum = o;
+  carve(*P);
+  *plan_out = P;
+  return 0;
+}
+void fnd_plan_destroy(void* plan) { delete as_plan(plan); }
+size_t fnd_plan_workspace_bytes(const void* plan) { return plan ? static_cast<size_t>(static_cast<const Plan*>(plan)->ws_bytes) : 0; }
+long long fnd_plan_buffer_offset(const void* plan, const char* name) {
+  if (!plan || !name) return -1;
+  const Plan* P = static_cast<const Plan*>(plan);
+  auto it = P->bufs.find(name);
+  return it == P->bufs.end() ? -1 : it->second.off;
+}
+long long fnd_plan_buffer_bytes(const void* plan, const char* name) {
+  if (!plan || !name) return -1;
+  const Plan* P = static_cast<const Plan*>(plan);
+  auto it = P->bufs.find(name);
+  return it == P->bufs.end() ? -1 : it->second.bytes;
+}
+
+int fnd_plan_bind(void* plan, void* workspace, float* params, float* grads, float* adam_m, float* adam_v, void* shadow_hi,
+                  void* shadow_lo, void* stream) {
+  Plan* PP = as_plan(plan);
+  if (!PP || !workspace || !params || !grads || !shadow_hi) return -1;
+  Plan& P = *PP;
+  if (P.ncombo == 3 && !shadow_lo) return -2;
+  if ((reinterpret_cast<uintptr_t>(workspace) & 255) || (reinterpret_cast<uintptr_t>(params) & 255) ||
+      (reinterpret_cast<uintptr_t>(grads) & 255) || (reinterpret_cast<uintptr_t>(shadow_hi) & 255))
+    return -3;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  FND_CUDA_OK(init_gemm_attrs());
+  P.ws = static_cast<uint8_t*>(workspace);
+  P.params = params; P.grads = grads; P.m = adam_m; P.v = adam_v;
+  P.sh_hi = static_cast<__nv_bfloat16*>(shadow_hi);
+  P.sh_lo = P.ncombo == 3 ? static_cast<__nv_bfloat16*>(shadow_lo) : nullptr;
+  FND_CUDA_OK(cudaMemsetAsync(P.ws, 0, static_cast<size_t>(P.ws_bytes), st));
+  GemmTable* all[] = {&P.fwd_proj, &P.fwd_qkv, &P.fwd_f0, &P.fwd_f1, &P.fwd_p0, &P.fwd_p1, &P.dg_p1, &P.dg_p0_fused,
+                      &P.dg_p0_split, &P.dg_f1, &P.dg_f0, &P.dg_qkv, &P.wg_all, &P.wg_clf, &P.wg_fus};
+  for (GemmTable* T : all) T->host.clear();
+  P.fin_all.host.clear(); P.fin_clf.host.clear(); P.fin_fus.host.clear();
+  FND_OK(build_tables(P));
+  FND_OK(upload_tables(P, st));
+  DevState hs;
+  memset(&hs, 0, sizeof(hs));
+  hs.rng[0] = 0x9E3779B9u; hs.rng[1] = 0x7F4A7C15u;
+  hs.lr = 2e-4f; hs.beta1 = 0.9f; hs.beta2 = 0.999f; hs.eps = 1e-8f; hs.weight_decay = 1e-4f; hs.max_norm = 5.0f;
+  hs.bc1 = 1.0f; hs.bc2 = 1.0f; hs.clip_coef = 1.0f;
+  hs.loss_scale = 1.0f / static_cast<float>(P.B);
+  FND_CUDA_OK(cudaMemcpyAsync(P.state(), &hs, sizeof(hs), cudaMemcpyHostToDevice, st));
+  FND_CUDA_OK(cudaStreamSynchronize(st));   // hs / host tables are stack or plan-owned pageable memory
+  P.bound = true;
+  return 0;
+}
+
+// ------------------------------- state -------------------------------
+static int write_state(Plan& P, size_t field_off, const void* src, size_t bytes, cudaStream_t st) {
+  FND_CUDA_OK(cudaMemcpyAsync(reinterpret_cast<uint8_t*>(P.state()) + field_off, src, bytes, cudaMemcpyHostToDevice, st));
+  FND_CUDA_OK(cudaStreamSynchronize(st));
+  return 0;
+}
+int fnd_set_hyper(void* plan, float lr, float beta1, float beta2, float eps, float weight_decay, float max_norm, void* stream) {
+  FND_PLAN(plan);
+  const float h[6] = {lr, beta1, beta2, eps, weight_decay, max_norm};
+  return write_state(P, offsetof(DevState, lr), h, sizeof(h), st);
+}
+int fnd_set_lr(void* plan, float lr, void* stream) {
+  FND_PLAN(plan);
+  return write_state(P, offsetof(DevState, lr), &lr, sizeof(lr), st);
+}
+int fnd_set_seed(void* plan, unsigned long long seed, void* stream) {
+  FND_PLAN(plan);
+  const uint32_t r[2] = {static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32)};
+  return write_state(P, offsetof(DevState, rng), r, sizeof(r), st);
+}
+int fnd_set_loss_scale(void* plan, float scale, void* stream) {
+  FND_PLAN(plan);
+  return write_state(P, offsetof(DevState, loss_scale), &scale, sizeof(scale), st);
+}
+int fnd_refresh_shadows(void* plan, void* stream) {
+  FND_PLAN(plan);
+  AdamWParams a = adamw_params(P);
+  shadow_refresh_kernel<<<148 * 8, 256, 0, st>>>(a);
+  FND_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+int fnd_check_error(void* plan, void* stream) {
+  FND_PLAN(plan);
+  int herr = 0;
+  FND_CUDA_OK(cudaMemcpyAsync(&herr, &P.state()->err, sizeof(int), cudaMemcpyDeviceToHost, st));
+  FND_CUDA_OK(cudaStreamSynchronize(st));
+  if (herr) {
+    FND_CUDA_OK(cudaMemsetAsync(&P.state()->err, 0, sizeof(int), st));
+    FND_CUDA_OK(cudaStreamSynchronize(st));
+  }
+  return herr;
+}
+int fnd_export_dropout_mask(void* plan, int layer, float* out, long long n, void* stream) {
+  FND_PLAN(plan);
+  if (!out || n <= 0) return -1;
+  float p = 0.f;
+  switch (layer) {
+    case kStreamFuse0: case kStreamFuse1: p = P.d.fusion_dropout; break;
+    case kStreamPre0: case kStreamPre1: p = P.d.clf_dropout; break;
+    case kStreamTree: p = P.d.tree_dropout; break;
+    default: return -2;
+  }
+  dropout_mask_kernel<<<256, 256, 0, st>>>(out, static_cast<size_t>(n), p, layer, P.state());
+  FND_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------- module-level entry points -------------------------------
+int fnd_fusion_forward(void* plan, const fnd_inputs* in, int training, void* stream) {
+  FND_PLAN(plan);
+  if (!in) return -1;
+  FND_OK(fusion_forward_impl(P, in, training, false, st));
+  return fusion_head_impl(P, st);
+}
+
+int fnd_classifier_forward(void* plan, const float* fused, const float* aux, int aux_pitch, int training, void* stream) {
+  FND_PLAN(plan);
+  P.last_training = training;
+  if (fused || aux) {
+    // stage external inputs: cast `fused` to the bf16 operand planes and copy aux rows
+    PrepParams pp;
+    memset(&pp, 0, sizeof(pp));
+    pp.nmod = fused ? 1 : 0;
+    pp.x[0] = fused; pp.xpitch[0] = P.H; pp.xdim[0] = P.H; pp.xoff[0] = 0; pp.dsum = P.H;
+    pp.aux_src = (P.d.aux_dim && aux) ? aux : nullptr; pp.aux_pitch = aux_pitch; pp.aux_dst = P.buf<float>("aux");
+    pp.out_hi = P.buf<__nv_bfloat16>("fusedbf_hi"); pp.out_lo = P.buf<__nv_bfloat16>("fusedbf_lo");
+    pp.B = P.B; pp.gates = P.W("clf.node.trees.0.gates.0"); pp.alpha = P.buf<float>("alpha"); pp.TD = P.TD; pp.H = P.H;
+    pp.rng = P.state()->rng; pp.bump_clf = training ? 1 : 0;
+    prep_kernel<<<P.B + P.TD, kRowThreads, 0, st>>>(pp);
+    FND_CUDA_OK(cudaGetLastError());
+  }
+  FND_OK(classifier_gemms_impl(P, training, st));
+  HeadParams h = head_params(P, training);
+  return run_head<true, false, false>(P, h, st);
+}
+
+int fnd_ce_loss_fwd_bwd(void* plan, const long long* labels, void* stream) {
+  FND_PLAN(plan);
+  HeadParams h = head_params(P, P.last_training);
+  if (labels) h.labels = labels;
+  return run_head<false, true, false>(P, h, st);
+}
+
+int fnd_classifier_backward(void* plan, const float* dlogits, void* stream) {
+  FND_PLAN(plan);
+  const int tr = P.last_training;
+  HeadParams h = head_params(P, tr);
+  h.dlogits_in = dlogits ? dlogits : P.buf<float>("dlogits");
+  FND_OK((run_head<false, false, true>(P, h, st)));
+  FND_OK(run_gemm(P, P.dg_p1, tr, st));
+  FND_OK(run_gemm(P, P.dg_p0_split, tr, st));
+  FND_OK(run_gemm(P, P.wg_clf, tr, st));
+  return run_finalize(P, P.fin_clf, kSlotScratch, 0, false, 0, st);
+}
+
+int fnd_fusion_backward(void* plan, const float* dfused, const float* dfusion_logits, void* stream) {
+  FND_PLAN(plan);
+  const int tr = P.last_training;
+  const float* df = dfused ? dfused : P.buf<float>("dfused");
+  if (dfusion_logits) {
+    // d fused += dlogits . W_classifier   (fusion.classifier, cross_modal_transformer.py:198)
+    float* acc = P.buf<float>("dfused");
+    if (df != acc) FND_CUDA_OK(cudaMemcpyAsync(acc, df, static_cast<size_t>(P.B) * P.H * 4, cudaMemcpyDeviceToDevice, st));
+    rowlinear2_dgrad_kernel<<<P.B, 256, 0, st>>>(dfusion_logits, P.W("fusion.classifier.weight"), acc, P.B, P.H, 1);
+    FND_CUDA_OK(cudaGetLastError());
+    df = acc;
+  }
+  GateParams g;
+  memset(&g, 0, sizeof(g));
+  g.dy = df; g.z = P.buf<float>("z_f1");
+  g.out_hi = P.buf<__nv_bfloat16>("dz_f1_hi"); g.out_lo = P.buf<__nv_bfloat16>("dz_f1_lo");
+  g.drop_p = P.d.fusion_dropout; g.stream = kStreamFuse1; g.training = tr; g.state = P.state();
+  g.n = static_cast<size_t>(P.B) * P.H;
+  gate_kernel<<<ceil_div(static_cast<int>(g.n / 4), 256), 256, 0, st>>>(g);
+  FND_CUDA_OK(cudaGetLastError());
+  FND_OK(run_gemm(P, P.dg_f1, tr, st));
+  FND_OK(run_gemm(P, P.dg_f0, tr, st));
+  FND_OK(run_assemble_bwd(P, st));
+  FND_OK(run_gemm(P, P.dg_qkv, tr, st));
+  FND_OK(run_gemm(P, P.wg_fus, tr, st));
+  return run_finalize(P, P.fin_fus, kSlotScratch, 0, false, 0, st);
+}
+
+int fnd_clip_adamw_step(void* plan, int norm_from_slots, void* stream) {
+  FND_PLAN(plan);
+  if (!P.m || !P.v) return -6;
+  if (!norm_from_slots) {
+    // norm over the (possibly all-reduced) gradient arena + optimizer-step bookkeeping
+    float* slots = P.buf<float>("slots");
+    const int nb = 148 * 4;
+    sumsq_kernel<<<nb, 256, 0, st>>>(P.grads, static_cast<size_t>(P.L.n_hot), slots + kSlotSumsq);
+    FND_CUDA_OK(cudaGetLastError());
+    norm_finish_kernel<<<1, 256, 0, st>>>(slots + kSlotSumsq, nb, P.state(), 1);
+    FND_CUDA_OK(cudaGetLastError());
+  } else {
+    step_kernel<<<1, 32, 0, st>>>(P.state());
+    FND_CUDA_OK(cudaGetLastError());
+  }
+  AdamWParams a = adamw_params(P);
+  adamw_kernel<<<148 * 8, 256, 0, st>>>(a);
+  FND_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------- fused trainer step -------------------------------
+static int train_fwd_bwd_impl(void* plan, const fnd_inputs* in, int update_step, void* stream) {
+  FND_PLAN(plan);
+  if (!in || !in->labels) return -1;
+  FND_OK(fusion_forward_impl(P, in, 1, true, st));
+  FND_OK(classifier_gemms_impl(P, 1, st));
+  HeadParams h = head_params(P, 1);
+  FND_OK((run_head<true, true, true>(P, h, st)));
+  FND_OK(run_gemm(P, P.dg_p1, 1, st));
+  FND_OK(run_gemm(P, P.dg_p0_fused, 1, st));
+  FND_OK(run_gemm(P, P.dg_f1, 1, st));
+  FND_OK(run_gemm(P, P.dg_f0, 1, st));
+  FND_OK(run_assemble_bwd(P, st));
+  FND_OK(run_gemm(P, P.dg_qkv, 1, st));
+  FND_OK(run_gemm(P, P.wg_all, 1, st));
+  return run_finalize(P, P.fin_all, P.wg_all.grid, P.total_slots, true, update_step, st);
+}
+
+int fnd_train_fwd_bwd(void* plan, const fnd_inputs* in, void* stream) { return train_fwd_bwd_impl(plan, in, 0, stream); }
+
+int fnd_train_step(void* plan, const fnd_inputs* in, void* stream) {
+  // finalize (last kernel of fwd_bwd) publishes norm, clip coefficient AND the step bookkeeping; AdamW follows.
+  FND_OK(train_fwd_bwd_impl(plan, in, 1, stream));
+  FND_PLAN(plan);
+  if (!P.m || !P.v) return -6;
+  AdamWParams a = adamw_params(P);
+  adamw_kernel<<<148 * 8, 256, 0, st>>>(a);
+  FND_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int fnd_eval_step(void* plan, const fnd_inputs* in, void* stream) {
+  FND_PLAN(plan);
+  if (!in) return -1;
+  FND_OK(fusion_forward_impl(P, in, 0, false, st));
+  FND_OK(fusion_head_impl(P, st));
+  FND_OK(classifier_gemms_impl(P, 0, st));
+  HeadParams h = head_params(P, 0);
+  if (in->labels) return run_head<true, true, false>(P, h, st);
+  return run_head<true, false, false>(P, h, st);
+}
+
+int fnd_launch_count(const void* plan, const char* entry) {
+  if (!plan || !entry) return -1;
+  const std::string e(entry);
+  const int fusion_fwd = 6;   // prep, proj, qkv, assemble, f0, f1
+  if (e == "fusion_forward") return fusion_fwd + 1;
+  if (e == "classifier_forward") return 3;
+  if (e == "eval_step") return fusion_fwd + 1 + 2 + 1;
+  if (e == "train_fwd_bwd") return fusion_fwd + 2 + 1 + 4 + 1 + 1 + 1 + 1;
+  if (e == "clip_adamw_step") return 3;
+  if (e == "train_step") return fusion_fwd + 2 + 1 + 4 + 1 + 1 + 1 + 1 + 1;
+  return -2;
+}
+
+// ------------------------------- raw GEMM utility -------------------------------
 size_t fnd_gemm_scratch_bytes(int M, int N, int bn, int splits) {
   size_t b = align_up(sizeof(GemmProblem), 256);
-  b += 256;                                                              // error flag
+  b += 256;                                                                   // error flag
   b += align_up(sizeof(int) * ceil_div(M, kGemmBM) * ceil_div(N, bn), 256);   // split-K counters
   if (splits > 1) b += splitk_ws_floats(M, N, bn, splits) * sizeof(float);
   return b + 256;
@@ -43,8 +772,7 @@ int fnd_gemm_bf16(const void* a_hi, const void* a_lo, int a_pitch, int a_mn, con
   off += ctr_bytes;
   float* dws = reinterpret_cast<float*>(base + off);
 
-  EpiParams epi;
-  memset(&epi, 0, sizeof(epi));
+  EpiParams epi = epi_zero();
   epi.out_f32 = c;
   epi.f32_pitch = c_pitch;
   Operand A{static_cast<const __nv_bfloat16*>(a_hi), static_cast<const __nv_bfloat16*>(a_lo), a_pitch, a_mn != 0};
@@ -53,9 +781,10 @@ int fnd_gemm_bf16(const void* a_hi, const void* a_lo, int a_pitch, int a_mn, con
   int r = fill_problem(hp, A, B, M, N, K, bn, splits, ncombo, kEvictNormal, kEvictNormal, dws, dctr, epi);
   if (r) return r;
   const int grid = finish_table(&hp, 1);
+  FND_CUDA_OK(init_gemm_attrs());
   FND_CUDA_OK(cudaMemsetAsync(derr, 0, 256 + ctr_bytes, st));
   FND_CUDA_OK(cudaMemcpyAsync(dtab, &hp, sizeof(hp), cudaMemcpyHostToDevice, st));
-  RunCtx ctx{derr, nullptr};
+  RunCtx ctx{derr, nullptr, 0};
   const int kind = (a_mn ? (b_mn ? 2 : 3) : (b_mn ? 1 : 0));
   FND_CUDA_OK(launch_gemm(kind, dtab, 1, grid, ctx, st));
   int herr = 0;

@@ -253,6 +253,14 @@ __device__ __forceinline__ void dropout_mult4(const DropCfg& d, uint32_t stream,
   m[3] = r.w >= d.thresh ? d.inv_keep : 0.f;
 }
 
+// Dropout salts: rng[2] advances once per fusion forward, rng[3] once per classifier forward, so the two modules
+// can be driven independently (module-level API) and a backward always regenerates its own forward's masks.
+// Streams 1,2 (fuse_mlp) belong to the fusion module; 3,4,5 (pre.*, tree logits) to the classifier.
+__device__ __forceinline__ uint32_t stream_key(const uint32_t* rng, int stream) {
+  const uint32_t salt = rng ? (stream >= 3 ? rng[3] : rng[2]) : 0u;
+  return static_cast<uint32_t>(stream) ^ (salt << 8);
+}
+
 // ------------------------------------------------------------------------------------------
 // Warp / block reductions
 // ------------------------------------------------------------------------------------------

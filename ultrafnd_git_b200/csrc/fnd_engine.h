@@ -1,0 +1,330 @@
+// fnd_engine.h — host side of the fusion hot path: parameter arena layout, per-batch plan (workspace carve-up,
+// TMA descriptors, GEMM problem tables, finalize job tables) and the launch sequences of every entry point.
+//
+// Data layout in HBM (all row-major):
+//   arena (fp32)  : [GEMM weights | bypass.weight | NODE gates | biases | thresholds | leaf tables | evidence MLPs | cold]
+//   shadows (bf16): same element offsets as the arena for the GEMM weights (+ a re-pitched pre.0.weight)
+//   workspace     : DevState | packed inputs Xbf [B,dsum] | P [B,5H] | Q [B,9H] | fused_cat [B,16H] | ... (see carve())
+#pragma once
+#include "../../include/fnd_b200.h"
+#include "fnd_gemm_host.h"
+#include "fnd_optim.cuh"
+#include <map>
+#include <string>
+#include <vector>
+
+namespace fnd {
+
+inline long long align64(long long x) { return (x + 63) / 64 * 64; }
+
+// -------------------------------------------------------------------------------------------------
+// Arena layout
+// -------------------------------------------------------------------------------------------------
+struct ParamEntry {
+  std::string name;
+  long long offset;
+  int ndim, rows, cols;
+  int hot;
+  long long numel() const { return ndim == 0 ? 1 : (ndim == 1 ? rows : static_cast<long long>(rows) * cols); }
+};
+
+struct ArenaLayout {
+  std::vector<ParamEntry> entries;
+  std::map<std::string, long long> off;
+  long long n_shadow = 0, n_hot = 0, n_total = 0;
+  long long rp_elems = 0;    // re-pitched pre.0.weight shadow (elements)
+  int rp_pitch = 0;
+  int evstride = 0;
+  long long at(const std::string& k) const { return off.at(k); }
+};
+
+inline int dims_ok(const fnd_dims& d) {
+  if (d.hidden != 512 && d.hidden != 1024) return 0;
+  const int ds[5] = {d.d_text, d.d_audio, d.d_visual, d.d_temporal, d.d_gnn};
+  for (int i = 0; i < 5; ++i)
+    if (ds[i] <= 0 || ds[i] % 64) return 0;
+  if (d.aux_dim != 0 && d.aux_dim != 2) return 0;
+  if (d.trees < 1 || d.depth < 1 || d.depth > 4 || d.trees * d.depth > kMaxTD) return 0;
+  return 1;
+}
+
+inline ArenaLayout make_layout(const fnd_dims& d) {
+  ArenaLayout L;
+  const int H = d.hidden;
+  long long cur = 0;
+  auto add = [&](const std::string& name, int ndim, int rows, int cols, int hot) {
+    ParamEntry e{name, cur, ndim, rows, cols, hot};
+    L.entries.push_back(e);
+    L.off[name] = cur;
+    cur += e.numel();
+  };
+  auto pad = [&]() { cur = align64(cur); };
+  // ---- GEMM weights (shadowed) ----
+  const char* pn[5] = {"text_proj", "audio_proj", "visual_proj", "temporal_proj", "gnn_proj"};
+  const int pd[5] = {d.d_text, d.d_audio, d.d_visual, d.d_temporal, d.d_gnn};
+  const int nmod = d.use_gnn ? 5 : 4;
+  for (int i = 0; i < nmod; ++i) { add(std::string("fusion.") + pn[i] + ".weight", 2, H, pd[i], 1); pad(); }
+  // q/k/v weights stacked by the projection's INPUT so one GEMM serves each input (Q layout, fnd_rows.cuh)
+  const char* qn[9] = {"attn_tv.q", "attn_ta.q", "attn_tv.k", "attn_tv.v", "attn_vu.q", "attn_ta.k", "attn_ta.v",
+                       "attn_vu.k", "attn_vu.v"};
+  for (int i = 0; i < 9; ++i) add(std::string("fusion.") + qn[i] + ".weight", 2, H, H, 1);
+  pad();
+  const int nslots = d.use_gnn ? 16 : 15;
+  add("fusion.fuse_mlp.0.weight", 2, 2 * H, nslots * H, 1); pad();
+  add("fusion.fuse_mlp.3.weight", 2, H, 2 * H, 1); pad();
+  add("clf.pre.0.weight", 2, H, H + d.aux_dim, 1); pad();
+  add("clf.pre.3.weight", 2, H, H, 1); pad();
+  L.n_shadow = cur;
+  // ---- everything else that trains ----
+  add("clf.bypass.weight", 2, 2, H, 1); pad();
+  for (int t = 0; t < d.trees; ++t)
+    for (int k = 0; k < d.depth; ++k) add("clf.node.trees." + std::to_string(t) + ".gates." + std::to_string(k), 1, H, 0, 1);
+  pad();
+  for (int i = 0; i < nmod; ++i) add(std::string("fusion.") + pn[i] + ".bias", 1, H, 0, 1);
+  pad();
+  for (int i = 0; i < 9; ++i) add(std::string("fusion.") + qn[i] + ".bias", 1, H, 0, 1);
+  pad();
+  add("fusion.fuse_mlp.0.bias", 1, 2 * H, 0, 1); pad();
+  add("fusion.fuse_mlp.3.bias", 1, H, 0, 1); pad();
+  add("clf.pre.0.bias", 1, H, 0, 1); pad();
+  add("clf.pre.3.bias", 1, H, 0, 1); pad();
+  add("clf.bypass.bias", 1, 2, 0, 1); pad();
+  for (int t = 0; t < d.trees; ++t)
+    for (int k = 0; k < d.depth; ++k) add("clf.node.trees." + std::to_string(t) + ".thresh." + std::to_string(k), 1, 1, 0, 1);
+  pad();
+  for (int t = 0; t < d.trees; ++t) add("clf.node.trees." + std::to_string(t) + ".leaf_logits", 2, 1 << d.depth, 2, 1);
+  pad();
+  const char* an[3] = {"attn_tv", "attn_ta", "attn_vu"};
+  L.evstride = static_cast<int>(align64(5 * H + 1));
+  for (int k = 0; k < 3; ++k) {
+    const std::string b = std::string("fusion.") + an[k] + ".evidence_proj.";
+    add(b + "0.weight", 2, H, 3, 1);
+    add(b + "0.bias", 1, H, 0, 1);
+    add(b + "2.weight", 2, 1, H, 1);
+    add(b + "2.bias", 1, 1, 0, 1);
+    pad();
+  }
+  L.n_hot = cur;
+  // ---- cold: present in state_dict / parameters() but never updated by the reference step ----
+  add("fusion.classifier.weight", 2, 2, H, 0); pad();
+  add("fusion.classifier.bias", 1, 2, 0, 0); pad();
+  add("clf.temperature", 0, 0, 0, 0);
+  for (int t = 0; t < d.trees; ++t) add("clf.node.trees." + std::to_string(t) + ".tau", 0, 0, 0, 0);
+  pad();
+  add("fusion.semantic.text_proj.0.weight", 2, 512, 512, 0);
+  add("fusion.semantic.text_proj.0.bias", 1, 512, 0, 0);
+  add("fusion.semantic.vision_proj.0.weight", 2, 512, 512, 0);
+  add("fusion.semantic.vision_proj.0.bias", 1, 512, 0, 0);
+  pad();
+  L.n_total = cur;
+  L.rp_pitch = d.aux_dim ? H + 8 : H;
+  L.rp_elems = d.aux_dim ? static_cast<long long>(H) * L.rp_pitch : 0;
+  return L;
+}
+
+// -------------------------------------------------------------------------------------------------
+// Plan
+// -------------------------------------------------------------------------------------------------
+struct WsBuf { long long off; long long bytes; };
+
+struct GemmTable {
+  std::vector<GemmProblem> host;
+  GemmProblem* dev = nullptr;
+  int kind = 0;     // 0 fwd (K,K), 1 dgrad (K,MN), 2 wgrad (MN,MN)
+  int grid = 0;
+};
+struct FinTable {
+  std::vector<FinJob> host;
+  FinJob* dev = nullptr;
+  int grid = 0;
+};
+
+struct Plan {
+  fnd_dims d;
+  ArenaLayout L;
+  int B = 0, mode = 0, ncombo = 1;
+  int H = 0, nmod = 0, nslots = 0, dsum = 0, TD = 0, leaves = 0;
+  int xoff[5] = {0, 0, 0, 0, 0}, xdim[5] = {0, 0, 0, 0, 0};
+  int n_asm_ctas = 0;
+  int splits_f0 = 1, splits_f1 = 1;
+  bool bound = false;
+  int last_training = 0;
+  // workspace
+  std::map<std::string, WsBuf> bufs;
+  std::vector<std::string> order;
+  long long ws_bytes = 0;
+  uint8_t* ws = nullptr;
+  float *params = nullptr, *grads = nullptr, *m = nullptr, *v = nullptr;
+  __nv_bfloat16 *sh_hi = nullptr, *sh_lo = nullptr;
+  // tables
+  GemmTable fwd_proj, fwd_qkv, fwd_f0, fwd_f1, fwd_p0, fwd_p1;
+  GemmTable dg_p1, dg_p0_fused, dg_p0_split, dg_f1, dg_f0, dg_qkv;
+  GemmTable wg_all, wg_clf, wg_fus;
+  FinTable fin_all, fin_clf, fin_fus;
+  int total_slots = 0;
+
+  template <class T> T* buf(const std::string& name) const {
+    auto it = bufs.find(name);
+    return it == bufs.end() ? nullptr : reinterpret_cast<T*>(ws + it->second.off);
+  }
+  DevState* state() const { return buf<DevState>("state"); }
+  float* W(const std::string& k) const { return params + L.at(k); }
+  float* G(const std::string& k) const { return grads + L.at(k); }
+  const __nv_bfloat16* Sh(const std::string& k) const { return sh_hi + L.at(k); }
+  const __nv_bfloat16* Sl(const std::string& k) const { return sh_lo ? sh_lo + L.at(k) : nullptr; }
+};
+
+inline void plan_add(Plan& P, const std::string& name, long long bytes) {
+  WsBuf b{P.ws_bytes, bytes};
+  P.bufs[name] = b;
+  P.order.push_back(name);
+  P.ws_bytes += (bytes + 255) / 256 * 256;
+}
+// bf16 activation plane(s): "<name>_hi" always, "<name>_lo" in fp32x3 mode
+inline void plan_add_bf(Plan& P, const std::string& name, long long elems) {
+  plan_add(P, name + "_hi", elems * 2);
+  if (P.ncombo == 3) plan_add(P, name + "_lo", elems * 2);
+}
+
+inline int pick_splits(int tiles, int kb_total, int target_ctas) {
+  int s = target_ctas / (tiles > 0 ? tiles : 1);
+  if (s < 1) s = 1;
+  const int max_s = kb_total / 4 > 0 ? kb_total / 4 : 1;   // at least 4 k-blocks per split
+  if (s > max_s) s = max_s;
+  if (s > 32) s = 32;
+  return s;
+}
+
+inline void carve(Plan& P) {
+  const long long B = P.B, H = P.H;
+  const int TD = P.TD;
+  plan_add(P, "state", sizeof(DevState));
+  plan_add(P, "aux", B * 2 * 4);
+  plan_add(P, "labels", B * 8);
+  plan_add_bf(P, "xbf", B * P.dsum);
+  plan_add(P, "P", B * 5 * H * 4);
+  plan_add_bf(P, "pbf", B * 5 * H);
+  plan_add(P, "Q", B * 9 * H * 4);
+  plan_add(P, "rowstat", B * 16 * 4);
+  plan_add_bf(P, "fused_cat", B * P.nslots * H);
+  plan_add(P, "z_f0", B * 2 * H * 4);
+  plan_add_bf(P, "h1", B * 2 * H);
+  plan_add(P, "z_f1", B * H * 4);
+  plan_add(P, "fused", B * H * 4);
+  plan_add_bf(P, "fusedbf", B * H);
+  plan_add(P, "fusion_logits", B * 2 * 4);
+  plan_add(P, "z_p0", B * H * 4);
+  plan_add_bf(P, "xp1", B * H);
+  plan_add(P, "z_p1", B * H * 4);
+  plan_add(P, "h", B * H * 4);
+  plan_add_bf(P, "hbf", B * H);
+  plan_add(P, "alpha", static_cast<long long>(kMaxTD) * H * 4);
+  plan_add(P, "svals", B * 32 * 4);
+  plan_add(P, "logits", B * 2 * 4);
+  plan_add(P, "probs", B * 2 * 4);
+  plan_add(P, "loss_row", B * 4);
+  plan_add(P, "dlogits", B * 2 * 4);
+  // backward
+  plan_add(P, "dF", B * kDFCols * 4);
+  plan_add_bf(P, "dFbf", B * kDFCols);
+  plan_add(P, "leafc", B * P.d.trees * P.leaves * 2 * 4);
+  plan_add(P, "dAraw", static_cast<long long>(64) * H * 4);
+  plan_add_bf(P, "dz_p1", B * H);
+  plan_add_bf(P, "dz_p0", B * H);
+  plan_add(P, "dfused", B * H * 4);
+  plan_add_bf(P, "dz_f1", B * H);
+  plan_add_bf(P, "dz_f0", B * 2 * H);
+  plan_add(P, "dcat", B * P.nslots * H * 4);
+  plan_add(P, "dPdirect", B * 5 * H * 4);
+  plan_add_bf(P, "dQ", B * 9 * H);
+  plan_add_bf(P, "dP", B * 5 * H);
+  P.n_asm_ctas = static_cast<int>(B < 296 ? B : 296);
+  plan_add(P, "ev_partial", static_cast<long long>(P.n_asm_ctas) * 3 * P.L.evstride * 4);
+  (void)TD;
+  // split-K workspaces / counters for the two skinny weight-streaming GEMMs (fuse_mlp.0, fuse_mlp.3)
+  const int tm = ceil_div(P.B, kGemmBM);
+  P.splits_f0 = pick_splits(tm * (2 * P.H / 64), P.nslots * P.H / kGemmBK, 296);
+  P.splits_f1 = pick_splits(tm * (P.H / 64), 2 * P.H / kGemmBK, 296);
+  if (P.splits_f0 > 1) {
+    plan_add(P, "splitws_f0", static_cast<long long>(splitk_ws_floats(P.B, 2 * P.H, 64, P.splits_f0)) * 4);
+    plan_add(P, "splitctr_f0", static_cast<long long>(tm) * (2 * P.H / 64) * 4);
+  }
+  if (P.splits_f1 > 1) {
+    plan_add(P, "splitws_f1", static_cast<long long>(splitk_ws_floats(P.B, P.H, 64, P.splits_f1)) * 4);
+    plan_add(P, "splitctr_f1", static_cast<long long>(tm) * (P.H / 64) * 4);
+  }
+  // per-CTA sum-of-squares slots (wgrad CTAs + finalize CTAs); generous upper bound, zero-initialised at bind
+  plan_add(P, "slots", 16384 * 4);
+  // device copies of the kernel tables
+  plan_add(P, "tables", 64 * static_cast<long long>(sizeof(GemmProblem)) + 96 * static_cast<long long>(sizeof(FinJob)) + 4096);
+}
+
+// ---- small helpers for table construction ----
+struct TableBuilder {
+  Plan& P;
+  explicit TableBuilder(Plan& p) : P(p) {}
+  Operand act(const std::string& name, long long col, int pitch, bool mn) const {
+    Operand o;
+    o.hi = P.buf<__nv_bfloat16>(name + "_hi") + col;
+    const __nv_bfloat16* lo = P.buf<__nv_bfloat16>(name + "_lo");
+    o.lo = lo ? lo + col : nullptr;
+    o.pitch = pitch;
+    o.mn_major = mn;
+    return o;
+  }
+  Operand weight(const std::string& key, int pitch, bool mn) const {
+    Operand o;
+    o.hi = P.Sh(key);
+    o.lo = P.Sl(key);
+    o.pitch = pitch;
+    o.mn_major = mn;
+    return o;
+  }
+  Operand weight_rp(bool mn) const {      // re-pitched pre.0.weight shadow
+    Operand o;
+    if (P.d.aux_dim) {
+      o.hi = P.sh_hi + P.L.n_shadow;
+      o.lo = P.sh_lo ? P.sh_lo + P.L.n_shadow : nullptr;
+      o.pitch = P.L.rp_pitch;
+    } else {
+      o.hi = P.Sh("clf.pre.0.weight");
+      o.lo = P.Sl("clf.pre.0.weight");
+      o.pitch = P.H;
+    }
+    o.mn_major = mn;
+    return o;
+  }
+};
+
+inline EpiParams epi_zero() {
+  EpiParams e;
+  memset(&e, 0, sizeof(e));
+  return e;
+}
+
+struct SplitAlloc { std::string ws_name, ctr_name; };
+
+inline int add_problem(Plan& P, GemmTable& T, const Operand& A, const Operand& B, int M, int N, int K, int bn, int splits,
+                       const EpiParams& epi, const std::string& tag) {
+  GemmProblem g;
+  float* ws = nullptr;
+  int* ctr = nullptr;
+  // clamp the split factor exactly as fill_problem will
+  const int kb_total = ceil_div(K, kGemmBK);
+  if (splits > kb_total) splits = kb_total;
+  if (splits > 1) {
+    const int kps = ceil_div(kb_total, splits);
+    splits = ceil_div(kb_total, kps);
+  }
+  if (splits > 1) {
+    ws = P.buf<float>("splitws_" + tag);
+    ctr = P.buf<int>("splitctr_" + tag);
+    if (!ws || !ctr) return -30;
+  }
+  int r = fill_problem(g, A, B, M, N, K, bn, splits, P.ncombo, kEvictNormal, kEvictNormal, ws, ctr, epi);
+  if (r) return r;
+  T.host.push_back(g);
+  return 0;
+}
+
+}  // namespace fnd

@@ -78,7 +78,8 @@ struct alignas(128) GemmProblem {
 
 struct RunCtx {
   int* err;                          // device error flag
-  const uint32_t* rng;               // [0] seed lo, [1] seed hi, [2] step (dropout counter salt)
+  const uint32_t* rng;               // [0] seed lo, [1] seed hi, [2] fusion salt, [3] classifier salt
+  int training;                      // 0: every dropout (forward masks and backward gates) is the identity
 };
 
 __device__ __forceinline__ void epi_named_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
@@ -242,9 +243,8 @@ fnd_gemm_kernel(const GemmProblem* __restrict__ probs, int nprob, RunCtx ctx) {
     if (proceed) {
       const uint32_t seed_lo = ctx.rng ? ctx.rng[0] : 0u;
       const uint32_t seed_hi = ctx.rng ? ctx.rng[1] : 0u;
-      const uint32_t rstep = ctx.rng ? ctx.rng[2] : 0u;
-      DropCfg dfw = make_dropcfg(E.drop_p, (static_cast<uint64_t>(seed_hi) << 32) | seed_lo);
-      DropCfg dbw = make_dropcfg(E.gate_p, (static_cast<uint64_t>(seed_hi) << 32) | seed_lo);
+      DropCfg dfw = make_dropcfg(ctx.training ? E.drop_p : 0.f, (static_cast<uint64_t>(seed_hi) << 32) | seed_lo);
+      DropCfg dbw = make_dropcfg(ctx.training ? E.gate_p : 0.f, (static_cast<uint64_t>(seed_hi) << 32) | seed_lo);
       float a0 = 0.f, a1 = 0.f;
       if (E.aux && row_ok) {
         a0 = E.aux[static_cast<size_t>(m) * 2];
@@ -310,12 +310,12 @@ fnd_gemm_kernel(const GemmProblem* __restrict__ probs, int nprob, RunCtx ctx) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
         }
-        if (E.drop_p > 0.f) {
+        if (dfw.p > 0.f) {
           const uint64_t e0 = static_cast<uint64_t>(m) * static_cast<uint64_t>(P.N) + n0;   // multiple of 4
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             float mm[4];
-            dropout_mult4(dfw, static_cast<uint32_t>(E.drop_stream) ^ (rstep << 8), (e0 + j) >> 2, mm);
+            dropout_mult4(dfw, stream_key(ctx.rng, E.drop_stream), (e0 + j) >> 2, mm);
             v[j] *= mm[0]; v[j + 1] *= mm[1]; v[j + 2] *= mm[2]; v[j + 3] *= mm[3];
           }
         }
@@ -325,8 +325,8 @@ fnd_gemm_kernel(const GemmProblem* __restrict__ probs, int nprob, RunCtx ctx) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             float mm[4] = {1.f, 1.f, 1.f, 1.f};
-            if (E.gate_p > 0.f)
-              dropout_mult4(dbw, static_cast<uint32_t>(E.gate_stream) ^ (rstep << 8), (e0 + j) >> 2, mm);
+            if (dbw.p > 0.f)
+              dropout_mult4(dbw, stream_key(ctx.rng, E.gate_stream), (e0 + j) >> 2, mm);
 #pragma unroll
             for (int q = 0; q < 4; ++q)
               if (full || n0 + j + q < P.N) v[j + q] *= gelu_erf_grad(z[j + q]) * mm[q];

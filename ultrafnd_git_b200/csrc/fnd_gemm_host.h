@@ -68,15 +68,21 @@ inline int finish_table(GemmProblem* probs, int n) {
   return c;
 }
 
+// Opt every GEMM variant into its dynamic shared-memory size (per device; called at bind time so that no
+// attribute call ever happens inside a stream capture).
+inline cudaError_t init_gemm_attrs() {
+  cudaError_t e;
+  e = cudaFuncSetAttribute(fnd_gemm_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(fnd_gemm_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(fnd_gemm_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(fnd_gemm_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes);
+}
+
 template <bool A_MN, bool B_MN>
 inline cudaError_t launch_gemm_t(const GemmProblem* dev_table, int nprob, int grid, RunCtx ctx, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(fnd_gemm_kernel<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         kGemmSmemBytes);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
   fnd_gemm_kernel<A_MN, B_MN><<<grid, kGemmThreads, kGemmSmemBytes, st>>>(dev_table, nprob, ctx);
   return cudaGetLastError();
 }

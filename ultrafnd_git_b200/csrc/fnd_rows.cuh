@@ -1,0 +1,829 @@
+// fnd_rows.cuh — the memory-bound "row" kernels of the fusion hot path (CUDA cores, 64/128-bit accesses).
+//
+// Everything between the tensor-core GEMMs lives here, one launch per stage instead of ~150 ATen ops:
+//   prep_kernel          input cast (+ optional gather from a device-resident feature cache) to bf16 hi/lo,
+//                        and softmax of the NODE feature gates (alpha)
+//   assemble_fwd_kernel  evidence scalars, sigmoid co-attention score, evidence gate MLP, co-attention mix,
+//                        8 pairwise interactions, written straight into the 16 slots of fused_cat (bf16)
+//   assemble_bwd_kernel  the matching backward (slot grads -> dP, dQ, evidence-MLP parameter partials)
+//   head_kernel          NODE oblivious-tree ensemble + bypass + temperature softmax + cross-entropy and
+//                        their backward, one warp per sample
+//   rowlinear kernels    the tiny Linear(H,2) heads (fusion.classifier)
+//   finalize_kernel      batch reductions for bias / threshold / leaf / evidence grads, gate softmax backward,
+//                        global gradient norm and the optimizer step bookkeeping
+//
+// Reference semantics followed (paths relative to the reference checkout):
+//   src/models/fusion/cross_modal_transformer.py:39-55,153-195   src/models/fusion/deep_truth_classifier.py:54-74,88-90,161-170
+//   src/training/forensic_trainer.py:287
+#pragma once
+#include "fnd_common.cuh"
+
+namespace fnd {
+
+constexpr int kRowThreads = 256;
+constexpr int kMaxTD = 32;        // trees * depth
+constexpr int kMaxLeaves = 16;    // depth <= 4
+constexpr int kDFCols = 64;       // padded width of the head's per-row gradient matrix dF = [dfeat | dlogits | 0]
+
+// Dropout stream ids (must match between forward and backward of the same layer)
+enum : int { kStreamFuse0 = 1, kStreamFuse1 = 2, kStreamPre0 = 3, kStreamPre1 = 4, kStreamTree = 5 };
+
+// Small device-resident state block shared by all kernels of a plan.
+struct DevState {
+  uint32_t rng[4];        // seed lo, seed hi, fusion dropout salt, classifier dropout salt
+  float lr, beta1, beta2, eps, weight_decay, max_norm;
+  float bc1, bc2;         // 1 - beta^t for the CURRENT step (written by finalize)
+  int step;               // optimizer steps taken
+  float loss;             // mean loss of the last step
+  float grad_norm;        // global L2 norm of the last step's gradients (before clipping)
+  float clip_coef;        // min(1, max_norm / (norm + 1e-6))
+  int err;                // device error flag
+  float loss_scale;       // d(loss)/d(row loss): 1 / global batch
+  unsigned int fin_counter;   // finalize kernel last-CTA election
+  int pad[3];
+};
+
+// ---------------------------------------------------------------------------------------------
+// block-wide sum of NV values (all threads receive the result)
+// ---------------------------------------------------------------------------------------------
+template <int NV>
+__device__ __forceinline__ void block_sum(float (&v)[NV], float* smem /* [8*NV] */) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) v[i] = warp_sum(v[i]);
+  __syncthreads();
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) smem[warp * NV + i] = v[i];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < kRowThreads / 32; ++w) s += smem[w * NV + i];
+    v[i] = s;
+  }
+}
+
+__device__ __forceinline__ void store_bf2(__nv_bfloat16* hi, __nv_bfloat16* lo, size_t idx, float a, float b) {
+  const uint32_t ph = pack_bf16x2(a, b);
+  *reinterpret_cast<uint32_t*>(hi + idx) = ph;
+  if (lo) {
+    const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&ph);
+    *reinterpret_cast<uint32_t*>(lo + idx) = pack_bf16x2(a - __low2float(h2), b - __high2float(h2));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// prep: cast inputs to bf16 hi/lo, gather aux/labels, and alpha = softmax(gates)
+// ---------------------------------------------------------------------------------------------
+struct PrepParams {
+  const float* x[5];          // per-modality inputs (text, audio, visual, temporal, gnn); row pitch xpitch[i]
+  int xpitch[5];
+  int xdim[5];
+  int xoff[5];                // column offset of modality i inside the packed [B, dsum] bf16 matrix
+  int nmod;                   // 4 or 5
+  int dsum;                   // packed row width
+  const long long* gather;    // optional row indices into x[*] (device-resident cache); null = identity
+  const float* aux_src;       // optional [*,2] source for aux (gathered alongside); null = skip
+  int aux_pitch;
+  const long long* label_src; // optional labels source
+  float* aux_dst;             // [B,2]
+  long long* label_dst;       // [B]
+  __nv_bfloat16* out_hi;
+  __nv_bfloat16* out_lo;      // null in bf16 mode
+  int B;
+  const float* gates;         // [TD, H] fp32 (master)
+  float* alpha;               // [TD, H]
+  int TD, H;
+  uint32_t* rng;              // DevState.rng; salts bumped by block 0 (a forward starts here)
+  int bump_fusion, bump_clf;
+};
+
+__global__ void __launch_bounds__(kRowThreads) prep_kernel(PrepParams p) {
+  __shared__ float red[8 * 1];
+  const int b = blockIdx.x;
+  if (b == 0 && threadIdx.x == 0 && p.rng) {
+    if (p.bump_fusion) p.rng[2] += 1u;
+    if (p.bump_clf) p.rng[3] += 1u;
+  }
+  if (b < p.B) {
+    const long long src = p.gather ? p.gather[b] : static_cast<long long>(b);
+    for (int m = 0; m < p.nmod; ++m) {
+      const float* xs = p.x[m] + static_cast<size_t>(src) * p.xpitch[m];
+      const size_t obase = static_cast<size_t>(b) * p.dsum + p.xoff[m];
+      for (int c = threadIdx.x * 4; c < p.xdim[m]; c += kRowThreads * 4) {
+        const float4 v = ldg_f4(xs + c);
+        store_bf2(p.out_hi, p.out_lo, obase + c, v.x, v.y);
+        store_bf2(p.out_hi, p.out_lo, obase + c + 2, v.z, v.w);
+      }
+    }
+    if (threadIdx.x == 0) {
+      if (p.aux_src && p.aux_dst) {
+        p.aux_dst[b * 2] = p.aux_src[static_cast<size_t>(src) * p.aux_pitch];
+        p.aux_dst[b * 2 + 1] = p.aux_src[static_cast<size_t>(src) * p.aux_pitch + 1];
+      }
+      if (p.label_src && p.label_dst) p.label_dst[b] = p.label_src[src];
+    }
+  } else {
+    // alpha row k = softmax(gates[k, :])   (deep_truth_classifier.py:64)
+    const int k = b - p.B;
+    if (k >= p.TD) return;
+    const float* g = p.gates + static_cast<size_t>(k) * p.H;
+    float mx = -INFINITY;
+    for (int j = threadIdx.x; j < p.H; j += kRowThreads) mx = fmaxf(mx, g[j]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    __shared__ float smx[8];
+    if ((threadIdx.x & 31) == 0) smx[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    mx = smx[0];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) mx = fmaxf(mx, smx[w]);
+    float s[1] = {0.f};
+    for (int j = threadIdx.x; j < p.H; j += kRowThreads) s[0] += expf(g[j] - mx);
+    block_sum<1>(s, red);
+    const float inv = 1.0f / s[0];
+    for (int j = threadIdx.x; j < p.H; j += kRowThreads) p.alpha[static_cast<size_t>(k) * p.H + j] = expf(g[j] - mx) * inv;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// assemble forward
+// ---------------------------------------------------------------------------------------------
+// P layout [B, 5H]: t | a | v | u | g.     Q layout [B, 9H] (grouped by the projection's input):
+//   0 q_tv | 1 q_ta | 2 k_tv | 3 v_tv | 4 q_vu | 5 k_ta | 6 v_ta | 7 k_vu | 8 v_vu
+// fused_cat slots [B, 16H]: t a v u | t+a t*a |t-a| t+v t*v |t-v| t+u v+u | tv* ta* vu* | g
+// rowstat [B,16]: 0 semantic_conflict 1 emotion 2 delay | 3..5 attn(tv,ta,vu) | 6..8 gate(tv,ta,vu)
+struct EvidenceParams {      // one ForensicCoAttention.evidence_proj (Linear(3,H) -> GELU -> Linear(H,1))
+  const float* w1;           // [H,3]
+  const float* b1;           // [H]
+  const float* w2;           // [H]
+  const float* b2;           // [1]
+};
+struct AssembleParams {
+  const float* P;            // [B,5H]
+  const float* Q;            // [B,9H]
+  EvidenceParams ev[3];      // tv, ta, vu
+  __nv_bfloat16* cat_hi;     // [B, nslots*H]
+  __nv_bfloat16* cat_lo;
+  float* rowstat;            // [B,16]
+  int B, H, use_gnn;
+};
+
+__device__ __forceinline__ float2 ld2(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
+
+template <int CH>   // CH = H / 512 chunks of 2 consecutive elements per thread
+__global__ void __launch_bounds__(kRowThreads) assemble_fwd_kernel(AssembleParams p) {
+  __shared__ float red[8 * 9];
+  const int H = p.H;
+  const int nslots = p.use_gnn ? 16 : 15;
+  for (int b = blockIdx.x; b < p.B; b += gridDim.x) {
+    const float* Pr = p.P + static_cast<size_t>(b) * 5 * H;
+    const float* Qr = p.Q + static_cast<size_t>(b) * 9 * H;
+    float2 t[CH], a[CH], v[CH], u[CH], q[9][CH];
+    float s[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      const int j = c * 512 + 2 * threadIdx.x;
+      t[c] = ld2(Pr + j); a[c] = ld2(Pr + H + j); v[c] = ld2(Pr + 2 * H + j); u[c] = ld2(Pr + 3 * H + j);
+#pragma unroll
+      for (int i = 0; i < 9; ++i) q[i][c] = ld2(Qr + i * H + j);
+      s[0] += t[c].x * t[c].x + t[c].y * t[c].y;
+      s[1] += v[c].x * v[c].x + v[c].y * v[c].y;
+      s[2] += u[c].x * u[c].x + u[c].y * u[c].y;
+      s[3] += t[c].x * v[c].x + t[c].y * v[c].y;
+      s[4] += t[c].x * u[c].x + t[c].y * u[c].y;
+      s[5] += fabsf(t[c].x) + fabsf(t[c].y);
+      s[6] += q[0][c].x * q[2][c].x + q[0][c].y * q[2][c].y;     // q_tv . k_tv
+      s[7] += q[1][c].x * q[5][c].x + q[1][c].y * q[5][c].y;     // q_ta . k_ta
+      s[8] += q[4][c].x * q[7][c].x + q[4][c].y * q[7][c].y;     // q_vu . k_vu
+    }
+    block_sum<9>(s, red);
+    // evidence scalars (no-grad in the reference, cross_modal_transformer.py:153-164)
+    const float nt = fmaxf(sqrtf(s[0]), 1e-12f), nv = fmaxf(sqrtf(s[1]), 1e-12f), nu = fmaxf(sqrtf(s[2]), 1e-12f);
+    const float ctv = fminf(fmaxf(s[3] / (nt * nv), -1.f), 1.f);
+    const float ctu = fminf(fmaxf(s[4] / (nt * nu), -1.f), 1.f);
+    const float sc = 1.0f - 0.5f * (ctv + 1.0f);
+    const float emo = tanhf(s[5] / static_cast<float>(H));
+    const float delay = 1.0f - 0.5f * (ctu + 1.0f);
+    const float inv_scale = rsqrtf(static_cast<float>(H));
+    const float att[3] = {sigmoidf_(s[6] * inv_scale), sigmoidf_(s[7] * inv_scale), sigmoidf_(s[8] * inv_scale)};
+    const float ev[3][3] = {{sc, emo, 0.f}, {emo, 0.f, 0.f}, {delay, 0.f, 0.f}};
+    // evidence gate MLP: sum_j w2[j] * gelu(w1[j,:].e + b1[j])
+    float gs[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const EvidenceParams& E = p.ev[k];
+      for (int j = threadIdx.x; j < H; j += kRowThreads) {
+        const float h1 = E.w1[j * 3] * ev[k][0] + E.w1[j * 3 + 1] * ev[k][1] + E.w1[j * 3 + 2] * ev[k][2] + E.b1[j];
+        gs[k] += E.w2[j] * gelu_erf(h1);
+      }
+    }
+    block_sum<3>(gs, red);
+    float gate[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) gate[k] = sigmoidf_(gs[k] + p.ev[k].b2[0]);
+    if (threadIdx.x == 0) {
+      float* rs = p.rowstat + static_cast<size_t>(b) * 16;
+      rs[0] = sc; rs[1] = emo; rs[2] = delay;
+      rs[3] = att[0]; rs[4] = att[1]; rs[5] = att[2];
+      rs[6] = gate[0]; rs[7] = gate[1]; rs[8] = gate[2];
+    }
+    const size_t row = static_cast<size_t>(b) * nslots * H;
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      const int j = c * 512 + 2 * threadIdx.x;
+      auto put = [&](int slot, float x, float y) { store_bf2(p.cat_hi, p.cat_lo, row + static_cast<size_t>(slot) * H + j, x, y); };
+      const float2 T = t[c], A = a[c], V = v[c], U = u[c];
+      put(0, T.x, T.y); put(1, A.x, A.y); put(2, V.x, V.y); put(3, U.x, U.y);
+      put(4, T.x + A.x, T.y + A.y); put(5, T.x * A.x, T.y * A.y); put(6, fabsf(T.x - A.x), fabsf(T.y - A.y));
+      put(7, T.x + V.x, T.y + V.y); put(8, T.x * V.x, T.y * V.y); put(9, fabsf(T.x - V.x), fabsf(T.y - V.y));
+      put(10, T.x + U.x, T.y + U.y); put(11, V.x + U.x, V.y + U.y);
+      // out = gate*attn*vv + (1-gate)*0.5*(x+y)    (cross_modal_transformer.py:52-54)
+      const float2 vtv = q[3][c], vta = q[6][c], vvu = q[8][c];
+      put(12, gate[0] * att[0] * vtv.x + (1.f - gate[0]) * 0.5f * (T.x + V.x),
+              gate[0] * att[0] * vtv.y + (1.f - gate[0]) * 0.5f * (T.y + V.y));
+      put(13, gate[1] * att[1] * vta.x + (1.f - gate[1]) * 0.5f * (T.x + A.x),
+              gate[1] * att[1] * vta.y + (1.f - gate[1]) * 0.5f * (T.y + A.y));
+      put(14, gate[2] * att[2] * vvu.x + (1.f - gate[2]) * 0.5f * (V.x + U.x),
+              gate[2] * att[2] * vvu.y + (1.f - gate[2]) * 0.5f * (V.y + U.y));
+      if (p.use_gnn) {
+        const float2 G = ld2(Pr + 4 * H + j);
+        put(15, G.x, G.y);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// assemble backward
+// ---------------------------------------------------------------------------------------------
+// evidence partial row layout (== arena layout of the evidence parameters), per block k:
+//   [k*evstride + 0 .. 3H) w1 grads | [3H..4H) b1 | [4H..5H) w2 | [5H] b2 | pad to evstride
+struct AssembleBwdParams {
+  const float* P;
+  const float* Q;
+  const float* dcat;         // [B, nslots*H] fp32
+  const float* rowstat;
+  EvidenceParams ev[3];
+  float* dPdirect;           // [B,5H] fp32: direct (non-GEMM) part of d{t,a,v,u}; g part final
+  __nv_bfloat16* dQ_hi;      // [B,9H]
+  __nv_bfloat16* dQ_lo;
+  __nv_bfloat16* dP_hi;      // [B,5H] bf16: only the g part is written here (t,a,v,u come from the qkv dgrad)
+  __nv_bfloat16* dP_lo;
+  float* ev_partial;         // [gridDim.x, 3*evstride]
+  int evstride;
+  int B, H, use_gnn;
+};
+
+template <int CH>
+__global__ void __launch_bounds__(kRowThreads) assemble_bwd_kernel(AssembleBwdParams p) {
+  __shared__ float red[8 * 6];
+  const int H = p.H;
+  const int nslots = p.use_gnn ? 16 : 15;
+  // per-thread evidence-MLP accumulators: hidden units j = threadIdx.x + m*256
+  constexpr int HU = CH * 2;
+  float aw1[3][HU][3], ab1[3][HU], aw2[3][HU], ab2[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    ab2[k] = 0.f;
+#pragma unroll
+    for (int m = 0; m < HU; ++m) {
+      ab1[k][m] = 0.f; aw2[k][m] = 0.f;
+      aw1[k][m][0] = 0.f; aw1[k][m][1] = 0.f; aw1[k][m][2] = 0.f;
+    }
+  }
+  for (int b = blockIdx.x; b < p.B; b += gridDim.x) {
+    const float* Pr = p.P + static_cast<size_t>(b) * 5 * H;
+    const float* Qr = p.Q + static_cast<size_t>(b) * 9 * H;
+    const float* Dr = p.dcat + static_cast<size_t>(b) * nslots * H;
+    const float* rs = p.rowstat + static_cast<size_t>(b) * 16;
+    const float sc = rs[0], emo = rs[1], delay = rs[2];
+    const float att[3] = {rs[3], rs[4], rs[5]};
+    const float gate[3] = {rs[6], rs[7], rs[8]};
+    float2 t[CH], a[CH], v[CH], u[CH], d12[CH], d13[CH], d14[CH];
+    float s[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // sum vv*dout (x3), sum dout*(att*vv - base) (x3)
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      const int j = c * 512 + 2 * threadIdx.x;
+      t[c] = ld2(Pr + j); a[c] = ld2(Pr + H + j); v[c] = ld2(Pr + 2 * H + j); u[c] = ld2(Pr + 3 * H + j);
+      d12[c] = ld2(Dr + 12 * H + j); d13[c] = ld2(Dr + 13 * H + j); d14[c] = ld2(Dr + 14 * H + j);
+      const float2 vtv = ld2(Qr + 3 * H + j), vta = ld2(Qr + 6 * H + j), vvu = ld2(Qr + 8 * H + j);
+      s[0] += vtv.x * d12[c].x + vtv.y * d12[c].y;
+      s[1] += vta.x * d13[c].x + vta.y * d13[c].y;
+      s[2] += vvu.x * d14[c].x + vvu.y * d14[c].y;
+      s[3] += d12[c].x * (att[0] * vtv.x - 0.5f * (t[c].x + v[c].x)) + d12[c].y * (att[0] * vtv.y - 0.5f * (t[c].y + v[c].y));
+      s[4] += d13[c].x * (att[1] * vta.x - 0.5f * (t[c].x + a[c].x)) + d13[c].y * (att[1] * vta.y - 0.5f * (t[c].y + a[c].y));
+      s[5] += d14[c].x * (att[2] * vvu.x - 0.5f * (v[c].x + u[c].x)) + d14[c].y * (att[2] * vvu.y - 0.5f * (v[c].y + u[c].y));
+    }
+    block_sum<6>(s, red);
+    const float inv_scale = rsqrtf(static_cast<float>(H));
+    float dscore[3], dpre[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      dscore[k] = gate[k] * s[k] * att[k] * (1.f - att[k]) * inv_scale;   // d(q.k) coefficient
+      dpre[k] = s[3 + k] * gate[k] * (1.f - gate[k]);                      // d(gate pre-activation)
+    }
+    // ---- evidence MLP parameter gradients (evidence itself is no-grad) ----
+    const float ev[3][3] = {{sc, emo, 0.f}, {emo, 0.f, 0.f}, {delay, 0.f, 0.f}};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const EvidenceParams& E = p.ev[k];
+#pragma unroll
+      for (int m = 0; m < HU; ++m) {
+        const int j = threadIdx.x + m * kRowThreads;
+        const float h1 = E.w1[j * 3] * ev[k][0] + E.w1[j * 3 + 1] * ev[k][1] + E.w1[j * 3 + 2] * ev[k][2] + E.b1[j];
+        aw2[k][m] += dpre[k] * gelu_erf(h1);
+        const float dh1 = dpre[k] * E.w2[j] * gelu_erf_grad(h1);
+        ab1[k][m] += dh1;
+        aw1[k][m][0] += dh1 * ev[k][0];
+        aw1[k][m][1] += dh1 * ev[k][1];
+        aw1[k][m][2] += dh1 * ev[k][2];
+      }
+      ab2[k] += dpre[k];
+    }
+    // ---- element-wise gradients ----
+    const size_t prow = static_cast<size_t>(b) * 5 * H;
+    const size_t qrow = static_cast<size_t>(b) * 9 * H;
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      const int j = c * 512 + 2 * threadIdx.x;
+      const float2 T = t[c], A = a[c], V = v[c], U = u[c];
+      auto D = [&](int slot) { return ld2(Dr + slot * H + j); };
+      const float2 d0 = D(0), d1 = D(1), d2 = D(2), d3 = D(3), d4 = D(4), d5 = D(5), d6 = D(6), d7 = D(7), d8 = D(8),
+                   d9 = D(9), d10 = D(10), d11 = D(11);
+      auto sgn = [](float x) { return x > 0.f ? 1.f : (x < 0.f ? -1.f : 0.f); };
+      const float b0 = (1.f - gate[0]) * 0.5f, b1 = (1.f - gate[1]) * 0.5f, b2 = (1.f - gate[2]) * 0.5f;
+      float2 dt, da, dv, du;
+      dt.x = d0.x + d4.x + A.x * d5.x + sgn(T.x - A.x) * d6.x + d7.x + V.x * d8.x + sgn(T.x - V.x) * d9.x + d10.x + b0 * d12[c].x + b1 * d13[c].x;
+      dt.y = d0.y + d4.y + A.y * d5.y + sgn(T.y - A.y) * d6.y + d7.y + V.y * d8.y + sgn(T.y - V.y) * d9.y + d10.y + b0 * d12[c].y + b1 * d13[c].y;
+      da.x = d1.x + d4.x + T.x * d5.x - sgn(T.x - A.x) * d6.x + b1 * d13[c].x;
+      da.y = d1.y + d4.y + T.y * d5.y - sgn(T.y - A.y) * d6.y + b1 * d13[c].y;
+      dv.x = d2.x + d7.x + T.x * d8.x - sgn(T.x - V.x) * d9.x + d11.x + b0 * d12[c].x + b2 * d14[c].x;
+      dv.y = d2.y + d7.y + T.y * d8.y - sgn(T.y - V.y) * d9.y + d11.y + b0 * d12[c].y + b2 * d14[c].y;
+      du.x = d3.x + d10.x + d11.x + b2 * d14[c].x;
+      du.y = d3.y + d10.y + d11.y + b2 * d14[c].y;
+      *reinterpret_cast<float2*>(p.dPdirect + prow + j) = dt;
+      *reinterpret_cast<float2*>(p.dPdirect + prow + H + j) = da;
+      *reinterpret_cast<float2*>(p.dPdirect + prow + 2 * H + j) = dv;
+      *reinterpret_cast<float2*>(p.dPdirect + prow + 3 * H + j) = du;
+      if (p.use_gnn) {
+        const float2 dg = D(15);
+        *reinterpret_cast<float2*>(p.dPdirect + prow + 4 * H + j) = dg;
+        store_bf2(p.dP_hi, p.dP_lo, prow + 4 * H + j, dg.x, dg.y);
+      }
+      // dQ: q/k get dscore * (the other), v gets gate*attn*dout
+      const float2 qtv = ld2(Qr + j), qta = ld2(Qr + H + j), ktv = ld2(Qr + 2 * H + j), qvu = ld2(Qr + 4 * H + j),
+                   kta = ld2(Qr + 5 * H + j), kvu = ld2(Qr + 7 * H + j);
+      auto putq = [&](int slot, float x, float y) { store_bf2(p.dQ_hi, p.dQ_lo, qrow + static_cast<size_t>(slot) * H + j, x, y); };
+      putq(0, dscore[0] * ktv.x, dscore[0] * ktv.y);
+      putq(1, dscore[1] * kta.x, dscore[1] * kta.y);
+      putq(2, dscore[0] * qtv.x, dscore[0] * qtv.y);
+      putq(3, gate[0] * att[0] * d12[c].x, gate[0] * att[0] * d12[c].y);
+      putq(4, dscore[2] * kvu.x, dscore[2] * kvu.y);
+      putq(5, dscore[1] * qta.x, dscore[1] * qta.y);
+      putq(6, gate[1] * att[1] * d13[c].x, gate[1] * att[1] * d13[c].y);
+      putq(7, dscore[2] * qvu.x, dscore[2] * qvu.y);
+      putq(8, gate[2] * att[2] * d14[c].x, gate[2] * att[2] * d14[c].y);
+    }
+    __syncthreads();
+  }
+  // ---- flush evidence partials for this CTA ----
+  float* out = p.ev_partial + static_cast<size_t>(blockIdx.x) * 3 * p.evstride;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    float* o = out + k * p.evstride;
+#pragma unroll
+    for (int m = 0; m < HU; ++m) {
+      const int j = threadIdx.x + m * kRowThreads;
+      o[j * 3] = aw1[k][m][0]; o[j * 3 + 1] = aw1[k][m][1]; o[j * 3 + 2] = aw1[k][m][2];
+      o[3 * H + j] = ab1[k][m];
+      o[4 * H + j] = aw2[k][m];
+    }
+    if (threadIdx.x == 0) o[5 * H] = ab2[k];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// NODE head + bypass + temperature softmax + cross-entropy, forward and backward. One warp per row.
+// ---------------------------------------------------------------------------------------------
+struct HeadParams {
+  const float* h;            // [B,H] fp32 (output of pre.3 + GELU + dropout)
+  const float* alpha;        // [TD,H]
+  const float* thresh;       // [TD]
+  const float* leaf;         // [T, L, 2]
+  const float* wb;           // [2,H] bypass weight
+  const float* bb;           // [2]
+  const float* temperature;  // scalar parameter (clamped to [0.5, 5])
+  const long long* labels;   // [B] (CE)
+  const float* dlogits_in;   // [B,2] external dlogits (split API backward); null when CE computes them
+  float tau, tree_drop_p;
+  int training;
+  float* logits;             // [B,2]
+  float* probs;              // [B,2]
+  float* svals;              // [B,32] saved sigmoid outputs
+  float* loss_row;           // [B]
+  float* dlogits_out;        // [B,2] (CE)
+  // backward outputs
+  float* dF;                 // [B,64] fp32: dfeat[0..TD) | dlogits[TD..TD+2) | 0
+  __nv_bfloat16* dF_hi;      // [B,64]
+  __nv_bfloat16* dF_lo;
+  float* leafc;              // [B, T*L*2] per-row leaf-table contributions
+  const float* z_pre1;       // [B,H] pre-activation of pre.3 (for the GELU/dropout backward)
+  float pre_drop_p;
+  __nv_bfloat16* dz_hi;      // [B,H] gradient w.r.t. pre.3's pre-activation
+  __nv_bfloat16* dz_lo;
+  const DevState* state;
+  int B, H, T, D;
+};
+
+template <bool FWD, bool CE, bool BWD, int NF4>   // NF4 = H/128 float4 per lane
+__global__ void __launch_bounds__(256) head_kernel(HeadParams p) {
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int b = blockIdx.x * 8 + warp;
+  if (b >= p.B) return;
+  const int H = p.H, T = p.T, D = p.D, TD = T * D, L = 1 << D;
+  const DropCfg dtree = make_dropcfg(p.training ? p.tree_drop_p : 0.f,
+                                     (static_cast<uint64_t>(p.state->rng[1]) << 32) | p.state->rng[0]);
+  float sv[kMaxTD];
+  float lg[2];
+  if (FWD) {
+    float4 hv[NF4];
+#pragma unroll
+    for (int i = 0; i < NF4; ++i) hv[i] = ldg_f4(p.h + static_cast<size_t>(b) * H + i * 128 + lane * 4);
+    float byp[2];
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      float acc = 0.f;
+#pragma unroll
+      for (int i = 0; i < NF4; ++i) {
+        const float4 w = ldg_f4(p.wb + static_cast<size_t>(c) * H + i * 128 + lane * 4);
+        acc += hv[i].x * w.x + hv[i].y * w.y + hv[i].z * w.z + hv[i].w * w.w;
+      }
+      byp[c] = warp_sum(acc) + p.bb[c];
+    }
+    for (int k = 0; k < TD; ++k) {
+      float acc = 0.f;
+#pragma unroll
+      for (int i = 0; i < NF4; ++i) {
+        const float4 w = ldg_f4(p.alpha + static_cast<size_t>(k) * H + i * 128 + lane * 4);
+        acc += hv[i].x * w.x + hv[i].y * w.y + hv[i].z * w.z + hv[i].w * w.w;
+      }
+      const float feat = warp_sum(acc);
+      sv[k] = sigmoidf_(p.tau * (feat - p.thresh[k]));
+    }
+    if (p.svals && lane < TD) {
+      // every lane holds all sv[] (warp_sum broadcasts); lane k stores element k
+      float mine = 0.f;
+      for (int k = 0; k < TD; ++k) mine = (lane == k) ? sv[k] : mine;
+      p.svals[static_cast<size_t>(b) * 32 + lane] = mine;
+    }
+    // tree logits (all lanes compute redundantly: 6 trees x 16 leaves)
+    float node[2] = {0.f, 0.f};
+    for (int i = 0; i < T; ++i) {
+      float tl0 = 0.f, tl1 = 0.f;
+      for (int leafi = 0; leafi < L; ++leafi) {
+        float pr = 1.f;
+        for (int d = 0; d < D; ++d) pr *= ((leafi >> d) & 1) ? sv[i * D + d] : (1.f - sv[i * D + d]);
+        tl0 += pr * p.leaf[(i * L + leafi) * 2];
+        tl1 += pr * p.leaf[(i * L + leafi) * 2 + 1];
+      }
+      float m0 = 1.f, m1 = 1.f;
+      if (dtree.p > 0.f) {
+        // element index of tree logit (b, i, c) is b*T*2 + i*2 + c; 2 per tree -> one philox word pair
+        const uint64_t e = static_cast<uint64_t>(b) * T * 2 + i * 2;
+        float mm[4];
+        dropout_mult4(dtree, stream_key(p.state->rng, kStreamTree), e >> 2, mm);
+        m0 = mm[e & 3]; m1 = mm[(e & 3) + 1];
+      }
+      node[0] += tl0 * m0; node[1] += tl1 * m1;
+    }
+    lg[0] = node[0] / static_cast<float>(T) + byp[0];
+    lg[1] = node[1] / static_cast<float>(T) + byp[1];
+    if (lane == 0) {
+      p.logits[b * 2] = lg[0]; p.logits[b * 2 + 1] = lg[1];
+      const float tc = fminf(fmaxf(p.temperature[0], 0.5f), 5.0f);
+      const float a0 = lg[0] / tc, a1 = lg[1] / tc, mx = fmaxf(a0, a1);
+      const float e0 = expf(a0 - mx), e1 = expf(a1 - mx);
+      p.probs[b * 2] = e0 / (e0 + e1); p.probs[b * 2 + 1] = e1 / (e0 + e1);
+    }
+  } else {
+    for (int k = 0; k < TD; ++k) sv[k] = p.svals[static_cast<size_t>(b) * 32 + k];
+    lg[0] = p.logits[b * 2]; lg[1] = p.logits[b * 2 + 1];
+  }
+  float dl[2] = {0.f, 0.f};
+  if (CE) {
+    // F.cross_entropy, mean reduction (forensic_trainer.py:287)
+    const int y = static_cast<int>(p.labels[b]);
+    const float mx = fmaxf(lg[0], lg[1]);
+    const float e0 = expf(lg[0] - mx), e1 = expf(lg[1] - mx), se = e0 + e1;
+    const float loss = logf(se) + mx - lg[y];
+    const float sc = p.state->loss_scale;
+    dl[0] = (e0 / se - (y == 0 ? 1.f : 0.f)) * sc;
+    dl[1] = (e1 / se - (y == 1 ? 1.f : 0.f)) * sc;
+    if (lane == 0) {
+      p.loss_row[b] = loss;
+      if (p.dlogits_out) { p.dlogits_out[b * 2] = dl[0]; p.dlogits_out[b * 2 + 1] = dl[1]; }
+    }
+  } else if (BWD) {
+    dl[0] = p.dlogits_in[b * 2]; dl[1] = p.dlogits_in[b * 2 + 1];
+  }
+  if (BWD) {
+    float dfeat[kMaxTD];
+    for (int i = 0; i < T; ++i) {
+      float m0 = 1.f, m1 = 1.f;
+      if (dtree.p > 0.f) {
+        const uint64_t e = static_cast<uint64_t>(b) * T * 2 + i * 2;
+        float mm[4];
+        dropout_mult4(dtree, stream_key(p.state->rng, kStreamTree), e >> 2, mm);
+        m0 = mm[e & 3]; m1 = mm[(e & 3) + 1];
+      }
+      const float dt0 = dl[0] * m0 / static_cast<float>(T), dt1 = dl[1] * m1 / static_cast<float>(T);
+      float ds[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int leafi = 0; leafi < L; ++leafi) {
+        float pr = 1.f;
+        for (int d = 0; d < D; ++d) pr *= ((leafi >> d) & 1) ? sv[i * D + d] : (1.f - sv[i * D + d]);
+        const float l0 = p.leaf[(i * L + leafi) * 2], l1 = p.leaf[(i * L + leafi) * 2 + 1];
+        if (lane == 0) {
+          p.leafc[static_cast<size_t>(b) * T * L * 2 + (i * L + leafi) * 2] = pr * dt0;
+          p.leafc[static_cast<size_t>(b) * T * L * 2 + (i * L + leafi) * 2 + 1] = pr * dt1;
+        }
+        const float dpr = l0 * dt0 + l1 * dt1;
+        for (int d = 0; d < D; ++d) {
+          float others = 1.f;
+          for (int d2 = 0; d2 < D; ++d2)
+            if (d2 != d) others *= ((leafi >> d2) & 1) ? sv[i * D + d2] : (1.f - sv[i * D + d2]);
+          ds[d] += dpr * (((leafi >> d) & 1) ? others : -others);
+        }
+      }
+      for (int d = 0; d < D; ++d) {
+        const float s = sv[i * D + d];
+        dfeat[i * D + d] = ds[d] * p.tau * s * (1.f - s);
+      }
+    }
+    // dF row: lanes write 2 columns each
+    {
+      float c0 = 0.f, c1 = 0.f;
+      for (int k = 0; k < TD; ++k) {
+        c0 = (2 * lane == k) ? dfeat[k] : c0;
+        c1 = (2 * lane + 1 == k) ? dfeat[k] : c1;
+      }
+      if (2 * lane == TD) c0 = dl[0];
+      if (2 * lane + 1 == TD) c1 = dl[0];
+      if (2 * lane == TD + 1) c0 = dl[1];
+      if (2 * lane + 1 == TD + 1) c1 = dl[1];
+      *reinterpret_cast<float2*>(p.dF + static_cast<size_t>(b) * kDFCols + 2 * lane) = make_float2(c0, c1);
+      store_bf2(p.dF_hi, p.dF_lo, static_cast<size_t>(b) * kDFCols + 2 * lane, c0, c1);
+    }
+    // dh = sum_k dfeat[k]*alpha[k,:] + sum_c dl[c]*wb[c,:]; then the GELU/dropout backward of pre.3
+    const DropCfg dpre = make_dropcfg(p.training ? p.pre_drop_p : 0.f,
+                                      (static_cast<uint64_t>(p.state->rng[1]) << 32) | p.state->rng[0]);
+#pragma unroll
+    for (int i = 0; i < NF4; ++i) {
+      const int j = i * 128 + lane * 4;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int k = 0; k < TD; ++k) {
+        const float4 w = ldg_f4(p.alpha + static_cast<size_t>(k) * H + j);
+        acc.x += dfeat[k] * w.x; acc.y += dfeat[k] * w.y; acc.z += dfeat[k] * w.z; acc.w += dfeat[k] * w.w;
+      }
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const float4 w = ldg_f4(p.wb + static_cast<size_t>(c) * H + j);
+        acc.x += dl[c] * w.x; acc.y += dl[c] * w.y; acc.z += dl[c] * w.z; acc.w += dl[c] * w.w;
+      }
+      const float4 z = ldg_f4(p.z_pre1 + static_cast<size_t>(b) * H + j);
+      float mm[4] = {1.f, 1.f, 1.f, 1.f};
+      if (dpre.p > 0.f)
+        dropout_mult4(dpre, stream_key(p.state->rng, kStreamPre1), (static_cast<uint64_t>(b) * H + j) >> 2, mm);
+      acc.x *= gelu_erf_grad(z.x) * mm[0]; acc.y *= gelu_erf_grad(z.y) * mm[1];
+      acc.z *= gelu_erf_grad(z.z) * mm[2]; acc.w *= gelu_erf_grad(z.w) * mm[3];
+      store_bf2(p.dz_hi, p.dz_lo, static_cast<size_t>(b) * H + j, acc.x, acc.y);
+      store_bf2(p.dz_hi, p.dz_lo, static_cast<size_t>(b) * H + j + 2, acc.z, acc.w);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Tiny Linear(H, 2): y = x W^T + b, one warp per row (fusion.classifier, cross_modal_transformer.py:130,198)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) rowlinear2_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                             const float* __restrict__ bias, float* __restrict__ y,
+                                                             int B, int H) {
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (b >= B) return;
+  float a0 = 0.f, a1 = 0.f;
+  for (int j = lane * 4; j < H; j += 128) {
+    const float4 xv = ldg_f4(x + static_cast<size_t>(b) * H + j);
+    const float4 w0 = ldg_f4(w + j), w1 = ldg_f4(w + H + j);
+    a0 += xv.x * w0.x + xv.y * w0.y + xv.z * w0.z + xv.w * w0.w;
+    a1 += xv.x * w1.x + xv.y * w1.y + xv.z * w1.z + xv.w * w1.w;
+  }
+  a0 = warp_sum(a0); a1 = warp_sum(a1);
+  if (lane == 0) { y[b * 2] = a0 + bias[0]; y[b * 2 + 1] = a1 + bias[1]; }
+}
+
+// dx[b,:] (+)= dy[b,0]*w[0,:] + dy[b,1]*w[1,:]
+__global__ void __launch_bounds__(256) rowlinear2_dgrad_kernel(const float* __restrict__ dy, const float* __restrict__ w,
+                                                               float* __restrict__ dx, int B, int H, int accumulate) {
+  const int b = blockIdx.x;
+  if (b >= B) return;
+  const float d0 = dy[b * 2], d1 = dy[b * 2 + 1];
+  for (int j = threadIdx.x; j < H; j += blockDim.x) {
+    const float v = d0 * w[j] + d1 * w[H + j];
+    float* o = dx + static_cast<size_t>(b) * H + j;
+    *o = accumulate ? (*o + v) : v;
+  }
+}
+
+// dz = dy * gelu'(z) * dropout_mask  ->  bf16 hi/lo     (entry gate of a split-API backward)
+struct GateParams {
+  const float* dy; const float* z;
+  __nv_bfloat16* out_hi; __nv_bfloat16* out_lo;
+  float drop_p; int stream; int training;
+  const DevState* state;
+  size_t n;       // elements, multiple of 4
+};
+__global__ void __launch_bounds__(256) gate_kernel(GateParams p) {
+  const DropCfg dc = make_dropcfg(p.training ? p.drop_p : 0.f,
+                                  (static_cast<uint64_t>(p.state->rng[1]) << 32) | p.state->rng[0]);
+  for (size_t i = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 4; i < p.n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x * 4) {
+    const float4 d = ldg_f4(p.dy + i), z = ldg_f4(p.z + i);
+    float mm[4] = {1.f, 1.f, 1.f, 1.f};
+    if (dc.p > 0.f) dropout_mult4(dc, stream_key(p.state->rng, p.stream), i >> 2, mm);
+    store_bf2(p.out_hi, p.out_lo, i, d.x * gelu_erf_grad(z.x) * mm[0], d.y * gelu_erf_grad(z.y) * mm[1]);
+    store_bf2(p.out_hi, p.out_lo, i + 2, d.z * gelu_erf_grad(z.z) * mm[2], d.w * gelu_erf_grad(z.w) * mm[3]);
+  }
+}
+
+// Exports the dropout keep-multipliers the NEXT forward will draw for one stream (tests replay them in the CPU
+// oracle): the forward's prep kernel bumps the salt before any mask is generated, hence salt + 1 here.
+__global__ void dropout_mask_kernel(float* out, size_t n, float p, int stream, const DevState* state) {
+  const DropCfg dc = make_dropcfg(p, (static_cast<uint64_t>(state->rng[1]) << 32) | state->rng[0]);
+  const uint32_t salt = (stream >= 3 ? state->rng[3] : state->rng[2]) + 1u;
+  for (size_t i4 = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i4 * 4 < n;
+       i4 += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    float mm[4];
+    dropout_mult4(dc, static_cast<uint32_t>(stream) ^ (salt << 8), i4, mm);
+    for (int q = 0; q < 4; ++q)
+      if (i4 * 4 + q < n) out[i4 * 4 + q] = mm[q];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// finalize: batch reductions + gate softmax backward + gradient norm + step bookkeeping
+// ---------------------------------------------------------------------------------------------
+enum : int { kJobColsumF32 = 0, kJobColsumBF16 = 1, kJobColsumAux = 2, kJobSoftmaxBwd = 3 };
+struct FinJob {
+  int type;
+  int rows, cols;               // reduce over rows; cols outputs
+  int src_pitch;
+  const float* src_f32;
+  const __nv_bfloat16* src_hi;
+  const __nv_bfloat16* src_lo;
+  const float* aux;             // [rows,2]  (kJobColsumAux)   | alpha [cols_total] (kJobSoftmaxBwd)
+  float* dst;
+  int dst_pitch;                // kJobColsumAux: dst[n*dst_pitch + k]
+  float scale;
+  int cta_begin, cta_count;     // 64 columns per CTA (softmax-bwd: one row per CTA)
+  int want_norm;                // include outputs in the gradient norm
+};
+struct FinParams {
+  const FinJob* jobs;
+  int njobs;
+  float* slots;                 // [total_slots]: GEMM wgrad CTAs first, then this kernel's CTAs
+  int slot_base;                // index of this kernel's first slot
+  int total_slots;
+  const float* loss_row;        // [B] (may be null)
+  int B;
+  DevState* state;
+  int update_step;              // 1: advance optimizer step / rng salt and publish bias corrections
+};
+
+__global__ void __launch_bounds__(256) finalize_kernel(FinParams p) {
+  __shared__ float sm[4][64];
+  __shared__ float red[8];
+  __shared__ int is_last;
+  int ji = 0;
+  while (ji + 1 < p.njobs && static_cast<int>(blockIdx.x) >= p.jobs[ji + 1].cta_begin) ++ji;
+  const FinJob J = p.jobs[ji];
+  const int local = blockIdx.x - J.cta_begin;
+  float ss = 0.f;
+  if (J.type == kJobSoftmaxBwd) {
+    // dgate[j] = alpha[j] * (draw[j] - sum_j' alpha[j'] draw[j'])       (softmax backward of deep_truth_classifier.py:64)
+    const int k = local;
+    const float* al = J.aux + static_cast<size_t>(k) * J.cols;
+    const float* dr = J.src_f32 + static_cast<size_t>(k) * J.src_pitch;
+    float dot = 0.f;
+    for (int j = threadIdx.x; j < J.cols; j += 256) dot += al[j] * dr[j];
+    dot = warp_sum(dot);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = dot;
+    __syncthreads();
+    dot = 0.f;
+    for (int w = 0; w < 8; ++w) dot += red[w];
+    for (int j = threadIdx.x; j < J.cols; j += 256) {
+      const float g = al[j] * (dr[j] - dot) * J.scale;
+      J.dst[static_cast<size_t>(k) * J.dst_pitch + j] = g;
+      ss += g * g;
+    }
+    __syncthreads();
+  } else {
+    const int cg = threadIdx.x & 63, rg = threadIdx.x >> 6;
+    const int col = local * 64 + cg;
+    float acc0 = 0.f, acc1 = 0.f;
+    if (col < J.cols) {
+      if (J.type == kJobColsumF32) {
+        for (int r = rg; r < J.rows; r += 4) acc0 += J.src_f32[static_cast<size_t>(r) * J.src_pitch + col];
+      } else if (J.type == kJobColsumBF16) {
+        for (int r = rg; r < J.rows; r += 4) {
+          const size_t i = static_cast<size_t>(r) * J.src_pitch + col;
+          float v = __bfloat162float(J.src_hi[i]);
+          if (J.src_lo) v += __bfloat162float(J.src_lo[i]);
+          acc0 += v;
+        }
+      } else {  // kJobColsumAux
+        for (int r = rg; r < J.rows; r += 4) {
+          const size_t i = static_cast<size_t>(r) * J.src_pitch + col;
+          float v = __bfloat162float(J.src_hi[i]);
+          if (J.src_lo) v += __bfloat162float(J.src_lo[i]);
+          acc0 += v * J.aux[r * 2];
+          acc1 += v * J.aux[r * 2 + 1];
+        }
+      }
+    }
+    sm[rg][cg] = acc0;
+    __syncthreads();
+    float t0 = (sm[0][cg] + sm[1][cg]) + (sm[2][cg] + sm[3][cg]);
+    __syncthreads();
+    float t1 = 0.f;
+    if (J.type == kJobColsumAux) {
+      sm[rg][cg] = acc1;
+      __syncthreads();
+      t1 = (sm[0][cg] + sm[1][cg]) + (sm[2][cg] + sm[3][cg]);
+    }
+    if (rg == 0 && col < J.cols) {
+      t0 *= J.scale; t1 *= J.scale;
+      if (J.type == kJobColsumAux) {
+        J.dst[static_cast<size_t>(col) * J.dst_pitch] = t0;
+        J.dst[static_cast<size_t>(col) * J.dst_pitch + 1] = t1;
+        ss = t0 * t0 + t1 * t1;
+      } else {
+        J.dst[col] = t0;
+        ss = t0 * t0;
+      }
+    }
+  }
+  // ---- this CTA's contribution to the gradient norm ----
+  ss = J.want_norm ? ss : 0.f;
+  ss = warp_sum(ss);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tot = 0.f;
+    for (int w = 0; w < 8; ++w) tot += red[w];
+    p.slots[p.slot_base + blockIdx.x] = tot;
+    __threadfence();
+    const unsigned int old = atomicAdd(&p.state->fin_counter, 1u);
+    is_last = (old == gridDim.x - 1) ? 1 : 0;
+  }
+  __syncthreads();
+  if (!is_last) return;
+  // ---- last CTA: global norm (fixed-order, double accumulation), mean loss, step bookkeeping ----
+  __threadfence();
+  double part = 0.0;
+  for (int i = threadIdx.x; i < p.total_slots; i += 256) part += static_cast<double>(__ldcg(p.slots + i));
+  double lsum = 0.0;
+  if (p.loss_row)
+    for (int i = threadIdx.x; i < p.B; i += 256) lsum += static_cast<double>(__ldcg(p.loss_row + i));
+  __shared__ double dred[2][256];
+  dred[0][threadIdx.x] = part; dred[1][threadIdx.x] = lsum;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      dred[0][threadIdx.x] += dred[0][threadIdx.x + o];
+      dred[1][threadIdx.x] += dred[1][threadIdx.x + o];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    DevState* S = p.state;
+    const float norm = static_cast<float>(sqrt(dred[0][0]));
+    S->grad_norm = norm;
+    S->clip_coef = (S->max_norm > 0.f) ? fminf(1.0f, S->max_norm / (norm + 1e-6f)) : 1.0f;
+    if (p.loss_row) S->loss = static_cast<float>(dred[1][0] * static_cast<double>(S->loss_scale));
+    if (p.update_step) {
+      S->step += 1;
+      S->bc1 = 1.0f - powf(S->beta1, static_cast<float>(S->step));
+      S->bc2 = 1.0f - powf(S->beta2, static_cast<float>(S->step));
+    }
+    S->fin_counter = 0u;
+  }
+}
+
+}  // namespace fnd

@@ -1,0 +1,373 @@
+"""Host-side engine: the flat parameter arena and the per-batch plans, bound to libfnd_b200.so through ctypes.
+
+PyTorch is plumbing here: it owns device memory (the arena, gradient / optimizer buffers, bf16 shadows and each
+plan's workspace are plain ``torch`` tensors whose ``data_ptr()`` is handed to the C ABI) and supplies the CUDA
+stream. All arithmetic of the hot path runs in the library's kernels. There is no CPU or eager fallback: any
+compute entry point raises when CUDA or the library is unavailable.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import FndDims, FndInputs, check
+
+MODE_BF16 = 0
+MODE_FP32X3 = 1
+
+LAYER_STREAMS = {"fuse0": 1, "fuse1": 2, "pre0": 3, "pre1": 4, "tree": 5}
+
+
+def default_precision() -> int:
+    """bf16 unless FND_PRECISION=fp32 (the bf16x3 tensor-core mode with fp32-equivalent results)."""
+    v = os.environ.get("FND_PRECISION", "bf16").lower()
+    if v in ("bf16", "0"):
+        return MODE_BF16
+    if v in ("fp32", "fp32x3", "1"):
+        return MODE_FP32X3
+    raise ValueError(f"FND_PRECISION={v!r}: expected 'bf16' or 'fp32'")
+
+
+@dataclass
+class Dims:
+    """Model dimensions (fusion.yaml + classifier.yaml of the reference; input widths are fixed by
+    cross_modal_transformer.py:96-99)."""
+    hidden: int = 512
+    d_text: int = 768
+    d_audio: int = 128
+    d_visual: int = 512
+    d_temporal: int = 256
+    d_gnn: int = 128
+    use_gnn: bool = True
+    aux_dim: int = 2
+    trees: int = 6
+    depth: int = 4
+    fusion_dropout: float = 0.1
+    clf_dropout: float = 0.1
+    tree_dropout: float = 0.3
+    node_tau: float = 10.0
+
+    def to_c(self) -> FndDims:
+        return FndDims(self.hidden, self.d_text, self.d_audio, self.d_visual, self.d_temporal, self.d_gnn,
+                       int(self.use_gnn), self.aux_dim, self.trees, self.depth, self.fusion_dropout,
+                       self.clf_dropout, self.tree_dropout, self.node_tau)
+
+    def validate(self) -> None:
+        if self.hidden not in (512, 1024):
+            raise NotImplementedError(f"hidden_dim={self.hidden}: the sm_100a kernels support 512 and 1024")
+        if self.aux_dim not in (0, 2):
+            raise NotImplementedError(f"aux_dim={self.aux_dim}: supported values are 0 and 2")
+        if self.depth > 4 or self.trees * self.depth > 32 or self.trees < 1 or self.depth < 1:
+            raise NotImplementedError("NODE head: depth <= 4 and trees*depth <= 32 are supported")
+        if self.d_gnn % 64:
+            raise NotImplementedError("gnn_dim must be a multiple of 64")
+
+
+@dataclass
+class ParamInfo:
+    name: str
+    offset: int
+    shape: Tuple[int, ...]
+    hot: bool
+
+    @property
+    def numel(self) -> int:
+        n = 1
+        for s in self.shape:
+            n *= s
+        return n
+
+
+def param_table(dims: Dims) -> List[ParamInfo]:
+    """The arena layout as the library defines it (fnd_param_info)."""
+    lib = _lib.load()
+    cd = dims.to_c()
+    n = lib.fnd_param_count(ctypes.byref(cd))
+    if n <= 0:
+        raise _lib.FndError(f"fnd_param_count rejected dims {dims}")
+    out = []
+    name = ctypes.create_string_buffer(128)
+    off = ctypes.c_longlong()
+    ndim, rows, cols, hot = ctypes.c_int(), ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    for i in range(n):
+        check(lib.fnd_param_info(ctypes.byref(cd), i, name, 128, ctypes.byref(off), ctypes.byref(ndim),
+                                 ctypes.byref(rows), ctypes.byref(cols), ctypes.byref(hot)), "fnd_param_info")
+        shape: Tuple[int, ...] = () if ndim.value == 0 else ((rows.value,) if ndim.value == 1 else (rows.value, cols.value))
+        out.append(ParamInfo(name.value.decode(), off.value, shape, bool(hot.value)))
+    return out
+
+
+class Plan:
+    """One (batch, mode) plan: workspace tensor + the library's plan handle."""
+
+    def __init__(self, engine: "Engine", batch: int):
+        self.engine = engine
+        self.batch = batch
+        self.lib = engine.lib
+        handle = ctypes.c_void_p()
+        cd = engine.dims.to_c()
+        check(self.lib.fnd_plan_create(ctypes.byref(cd), batch, engine.mode, ctypes.byref(handle)), "fnd_plan_create")
+        self.handle = handle
+        nbytes = self.lib.fnd_plan_workspace_bytes(handle)
+        self.workspace = torch.zeros(nbytes + 256, dtype=torch.uint8, device=engine.device)
+        self._ws_base = (self.workspace.data_ptr() + 255) // 256 * 256
+        self._ws_shift = self._ws_base - self.workspace.data_ptr()
+        self.forward_id = 0
+        self.bind()
+
+    def bind(self) -> None:
+        e = self.engine
+        check(self.lib.fnd_plan_bind(self.handle, self._ws_base, e.params.data_ptr(), e.grads.data_ptr(),
+                                     e.adam_m.data_ptr() if e.adam_m is not None else None,
+                                     e.adam_v.data_ptr() if e.adam_v is not None else None,
+                                     e.shadow_hi.data_ptr(), e.shadow_lo.data_ptr() if e.shadow_lo is not None else None,
+                                     e.stream_ptr()), "fnd_plan_bind")
+        h = e.hyper
+        check(self.lib.fnd_set_hyper(self.handle, h["lr"], h["beta1"], h["beta2"], h["eps"], h["weight_decay"],
+                                     h["max_norm"], e.stream_ptr()), "fnd_set_hyper")
+        check(self.lib.fnd_set_seed(self.handle, e.seed, e.stream_ptr()), "fnd_set_seed")
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                self.lib.fnd_plan_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    def buffer(self, name: str, dtype: torch.dtype, shape: Tuple[int, ...]) -> torch.Tensor:
+        """Zero-copy view of a named workspace buffer."""
+        off = self.lib.fnd_plan_buffer_offset(self.handle, name.encode())
+        if off < 0:
+            raise KeyError(name)
+        nbytes = self.lib.fnd_plan_buffer_bytes(self.handle, name.encode())
+        raw = self.workspace[self._ws_shift + off: self._ws_shift + off + nbytes]
+        t = raw.view(dtype)
+        n = 1
+        for s in shape:
+            n *= s
+        return t[:n].view(*shape)
+
+    def state(self) -> Dict[str, float]:
+        """Reads DevState (synchronises)."""
+        raw = self.buffer("state", torch.uint8, (88,)).cpu().numpy().tobytes()
+        import struct
+        rng = struct.unpack_from("<4I", raw, 0)
+        lr, b1, b2, eps, wd, mx, bc1, bc2 = struct.unpack_from("<8f", raw, 16)
+        step, = struct.unpack_from("<i", raw, 48)
+        loss, gnorm, coef = struct.unpack_from("<3f", raw, 52)
+        err, = struct.unpack_from("<i", raw, 64)
+        lscale, = struct.unpack_from("<f", raw, 68)
+        return {"rng": rng, "lr": lr, "beta1": b1, "beta2": b2, "eps": eps, "weight_decay": wd, "max_norm": mx,
+                "bc1": bc1, "bc2": bc2, "step": step, "loss": loss, "grad_norm": gnorm, "clip_coef": coef,
+                "err": err, "loss_scale": lscale}
+
+    def check_error(self) -> None:
+        check(self.lib.fnd_check_error(self.handle, self.engine.stream_ptr()), "device error flag")
+
+    def launch_count(self, entry: str) -> int:
+        return self.lib.fnd_launch_count(self.handle, entry.encode())
+
+    def dropout_masks(self) -> Dict[str, torch.Tensor]:
+        """Keep-multipliers the NEXT training forward will draw (test support: replayed in the CPU oracle)."""
+        d, B = self.engine.dims, self.batch
+        shapes = {"fuse0": (B, 2 * d.hidden), "fuse1": (B, d.hidden), "pre0": (B, d.hidden), "pre1": (B, d.hidden),
+                  "tree": (B, d.trees, 2)}
+        out = {}
+        for k, shp in shapes.items():
+            n = 1
+            for s in shp:
+                n *= s
+            t = torch.empty(n, dtype=torch.float32, device=self.engine.device)
+            check(self.lib.fnd_export_dropout_mask(self.handle, LAYER_STREAMS[k], t.data_ptr(), n,
+                                                   self.engine.stream_ptr()), "fnd_export_dropout_mask")
+            out[k] = t.view(*shp)
+        return out
+
+
+class Engine:
+    """Flat fp32 parameter arena (+ grads, Adam moments, bf16 operand shadows) and the plans that run on it."""
+
+    def __init__(self, dims: Dims, device: Optional[torch.device] = None, mode: Optional[int] = None):
+        dims.validate()
+        self.lib = _lib.load()
+        self.dims = dims
+        self.mode = default_precision() if mode is None else mode
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
+        self.device = torch.device(device)
+        self.table = param_table(dims)
+        self.index = {p.name: p for p in self.table}
+        cd = dims.to_c()
+        self.n_total = self.lib.fnd_arena_total_elems(ctypes.byref(cd))
+        self.n_hot = self.lib.fnd_arena_hot_elems(ctypes.byref(cd))
+        self.n_shadow = self.lib.fnd_arena_shadow_elems(ctypes.byref(cd))
+        self.n_shadow_buf = self.lib.fnd_arena_shadow_buffer_elems(ctypes.byref(cd))
+        self.params = torch.zeros(self.n_total, dtype=torch.float32, device=self.device)
+        self.grads: Optional[torch.Tensor] = None
+        self.shadow_hi: Optional[torch.Tensor] = None
+        self.shadow_lo: Optional[torch.Tensor] = None
+        self.adam_m: Optional[torch.Tensor] = None
+        self.adam_v: Optional[torch.Tensor] = None
+        self.plans: Dict[int, Plan] = {}
+        self.hyper = {"lr": 2e-4, "beta1": 0.9, "beta2": 0.999, "eps": 1e-8, "weight_decay": 1e-4, "max_norm": 5.0}
+        self.seed = 0x5EED5EED
+        self._shadow_version: Optional[int] = None
+        self.attached: list = []          # weakrefs to the nn.Modules whose parameters live in this arena
+        self._alloc_device_buffers()
+
+    def param_version(self) -> int:
+        """Sum of the autograd version counters of every attached parameter: changes whenever torch code (an
+        optimizer step, load_state_dict, ...) writes a parameter in place, which is when the bf16 shadows go stale."""
+        total = 0
+        for ref in self.attached:
+            m = ref()
+            if m is not None and getattr(m, "_engine", None) is self:
+                total += m._param_version()
+        return total
+
+    # ---------------------------------------------------------------- memory
+    def _alloc_device_buffers(self) -> None:
+        if self.device.type != "cuda":
+            return
+        self.grads = torch.zeros(self.n_hot, dtype=torch.float32, device=self.device)
+        self.shadow_hi = torch.zeros(self.n_shadow_buf, dtype=torch.bfloat16, device=self.device)
+        self.shadow_lo = torch.zeros(self.n_shadow_buf, dtype=torch.bfloat16, device=self.device) if self.mode == MODE_FP32X3 else None
+
+    def enable_optimizer(self) -> None:
+        """Allocate the Adam moments (needed by fnd_clip_adamw_step / fnd_train_step) and re-bind the plans."""
+        self.require_cuda()
+        if self.adam_m is None:
+            self.adam_m = torch.zeros(self.n_hot, dtype=torch.float32, device=self.device)
+            self.adam_v = torch.zeros(self.n_hot, dtype=torch.float32, device=self.device)
+            for p in self.plans.values():
+                p.bind()
+
+    def view(self, name: str) -> torch.Tensor:
+        p = self.index[name]
+        return self.params[p.offset: p.offset + p.numel].view(p.shape)
+
+    def grad_view(self, name: str, grads: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:
+        p = self.index[name]
+        if not p.hot:
+            return None
+        g = self.grads if grads is None else grads
+        return g[p.offset: p.offset + p.numel].view(p.shape)
+
+    def to(self, device: torch.device) -> None:
+        device = torch.device(device)
+        if device == self.device:
+            return
+        self.params = self.params.to(device)
+        self.device = device
+        self.plans.clear()
+        self.adam_m = self.adam_v = None
+        self.grads = self.shadow_hi = self.shadow_lo = None
+        self._shadow_version = None
+        self._alloc_device_buffers()
+
+    def set_mode(self, mode: int) -> None:
+        if mode != self.mode:
+            self.mode = mode
+            self.plans.clear()
+            self._shadow_version = None
+            self._alloc_device_buffers()
+            self.adam_m = self.adam_v = None
+
+    def set_dropout(self, fusion_p: Optional[float] = None, clf_p: Optional[float] = None, tree_p: Optional[float] = None) -> None:
+        changed = False
+        for attr, v in (("fusion_dropout", fusion_p), ("clf_dropout", clf_p), ("tree_dropout", tree_p)):
+            if v is not None and float(v) != getattr(self.dims, attr):
+                setattr(self.dims, attr, float(v))
+                changed = True
+        if changed:
+            self.plans.clear()
+
+    # ---------------------------------------------------------------- plumbing
+    def require_cuda(self) -> None:
+        if self.device.type != "cuda":
+            raise RuntimeError("ultrafnd_git_b200 runs on CUDA (sm_100a) only: no CPU fallback exists. "
+                               "Move the module to a CUDA device.")
+
+    def stream_ptr(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def plan(self, batch: int) -> Plan:
+        self.require_cuda()
+        p = self.plans.get(batch)
+        if p is None:
+            with torch.cuda.device(self.device):
+                p = Plan(self, batch)
+            self.plans[batch] = p
+        return p
+
+    def any_plan(self) -> Plan:
+        if not self.plans:
+            return self.plan(1)
+        return next(iter(self.plans.values()))
+
+    def refresh_shadows(self, version: Optional[int] = None) -> None:
+        """Rebuild the bf16 operand copies of the GEMM weights from the fp32 master arena."""
+        self.require_cuda()
+        check(self.lib.fnd_refresh_shadows(self.any_plan().handle, self.stream_ptr()), "fnd_refresh_shadows")
+        self._shadow_version = version
+
+    def ensure_shadows(self, version: int) -> None:
+        if self._shadow_version != version:
+            self.refresh_shadows(version)
+
+    def set_hyper(self, **kw) -> None:
+        self.hyper.update(kw)
+        for p in self.plans.values():
+            h = self.hyper
+            check(self.lib.fnd_set_hyper(p.handle, h["lr"], h["beta1"], h["beta2"], h["eps"], h["weight_decay"],
+                                         h["max_norm"], self.stream_ptr()), "fnd_set_hyper")
+
+    def set_lr(self, lr: float) -> None:
+        self.hyper["lr"] = lr
+        for p in self.plans.values():
+            check(self.lib.fnd_set_lr(p.handle, lr, self.stream_ptr()), "fnd_set_lr")
+
+    def set_seed(self, seed: int) -> None:
+        self.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+        for p in self.plans.values():
+            check(self.lib.fnd_set_seed(p.handle, self.seed, self.stream_ptr()), "fnd_set_seed")
+
+
+def make_inputs(feats: Dict[str, Optional[torch.Tensor]], aux: Optional[torch.Tensor] = None,
+                labels: Optional[torch.Tensor] = None, gather: Optional[torch.Tensor] = None,
+                use_gnn: bool = True) -> Tuple[FndInputs, list]:
+    """Pack device tensors into an ``fnd_inputs`` struct. Returns the struct and the tensors it points into (keep
+    them alive until the call has been enqueued)."""
+    keys = ["text_features", "audio_features", "visual_features", "temporal_features"] + (["gnn_feat"] if use_gnn else [])
+    inp = FndInputs()
+    keep = []
+    for i, k in enumerate(keys):
+        t = feats[k]
+        if t.dtype != torch.float32 or t.stride(-1) != 1:
+            t = t.to(torch.float32).contiguous()
+        if t.stride(0) % 4 or t.data_ptr() % 16:
+            t = t.contiguous().clone()
+        keep.append(t)
+        inp.x[i] = t.data_ptr()
+        inp.pitch[i] = t.stride(0) if t.shape[0] > 1 else t.shape[-1]
+    if aux is not None:
+        if aux.dtype != torch.float32 or aux.stride(-1) != 1:
+            aux = aux.to(torch.float32).contiguous()
+        keep.append(aux)
+        inp.aux = aux.data_ptr()
+        inp.aux_pitch = aux.stride(0) if aux.shape[0] > 1 else aux.shape[-1]
+    if labels is not None:
+        labels = labels.to(torch.int64).contiguous()
+        keep.append(labels)
+        inp.labels = labels.data_ptr()
+    if gather is not None:
+        gather = gather.to(torch.int64).contiguous()
+        keep.append(gather)
+        inp.gather = gather.data_ptr()
+    return inp, keep

@@ -1,0 +1,201 @@
+"""Fused trainer step: ForensicTrainer._forward_batch + F.cross_entropy + backward + clip_grad_norm_ + AdamW
+(src/training/forensic_trainer.py:238-298) as ONE stream-ordered launch sequence inside libfnd_b200.so, optionally
+replayed from a CUDA graph.
+
+``FusedStep`` owns static device input buffers (so a captured graph can be replayed while a copy stream refills
+them) or, alternatively, gathers each batch from a device-resident feature cache by row index.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, Optional
+
+import torch
+
+from . import engine as E
+from ._lib import FndInputs, check
+from .modules import CrossModalTransformer, DeepTruthClassifier, pair_modules
+
+FEATURE_KEYS = ("text_features", "audio_features", "visual_features", "temporal_features", "gnn_feat")
+
+
+class DeviceCache:
+    """The whole feature cache as one fp32 matrix on the device: columns [text | audio | visual | temporal | gnn | aux]
+    with a 16-byte-aligned row pitch, plus int64 labels. Replaces CachedTensorDataset + default collate +
+    ``gnn_Z[global_idx]`` + ``.to(device)`` per step (forensic_trainer.py:60-83,238-263)."""
+
+    def __init__(self, feats: Dict[str, torch.Tensor], aux: torch.Tensor, labels: torch.Tensor, device: torch.device):
+        widths = [feats[k].shape[1] for k in FEATURE_KEYS]
+        self.offsets = [0]
+        for w in widths:
+            self.offsets.append(self.offsets[-1] + w)
+        self.aux_off = self.offsets[-1]
+        total = self.aux_off + 2
+        self.pitch = (total + 3) // 4 * 4
+        n = labels.shape[0]
+        self.n = n
+        m = torch.zeros(n, self.pitch, dtype=torch.float32)
+        for k, o in zip(FEATURE_KEYS, self.offsets):
+            m[:, o:o + feats[k].shape[1]] = feats[k].to(torch.float32)
+        m[:, self.aux_off:self.aux_off + 2] = aux.to(torch.float32)
+        self.matrix = m.to(device)
+        self.labels = labels.to(torch.int64).to(device)
+        self.widths = widths
+
+    def inputs(self, gather: torch.Tensor) -> FndInputs:
+        inp = FndInputs()
+        base = self.matrix.data_ptr()
+        for i in range(5):
+            inp.x[i] = base + 4 * self.offsets[i]
+            inp.pitch[i] = self.pitch
+        inp.aux = base + 4 * self.aux_off
+        inp.aux_pitch = self.pitch
+        inp.labels = self.labels.data_ptr()
+        inp.gather = gather.data_ptr()
+        return inp
+
+
+class FusedStep:
+    """Runs fnd_train_step / fnd_eval_step for a (fusion, classifier) pair at a fixed batch size."""
+
+    def __init__(self, fusion: CrossModalTransformer, clf: DeepTruthClassifier, batch: int,
+                 precision: Optional[str] = None, use_graph: bool = True):
+        self.fusion, self.clf = fusion, clf
+        self.engine = pair_modules(fusion, clf, precision)
+        self.engine.require_cuda()
+        self.engine.enable_optimizer()
+        self.batch = batch
+        self.plan = self.engine.plan(batch)
+        self.use_graph = use_graph
+        self._graphs: Dict[str, torch.cuda.CUDAGraph] = {}
+        dev = self.engine.device
+        d = self.engine.dims
+        widths = [d.d_text, d.d_audio, d.d_visual, d.d_temporal, d.d_gnn]
+        # static staging buffers: [B, sum(widths)+2] fp32 (+ labels, gather indices)
+        self.in_off = [0]
+        for w in widths:
+            self.in_off.append(self.in_off[-1] + w)
+        self.aux_off = self.in_off[-1]
+        self.in_pitch = (self.aux_off + 2 + 3) // 4 * 4
+        self.static_in = torch.zeros(batch, self.in_pitch, dtype=torch.float32, device=dev)
+        self.static_labels = torch.zeros(batch, dtype=torch.int64, device=dev)
+        self.static_gather = torch.zeros(batch, dtype=torch.int64, device=dev)
+        self._inp_static = self._make_static_inputs()
+        self._inp_cache: Optional[FndInputs] = None
+        self._cache: Optional[DeviceCache] = None
+        self.engine.refresh_shadows(self.engine.param_version())
+
+    # ------------------------------------------------------------------ inputs
+    def _make_static_inputs(self) -> FndInputs:
+        inp = FndInputs()
+        base = self.static_in.data_ptr()
+        for i in range(5):
+            inp.x[i] = base + 4 * self.in_off[i]
+            inp.pitch[i] = self.in_pitch
+        inp.aux = base + 4 * self.aux_off
+        inp.aux_pitch = self.in_pitch
+        inp.labels = self.static_labels.data_ptr()
+        inp.gather = None
+        return inp
+
+    def host_staging(self) -> Dict[str, torch.Tensor]:
+        """Pinned host buffers with the static device buffers' layout (for the end-to-end path)."""
+        return {"inputs": torch.zeros(self.batch, self.in_pitch, dtype=torch.float32).pin_memory(),
+                "labels": torch.zeros(self.batch, dtype=torch.int64).pin_memory()}
+
+    def pack_host(self, batch: Dict[str, torch.Tensor], staging: Dict[str, torch.Tensor]) -> None:
+        m = staging["inputs"]
+        for k, o in zip(FEATURE_KEYS, self.in_off):
+            m[:, o:o + batch[k].shape[1]] = batch[k]
+        m[:, self.aux_off:self.aux_off + 2] = batch["aux"]
+        staging["labels"].copy_(batch["label"])
+
+    def load_batch(self, batch: Dict[str, torch.Tensor]) -> None:
+        """Copy one batch of (device or host) tensors into the static input buffers."""
+        for k, o in zip(FEATURE_KEYS, self.in_off):
+            self.static_in[:, o:o + batch[k].shape[1]].copy_(batch[k], non_blocking=True)
+        self.static_in[:, self.aux_off:self.aux_off + 2].copy_(batch["aux"], non_blocking=True)
+        if "label" in batch:
+            self.static_labels.copy_(batch["label"], non_blocking=True)
+
+    def upload(self, staging: Dict[str, torch.Tensor]) -> None:
+        self.static_in.copy_(staging["inputs"], non_blocking=True)
+        self.static_labels.copy_(staging["labels"], non_blocking=True)
+
+    def attach_cache(self, cache: DeviceCache) -> None:
+        self._cache = cache
+        self._inp_cache = cache.inputs(self.static_gather)
+        self._graphs.clear()
+
+    # ------------------------------------------------------------------ launches
+    def _run(self, entry: str, inp: FndInputs) -> None:
+        lib, h = self.engine.lib, self.plan.handle
+        fn = {"train_step": lib.fnd_train_step, "train_fwd_bwd": lib.fnd_train_fwd_bwd, "eval_step": lib.fnd_eval_step}[entry]
+        check(fn(h, ctypes.byref(inp), self.engine.stream_ptr()), "fnd_" + entry)
+
+    def _launch(self, entry: str, from_cache: bool) -> None:
+        inp = self._inp_cache if from_cache else self._inp_static
+        if inp is None:
+            raise RuntimeError("attach_cache() first")
+        if not self.use_graph:
+            self._run(entry, inp)
+            return
+        key = entry + ("/cache" if from_cache else "/static")
+        g = self._graphs.get(key)
+        if g is None:
+            # warm-up on a side stream (first launches set function attributes), then capture
+            s = torch.cuda.Stream(self.engine.device)
+            s.wait_stream(torch.cuda.current_stream(self.engine.device))
+            with torch.cuda.stream(s):
+                self._run("eval_step", inp)
+            torch.cuda.current_stream(self.engine.device).wait_stream(s)
+            torch.cuda.synchronize(self.engine.device)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._run(entry, inp)
+            self._graphs[key] = g
+        g.replay()
+
+    def train_step(self, from_cache: bool = False) -> None:
+        """One optimizer step on the batch currently in the static buffers (or gathered from the cache)."""
+        self._launch("train_step", from_cache)
+        self.plan.forward_id += 1
+
+    def train_fwd_bwd(self, from_cache: bool = False) -> None:
+        """Forward + loss + backward only (gradients left in the arena for an all-reduce)."""
+        self._launch("train_fwd_bwd", from_cache)
+        self.plan.forward_id += 1
+
+    def optimizer_step(self, norm_from_slots: bool = False) -> None:
+        check(self.engine.lib.fnd_clip_adamw_step(self.plan.handle, int(norm_from_slots), self.engine.stream_ptr()),
+              "fnd_clip_adamw_step")
+
+    def eval_step(self, from_cache: bool = False) -> None:
+        self._launch("eval_step", from_cache)
+        self.plan.forward_id += 1
+
+    # ------------------------------------------------------------------ results (zero-copy views of the workspace)
+    def logits(self) -> torch.Tensor:
+        return self.plan.buffer("logits", torch.float32, (self.batch, 2))
+
+    def probs(self) -> torch.Tensor:
+        return self.plan.buffer("probs", torch.float32, (self.batch, 2))
+
+    def fused(self) -> torch.Tensor:
+        return self.plan.buffer("fused", torch.float32, (self.batch, self.engine.dims.hidden))
+
+    def loss_rows(self) -> torch.Tensor:
+        return self.plan.buffer("loss_row", torch.float32, (self.batch,))
+
+    def forensic(self) -> Dict[str, torch.Tensor]:
+        rs = self.plan.buffer("rowstat", torch.float32, (self.batch, 16))
+        return {"semantic_conflict": rs[:, 0], "emotion_intensity": rs[:, 1], "temporal_delay": rs[:, 2]}
+
+    def loss_scalar_view(self) -> torch.Tensor:
+        """Device view of DevState.loss (mean loss of the last training step)."""
+        return self.plan.buffer("state", torch.float32, (22,))[13:14]
+
+    def mark_params_updated(self) -> None:
+        """The library's AdamW updates the arena (and the shadows) behind torch's back; keep the modules' shadow
+        bookkeeping consistent so a later module-level forward does not refresh needlessly."""
+        self.engine._shadow_version = self.engine.param_version()
