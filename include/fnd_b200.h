@@ -129,6 +129,11 @@ int fnd_train_fwd_bwd(void* plan, const fnd_inputs* in, void* stream);
 int fnd_train_step(void* plan, const fnd_inputs* in, void* stream);
 int fnd_eval_step(void* plan, const fnd_inputs* in, void* stream);
 
+/* Per-kernel timing for benchmarks: between begin and end every kernel launch of this plan is followed by a
+ * cudaEvent on `stream`; end synchronises and returns, per kernel name (64-byte slots in `names`), the summed
+ * milliseconds between consecutive events. Not capturable; do not use around graph replays. */
+int fnd_profile_begin(void* plan, void* stream);
+int fnd_profile_end(void* plan, void* stream, char* names, float* ms, int cap, int* count);
 /* Number of kernel launches one call of the named entry point issues ("train_step", "eval_step", ...). */
 int fnd_launch_count(const void* plan, const char* entry);
 /* Dropout keep-multipliers (0 or 1/(1-p)) that the NEXT training forward will use for a layer

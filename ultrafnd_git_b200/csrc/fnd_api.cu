@@ -279,8 +279,17 @@ static inline RunCtx make_ctx(const Plan& P, int training) {
   c.training = training;
   return c;
 }
-static int run_gemm(const Plan& P, const GemmTable& T, int training, cudaStream_t st) {
+static void mark(const Plan& Pc, const char* name, cudaStream_t st) {
+  Plan& P = const_cast<Plan&>(Pc);
+  if (!P.profiling) return;
+  cudaEvent_t ev;
+  if (cudaEventCreate(&ev) != cudaSuccess) return;
+  cudaEventRecord(ev, st);
+  P.marks.emplace_back(name, ev);
+}
+static int run_gemm(const Plan& P, const GemmTable& T, int training, cudaStream_t st, const char* name) {
   FND_CUDA_OK(launch_gemm(T.kind, T.dev, static_cast<int>(T.host.size()), T.grid, make_ctx(P, training), st));
+  mark(P, name, st);
   return 0;
 }
 
@@ -303,6 +312,7 @@ static int run_prep(Plan& P, const fnd_inputs* in, int training, bool bump_clf, 
   pp.rng = P.state()->rng; pp.bump_fusion = training ? 1 : 0; pp.bump_clf = (training && bump_clf) ? 1 : 0;
   prep_kernel<<<P.B + P.TD, kRowThreads, 0, st>>>(pp);
   FND_CUDA_OK(cudaGetLastError());
+  mark(P, "prep", st);
   return 0;
 }
 
@@ -327,6 +337,7 @@ static int run_assemble_fwd(Plan& P, cudaStream_t st) {
   if (P.H == 512) assemble_fwd_kernel<1><<<grid, kRowThreads, 0, st>>>(a);
   else assemble_fwd_kernel<2><<<grid, kRowThreads, 0, st>>>(a);
   FND_CUDA_OK(cudaGetLastError());
+  mark(P, "assemble_fwd", st);
   return 0;
 }
 
@@ -343,6 +354,7 @@ static int run_assemble_bwd(Plan& P, cudaStream_t st) {
   if (P.H == 512) assemble_bwd_kernel<1><<<P.n_asm_ctas, kRowThreads, 0, st>>>(a);
   else assemble_bwd_kernel<2><<<P.n_asm_ctas, kRowThreads, 0, st>>>(a);
   FND_CUDA_OK(cudaGetLastError());
+  mark(P, "assemble_bwd", st);
   return 0;
 }
 
@@ -370,6 +382,7 @@ static int run_head(const Plan& P, const HeadParams& h, cudaStream_t st) {
   if (P.H == 512) head_kernel<FWD, CE, BWD, 4><<<grid, 256, 0, st>>>(h);
   else head_kernel<FWD, CE, BWD, 8><<<grid, 256, 0, st>>>(h);
   FND_CUDA_OK(cudaGetLastError());
+  mark(P, "head", st);
   return 0;
 }
 
@@ -383,6 +396,7 @@ static int run_finalize(Plan& P, const FinTable& T, int slot_base, int total_slo
   f.state = P.state(); f.update_step = update_step;
   finalize_kernel<<<T.grid, 256, 0, st>>>(f);
   FND_CUDA_OK(cudaGetLastError());
+  mark(P, "finalize", st);
   return 0;
 }
 
@@ -405,11 +419,11 @@ static AdamWParams adamw_params(const Plan& P) {
 static int fusion_forward_impl(Plan& P, const fnd_inputs* in, int training, bool bump_clf, cudaStream_t st) {
   P.last_training = training;
   FND_OK(run_prep(P, in, training, bump_clf, st));
-  FND_OK(run_gemm(P, P.fwd_proj, training, st));
-  FND_OK(run_gemm(P, P.fwd_qkv, training, st));
+  FND_OK(run_gemm(P, P.fwd_proj, training, st, "gemm_proj"));
+  FND_OK(run_gemm(P, P.fwd_qkv, training, st, "gemm_qkv"));
   FND_OK(run_assemble_fwd(P, st));
-  FND_OK(run_gemm(P, P.fwd_f0, training, st));
-  FND_OK(run_gemm(P, P.fwd_f1, training, st));
+  FND_OK(run_gemm(P, P.fwd_f0, training, st, "gemm_fuse0"));
+  FND_OK(run_gemm(P, P.fwd_f1, training, st, "gemm_fuse1"));
   return 0;
 }
 static int fusion_head_impl(Plan& P, cudaStream_t st) {   // fusion.classifier: returned for API parity only
@@ -417,11 +431,12 @@ static int fusion_head_impl(Plan& P, cudaStream_t st) {   // fusion.classifier: 
                                                           P.W("fusion.classifier.bias"), P.buf<float>("fusion_logits"),
                                                           P.B, P.H);
   FND_CUDA_OK(cudaGetLastError());
+  mark(P, "fusion_head", st);
   return 0;
 }
 static int classifier_gemms_impl(Plan& P, int training, cudaStream_t st) {
-  FND_OK(run_gemm(P, P.fwd_p0, training, st));
-  FND_OK(run_gemm(P, P.fwd_p1, training, st));
+  FND_OK(run_gemm(P, P.fwd_p0, training, st, "gemm_pre0"));
+  FND_OK(run_gemm(P, P.fwd_p1, training, st, "gemm_pre1"));
   return 0;
 }
 
@@ -636,9 +651,9 @@ int fnd_classifier_backward(void* plan, const float* dlogits, void* stream) {
   HeadParams h = head_params(P, tr);
   h.dlogits_in = dlogits ? dlogits : P.buf<float>("dlogits");
   FND_OK((run_head<false, false, true>(P, h, st)));
-  FND_OK(run_gemm(P, P.dg_p1, tr, st));
-  FND_OK(run_gemm(P, P.dg_p0_split, tr, st));
-  FND_OK(run_gemm(P, P.wg_clf, tr, st));
+  FND_OK(run_gemm(P, P.dg_p1, tr, st, "dgrad_pre1"));
+  FND_OK(run_gemm(P, P.dg_p0_split, tr, st, "dgrad_pre0"));
+  FND_OK(run_gemm(P, P.wg_clf, tr, st, "wgrad_clf"));
   return run_finalize(P, P.fin_clf, kSlotScratch, 0, false, 0, st);
 }
 
@@ -662,11 +677,11 @@ int fnd_fusion_backward(void* plan, const float* dfused, const float* dfusion_lo
   g.n = static_cast<size_t>(P.B) * P.H;
   gate_kernel<<<ceil_div(static_cast<int>(g.n / 4), 256), 256, 0, st>>>(g);
   FND_CUDA_OK(cudaGetLastError());
-  FND_OK(run_gemm(P, P.dg_f1, tr, st));
-  FND_OK(run_gemm(P, P.dg_f0, tr, st));
+  FND_OK(run_gemm(P, P.dg_f1, tr, st, "dgrad_fuse1"));
+  FND_OK(run_gemm(P, P.dg_f0, tr, st, "dgrad_fuse0"));
   FND_OK(run_assemble_bwd(P, st));
-  FND_OK(run_gemm(P, P.dg_qkv, tr, st));
-  FND_OK(run_gemm(P, P.wg_fus, tr, st));
+  FND_OK(run_gemm(P, P.dg_qkv, tr, st, "dgrad_qkv"));
+  FND_OK(run_gemm(P, P.wg_fus, tr, st, "wgrad_fusion"));
   return run_finalize(P, P.fin_fus, kSlotScratch, 0, false, 0, st);
 }
 
@@ -681,13 +696,16 @@ int fnd_clip_adamw_step(void* plan, int norm_from_slots, void* stream) {
     FND_CUDA_OK(cudaGetLastError());
     norm_finish_kernel<<<1, 256, 0, st>>>(slots + kSlotSumsq, nb, P.state(), 1);
     FND_CUDA_OK(cudaGetLastError());
+    mark(P, "grad_norm", st);
   } else {
     step_kernel<<<1, 32, 0, st>>>(P.state());
     FND_CUDA_OK(cudaGetLastError());
+    mark(P, "step_bookkeeping", st);
   }
   AdamWParams a = adamw_params(P);
   adamw_kernel<<<148 * 8, 256, 0, st>>>(a);
   FND_CUDA_OK(cudaGetLastError());
+  mark(P, "adamw", st);
   return 0;
 }
 
@@ -699,13 +717,13 @@ static int train_fwd_bwd_impl(void* plan, const fnd_inputs* in, int update_step,
   FND_OK(classifier_gemms_impl(P, 1, st));
   HeadParams h = head_params(P, 1);
   FND_OK((run_head<true, true, true>(P, h, st)));
-  FND_OK(run_gemm(P, P.dg_p1, 1, st));
-  FND_OK(run_gemm(P, P.dg_p0_fused, 1, st));
-  FND_OK(run_gemm(P, P.dg_f1, 1, st));
-  FND_OK(run_gemm(P, P.dg_f0, 1, st));
+  FND_OK(run_gemm(P, P.dg_p1, 1, st, "dgrad_pre1"));
+  FND_OK(run_gemm(P, P.dg_p0_fused, 1, st, "dgrad_pre0"));
+  FND_OK(run_gemm(P, P.dg_f1, 1, st, "dgrad_fuse1"));
+  FND_OK(run_gemm(P, P.dg_f0, 1, st, "dgrad_fuse0"));
   FND_OK(run_assemble_bwd(P, st));
-  FND_OK(run_gemm(P, P.dg_qkv, 1, st));
-  FND_OK(run_gemm(P, P.wg_all, 1, st));
+  FND_OK(run_gemm(P, P.dg_qkv, 1, st, "dgrad_qkv"));
+  FND_OK(run_gemm(P, P.wg_all, 1, st, "wgrad_all"));
   return run_finalize(P, P.fin_all, P.wg_all.grid, P.total_slots, true, update_step, st);
 }
 
@@ -719,6 +737,7 @@ int fnd_train_step(void* plan, const fnd_inputs* in, void* stream) {
   AdamWParams a = adamw_params(P);
   adamw_kernel<<<148 * 8, 256, 0, st>>>(a);
   FND_CUDA_OK(cudaGetLastError());
+  mark(P, "adamw", st);
   return 0;
 }
 
@@ -731,6 +750,43 @@ int fnd_eval_step(void* plan, const fnd_inputs* in, void* stream) {
   HeadParams h = head_params(P, 0);
   if (in->labels) return run_head<true, true, false>(P, h, st);
   return run_head<true, false, false>(P, h, st);
+}
+
+int fnd_profile_begin(void* plan, void* stream) {
+  FND_PLAN(plan);
+  for (auto& m : P.marks) cudaEventDestroy(m.second);
+  P.marks.clear();
+  P.profiling = true;
+  mark(P, "begin", st);
+  return 0;
+}
+
+int fnd_profile_end(void* plan, void* stream, char* names, float* ms, int cap, int* count) {
+  FND_PLAN(plan);
+  if (!names || !ms || !count || cap < 1) return -1;
+  P.profiling = false;
+  FND_CUDA_OK(cudaStreamSynchronize(st));
+  // aggregate by name, in order of first appearance: ms[i] = total time attributed to kernel `names[i]`
+  int n = 0;
+  for (size_t i = 1; i < P.marks.size(); ++i) {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, P.marks[i - 1].second, P.marks[i].second) != cudaSuccess) t = 0.f;
+    int slot = -1;
+    for (int j = 0; j < n; ++j)
+      if (strncmp(names + 64 * j, P.marks[i].first, 63) == 0) { slot = j; break; }
+    if (slot < 0) {
+      if (n >= cap) continue;
+      slot = n++;
+      strncpy(names + 64 * slot, P.marks[i].first, 63);
+      names[64 * slot + 63] = 0;
+      ms[slot] = 0.f;
+    }
+    ms[slot] += t;
+  }
+  *count = n;
+  for (auto& m : P.marks) cudaEventDestroy(m.second);
+  P.marks.clear();
+  return 0;
 }
 
 int fnd_launch_count(const void* plan, const char* entry) {

@@ -162,6 +162,9 @@ struct Plan {
   GemmTable wg_all, wg_clf, wg_fus;
   FinTable fin_all, fin_clf, fin_fus;
   int total_slots = 0;
+  // optional per-kernel timing (bench/profiling only): an event is recorded after every launch
+  bool profiling = false;
+  std::vector<std::pair<const char*, cudaEvent_t>> marks;
 
   template <class T> T* buf(const std::string& name) const {
     auto it = bufs.find(name);
