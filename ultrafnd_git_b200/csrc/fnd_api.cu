@@ -378,9 +378,16 @@ static HeadParams head_params(const Plan& P, int training) {
 }
 template <bool FWD, bool CE, bool BWD>
 static int run_head(const Plan& P, const HeadParams& h, cudaStream_t st) {
-  const int grid = ceil_div(P.B, 8);
-  if (P.H == 512) head_kernel<FWD, CE, BWD, 4><<<grid, 256, 0, st>>>(h);
-  else head_kernel<FWD, CE, BWD, 8><<<grid, 256, 0, st>>>(h);
+  if (P.d.trees != 6 || P.d.depth != 4) return -50;     // only the reference's NODE shape is instantiated
+  const int grid = ceil_div(P.B, 8) < 296 ? ceil_div(P.B, 8) : 296;
+  const size_t smem = static_cast<size_t>(P.TD + 2) * P.H * sizeof(float);
+  if (P.H == 512) {
+    FND_CUDA_OK(cudaFuncSetAttribute(head_kernel<FWD, CE, BWD, 4, 6, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    head_kernel<FWD, CE, BWD, 4, 6, 4><<<grid, 256, smem, st>>>(h);
+  } else {
+    FND_CUDA_OK(cudaFuncSetAttribute(head_kernel<FWD, CE, BWD, 8, 6, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    head_kernel<FWD, CE, BWD, 8, 6, 4><<<grid, 256, smem, st>>>(h);
+  }
   FND_CUDA_OK(cudaGetLastError());
   mark(P, "head", st);
   return 0;

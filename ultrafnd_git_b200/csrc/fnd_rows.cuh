@@ -440,169 +440,195 @@ struct HeadParams {
   int B, H, T, D;
 };
 
-template <bool FWD, bool CE, bool BWD, int NF4>   // NF4 = H/128 float4 per lane
+// Tree shape is a compile-time parameter (T trees of depth D: the reference ships 6 x 4, classifier.yaml:12-14) so
+// the routing probabilities live in registers and every loop unrolls. alpha [TD,H] and the bypass weight [2,H] are
+// staged once per CTA in shared memory; each warp then walks rows b = blockIdx*8 + warp, += gridDim*8.
+template <bool FWD, bool CE, bool BWD, int NF4, int T, int D>   // NF4 = H/128 float4 per lane
 __global__ void __launch_bounds__(256) head_kernel(HeadParams p) {
+  constexpr int TD = T * D, L = 1 << D, H = NF4 * 128;
+  extern __shared__ float4 head_smem[];
+  float4* alpha_s = head_smem;                     // [TD][H/4]
+  float4* wb_s = head_smem + TD * (H / 4);         // [2][H/4]
+  __shared__ float leaf[T * L * 2];                // leaf tables and thresholds: broadcast reads
+  __shared__ float thr[TD];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-  const int b = blockIdx.x * 8 + warp;
-  if (b >= p.B) return;
-  const int H = p.H, T = p.T, D = p.D, TD = T * D, L = 1 << D;
+  for (int i = threadIdx.x; i < TD * (H / 4); i += 256) alpha_s[i] = ldg_f4(p.alpha + 4 * i);
+  for (int i = threadIdx.x; i < 2 * (H / 4); i += 256) wb_s[i] = ldg_f4(p.wb + 4 * i);
+  for (int i = threadIdx.x; i < T * L * 2; i += 256) leaf[i] = __ldg(p.leaf + i);
+  if (threadIdx.x < TD) thr[threadIdx.x] = __ldg(p.thresh + threadIdx.x);
+  __syncthreads();
   const DropCfg dtree = make_dropcfg(p.training ? p.tree_drop_p : 0.f,
                                      (static_cast<uint64_t>(p.state->rng[1]) << 32) | p.state->rng[0]);
-  float sv[kMaxTD];
-  float lg[2];
-  if (FWD) {
-    float4 hv[NF4];
+  const DropCfg dpre = make_dropcfg(p.training ? p.pre_drop_p : 0.f,
+                                    (static_cast<uint64_t>(p.state->rng[1]) << 32) | p.state->rng[0]);
+  const uint32_t tree_key = stream_key(p.state->rng, kStreamTree);
+  const uint32_t pre_key = stream_key(p.state->rng, kStreamPre1);
+
+  for (int b = blockIdx.x * 8 + warp; b < p.B; b += gridDim.x * 8) {
+    float sv[TD];
+    float lg[2];
+    float tmask[T][2];
 #pragma unroll
-    for (int i = 0; i < NF4; ++i) hv[i] = ldg_f4(p.h + static_cast<size_t>(b) * H + i * 128 + lane * 4);
-    float byp[2];
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      float acc = 0.f;
-#pragma unroll
-      for (int i = 0; i < NF4; ++i) {
-        const float4 w = ldg_f4(p.wb + static_cast<size_t>(c) * H + i * 128 + lane * 4);
-        acc += hv[i].x * w.x + hv[i].y * w.y + hv[i].z * w.z + hv[i].w * w.w;
-      }
-      byp[c] = warp_sum(acc) + p.bb[c];
-    }
-    for (int k = 0; k < TD; ++k) {
-      float acc = 0.f;
-#pragma unroll
-      for (int i = 0; i < NF4; ++i) {
-        const float4 w = ldg_f4(p.alpha + static_cast<size_t>(k) * H + i * 128 + lane * 4);
-        acc += hv[i].x * w.x + hv[i].y * w.y + hv[i].z * w.z + hv[i].w * w.w;
-      }
-      const float feat = warp_sum(acc);
-      sv[k] = sigmoidf_(p.tau * (feat - p.thresh[k]));
-    }
-    if (p.svals && lane < TD) {
-      // every lane holds all sv[] (warp_sum broadcasts); lane k stores element k
-      float mine = 0.f;
-      for (int k = 0; k < TD; ++k) mine = (lane == k) ? sv[k] : mine;
-      p.svals[static_cast<size_t>(b) * 32 + lane] = mine;
-    }
-    // tree logits (all lanes compute redundantly: 6 trees x 16 leaves)
-    float node[2] = {0.f, 0.f};
     for (int i = 0; i < T; ++i) {
-      float tl0 = 0.f, tl1 = 0.f;
-      for (int leafi = 0; leafi < L; ++leafi) {
-        float pr = 1.f;
-        for (int d = 0; d < D; ++d) pr *= ((leafi >> d) & 1) ? sv[i * D + d] : (1.f - sv[i * D + d]);
-        tl0 += pr * p.leaf[(i * L + leafi) * 2];
-        tl1 += pr * p.leaf[(i * L + leafi) * 2 + 1];
-      }
-      float m0 = 1.f, m1 = 1.f;
+      tmask[i][0] = 1.f; tmask[i][1] = 1.f;
       if (dtree.p > 0.f) {
-        // element index of tree logit (b, i, c) is b*T*2 + i*2 + c; 2 per tree -> one philox word pair
+        // element index of tree logit (b, i, c) is b*T*2 + i*2 + c
         const uint64_t e = static_cast<uint64_t>(b) * T * 2 + i * 2;
         float mm[4];
-        dropout_mult4(dtree, stream_key(p.state->rng, kStreamTree), e >> 2, mm);
-        m0 = mm[e & 3]; m1 = mm[(e & 3) + 1];
-      }
-      node[0] += tl0 * m0; node[1] += tl1 * m1;
-    }
-    lg[0] = node[0] / static_cast<float>(T) + byp[0];
-    lg[1] = node[1] / static_cast<float>(T) + byp[1];
-    if (lane == 0) {
-      p.logits[b * 2] = lg[0]; p.logits[b * 2 + 1] = lg[1];
-      const float tc = fminf(fmaxf(p.temperature[0], 0.5f), 5.0f);
-      const float a0 = lg[0] / tc, a1 = lg[1] / tc, mx = fmaxf(a0, a1);
-      const float e0 = expf(a0 - mx), e1 = expf(a1 - mx);
-      p.probs[b * 2] = e0 / (e0 + e1); p.probs[b * 2 + 1] = e1 / (e0 + e1);
-    }
-  } else {
-    for (int k = 0; k < TD; ++k) sv[k] = p.svals[static_cast<size_t>(b) * 32 + k];
-    lg[0] = p.logits[b * 2]; lg[1] = p.logits[b * 2 + 1];
-  }
-  float dl[2] = {0.f, 0.f};
-  if (CE) {
-    // F.cross_entropy, mean reduction (forensic_trainer.py:287)
-    const int y = static_cast<int>(p.labels[b]);
-    const float mx = fmaxf(lg[0], lg[1]);
-    const float e0 = expf(lg[0] - mx), e1 = expf(lg[1] - mx), se = e0 + e1;
-    const float loss = logf(se) + mx - lg[y];
-    const float sc = p.state->loss_scale;
-    dl[0] = (e0 / se - (y == 0 ? 1.f : 0.f)) * sc;
-    dl[1] = (e1 / se - (y == 1 ? 1.f : 0.f)) * sc;
-    if (lane == 0) {
-      p.loss_row[b] = loss;
-      if (p.dlogits_out) { p.dlogits_out[b * 2] = dl[0]; p.dlogits_out[b * 2 + 1] = dl[1]; }
-    }
-  } else if (BWD) {
-    dl[0] = p.dlogits_in[b * 2]; dl[1] = p.dlogits_in[b * 2 + 1];
-  }
-  if (BWD) {
-    float dfeat[kMaxTD];
-    for (int i = 0; i < T; ++i) {
-      float m0 = 1.f, m1 = 1.f;
-      if (dtree.p > 0.f) {
-        const uint64_t e = static_cast<uint64_t>(b) * T * 2 + i * 2;
-        float mm[4];
-        dropout_mult4(dtree, stream_key(p.state->rng, kStreamTree), e >> 2, mm);
-        m0 = mm[e & 3]; m1 = mm[(e & 3) + 1];
-      }
-      const float dt0 = dl[0] * m0 / static_cast<float>(T), dt1 = dl[1] * m1 / static_cast<float>(T);
-      float ds[4] = {0.f, 0.f, 0.f, 0.f};
-      for (int leafi = 0; leafi < L; ++leafi) {
-        float pr = 1.f;
-        for (int d = 0; d < D; ++d) pr *= ((leafi >> d) & 1) ? sv[i * D + d] : (1.f - sv[i * D + d]);
-        const float l0 = p.leaf[(i * L + leafi) * 2], l1 = p.leaf[(i * L + leafi) * 2 + 1];
-        if (lane == 0) {
-          p.leafc[static_cast<size_t>(b) * T * L * 2 + (i * L + leafi) * 2] = pr * dt0;
-          p.leafc[static_cast<size_t>(b) * T * L * 2 + (i * L + leafi) * 2 + 1] = pr * dt1;
-        }
-        const float dpr = l0 * dt0 + l1 * dt1;
-        for (int d = 0; d < D; ++d) {
-          float others = 1.f;
-          for (int d2 = 0; d2 < D; ++d2)
-            if (d2 != d) others *= ((leafi >> d2) & 1) ? sv[i * D + d2] : (1.f - sv[i * D + d2]);
-          ds[d] += dpr * (((leafi >> d) & 1) ? others : -others);
-        }
-      }
-      for (int d = 0; d < D; ++d) {
-        const float s = sv[i * D + d];
-        dfeat[i * D + d] = ds[d] * p.tau * s * (1.f - s);
+        dropout_mult4(dtree, tree_key, e >> 2, mm);
+        tmask[i][0] = mm[e & 3]; tmask[i][1] = mm[(e & 3) + 1];
       }
     }
-    // dF row: lanes write 2 columns each
-    {
-      float c0 = 0.f, c1 = 0.f;
-      for (int k = 0; k < TD; ++k) {
-        c0 = (2 * lane == k) ? dfeat[k] : c0;
-        c1 = (2 * lane + 1 == k) ? dfeat[k] : c1;
-      }
-      if (2 * lane == TD) c0 = dl[0];
-      if (2 * lane + 1 == TD) c1 = dl[0];
-      if (2 * lane == TD + 1) c0 = dl[1];
-      if (2 * lane + 1 == TD + 1) c1 = dl[1];
-      *reinterpret_cast<float2*>(p.dF + static_cast<size_t>(b) * kDFCols + 2 * lane) = make_float2(c0, c1);
-      store_bf2(p.dF_hi, p.dF_lo, static_cast<size_t>(b) * kDFCols + 2 * lane, c0, c1);
-    }
-    // dh = sum_k dfeat[k]*alpha[k,:] + sum_c dl[c]*wb[c,:]; then the GELU/dropout backward of pre.3
-    const DropCfg dpre = make_dropcfg(p.training ? p.pre_drop_p : 0.f,
-                                      (static_cast<uint64_t>(p.state->rng[1]) << 32) | p.state->rng[0]);
+    if (FWD) {
+      float4 hv[NF4];
 #pragma unroll
-    for (int i = 0; i < NF4; ++i) {
-      const int j = i * 128 + lane * 4;
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int k = 0; k < TD; ++k) {
-        const float4 w = ldg_f4(p.alpha + static_cast<size_t>(k) * H + j);
-        acc.x += dfeat[k] * w.x; acc.y += dfeat[k] * w.y; acc.z += dfeat[k] * w.z; acc.w += dfeat[k] * w.w;
-      }
+      for (int i = 0; i < NF4; ++i) hv[i] = ldg_f4(p.h + static_cast<size_t>(b) * H + i * 128 + lane * 4);
+      float byp[2];
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
-        const float4 w = ldg_f4(p.wb + static_cast<size_t>(c) * H + j);
-        acc.x += dl[c] * w.x; acc.y += dl[c] * w.y; acc.z += dl[c] * w.z; acc.w += dl[c] * w.w;
+        float acc = 0.f;
+#pragma unroll
+        for (int i = 0; i < NF4; ++i) {
+          const float4 w = wb_s[c * (H / 4) + i * 32 + lane];
+          acc += hv[i].x * w.x + hv[i].y * w.y + hv[i].z * w.z + hv[i].w * w.w;
+        }
+        byp[c] = warp_sum(acc) + __ldg(p.bb + c);
       }
-      const float4 z = ldg_f4(p.z_pre1 + static_cast<size_t>(b) * H + j);
-      float mm[4] = {1.f, 1.f, 1.f, 1.f};
-      if (dpre.p > 0.f)
-        dropout_mult4(dpre, stream_key(p.state->rng, kStreamPre1), (static_cast<uint64_t>(b) * H + j) >> 2, mm);
-      acc.x *= gelu_erf_grad(z.x) * mm[0]; acc.y *= gelu_erf_grad(z.y) * mm[1];
-      acc.z *= gelu_erf_grad(z.z) * mm[2]; acc.w *= gelu_erf_grad(z.w) * mm[3];
-      store_bf2(p.dz_hi, p.dz_lo, static_cast<size_t>(b) * H + j, acc.x, acc.y);
-      store_bf2(p.dz_hi, p.dz_lo, static_cast<size_t>(b) * H + j + 2, acc.z, acc.w);
+#pragma unroll
+      for (int k = 0; k < TD; ++k) {
+        float acc = 0.f;
+#pragma unroll
+        for (int i = 0; i < NF4; ++i) {
+          const float4 w = alpha_s[k * (H / 4) + i * 32 + lane];
+          acc += hv[i].x * w.x + hv[i].y * w.y + hv[i].z * w.z + hv[i].w * w.w;
+        }
+        sv[k] = sigmoidf_(p.tau * (warp_sum(acc) - thr[k]));
+      }
+      if (p.svals) {
+        float mine = 0.f;
+#pragma unroll
+        for (int k = 0; k < TD; ++k) mine = (lane == k) ? sv[k] : mine;
+        if (lane < TD) p.svals[static_cast<size_t>(b) * 32 + lane] = mine;
+      }
+      float node0 = 0.f, node1 = 0.f;
+#pragma unroll
+      for (int i = 0; i < T; ++i) {
+        float tl0 = 0.f, tl1 = 0.f;
+#pragma unroll
+        for (int leafi = 0; leafi < L; ++leafi) {
+          float pr = 1.f;
+#pragma unroll
+          for (int d = 0; d < D; ++d) pr *= ((leafi >> d) & 1) ? sv[i * D + d] : (1.f - sv[i * D + d]);
+          tl0 += pr * leaf[(i * L + leafi) * 2];
+          tl1 += pr * leaf[(i * L + leafi) * 2 + 1];
+        }
+        node0 += tl0 * tmask[i][0]; node1 += tl1 * tmask[i][1];
+      }
+      lg[0] = node0 / static_cast<float>(T) + byp[0];
+      lg[1] = node1 / static_cast<float>(T) + byp[1];
+      if (lane == 0) {
+        p.logits[b * 2] = lg[0]; p.logits[b * 2 + 1] = lg[1];
+        const float tc = fminf(fmaxf(__ldg(p.temperature), 0.5f), 5.0f);
+        const float a0 = lg[0] / tc, a1 = lg[1] / tc, mx = fmaxf(a0, a1);
+        const float e0 = expf(a0 - mx), e1 = expf(a1 - mx);
+        p.probs[b * 2] = e0 / (e0 + e1); p.probs[b * 2 + 1] = e1 / (e0 + e1);
+      }
+    } else {
+      const float mine = (BWD && lane < TD) ? p.svals[static_cast<size_t>(b) * 32 + lane] : 0.f;
+#pragma unroll
+      for (int k = 0; k < TD; ++k) sv[k] = __shfl_sync(0xffffffffu, mine, k);
+      lg[0] = p.logits[b * 2]; lg[1] = p.logits[b * 2 + 1];
+    }
+    float dl[2] = {0.f, 0.f};
+    if (CE) {
+      // F.cross_entropy, mean reduction (forensic_trainer.py:287)
+      const int y = static_cast<int>(p.labels[b]);
+      const float mx = fmaxf(lg[0], lg[1]);
+      const float e0 = expf(lg[0] - mx), e1 = expf(lg[1] - mx), se = e0 + e1;
+      const float loss = logf(se) + mx - (y == 0 ? lg[0] : lg[1]);
+      const float sc = p.state->loss_scale;
+      dl[0] = (e0 / se - (y == 0 ? 1.f : 0.f)) * sc;
+      dl[1] = (e1 / se - (y == 1 ? 1.f : 0.f)) * sc;
+      if (lane == 0) {
+        p.loss_row[b] = loss;
+        if (p.dlogits_out) { p.dlogits_out[b * 2] = dl[0]; p.dlogits_out[b * 2 + 1] = dl[1]; }
+      }
+    } else if (BWD) {
+      dl[0] = p.dlogits_in[b * 2]; dl[1] = p.dlogits_in[b * 2 + 1];
+    }
+    if (BWD) {
+      float dfeat[TD];
+#pragma unroll
+      for (int i = 0; i < T; ++i) {
+        const float dt0 = dl[0] * tmask[i][0] / static_cast<float>(T), dt1 = dl[1] * tmask[i][1] / static_cast<float>(T);
+        float ds[D];
+#pragma unroll
+        for (int d = 0; d < D; ++d) ds[d] = 0.f;
+        float myleaf0 = 0.f, myleaf1 = 0.f;          // lane `leafi` keeps leaf `leafi`'s contribution (L <= 32)
+#pragma unroll
+        for (int leafi = 0; leafi < L; ++leafi) {
+          float pr = 1.f;
+#pragma unroll
+          for (int d = 0; d < D; ++d) pr *= ((leafi >> d) & 1) ? sv[i * D + d] : (1.f - sv[i * D + d]);
+          if (lane == leafi) { myleaf0 = pr * dt0; myleaf1 = pr * dt1; }
+          const float dpr = leaf[(i * L + leafi) * 2] * dt0 + leaf[(i * L + leafi) * 2 + 1] * dt1;
+#pragma unroll
+          for (int d = 0; d < D; ++d) {
+            float others = 1.f;
+#pragma unroll
+            for (int d2 = 0; d2 < D; ++d2)
+              if (d2 != d) others *= ((leafi >> d2) & 1) ? sv[i * D + d2] : (1.f - sv[i * D + d2]);
+            ds[d] += dpr * (((leafi >> d) & 1) ? others : -others);
+          }
+        }
+        if (lane < L)
+          *reinterpret_cast<float2*>(p.leafc + static_cast<size_t>(b) * T * L * 2 + (i * L + lane) * 2) =
+              make_float2(myleaf0, myleaf1);
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+          const float s = sv[i * D + d];
+          dfeat[i * D + d] = ds[d] * p.tau * s * (1.f - s);
+        }
+      }
+      // dF row [dfeat | dlogits | 0]: lanes write 2 columns each
+      {
+        float c0 = 0.f, c1 = 0.f;
+#pragma unroll
+        for (int k = 0; k < TD; ++k) {
+          c0 = (2 * lane == k) ? dfeat[k] : c0;
+          c1 = (2 * lane + 1 == k) ? dfeat[k] : c1;
+        }
+        if (2 * lane == TD) c0 = dl[0];
+        if (2 * lane + 1 == TD) c1 = dl[0];
+        if (2 * lane == TD + 1) c0 = dl[1];
+        if (2 * lane + 1 == TD + 1) c1 = dl[1];
+        *reinterpret_cast<float2*>(p.dF + static_cast<size_t>(b) * kDFCols + 2 * lane) = make_float2(c0, c1);
+        store_bf2(p.dF_hi, p.dF_lo, static_cast<size_t>(b) * kDFCols + 2 * lane, c0, c1);
+      }
+      // dh = sum_k dfeat[k]*alpha[k,:] + sum_c dl[c]*wb[c,:]; then the GELU/dropout backward of pre.3
+#pragma unroll
+      for (int i = 0; i < NF4; ++i) {
+        const int j = i * 128 + lane * 4;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < TD; ++k) {
+          const float4 w = alpha_s[k * (H / 4) + i * 32 + lane];
+          acc.x += dfeat[k] * w.x; acc.y += dfeat[k] * w.y; acc.z += dfeat[k] * w.z; acc.w += dfeat[k] * w.w;
+        }
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const float4 w = wb_s[c * (H / 4) + i * 32 + lane];
+          acc.x += dl[c] * w.x; acc.y += dl[c] * w.y; acc.z += dl[c] * w.z; acc.w += dl[c] * w.w;
+        }
+        const float4 z = ldg_f4(p.z_pre1 + static_cast<size_t>(b) * H + j);
+        float mm[4] = {1.f, 1.f, 1.f, 1.f};
+        if (dpre.p > 0.f) dropout_mult4(dpre, pre_key, (static_cast<uint64_t>(b) * H + j) >> 2, mm);
+        acc.x *= gelu_erf_grad(z.x) * mm[0]; acc.y *= gelu_erf_grad(z.y) * mm[1];
+        acc.z *= gelu_erf_grad(z.z) * mm[2]; acc.w *= gelu_erf_grad(z.w) * mm[3];
+        store_bf2(p.dz_hi, p.dz_lo, static_cast<size_t>(b) * H + j, acc.x, acc.y);
+        store_bf2(p.dz_hi, p.dz_lo, static_cast<size_t>(b) * H + j + 2, acc.z, acc.w);
+      }
     }
   }
 }
