@@ -170,6 +170,13 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
       : "r"(taddr)
       : "memory");
 }
+// 32 lanes x 8 consecutive fp32 columns.
+__device__ __forceinline__ void tmem_ld_32x8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // Shared-memory matrix descriptor (tcgen05 "SmemDescriptor", version 1, SWIZZLE_128B).
@@ -219,7 +226,7 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
 // under key (seed, stream). Dropout keeps element i iff word(i & 3) of counter (i >> 2) >= p * 2^32,
 // so forward and backward regenerate identical masks from (seed, stream, element index) alone.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint4 philox4x32_10(uint64_t ctr, uint32_t key0, uint32_t key1, uint32_t stream) {
+__device__ __noinline__ uint4 philox4x32_10(uint64_t ctr, uint32_t key0, uint32_t key1, uint32_t stream) {
   uint32_t c0 = static_cast<uint32_t>(ctr), c1 = static_cast<uint32_t>(ctr >> 32), c2 = stream, c3 = 0x5eedf17du;
   uint32_t k0 = key0, k1 = key1;
 #pragma unroll

@@ -202,13 +202,15 @@ fnd_gemm_kernel(const GemmProblem* __restrict__ probs, int nprob, RunCtx ctx) {
     __syncwarp();
   } else {
     // ================= epilogue (warps 2..5) =================
+    // Deliberately ROLLED (8 columns per iteration, #pragma unroll 1): a fully unrolled epilogue was ~100 KB of
+    // straight-line SASS and made every small launch instruction-fetch bound (~25 us fixed cost, measured).
     const EpiParams& E = P.epi;
     const int lane_grp = warp & 3;                 // TMEM lane quarter this warp may access
     const int row = lane_grp * 32 + lane;
     const int m = tm * kGemmBM + row;
     const bool row_ok = m < P.M;
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16);
-    const int nchunks = bn / 32;
+    const int ngroups = bn / 8;
     const int epi_tid = threadIdx.x - 64;
     bool proceed = mbar_wait(accum_bar, 0u, ctx.err, FND_DEV_TIMEOUT_EPILOGUE);
     tc_fence_after_sync();
@@ -217,15 +219,15 @@ fnd_gemm_kernel(const GemmProblem* __restrict__ probs, int nprob, RunCtx ctx) {
     if (splits > 1) {
       ws_tile = P.splitk_ws + static_cast<size_t>(tile) * splits * (kGemmBM * bn);
       float* mine = ws_tile + static_cast<size_t>(split) * (kGemmBM * bn) + static_cast<size_t>(row) * bn;
-      for (int ch = 0; ch < nchunks; ++ch) {
-        uint32_t r[32];
-        tmem_ld_32x32(taddr + ch * 32, r);
+#pragma unroll 1
+      for (int g = 0; g < ngroups; ++g) {
+        uint32_t r[8];
+        tmem_ld_32x8(taddr + g * 8, r);
         tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 32; j += 4)
-          __stcg(reinterpret_cast<float4*>(mine + ch * 32 + j),
-                 make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
-                             __uint_as_float(r[j + 3])));
+        __stcg(reinterpret_cast<float4*>(mine + g * 8),
+               make_float4(__uint_as_float(r[0]), __uint_as_float(r[1]), __uint_as_float(r[2]), __uint_as_float(r[3])));
+        __stcg(reinterpret_cast<float4*>(mine + g * 8 + 4),
+               make_float4(__uint_as_float(r[4]), __uint_as_float(r[5]), __uint_as_float(r[6]), __uint_as_float(r[7])));
       }
       __threadfence();
       epi_named_barrier();
@@ -240,161 +242,130 @@ fnd_gemm_kernel(const GemmProblem* __restrict__ probs, int nprob, RunCtx ctx) {
       if (proceed) __threadfence();
     }
 
+    float ss = 0.f;
     if (proceed) {
-      const uint32_t seed_lo = ctx.rng ? ctx.rng[0] : 0u;
-      const uint32_t seed_hi = ctx.rng ? ctx.rng[1] : 0u;
-      DropCfg dfw = make_dropcfg(ctx.training ? E.drop_p : 0.f, (static_cast<uint64_t>(seed_hi) << 32) | seed_lo);
-      DropCfg dbw = make_dropcfg(ctx.training ? E.gate_p : 0.f, (static_cast<uint64_t>(seed_hi) << 32) | seed_lo);
+      const uint64_t seed = ctx.rng ? ((static_cast<uint64_t>(ctx.rng[1]) << 32) | ctx.rng[0]) : 0ull;
+      const DropCfg dfw = make_dropcfg(ctx.training ? E.drop_p : 0.f, seed);
+      const DropCfg dbw = make_dropcfg(ctx.training ? E.gate_p : 0.f, seed);
+      const uint32_t key_fw = stream_key(ctx.rng, E.drop_stream);
+      const uint32_t key_bw = stream_key(ctx.rng, E.gate_stream);
       float a0 = 0.f, a1 = 0.f;
       if (E.aux && row_ok) {
         a0 = E.aux[static_cast<size_t>(m) * 2];
         a1 = E.aux[static_cast<size_t>(m) * 2 + 1];
       }
-      float ss = 0.f;
-      for (int ch = 0; ch < nchunks; ++ch) {
-        float v[32];
+#pragma unroll 1
+      for (int g = 0; g < ngroups; ++g) {
+        float v[8];
         if (splits > 1) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = 0.f;
-          for (int s = 0; s < splits; ++s) {
-            const float* src = ws_tile + static_cast<size_t>(s) * (kGemmBM * bn) + static_cast<size_t>(row) * bn + ch * 32;
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 t = ldcg_f4(src + j);
-              v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
-            }
+          for (int j = 0; j < 8; ++j) v[j] = 0.f;
+#pragma unroll 1
+          for (int s2 = 0; s2 < splits; ++s2) {        // fixed split order => deterministic sum
+            const float* src = ws_tile + static_cast<size_t>(s2) * (kGemmBM * bn) + static_cast<size_t>(row) * bn + g * 8;
+            const float4 t0 = ldcg_f4(src), t1 = ldcg_f4(src + 4);
+            v[0] += t0.x; v[1] += t0.y; v[2] += t0.z; v[3] += t0.w;
+            v[4] += t1.x; v[5] += t1.y; v[6] += t1.z; v[7] += t1.w;
           }
         } else {
-          uint32_t r[32];
-          tmem_ld_32x32(taddr + ch * 32, r);
+          uint32_t r[8];
+          tmem_ld_32x8(taddr + g * 8, r);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[j]);
         }
-        const int n0 = tn * bn + ch * 32;
-        if (!row_ok || n0 >= P.N) continue;
-        const bool full = (n0 + 32 <= P.N);
+        const int n0 = tn * bn + g * 8;
+        if (!row_ok || n0 >= P.N) continue;          // N is a multiple of 8 (checked on the host)
 
         if (E.bias) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (full || n0 + j < P.N) v[j] += __ldg(E.bias + n0 + j);
+          const float4 b0 = ldg_f4(E.bias + n0), b1 = ldg_f4(E.bias + n0 + 4);
+          v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+          v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
         }
         if (E.aux) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (full || n0 + j < P.N) {
-              const float* w = E.aux_w + static_cast<size_t>(n0 + j) * E.aux_w_pitch;
-              v[j] += a0 * __ldg(w) + a1 * __ldg(w + 1);
-            }
+          for (int j = 0; j < 8; ++j) {
+            const float* w = E.aux_w + static_cast<size_t>(n0 + j) * E.aux_w_pitch;
+            v[j] += a0 * __ldg(w) + a1 * __ldg(w + 1);
+          }
         }
         if (E.add_in) {
           const float* src = E.add_in + static_cast<size_t>(m) * E.add_pitch + n0;
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (full || n0 + j < P.N) v[j] += src[j];
+          const float4 t0 = ldg_f4(src), t1 = ldg_f4(src + 4);
+          v[0] += t0.x; v[1] += t0.y; v[2] += t0.z; v[3] += t0.w;
+          v[4] += t1.x; v[5] += t1.y; v[6] += t1.z; v[7] += t1.w;
         }
         if (E.out_pre) {
           float* dst = E.out_pre + static_cast<size_t>(m) * E.pre_pitch + n0;
-          if (full && (E.pre_pitch & 3) == 0) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (n0 + j < P.N) dst[j] = v[j];
-          }
+          *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+          *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
         }
         if (E.act == 1) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+          for (int j = 0; j < 8; ++j) v[j] = gelu_erf(v[j]);
         }
+        const uint64_t e0 = static_cast<uint64_t>(m) * static_cast<uint64_t>(P.N) + n0;   // multiple of 8
         if (dfw.p > 0.f) {
-          const uint64_t e0 = static_cast<uint64_t>(m) * static_cast<uint64_t>(P.N) + n0;   // multiple of 4
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float mm[4];
-            dropout_mult4(dfw, stream_key(ctx.rng, E.drop_stream), (e0 + j) >> 2, mm);
-            v[j] *= mm[0]; v[j + 1] *= mm[1]; v[j + 2] *= mm[2]; v[j + 3] *= mm[3];
-          }
+          float mm[4];
+          dropout_mult4(dfw, key_fw, e0 >> 2, mm);
+          v[0] *= mm[0]; v[1] *= mm[1]; v[2] *= mm[2]; v[3] *= mm[3];
+          dropout_mult4(dfw, key_fw, (e0 >> 2) + 1, mm);
+          v[4] *= mm[0]; v[5] *= mm[1]; v[6] *= mm[2]; v[7] *= mm[3];
         }
         if (E.gate_z) {
           const float* z = E.gate_z + static_cast<size_t>(m) * E.gate_pitch + n0;
-          const uint64_t e0 = static_cast<uint64_t>(m) * static_cast<uint64_t>(P.N) + n0;
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float mm[4] = {1.f, 1.f, 1.f, 1.f};
-            if (dbw.p > 0.f)
-              dropout_mult4(dbw, stream_key(ctx.rng, E.gate_stream), (e0 + j) >> 2, mm);
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-              if (full || n0 + j + q < P.N) v[j + q] *= gelu_erf_grad(z[j + q]) * mm[q];
+          const float4 z0 = ldg_f4(z), z1 = ldg_f4(z + 4);
+          float mm[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f};
+          if (dbw.p > 0.f) {
+            float t4[4];
+            dropout_mult4(dbw, key_bw, e0 >> 2, t4);
+            mm[0] = t4[0]; mm[1] = t4[1]; mm[2] = t4[2]; mm[3] = t4[3];
+            dropout_mult4(dbw, key_bw, (e0 >> 2) + 1, t4);
+            mm[4] = t4[0]; mm[5] = t4[1]; mm[6] = t4[2]; mm[7] = t4[3];
           }
+          v[0] *= gelu_erf_grad(z0.x) * mm[0]; v[1] *= gelu_erf_grad(z0.y) * mm[1];
+          v[2] *= gelu_erf_grad(z0.z) * mm[2]; v[3] *= gelu_erf_grad(z0.w) * mm[3];
+          v[4] *= gelu_erf_grad(z1.x) * mm[4]; v[5] *= gelu_erf_grad(z1.y) * mm[5];
+          v[6] *= gelu_erf_grad(z1.z) * mm[6]; v[7] *= gelu_erf_grad(z1.w) * mm[7];
         }
         if (E.out_f32) {
           float* dst = E.out_f32 + static_cast<size_t>(m) * E.f32_pitch + n0;
-          if (full && (E.f32_pitch & 3) == 0 && (reinterpret_cast<uintptr_t>(E.out_f32) & 15) == 0) {
+          if ((E.f32_pitch & 3) == 0) {
+            *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+            *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
+          } else {                                   // even pitch (pre.0.weight: 514): 8-byte aligned rows
 #pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (n0 + j < P.N) dst[j] = v[j];
+            for (int j = 0; j < 8; j += 2) *reinterpret_cast<float2*>(dst + j) = make_float2(v[j], v[j + 1]);
           }
         }
         if (E.out_hi) {
-          __nv_bfloat16* dh = E.out_hi + static_cast<size_t>(m) * E.bf_pitch + n0;
-          const bool vec = full && (E.bf_pitch & 7) == 0;
-          if (vec) {
-            uint32_t ph[16];
+          const size_t o = static_cast<size_t>(m) * E.bf_pitch + n0;
+          uint32_t ph[4];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) ph[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+          for (int j = 0; j < 4; ++j) ph[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+          *reinterpret_cast<uint4*>(E.out_hi + o) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+          if (E.out_lo) {
+            uint32_t pl[4];
 #pragma unroll
-            for (int j = 0; j < 16; j += 4)
-              *reinterpret_cast<uint4*>(dh + 2 * j) = make_uint4(ph[j], ph[j + 1], ph[j + 2], ph[j + 3]);
-            if (E.out_lo) {
-              __nv_bfloat16* dl = E.out_lo + static_cast<size_t>(m) * E.bf_pitch + n0;
-              uint32_t pl[16];
-#pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&ph[j]);
-                pl[j] = pack_bf16x2(v[2 * j] - __low2float(h2), v[2 * j + 1] - __high2float(h2));
-              }
-#pragma unroll
-              for (int j = 0; j < 16; j += 4)
-                *reinterpret_cast<uint4*>(dl + 2 * j) = make_uint4(pl[j], pl[j + 1], pl[j + 2], pl[j + 3]);
+            for (int j = 0; j < 4; ++j) {
+              const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&ph[j]);
+              pl[j] = pack_bf16x2(v[2 * j] - __low2float(h2), v[2 * j + 1] - __high2float(h2));
             }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (n0 + j < P.N) {
-                __nv_bfloat16 h, l;
-                split_bf16(v[j], h, l);
-                dh[j] = h;
-                if (E.out_lo) E.out_lo[static_cast<size_t>(m) * E.bf_pitch + n0 + j] = l;
-              }
+            *reinterpret_cast<uint4*>(E.out_lo + o) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
           }
         }
         if (E.sumsq_slots) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (full || n0 + j < P.N) ss += v[j] * v[j];
+          for (int j = 0; j < 8; ++j) ss += v[j] * v[j];
         }
       }
-      if (E.sumsq_slots) {
-        ss = warp_sum(ss);
-        if (lane == 0) red_smem[lane_grp] = ss;
-        epi_named_barrier();
-        if (epi_tid == 0) {
-          // fixed order => deterministic
-          E.sumsq_slots[local] = (red_smem[2] + red_smem[3]) + (red_smem[0] + red_smem[1]);
-        }
-      }
-    } else if (P.epi.sumsq_slots && splits > 1) {
-      // non-last split CTAs contribute zero to the norm
-      if (epi_tid == 0) P.epi.sumsq_slots[local] = 0.f;
+    }
+    if (E.sumsq_slots) {
+      // every epilogue thread takes part (non-last split CTAs contribute 0) => fixed order, deterministic
+      ss = warp_sum(ss);
+      if (lane == 0) red_smem[lane_grp] = ss;
+      epi_named_barrier();
+      if (epi_tid == 0) E.sumsq_slots[local] = (red_smem[2] + red_smem[3]) + (red_smem[0] + red_smem[1]);
     }
   }
 

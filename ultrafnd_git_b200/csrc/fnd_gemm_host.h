@@ -27,6 +27,7 @@ inline int fill_problem(GemmProblem& p, const Operand& A, const Operand& B, int 
   if (B.mn_major && bn < 64) return -11;
   if (ncombo != 1 && ncombo != 3) return -12;
   if (ncombo == 3 && (!A.lo || !B.lo)) return -13;
+  if (N % 8) return -15;                 // the epilogue works on 8-column groups
   p.M = M; p.N = N; p.K = K;
   p.bn = bn;
   p.ncombo = ncombo;

@@ -440,9 +440,11 @@ struct HeadParams {
   int B, H, T, D;
 };
 
-// Tree shape is a compile-time parameter (T trees of depth D: the reference ships 6 x 4, classifier.yaml:12-14) so
-// the routing probabilities live in registers and every loop unrolls. alpha [TD,H] and the bypass weight [2,H] are
-// staged once per CTA in shared memory; each warp then walks rows b = blockIdx*8 + warp, += gridDim*8.
+// Tree shape is a compile-time parameter (T trees of depth D: the reference ships 6 x 4, classifier.yaml:12-14).
+// alpha [TD,H] and the bypass weight [2,H] are staged once per CTA in shared memory; each warp then walks rows
+// b = blockIdx*8 + warp, += gridDim*8. Per-row routing probabilities / feature gradients sit in per-warp shared
+// memory so the tree loops can stay ROLLED: the fully unrolled version was >110 KB of SASS and instruction-fetch
+// bound (33 us for 128 rows).
 template <bool FWD, bool CE, bool BWD, int NF4, int T, int D>   // NF4 = H/128 float4 per lane
 __global__ void __launch_bounds__(256) head_kernel(HeadParams p) {
   constexpr int TD = T * D, L = 1 << D, H = NF4 * 128;
@@ -451,35 +453,26 @@ __global__ void __launch_bounds__(256) head_kernel(HeadParams p) {
   float4* wb_s = head_smem + TD * (H / 4);         // [2][H/4]
   __shared__ float leaf[T * L * 2];                // leaf tables and thresholds: broadcast reads
   __shared__ float thr[TD];
+  __shared__ float sv_all[8][TD];                  // per-warp sigmoid outputs of the current row
+  __shared__ float df_all[8][TD + 2];              // per-warp dfeat | dlogits of the current row
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
+  float* sv = sv_all[warp];
+  float* df = df_all[warp];
   for (int i = threadIdx.x; i < TD * (H / 4); i += 256) alpha_s[i] = ldg_f4(p.alpha + 4 * i);
   for (int i = threadIdx.x; i < 2 * (H / 4); i += 256) wb_s[i] = ldg_f4(p.wb + 4 * i);
   for (int i = threadIdx.x; i < T * L * 2; i += 256) leaf[i] = __ldg(p.leaf + i);
   if (threadIdx.x < TD) thr[threadIdx.x] = __ldg(p.thresh + threadIdx.x);
   __syncthreads();
-  const DropCfg dtree = make_dropcfg(p.training ? p.tree_drop_p : 0.f,
-                                     (static_cast<uint64_t>(p.state->rng[1]) << 32) | p.state->rng[0]);
-  const DropCfg dpre = make_dropcfg(p.training ? p.pre_drop_p : 0.f,
-                                    (static_cast<uint64_t>(p.state->rng[1]) << 32) | p.state->rng[0]);
+  const uint64_t seed = (static_cast<uint64_t>(p.state->rng[1]) << 32) | p.state->rng[0];
+  const DropCfg dtree = make_dropcfg(p.training ? p.tree_drop_p : 0.f, seed);
+  const DropCfg dpre = make_dropcfg(p.training ? p.pre_drop_p : 0.f, seed);
   const uint32_t tree_key = stream_key(p.state->rng, kStreamTree);
   const uint32_t pre_key = stream_key(p.state->rng, kStreamPre1);
+  const float inv_T = 1.0f / static_cast<float>(T);
 
   for (int b = blockIdx.x * 8 + warp; b < p.B; b += gridDim.x * 8) {
-    float sv[TD];
     float lg[2];
-    float tmask[T][2];
-#pragma unroll
-    for (int i = 0; i < T; ++i) {
-      tmask[i][0] = 1.f; tmask[i][1] = 1.f;
-      if (dtree.p > 0.f) {
-        // element index of tree logit (b, i, c) is b*T*2 + i*2 + c
-        const uint64_t e = static_cast<uint64_t>(b) * T * 2 + i * 2;
-        float mm[4];
-        dropout_mult4(dtree, tree_key, e >> 2, mm);
-        tmask[i][0] = mm[e & 3]; tmask[i][1] = mm[(e & 3) + 1];
-      }
-    }
     if (FWD) {
       float4 hv[NF4];
 #pragma unroll
@@ -495,7 +488,8 @@ __global__ void __launch_bounds__(256) head_kernel(HeadParams p) {
         }
         byp[c] = warp_sum(acc) + __ldg(p.bb + c);
       }
-#pragma unroll
+      float mine = 0.f;
+#pragma unroll 2
       for (int k = 0; k < TD; ++k) {
         float acc = 0.f;
 #pragma unroll
@@ -503,30 +497,40 @@ __global__ void __launch_bounds__(256) head_kernel(HeadParams p) {
           const float4 w = alpha_s[k * (H / 4) + i * 32 + lane];
           acc += hv[i].x * w.x + hv[i].y * w.y + hv[i].z * w.z + hv[i].w * w.w;
         }
-        sv[k] = sigmoidf_(p.tau * (warp_sum(acc) - thr[k]));
+        const float sk = sigmoidf_(p.tau * (warp_sum(acc) - thr[k]));
+        mine = (lane == k) ? sk : mine;
       }
-      if (p.svals) {
-        float mine = 0.f;
-#pragma unroll
-        for (int k = 0; k < TD; ++k) mine = (lane == k) ? sv[k] : mine;
-        if (lane < TD) p.svals[static_cast<size_t>(b) * 32 + lane] = mine;
+      if (lane < TD) {
+        sv[lane] = mine;
+        if (p.svals) p.svals[static_cast<size_t>(b) * 32 + lane] = mine;
       }
+      __syncwarp();
       float node0 = 0.f, node1 = 0.f;
-#pragma unroll
+#pragma unroll 1
       for (int i = 0; i < T; ++i) {
+        float s[D];
+#pragma unroll
+        for (int d = 0; d < D; ++d) s[d] = sv[i * D + d];
         float tl0 = 0.f, tl1 = 0.f;
 #pragma unroll
         for (int leafi = 0; leafi < L; ++leafi) {
           float pr = 1.f;
 #pragma unroll
-          for (int d = 0; d < D; ++d) pr *= ((leafi >> d) & 1) ? sv[i * D + d] : (1.f - sv[i * D + d]);
+          for (int d = 0; d < D; ++d) pr *= ((leafi >> d) & 1) ? s[d] : (1.f - s[d]);
           tl0 += pr * leaf[(i * L + leafi) * 2];
           tl1 += pr * leaf[(i * L + leafi) * 2 + 1];
         }
-        node0 += tl0 * tmask[i][0]; node1 += tl1 * tmask[i][1];
+        float m0 = 1.f, m1 = 1.f;
+        if (dtree.p > 0.f) {
+          const uint64_t e = static_cast<uint64_t>(b) * T * 2 + i * 2;     // element index of tree logit (b, i, 0)
+          float mm[4];
+          dropout_mult4(dtree, tree_key, e >> 2, mm);
+          m0 = (e & 2) ? mm[2] : mm[0]; m1 = (e & 2) ? mm[3] : mm[1];
+        }
+        node0 += tl0 * m0; node1 += tl1 * m1;
       }
-      lg[0] = node0 / static_cast<float>(T) + byp[0];
-      lg[1] = node1 / static_cast<float>(T) + byp[1];
+      lg[0] = node0 * inv_T + byp[0];
+      lg[1] = node1 * inv_T + byp[1];
       if (lane == 0) {
         p.logits[b * 2] = lg[0]; p.logits[b * 2 + 1] = lg[1];
         const float tc = fminf(fmaxf(__ldg(p.temperature), 0.5f), 5.0f);
@@ -535,9 +539,8 @@ __global__ void __launch_bounds__(256) head_kernel(HeadParams p) {
         p.probs[b * 2] = e0 / (e0 + e1); p.probs[b * 2 + 1] = e1 / (e0 + e1);
       }
     } else {
-      const float mine = (BWD && lane < TD) ? p.svals[static_cast<size_t>(b) * 32 + lane] : 0.f;
-#pragma unroll
-      for (int k = 0; k < TD; ++k) sv[k] = __shfl_sync(0xffffffffu, mine, k);
+      if (BWD && lane < TD) sv[lane] = p.svals[static_cast<size_t>(b) * 32 + lane];
+      __syncwarp();
       lg[0] = p.logits[b * 2]; lg[1] = p.logits[b * 2 + 1];
     }
     float dl[2] = {0.f, 0.f};
@@ -558,10 +561,19 @@ __global__ void __launch_bounds__(256) head_kernel(HeadParams p) {
       dl[0] = p.dlogits_in[b * 2]; dl[1] = p.dlogits_in[b * 2 + 1];
     }
     if (BWD) {
-      float dfeat[TD];
-#pragma unroll
+#pragma unroll 1
       for (int i = 0; i < T; ++i) {
-        const float dt0 = dl[0] * tmask[i][0] / static_cast<float>(T), dt1 = dl[1] * tmask[i][1] / static_cast<float>(T);
+        float s[D];
+#pragma unroll
+        for (int d = 0; d < D; ++d) s[d] = sv[i * D + d];
+        float m0 = 1.f, m1 = 1.f;
+        if (dtree.p > 0.f) {
+          const uint64_t e = static_cast<uint64_t>(b) * T * 2 + i * 2;
+          float mm[4];
+          dropout_mult4(dtree, tree_key, e >> 2, mm);
+          m0 = (e & 2) ? mm[2] : mm[0]; m1 = (e & 2) ? mm[3] : mm[1];
+        }
+        const float dt0 = dl[0] * m0 * inv_T, dt1 = dl[1] * m1 * inv_T;
         float ds[D];
 #pragma unroll
         for (int d = 0; d < D; ++d) ds[d] = 0.f;
@@ -570,7 +582,7 @@ __global__ void __launch_bounds__(256) head_kernel(HeadParams p) {
         for (int leafi = 0; leafi < L; ++leafi) {
           float pr = 1.f;
 #pragma unroll
-          for (int d = 0; d < D; ++d) pr *= ((leafi >> d) & 1) ? sv[i * D + d] : (1.f - sv[i * D + d]);
+          for (int d = 0; d < D; ++d) pr *= ((leafi >> d) & 1) ? s[d] : (1.f - s[d]);
           if (lane == leafi) { myleaf0 = pr * dt0; myleaf1 = pr * dt1; }
           const float dpr = leaf[(i * L + leafi) * 2] * dt0 + leaf[(i * L + leafi) * 2 + 1] * dt1;
 #pragma unroll
@@ -578,57 +590,59 @@ __global__ void __launch_bounds__(256) head_kernel(HeadParams p) {
             float others = 1.f;
 #pragma unroll
             for (int d2 = 0; d2 < D; ++d2)
-              if (d2 != d) others *= ((leafi >> d2) & 1) ? sv[i * D + d2] : (1.f - sv[i * D + d2]);
+              if (d2 != d) others *= ((leafi >> d2) & 1) ? s[d2] : (1.f - s[d2]);
             ds[d] += dpr * (((leafi >> d) & 1) ? others : -others);
           }
         }
         if (lane < L)
           *reinterpret_cast<float2*>(p.leafc + static_cast<size_t>(b) * T * L * 2 + (i * L + lane) * 2) =
               make_float2(myleaf0, myleaf1);
+        if (lane == 0) {
 #pragma unroll
-        for (int d = 0; d < D; ++d) {
-          const float s = sv[i * D + d];
-          dfeat[i * D + d] = ds[d] * p.tau * s * (1.f - s);
+          for (int d = 0; d < D; ++d) df[i * D + d] = ds[d] * p.tau * s[d] * (1.f - s[d]);
         }
       }
+      if (lane == 0) { df[TD] = dl[0]; df[TD + 1] = dl[1]; }
+      __syncwarp();
       // dF row [dfeat | dlogits | 0]: lanes write 2 columns each
       {
-        float c0 = 0.f, c1 = 0.f;
-#pragma unroll
-        for (int k = 0; k < TD; ++k) {
-          c0 = (2 * lane == k) ? dfeat[k] : c0;
-          c1 = (2 * lane + 1 == k) ? dfeat[k] : c1;
-        }
-        if (2 * lane == TD) c0 = dl[0];
-        if (2 * lane + 1 == TD) c1 = dl[0];
-        if (2 * lane == TD + 1) c0 = dl[1];
-        if (2 * lane + 1 == TD + 1) c1 = dl[1];
+        const float c0 = (2 * lane < TD + 2) ? df[2 * lane] : 0.f;
+        const float c1 = (2 * lane + 1 < TD + 2) ? df[2 * lane + 1] : 0.f;
         *reinterpret_cast<float2*>(p.dF + static_cast<size_t>(b) * kDFCols + 2 * lane) = make_float2(c0, c1);
         store_bf2(p.dF_hi, p.dF_lo, static_cast<size_t>(b) * kDFCols + 2 * lane, c0, c1);
       }
       // dh = sum_k dfeat[k]*alpha[k,:] + sum_c dl[c]*wb[c,:]; then the GELU/dropout backward of pre.3
+      float4 acc[NF4];
 #pragma unroll
       for (int i = 0; i < NF4; ++i) {
-        const int j = i * 128 + lane * 4;
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 w0 = wb_s[i * 32 + lane], w1 = wb_s[(H / 4) + i * 32 + lane];
+        acc[i] = make_float4(dl[0] * w0.x + dl[1] * w1.x, dl[0] * w0.y + dl[1] * w1.y, dl[0] * w0.z + dl[1] * w1.z,
+                             dl[0] * w0.w + dl[1] * w1.w);
+      }
+#pragma unroll 2
+      for (int k = 0; k < TD; ++k) {
+        const float f = df[k];
 #pragma unroll
-        for (int k = 0; k < TD; ++k) {
+        for (int i = 0; i < NF4; ++i) {
           const float4 w = alpha_s[k * (H / 4) + i * 32 + lane];
-          acc.x += dfeat[k] * w.x; acc.y += dfeat[k] * w.y; acc.z += dfeat[k] * w.z; acc.w += dfeat[k] * w.w;
+          acc[i].x += f * w.x; acc[i].y += f * w.y; acc[i].z += f * w.z; acc[i].w += f * w.w;
         }
+      }
+#pragma unroll 1
+      for (int i = 0; i < NF4; ++i) {
+        const int j = i * 128 + lane * 4;
+        float4 a = acc[0];
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          const float4 w = wb_s[c * (H / 4) + i * 32 + lane];
-          acc.x += dl[c] * w.x; acc.y += dl[c] * w.y; acc.z += dl[c] * w.z; acc.w += dl[c] * w.w;
-        }
+        for (int q = 1; q < NF4; ++q) a = (i == q) ? acc[q] : a;
         const float4 z = ldg_f4(p.z_pre1 + static_cast<size_t>(b) * H + j);
         float mm[4] = {1.f, 1.f, 1.f, 1.f};
         if (dpre.p > 0.f) dropout_mult4(dpre, pre_key, (static_cast<uint64_t>(b) * H + j) >> 2, mm);
-        acc.x *= gelu_erf_grad(z.x) * mm[0]; acc.y *= gelu_erf_grad(z.y) * mm[1];
-        acc.z *= gelu_erf_grad(z.z) * mm[2]; acc.w *= gelu_erf_grad(z.w) * mm[3];
-        store_bf2(p.dz_hi, p.dz_lo, static_cast<size_t>(b) * H + j, acc.x, acc.y);
-        store_bf2(p.dz_hi, p.dz_lo, static_cast<size_t>(b) * H + j + 2, acc.z, acc.w);
+        a.x *= gelu_erf_grad(z.x) * mm[0]; a.y *= gelu_erf_grad(z.y) * mm[1];
+        a.z *= gelu_erf_grad(z.z) * mm[2]; a.w *= gelu_erf_grad(z.w) * mm[3];
+        store_bf2(p.dz_hi, p.dz_lo, static_cast<size_t>(b) * H + j, a.x, a.y);
+        store_bf2(p.dz_hi, p.dz_lo, static_cast<size_t>(b) * H + j + 2, a.z, a.w);
       }
+      __syncwarp();
     }
   }
 }
