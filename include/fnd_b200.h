@@ -157,6 +157,13 @@ int fnd_gemm_bf16(const void* a_hi, const void* a_lo, int a_pitch, int a_mn, con
                   int b_pitch, int b_mn, float* c, int c_pitch, int M, int N, int K, int bn, int splits, int ncombo,
                   void* scratch, size_t scratch_bytes, void* stream);
 
+/* Probe variant: launches the kernel `reps` times back to back and, when `stamps` is non-NULL, has every CTA record
+ * eight clock64() stamps into stamps[cta*8 + i] (0 start, 1 setup done, 2 first operands landed, 3 last MMA issued,
+ * 4 accumulator ready, 5 split-K exchange done, 6 epilogue done, 7 all warps done). Used by tools/gemm_probe.py. */
+int fnd_gemm_bf16_probe(const void* a_hi, const void* a_lo, int a_pitch, int a_mn, const void* b_hi, const void* b_lo,
+                        int b_pitch, int b_mn, float* c, int c_pitch, int M, int N, int K, int bn, int splits,
+                        int ncombo, void* scratch, size_t scratch_bytes, void* stream, long long* stamps, int reps);
+
 #ifdef __cplusplus
 }
 #endif

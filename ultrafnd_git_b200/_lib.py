@@ -134,6 +134,9 @@ def _signatures() -> Dict[str, tuple]:
         "fnd_export_dropout_mask": (_c_int, [_c_void_p, _c_int, _c_void_p, ll, _c_void_p]),
         "fnd_check_error": (_c_int, [_c_void_p, _c_void_p]),
         "fnd_gemm_scratch_bytes": (_c_size_t, [_c_int] * 4),
+        "fnd_gemm_bf16_probe": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_void_p, _c_void_p, _c_int, _c_int,
+                                         _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,
+                                         _c_void_p, _c_size_t, _c_void_p, _c_void_p, _c_int]),
         "fnd_gemm_bf16": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_void_p, _c_void_p, _c_int, _c_int,
                                    _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,
                                    _c_void_p, _c_size_t, _c_void_p]),

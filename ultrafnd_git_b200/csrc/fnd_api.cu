@@ -248,15 +248,6 @@ static int upload_tables(Plan& P, cudaStream_t st) {
   uint8_t* base = P.buf<uint8_t>("tables");
   size_t off = 0;
   const size_t cap = static_cast<size_t>(P.bufs["tables"].bytes);
-  GemmTable* all[] = {&P.fwd_proj, &P.fwd_qkv, &P.fwd_f0, &P.fwd_f1, &P.fwd_p0, &P.fwd_p1, &P.dg_p1, &P.dg_p0_fused,
-                      &P.dg_p0_split, &P.dg_f1, &P.dg_f0, &P.dg_qkv, &P.wg_all, &P.wg_clf, &P.wg_fus};
-  for (GemmTable* T : all) {
-    const size_t bytes = T->host.size() * sizeof(GemmProblem);
-    if (off + bytes > cap) return -32;
-    T->dev = reinterpret_cast<GemmProblem*>(base + off);
-    FND_CUDA_OK(cudaMemcpyAsync(T->dev, T->host.data(), bytes, cudaMemcpyHostToDevice, st));
-    off = align_up(off + bytes, 256);
-  }
   FinTable* fins[] = {&P.fin_all, &P.fin_clf, &P.fin_fus};
   for (FinTable* T : fins) {
     const size_t bytes = T->host.size() * sizeof(FinJob);
@@ -277,6 +268,7 @@ static inline RunCtx make_ctx(const Plan& P, int training) {
   c.err = &S->err;
   c.rng = S->rng;
   c.training = training;
+  c.dbg = nullptr;
   return c;
 }
 static void mark(const Plan& Pc, const char* name, cudaStream_t st) {
@@ -288,7 +280,7 @@ static void mark(const Plan& Pc, const char* name, cudaStream_t st) {
   P.marks.emplace_back(name, ev);
 }
 static int run_gemm(const Plan& P, const GemmTable& T, int training, cudaStream_t st, const char* name) {
-  FND_CUDA_OK(launch_gemm(T.kind, T.dev, static_cast<int>(T.host.size()), T.grid, make_ctx(P, training), st));
+  FND_CUDA_OK(launch_gemm(T.kind, T.host.data(), static_cast<int>(T.host.size()), T.grid, make_ctx(P, training), st));
   mark(P, name, st);
   return 0;
 }
@@ -818,9 +810,28 @@ size_t fnd_gemm_scratch_bytes(int M, int N, int bn, int splits) {
   return b + 256;
 }
 
+static int gemm_bf16_impl(const void* a_hi, const void* a_lo, int a_pitch, int a_mn, const void* b_hi, const void* b_lo,
+                          int b_pitch, int b_mn, float* c, int c_pitch, int M, int N, int K, int bn, int splits, int ncombo,
+                          void* scratch, size_t scratch_bytes, void* stream, long long* stamps, int reps);
+
 int fnd_gemm_bf16(const void* a_hi, const void* a_lo, int a_pitch, int a_mn, const void* b_hi, const void* b_lo,
                   int b_pitch, int b_mn, float* c, int c_pitch, int M, int N, int K, int bn, int splits, int ncombo,
                   void* scratch, size_t scratch_bytes, void* stream) {
+  return gemm_bf16_impl(a_hi, a_lo, a_pitch, a_mn, b_hi, b_lo, b_pitch, b_mn, c, c_pitch, M, N, K, bn, splits, ncombo,
+                        scratch, scratch_bytes, stream, nullptr, 1);
+}
+
+int fnd_gemm_bf16_probe(const void* a_hi, const void* a_lo, int a_pitch, int a_mn, const void* b_hi, const void* b_lo,
+                        int b_pitch, int b_mn, float* c, int c_pitch, int M, int N, int K, int bn, int splits, int ncombo,
+                        void* scratch, size_t scratch_bytes, void* stream, long long* stamps, int reps) {
+  return gemm_bf16_impl(a_hi, a_lo, a_pitch, a_mn, b_hi, b_lo, b_pitch, b_mn, c, c_pitch, M, N, K, bn, splits, ncombo,
+                        scratch, scratch_bytes, stream, stamps, reps);
+}
+}  // extern "C"
+
+static int gemm_bf16_impl(const void* a_hi, const void* a_lo, int a_pitch, int a_mn, const void* b_hi, const void* b_lo,
+                          int b_pitch, int b_mn, float* c, int c_pitch, int M, int N, int K, int bn, int splits, int ncombo,
+                          void* scratch, size_t scratch_bytes, void* stream, long long* stamps, int reps) {
   if (!a_hi || !b_hi || !c || !scratch) return -1;
   if (scratch_bytes < fnd_gemm_scratch_bytes(M, N, bn, splits)) return -2;
   if ((reinterpret_cast<uintptr_t>(scratch) & 255) != 0) return -3;
@@ -846,14 +857,12 @@ int fnd_gemm_bf16(const void* a_hi, const void* a_lo, int a_pitch, int a_mn, con
   const int grid = finish_table(&hp, 1);
   FND_CUDA_OK(init_gemm_attrs());
   FND_CUDA_OK(cudaMemsetAsync(derr, 0, 256 + ctr_bytes, st));
-  FND_CUDA_OK(cudaMemcpyAsync(dtab, &hp, sizeof(hp), cudaMemcpyHostToDevice, st));
-  RunCtx ctx{derr, nullptr, 0};
+  RunCtx ctx{derr, nullptr, 0, stamps};
   const int kind = (a_mn ? (b_mn ? 2 : 3) : (b_mn ? 1 : 0));
-  FND_CUDA_OK(launch_gemm(kind, dtab, 1, grid, ctx, st));
+  (void)dtab;
+  for (int r = 0; r < (reps < 1 ? 1 : reps); ++r) FND_CUDA_OK(launch_gemm(kind, &hp, 1, grid, ctx, st));
   int herr = 0;
   FND_CUDA_OK(cudaMemcpyAsync(&herr, derr, sizeof(int), cudaMemcpyDeviceToHost, st));
   FND_CUDA_OK(cudaStreamSynchronize(st));
   return herr;
 }
-
-}  // extern "C"

@@ -71,7 +71,7 @@ struct alignas(128) GemmProblem {
   int ncombo;                        // 1 bf16, 3 fp32x3
   int bn;                            // tile width: 32/64/128 (MN-major B: 64/128)
   unsigned long long hintA, hintB;   // L2 eviction hints for the two operand streams
-  float* splitk_ws;                  // [tiles][splits][128][bn] fp32
+  float* splitk_ws;                  // [tiles][splits][bn/8][128][8] fp32
   int* splitk_ctr;                   // [tiles], zero between launches
   EpiParams epi;
 };
@@ -80,13 +80,25 @@ struct RunCtx {
   int* err;                          // device error flag
   const uint32_t* rng;               // [0] seed lo, [1] seed hi, [2] fusion salt, [3] classifier salt
   int training;                      // 0: every dropout (forward masks and backward gates) is the identity
+  long long* dbg;                    // optional [grid][8] clock64 stamps (probe builds only; null in production)
 };
+#define FND_STAMP(i) do { if (ctx.dbg) ctx.dbg[static_cast<size_t>(blockIdx.x) * 8 + (i)] = clock64(); } while (0)
 
 __device__ __forceinline__ void epi_named_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
-template <bool A_MN, bool B_MN>
+// The problem table travels BY VALUE in kernel-parameter space (constant bank): no global-memory fetch of table or
+// TMA descriptors sits on the critical path of a launch (after an L2 flush those were two dependent HBM round trips).
+template <int CAP>
+struct GemmTableP {
+  GemmProblem p[CAP];
+  int nprob;
+};
+
+template <bool A_MN, bool B_MN, int CAP>
 __global__ void __launch_bounds__(kGemmThreads, 1)
-fnd_gemm_kernel(const GemmProblem* __restrict__ probs, int nprob, RunCtx ctx) {
+fnd_gemm_kernel(const __grid_constant__ GemmTableP<CAP> tbl, RunCtx ctx) {
+  const GemmProblem* probs = tbl.p;
+  const int nprob = tbl.nprob;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kGemmStages * kGemmStageBytes);
@@ -98,6 +110,7 @@ fnd_gemm_kernel(const GemmProblem* __restrict__ probs, int nprob, RunCtx ctx) {
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) FND_STAMP(0);
 
   // ---- locate this CTA's work item ----
   int pi = 0;
@@ -140,6 +153,7 @@ fnd_gemm_kernel(const GemmProblem* __restrict__ probs, int nprob, RunCtx ctx) {
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) FND_STAMP(1);
 
   if (warp == 0) {
     // ================= TMA producer =================
@@ -182,6 +196,7 @@ fnd_gemm_kernel(const GemmProblem* __restrict__ probs, int nprob, RunCtx ctx) {
         const uint32_t ph = static_cast<uint32_t>(it / kGemmStages) & 1u;
         ok = mbar_wait(&full_bar[s], ph, ctx.err, FND_DEV_TIMEOUT_MMA);
         if (!ok) break;
+        if (it == 0) FND_STAMP(2);
         tc_fence_after_sync();
         const uint32_t aBase = smem_u32(smem + s * kGemmStageBytes);
         const uint32_t bBase = aBase + kGemmStageBytesA;
@@ -198,43 +213,63 @@ fnd_gemm_kernel(const GemmProblem* __restrict__ probs, int nprob, RunCtx ctx) {
         umma_commit(&empty_bar[s]);      // frees the smem stage once these MMAs retire
       }
       umma_commit(accum_bar);            // accumulator complete
+      FND_STAMP(3);
     }
     __syncwarp();
   } else {
     // ================= epilogue (warps 2..5) =================
     // Deliberately ROLLED (8 columns per iteration, #pragma unroll 1): a fully unrolled epilogue was ~100 KB of
     // straight-line SASS and made every small launch instruction-fetch bound (~25 us fixed cost, measured).
-    const EpiParams& E = P.epi;
+    // By VALUE: the inline-asm tcgen05/mbarrier wrappers carry "memory" clobbers, so fields read through a pointer
+    // into the problem table were re-loaded from global memory after every one of them (measured: ~0.7 us per
+    // 8-column group). Registers are plentiful here (accumulators live in TMEM).
+    const EpiParams E = P.epi;
+    const int PM = P.M, PN = P.N;
+    float* const ws_base = P.splitk_ws;
+    int* const ctr_base = P.splitk_ctr;
     const int lane_grp = warp & 3;                 // TMEM lane quarter this warp may access
     const int row = lane_grp * 32 + lane;
     const int m = tm * kGemmBM + row;
-    const bool row_ok = m < P.M;
+    const bool row_ok = m < PM;
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16);
     const int ngroups = bn / 8;
     const int epi_tid = threadIdx.x - 64;
+    // While the main loop runs, pull the epilogue's global operands towards L2 (they are cold after the optimizer
+    // has streamed ~0.5 GB through the cache): this thread's row of add_in / gate_z, and the tile's bias slice.
+    if (row_ok) {
+      const int nb = tn * bn;
+      if (E.gate_z)
+        for (int c = 0; c < bn; c += 32) prefetch_l2(E.gate_z + static_cast<size_t>(m) * E.gate_pitch + nb + c);
+      if (E.add_in)
+        for (int c = 0; c < bn; c += 32) prefetch_l2(E.add_in + static_cast<size_t>(m) * E.add_pitch + nb + c);
+      if (E.bias && row * 32 < bn) prefetch_l2(E.bias + nb + row * 32);
+    }
     bool proceed = mbar_wait(accum_bar, 0u, ctx.err, FND_DEV_TIMEOUT_EPILOGUE);
     tc_fence_after_sync();
+    if (epi_tid == 0) FND_STAMP(4);
 
     float* ws_tile = nullptr;
     if (splits > 1) {
-      ws_tile = P.splitk_ws + static_cast<size_t>(tile) * splits * (kGemmBM * bn);
-      float* mine = ws_tile + static_cast<size_t>(split) * (kGemmBM * bn) + static_cast<size_t>(row) * bn;
+      ws_tile = ws_base + static_cast<size_t>(tile) * splits * (kGemmBM * bn);
+      // partial layout [split][group][row][8]: a warp's 32 rows of one group are 1 KB contiguous, so both this
+      // write and the fix-up read below are fully coalesced
+      float* mine = ws_tile + static_cast<size_t>(split) * (kGemmBM * bn) + static_cast<size_t>(row) * 8;
 #pragma unroll 1
       for (int g = 0; g < ngroups; ++g) {
         uint32_t r[8];
         tmem_ld_32x8(taddr + g * 8, r);
         tmem_ld_wait();
-        __stcg(reinterpret_cast<float4*>(mine + g * 8),
+        __stcg(reinterpret_cast<float4*>(mine + g * (kGemmBM * 8)),
                make_float4(__uint_as_float(r[0]), __uint_as_float(r[1]), __uint_as_float(r[2]), __uint_as_float(r[3])));
-        __stcg(reinterpret_cast<float4*>(mine + g * 8 + 4),
+        __stcg(reinterpret_cast<float4*>(mine + g * (kGemmBM * 8) + 4),
                make_float4(__uint_as_float(r[4]), __uint_as_float(r[5]), __uint_as_float(r[6]), __uint_as_float(r[7])));
       }
       __threadfence();
       epi_named_barrier();
       if (epi_tid == 0) {
-        const int old = atomicAdd(&P.splitk_ctr[tile], 1);
+        const int old = atomicAdd(&ctr_base[tile], 1);
         const int last = (old == splits - 1) ? 1 : 0;
-        if (last) P.splitk_ctr[tile] = 0;     // re-arm for the next launch (graph replay safe)
+        if (last) ctr_base[tile] = 0;         // re-arm for the next launch (graph replay safe)
         *last_flag = last;
       }
       epi_named_barrier();
@@ -242,6 +277,7 @@ fnd_gemm_kernel(const GemmProblem* __restrict__ probs, int nprob, RunCtx ctx) {
       if (proceed) __threadfence();
     }
 
+    if (epi_tid == 0) FND_STAMP(5);
     float ss = 0.f;
     if (proceed) {
       const uint64_t seed = ctx.rng ? ((static_cast<uint64_t>(ctx.rng[1]) << 32) | ctx.rng[0]) : 0ull;
@@ -260,12 +296,26 @@ fnd_gemm_kernel(const GemmProblem* __restrict__ probs, int nprob, RunCtx ctx) {
         if (splits > 1) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) v[j] = 0.f;
+          // fixed split order => deterministic sum; loads are issued four splits at a time so the L2 round trips
+          // overlap instead of serialising (16 dependent trips per group made fuse_mlp.0 a 100 us kernel)
+          const float* src0 = ws_tile + static_cast<size_t>(g) * (kGemmBM * 8) + static_cast<size_t>(row) * 8;
+          const size_t sstride = static_cast<size_t>(kGemmBM) * bn;
 #pragma unroll 1
-          for (int s2 = 0; s2 < splits; ++s2) {        // fixed split order => deterministic sum
-            const float* src = ws_tile + static_cast<size_t>(s2) * (kGemmBM * bn) + static_cast<size_t>(row) * bn + g * 8;
-            const float4 t0 = ldcg_f4(src), t1 = ldcg_f4(src + 4);
-            v[0] += t0.x; v[1] += t0.y; v[2] += t0.z; v[3] += t0.w;
-            v[4] += t1.x; v[5] += t1.y; v[6] += t1.z; v[7] += t1.w;
+          for (int s2 = 0; s2 < splits; s2 += 4) {
+            float4 t[8];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const bool okq = s2 + q < splits;
+              const float* src = src0 + static_cast<size_t>(okq ? s2 + q : s2) * sstride;
+              t[2 * q] = ldcg_f4(src);
+              t[2 * q + 1] = ldcg_f4(src + 4);
+              if (!okq) { t[2 * q] = make_float4(0.f, 0.f, 0.f, 0.f); t[2 * q + 1] = t[2 * q]; }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              v[0] += t[2 * q].x; v[1] += t[2 * q].y; v[2] += t[2 * q].z; v[3] += t[2 * q].w;
+              v[4] += t[2 * q + 1].x; v[5] += t[2 * q + 1].y; v[6] += t[2 * q + 1].z; v[7] += t[2 * q + 1].w;
+            }
           }
         } else {
           uint32_t r[8];
@@ -275,7 +325,7 @@ fnd_gemm_kernel(const GemmProblem* __restrict__ probs, int nprob, RunCtx ctx) {
           for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[j]);
         }
         const int n0 = tn * bn + g * 8;
-        if (!row_ok || n0 >= P.N) continue;          // N is a multiple of 8 (checked on the host)
+        if (!row_ok || n0 >= PN) continue;           // N is a multiple of 8 (checked on the host)
 
         if (E.bias) {
           const float4 b0 = ldg_f4(E.bias + n0), b1 = ldg_f4(E.bias + n0 + 4);
@@ -304,7 +354,7 @@ fnd_gemm_kernel(const GemmProblem* __restrict__ probs, int nprob, RunCtx ctx) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) v[j] = gelu_erf(v[j]);
         }
-        const uint64_t e0 = static_cast<uint64_t>(m) * static_cast<uint64_t>(P.N) + n0;   // multiple of 8
+        const uint64_t e0 = static_cast<uint64_t>(m) * static_cast<uint64_t>(PN) + n0;   // multiple of 8
         if (dfw.p > 0.f) {
           float mm[4];
           dropout_mult4(dfw, key_fw, e0 >> 2, mm);
@@ -369,8 +419,10 @@ fnd_gemm_kernel(const GemmProblem* __restrict__ probs, int nprob, RunCtx ctx) {
     }
   }
 
+  if (threadIdx.x == 64) FND_STAMP(6);
   tc_fence_before_sync();
   __syncthreads();
+  if (threadIdx.x == 0) FND_STAMP(7);
   if (warp == 1) {
     tc_fence_after_sync();
     tmem_dealloc(tmem_base, kGemmTmemCols);
