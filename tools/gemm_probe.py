@@ -26,13 +26,16 @@ for (M, N, K, a_mn, b_mn, bn, splits) in CASES:
     grid = tiles * ((kb + kps - 1) // kps)
     stamps = torch.zeros(grid * 8, dtype=torch.int64, device=dev)
     st = torch.cuda.current_stream().cuda_stream
-    for reps in (1, 1, 1):
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    for cold in (0, 1):
+      for reps in (1, 1, 1):
+        if cold:
+            flush.zero_()
         lib.fnd_gemm_bf16_probe(A.data_ptr(), A.data_ptr(), A.shape[1], a_mn, B.data_ptr(), B.data_ptr(), B.shape[1], b_mn,
                                 C.data_ptr(), N, M, N, K, bn, splits, 1, sp, nb, st, stamps.data_ptr(), 1)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    t = stamps.view(grid, 8).cpu().double()
-    d = (t - t[:, :1]) / 1.965e3   # us at 1965 MHz
-    names = ["start", "setup", "first_full", "mma_issued", "accum_ready", "splitk_done", "epi_done", "all_done"]
-    print(f"case M{M} N{N} K{K} a{a_mn} b{b_mn} bn{bn} s{splits} grid {grid}: median us since CTA start:",
-          {n: round(float(d[:, i].median()), 2) for i, n in enumerate(names)}, " max all_done", round(float(d[:, 7].max()), 2))
+      torch.cuda.synchronize()
+      t = stamps.view(grid, 8).cpu().double()
+      d = (t - t[:, :1]) / 1.965e3   # us at 1965 MHz
+      names = ["start", "setup", "first_full", "mma_issued", "accum_ready", "splitk_done", "epi_done", "all_done"]
+      print(f"case M{M} N{N} K{K} a{a_mn} b{b_mn} bn{bn} s{splits} grid {grid} {'COLD' if cold else 'hot '}: median us:",
+            {n: round(float(d[:, i].median()), 2) for i, n in enumerate(names[1:7], 1)}, " max epi_done", round(float(d[:, 6].max()), 2))

@@ -246,8 +246,8 @@ inline void carve(Plan& P) {
   (void)TD;
   // split-K workspaces / counters for the two skinny weight-streaming GEMMs (fuse_mlp.0, fuse_mlp.3)
   const int tm = ceil_div(P.B, kGemmBM);
-  P.splits_f0 = pick_splits(tm * (2 * P.H / 64), P.nslots * P.H / kGemmBK, 296);
-  P.splits_f1 = pick_splits(tm * (P.H / 64), 2 * P.H / kGemmBK, 296);
+  P.splits_f0 = pick_splits(tm * (2 * P.H / 64), P.nslots * P.H / kGemmBK, 148);
+  P.splits_f1 = pick_splits(tm * (P.H / 64), 2 * P.H / kGemmBK, 148);
   if (P.splits_f0 > 1) {
     plan_add(P, "splitws_f0", static_cast<long long>(splitk_ws_floats(P.B, 2 * P.H, 64, P.splits_f0)) * 4);
     plan_add(P, "splitctr_f0", static_cast<long long>(tm) * (2 * P.H / 64) * 4);

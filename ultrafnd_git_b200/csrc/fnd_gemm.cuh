@@ -88,17 +88,20 @@ __device__ __forceinline__ void epi_named_barrier() { asm volatile("bar.sync 1, 
 
 // The problem table travels BY VALUE in kernel-parameter space (constant bank): no global-memory fetch of table or
 // TMA descriptors sits on the critical path of a launch (after an L2 flush those were two dependent HBM round trips).
-template <int CAP>
+// ONE kernel binary serves forward, dgrad and wgrad (operand majorness is a launch-uniform runtime flag): a training
+// step issues 13 GEMM launches, and sharing the code keeps it warm in the instruction caches between them.
+constexpr int kGemmTableCap = 16;
 struct GemmTableP {
-  GemmProblem p[CAP];
+  GemmProblem p[kGemmTableCap];
   int nprob;
+  int a_mn, b_mn;     // 0: K-major, 1: MN-major
 };
 
-template <bool A_MN, bool B_MN, int CAP>
 __global__ void __launch_bounds__(kGemmThreads, 1)
-fnd_gemm_kernel(const __grid_constant__ GemmTableP<CAP> tbl, RunCtx ctx) {
+fnd_gemm_kernel(const __grid_constant__ GemmTableP tbl, RunCtx ctx) {
   const GemmProblem* probs = tbl.p;
   const int nprob = tbl.nprob;
+  const bool A_MN = tbl.a_mn != 0, B_MN = tbl.b_mn != 0;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kGemmStages * kGemmStageBytes);
@@ -190,6 +193,8 @@ fnd_gemm_kernel(const __grid_constant__ GemmTableP<CAP> tbl, RunCtx ctx) {
     // ================= MMA issuer =================
     if (lane == 0) {
       const uint32_t idesc = make_idesc_bf16(kGemmBM, bn, A_MN ? 1 : 0, B_MN ? 1 : 0);
+      const uint32_t kstepA = A_MN ? 2048u : 32u, kstepB = B_MN ? 2048u : 32u;
+      const uint32_t lboA = A_MN ? 8192u : 16u, lboB = B_MN ? 8192u : 16u;
       bool ok = true;
       for (int it = 0; it < iters && ok; ++it) {
         const int s = it % kGemmStages;
@@ -204,10 +209,8 @@ fnd_gemm_kernel(const __grid_constant__ GemmTableP<CAP> tbl, RunCtx ctx) {
         for (int k = 0; k < kGemmBK / 16; ++k) {
           // K-major: 16 contraction elements = 32 B inside the 128-B swizzled row.
           // MN-major: 16 contraction rows of 128 B = 2048 B (two 8-row swizzle atoms).
-          const uint64_t ad = A_MN ? make_smem_desc_sw128(aBase + k * 2048, 8192, 1024)
-                                   : make_smem_desc_sw128(aBase + k * 32, 16, 1024);
-          const uint64_t bd = B_MN ? make_smem_desc_sw128(bBase + k * 2048, 8192, 1024)
-                                   : make_smem_desc_sw128(bBase + k * 32, 16, 1024);
+          const uint64_t ad = make_smem_desc_sw128(aBase + k * kstepA, lboA, 1024);
+          const uint64_t bd = make_smem_desc_sw128(bBase + k * kstepB, lboB, 1024);
           umma_f16(tmem_base, ad, bd, idesc, (it | k) != 0 ? 1u : 0u);
         }
         umma_commit(&empty_bar[s]);      // frees the smem stage once these MMAs retire
@@ -296,15 +299,15 @@ fnd_gemm_kernel(const __grid_constant__ GemmTableP<CAP> tbl, RunCtx ctx) {
         if (splits > 1) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) v[j] = 0.f;
-          // fixed split order => deterministic sum; loads are issued four splits at a time so the L2 round trips
+          // fixed split order => deterministic sum; loads are issued eight splits at a time so the L2 round trips
           // overlap instead of serialising (16 dependent trips per group made fuse_mlp.0 a 100 us kernel)
           const float* src0 = ws_tile + static_cast<size_t>(g) * (kGemmBM * 8) + static_cast<size_t>(row) * 8;
           const size_t sstride = static_cast<size_t>(kGemmBM) * bn;
 #pragma unroll 1
-          for (int s2 = 0; s2 < splits; s2 += 4) {
-            float4 t[8];
+          for (int s2 = 0; s2 < splits; s2 += 8) {
+            float4 t[16];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
+            for (int q = 0; q < 8; ++q) {
               const bool okq = s2 + q < splits;
               const float* src = src0 + static_cast<size_t>(okq ? s2 + q : s2) * sstride;
               t[2 * q] = ldcg_f4(src);
@@ -312,7 +315,7 @@ fnd_gemm_kernel(const __grid_constant__ GemmTableP<CAP> tbl, RunCtx ctx) {
               if (!okq) { t[2 * q] = make_float4(0.f, 0.f, 0.f, 0.f); t[2 * q + 1] = t[2 * q]; }
             }
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
+            for (int q = 0; q < 8; ++q) {
               v[0] += t[2 * q].x; v[1] += t[2 * q].y; v[2] += t[2 * q].z; v[3] += t[2 * q].w;
               v[4] += t[2 * q + 1].x; v[5] += t[2 * q + 1].y; v[6] += t[2 * q + 1].z; v[7] += t[2 * q + 1].w;
             }

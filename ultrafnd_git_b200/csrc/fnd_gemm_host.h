@@ -69,53 +69,25 @@ inline int finish_table(GemmProblem* probs, int n) {
   return c;
 }
 
-// Opt every GEMM variant into its dynamic shared-memory size (per device; called at bind time so that no
-// attribute call ever happens inside a stream capture).
-template <bool A_MN, bool B_MN>
-inline cudaError_t init_gemm_attrs_t() {
-  cudaError_t e;
-  e = cudaFuncSetAttribute(fnd_gemm_kernel<A_MN, B_MN, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes);
-  if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(fnd_gemm_kernel<A_MN, B_MN, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes);
-  if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(fnd_gemm_kernel<A_MN, B_MN, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes);
-}
+// Opt the GEMM kernel into its dynamic shared-memory size (per device; called at bind time so that no attribute
+// call ever happens inside a stream capture).
 inline cudaError_t init_gemm_attrs() {
-  cudaError_t e;
-  if ((e = init_gemm_attrs_t<false, false>()) != cudaSuccess) return e;
-  if ((e = init_gemm_attrs_t<false, true>()) != cudaSuccess) return e;
-  if ((e = init_gemm_attrs_t<true, true>()) != cudaSuccess) return e;
-  return init_gemm_attrs_t<true, false>();
+  return cudaFuncSetAttribute(fnd_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes);
 }
 
-template <bool A_MN, bool B_MN, int CAP>
-inline cudaError_t launch_gemm_c(const GemmProblem* host_table, int nprob, int grid, RunCtx ctx, cudaStream_t st) {
-  GemmTableP<CAP> t;
-  memcpy(t.p, host_table, sizeof(GemmProblem) * nprob);
-  t.nprob = nprob;
-  fnd_gemm_kernel<A_MN, B_MN, CAP><<<grid, kGemmThreads, kGemmSmemBytes, st>>>(t, ctx);
-  return cudaGetLastError();
-}
-template <bool A_MN, bool B_MN>
-inline cudaError_t launch_gemm_t(const GemmProblem* host_table, int nprob, int grid, RunCtx ctx, cudaStream_t st) {
-  if (nprob <= 1) return launch_gemm_c<A_MN, B_MN, 1>(host_table, nprob, grid, ctx, st);
-  if (nprob <= 5) return launch_gemm_c<A_MN, B_MN, 5>(host_table, nprob, grid, ctx, st);
-  if (nprob <= 16) return launch_gemm_c<A_MN, B_MN, 16>(host_table, nprob, grid, ctx, st);
-  return cudaErrorInvalidValue;
-}
-
-// kind: 0 = forward (A K-major, B K-major); 1 = dgrad (A K-major, B MN-major); 2 = wgrad (both MN-major).
-// `host_table` is copied into the kernel's parameter space at launch.
+// kind: 0 = forward (A K-major, B K-major); 1 = dgrad (A K-major, B MN-major); 2 = wgrad (both MN-major);
+// 3 = (A MN-major, B K-major). `host_table` is copied into the kernel's parameter space at launch.
 inline cudaError_t launch_gemm(int kind, const GemmProblem* host_table, int nprob, int grid, RunCtx ctx,
                                cudaStream_t st) {
   if (grid <= 0) return cudaSuccess;
-  switch (kind) {
-    case 0: return launch_gemm_t<false, false>(host_table, nprob, grid, ctx, st);
-    case 1: return launch_gemm_t<false, true>(host_table, nprob, grid, ctx, st);
-    case 2: return launch_gemm_t<true, true>(host_table, nprob, grid, ctx, st);
-    case 3: return launch_gemm_t<true, false>(host_table, nprob, grid, ctx, st);
-    default: return cudaErrorInvalidValue;
-  }
+  if (nprob < 1 || nprob > kGemmTableCap || kind < 0 || kind > 3) return cudaErrorInvalidValue;
+  GemmTableP t;
+  memcpy(t.p, host_table, sizeof(GemmProblem) * nprob);
+  t.nprob = nprob;
+  t.a_mn = (kind == 2 || kind == 3) ? 1 : 0;
+  t.b_mn = (kind == 1 || kind == 2) ? 1 : 0;
+  fnd_gemm_kernel<<<grid, kGemmThreads, kGemmSmemBytes, st>>>(t, ctx);
+  return cudaGetLastError();
 }
 
 }  // namespace fnd

@@ -53,12 +53,13 @@ __global__ void __launch_bounds__(256) adamw_kernel(AdamWParams a) {
   const float decay = 1.0f - lr * S->weight_decay;
   const float step_size = lr / S->bc1;
   const float inv_sqrt_bc2 = rsqrtf(S->bc2);
+  const uint64_t pol = l2_policy_evict_first();
   for (size_t i = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 4; i < a.n;
        i += static_cast<size_t>(gridDim.x) * blockDim.x * 4) {
-    float4 p = *reinterpret_cast<const float4*>(a.p + i);
-    const float4 g4 = __ldcs(reinterpret_cast<const float4*>(a.g + i));
-    float4 m = *reinterpret_cast<const float4*>(a.m + i);
-    float4 v = *reinterpret_cast<const float4*>(a.v + i);
+    float4 p = ld_f4_policy(a.p + i, pol);
+    const float4 g4 = ld_f4_policy(a.g + i, pol);
+    float4 m = ld_f4_policy(a.m + i, pol);
+    float4 v = ld_f4_policy(a.v + i, pol);
     float* pp = &p.x; float* mp = &m.x; float* vp = &v.x; const float* gp = &g4.x;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
@@ -69,9 +70,9 @@ __global__ void __launch_bounds__(256) adamw_kernel(AdamWParams a) {
       const float denom = sqrtf(vp[q]) * inv_sqrt_bc2 + eps;
       pp[q] -= step_size * (mp[q] / denom);
     }
-    *reinterpret_cast<float4*>(a.p + i) = p;
-    *reinterpret_cast<float4*>(a.m + i) = m;
-    *reinterpret_cast<float4*>(a.v + i) = v;
+    st_f4_policy(a.p + i, p, pol);
+    st_f4_policy(a.m + i, m, pol);
+    st_f4_policy(a.v + i, v, pol);
     shadow_store4(a, i, p);
   }
 }
