@@ -9,6 +9,7 @@
 #include "../../include/fnd_b200.h"
 #include "fnd_gemm_host.h"
 #include "fnd_optim.cuh"
+#include <cstdlib>
 #include <map>
 #include <string>
 #include <vector>
@@ -256,6 +257,7 @@ inline void carve(Plan& P) {
     plan_add(P, "splitws_f1", static_cast<long long>(splitk_ws_floats(P.B, P.H, 64, P.splits_f1)) * 4);
     plan_add(P, "splitctr_f1", static_cast<long long>(tm) * (P.H / 64) * 4);
   }
+  if (getenv("FND_DEBUG_STAMPS")) plan_add(P, "dbg", 8 * 8 * 4096);     // clock64 stamps of the row kernels (probes)
   // per-CTA sum-of-squares slots (wgrad CTAs + finalize CTAs); generous upper bound, zero-initialised at bind
   plan_add(P, "slots", 16384 * 4);
   // device copies of the kernel tables

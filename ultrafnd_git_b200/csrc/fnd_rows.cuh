@@ -438,153 +438,173 @@ struct HeadParams {
   __nv_bfloat16* dz_lo;
   const DevState* state;
   int B, H, T, D;
+  long long* dbg;            // optional [grid][8] clock64 stamps (probe only)
 };
+#define FND_HSTAMP(i) do { if (p.dbg && threadIdx.x == 0) p.dbg[static_cast<size_t>(blockIdx.x) * 8 + (i)] = clock64(); } while (0)
 
-// Tree shape is a compile-time parameter (T trees of depth D: the reference ships 6 x 4, classifier.yaml:12-14).
-// alpha [TD,H] and the bypass weight [2,H] are staged once per CTA in shared memory; each warp then walks rows
-// b = blockIdx*8 + warp, += gridDim*8. Per-row routing probabilities / feature gradients sit in per-warp shared
-// memory so the tree loops can stay ROLLED: the fully unrolled version was >110 KB of SASS and instruction-fetch
-// bound (33 us for 128 rows).
+// Tree shape is a compile-time parameter (T <= 8 trees of depth 4: the reference ships 6 x 4, classifier.yaml:12-14).
+// One warp per row; alpha [TD,H] | bypass weight [2,H] are staged once per CTA in shared memory as one [TD+2, H] matrix.
+// Lane-parallel layout (a straight per-lane port of the reference's loops took 22 us for 128 rows, measured):
+//   * the TD+2 dot products: every lane accumulates all TD+2 partial sums over its H/32 elements, the partials are
+//     transposed through a padded per-warp smem tile and lane k finishes dot k (and its sigmoid) — no shuffle chains;
+//   * the trees: lane = (tree = lane>>2, leaf quarter = lane&3), 4 leaves per lane, xor-shuffles to combine.
 template <bool FWD, bool CE, bool BWD, int NF4, int T, int D>   // NF4 = H/128 float4 per lane
 __global__ void __launch_bounds__(256) head_kernel(HeadParams p) {
-  constexpr int TD = T * D, L = 1 << D, H = NF4 * 128;
+  static_assert(D == 4 && T <= 8, "lane mapping assumes depth 4 and at most 8 trees");
+  constexpr int TD = T * D, L = 1 << D, H = NF4 * 128, NR = TD + 2;
   extern __shared__ float4 head_smem[];
-  float4* alpha_s = head_smem;                     // [TD][H/4]
-  float4* wb_s = head_smem + TD * (H / 4);         // [2][H/4]
-  __shared__ float leaf[T * L * 2];                // leaf tables and thresholds: broadcast reads
+  const float4* rows_s = head_smem;                            // [NR][H/4]: alpha rows then the 2 bypass rows
+  float* part_all = reinterpret_cast<float*>(head_smem + NR * (H / 4));   // [8 warps][NR][33]
+  __shared__ float leaf[T * L * 2];
   __shared__ float thr[TD];
-  __shared__ float sv_all[8][TD];                  // per-warp sigmoid outputs of the current row
-  __shared__ float df_all[8][TD + 2];              // per-warp dfeat | dlogits of the current row
+  __shared__ float sv_all[8][TD];
+  __shared__ float df_all[8][TD + 2];
+  __shared__ float byp_all[8][2];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
+  float* part = part_all + warp * (NR * 33);
   float* sv = sv_all[warp];
   float* df = df_all[warp];
-  for (int i = threadIdx.x; i < TD * (H / 4); i += 256) alpha_s[i] = ldg_f4(p.alpha + 4 * i);
-  for (int i = threadIdx.x; i < 2 * (H / 4); i += 256) wb_s[i] = ldg_f4(p.wb + 4 * i);
+  FND_HSTAMP(0);
+  {
+    float4* dst = head_smem;
+#pragma unroll 4
+    for (int i = threadIdx.x; i < TD * (H / 4); i += 256) dst[i] = ldg_f4(p.alpha + 4 * i);
+    for (int i = threadIdx.x; i < 2 * (H / 4); i += 256) dst[TD * (H / 4) + i] = ldg_f4(p.wb + 4 * i);
+  }
   for (int i = threadIdx.x; i < T * L * 2; i += 256) leaf[i] = __ldg(p.leaf + i);
   if (threadIdx.x < TD) thr[threadIdx.x] = __ldg(p.thresh + threadIdx.x);
-  __syncthreads();
   const uint64_t seed = (static_cast<uint64_t>(p.state->rng[1]) << 32) | p.state->rng[0];
   const DropCfg dtree = make_dropcfg(p.training ? p.tree_drop_p : 0.f, seed);
   const DropCfg dpre = make_dropcfg(p.training ? p.pre_drop_p : 0.f, seed);
   const uint32_t tree_key = stream_key(p.state->rng, kStreamTree);
   const uint32_t pre_key = stream_key(p.state->rng, kStreamPre1);
   const float inv_T = 1.0f / static_cast<float>(T);
+  const float bb0 = __ldg(p.bb), bb1 = __ldg(p.bb + 1);
+  const float tc = fminf(fmaxf(__ldg(p.temperature), 0.5f), 5.0f);
+  const float loss_scale = p.state->loss_scale;
+  const int tree = lane >> 2, quarter = lane & 3;
+  const bool tree_ok = tree < T;
+  __syncthreads();
+  FND_HSTAMP(1);
 
   for (int b = blockIdx.x * 8 + warp; b < p.B; b += gridDim.x * 8) {
-    float lg[2];
+    // tree-logit dropout multipliers of (b, tree, 0..1)
+    float m0 = 1.f, m1 = 1.f;
+    if (dtree.p > 0.f && tree_ok) {
+      const uint64_t e = static_cast<uint64_t>(b) * T * 2 + tree * 2;
+      float mm[4];
+      dropout_mult4(dtree, tree_key, e >> 2, mm);
+      m0 = (e & 2) ? mm[2] : mm[0]; m1 = (e & 2) ? mm[3] : mm[1];
+    }
+    // backward needs z of pre.3 for this row: issue the loads now, use them at the end
+    float4 zv[NF4];
+    if (BWD) {
+#pragma unroll
+      for (int i = 0; i < NF4; ++i) zv[i] = ldg_f4(p.z_pre1 + static_cast<size_t>(b) * H + i * 128 + lane * 4);
+    }
+    float lg0, lg1;
     if (FWD) {
       float4 hv[NF4];
 #pragma unroll
       for (int i = 0; i < NF4; ++i) hv[i] = ldg_f4(p.h + static_cast<size_t>(b) * H + i * 128 + lane * 4);
-      float byp[2];
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        float acc = 0.f;
-#pragma unroll
-        for (int i = 0; i < NF4; ++i) {
-          const float4 w = wb_s[c * (H / 4) + i * 32 + lane];
-          acc += hv[i].x * w.x + hv[i].y * w.y + hv[i].z * w.z + hv[i].w * w.w;
-        }
-        byp[c] = warp_sum(acc) + __ldg(p.bb + c);
-      }
-      float mine = 0.f;
-#pragma unroll 2
-      for (int k = 0; k < TD; ++k) {
-        float acc = 0.f;
+      for (int k = 0; k < NR; ++k) {
+        float a0 = 0.f, a1 = 0.f;
 #pragma unroll
         for (int i = 0; i < NF4; ++i) {
-          const float4 w = alpha_s[k * (H / 4) + i * 32 + lane];
-          acc += hv[i].x * w.x + hv[i].y * w.y + hv[i].z * w.z + hv[i].w * w.w;
+          const float4 w = rows_s[k * (H / 4) + i * 32 + lane];
+          a0 += hv[i].x * w.x + hv[i].z * w.z;
+          a1 += hv[i].y * w.y + hv[i].w * w.w;
         }
-        const float sk = sigmoidf_(p.tau * (warp_sum(acc) - thr[k]));
-        mine = (lane == k) ? sk : mine;
-      }
-      if (lane < TD) {
-        sv[lane] = mine;
-        if (p.svals) p.svals[static_cast<size_t>(b) * 32 + lane] = mine;
+        part[k * 33 + lane] = a0 + a1;
       }
       __syncwarp();
-      float node0 = 0.f, node1 = 0.f;
-#pragma unroll 1
-      for (int i = 0; i < T; ++i) {
+      if (lane < NR) {
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          s0 += part[lane * 33 + j]; s1 += part[lane * 33 + j + 1];
+          s2 += part[lane * 33 + j + 2]; s3 += part[lane * 33 + j + 3];
+        }
+        const float dot = (s0 + s1) + (s2 + s3);
+        if (lane < TD) {
+          const float sk = sigmoidf_(p.tau * (dot - thr[lane]));
+          sv[lane] = sk;
+          if (p.svals) p.svals[static_cast<size_t>(b) * 32 + lane] = sk;
+        } else {
+          byp_all[warp][lane - TD] = dot + (lane == TD ? bb0 : bb1);
+        }
+      }
+      __syncwarp();
+      FND_HSTAMP(3);
+      float tl0 = 0.f, tl1 = 0.f;
+      if (tree_ok) {
         float s[D];
 #pragma unroll
-        for (int d = 0; d < D; ++d) s[d] = sv[i * D + d];
-        float tl0 = 0.f, tl1 = 0.f;
+        for (int d = 0; d < D; ++d) s[d] = sv[tree * D + d];
 #pragma unroll
-        for (int leafi = 0; leafi < L; ++leafi) {
+        for (int j = 0; j < 4; ++j) {
+          const int leafi = quarter * 4 + j;
           float pr = 1.f;
 #pragma unroll
           for (int d = 0; d < D; ++d) pr *= ((leafi >> d) & 1) ? s[d] : (1.f - s[d]);
-          tl0 += pr * leaf[(i * L + leafi) * 2];
-          tl1 += pr * leaf[(i * L + leafi) * 2 + 1];
+          tl0 += pr * leaf[(tree * L + leafi) * 2];
+          tl1 += pr * leaf[(tree * L + leafi) * 2 + 1];
         }
-        float m0 = 1.f, m1 = 1.f;
-        if (dtree.p > 0.f) {
-          const uint64_t e = static_cast<uint64_t>(b) * T * 2 + i * 2;     // element index of tree logit (b, i, 0)
-          float mm[4];
-          dropout_mult4(dtree, tree_key, e >> 2, mm);
-          m0 = (e & 2) ? mm[2] : mm[0]; m1 = (e & 2) ? mm[3] : mm[1];
-        }
-        node0 += tl0 * m0; node1 += tl1 * m1;
+        tl0 *= m0; tl1 *= m1;
       }
-      lg[0] = node0 * inv_T + byp[0];
-      lg[1] = node1 * inv_T + byp[1];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        tl0 += __shfl_xor_sync(0xffffffffu, tl0, o);
+        tl1 += __shfl_xor_sync(0xffffffffu, tl1, o);
+      }
+      lg0 = tl0 * inv_T + byp_all[warp][0];
+      lg1 = tl1 * inv_T + byp_all[warp][1];
       if (lane == 0) {
-        p.logits[b * 2] = lg[0]; p.logits[b * 2 + 1] = lg[1];
-        const float tc = fminf(fmaxf(__ldg(p.temperature), 0.5f), 5.0f);
-        const float a0 = lg[0] / tc, a1 = lg[1] / tc, mx = fmaxf(a0, a1);
+        p.logits[b * 2] = lg0; p.logits[b * 2 + 1] = lg1;
+        const float a0 = lg0 / tc, a1 = lg1 / tc, mx = fmaxf(a0, a1);
         const float e0 = expf(a0 - mx), e1 = expf(a1 - mx);
         p.probs[b * 2] = e0 / (e0 + e1); p.probs[b * 2 + 1] = e1 / (e0 + e1);
       }
     } else {
       if (BWD && lane < TD) sv[lane] = p.svals[static_cast<size_t>(b) * 32 + lane];
       __syncwarp();
-      lg[0] = p.logits[b * 2]; lg[1] = p.logits[b * 2 + 1];
+      lg0 = p.logits[b * 2]; lg1 = p.logits[b * 2 + 1];
     }
-    float dl[2] = {0.f, 0.f};
+    FND_HSTAMP(4);
+    float dl0 = 0.f, dl1 = 0.f;
     if (CE) {
       // F.cross_entropy, mean reduction (forensic_trainer.py:287)
       const int y = static_cast<int>(p.labels[b]);
-      const float mx = fmaxf(lg[0], lg[1]);
-      const float e0 = expf(lg[0] - mx), e1 = expf(lg[1] - mx), se = e0 + e1;
-      const float loss = logf(se) + mx - (y == 0 ? lg[0] : lg[1]);
-      const float sc = p.state->loss_scale;
-      dl[0] = (e0 / se - (y == 0 ? 1.f : 0.f)) * sc;
-      dl[1] = (e1 / se - (y == 1 ? 1.f : 0.f)) * sc;
+      const float mx = fmaxf(lg0, lg1);
+      const float e0 = expf(lg0 - mx), e1 = expf(lg1 - mx), se = e0 + e1;
+      const float loss = logf(se) + mx - (y == 0 ? lg0 : lg1);
+      dl0 = (e0 / se - (y == 0 ? 1.f : 0.f)) * loss_scale;
+      dl1 = (e1 / se - (y == 1 ? 1.f : 0.f)) * loss_scale;
       if (lane == 0) {
         p.loss_row[b] = loss;
-        if (p.dlogits_out) { p.dlogits_out[b * 2] = dl[0]; p.dlogits_out[b * 2 + 1] = dl[1]; }
+        if (p.dlogits_out) { p.dlogits_out[b * 2] = dl0; p.dlogits_out[b * 2 + 1] = dl1; }
       }
     } else if (BWD) {
-      dl[0] = p.dlogits_in[b * 2]; dl[1] = p.dlogits_in[b * 2 + 1];
+      dl0 = p.dlogits_in[b * 2]; dl1 = p.dlogits_in[b * 2 + 1];
     }
     if (BWD) {
-#pragma unroll 1
-      for (int i = 0; i < T; ++i) {
-        float s[D];
+      float ds[D] = {0.f, 0.f, 0.f, 0.f};
+      float s[D] = {0.f, 0.f, 0.f, 0.f};
+      if (tree_ok) {
+        const float dt0 = dl0 * m0 * inv_T, dt1 = dl1 * m1 * inv_T;
 #pragma unroll
-        for (int d = 0; d < D; ++d) s[d] = sv[i * D + d];
-        float m0 = 1.f, m1 = 1.f;
-        if (dtree.p > 0.f) {
-          const uint64_t e = static_cast<uint64_t>(b) * T * 2 + i * 2;
-          float mm[4];
-          dropout_mult4(dtree, tree_key, e >> 2, mm);
-          m0 = (e & 2) ? mm[2] : mm[0]; m1 = (e & 2) ? mm[3] : mm[1];
-        }
-        const float dt0 = dl[0] * m0 * inv_T, dt1 = dl[1] * m1 * inv_T;
-        float ds[D];
+        for (int d = 0; d < D; ++d) s[d] = sv[tree * D + d];
+        float lc[8];
 #pragma unroll
-        for (int d = 0; d < D; ++d) ds[d] = 0.f;
-        float myleaf0 = 0.f, myleaf1 = 0.f;          // lane `leafi` keeps leaf `leafi`'s contribution (L <= 32)
-#pragma unroll
-        for (int leafi = 0; leafi < L; ++leafi) {
+        for (int j = 0; j < 4; ++j) {
+          const int leafi = quarter * 4 + j;
           float pr = 1.f;
 #pragma unroll
           for (int d = 0; d < D; ++d) pr *= ((leafi >> d) & 1) ? s[d] : (1.f - s[d]);
-          if (lane == leafi) { myleaf0 = pr * dt0; myleaf1 = pr * dt1; }
-          const float dpr = leaf[(i * L + leafi) * 2] * dt0 + leaf[(i * L + leafi) * 2 + 1] * dt1;
+          lc[2 * j] = pr * dt0; lc[2 * j + 1] = pr * dt1;
+          const float dpr = leaf[(tree * L + leafi) * 2] * dt0 + leaf[(tree * L + leafi) * 2 + 1] * dt1;
 #pragma unroll
           for (int d = 0; d < D; ++d) {
             float others = 1.f;
@@ -594,16 +614,22 @@ __global__ void __launch_bounds__(256) head_kernel(HeadParams p) {
             ds[d] += dpr * (((leafi >> d) & 1) ? others : -others);
           }
         }
-        if (lane < L)
-          *reinterpret_cast<float2*>(p.leafc + static_cast<size_t>(b) * T * L * 2 + (i * L + lane) * 2) =
-              make_float2(myleaf0, myleaf1);
-        if (lane == 0) {
-#pragma unroll
-          for (int d = 0; d < D; ++d) df[i * D + d] = ds[d] * p.tau * s[d] * (1.f - s[d]);
-        }
+        float* lcdst = p.leafc + static_cast<size_t>(b) * T * L * 2 + (tree * L + quarter * 4) * 2;
+        *reinterpret_cast<float4*>(lcdst) = make_float4(lc[0], lc[1], lc[2], lc[3]);
+        *reinterpret_cast<float4*>(lcdst + 4) = make_float4(lc[4], lc[5], lc[6], lc[7]);
       }
-      if (lane == 0) { df[TD] = dl[0]; df[TD + 1] = dl[1]; }
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        ds[d] += __shfl_xor_sync(0xffffffffu, ds[d], 1);
+        ds[d] += __shfl_xor_sync(0xffffffffu, ds[d], 2);
+      }
+      if (tree_ok && quarter == 0) {
+#pragma unroll
+        for (int d = 0; d < D; ++d) df[tree * D + d] = ds[d] * p.tau * s[d] * (1.f - s[d]);
+      }
+      if (lane == 31) { df[TD] = dl0; df[TD + 1] = dl1; }
       __syncwarp();
+      FND_HSTAMP(5);
       // dF row [dfeat | dlogits | 0]: lanes write 2 columns each
       {
         const float c0 = (2 * lane < TD + 2) ? df[2 * lane] : 0.f;
@@ -611,40 +637,37 @@ __global__ void __launch_bounds__(256) head_kernel(HeadParams p) {
         *reinterpret_cast<float2*>(p.dF + static_cast<size_t>(b) * kDFCols + 2 * lane) = make_float2(c0, c1);
         store_bf2(p.dF_hi, p.dF_lo, static_cast<size_t>(b) * kDFCols + 2 * lane, c0, c1);
       }
-      // dh = sum_k dfeat[k]*alpha[k,:] + sum_c dl[c]*wb[c,:]; then the GELU/dropout backward of pre.3
+      // dh = sum_k df[k] * rows[k,:]  (alpha rows carry dfeat, the two bypass rows carry dlogits)
       float4 acc[NF4];
 #pragma unroll
-      for (int i = 0; i < NF4; ++i) {
-        const float4 w0 = wb_s[i * 32 + lane], w1 = wb_s[(H / 4) + i * 32 + lane];
-        acc[i] = make_float4(dl[0] * w0.x + dl[1] * w1.x, dl[0] * w0.y + dl[1] * w1.y, dl[0] * w0.z + dl[1] * w1.z,
-                             dl[0] * w0.w + dl[1] * w1.w);
-      }
+      for (int i = 0; i < NF4; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 2
-      for (int k = 0; k < TD; ++k) {
+      for (int k = 0; k < NR; ++k) {
         const float f = df[k];
 #pragma unroll
         for (int i = 0; i < NF4; ++i) {
-          const float4 w = alpha_s[k * (H / 4) + i * 32 + lane];
+          const float4 w = rows_s[k * (H / 4) + i * 32 + lane];
           acc[i].x += f * w.x; acc[i].y += f * w.y; acc[i].z += f * w.z; acc[i].w += f * w.w;
         }
       }
-#pragma unroll 1
+      // GELU / dropout backward of pre.3
+#pragma unroll
       for (int i = 0; i < NF4; ++i) {
         const int j = i * 128 + lane * 4;
-        float4 a = acc[0];
-#pragma unroll
-        for (int q = 1; q < NF4; ++q) a = (i == q) ? acc[q] : a;
-        const float4 z = ldg_f4(p.z_pre1 + static_cast<size_t>(b) * H + j);
         float mm[4] = {1.f, 1.f, 1.f, 1.f};
         if (dpre.p > 0.f) dropout_mult4(dpre, pre_key, (static_cast<uint64_t>(b) * H + j) >> 2, mm);
+        const float4 z = zv[i];
+        float4 a = acc[i];
         a.x *= gelu_erf_grad(z.x) * mm[0]; a.y *= gelu_erf_grad(z.y) * mm[1];
         a.z *= gelu_erf_grad(z.z) * mm[2]; a.w *= gelu_erf_grad(z.w) * mm[3];
         store_bf2(p.dz_hi, p.dz_lo, static_cast<size_t>(b) * H + j, a.x, a.y);
         store_bf2(p.dz_hi, p.dz_lo, static_cast<size_t>(b) * H + j + 2, a.z, a.w);
       }
       __syncwarp();
+      FND_HSTAMP(6);
     }
   }
+  FND_HSTAMP(7);
 }
 
 // ---------------------------------------------------------------------------------------------
