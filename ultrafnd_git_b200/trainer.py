@@ -1,0 +1,371 @@
+"""B200 drop-in for the reference's live trainer (src/training/forensic_trainer.py): same ``TrainConfig`` fields,
+``ForensicTrainer(cfg)`` with ``fit() -> best_val_auc`` and ``test() -> dict``, the ``best.pt`` schema
+``{"fusion", "clf", "gnn", "cfg"}`` (:352-361), StepLR(3, 0.7) per epoch (:177,341), patience-3 early stopping on
+validation AUC (:362-366), and ``_forward_batch`` / ``_build_dataloaders`` / ``*_loader`` for the callers that poke at them
+(scripts/sanity_check.py:25-26).
+
+What changes underneath:
+  * the step is ``fnd_train_step`` / ``fnd_eval_step`` (one CUDA-graph replay per batch) instead of ~150 ATen ops
+    + autograd + a Python optimizer loop;
+  * the whole feature cache and the GCN embeddings live on the device as one matrix; a batch is a gather by row index
+    inside the first kernel (no DataLoader / collate / .to(device) per step);
+  * the six blocking D2H copies per step (:301-313) are replaced by device-side accumulation and ONE copy per epoch;
+  * with ``torch.distributed`` initialised, each global batch is sharded across ranks and gradients are all-reduced
+    (NCCL) between ``fnd_train_fwd_bwd`` and ``fnd_clip_adamw_step``.
+The data pipeline and graph construction stay the reference's (out of scope, SURVEY.md §2 #9,#14): pass a prebuilt
+``cache`` dict, or have the reference importable as ``src.data_pipeline.fakesv_dataset``.
+"""
+from __future__ import annotations
+
+import math
+import os
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .fused import DeviceCache, FusedStep, FEATURE_KEYS
+from .metrics import aggregate_epoch_metrics, pretty_print
+from .modules import CrossModalTransformer, DeepTruthClassifier, pair_modules
+
+
+@dataclass
+class TrainConfig:
+    """Field-for-field the reference's TrainConfig (forensic_trainer.py:90-107)."""
+    data_root: str
+    ocr_phrase_pkl: Optional[str]
+    out_dir: str = "outputs"
+    batch_size: int = 16
+    epochs: int = 8
+    lr: float = 2e-4
+    weight_decay: float = 1e-4
+    gnn_dim: int = 128
+    gnn_overlap_thresh: float = 0.12
+    seed: int = 42
+    use_mps: bool = True          # accepted and ignored: this trainer runs on CUDA
+    use_gnn: bool = True
+    save_best: bool = True
+    grad_clip: float = 5.0
+    early_stop_patience: int = 3
+
+
+class SimpleGCN(nn.Module):
+    """Two-layer dense GCN (forensic_trainer.py:25-53): z = lin2(Â · drop(gelu(lin1(Â x)))), Â = D^-1/2 (A+I) D^-1/2.
+    Runs once at start-up to produce the constant ``gnn_Z`` table; plain torch on the GPU (not a hot-path kernel)."""
+
+    def __init__(self, in_dim: int, hid: int = 128, out_dim: int = 128, dropout: float = 0.3):
+        super().__init__()
+        self.lin1 = nn.Linear(in_dim, hid)
+        self.lin2 = nn.Linear(hid, out_dim)
+        self.drop = nn.Dropout(dropout)
+
+    @staticmethod
+    def normalise(adj: torch.Tensor) -> torch.Tensor:
+        a_hat = adj + torch.eye(adj.shape[0], device=adj.device, dtype=adj.dtype)
+        d = (a_hat.sum(-1) + 1e-9).pow(-0.5)
+        return d[:, None] * a_hat * d[None, :]
+
+    def forward(self, x: torch.Tensor, adj: torch.Tensor) -> torch.Tensor:
+        a = self.normalise(adj)
+        h = self.drop(F.gelu(self.lin1(a @ x)))
+        return self.lin2(a @ h)
+
+
+def build_adj_from_ocr(ocr_sets, thresh: float = 0.12) -> np.ndarray:
+    """Jaccard-threshold adjacency (forensic_trainer.py:113-132) computed from a token-incidence matrix instead of an
+    O(N^2) Python loop; identical result (1 on the diagonal; edge iff |a∩b| / (|a∪b| + 1e-9) >= thresh)."""
+    n = len(ocr_sets)
+    vocab: Dict[str, int] = {}
+    rows, cols = [], []
+    for i, s in enumerate(ocr_sets):
+        for tok in s:
+            rows.append(i)
+            cols.append(vocab.setdefault(tok, len(vocab)))
+    inc = torch.zeros(n, max(len(vocab), 1), dtype=torch.float32)
+    if rows:
+        inc[torch.tensor(rows), torch.tensor(cols)] = 1.0
+    inter = inc @ inc.t()
+    size = inc.sum(-1)
+    union = size[:, None] + size[None, :] - inter
+    jac = inter / (union + 1e-9)
+    both_empty = (size[:, None] == 0) & (size[None, :] == 0)
+    a = ((jac >= thresh) & ~both_empty).float()
+    a.fill_diagonal_(1.0)
+    return a.numpy()
+
+
+def shard_indices(global_idx: torch.Tensor, rank: int, world: int) -> torch.Tensor:
+    """This rank's share of one global batch: every world-th sample starting at `rank` (disjoint, exhaustive; shard
+    sizes differ by at most one). With per-rank loss scale 1/len(global batch) a SUM all-reduce of the gradients yields
+    exactly the single-process mean-loss gradient."""
+    return global_idx[rank::world] if world > 1 else global_idx
+
+
+class CachedTensorDataset(torch.utils.data.Dataset):
+    """API-compatibility view of one split (forensic_trainer.py:60-83); the fused loops do not use it."""
+
+    def __init__(self, cache: Dict, indices: np.ndarray):
+        self.T = torch.from_numpy(np.asarray(cache["text"])[indices])
+        self.A = torch.from_numpy(np.asarray(cache["audio"])[indices])
+        self.V = torch.from_numpy(np.asarray(cache["visual"])[indices])
+        self.U = torch.from_numpy(np.asarray(cache["temporal"])[indices])
+        self.AUX = torch.from_numpy(np.asarray(cache["aux"])[indices])
+        self.y = torch.from_numpy(np.asarray(cache["labels"])[indices]).long()
+
+    def __len__(self):
+        return self.T.shape[0]
+
+    def __getitem__(self, i):
+        return {"text_features": self.T[i], "audio_features": self.A[i], "visual_features": self.V[i],
+                "temporal_features": self.U[i], "aux": self.AUX[i], "label": self.y[i], "index": i}
+
+
+class ForensicTrainer:
+    def __init__(self, cfg: TrainConfig, cache: Optional[Dict] = None, precision: Optional[str] = None,
+                 use_graph: bool = True):
+        self.cfg = cfg
+        os.makedirs(cfg.out_dir, exist_ok=True)
+        if not torch.cuda.is_available():
+            raise RuntimeError("ultrafnd_git_b200.ForensicTrainer needs a CUDA device (no CPU fallback)")
+        self.dist = torch.distributed.is_available() and torch.distributed.is_initialized()
+        self.world = torch.distributed.get_world_size() if self.dist else 1
+        self.rank = torch.distributed.get_rank() if self.dist else 0
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        self.dtype = torch.float32
+        torch.manual_seed(cfg.seed)
+        np.random.seed(cfg.seed)
+
+        if cache is None:
+            try:
+                from src.data_pipeline.fakesv_dataset import FakeSVRawDataset, build_gnn_cache_from_raw_dataset
+            except Exception as e:  # pragma: no cover - needs the reference checkout
+                raise RuntimeError("no feature cache given and the reference data pipeline "
+                                   "(src.data_pipeline.fakesv_dataset) is not importable") from e
+            raw = FakeSVRawDataset(cfg.data_root)
+            cache = build_gnn_cache_from_raw_dataset(raw, ocr_phrase_pkl=cfg.ocr_phrase_pkl, text_dim=768, audio_dim=128,
+                                                     visual_dim=512, temporal_dim=256, seed=cfg.seed)
+        self.cache = cache
+        self.tr_idx, self.va_idx, self.te_idx = (np.asarray(x) for x in cache["split"])
+        if "gnn_Z" not in cache or cache["gnn_Z"] is None:
+            self._build_gnn()
+        else:
+            self.gnn = None
+        self.train_loader, self.val_loader, self.test_loader = self._build_dataloaders()
+
+        self.fusion = CrossModalTransformer(config_path="configs/model_configs/fusion.yaml", precision=precision)
+        self.clf = DeepTruthClassifier(config_path="configs/model_configs/classifier.yaml", precision=precision)
+        if cfg.use_gnn is False and self.fusion.use_gnn:
+            # the reference crashes in fuse_mlp.0 in this configuration (SURVEY.md §7 hard parts); say so up front
+            raise RuntimeError("use_gnn=False with fusion.yaml use_gnn: true: the reference's fuse_mlp.0 is sized for 16 "
+                               "slots and fails with a shape error; edit fusion.yaml as well")
+        self.engine = pair_modules(self.fusion, self.clf, precision)
+        if self.dist:
+            torch.distributed.broadcast(self.engine.params, src=0)
+        self.engine.set_hyper(lr=cfg.lr, weight_decay=cfg.weight_decay, max_norm=float(cfg.grad_clip or 0.0))
+        self.engine.set_seed(cfg.seed + 1000003 * self.rank)
+        self.use_graph = use_graph
+        self.precision = precision
+        self._steps: Dict[int, FusedStep] = {}
+        self._last_step: Optional[FusedStep] = None
+
+        feats = {"text_features": torch.as_tensor(np.asarray(cache["text"])),
+                 "audio_features": torch.as_tensor(np.asarray(cache["audio"])),
+                 "visual_features": torch.as_tensor(np.asarray(cache["visual"])),
+                 "temporal_features": torch.as_tensor(np.asarray(cache["temporal"])),
+                 "gnn_feat": torch.as_tensor(np.asarray(torch.as_tensor(cache["gnn_Z"]).detach().cpu()))}
+        self.dcache = DeviceCache(feats, torch.as_tensor(np.asarray(cache["aux"])),
+                                  torch.as_tensor(np.asarray(cache["labels"])), self.device)
+        self.lr = cfg.lr
+        self.epoch = 0
+        self.best_val_auc = -1.0
+        self.no_improve = 0
+        self.ckpt_path = os.path.join(cfg.out_dir, "best.pt")
+
+    # ------------------------------------------------------------------ start-up stages (not the hot path)
+    def _build_gnn(self) -> None:
+        """forensic_trainer.py:184-224: compact node features, OCR-Jaccard graph, 2-epoch degree-regression pre-train,
+        then a constant embedding table."""
+        c, cfg = self.cache, self.cfg
+        T, A, V, U = (np.asarray(c[k]) for k in ("text", "audio", "visual", "temporal"))
+        X = np.concatenate([T[:, :192], A[:, :32], V[:, :128], U[:, :64]], axis=1).astype(np.float32)
+        X /= (np.linalg.norm(X, axis=1, keepdims=True) + 1e-9)
+        adj = build_adj_from_ocr(c["ocr_sets"], thresh=cfg.gnn_overlap_thresh)
+        self.X = torch.from_numpy(X).to(self.device)
+        self.Adj = torch.from_numpy(adj).to(self.device)
+        self.gnn = SimpleGCN(self.X.shape[1], hid=2 * cfg.gnn_dim, out_dim=cfg.gnn_dim, dropout=0.2).to(self.device)
+        if cfg.use_gnn:
+            opt = torch.optim.Adam(self.gnn.parameters(), lr=1e-3, weight_decay=1e-4)
+            target = self.Adj.sum(-1, keepdim=True) / max(1.0, self.Adj.shape[0])
+            head = nn.Linear(cfg.gnn_dim, 1, device=self.device)
+            for _ in range(2):
+                self.gnn.train()
+                loss = F.mse_loss(torch.sigmoid(head(self.gnn(self.X, self.Adj))), target)
+                opt.zero_grad(); loss.backward(); opt.step()
+        self.gnn.eval()
+        with torch.no_grad():
+            self.cache["gnn_Z"] = self.gnn(self.X, self.Adj).detach()
+
+    def _build_dataloaders(self):
+        mk = lambda idx, shuf: torch.utils.data.DataLoader(CachedTensorDataset(self.cache, idx),
+                                                            batch_size=self.cfg.batch_size, shuffle=shuf, drop_last=False)
+        return mk(self.tr_idx, True), mk(self.va_idx, False), mk(self.te_idx, False)
+
+    # ------------------------------------------------------------------ module-level forward (API compatibility)
+    def _forward_batch(self, batch, split: str) -> Dict[str, torch.Tensor]:
+        """forensic_trainer.py:238-271 through the module API (autograd-capable); the epoch loops use the fused path."""
+        idx = {"train": self.tr_idx, "val": self.va_idx}.get(split, self.te_idx)
+        gidx = torch.as_tensor(idx, device=self.device)[batch["index"].to(self.device)]
+        feats = {k: batch[k].to(self.device, dtype=self.dtype) for k in FEATURE_KEYS[:4]}
+        feats["gnn_feat"] = torch.as_tensor(self.cache["gnn_Z"]).to(self.device)[gidx] if self.cfg.use_gnn else None
+        fo = self.fusion(feats)
+        co = self.clf(fo["fused"], batch["aux"].to(self.device, dtype=self.dtype))
+        return {"logits": co["logits"], "probs": co["probs"], "y": batch["label"].to(self.device),
+                "forensic": fo.get("forensic", {})}
+
+    # ------------------------------------------------------------------ fused epoch loop
+    def _step_for(self, batch: int, global_batch: Optional[int] = None) -> FusedStep:
+        st = self._steps.get(batch)
+        if st is None:
+            st = FusedStep(self.fusion, self.clf, batch, precision=self.precision, use_graph=self.use_graph)
+            st.attach_cache(self.dcache)
+            self._steps[batch] = st
+        if self.dist and global_batch is not None and getattr(st, "_global_batch", None) != global_batch:
+            from ._lib import check
+            check(st.engine.lib.fnd_set_loss_scale(st.plan.handle, 1.0 / global_batch, st.engine.stream_ptr()),
+                  "fnd_set_loss_scale")
+            st._global_batch = global_batch
+        if self._last_step is not None and self._last_step is not st:
+            # optimizer step count / bias corrections / dropout salts live in each plan's DevState: carry them over
+            src = self._last_step.plan.buffer("state", torch.float32, (22,))
+            dst = st.plan.buffer("state", torch.float32, (22,))
+            keep_scale = dst[17:18].clone()
+            dst.copy_(src)
+            dst[17:18].copy_(keep_scale)
+        self._last_step = st
+        return st
+
+    def _epoch_loop(self, split: str) -> Tuple[float, Dict[str, float]]:
+        is_train = split == "train"
+        idx_np = {"train": self.tr_idx, "val": self.va_idx}.get(split, self.te_idx)
+        n = len(idx_np)
+        self.fusion.train(is_train); self.clf.train(is_train)
+        order = torch.as_tensor(idx_np, dtype=torch.int64)
+        if is_train:
+            g = torch.Generator().manual_seed(self.cfg.seed * 7919 + self.epoch)
+            order = order[torch.randperm(n, generator=g)]
+        order = order.to(self.device)
+        bs = self.cfg.batch_size
+        # device-side epoch buffers: one D2H copy at the end instead of six per step (forensic_trainer.py:301-313)
+        loss_rows = torch.empty(n, device=self.device)
+        p1 = torch.empty(n, device=self.device)
+        ys = torch.empty(n, dtype=torch.int64, device=self.device)
+        forensic = torch.empty(n, 3, device=self.device)
+        done = 0
+        for start in range(0, n, bs):
+            gidx = order[start:start + bs]
+            local = shard_indices(gidx, self.rank, self.world)
+            if local.numel() == 0:
+                continue
+            st = self._step_for(int(local.numel()), int(gidx.numel()))
+            st.static_gather.copy_(local)
+            if is_train:
+                if self.dist:
+                    st.train_fwd_bwd(from_cache=True)
+                    torch.distributed.all_reduce(st.engine.grads)
+                    st.optimizer_step(norm_from_slots=False)
+                else:
+                    st.train_step(from_cache=True)
+            else:
+                st.eval_step(from_cache=True)
+            k = int(local.numel())
+            loss_rows[done:done + k] = st.loss_rows()
+            p1[done:done + k] = st.probs()[:, 1]
+            ys[done:done + k] = self.dcache.labels[local]
+            forensic[done:done + k] = st.plan.buffer("rowstat", torch.float32, (k, 16))[:, :3]
+            done += k
+        if is_train and self._last_step is not None:
+            self._last_step.mark_params_updated()
+            self._last_step.plan.check_error()
+        loss_rows, p1, ys, forensic = loss_rows[:done], p1[:done], ys[:done], forensic[:done]
+        if self.dist:
+            def gather(t):
+                parts = [torch.empty_like(t) for _ in range(self.world)]
+                torch.distributed.all_gather(parts, t)       # equal shard sizes: global batches are split evenly
+                return torch.cat(parts)
+            if n % self.world == 0 and bs % self.world == 0:
+                loss_rows, p1, ys, forensic = gather(loss_rows), gather(p1), gather(ys), gather(forensic)
+        loss_mean = float(loss_rows.mean().cpu()) if done else 0.0
+        f = forensic.cpu().numpy()
+        metrics = aggregate_epoch_metrics(ys.cpu().numpy(), p1.cpu().numpy(),
+                                          {"semantic_conflict": f[:, 0], "emotion_intensity": f[:, 1],
+                                           "temporal_delay": f[:, 2]} if done else None, threshold=0.5)
+        return loss_mean, metrics
+
+    def fit(self) -> float:
+        self.no_improve = 0
+        for epoch in range(1, self.cfg.epochs + 1):
+            self.epoch = epoch
+            tr_loss, tr_m = self._epoch_loop("train")
+            va_loss, va_m = self._epoch_loop("val")
+            if epoch % 3 == 0:                       # StepLR(step_size=3, gamma=0.7), stepped once per epoch
+                self.lr *= 0.7
+                self.engine.set_lr(self.lr)
+            if self.rank == 0:
+                print(f"[Epoch {epoch:02d}] train_loss={tr_loss:.4f} | ", end=""); pretty_print("train", tr_m)
+                print(f"           val_loss={va_loss:.4f} | ", end=""); pretty_print("val", va_m)
+            val_auc = float(va_m.get("auc", 0.5))
+            if val_auc > self.best_val_auc + 1e-4 and self.cfg.save_best:
+                self.best_val_auc = val_auc
+                self.no_improve = 0
+                if self.rank == 0:
+                    torch.save({"fusion": {k: v.detach().cpu() for k, v in self.fusion.state_dict().items()},
+                                "clf": {k: v.detach().cpu() for k, v in self.clf.state_dict().items()},
+                                "gnn": self.gnn.state_dict() if (self.cfg.use_gnn and self.gnn is not None) else None,
+                                "cfg": dict(self.cfg.__dict__)}, self.ckpt_path)
+                    print(f"  ↳ saved best checkpoint to {self.ckpt_path} (val_auc={self.best_val_auc:.3f})")
+            else:
+                self.no_improve += 1
+                if self.no_improve >= self.cfg.early_stop_patience:
+                    if self.rank == 0:
+                        print(f"↳ Early stopping (no val AUC improvement for {self.cfg.early_stop_patience} epochs)")
+                    break
+        return self.best_val_auc
+
+    def test(self) -> Dict[str, float]:
+        if os.path.exists(self.ckpt_path):
+            ck = torch.load(self.ckpt_path, map_location="cpu")
+            self.fusion.load_state_dict(ck["fusion"])
+            self.clf.load_state_dict(ck["clf"])
+            if self.cfg.use_gnn and ck.get("gnn") is not None and self.gnn is not None:
+                self.gnn.load_state_dict(ck["gnn"])
+            self.engine.refresh_shadows(self.engine.param_version())
+        ts_loss, m = self._epoch_loop("test")
+        if self.rank == 0:
+            print(f"[Test] loss={ts_loss:.4f} | ", end=""); pretty_print("test", m)
+        return {"test_loss": ts_loss, "test_acc": m.get("accuracy", 0.0), "test_auc": m.get("auc", 0.5),
+                "test_precision": m.get("precision", 0.0), "test_recall": m.get("recall", 0.0), "test_f1": m.get("f1", 0.0),
+                "test_cmcs": m.get("cmcs", 0.0), "test_dfdr": m.get("dfdr", 0.0)}
+
+
+def synthetic_cache(n: int = 256, seed: int = 0) -> Dict:
+    """A FakeSV-shaped feature cache with the keys build_gnn_cache_from_raw_dataset returns (fakesv_dataset.py:242-252),
+    filled with separable synthetic data (tests, smoke runs, benchmarks: there is no dataset offline)."""
+    g = np.random.RandomState(seed)
+    labels = g.randint(0, 2, size=n).astype(np.int64)
+    shift = (labels[:, None] * 2 - 1).astype(np.float32)
+
+    def feat(d, scale):
+        x = g.randn(n, d).astype(np.float32)
+        x[:, : d // 8] += scale * shift
+        return x / (np.linalg.norm(x, axis=1, keepdims=True) + 1e-9)
+    idx = g.permutation(n)
+    n_tr, n_va = int(0.7 * n), int(0.15 * n)
+    vocab = [f"tok{i}" for i in range(64)]
+    ocr = [set(g.choice(vocab, size=g.randint(0, 6), replace=False).tolist()) for _ in range(n)]
+    return {"ids": np.array([f"v{i}" for i in range(n)]), "text": feat(768, 0.6), "audio": feat(128, 0.4),
+            "visual": feat(512, 0.5), "temporal": (0.05 * g.randn(n, 256)).astype(np.float32),
+            "aux": g.rand(n, 2).astype(np.float32), "labels": labels, "ocr_sets": ocr,
+            "split": (idx[:n_tr], idx[n_tr:n_tr + n_va], idx[n_tr + n_va:])}
