@@ -1,0 +1,33 @@
+#!/usr/bin/env python3
+"""In-kernel phase stamps of every GEMM/head launch inside a real (un-graphed, L2-flushed) training step."""
+import os, sys
+os.environ["FND_DEBUG_STAMPS"] = "1"
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from ultrafnd_git_b200.fused import FusedStep
+from ultrafnd_git_b200.modules import CrossModalTransformer, DeepTruthClassifier
+import bench
+torch.manual_seed(0)
+B = 128
+f, c = CrossModalTransformer(precision="bf16"), DeepTruthClassifier(precision="bf16")
+f.train(); c.train()
+step = FusedStep(f, c, B, use_graph=False)
+step.load_batch({k: v.cuda() for k, v in bench.synth_batch(B, 1).items()})
+flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+for it in range(3):
+    flush.zero_()
+    step.train_step()
+torch.cuda.synchronize()
+names = ["gemm_proj", "gemm_qkv", "gemm_fuse0", "gemm_fuse1", "gemm_pre0", "gemm_pre1", "head", "dgrad_pre1", "dgrad_pre0",
+         "dgrad_fuse1", "dgrad_fuse0", "dgrad_qkv", "wgrad_all"]
+grids = [40, 72, 144, 32, 8, 8, 16, 8, 8, 16, 128, 32, 780]
+buf = step.plan.buffer("dbg", torch.int64, (40, 1024, 8)).cpu().double()
+lab = ["setup", "first_full", "mma_issued", "accum_rdy", "splitk", "epi_done"]
+for i, (n, g) in enumerate(zip(names, grids)):
+    t = buf[i, :g]
+    d = (t - t[:, :1]) / 1.965e3
+    if n == "head":
+        print(f"{n:12s} grid {g:4d} median us:", [round(float(d[:, j].median()), 2) for j in range(1, 8)])
+    else:
+        print(f"{n:12s} grid {g:4d} median us:", {l: round(float(d[:, j + 1].median()), 2) for j, l in enumerate(lab)},
+              "max epi", round(float(d[:, 6].max()), 2))

@@ -203,11 +203,27 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n, int a_mn_ma
 // ------------------------------------------------------------------------------------------
 // Math helpers
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+// Exact-erf GELU (nn.GELU() default) and its derivative. erf uses Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, far
+// below both parity tolerances) because it needs ONE exp and one reciprocal; that exp(-x^2/2) is also the Gaussian pdf
+// the derivative needs. The epilogues run one warp per scheduler, so instruction count on this path is latency.
+__device__ __forceinline__ void gelu_cdf_pdf(float x, float& cdf, float& pdf) {
+  const float ax = fabsf(x) * 0.70710678118654752440f;
+  const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
+  const float e = __expf(-ax * ax);                    // exp(-x^2 / 2)
+  const float poly = t * fmaf(t, fmaf(t, fmaf(t, fmaf(t, 1.061405429f, -1.453152027f), 1.421413741f), -0.284496736f), 0.254829592f);
+  const float erf_abs = fmaf(-poly, e, 1.0f);
+  cdf = 0.5f * (1.0f + copysignf(erf_abs, x));
+  pdf = 0.39894228040143267794f * e;
+}
+__device__ __forceinline__ float gelu_erf(float x) {
+  float cdf, pdf;
+  gelu_cdf_pdf(x, cdf, pdf);
+  return x * cdf;
+}
 __device__ __forceinline__ float gelu_erf_grad(float x) {
-  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
-  const float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
-  return cdf + x * pdf;
+  float cdf, pdf;
+  gelu_cdf_pdf(x, cdf, pdf);
+  return fmaf(x, pdf, cdf);
 }
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
 
@@ -240,29 +256,41 @@ __device__ __noinline__ uint4 philox4x32_10(uint64_t ctr, uint32_t key0, uint32_
   }
   return make_uint4(c0, c1, c2, c3);
 }
-// Dropout multiplier for 4 consecutive elements starting at (idx4 * 4): 0 or 1/(1-p).
+// Dropout keep-multipliers (0 or 1/(1-p)) for the 8 consecutive elements [8*idx8, 8*idx8+8): one Philox call yields
+// 128 bits = eight 16-bit uniforms; element q keeps iff its 16 bits >= round(p * 65536).
 struct DropCfg {
   float p;            // drop probability (0 => disabled)
   float inv_keep;     // 1/(1-p)
-  uint32_t thresh;    // keep iff rnd >= thresh, thresh = p * 2^32
+  uint32_t thresh;    // 16-bit threshold
   uint32_t key0, key1;
 };
 __host__ __device__ inline DropCfg make_dropcfg(float p, uint64_t seed) {
   DropCfg d;
   d.p = p;
   d.inv_keep = p > 0.f ? 1.0f / (1.0f - p) : 1.0f;
-  double t = static_cast<double>(p) * 4294967296.0;
-  d.thresh = t >= 4294967295.0 ? 0xFFFFFFFFu : static_cast<uint32_t>(t);
+  const float t = p * 65536.0f + 0.5f;
+  d.thresh = t >= 65535.0f ? 65535u : static_cast<uint32_t>(t);
   d.key0 = static_cast<uint32_t>(seed);
   d.key1 = static_cast<uint32_t>(seed >> 32);
   return d;
 }
-__device__ __forceinline__ void dropout_mult4(const DropCfg& d, uint32_t stream, uint64_t idx4, float (&m)[4]) {
-  const uint4 r = philox4x32_10(idx4, d.key0, d.key1, stream);
-  m[0] = r.x >= d.thresh ? d.inv_keep : 0.f;
-  m[1] = r.y >= d.thresh ? d.inv_keep : 0.f;
-  m[2] = r.z >= d.thresh ? d.inv_keep : 0.f;
-  m[3] = r.w >= d.thresh ? d.inv_keep : 0.f;
+__device__ __forceinline__ void dropout_mult8(const DropCfg& d, uint32_t stream, uint64_t idx8, float (&m)[8]) {
+  const uint4 r = philox4x32_10(idx8, d.key0, d.key1, stream);
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    m[2 * q] = (w[q] & 0xFFFFu) >= d.thresh ? d.inv_keep : 0.f;
+    m[2 * q + 1] = (w[q] >> 16) >= d.thresh ? d.inv_keep : 0.f;
+  }
+}
+// multiplier of ONE element (rare paths: tree-logit masks)
+__device__ __forceinline__ float dropout_mult1(const DropCfg& d, uint32_t stream, uint64_t idx) {
+  float m[8];
+  dropout_mult8(d, stream, idx >> 3, m);
+  float out = m[0];
+#pragma unroll
+  for (int q = 1; q < 8; ++q) out = ((idx & 7) == static_cast<uint64_t>(q)) ? m[q] : out;
+  return out;
 }
 
 // Dropout salts: rng[2] advances once per fusion forward, rng[3] once per classifier forward, so the two modules

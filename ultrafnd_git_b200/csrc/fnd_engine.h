@@ -164,6 +164,7 @@ struct Plan {
   FinTable fin_all, fin_clf, fin_fus;
   int total_slots = 0;
   // optional per-kernel timing (bench/profiling only): an event is recorded after every launch
+  int dbg_launch = 0;            // probe builds: index of the next launch's stamp region
   bool profiling = false;
   std::vector<std::pair<const char*, cudaEvent_t>> marks;
 
@@ -257,7 +258,7 @@ inline void carve(Plan& P) {
     plan_add(P, "splitws_f1", static_cast<long long>(splitk_ws_floats(P.B, P.H, 64, P.splits_f1)) * 4);
     plan_add(P, "splitctr_f1", static_cast<long long>(tm) * (P.H / 64) * 4);
   }
-  if (getenv("FND_DEBUG_STAMPS")) plan_add(P, "dbg", 8 * 8 * 4096);     // clock64 stamps of the row kernels (probes)
+  if (getenv("FND_DEBUG_STAMPS")) plan_add(P, "dbg", 8LL * 8 * 1024 * 40);     // clock64 stamps of the row kernels (probes)
   // per-CTA sum-of-squares slots (wgrad CTAs + finalize CTAs); generous upper bound, zero-initialised at bind
   plan_add(P, "slots", 16384 * 4);
   // device copies of the kernel tables

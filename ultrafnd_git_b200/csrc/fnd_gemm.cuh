@@ -359,23 +359,16 @@ fnd_gemm_kernel(const __grid_constant__ GemmTableP tbl, RunCtx ctx) {
         }
         const uint64_t e0 = static_cast<uint64_t>(m) * static_cast<uint64_t>(PN) + n0;   // multiple of 8
         if (dfw.p > 0.f) {
-          float mm[4];
-          dropout_mult4(dfw, key_fw, e0 >> 2, mm);
-          v[0] *= mm[0]; v[1] *= mm[1]; v[2] *= mm[2]; v[3] *= mm[3];
-          dropout_mult4(dfw, key_fw, (e0 >> 2) + 1, mm);
-          v[4] *= mm[0]; v[5] *= mm[1]; v[6] *= mm[2]; v[7] *= mm[3];
+          float mm[8];
+          dropout_mult8(dfw, key_fw, e0 >> 3, mm);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] *= mm[j];
         }
         if (E.gate_z) {
           const float* z = E.gate_z + static_cast<size_t>(m) * E.gate_pitch + n0;
           const float4 z0 = ldg_f4(z), z1 = ldg_f4(z + 4);
           float mm[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f};
-          if (dbw.p > 0.f) {
-            float t4[4];
-            dropout_mult4(dbw, key_bw, e0 >> 2, t4);
-            mm[0] = t4[0]; mm[1] = t4[1]; mm[2] = t4[2]; mm[3] = t4[3];
-            dropout_mult4(dbw, key_bw, (e0 >> 2) + 1, t4);
-            mm[4] = t4[0]; mm[5] = t4[1]; mm[6] = t4[2]; mm[7] = t4[3];
-          }
+          if (dbw.p > 0.f) dropout_mult8(dbw, key_bw, e0 >> 3, mm);
           v[0] *= gelu_erf_grad(z0.x) * mm[0]; v[1] *= gelu_erf_grad(z0.y) * mm[1];
           v[2] *= gelu_erf_grad(z0.z) * mm[2]; v[3] *= gelu_erf_grad(z0.w) * mm[3];
           v[4] *= gelu_erf_grad(z1.x) * mm[4]; v[5] *= gelu_erf_grad(z1.y) * mm[5];

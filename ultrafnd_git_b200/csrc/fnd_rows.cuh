@@ -493,9 +493,8 @@ __global__ void __launch_bounds__(256) head_kernel(HeadParams p) {
     float m0 = 1.f, m1 = 1.f;
     if (dtree.p > 0.f && tree_ok) {
       const uint64_t e = static_cast<uint64_t>(b) * T * 2 + tree * 2;
-      float mm[4];
-      dropout_mult4(dtree, tree_key, e >> 2, mm);
-      m0 = (e & 2) ? mm[2] : mm[0]; m1 = (e & 2) ? mm[3] : mm[1];
+      m0 = dropout_mult1(dtree, tree_key, e);
+      m1 = dropout_mult1(dtree, tree_key, e + 1);
     }
     // backward needs z of pre.3 for this row: issue the loads now, use them at the end
     float4 zv[NF4];
@@ -655,7 +654,14 @@ __global__ void __launch_bounds__(256) head_kernel(HeadParams p) {
       for (int i = 0; i < NF4; ++i) {
         const int j = i * 128 + lane * 4;
         float mm[4] = {1.f, 1.f, 1.f, 1.f};
-        if (dpre.p > 0.f) dropout_mult4(dpre, pre_key, (static_cast<uint64_t>(b) * H + j) >> 2, mm);
+        if (dpre.p > 0.f) {
+          // this lane's 4 elements are one half of an 8-element dropout group (lane parity picks the half)
+          float m8[8];
+          dropout_mult8(dpre, pre_key, (static_cast<uint64_t>(b) * H + j) >> 3, m8);
+          const bool hi_half = (lane & 1) != 0;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) mm[q] = hi_half ? m8[4 + q] : m8[q];
+        }
         const float4 z = zv[i];
         float4 a = acc[i];
         a.x *= gelu_erf_grad(z.x) * mm[0]; a.y *= gelu_erf_grad(z.y) * mm[1];
@@ -709,18 +715,21 @@ struct GateParams {
   __nv_bfloat16* out_hi; __nv_bfloat16* out_lo;
   float drop_p; int stream; int training;
   const DevState* state;
-  size_t n;       // elements, multiple of 4
+  size_t n;       // elements, multiple of 8
 };
 __global__ void __launch_bounds__(256) gate_kernel(GateParams p) {
   const DropCfg dc = make_dropcfg(p.training ? p.drop_p : 0.f,
                                   (static_cast<uint64_t>(p.state->rng[1]) << 32) | p.state->rng[0]);
-  for (size_t i = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 4; i < p.n;
-       i += static_cast<size_t>(gridDim.x) * blockDim.x * 4) {
-    const float4 d = ldg_f4(p.dy + i), z = ldg_f4(p.z + i);
-    float mm[4] = {1.f, 1.f, 1.f, 1.f};
-    if (dc.p > 0.f) dropout_mult4(dc, stream_key(p.state->rng, p.stream), i >> 2, mm);
-    store_bf2(p.out_hi, p.out_lo, i, d.x * gelu_erf_grad(z.x) * mm[0], d.y * gelu_erf_grad(z.y) * mm[1]);
-    store_bf2(p.out_hi, p.out_lo, i + 2, d.z * gelu_erf_grad(z.z) * mm[2], d.w * gelu_erf_grad(z.w) * mm[3]);
+  for (size_t i = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 8; i < p.n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x * 8) {
+    float mm[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f};
+    if (dc.p > 0.f) dropout_mult8(dc, stream_key(p.state->rng, p.stream), i >> 3, mm);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const float4 d = ldg_f4(p.dy + i + 4 * h), z = ldg_f4(p.z + i + 4 * h);
+      store_bf2(p.out_hi, p.out_lo, i + 4 * h, d.x * gelu_erf_grad(z.x) * mm[4 * h], d.y * gelu_erf_grad(z.y) * mm[4 * h + 1]);
+      store_bf2(p.out_hi, p.out_lo, i + 4 * h + 2, d.z * gelu_erf_grad(z.z) * mm[4 * h + 2], d.w * gelu_erf_grad(z.w) * mm[4 * h + 3]);
+    }
   }
 }
 
@@ -729,12 +738,12 @@ __global__ void __launch_bounds__(256) gate_kernel(GateParams p) {
 __global__ void dropout_mask_kernel(float* out, size_t n, float p, int stream, const DevState* state) {
   const DropCfg dc = make_dropcfg(p, (static_cast<uint64_t>(state->rng[1]) << 32) | state->rng[0]);
   const uint32_t salt = (stream >= 3 ? state->rng[3] : state->rng[2]) + 1u;
-  for (size_t i4 = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i4 * 4 < n;
-       i4 += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    float mm[4];
-    dropout_mult4(dc, static_cast<uint32_t>(stream) ^ (salt << 8), i4, mm);
-    for (int q = 0; q < 4; ++q)
-      if (i4 * 4 + q < n) out[i4 * 4 + q] = mm[q];
+  for (size_t i8 = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i8 * 8 < n;
+       i8 += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    float mm[8];
+    dropout_mult8(dc, static_cast<uint32_t>(stream) ^ (salt << 8), i8, mm);
+    for (int q = 0; q < 8; ++q)
+      if (i8 * 8 + q < n) out[i8 * 8 + q] = mm[q];
   }
 }
 
