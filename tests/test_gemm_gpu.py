@@ -61,6 +61,14 @@ CASES = [
     (512, 512, 4, 1, 1, 64, 1),
     (24, 512, 300, 1, 1, 128, 1),
     (128, 128, 128, 1, 0, 128, 1),
+    # narrow tiles / deep rings / distributed split-K fix-up (the configurations the batch-128 step uses)
+    (128, 512, 512, 0, 0, 16, 1),
+    (128, 2560, 768, 0, 0, 32, 1),
+    (128, 1024, 8192, 0, 0, 128, 16),
+    (128, 512, 1024, 0, 0, 16, 4),
+    (128, 64, 2048, 0, 0, 16, 16),
+    (77, 512, 1536, 0, 1, 64, 3),
+    (128, 512, 4096, 0, 0, 64, 7),
 ]
 
 

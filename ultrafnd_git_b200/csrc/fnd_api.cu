@@ -50,7 +50,7 @@ static int build_tables(Plan& P) {
       e.bf_pitch = 5 * H;
     }
     FND_OK(add_problem(P, P.fwd_proj, tb.act("xbf", P.xoff[i], P.dsum, false), tb.weight(key + ".weight", P.xdim[i], false),
-                       B, H, P.xdim[i], 64, 1, e, ""));
+                       B, H, P.xdim[i], P.cfg_proj.bn, 1, e, "", 1));
   }
   P.fwd_qkv.kind = 0;
   for (int g = 0; g < 4; ++g) {
@@ -58,7 +58,7 @@ static int build_tables(Plan& P) {
     e.bias = P.W(std::string(qg[g].first) + ".bias");
     e.out_f32 = P.buf<float>("Q") + qg[g].q_col; e.f32_pitch = 9 * H;
     FND_OK(add_problem(P, P.fwd_qkv, tb.act("pbf", qg[g].in_col, 5 * H, false),
-                       tb.weight(std::string(qg[g].first) + ".weight", H, false), B, qg[g].n, H, 64, 1, e, ""));
+                       tb.weight(std::string(qg[g].first) + ".weight", H, false), B, qg[g].n, H, P.cfg_qkv.bn, 1, e, "", 1));
   }
   {
     P.fwd_f0.kind = 0;
@@ -68,7 +68,7 @@ static int build_tables(Plan& P) {
     e.act = 1; e.drop_p = d.fusion_dropout; e.drop_stream = kStreamFuse0;
     e.out_hi = P.buf<__nv_bfloat16>("h1_hi"); e.out_lo = P.buf<__nv_bfloat16>("h1_lo"); e.bf_pitch = 2 * H;
     FND_OK(add_problem(P, P.fwd_f0, tb.act("fused_cat", 0, catw, false), tb.weight("fusion.fuse_mlp.0.weight", catw, false),
-                       B, 2 * H, catw, 64, P.splits_f0, e, "f0"));
+                       B, 2 * H, catw, P.cfg_f0.bn, P.cfg_f0.splits, e, "f0", 1));
   }
   {
     P.fwd_f1.kind = 0;
@@ -79,7 +79,7 @@ static int build_tables(Plan& P) {
     e.out_f32 = P.buf<float>("fused"); e.f32_pitch = H;
     e.out_hi = P.buf<__nv_bfloat16>("fusedbf_hi"); e.out_lo = P.buf<__nv_bfloat16>("fusedbf_lo"); e.bf_pitch = H;
     FND_OK(add_problem(P, P.fwd_f1, tb.act("h1", 0, 2 * H, false), tb.weight("fusion.fuse_mlp.3.weight", 2 * H, false),
-                       B, H, 2 * H, 64, P.splits_f1, e, "f1"));
+                       B, H, 2 * H, P.cfg_f1.bn, P.cfg_f1.splits, e, "f1", 1));
   }
   {
     P.fwd_p0.kind = 0;
@@ -92,7 +92,7 @@ static int build_tables(Plan& P) {
     e.out_pre = P.buf<float>("z_p0"); e.pre_pitch = H;
     e.act = 1; e.drop_p = d.clf_dropout; e.drop_stream = kStreamPre0;
     e.out_hi = P.buf<__nv_bfloat16>("xp1_hi"); e.out_lo = P.buf<__nv_bfloat16>("xp1_lo"); e.bf_pitch = H;
-    FND_OK(add_problem(P, P.fwd_p0, tb.act("fusedbf", 0, H, false), tb.weight_rp(false), B, H, H, 64, 1, e, ""));
+    FND_OK(add_problem(P, P.fwd_p0, tb.act("fusedbf", 0, H, false), tb.weight_rp(false), B, H, H, P.cfg_pre.bn, 1, e, "", 1));
   }
   {
     P.fwd_p1.kind = 0;
@@ -102,7 +102,7 @@ static int build_tables(Plan& P) {
     e.act = 1; e.drop_p = d.clf_dropout; e.drop_stream = kStreamPre1;
     e.out_f32 = P.buf<float>("h"); e.f32_pitch = H;
     e.out_hi = P.buf<__nv_bfloat16>("hbf_hi"); e.out_lo = P.buf<__nv_bfloat16>("hbf_lo"); e.bf_pitch = H;
-    FND_OK(add_problem(P, P.fwd_p1, tb.act("xp1", 0, H, false), tb.weight("clf.pre.3.weight", H, false), B, H, H, 64, 1, e, ""));
+    FND_OK(add_problem(P, P.fwd_p1, tb.act("xp1", 0, H, false), tb.weight("clf.pre.3.weight", H, false), B, H, H, P.cfg_pre.bn, 1, e, "", 1));
   }
 
   // ---------------- dgrad (A = dY K-major, B = W viewed MN-major) ----------------
@@ -111,7 +111,7 @@ static int build_tables(Plan& P) {
     EpiParams e = epi_zero();
     e.gate_z = P.buf<float>("z_p0"); e.gate_pitch = H; e.gate_p = d.clf_dropout; e.gate_stream = kStreamPre0;
     e.out_hi = P.buf<__nv_bfloat16>("dz_p0_hi"); e.out_lo = P.buf<__nv_bfloat16>("dz_p0_lo"); e.bf_pitch = H;
-    FND_OK(add_problem(P, P.dg_p1, tb.act("dz_p1", 0, H, false), tb.weight("clf.pre.3.weight", H, true), B, H, H, 64, 1, e, ""));
+    FND_OK(add_problem(P, P.dg_p1, tb.act("dz_p1", 0, H, false), tb.weight("clf.pre.3.weight", H, true), B, H, H, P.cfg_dg_pre.bn, 1, e, "", 1));
   }
   for (int fusedpath = 0; fusedpath < 2; ++fusedpath) {
     GemmTable& T = fusedpath ? P.dg_p0_fused : P.dg_p0_split;
@@ -123,7 +123,7 @@ static int build_tables(Plan& P) {
     } else {
       e.out_f32 = P.buf<float>("dfused"); e.f32_pitch = H;
     }
-    FND_OK(add_problem(P, T, tb.act("dz_p0", 0, H, false), tb.weight_rp(true), B, H, H, 64, 1, e, ""));
+    FND_OK(add_problem(P, T, tb.act("dz_p0", 0, H, false), tb.weight_rp(true), B, H, H, P.cfg_dg_pre.bn, 1, e, "", 1));
   }
   {
     P.dg_f1.kind = 1;
@@ -131,14 +131,14 @@ static int build_tables(Plan& P) {
     e.gate_z = P.buf<float>("z_f0"); e.gate_pitch = 2 * H; e.gate_p = d.fusion_dropout; e.gate_stream = kStreamFuse0;
     e.out_hi = P.buf<__nv_bfloat16>("dz_f0_hi"); e.out_lo = P.buf<__nv_bfloat16>("dz_f0_lo"); e.bf_pitch = 2 * H;
     FND_OK(add_problem(P, P.dg_f1, tb.act("dz_f1", 0, H, false), tb.weight("fusion.fuse_mlp.3.weight", 2 * H, true),
-                       B, 2 * H, H, 64, 1, e, ""));
+                       B, 2 * H, H, P.cfg_dg_f1.bn, P.cfg_dg_f1.splits, e, "dgf1", 1));
   }
   {
     P.dg_f0.kind = 1;
     EpiParams e = epi_zero();
     e.out_f32 = P.buf<float>("dcat"); e.f32_pitch = catw;
     FND_OK(add_problem(P, P.dg_f0, tb.act("dz_f0", 0, 2 * H, false), tb.weight("fusion.fuse_mlp.0.weight", catw, true),
-                       B, catw, 2 * H, 64, 1, e, ""));
+                       B, catw, 2 * H, P.cfg_dg_f0.bn, P.cfg_dg_f0.splits, e, "dgf0", 1));
   }
   P.dg_qkv.kind = 1;
   for (int g = 0; g < 4; ++g) {
@@ -148,14 +148,14 @@ static int build_tables(Plan& P) {
     e.out_lo = P.buf<__nv_bfloat16>("dP_lo") ? P.buf<__nv_bfloat16>("dP_lo") + qg[g].in_col : nullptr;
     e.bf_pitch = 5 * H;
     FND_OK(add_problem(P, P.dg_qkv, tb.act("dQ", qg[g].q_col, 9 * H, false),
-                       tb.weight(std::string(qg[g].first) + ".weight", H, true), B, H, qg[g].n, 64, 1, e, ""));
+                       tb.weight(std::string(qg[g].first) + ".weight", H, true), B, H, qg[g].n, P.cfg_dg_qkv.bn, 1, e, "", 1));
   }
 
   // ---------------- wgrad (dW[N_out, K_in] = dY^T X; both operands MN-major; contraction = batch) -------------
   auto wg = [&](GemmTable& T, const Operand& dY, const Operand& X, int n_out, int k_in, float* dst, int pitch) -> int {
     EpiParams e = epi_zero();
     e.out_f32 = dst; e.f32_pitch = pitch;
-    return add_problem(P, T, dY, X, n_out, k_in, B, 128, 1, e, "");
+    return add_problem(P, T, dY, X, n_out, k_in, B, 128, 1, e, "", 0);
   };
   auto build_wg = [&](GemmTable& T, bool clf, bool fus) -> int {
     T.kind = 2;
@@ -273,16 +273,26 @@ static inline RunCtx make_ctx(const Plan& P, int training) {
   c.dbg = dbg ? dbg + static_cast<size_t>((Pm.dbg_launch++) % 40) * 1024 * 8 : nullptr;
   return c;
 }
+// PDL chaining: the first launch of an entry point is an ordinary launch (full dependency on whatever precedes it in
+// the stream); every later launch of the same entry point carries the programmatic-serialization attribute.
+static bool take_pdl(const Plan& Pc) {
+  Plan& P = const_cast<Plan&>(Pc);
+  const bool v = P.pdl_next;
+  P.pdl_next = true;
+  return v;
+}
 static void mark(const Plan& Pc, const char* name, cudaStream_t st) {
   Plan& P = const_cast<Plan&>(Pc);
   if (!P.profiling) return;
+  P.pdl_next = false;          // an event record sits between the two kernels
   cudaEvent_t ev;
   if (cudaEventCreate(&ev) != cudaSuccess) return;
   cudaEventRecord(ev, st);
   P.marks.emplace_back(name, ev);
 }
 static int run_gemm(const Plan& P, const GemmTable& T, int training, cudaStream_t st, const char* name) {
-  FND_CUDA_OK(launch_gemm(T.kind, T.host.data(), static_cast<int>(T.host.size()), T.grid, make_ctx(P, training), st));
+  FND_CUDA_OK(launch_gemm(T.kind, T.host.data(), static_cast<int>(T.host.size()), T.grid, make_ctx(P, training), st,
+                          take_pdl(P)));
   mark(P, name, st);
   return 0;
 }
@@ -304,8 +314,7 @@ static int run_prep(Plan& P, const fnd_inputs* in, int training, bool bump_clf, 
   pp.gates = P.W("clf.node.trees.0.gates.0"); pp.alpha = P.buf<float>("alpha");
   pp.TD = P.TD; pp.H = P.H;
   pp.rng = P.state()->rng; pp.bump_fusion = training ? 1 : 0; pp.bump_clf = (training && bump_clf) ? 1 : 0;
-  prep_kernel<<<P.B + P.TD, kRowThreads, 0, st>>>(pp);
-  FND_CUDA_OK(cudaGetLastError());
+  FND_CUDA_OK(launch_k(prep_kernel, P.B + P.TD, kRowThreads, 0, st, take_pdl(P), pp));
   mark(P, "prep", st);
   return 0;
 }
@@ -328,9 +337,8 @@ static int run_assemble_fwd(Plan& P, cudaStream_t st) {
   a.rowstat = P.buf<float>("rowstat");
   a.B = P.B; a.H = P.H; a.use_gnn = P.d.use_gnn;
   const int grid = P.B < 1184 ? P.B : 1184;
-  if (P.H == 512) assemble_fwd_kernel<1><<<grid, kRowThreads, 0, st>>>(a);
-  else assemble_fwd_kernel<2><<<grid, kRowThreads, 0, st>>>(a);
-  FND_CUDA_OK(cudaGetLastError());
+  if (P.H == 512) FND_CUDA_OK(launch_k(assemble_fwd_kernel<1>, grid, kRowThreads, 0, st, take_pdl(P), a));
+  else FND_CUDA_OK(launch_k(assemble_fwd_kernel<2>, grid, kRowThreads, 0, st, take_pdl(P), a));
   mark(P, "assemble_fwd", st);
   return 0;
 }
@@ -345,9 +353,8 @@ static int run_assemble_bwd(Plan& P, cudaStream_t st) {
   a.dP_hi = P.buf<__nv_bfloat16>("dP_hi"); a.dP_lo = P.buf<__nv_bfloat16>("dP_lo");
   a.ev_partial = P.buf<float>("ev_partial"); a.evstride = P.L.evstride;
   a.B = P.B; a.H = P.H; a.use_gnn = P.d.use_gnn;
-  if (P.H == 512) assemble_bwd_kernel<1><<<P.n_asm_ctas, kRowThreads, 0, st>>>(a);
-  else assemble_bwd_kernel<2><<<P.n_asm_ctas, kRowThreads, 0, st>>>(a);
-  FND_CUDA_OK(cudaGetLastError());
+  if (P.H == 512) FND_CUDA_OK(launch_k(assemble_bwd_kernel<1>, P.n_asm_ctas, kRowThreads, 0, st, take_pdl(P), a));
+  else FND_CUDA_OK(launch_k(assemble_bwd_kernel<2>, P.n_asm_ctas, kRowThreads, 0, st, take_pdl(P), a));
   mark(P, "assemble_bwd", st);
   return 0;
 }
@@ -380,10 +387,10 @@ static int run_head(const Plan& P, const HeadParams& h, cudaStream_t st) {
   const size_t smem = static_cast<size_t>(P.TD + 2) * P.H * sizeof(float) + 8 * (P.TD + 2) * 33 * sizeof(float);
   if (P.H == 512) {
     FND_CUDA_OK(cudaFuncSetAttribute(head_kernel<FWD, CE, BWD, 4, 6, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    head_kernel<FWD, CE, BWD, 4, 6, 4><<<grid, 256, smem, st>>>(h);
+    FND_CUDA_OK(launch_k(head_kernel<FWD, CE, BWD, 4, 6, 4>, grid, 256, smem, st, take_pdl(P), h));
   } else {
     FND_CUDA_OK(cudaFuncSetAttribute(head_kernel<FWD, CE, BWD, 8, 6, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    head_kernel<FWD, CE, BWD, 8, 6, 4><<<grid, 256, smem, st>>>(h);
+    FND_CUDA_OK(launch_k(head_kernel<FWD, CE, BWD, 8, 6, 4>, grid, 256, smem, st, take_pdl(P), h));
   }
   FND_CUDA_OK(cudaGetLastError());
   mark(P, "head", st);
@@ -398,8 +405,7 @@ static int run_finalize(Plan& P, const FinTable& T, int slot_base, int total_slo
   f.slots = P.buf<float>("slots"); f.slot_base = slot_base; f.total_slots = total_slots;
   f.loss_row = with_loss ? P.buf<float>("loss_row") : nullptr; f.B = P.B;
   f.state = P.state(); f.update_step = update_step;
-  finalize_kernel<<<T.grid, 256, 0, st>>>(f);
-  FND_CUDA_OK(cudaGetLastError());
+  FND_CUDA_OK(launch_k(finalize_kernel, T.grid, 256, 0, st, take_pdl(P), f));
   mark(P, "finalize", st);
   return 0;
 }
@@ -432,10 +438,8 @@ static int fusion_forward_impl(Plan& P, const fnd_inputs* in, int training, bool
   return 0;
 }
 static int fusion_head_impl(Plan& P, cudaStream_t st) {   // fusion.classifier: returned for API parity only
-  rowlinear2_fwd_kernel<<<ceil_div(P.B, 8), 256, 0, st>>>(P.buf<float>("fused"), P.W("fusion.classifier.weight"),
-                                                          P.W("fusion.classifier.bias"), P.buf<float>("fusion_logits"),
-                                                          P.B, P.H);
-  FND_CUDA_OK(cudaGetLastError());
+  FND_CUDA_OK(launch_k(rowlinear2_fwd_kernel, ceil_div(P.B, 8), 256, 0, st, take_pdl(P), P.buf<float>("fused"),
+                       P.W("fusion.classifier.weight"), P.W("fusion.classifier.bias"), P.buf<float>("fusion_logits"), P.B, P.H));
   mark(P, "fusion_head", st);
   return 0;
 }
@@ -451,6 +455,7 @@ static Plan* as_plan(void* p) { return static_cast<Plan*>(p); }
   if (!PP) return -1;                    \
   if (!PP->bound) return -5;             \
   Plan& P = *PP;                         \
+  P.pdl_next = false;                    \
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream)
 
 extern "C" {
@@ -635,8 +640,7 @@ int fnd_classifier_forward(void* plan, const float* fused, const float* aux, int
     pp.out_hi = P.buf<__nv_bfloat16>("fusedbf_hi"); pp.out_lo = P.buf<__nv_bfloat16>("fusedbf_lo");
     pp.B = P.B; pp.gates = P.W("clf.node.trees.0.gates.0"); pp.alpha = P.buf<float>("alpha"); pp.TD = P.TD; pp.H = P.H;
     pp.rng = P.state()->rng; pp.bump_clf = training ? 1 : 0;
-    prep_kernel<<<P.B + P.TD, kRowThreads, 0, st>>>(pp);
-    FND_CUDA_OK(cudaGetLastError());
+    FND_CUDA_OK(launch_k(prep_kernel, P.B + P.TD, kRowThreads, 0, st, take_pdl(P), pp));
   }
   FND_OK(classifier_gemms_impl(P, training, st));
   HeadParams h = head_params(P, training);
@@ -670,8 +674,9 @@ int fnd_fusion_backward(void* plan, const float* dfused, const float* dfusion_lo
     // d fused += dlogits . W_classifier   (fusion.classifier, cross_modal_transformer.py:198)
     float* acc = P.buf<float>("dfused");
     if (df != acc) FND_CUDA_OK(cudaMemcpyAsync(acc, df, static_cast<size_t>(P.B) * P.H * 4, cudaMemcpyDeviceToDevice, st));
-    rowlinear2_dgrad_kernel<<<P.B, 256, 0, st>>>(dfusion_logits, P.W("fusion.classifier.weight"), acc, P.B, P.H, 1);
-    FND_CUDA_OK(cudaGetLastError());
+    P.pdl_next = false;     // a memcpy node may precede this launch
+    FND_CUDA_OK(launch_k(rowlinear2_dgrad_kernel, P.B, 256, 0, st, take_pdl(P), dfusion_logits,
+                         P.W("fusion.classifier.weight"), acc, P.B, P.H, 1));
     df = acc;
   }
   GateParams g;
@@ -680,8 +685,7 @@ int fnd_fusion_backward(void* plan, const float* dfused, const float* dfusion_lo
   g.out_hi = P.buf<__nv_bfloat16>("dz_f1_hi"); g.out_lo = P.buf<__nv_bfloat16>("dz_f1_lo");
   g.drop_p = P.d.fusion_dropout; g.stream = kStreamFuse1; g.training = tr; g.state = P.state();
   g.n = static_cast<size_t>(P.B) * P.H;
-  gate_kernel<<<ceil_div(static_cast<int>(g.n / 8), 256), 256, 0, st>>>(g);
-  FND_CUDA_OK(cudaGetLastError());
+  FND_CUDA_OK(launch_k(gate_kernel, ceil_div(static_cast<int>(g.n / 8), 256), 256, 0, st, take_pdl(P), g));
   FND_OK(run_gemm(P, P.dg_f1, tr, st, "dgrad_fuse1"));
   FND_OK(run_gemm(P, P.dg_f0, tr, st, "dgrad_fuse0"));
   FND_OK(run_assemble_bwd(P, st));
@@ -697,19 +701,15 @@ int fnd_clip_adamw_step(void* plan, int norm_from_slots, void* stream) {
     // norm over the (possibly all-reduced) gradient arena + optimizer-step bookkeeping
     float* slots = P.buf<float>("slots");
     const int nb = 148 * 4;
-    sumsq_kernel<<<nb, 256, 0, st>>>(P.grads, static_cast<size_t>(P.L.n_hot), slots + kSlotSumsq);
-    FND_CUDA_OK(cudaGetLastError());
-    norm_finish_kernel<<<1, 256, 0, st>>>(slots + kSlotSumsq, nb, P.state(), 1);
-    FND_CUDA_OK(cudaGetLastError());
+    FND_CUDA_OK(launch_k(sumsq_kernel, nb, 256, 0, st, take_pdl(P), P.grads, static_cast<size_t>(P.L.n_hot), slots + kSlotSumsq));
+    FND_CUDA_OK(launch_k(norm_finish_kernel, 1, 256, 0, st, take_pdl(P), slots + kSlotSumsq, nb, P.state(), 1));
     mark(P, "grad_norm", st);
   } else {
-    step_kernel<<<1, 32, 0, st>>>(P.state());
-    FND_CUDA_OK(cudaGetLastError());
+    FND_CUDA_OK(launch_k(step_kernel, 1, 32, 0, st, take_pdl(P), P.state()));
     mark(P, "step_bookkeeping", st);
   }
   AdamWParams a = adamw_params(P);
-  adamw_kernel<<<148 * 8, 256, 0, st>>>(a);
-  FND_CUDA_OK(cudaGetLastError());
+  FND_CUDA_OK(launch_k(adamw_kernel, 148 * 8, 256, 0, st, take_pdl(P), a));
   mark(P, "adamw", st);
   return 0;
 }
@@ -738,10 +738,10 @@ int fnd_train_step(void* plan, const fnd_inputs* in, void* stream) {
   // finalize (last kernel of fwd_bwd) publishes norm, clip coefficient AND the step bookkeeping; AdamW follows.
   FND_OK(train_fwd_bwd_impl(plan, in, 1, stream));
   FND_PLAN(plan);
+  P.pdl_next = true;        // continues the chain started by train_fwd_bwd_impl
   if (!P.m || !P.v) return -6;
   AdamWParams a = adamw_params(P);
-  adamw_kernel<<<148 * 8, 256, 0, st>>>(a);
-  FND_CUDA_OK(cudaGetLastError());
+  FND_CUDA_OK(launch_k(adamw_kernel, 148 * 8, 256, 0, st, take_pdl(P), a));
   mark(P, "adamw", st);
   return 0;
 }
@@ -811,7 +811,7 @@ int fnd_launch_count(const void* plan, const char* entry) {
 size_t fnd_gemm_scratch_bytes(int M, int N, int bn, int splits) {
   size_t b = align_up(sizeof(GemmProblem), 256);
   b += 256;                                                                   // error flag
-  b += align_up(sizeof(int) * ceil_div(M, kGemmBM) * ceil_div(N, bn), 256);   // split-K counters
+  b += align_up(sizeof(int) * 2 * ceil_div(M, kGemmBM) * ceil_div(N, bn), 256);   // split-K counters (arrive, depart)
   if (splits > 1) b += splitk_ws_floats(M, N, bn, splits) * sizeof(float);
   return b + 256;
 }
@@ -848,7 +848,7 @@ static int gemm_bf16_impl(const void* a_hi, const void* a_lo, int a_pitch, int a
   int* derr = reinterpret_cast<int*>(base + off);
   off += 256;
   int* dctr = reinterpret_cast<int*>(base + off);
-  const size_t ctr_bytes = align_up(sizeof(int) * ceil_div(M, kGemmBM) * ceil_div(N, bn), 256);
+  const size_t ctr_bytes = align_up(sizeof(int) * 2 * ceil_div(M, kGemmBM) * ceil_div(N, bn), 256);
   off += ctr_bytes;
   float* dws = reinterpret_cast<float*>(base + off);
 

@@ -43,6 +43,18 @@ __device__ __forceinline__ bool elect_one() {
 }
 
 // ------------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL). Every kernel of a step is launched with the programmatic-stream-serialization
+// attribute: its CTAs become resident while the previous kernel is still running, do their prologue (barrier init,
+// TMEM allocation, descriptor prefetch, loads of STATIC data such as weights) and then block in griddep_wait() until
+// the previous kernel has completed and its writes are visible.
+// Invariant kept by every kernel here: griddep_launch() is issued only AFTER the kernel's own griddep_wait() has
+// returned, so the pre-wait part of kernel N+1 can overlap kernel N only — never N-1. Data read before the wait must
+// therefore not be written by the IMMEDIATE predecessor; the first kernel of a step is launched without the attribute.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// ------------------------------------------------------------------------------------------
 // mbarrier
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -208,7 +220,7 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n, int a_mn_ma
 // the derivative needs. The epilogues run one warp per scheduler, so instruction count on this path is latency.
 __device__ __forceinline__ void gelu_cdf_pdf(float x, float& cdf, float& pdf) {
   const float ax = fabsf(x) * 0.70710678118654752440f;
-  const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, ax, 1.0f));
   const float e = __expf(-ax * ax);                    // exp(-x^2 / 2)
   const float poly = t * fmaf(t, fmaf(t, fmaf(t, fmaf(t, 1.061405429f, -1.453152027f), 1.421413741f), -0.284496736f), 0.254829592f);
   const float erf_abs = fmaf(-poly, e, 1.0f);

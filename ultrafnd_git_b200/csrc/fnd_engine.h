@@ -140,6 +140,43 @@ struct FinTable {
   int grid = 0;
 };
 
+// Tile width and split-K factor of one GEMM launch (all problems of a launch share them).
+struct GemmCfg { int bn = 64; int splits = 1; };
+
+// At the reference's batch sizes every GEMM is a latency chain: prefer the NARROWEST tile that still fits the launch
+// in one wave of 148 CTAs (more SMs streaming weights, shorter epilogue per CTA). Long-K problems (K >= 2048) take
+// 128-wide tiles instead so the activation panel is re-read by few CTAs, and are split along K (one CTA per SM, see
+// fnd_gemm.cuh) when a CTA would otherwise stream more than ~600 KB by itself.
+inline GemmCfg pick_cfg(int B, const std::vector<std::pair<int, int>>& nk, bool b_mn, int ncombo, bool allow_split) {
+  const int tm = ceil_div(B, kGemmBM);
+  int kmax = 0;
+  for (auto& p : nk) kmax = p.second > kmax ? p.second : kmax;
+  const int kb = ceil_div(kmax, kGemmBK);
+  auto ctas_at = [&](int bn) {
+    int c = 0;
+    for (auto& p : nk) c += tm * ceil_div(p.first, bn);
+    return c;
+  };
+  GemmCfg c;
+  c.bn = 128;
+  if (kb < 32) {
+    const int cands[4] = {16, 32, 64, 128};
+    for (int i = b_mn ? 2 : 0; i < 4; ++i)
+      if (ctas_at(cands[i]) <= 148) { c.bn = cands[i]; break; }
+  }
+  const int ctas = ctas_at(c.bn);
+  const long long per_cta = static_cast<long long>(kb) * ncombo * (kGemmStageBytesA + c.bn * kGemmBK * 2);
+  if (allow_split && nk.size() == 1 && per_cta > 600 * 1024) {
+    int sp = static_cast<int>(per_cta / (256 * 1024));
+    if (sp > 148 / ctas) sp = 148 / ctas;
+    if (sp > 16) sp = 16;
+    if (sp > c.bn / 2) sp = c.bn / 2;
+    if (sp > kb) sp = kb;
+    c.splits = sp < 1 ? 1 : sp;
+  }
+  return c;
+}
+
 struct Plan {
   fnd_dims d;
   ArenaLayout L;
@@ -147,7 +184,7 @@ struct Plan {
   int H = 0, nmod = 0, nslots = 0, dsum = 0, TD = 0, leaves = 0;
   int xoff[5] = {0, 0, 0, 0, 0}, xdim[5] = {0, 0, 0, 0, 0};
   int n_asm_ctas = 0;
-  int splits_f0 = 1, splits_f1 = 1;
+  GemmCfg cfg_proj, cfg_qkv, cfg_f0, cfg_f1, cfg_pre, cfg_dg_pre, cfg_dg_f1, cfg_dg_f0, cfg_dg_qkv;
   bool bound = false;
   int last_training = 0;
   // workspace
@@ -165,6 +202,7 @@ struct Plan {
   int total_slots = 0;
   // optional per-kernel timing (bench/profiling only): an event is recorded after every launch
   int dbg_launch = 0;            // probe builds: index of the next launch's stamp region
+  bool pdl_next = false;         // the next launch may carry the programmatic-serialization attribute
   bool profiling = false;
   std::vector<std::pair<const char*, cudaEvent_t>> marks;
 
@@ -189,15 +227,6 @@ inline void plan_add(Plan& P, const std::string& name, long long bytes) {
 inline void plan_add_bf(Plan& P, const std::string& name, long long elems) {
   plan_add(P, name + "_hi", elems * 2);
   if (P.ncombo == 3) plan_add(P, name + "_lo", elems * 2);
-}
-
-inline int pick_splits(int tiles, int kb_total, int target_ctas) {
-  int s = target_ctas / (tiles > 0 ? tiles : 1);
-  if (s < 1) s = 1;
-  const int max_s = kb_total / 4 > 0 ? kb_total / 4 : 1;   // at least 4 k-blocks per split
-  if (s > max_s) s = max_s;
-  if (s > 32) s = 32;
-  return s;
 }
 
 inline void carve(Plan& P) {
@@ -246,17 +275,29 @@ inline void carve(Plan& P) {
   P.n_asm_ctas = static_cast<int>(B < 296 ? B : 296);
   plan_add(P, "ev_partial", static_cast<long long>(P.n_asm_ctas) * 3 * P.L.evstride * 4);
   (void)TD;
-  // split-K workspaces / counters for the two skinny weight-streaming GEMMs (fuse_mlp.0, fuse_mlp.3)
-  const int tm = ceil_div(P.B, kGemmBM);
-  P.splits_f0 = pick_splits(tm * (2 * P.H / 64), P.nslots * P.H / kGemmBK, 148);
-  P.splits_f1 = pick_splits(tm * (P.H / 64), 2 * P.H / kGemmBK, 148);
-  if (P.splits_f0 > 1) {
-    plan_add(P, "splitws_f0", static_cast<long long>(splitk_ws_floats(P.B, 2 * P.H, 64, P.splits_f0)) * 4);
-    plan_add(P, "splitctr_f0", static_cast<long long>(tm) * (2 * P.H / 64) * 4);
-  }
-  if (P.splits_f1 > 1) {
-    plan_add(P, "splitws_f1", static_cast<long long>(splitk_ws_floats(P.B, P.H, 64, P.splits_f1)) * 4);
-    plan_add(P, "splitctr_f1", static_cast<long long>(tm) * (P.H / 64) * 4);
+  // per-launch tile / split-K configuration; split-K workspaces + (arrive, depart) counters where a launch splits
+  {
+    const int Hh = P.H, cat = P.nslots * P.H, nc = P.ncombo;
+    std::vector<std::pair<int, int>> proj, qkv = {{2 * Hh, Hh}, {3 * Hh, Hh}, {2 * Hh, Hh}, {2 * Hh, Hh}};
+    for (int i = 0; i < P.nmod; ++i) proj.push_back({Hh, P.xdim[i]});
+    P.cfg_proj = pick_cfg(P.B, proj, false, nc, false);
+    P.cfg_qkv = pick_cfg(P.B, qkv, false, nc, false);
+    P.cfg_f0 = pick_cfg(P.B, {{2 * Hh, cat}}, false, nc, true);
+    P.cfg_f1 = pick_cfg(P.B, {{Hh, 2 * Hh}}, false, nc, true);
+    P.cfg_pre = pick_cfg(P.B, {{Hh, Hh}}, false, nc, false);
+    P.cfg_dg_pre = pick_cfg(P.B, {{Hh, Hh}}, true, nc, false);
+    P.cfg_dg_f1 = pick_cfg(P.B, {{2 * Hh, Hh}}, true, nc, true);
+    P.cfg_dg_f0 = pick_cfg(P.B, {{cat, 2 * Hh}}, true, nc, true);
+    P.cfg_dg_qkv = pick_cfg(P.B, {{Hh, 2 * Hh}, {Hh, 3 * Hh}, {Hh, 2 * Hh}, {Hh, 2 * Hh}}, true, nc, false);
+    auto split_bufs = [&](const char* tag, const GemmCfg& c, int N) {
+      if (c.splits <= 1) return;
+      plan_add(P, std::string("splitws_") + tag, static_cast<long long>(splitk_ws_floats(P.B, N, c.bn, c.splits)) * 4);
+      plan_add(P, std::string("splitctr_") + tag, static_cast<long long>(ceil_div(P.B, kGemmBM)) * ceil_div(N, c.bn) * 2 * 4);
+    };
+    split_bufs("f0", P.cfg_f0, 2 * Hh);
+    split_bufs("f1", P.cfg_f1, Hh);
+    split_bufs("dgf1", P.cfg_dg_f1, 2 * Hh);
+    split_bufs("dgf0", P.cfg_dg_f0, cat);
   }
   if (getenv("FND_DEBUG_STAMPS")) plan_add(P, "dbg", 8LL * 8 * 1024 * 40);     // clock64 stamps of the row kernels (probes)
   // per-CTA sum-of-squares slots (wgrad CTAs + finalize CTAs); generous upper bound, zero-initialised at bind
@@ -311,7 +352,7 @@ inline EpiParams epi_zero() {
 struct SplitAlloc { std::string ws_name, ctr_name; };
 
 inline int add_problem(Plan& P, GemmTable& T, const Operand& A, const Operand& B, int M, int N, int K, int bn, int splits,
-                       const EpiParams& epi, const std::string& tag) {
+                       const EpiParams& epi, const std::string& tag, int b_static) {
   GemmProblem g;
   float* ws = nullptr;
   int* ctr = nullptr;
@@ -327,7 +368,7 @@ inline int add_problem(Plan& P, GemmTable& T, const Operand& A, const Operand& B
     ctr = P.buf<int>("splitctr_" + tag);
     if (!ws || !ctr) return -30;
   }
-  int r = fill_problem(g, A, B, M, N, K, bn, splits, P.ncombo, kEvictNormal, kEvictNormal, ws, ctr, epi);
+  int r = fill_problem(g, A, B, M, N, K, bn, splits, P.ncombo, kEvictNormal, kEvictNormal, ws, ctr, epi, b_static);
   if (r) return r;
   T.host.push_back(g);
   return 0;

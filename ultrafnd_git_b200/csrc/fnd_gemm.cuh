@@ -2,22 +2,31 @@
 //
 //   C[M,N] = sum_k A[m,k] * B[n,k]      (bf16 operands, fp32 accumulation in TMEM)
 //
-// One launch runs a TABLE of independent problems (GemmProblem, in device memory); each CTA owns one
-// (tile_m, tile_n, k-split) work item of one problem.  Operands arrive by TMA (SWIZZLE_128B) into a
-// 3-stage shared-memory ring, a single elected thread issues tcgen05.mma (UMMA 128 x BN x 16), the
-// accumulator lives in TMEM and four epilogue warps read it back with tcgen05.ld.
+// One launch runs a TABLE of independent problems (GemmProblem, passed by value in kernel-parameter space); each CTA
+// owns one (tile_m, tile_n, k-split) work item of one problem. Operands arrive by TMA (SWIZZLE_128B) into a deep
+// shared-memory ring (as many stages as fit in ~208 KB: 6..11), a single elected thread issues tcgen05.mma
+// (UMMA 128 x BN x 16, BN = 16/32/64/128), the accumulator lives in TMEM and EIGHT epilogue warps (two per TMEM lane
+// quarter, splitting the column groups) read it back with tcgen05.ld.
 //
-// Either operand may be K-major (contraction index contiguous in memory: activations x weights of
-// nn.Linear) or MN-major (row index contiguous: what dgrad needs for W and wgrad needs for dY and X),
-// selected by template flags, so forward, dgrad and wgrad all read the SAME row-major tensors — no
-// transposed copies are ever materialised.
+// Why this shape: at the reference's batch (128) every GEMM of the step is a latency chain, not a throughput problem
+// (DESIGN.md §4). The ring is deep enough that ALL k-blocks of a K<=512 problem are in flight at once; narrow tiles
+// put 16..144 CTAs on the 148 SMs instead of 8; two epilogue warps per scheduler hide each other's dependent-issue
+// latency; and the kernel is PDL-aware: it becomes resident under its predecessor, sets up barriers/TMEM and already
+// streams its WEIGHT tiles (static data) before griddepcontrol.wait releases the activation loads.
 //
-// Precision modes: ncombo == 1 is plain bf16; ncombo == 3 is "fp32x3": every operand is stored as a
-// bf16 (hi, lo) pair and the k-loop runs the three products Ah*Bh + Ah*Bl + Al*Bh, which reproduces
-// fp32 GEMM to ~2^-17 relative while staying on the tensor pipe.
+// Either operand may be K-major (contraction index contiguous in memory: activations x weights of nn.Linear) or
+// MN-major (row index contiguous: what dgrad needs for W and wgrad needs for dY and X), selected by launch-uniform
+// flags, so forward, dgrad and wgrad all read the SAME row-major tensors — no transposed copies are ever materialised.
 //
-// Split-K: each split writes its fp32 partial tile to a workspace, bumps a per-tile counter, and the
-// LAST arriving CTA sums the partials in split order (deterministic) and runs the epilogue.
+// Precision modes: ncombo == 1 is plain bf16; ncombo == 3 is "fp32x3": every operand is stored as a bf16 (hi, lo)
+// pair and the k-loop runs the three products Ah*Bh + Ah*Bl + Al*Bh, which reproduces fp32 GEMM to ~2^-17 relative
+// while staying on the tensor pipe.
+//
+// Split-K: the `splits` CTAs of one output tile are co-resident (the host keeps split launches <= 148 CTAs, one CTA
+// per SM). Each writes its fp32 partial tile to an L2-resident workspace and arrives on a per-tile counter; once all
+// have arrived EVERY CTA of the tile finishes a disjoint share of the tile (32-row x 8-column units, round-robin over
+// the splits), summing the partials in fixed split order (deterministic) and running the epilogue on its share — the
+// fix-up is spread over all splits instead of serialising on the last arriver.
 //
 // Replaces (reference, all via ATen addmm on CPU): nn.Linear forward/backward at
 //   src/models/fusion/cross_modal_transformer.py:96-102,122-129,147-150,186,197 and
@@ -29,12 +38,13 @@ namespace fnd {
 
 constexpr int kGemmBM = 128;          // UMMA M (rows of A per tile)
 constexpr int kGemmBK = 64;           // contraction elements per stage (128 B of bf16)
-constexpr int kGemmStages = 3;
+constexpr int kGemmMaxStages = 12;
 constexpr int kGemmStageBytesA = kGemmBM * kGemmBK * 2;   // 16 KB
-constexpr int kGemmStageBytesB = 128 * kGemmBK * 2;       // 16 KB (BN <= 128)
-constexpr int kGemmStageBytes = kGemmStageBytesA + kGemmStageBytesB;
-constexpr int kGemmSmemBytes = kGemmStages * kGemmStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
-constexpr int kGemmThreads = 192;     // warp0 TMA, warp1 MMA+TMEM, warps2-5 epilogue
+constexpr int kGemmOperandBudget = 208 * 1024;            // operand ring
+constexpr int kGemmSmemBytes = kGemmOperandBudget + 1024 /*align slack*/ + 512 /*barriers*/;
+constexpr int kGemmEpiWarps = 8;
+constexpr int kGemmEpiThreads = kGemmEpiWarps * 32;
+constexpr int kGemmThreads = 64 + kGemmEpiThreads;        // warp0 TMA, warp1 MMA+TMEM, warps2-9 epilogue
 constexpr int kGemmTmemCols = 128;
 
 // Everything the epilogue may do to an accumulator value v at (m, n), in this order.
@@ -69,10 +79,12 @@ struct alignas(128) GemmProblem {
   int tiles_m, tiles_n, splits, kb_per_split, kb_total;
   int cta_begin, cta_count;
   int ncombo;                        // 1 bf16, 3 fp32x3
-  int bn;                            // tile width: 32/64/128 (MN-major B: 64/128)
+  int bn;                            // tile width: 16/32/64/128 (MN-major B: 64/128)
+  int nstages, stage_bytes;          // operand ring geometry (host: fill_problem)
+  int b_static;                      // 1: operand B is static data (weights): its loads may precede griddepcontrol.wait
   unsigned long long hintA, hintB;   // L2 eviction hints for the two operand streams
   float* splitk_ws;                  // [tiles][splits][bn/8][128][8] fp32
-  int* splitk_ctr;                   // [tiles], zero between launches
+  int* splitk_ctr;                   // [tiles][2] (arrive, depart), zero between launches
   EpiParams epi;
 };
 
@@ -84,18 +96,104 @@ struct RunCtx {
 };
 #define FND_STAMP(i) do { if (ctx.dbg) ctx.dbg[static_cast<size_t>(blockIdx.x) * 8 + (i)] = clock64(); } while (0)
 
-__device__ __forceinline__ void epi_named_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epi_named_barrier() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 // The problem table travels BY VALUE in kernel-parameter space (constant bank): no global-memory fetch of table or
 // TMA descriptors sits on the critical path of a launch (after an L2 flush those were two dependent HBM round trips).
 // ONE kernel binary serves forward, dgrad and wgrad (operand majorness is a launch-uniform runtime flag): a training
-// step issues 13 GEMM launches, and sharing the code keeps it warm in the instruction caches between them.
+// step issues 12 GEMM launches, and sharing the code keeps it warm in the instruction caches between them.
 constexpr int kGemmTableCap = 16;
 struct GemmTableP {
   GemmProblem p[kGemmTableCap];
   int nprob;
   int a_mn, b_mn;     // 0: K-major, 1: MN-major
 };
+
+struct EpiCtx {
+  DropCfg dfw, dbw;
+  uint32_t key_fw, key_bw;
+};
+
+// One 8-column group of one output row: everything that happens after the accumulator value is known.
+__device__ __forceinline__ float epi_group(const EpiParams& E, const EpiCtx& X, float (&v)[8], int m, int n0, int PN,
+                                           float a0, float a1) {
+  if (E.bias) {
+    const float4 b0 = ldg_f4(E.bias + n0), b1 = ldg_f4(E.bias + n0 + 4);
+    v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+    v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+  }
+  if (E.aux) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float2 w = __ldg(reinterpret_cast<const float2*>(E.aux_w + static_cast<size_t>(n0 + j) * E.aux_w_pitch));
+      v[j] = fmaf(a0, w.x, fmaf(a1, w.y, v[j]));
+    }
+  }
+  if (E.add_in) {
+    const float* src = E.add_in + static_cast<size_t>(m) * E.add_pitch + n0;
+    const float4 t0 = ldg_f4(src), t1 = ldg_f4(src + 4);
+    v[0] += t0.x; v[1] += t0.y; v[2] += t0.z; v[3] += t0.w;
+    v[4] += t1.x; v[5] += t1.y; v[6] += t1.z; v[7] += t1.w;
+  }
+  if (E.out_pre) {
+    float* dst = E.out_pre + static_cast<size_t>(m) * E.pre_pitch + n0;
+    *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
+  }
+  if (E.act == 1) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = gelu_erf(v[j]);
+  }
+  const uint64_t e0 = static_cast<uint64_t>(m) * static_cast<uint64_t>(PN) + n0;   // multiple of 8
+  if (X.dfw.p > 0.f) {
+    float mm[8];
+    dropout_mult8(X.dfw, X.key_fw, e0 >> 3, mm);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] *= mm[j];
+  }
+  if (E.gate_z) {
+    const float* z = E.gate_z + static_cast<size_t>(m) * E.gate_pitch + n0;
+    const float4 z0 = ldg_f4(z), z1 = ldg_f4(z + 4);
+    float mm[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f};
+    if (X.dbw.p > 0.f) dropout_mult8(X.dbw, X.key_bw, e0 >> 3, mm);
+    v[0] *= gelu_erf_grad(z0.x) * mm[0]; v[1] *= gelu_erf_grad(z0.y) * mm[1];
+    v[2] *= gelu_erf_grad(z0.z) * mm[2]; v[3] *= gelu_erf_grad(z0.w) * mm[3];
+    v[4] *= gelu_erf_grad(z1.x) * mm[4]; v[5] *= gelu_erf_grad(z1.y) * mm[5];
+    v[6] *= gelu_erf_grad(z1.z) * mm[6]; v[7] *= gelu_erf_grad(z1.w) * mm[7];
+  }
+  if (E.out_f32) {
+    float* dst = E.out_f32 + static_cast<size_t>(m) * E.f32_pitch + n0;
+    if ((E.f32_pitch & 3) == 0) {
+      *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+      *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    } else {                                   // even pitch (pre.0.weight: 514): 8-byte aligned rows
+#pragma unroll
+      for (int j = 0; j < 8; j += 2) *reinterpret_cast<float2*>(dst + j) = make_float2(v[j], v[j + 1]);
+    }
+  }
+  if (E.out_hi) {
+    const size_t o = static_cast<size_t>(m) * E.bf_pitch + n0;
+    uint32_t ph[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) ph[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+    *reinterpret_cast<uint4*>(E.out_hi + o) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+    if (E.out_lo) {
+      uint32_t pl[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&ph[j]);
+        pl[j] = pack_bf16x2(v[2 * j] - __low2float(h2), v[2 * j + 1] - __high2float(h2));
+      }
+      *reinterpret_cast<uint4*>(E.out_lo + o) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+    }
+  }
+  float ss = 0.f;
+  if (E.sumsq_slots) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) ss = fmaf(v[j], v[j], ss);
+  }
+  return ss;
+}
 
 __global__ void __launch_bounds__(kGemmThreads, 1)
 fnd_gemm_kernel(const __grid_constant__ GemmTableP tbl, RunCtx ctx) {
@@ -104,12 +202,11 @@ fnd_gemm_kernel(const __grid_constant__ GemmTableP tbl, RunCtx ctx) {
   const bool A_MN = tbl.a_mn != 0, B_MN = tbl.b_mn != 0;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kGemmStages * kGemmStageBytes);
-  uint64_t* empty_bar = full_bar + kGemmStages;
-  uint64_t* accum_bar = empty_bar + kGemmStages;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kGemmOperandBudget);
+  uint64_t* empty_bar = full_bar + kGemmMaxStages;
+  uint64_t* accum_bar = empty_bar + kGemmMaxStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
-  volatile int* last_flag = reinterpret_cast<volatile int*>(tmem_slot + 1);
-  float* red_smem = reinterpret_cast<float*>(tmem_slot + 2);   // 4 floats
+  float* red_smem = reinterpret_cast<float*>(tmem_slot + 2);   // 8 floats
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -127,6 +224,8 @@ fnd_gemm_kernel(const __grid_constant__ GemmTableP tbl, RunCtx ctx) {
   const int tn = tile / P.tiles_m;
   const int bn = P.bn;
   const int ncombo = P.ncombo;
+  const int nstages = P.nstages;
+  const int stage_bytes = P.stage_bytes;
   const int kb0 = split * P.kb_per_split;
   const int kb1 = min(kb0 + P.kb_per_split, P.kb_total);
   const int iters = (kb1 - kb0) * ncombo;
@@ -141,7 +240,7 @@ fnd_gemm_kernel(const __grid_constant__ GemmTableP tbl, RunCtx ctx) {
   }
   if (warp == 1) {
     if (lane == 0) {
-      for (int s = 0; s < kGemmStages; ++s) {
+      for (int s = 0; s < nstages; ++s) {
         mbar_init(&full_bar[s], 1);
         mbar_init(&empty_bar[s], 1);
       }
@@ -163,29 +262,48 @@ fnd_gemm_kernel(const __grid_constant__ GemmTableP tbl, RunCtx ctx) {
     if (lane == 0) {
       const uint32_t bytesB = static_cast<uint32_t>(bn) * kGemmBK * 2;
       const uint32_t tx = kGemmStageBytesA + bytesB;
-      for (int it = 0; it < iters; ++it) {
-        const int s = it % kGemmStages;
-        const uint32_t ph = static_cast<uint32_t>(it / kGemmStages) & 1u;
-        if (!mbar_wait(&empty_bar[s], ph ^ 1u, ctx.err, FND_DEV_TIMEOUT_PRODUCER)) break;
+      auto load_a = [&](int it) {
+        const int s = it % nstages;
         const int kb = kb0 + it / ncombo;
         const int c = it - (it / ncombo) * ncombo;
         const void* mapA = &P.tmA[c == 2 ? 1 : 0];
-        const void* mapB = &P.tmB[c == 1 ? 1 : 0];
-        uint8_t* sA = smem + s * kGemmStageBytes;
-        uint8_t* sB = sA + kGemmStageBytesA;
-        mbar_arrive_expect_tx(&full_bar[s], tx);
+        uint8_t* sA = smem + s * stage_bytes;
         if (!A_MN) {
           tma_load_2d(sA, mapA, &full_bar[s], kb * kGemmBK, tm * kGemmBM, P.hintA);
         } else {
           tma_load_2d(sA, mapA, &full_bar[s], tm * kGemmBM, kb * kGemmBK, P.hintA);
           tma_load_2d(sA + 8192, mapA, &full_bar[s], tm * kGemmBM + 64, kb * kGemmBK, P.hintA);
         }
+      };
+      auto load_b = [&](int it) {
+        const int s = it % nstages;
+        const int kb = kb0 + it / ncombo;
+        const int c = it - (it / ncombo) * ncombo;
+        const void* mapB = &P.tmB[c == 1 ? 1 : 0];
+        uint8_t* sB = smem + s * stage_bytes + kGemmStageBytesA;
         if (!B_MN) {
           tma_load_2d(sB, mapB, &full_bar[s], kb * kGemmBK, tn * bn, P.hintB);
         } else {
           for (int ch = 0; ch < bn / 64; ++ch)
             tma_load_2d(sB + ch * 8192, mapB, &full_bar[s], tn * bn + ch * 64, kb * kGemmBK, P.hintB);
         }
+      };
+      // Static operand (weights): fill the ring's first pass before waiting for the predecessor kernel.
+      const int npre = P.b_static ? min(iters, nstages) : 0;
+      for (int it = 0; it < npre; ++it) {
+        mbar_arrive_expect_tx(&full_bar[it], tx);
+        load_b(it);
+      }
+      griddep_wait();
+      griddep_launch();
+      for (int it = 0; it < npre; ++it) load_a(it);
+      for (int it = npre; it < iters; ++it) {
+        const int s = it % nstages;
+        const uint32_t ph = static_cast<uint32_t>(it / nstages) & 1u;
+        if (!mbar_wait(&empty_bar[s], ph ^ 1u, ctx.err, FND_DEV_TIMEOUT_PRODUCER)) break;
+        mbar_arrive_expect_tx(&full_bar[s], tx);
+        load_a(it);
+        load_b(it);
       }
     }
     __syncwarp();
@@ -197,13 +315,13 @@ fnd_gemm_kernel(const __grid_constant__ GemmTableP tbl, RunCtx ctx) {
       const uint32_t lboA = A_MN ? 8192u : 16u, lboB = B_MN ? 8192u : 16u;
       bool ok = true;
       for (int it = 0; it < iters && ok; ++it) {
-        const int s = it % kGemmStages;
-        const uint32_t ph = static_cast<uint32_t>(it / kGemmStages) & 1u;
+        const int s = it % nstages;
+        const uint32_t ph = static_cast<uint32_t>(it / nstages) & 1u;
         ok = mbar_wait(&full_bar[s], ph, ctx.err, FND_DEV_TIMEOUT_MMA);
         if (!ok) break;
         if (it == 0) FND_STAMP(2);
         tc_fence_after_sync();
-        const uint32_t aBase = smem_u32(smem + s * kGemmStageBytes);
+        const uint32_t aBase = smem_u32(smem + s * stage_bytes);
         const uint32_t bBase = aBase + kGemmStageBytesA;
 #pragma unroll
         for (int k = 0; k < kGemmBK / 16; ++k) {
@@ -220,45 +338,75 @@ fnd_gemm_kernel(const __grid_constant__ GemmTableP tbl, RunCtx ctx) {
     }
     __syncwarp();
   } else {
-    // ================= epilogue (warps 2..5) =================
+    // ================= epilogue (warps 2..9) =================
     // Deliberately ROLLED (8 columns per iteration, #pragma unroll 1): a fully unrolled epilogue was ~100 KB of
     // straight-line SASS and made every small launch instruction-fetch bound (~25 us fixed cost, measured).
     // By VALUE: the inline-asm tcgen05/mbarrier wrappers carry "memory" clobbers, so fields read through a pointer
-    // into the problem table were re-loaded from global memory after every one of them (measured: ~0.7 us per
-    // 8-column group). Registers are plentiful here (accumulators live in TMEM).
+    // into the problem table were re-loaded after every one of them. Registers are plentiful here.
     const EpiParams E = P.epi;
     const int PM = P.M, PN = P.N;
     float* const ws_base = P.splitk_ws;
     int* const ctr_base = P.splitk_ctr;
-    const int lane_grp = warp & 3;                 // TMEM lane quarter this warp may access
+    const int ew = warp - 2;                       // 0..7
+    const int lane_grp = warp & 3;                 // TMEM lane quarter this warp may access (hardware rule: warp % 4)
+    const int half = ew >> 2;                      // the two warps of a lane quarter alternate column groups
     const int row = lane_grp * 32 + lane;
     const int m = tm * kGemmBM + row;
     const bool row_ok = m < PM;
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16);
     const int ngroups = bn / 8;
     const int epi_tid = threadIdx.x - 64;
-    // While the main loop runs, pull the epilogue's global operands towards L2 (they are cold after the optimizer
-    // has streamed ~0.5 GB through the cache): this thread's row of add_in / gate_z, and the tile's bias slice.
-    if (row_ok) {
-      const int nb = tn * bn;
+    const int nb = tn * bn;
+    // static epilogue operand: pull the tile's bias slice towards L2 before the predecessor finishes
+    if (E.bias && epi_tid * 32 < bn) prefetch_l2(E.bias + nb + epi_tid * 32);
+    griddep_wait();
+    // While the main loop runs, pull this thread's row of the activation-side epilogue operands towards L2 (they are
+    // cold after the optimizer has streamed ~0.5 GB through the cache).
+    if (row_ok && half == 0) {
       if (E.gate_z)
         for (int c = 0; c < bn; c += 32) prefetch_l2(E.gate_z + static_cast<size_t>(m) * E.gate_pitch + nb + c);
       if (E.add_in)
         for (int c = 0; c < bn; c += 32) prefetch_l2(E.add_in + static_cast<size_t>(m) * E.add_pitch + nb + c);
-      if (E.bias && row * 32 < bn) prefetch_l2(E.bias + nb + row * 32);
     }
-    bool proceed = mbar_wait(accum_bar, 0u, ctx.err, FND_DEV_TIMEOUT_EPILOGUE);
+    const uint64_t seed = ctx.rng ? ((static_cast<uint64_t>(ctx.rng[1]) << 32) | ctx.rng[0]) : 0ull;
+    EpiCtx X;
+    X.dfw = make_dropcfg(ctx.training ? E.drop_p : 0.f, seed);
+    X.dbw = make_dropcfg(ctx.training ? E.gate_p : 0.f, seed);
+    X.key_fw = stream_key(ctx.rng, E.drop_stream);
+    X.key_bw = stream_key(ctx.rng, E.gate_stream);
+
+    const bool proceed = mbar_wait(accum_bar, 0u, ctx.err, FND_DEV_TIMEOUT_EPILOGUE);
     tc_fence_after_sync();
     if (epi_tid == 0) FND_STAMP(4);
+    float ss = 0.f;
 
-    float* ws_tile = nullptr;
-    if (splits > 1) {
-      ws_tile = ws_base + static_cast<size_t>(tile) * splits * (kGemmBM * bn);
-      // partial layout [split][group][row][8]: a warp's 32 rows of one group are 1 KB contiguous, so both this
-      // write and the fix-up read below are fully coalesced
+    if (splits == 1) {
+      float a0 = 0.f, a1 = 0.f;
+      if (E.aux && row_ok) {
+        a0 = E.aux[static_cast<size_t>(m) * 2];
+        a1 = E.aux[static_cast<size_t>(m) * 2 + 1];
+      }
+      if (epi_tid == 0) FND_STAMP(5);
+#pragma unroll 1
+      for (int g = half; g < ngroups; g += 2) {
+        uint32_t r[8];
+        tmem_ld_32x8(taddr + g * 8, r);
+        tmem_ld_wait();
+        const int n0 = nb + g * 8;
+        if (!proceed || !row_ok || n0 >= PN) continue;           // N is a multiple of 8 (checked on the host)
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[j]);
+        ss += epi_group(E, X, v, m, n0, PN, a0, a1);
+      }
+    } else {
+      // ---- split-K: publish this CTA's partial tile, wait for the other splits, finish a share of the tile ----
+      // partial layout [split][group][row][8]: a warp's 32 rows of one group are 1 KB contiguous, so both the write
+      // and the fix-up reads are fully coalesced
+      float* const ws_tile = ws_base + static_cast<size_t>(tile) * splits * (kGemmBM * bn);
       float* mine = ws_tile + static_cast<size_t>(split) * (kGemmBM * bn) + static_cast<size_t>(row) * 8;
 #pragma unroll 1
-      for (int g = 0; g < ngroups; ++g) {
+      for (int g = half; g < ngroups; g += 2) {
         uint32_t r[8];
         tmem_ld_32x8(taddr + g * 8, r);
         tmem_ld_wait();
@@ -269,149 +417,82 @@ fnd_gemm_kernel(const __grid_constant__ GemmTableP tbl, RunCtx ctx) {
       }
       __threadfence();
       epi_named_barrier();
+      int* const ctr = ctr_base + 2 * tile;
       if (epi_tid == 0) {
-        const int old = atomicAdd(&ctr_base[tile], 1);
-        const int last = (old == splits - 1) ? 1 : 0;
-        if (last) ctr_base[tile] = 0;         // re-arm for the next launch (graph replay safe)
-        *last_flag = last;
+        atomicAdd(&ctr[0], 1);
+        // all `splits` CTAs of this tile are resident (grid <= SM count, one CTA per SM): bounded spin
+        long long t0 = 0;
+        for (uint32_t spins = 1;; ++spins) {
+          if (*reinterpret_cast<volatile int*>(&ctr[0]) >= splits) break;
+          if ((spins & 255u) == 0u) {
+            const long long now = clock64();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 4000000000ll) {
+              if (ctx.err) atomicExch(ctx.err, FND_DEV_TIMEOUT_SPLITK);
+              break;
+            }
+          }
+        }
+        __threadfence();
       }
       epi_named_barrier();
-      proceed = proceed && (*last_flag != 0);
-      if (proceed) __threadfence();
-    }
-
-    if (epi_tid == 0) FND_STAMP(5);
-    float ss = 0.f;
-    if (proceed) {
-      const uint64_t seed = ctx.rng ? ((static_cast<uint64_t>(ctx.rng[1]) << 32) | ctx.rng[0]) : 0ull;
-      const DropCfg dfw = make_dropcfg(ctx.training ? E.drop_p : 0.f, seed);
-      const DropCfg dbw = make_dropcfg(ctx.training ? E.gate_p : 0.f, seed);
-      const uint32_t key_fw = stream_key(ctx.rng, E.drop_stream);
-      const uint32_t key_bw = stream_key(ctx.rng, E.gate_stream);
-      float a0 = 0.f, a1 = 0.f;
-      if (E.aux && row_ok) {
-        a0 = E.aux[static_cast<size_t>(m) * 2];
-        a1 = E.aux[static_cast<size_t>(m) * 2 + 1];
-      }
+      if (epi_tid == 0) FND_STAMP(5);
+      // units: u = g * 4 + q  (q = 32-row quarter); unit u belongs to split (u % splits); this CTA's units are dealt
+      // round-robin to its eight epilogue warps
+      const int nunits = ngroups * 4;
+      const size_t sstride = static_cast<size_t>(kGemmBM) * bn;
 #pragma unroll 1
-      for (int g = 0; g < ngroups; ++g) {
+      for (int u = split + ew * splits; u < nunits; u += kGemmEpiWarps * splits) {
+        const int g = u >> 2, q = u & 3;
+        const int urow = q * 32 + lane;
+        const int um = tm * kGemmBM + urow;
+        const int n0 = nb + g * 8;
         float v[8];
-        if (splits > 1) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = 0.f;
-          // fixed split order => deterministic sum; loads are issued eight splits at a time so the L2 round trips
-          // overlap instead of serialising (16 dependent trips per group made fuse_mlp.0 a 100 us kernel)
-          const float* src0 = ws_tile + static_cast<size_t>(g) * (kGemmBM * 8) + static_cast<size_t>(row) * 8;
-          const size_t sstride = static_cast<size_t>(kGemmBM) * bn;
+        for (int jj = 0; jj < 8; ++jj) v[jj] = 0.f;
+        // fixed split order => deterministic sum; loads are issued eight splits at a time so the L2 round trips
+        // overlap instead of serialising
+        const float* src0 = ws_tile + static_cast<size_t>(g) * (kGemmBM * 8) + static_cast<size_t>(urow) * 8;
 #pragma unroll 1
-          for (int s2 = 0; s2 < splits; s2 += 8) {
-            float4 t[16];
+        for (int s2 = 0; s2 < splits; s2 += 8) {
+          float4 t[16];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              const bool okq = s2 + q < splits;
-              const float* src = src0 + static_cast<size_t>(okq ? s2 + q : s2) * sstride;
-              t[2 * q] = ldcg_f4(src);
-              t[2 * q + 1] = ldcg_f4(src + 4);
-              if (!okq) { t[2 * q] = make_float4(0.f, 0.f, 0.f, 0.f); t[2 * q + 1] = t[2 * q]; }
-            }
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              v[0] += t[2 * q].x; v[1] += t[2 * q].y; v[2] += t[2 * q].z; v[3] += t[2 * q].w;
-              v[4] += t[2 * q + 1].x; v[5] += t[2 * q + 1].y; v[6] += t[2 * q + 1].z; v[7] += t[2 * q + 1].w;
-            }
+          for (int qq = 0; qq < 8; ++qq) {
+            const bool okq = s2 + qq < splits;
+            const float* src = src0 + static_cast<size_t>(okq ? s2 + qq : s2) * sstride;
+            t[2 * qq] = ldcg_f4(src);
+            t[2 * qq + 1] = ldcg_f4(src + 4);
+            if (!okq) { t[2 * qq] = make_float4(0.f, 0.f, 0.f, 0.f); t[2 * qq + 1] = t[2 * qq]; }
           }
-        } else {
-          uint32_t r[8];
-          tmem_ld_32x8(taddr + g * 8, r);
-          tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[j]);
+          for (int qq = 0; qq < 8; ++qq) {
+            v[0] += t[2 * qq].x; v[1] += t[2 * qq].y; v[2] += t[2 * qq].z; v[3] += t[2 * qq].w;
+            v[4] += t[2 * qq + 1].x; v[5] += t[2 * qq + 1].y; v[6] += t[2 * qq + 1].z; v[7] += t[2 * qq + 1].w;
+          }
         }
-        const int n0 = tn * bn + g * 8;
-        if (!row_ok || n0 >= PN) continue;           // N is a multiple of 8 (checked on the host)
-
-        if (E.bias) {
-          const float4 b0 = ldg_f4(E.bias + n0), b1 = ldg_f4(E.bias + n0 + 4);
-          v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-          v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-        }
+        if (!proceed || um >= PM || n0 >= PN) continue;
+        float a0 = 0.f, a1 = 0.f;
         if (E.aux) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float* w = E.aux_w + static_cast<size_t>(n0 + j) * E.aux_w_pitch;
-            v[j] += a0 * __ldg(w) + a1 * __ldg(w + 1);
-          }
+          a0 = E.aux[static_cast<size_t>(um) * 2];
+          a1 = E.aux[static_cast<size_t>(um) * 2 + 1];
         }
-        if (E.add_in) {
-          const float* src = E.add_in + static_cast<size_t>(m) * E.add_pitch + n0;
-          const float4 t0 = ldg_f4(src), t1 = ldg_f4(src + 4);
-          v[0] += t0.x; v[1] += t0.y; v[2] += t0.z; v[3] += t0.w;
-          v[4] += t1.x; v[5] += t1.y; v[6] += t1.z; v[7] += t1.w;
-        }
-        if (E.out_pre) {
-          float* dst = E.out_pre + static_cast<size_t>(m) * E.pre_pitch + n0;
-          *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
-          *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
-        }
-        if (E.act == 1) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = gelu_erf(v[j]);
-        }
-        const uint64_t e0 = static_cast<uint64_t>(m) * static_cast<uint64_t>(PN) + n0;   // multiple of 8
-        if (dfw.p > 0.f) {
-          float mm[8];
-          dropout_mult8(dfw, key_fw, e0 >> 3, mm);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] *= mm[j];
-        }
-        if (E.gate_z) {
-          const float* z = E.gate_z + static_cast<size_t>(m) * E.gate_pitch + n0;
-          const float4 z0 = ldg_f4(z), z1 = ldg_f4(z + 4);
-          float mm[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f};
-          if (dbw.p > 0.f) dropout_mult8(dbw, key_bw, e0 >> 3, mm);
-          v[0] *= gelu_erf_grad(z0.x) * mm[0]; v[1] *= gelu_erf_grad(z0.y) * mm[1];
-          v[2] *= gelu_erf_grad(z0.z) * mm[2]; v[3] *= gelu_erf_grad(z0.w) * mm[3];
-          v[4] *= gelu_erf_grad(z1.x) * mm[4]; v[5] *= gelu_erf_grad(z1.y) * mm[5];
-          v[6] *= gelu_erf_grad(z1.z) * mm[6]; v[7] *= gelu_erf_grad(z1.w) * mm[7];
-        }
-        if (E.out_f32) {
-          float* dst = E.out_f32 + static_cast<size_t>(m) * E.f32_pitch + n0;
-          if ((E.f32_pitch & 3) == 0) {
-            *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
-            *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
-          } else {                                   // even pitch (pre.0.weight: 514): 8-byte aligned rows
-#pragma unroll
-            for (int j = 0; j < 8; j += 2) *reinterpret_cast<float2*>(dst + j) = make_float2(v[j], v[j + 1]);
-          }
-        }
-        if (E.out_hi) {
-          const size_t o = static_cast<size_t>(m) * E.bf_pitch + n0;
-          uint32_t ph[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) ph[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
-          *reinterpret_cast<uint4*>(E.out_hi + o) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
-          if (E.out_lo) {
-            uint32_t pl[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&ph[j]);
-              pl[j] = pack_bf16x2(v[2 * j] - __low2float(h2), v[2 * j + 1] - __high2float(h2));
-            }
-            *reinterpret_cast<uint4*>(E.out_lo + o) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
-          }
-        }
-        if (E.sumsq_slots) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) ss += v[j] * v[j];
-        }
+        ss += epi_group(E, X, v, um, n0, PN, a0, a1);
+      }
+      // depart: the last CTA to finish reading re-arms both counters for the next launch (graph-replay safe)
+      epi_named_barrier();
+      if (epi_tid == 0) {
+        const int old = atomicAdd(&ctr[1], 1);
+        if (old == splits - 1) { ctr[0] = 0; ctr[1] = 0; }
       }
     }
     if (E.sumsq_slots) {
-      // every epilogue thread takes part (non-last split CTAs contribute 0) => fixed order, deterministic
+      // every epilogue thread takes part => fixed order, deterministic
       ss = warp_sum(ss);
-      if (lane == 0) red_smem[lane_grp] = ss;
+      if (lane == 0) red_smem[ew] = ss;
       epi_named_barrier();
-      if (epi_tid == 0) E.sumsq_slots[local] = (red_smem[2] + red_smem[3]) + (red_smem[0] + red_smem[1]);
+      if (epi_tid == 0)
+        E.sumsq_slots[local] = ((red_smem[0] + red_smem[1]) + (red_smem[2] + red_smem[3])) +
+                               ((red_smem[4] + red_smem[5]) + (red_smem[6] + red_smem[7]));
     }
   }
 

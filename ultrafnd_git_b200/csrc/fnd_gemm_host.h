@@ -2,6 +2,8 @@
 #pragma once
 #include "fnd_gemm.cuh"
 #include "fnd_tmap.h"
+#include <cstdlib>
+#include <utility>
 #include <vector>
 
 namespace fnd {
@@ -18,12 +20,37 @@ struct Operand {
 
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// Launch with (pdl = true) or without the programmatic-stream-serialization attribute (see fnd_common.cuh: every
+// kernel of this library calls griddepcontrol.wait before touching data its predecessor may have produced).
+// FND_NO_PDL=1 in the environment disables the attribute globally (debugging aid).
+inline bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) v = getenv("FND_NO_PDL") ? 0 : 1;
+  return v != 0;
+}
+template <class... KArgs, class... Args>
+inline cudaError_t launch_k(void (*kern)(KArgs...), int grid, int block, size_t smem, cudaStream_t st, bool pdl,
+                            Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(static_cast<unsigned>(grid), 1, 1);
+  cfg.blockDim = dim3(static_cast<unsigned>(block), 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = (pdl && pdl_enabled()) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(std::forward<Args>(args))...);
+}
+
 // Fills one problem; returns 0 or a negative error. `cta_begin` is assigned by the caller (finish_table).
 inline int fill_problem(GemmProblem& p, const Operand& A, const Operand& B, int M, int N, int K, int bn, int splits,
                         int ncombo, unsigned long long hintA, unsigned long long hintB, float* ws, int* ctr,
-                        const EpiParams& epi) {
+                        const EpiParams& epi, int b_static = 0) {
   memset(&p, 0, sizeof(p));
-  if (bn != 32 && bn != 64 && bn != 128) return -10;
+  if (bn != 16 && bn != 32 && bn != 64 && bn != 128) return -10;
   if (B.mn_major && bn < 64) return -11;
   if (ncombo != 1 && ncombo != 3) return -12;
   if (ncombo == 3 && (!A.lo || !B.lo)) return -13;
@@ -31,6 +58,10 @@ inline int fill_problem(GemmProblem& p, const Operand& A, const Operand& B, int 
   p.M = M; p.N = N; p.K = K;
   p.bn = bn;
   p.ncombo = ncombo;
+  p.b_static = b_static;
+  p.stage_bytes = kGemmStageBytesA + bn * kGemmBK * 2;
+  p.nstages = kGemmOperandBudget / p.stage_bytes;
+  if (p.nstages > kGemmMaxStages) p.nstages = kGemmMaxStages;
   p.tiles_m = ceil_div(M, kGemmBM);
   p.tiles_n = ceil_div(N, bn);
   p.kb_total = ceil_div(K, kGemmBK);
@@ -78,7 +109,7 @@ inline cudaError_t init_gemm_attrs() {
 // kind: 0 = forward (A K-major, B K-major); 1 = dgrad (A K-major, B MN-major); 2 = wgrad (both MN-major);
 // 3 = (A MN-major, B K-major). `host_table` is copied into the kernel's parameter space at launch.
 inline cudaError_t launch_gemm(int kind, const GemmProblem* host_table, int nprob, int grid, RunCtx ctx,
-                               cudaStream_t st) {
+                               cudaStream_t st, bool pdl = false) {
   if (grid <= 0) return cudaSuccess;
   if (nprob < 1 || nprob > kGemmTableCap || kind < 0 || kind > 3) return cudaErrorInvalidValue;
   GemmTableP t;
@@ -86,8 +117,7 @@ inline cudaError_t launch_gemm(int kind, const GemmProblem* host_table, int npro
   t.nprob = nprob;
   t.a_mn = (kind == 2 || kind == 3) ? 1 : 0;
   t.b_mn = (kind == 1 || kind == 2) ? 1 : 0;
-  fnd_gemm_kernel<<<grid, kGemmThreads, kGemmSmemBytes, st>>>(t, ctx);
-  return cudaGetLastError();
+  return launch_k(fnd_gemm_kernel, grid, kGemmThreads, kGemmSmemBytes, st, pdl, t, ctx);
 }
 
 }  // namespace fnd

@@ -48,6 +48,8 @@ __device__ __forceinline__ void shadow_store4(const AdamWParams& a, size_t i, co
 }
 
 __global__ void __launch_bounds__(256) adamw_kernel(AdamWParams a) {
+  griddep_wait();
+  griddep_launch();
   const DevState* S = a.state;
   const float coef = S->clip_coef, lr = S->lr, b1 = S->beta1, b2 = S->beta2, eps = S->eps;
   const float decay = 1.0f - lr * S->weight_decay;
@@ -89,6 +91,8 @@ __global__ void __launch_bounds__(256) shadow_refresh_kernel(AdamWParams a) {
 // Sum of squares of a flat fp32 buffer into per-CTA slots (used after a gradient all-reduce, where the norm
 // must be taken over the REDUCED gradients rather than folded into the wgrad epilogues).
 __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, size_t n, float* __restrict__ slots) {
+  griddep_wait();
+  griddep_launch();
   __shared__ float red[8];
   float s = 0.f;
   for (size_t i = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 4; i < n;
@@ -112,10 +116,14 @@ __device__ __forceinline__ void advance_step(DevState* S) {
 }
 // Optimizer-step bookkeeping alone (when the norm was already produced by the fused step's finalize kernel).
 __global__ void step_kernel(DevState* S) {
+  griddep_wait();
+  griddep_launch();
   if (threadIdx.x == 0 && blockIdx.x == 0) advance_step(S);
 }
 __global__ void __launch_bounds__(256) norm_finish_kernel(const float* __restrict__ slots, int nslots, DevState* S,
                                                           int update_step) {
+  griddep_wait();
+  griddep_launch();
   __shared__ double dred[256];
   double part = 0.0;
   for (int i = threadIdx.x; i < nslots; i += 256) part += static_cast<double>(slots[i]);

@@ -102,6 +102,8 @@ struct PrepParams {
 };
 
 __global__ void __launch_bounds__(kRowThreads) prep_kernel(PrepParams p) {
+  griddep_wait();
+  griddep_launch();
   __shared__ float red[8 * 1];
   const int b = blockIdx.x;
   if (b == 0 && threadIdx.x == 0 && p.rng) {
@@ -176,6 +178,8 @@ __device__ __forceinline__ float2 ld2(const float* p) { return __ldg(reinterpret
 
 template <int CH>   // CH = H / 512 chunks of 2 consecutive elements per thread
 __global__ void __launch_bounds__(kRowThreads) assemble_fwd_kernel(AssembleParams p) {
+  griddep_wait();
+  griddep_launch();
   __shared__ float red[8 * 9];
   const int H = p.H;
   const int nslots = p.use_gnn ? 16 : 15;
@@ -281,6 +285,8 @@ struct AssembleBwdParams {
 
 template <int CH>
 __global__ void __launch_bounds__(kRowThreads) assemble_bwd_kernel(AssembleBwdParams p) {
+  griddep_wait();
+  griddep_launch();
   __shared__ float red[8 * 6];
   const int H = p.H;
   const int nslots = p.use_gnn ? 16 : 15;
@@ -474,6 +480,10 @@ __global__ void __launch_bounds__(256) head_kernel(HeadParams p) {
   }
   for (int i = threadIdx.x; i < T * L * 2; i += 256) leaf[i] = __ldg(p.leaf + i);
   if (threadIdx.x < TD) thr[threadIdx.x] = __ldg(p.thresh + threadIdx.x);
+  // everything staged so far is static for the immediate predecessor (parameters; alpha is written by prep, which is
+  // never the kernel directly before a head launch): only now wait for the producer of h / z_pre1 / logits
+  griddep_wait();
+  griddep_launch();
   const uint64_t seed = (static_cast<uint64_t>(p.state->rng[1]) << 32) | p.state->rng[0];
   const DropCfg dtree = make_dropcfg(p.training ? p.tree_drop_p : 0.f, seed);
   const DropCfg dpre = make_dropcfg(p.training ? p.pre_drop_p : 0.f, seed);
@@ -682,6 +692,8 @@ __global__ void __launch_bounds__(256) head_kernel(HeadParams p) {
 __global__ void __launch_bounds__(256) rowlinear2_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                              const float* __restrict__ bias, float* __restrict__ y,
                                                              int B, int H) {
+  griddep_wait();
+  griddep_launch();
   const int lane = threadIdx.x & 31;
   const int b = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (b >= B) return;
@@ -699,6 +711,8 @@ __global__ void __launch_bounds__(256) rowlinear2_fwd_kernel(const float* __rest
 // dx[b,:] (+)= dy[b,0]*w[0,:] + dy[b,1]*w[1,:]
 __global__ void __launch_bounds__(256) rowlinear2_dgrad_kernel(const float* __restrict__ dy, const float* __restrict__ w,
                                                                float* __restrict__ dx, int B, int H, int accumulate) {
+  griddep_wait();
+  griddep_launch();
   const int b = blockIdx.x;
   if (b >= B) return;
   const float d0 = dy[b * 2], d1 = dy[b * 2 + 1];
@@ -718,6 +732,8 @@ struct GateParams {
   size_t n;       // elements, multiple of 8
 };
 __global__ void __launch_bounds__(256) gate_kernel(GateParams p) {
+  griddep_wait();
+  griddep_launch();
   const DropCfg dc = make_dropcfg(p.training ? p.drop_p : 0.f,
                                   (static_cast<uint64_t>(p.state->rng[1]) << 32) | p.state->rng[0]);
   for (size_t i = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 8; i < p.n;
@@ -778,6 +794,8 @@ struct FinParams {
 };
 
 __global__ void __launch_bounds__(256) finalize_kernel(FinParams p) {
+  griddep_wait();
+  griddep_launch();
   __shared__ float sm[4][64];
   __shared__ float red[8];
   __shared__ int is_last;
