@@ -134,6 +134,9 @@ int fnd_eval_step(void* plan, const fnd_inputs* in, void* stream);
  * milliseconds between consecutive events. Not capturable; do not use around graph replays. */
 int fnd_profile_begin(void* plan, void* stream);
 int fnd_profile_end(void* plan, void* stream, char* names, float* ms, int cap, int* count);
+/* Debug aid: limit >= 0 makes every entry point issue only its first `limit` kernel launches (prefix timing of the
+ * step, tools/prefix_probe.py); -1 restores normal operation. Results are incomplete while a limit is set. */
+int fnd_debug_set_launch_limit(void* plan, int limit);
 /* Number of kernel launches one call of the named entry point issues ("train_step", "eval_step", ...). */
 int fnd_launch_count(const void* plan, const char* entry);
 /* Dropout keep-multipliers (0 or 1/(1-p)) that the NEXT training forward will use for a layer

@@ -16,8 +16,7 @@ import subprocess
 import sys
 
 STEP_ORDER = ["prep", "gemm_proj", "gemm_qkv", "assemble_fwd", "gemm_fuse0", "gemm_fuse1", "gemm_pre0", "gemm_pre1", "head",
-              "dgrad_pre1", "dgrad_pre0", "dgrad_fuse1", "dgrad_fuse0", "assemble_bwd", "dgrad_qkv", "wgrad_all", "finalize",
-              "adamw"]
+              "dgrad_pre1", "dgrad_pre0", "dgrad_fuse1", "dgrad_fuse0", "assemble_bwd", "dgrad_qkv", "wgrad_all", "adamw"]
 METRICS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
            "dram__throughput.avg.pct_of_peak_sustained_elapsed",
            "sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed",

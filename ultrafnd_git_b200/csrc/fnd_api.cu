@@ -223,6 +223,11 @@ static int build_tables(Plan& P) {
       job(T, kJobColsumF32, P.n_asm_ctas, 3 * P.L.evstride, 3 * P.L.evstride, P.buf<float>("ev_partial"), nullptr, nullptr,
           nullptr, P.G("fusion.attn_tv.evidence_proj.0.weight"), 0, 1.0f);
     }
+    if (clf && fus) {   // fused step only: mean loss (the stand-alone finalize launches compute it in their last CTA)
+      job(T, kJobLossMean, B, 1, 1, P.buf<float>("loss_row"), nullptr, nullptr, nullptr, nullptr, 0, 1.0f);
+      T.host.back().cta_count = 1;
+      T.host.back().want_norm = 0;
+    }
     int c = 0;
     for (auto& j : T.host) { j.cta_begin = c; c += j.cta_count; }
     T.grid = c;
@@ -281,6 +286,14 @@ static bool take_pdl(const Plan& Pc) {
   P.pdl_next = true;
   return v;
 }
+// Debug aid (tools/prefix_probe.py): when a launch limit is set, only the first `limit` launches of an entry point are
+// issued, so the marginal in-graph cost of every kernel can be measured by timing prefixes of the step.
+static bool launch_skipped(const Plan& Pc) {
+  Plan& P = const_cast<Plan&>(Pc);
+  if (P.launch_limit < 0) return false;
+  return P.launch_seq++ >= P.launch_limit;
+}
+#define FND_SKIP(P) do { if (launch_skipped(P)) return 0; } while (0)
 static void mark(const Plan& Pc, const char* name, cudaStream_t st) {
   Plan& P = const_cast<Plan&>(Pc);
   if (!P.profiling) return;
@@ -290,14 +303,17 @@ static void mark(const Plan& Pc, const char* name, cudaStream_t st) {
   cudaEventRecord(ev, st);
   P.marks.emplace_back(name, ev);
 }
-static int run_gemm(const Plan& P, const GemmTable& T, int training, cudaStream_t st, const char* name) {
+static int run_gemm(const Plan& P, const GemmTable& T, int training, cudaStream_t st, const char* name,
+                    const FinParams* fin = nullptr, int fin_ctas = 0) {
+  FND_SKIP(P);
   FND_CUDA_OK(launch_gemm(T.kind, T.host.data(), static_cast<int>(T.host.size()), T.grid, make_ctx(P, training), st,
-                          take_pdl(P)));
+                          take_pdl(P), fin, fin_ctas));
   mark(P, name, st);
   return 0;
 }
 
 static int run_prep(Plan& P, const fnd_inputs* in, int training, bool bump_clf, cudaStream_t st) {
+  FND_SKIP(P);
   PrepParams pp;
   memset(&pp, 0, sizeof(pp));
   for (int i = 0; i < P.nmod; ++i) {
@@ -329,6 +345,7 @@ static void fill_ev(const Plan& P, EvidenceParams (&ev)[3]) {
 }
 
 static int run_assemble_fwd(Plan& P, cudaStream_t st) {
+  FND_SKIP(P);
   AssembleParams a;
   memset(&a, 0, sizeof(a));
   a.P = P.buf<float>("P"); a.Q = P.buf<float>("Q");
@@ -344,6 +361,7 @@ static int run_assemble_fwd(Plan& P, cudaStream_t st) {
 }
 
 static int run_assemble_bwd(Plan& P, cudaStream_t st) {
+  FND_SKIP(P);
   AssembleBwdParams a;
   memset(&a, 0, sizeof(a));
   a.P = P.buf<float>("P"); a.Q = P.buf<float>("Q"); a.dcat = P.buf<float>("dcat"); a.rowstat = P.buf<float>("rowstat");
@@ -382,6 +400,7 @@ static HeadParams head_params(const Plan& P, int training) {
 }
 template <bool FWD, bool CE, bool BWD>
 static int run_head(const Plan& P, const HeadParams& h, cudaStream_t st) {
+  FND_SKIP(P);
   if (P.d.trees != 6 || P.d.depth != 4) return -50;     // only the reference's NODE shape is instantiated
   const int grid = ceil_div(P.B, 8) < 296 ? ceil_div(P.B, 8) : 296;
   const size_t smem = static_cast<size_t>(P.TD + 2) * P.H * sizeof(float) + 8 * (P.TD + 2) * 33 * sizeof(float);
@@ -397,14 +416,20 @@ static int run_head(const Plan& P, const HeadParams& h, cudaStream_t st) {
   return 0;
 }
 
-static int run_finalize(Plan& P, const FinTable& T, int slot_base, int total_slots, bool with_loss, int update_step,
-                        cudaStream_t st) {
+static FinParams fin_params(const Plan& P, const FinTable& T, int slot_base, int total_slots, bool with_loss, int update_step,
+                            int elect_last) {
   FinParams f;
   memset(&f, 0, sizeof(f));
   f.jobs = T.dev; f.njobs = static_cast<int>(T.host.size());
   f.slots = P.buf<float>("slots"); f.slot_base = slot_base; f.total_slots = total_slots;
   f.loss_row = with_loss ? P.buf<float>("loss_row") : nullptr; f.B = P.B;
-  f.state = P.state(); f.update_step = update_step;
+  f.state = P.state(); f.update_step = update_step; f.elect_last = elect_last;
+  return f;
+}
+static int run_finalize(Plan& P, const FinTable& T, int slot_base, int total_slots, bool with_loss, int update_step,
+                        cudaStream_t st) {
+  FND_SKIP(P);
+  FinParams f = fin_params(P, T, slot_base, total_slots, with_loss, update_step, 1);
   FND_CUDA_OK(launch_k(finalize_kernel, T.grid, 256, 0, st, take_pdl(P), f));
   mark(P, "finalize", st);
   return 0;
@@ -423,6 +448,7 @@ static AdamWParams adamw_params(const Plan& P) {
     a.rp_hi = P.sh_hi + P.L.n_shadow; a.rp_lo = P.sh_lo ? P.sh_lo + P.L.n_shadow : nullptr;
   }
   a.state = P.state();
+  a.slots = nullptr; a.nslots = 0;
   return a;
 }
 
@@ -456,6 +482,7 @@ static Plan* as_plan(void* p) { return static_cast<Plan*>(p); }
   if (!PP->bound) return -5;             \
   Plan& P = *PP;                         \
   P.pdl_next = false;                    \
+  P.launch_seq = 0;                      \
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream)
 
 extern "C" {
@@ -715,7 +742,7 @@ int fnd_clip_adamw_step(void* plan, int norm_from_slots, void* stream) {
 }
 
 // ------------------------------- fused trainer step -------------------------------
-static int train_fwd_bwd_impl(void* plan, const fnd_inputs* in, int update_step, void* stream) {
+static int train_fwd_bwd_impl(void* plan, const fnd_inputs* in, int fused_optimizer, void* stream) {
   FND_PLAN(plan);
   if (!in || !in->labels) return -1;
   FND_OK(fusion_forward_impl(P, in, 1, true, st));
@@ -728,19 +755,34 @@ static int train_fwd_bwd_impl(void* plan, const fnd_inputs* in, int update_step,
   FND_OK(run_gemm(P, P.dg_f0, 1, st, "dgrad_fuse0"));
   FND_OK(run_assemble_bwd(P, st));
   FND_OK(run_gemm(P, P.dg_qkv, 1, st, "dgrad_qkv"));
-  FND_OK(run_gemm(P, P.wg_all, 1, st, "wgrad_all"));
-  return run_finalize(P, P.fin_all, P.wg_all.grid, P.total_slots, true, update_step, st);
+  // Weight gradients of every GEMM; the trailing CTAs of the same launch run the finalize jobs (bias / threshold /
+  // leaf / evidence reductions, mean loss). Every CTA leaves its sum of squares in "slots"; whoever consumes the
+  // gradients next reduces the slots to the global norm (adamw_kernel in the fused step, norm_finish_kernel otherwise).
+  const FinParams f = fin_params(P, P.fin_all, P.wg_all.grid, P.total_slots, true, 0, 0);
+  FND_OK(run_gemm(P, P.wg_all, 1, st, "wgrad_all", &f, P.fin_all.grid));
+  if (!fused_optimizer) {
+    FND_SKIP(P);
+    FND_CUDA_OK(launch_k(norm_finish_kernel, 1, 256, 0, st, take_pdl(P), P.buf<float>("slots"), P.total_slots, P.state(), 0));
+    mark(P, "grad_norm", st);
+  }
+  return 0;
 }
 
 int fnd_train_fwd_bwd(void* plan, const fnd_inputs* in, void* stream) { return train_fwd_bwd_impl(plan, in, 0, stream); }
 
 int fnd_train_step(void* plan, const fnd_inputs* in, void* stream) {
-  // finalize (last kernel of fwd_bwd) publishes norm, clip coefficient AND the step bookkeeping; AdamW follows.
+  {
+    Plan* PP = as_plan(plan);
+    if (PP && PP->bound && (!PP->m || !PP->v)) return -6;
+  }
   FND_OK(train_fwd_bwd_impl(plan, in, 1, stream));
   FND_PLAN(plan);
   P.pdl_next = true;        // continues the chain started by train_fwd_bwd_impl
-  if (!P.m || !P.v) return -6;
+  P.launch_seq = 16;
+  FND_SKIP(P);
+  // AdamW reduces the norm slots itself (identical in every CTA), clips, steps and publishes the bookkeeping.
   AdamWParams a = adamw_params(P);
+  a.slots = P.buf<float>("slots"); a.nslots = P.total_slots;
   FND_CUDA_OK(launch_k(adamw_kernel, 148 * 8, 256, 0, st, take_pdl(P), a));
   mark(P, "adamw", st);
   return 0;
@@ -755,6 +797,13 @@ int fnd_eval_step(void* plan, const fnd_inputs* in, void* stream) {
   HeadParams h = head_params(P, 0);
   if (in->labels) return run_head<true, true, false>(P, h, st);
   return run_head<true, false, false>(P, h, st);
+}
+
+int fnd_debug_set_launch_limit(void* plan, int limit) {
+  Plan* PP = as_plan(plan);
+  if (!PP) return -1;
+  PP->launch_limit = limit;
+  return 0;
 }
 
 int fnd_profile_begin(void* plan, void* stream) {
@@ -801,9 +850,9 @@ int fnd_launch_count(const void* plan, const char* entry) {
   if (e == "fusion_forward") return fusion_fwd + 1;
   if (e == "classifier_forward") return 3;
   if (e == "eval_step") return fusion_fwd + 1 + 2 + 1;
-  if (e == "train_fwd_bwd") return fusion_fwd + 2 + 1 + 4 + 1 + 1 + 1 + 1;
+  if (e == "train_fwd_bwd") return fusion_fwd + 2 + 1 + 4 + 1 + 1 + 1 + 1;   // ... wgrad(+finalize CTAs), grad_norm
   if (e == "clip_adamw_step") return 3;
-  if (e == "train_step") return fusion_fwd + 2 + 1 + 4 + 1 + 1 + 1 + 1 + 1;
+  if (e == "train_step") return fusion_fwd + 2 + 1 + 4 + 1 + 1 + 1 + 1;       // ... wgrad(+finalize CTAs), adamw
   return -2;
 }
 

@@ -203,6 +203,7 @@ struct Plan {
   // optional per-kernel timing (bench/profiling only): an event is recorded after every launch
   int dbg_launch = 0;            // probe builds: index of the next launch's stamp region
   bool pdl_next = false;         // the next launch may carry the programmatic-serialization attribute
+  int launch_limit = -1, launch_seq = 0;   // debug: issue only the first `launch_limit` launches of an entry point
   bool profiling = false;
   std::vector<std::pair<const char*, cudaEvent_t>> marks;
 

@@ -33,6 +33,7 @@
 //   src/models/fusion/deep_truth_classifier.py:121-128,162.
 #pragma once
 #include "fnd_common.cuh"
+#include "fnd_rows.cuh"
 
 namespace fnd {
 
@@ -40,8 +41,9 @@ constexpr int kGemmBM = 128;          // UMMA M (rows of A per tile)
 constexpr int kGemmBK = 64;           // contraction elements per stage (128 B of bf16)
 constexpr int kGemmMaxStages = 12;
 constexpr int kGemmStageBytesA = kGemmBM * kGemmBK * 2;   // 16 KB
-constexpr int kGemmOperandBudget = 208 * 1024;            // operand ring
-constexpr int kGemmSmemBytes = kGemmOperandBudget + 1024 /*align slack*/ + 512 /*barriers*/;
+constexpr int kGemmOperandBudget = 208 * 1024;            // operand ring (upper bound; a launch asks for what it uses)
+constexpr int kGemmSmemHeader = 1024;                     // barriers, TMEM slot, reduction scratch (in front of the ring)
+constexpr int kGemmSmemBytes = kGemmOperandBudget + 1024 /*align slack*/ + kGemmSmemHeader;
 constexpr int kGemmEpiWarps = 8;
 constexpr int kGemmEpiThreads = kGemmEpiWarps * 32;
 constexpr int kGemmThreads = 64 + kGemmEpiThreads;        // warp0 TMA, warp1 MMA+TMEM, warps2-9 epilogue
@@ -107,6 +109,7 @@ struct GemmTableP {
   GemmProblem p[kGemmTableCap];
   int nprob;
   int a_mn, b_mn;     // 0: K-major, 1: MN-major
+  int gemm_ctas;      // CTAs [gemm_ctas, gridDim.x) of a kVariant == 1 launch run finalize jobs instead of a tile
 };
 
 struct EpiCtx {
@@ -129,17 +132,14 @@ __device__ __forceinline__ float epi_group(const EpiParams& E, const EpiCtx& X, 
       v[j] = fmaf(a0, w.x, fmaf(a1, w.y, v[j]));
     }
   }
+  // pitches of add_in / out_pre / gate_z are multiples of 8 floats (workspace buffers): 256-bit accesses
   if (E.add_in) {
-    const float* src = E.add_in + static_cast<size_t>(m) * E.add_pitch + n0;
-    const float4 t0 = ldg_f4(src), t1 = ldg_f4(src + 4);
-    v[0] += t0.x; v[1] += t0.y; v[2] += t0.z; v[3] += t0.w;
-    v[4] += t1.x; v[5] += t1.y; v[6] += t1.z; v[7] += t1.w;
+    float t[8];
+    ldg_f8(E.add_in + static_cast<size_t>(m) * E.add_pitch + n0, t);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] += t[j];
   }
-  if (E.out_pre) {
-    float* dst = E.out_pre + static_cast<size_t>(m) * E.pre_pitch + n0;
-    *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
-    *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
-  }
+  if (E.out_pre) st_f8(E.out_pre + static_cast<size_t>(m) * E.pre_pitch + n0, v);
   if (E.act == 1) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] = gelu_erf(v[j]);
@@ -152,18 +152,18 @@ __device__ __forceinline__ float epi_group(const EpiParams& E, const EpiCtx& X, 
     for (int j = 0; j < 8; ++j) v[j] *= mm[j];
   }
   if (E.gate_z) {
-    const float* z = E.gate_z + static_cast<size_t>(m) * E.gate_pitch + n0;
-    const float4 z0 = ldg_f4(z), z1 = ldg_f4(z + 4);
+    float z[8];
+    ldg_f8(E.gate_z + static_cast<size_t>(m) * E.gate_pitch + n0, z);
     float mm[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f};
     if (X.dbw.p > 0.f) dropout_mult8(X.dbw, X.key_bw, e0 >> 3, mm);
-    v[0] *= gelu_erf_grad(z0.x) * mm[0]; v[1] *= gelu_erf_grad(z0.y) * mm[1];
-    v[2] *= gelu_erf_grad(z0.z) * mm[2]; v[3] *= gelu_erf_grad(z0.w) * mm[3];
-    v[4] *= gelu_erf_grad(z1.x) * mm[4]; v[5] *= gelu_erf_grad(z1.y) * mm[5];
-    v[6] *= gelu_erf_grad(z1.z) * mm[6]; v[7] *= gelu_erf_grad(z1.w) * mm[7];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] *= gelu_erf_grad(z[j]) * mm[j];
   }
   if (E.out_f32) {
     float* dst = E.out_f32 + static_cast<size_t>(m) * E.f32_pitch + n0;
-    if ((E.f32_pitch & 3) == 0) {
+    if ((E.f32_pitch & 7) == 0) {
+      st_f8(dst, v);
+    } else if ((E.f32_pitch & 3) == 0) {
       *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
       *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
     } else {                                   // even pitch (pre.0.weight: 514): 8-byte aligned rows
@@ -195,18 +195,31 @@ __device__ __forceinline__ float epi_group(const EpiParams& E, const EpiCtx& X, 
   return ss;
 }
 
-__global__ void __launch_bounds__(kGemmThreads, 1)
-fnd_gemm_kernel(const __grid_constant__ GemmTableP tbl, RunCtx ctx) {
+// kVariant 0: general kernel (one CTA per SM, split-K capable).
+// kVariant 1: "light" kernel for the weight-gradient launch: no split-K, register-capped so that TWO CTAs share an SM
+//             (one CTA's store-bound epilogue overlaps the other's loads and MMAs; its ring is only as deep as its
+//             k-loop), and the trailing CTAs [gemm_ctas, gridDim.x) run the finalize jobs (bias / threshold / leaf /
+//             evidence gradient reductions, fnd_rows.cuh) concurrently with the tiles instead of in a kernel of their own.
+template <int kVariant>
+__global__ void __launch_bounds__(kGemmThreads, kVariant == 1 ? 2 : 1)
+fnd_gemm_kernel(const __grid_constant__ GemmTableP tbl, RunCtx ctx, const __grid_constant__ FinParams fin) {
+  if (kVariant == 1 && static_cast<int>(blockIdx.x) >= tbl.gemm_ctas) {
+    griddep_wait();
+    griddep_launch();
+    if (threadIdx.x < 256) finalize_cta(fin, static_cast<int>(blockIdx.x) - tbl.gemm_ctas, static_cast<int>(gridDim.x) - tbl.gemm_ctas);
+    return;
+  }
   const GemmProblem* probs = tbl.p;
   const int nprob = tbl.nprob;
   const bool A_MN = tbl.a_mn != 0, B_MN = tbl.b_mn != 0;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kGemmOperandBudget);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem);
   uint64_t* empty_bar = full_bar + kGemmMaxStages;
   uint64_t* accum_bar = empty_bar + kGemmMaxStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
   float* red_smem = reinterpret_cast<float*>(tmem_slot + 2);   // 8 floats
+  smem += kGemmSmemHeader;                                     // operand ring
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -380,7 +393,7 @@ fnd_gemm_kernel(const __grid_constant__ GemmTableP tbl, RunCtx ctx) {
     if (epi_tid == 0) FND_STAMP(4);
     float ss = 0.f;
 
-    if (splits == 1) {
+    if (kVariant == 1 || splits == 1) {
       float a0 = 0.f, a1 = 0.f;
       if (E.aux && row_ok) {
         a0 = E.aux[static_cast<size_t>(m) * 2];
@@ -399,7 +412,7 @@ fnd_gemm_kernel(const __grid_constant__ GemmTableP tbl, RunCtx ctx) {
         for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[j]);
         ss += epi_group(E, X, v, m, n0, PN, a0, a1);
       }
-    } else {
+    } else if (kVariant == 0) {
       // ---- split-K: publish this CTA's partial tile, wait for the other splits, finish a share of the tile ----
       // partial layout [split][group][row][8]: a warp's 32 rows of one group are 1 KB contiguous, so both the write
       // and the fix-up reads are fully coalesced
@@ -410,10 +423,10 @@ fnd_gemm_kernel(const __grid_constant__ GemmTableP tbl, RunCtx ctx) {
         uint32_t r[8];
         tmem_ld_32x8(taddr + g * 8, r);
         tmem_ld_wait();
-        __stcg(reinterpret_cast<float4*>(mine + g * (kGemmBM * 8)),
-               make_float4(__uint_as_float(r[0]), __uint_as_float(r[1]), __uint_as_float(r[2]), __uint_as_float(r[3])));
-        __stcg(reinterpret_cast<float4*>(mine + g * (kGemmBM * 8) + 4),
-               make_float4(__uint_as_float(r[4]), __uint_as_float(r[5]), __uint_as_float(r[6]), __uint_as_float(r[7])));
+        float pv[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) pv[j] = __uint_as_float(r[j]);
+        stcg_f8(mine + g * (kGemmBM * 8), pv);
       }
       __threadfence();
       epi_named_barrier();
@@ -455,19 +468,20 @@ fnd_gemm_kernel(const __grid_constant__ GemmTableP tbl, RunCtx ctx) {
         const float* src0 = ws_tile + static_cast<size_t>(g) * (kGemmBM * 8) + static_cast<size_t>(urow) * 8;
 #pragma unroll 1
         for (int s2 = 0; s2 < splits; s2 += 8) {
-          float4 t[16];
+          float t[8][8];
 #pragma unroll
           for (int qq = 0; qq < 8; ++qq) {
             const bool okq = s2 + qq < splits;
-            const float* src = src0 + static_cast<size_t>(okq ? s2 + qq : s2) * sstride;
-            t[2 * qq] = ldcg_f4(src);
-            t[2 * qq + 1] = ldcg_f4(src + 4);
-            if (!okq) { t[2 * qq] = make_float4(0.f, 0.f, 0.f, 0.f); t[2 * qq + 1] = t[2 * qq]; }
+            ldcg_f8(src0 + static_cast<size_t>(okq ? s2 + qq : s2) * sstride, t[qq]);
+            if (!okq) {
+#pragma unroll
+              for (int jj = 0; jj < 8; ++jj) t[qq][jj] = 0.f;
+            }
           }
 #pragma unroll
           for (int qq = 0; qq < 8; ++qq) {
-            v[0] += t[2 * qq].x; v[1] += t[2 * qq].y; v[2] += t[2 * qq].z; v[3] += t[2 * qq].w;
-            v[4] += t[2 * qq + 1].x; v[5] += t[2 * qq + 1].y; v[6] += t[2 * qq + 1].z; v[7] += t[2 * qq + 1].w;
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) v[jj] += t[qq][jj];
           }
         }
         if (!proceed || um >= PM || n0 >= PN) continue;

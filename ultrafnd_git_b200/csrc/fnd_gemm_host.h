@@ -55,6 +55,11 @@ inline int fill_problem(GemmProblem& p, const Operand& A, const Operand& B, int 
   if (ncombo != 1 && ncombo != 3) return -12;
   if (ncombo == 3 && (!A.lo || !B.lo)) return -13;
   if (N % 8) return -15;                 // the epilogue works on 8-column groups
+  // 256-bit epilogue accesses: fp32 operands whose pitch is a multiple of 8 floats must start 32-byte aligned
+  if (epi.out_f32 && (epi.f32_pitch & 7) == 0 && (reinterpret_cast<uintptr_t>(epi.out_f32) & 31)) return -16;
+  if (epi.out_pre && ((epi.pre_pitch & 7) || (reinterpret_cast<uintptr_t>(epi.out_pre) & 31))) return -16;
+  if (epi.add_in && ((epi.add_pitch & 7) || (reinterpret_cast<uintptr_t>(epi.add_in) & 31))) return -16;
+  if (epi.gate_z && ((epi.gate_pitch & 7) || (reinterpret_cast<uintptr_t>(epi.gate_z) & 31))) return -16;
   p.M = M; p.N = N; p.K = K;
   p.bn = bn;
   p.ncombo = ncombo;
@@ -71,6 +76,7 @@ inline int fill_problem(GemmProblem& p, const Operand& A, const Operand& B, int 
   p.splits = ceil_div(p.kb_total, p.kb_per_split);   // every split non-empty
   if (p.splits > 1 && (!ws || !ctr)) return -14;
   p.cta_count = p.tiles_m * p.tiles_n * p.splits;
+  if (p.nstages > p.kb_per_split * ncombo) p.nstages = p.kb_per_split * ncombo;   // never deeper than the k-loop
   p.hintA = hintA; p.hintB = hintB;
   p.splitk_ws = ws; p.splitk_ctr = ctr;
   p.epi = epi;
@@ -103,13 +109,27 @@ inline int finish_table(GemmProblem* probs, int n) {
 // Opt the GEMM kernel into its dynamic shared-memory size (per device; called at bind time so that no attribute
 // call ever happens inside a stream capture).
 inline cudaError_t init_gemm_attrs() {
-  return cudaFuncSetAttribute(fnd_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes);
+  cudaError_t e = cudaFuncSetAttribute(fnd_gemm_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(fnd_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes);
+}
+
+// Dynamic shared memory one launch of `host_table` needs: header + the deepest ring among its problems (+ align slack).
+inline int gemm_smem_bytes(const GemmProblem* host_table, int nprob) {
+  int ring = 0;
+  for (int i = 0; i < nprob; ++i) {
+    const int r = host_table[i].nstages * host_table[i].stage_bytes;
+    ring = r > ring ? r : ring;
+  }
+  return ring + 1024 + kGemmSmemHeader;
 }
 
 // kind: 0 = forward (A K-major, B K-major); 1 = dgrad (A K-major, B MN-major); 2 = wgrad (both MN-major);
 // 3 = (A MN-major, B K-major). `host_table` is copied into the kernel's parameter space at launch.
+// `fin` (optional): finalize jobs run by `fin_ctas` trailing CTAs of the launch (light variant, see fnd_gemm.cuh).
+// The light variant is chosen for launches without split-K whose ring is shallow enough for two CTAs per SM.
 inline cudaError_t launch_gemm(int kind, const GemmProblem* host_table, int nprob, int grid, RunCtx ctx,
-                               cudaStream_t st, bool pdl = false) {
+                               cudaStream_t st, bool pdl = false, const FinParams* fin = nullptr, int fin_ctas = 0) {
   if (grid <= 0) return cudaSuccess;
   if (nprob < 1 || nprob > kGemmTableCap || kind < 0 || kind > 3) return cudaErrorInvalidValue;
   GemmTableP t;
@@ -117,7 +137,16 @@ inline cudaError_t launch_gemm(int kind, const GemmProblem* host_table, int npro
   t.nprob = nprob;
   t.a_mn = (kind == 2 || kind == 3) ? 1 : 0;
   t.b_mn = (kind == 1 || kind == 2) ? 1 : 0;
-  return launch_k(fnd_gemm_kernel, grid, kGemmThreads, kGemmSmemBytes, st, pdl, t, ctx);
+  t.gemm_ctas = grid;
+  FinParams f;
+  memset(&f, 0, sizeof(f));
+  if (fin) f = *fin;
+  const int smem = gemm_smem_bytes(host_table, nprob);
+  bool light = kind == 2 && smem <= 100 * 1024;
+  for (int i = 0; i < nprob; ++i) light = light && host_table[i].splits == 1;
+  if (!light && fin_ctas > 0) return cudaErrorInvalidValue;
+  if (light) return launch_k(fnd_gemm_kernel<1>, grid + fin_ctas, kGemmThreads, smem, st, pdl, t, ctx, f);
+  return launch_k(fnd_gemm_kernel<0>, grid, kGemmThreads, smem, st, pdl, t, ctx, f);
 }
 
 }  // namespace fnd

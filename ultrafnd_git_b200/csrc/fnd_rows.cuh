@@ -766,7 +766,7 @@ __global__ void dropout_mask_kernel(float* out, size_t n, float p, int stream, c
 // ---------------------------------------------------------------------------------------------
 // finalize: batch reductions + gate softmax backward + gradient norm + step bookkeeping
 // ---------------------------------------------------------------------------------------------
-enum : int { kJobColsumF32 = 0, kJobColsumBF16 = 1, kJobColsumAux = 2, kJobSoftmaxBwd = 3 };
+enum : int { kJobColsumF32 = 0, kJobColsumBF16 = 1, kJobColsumAux = 2, kJobSoftmaxBwd = 3, kJobLossMean = 4 };
 struct FinJob {
   int type;
   int rows, cols;               // reduce over rows; cols outputs
@@ -778,33 +778,67 @@ struct FinJob {
   float* dst;
   int dst_pitch;                // kJobColsumAux: dst[n*dst_pitch + k]
   float scale;
-  int cta_begin, cta_count;     // 64 columns per CTA (softmax-bwd: one row per CTA)
+  int cta_begin, cta_count;     // 64 columns per CTA (softmax-bwd: one row per CTA; loss mean: one CTA)
   int want_norm;                // include outputs in the gradient norm
 };
 struct FinParams {
   const FinJob* jobs;
   int njobs;
-  float* slots;                 // [total_slots]: GEMM wgrad CTAs first, then this kernel's CTAs
-  int slot_base;                // index of this kernel's first slot
+  float* slots;                 // [total_slots]: GEMM wgrad CTAs first, then the finalize CTAs
+  int slot_base;                // index of the finalize CTAs' first slot
   int total_slots;
   const float* loss_row;        // [B] (may be null)
   int B;
   DevState* state;
-  int update_step;              // 1: advance optimizer step / rng salt and publish bias corrections
+  int update_step;              // 1: advance optimizer step and publish bias corrections
+  int elect_last;               // 1: the last CTA to finish reduces all slots to the gradient norm (stand-alone launches);
+                                // 0: slots only — the consumer (adamw_kernel / norm_finish_kernel) reduces them
 };
 
-__global__ void __launch_bounds__(256) finalize_kernel(FinParams p) {
-  griddep_wait();
-  griddep_launch();
+// Global gradient norm from the per-CTA sum-of-squares slots: fixed order, double accumulation; every thread of the
+// (256-thread) block receives the result. `dred` is 256 doubles of shared memory.
+__device__ __forceinline__ double block_reduce_slots(const float* slots, int n, double* dred) {
+  double part = 0.0;
+  for (int i = threadIdx.x; i < n; i += 256) part += static_cast<double>(__ldcg(slots + i));
+  dred[threadIdx.x] = part;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) dred[threadIdx.x] += dred[threadIdx.x + o];
+    __syncthreads();
+  }
+  const double r = dred[0];
+  __syncthreads();
+  return r;
+}
+__device__ __forceinline__ float clip_coef_of(float max_norm, float norm) {
+  return (max_norm > 0.f) ? fminf(1.0f, max_norm / (norm + 1e-6f)) : 1.0f;
+}
+
+// One finalize CTA (256 threads; `cta` = index among the finalize CTAs). Callable from any kernel whose block has
+// >= 256 threads: only threads [0,256) may enter.
+__device__ __forceinline__ void finalize_cta(const FinParams& p, int cta, int ncta) {
   __shared__ float sm[4][64];
   __shared__ float red[8];
   __shared__ int is_last;
+  __shared__ double dred[256];
   int ji = 0;
-  while (ji + 1 < p.njobs && static_cast<int>(blockIdx.x) >= p.jobs[ji + 1].cta_begin) ++ji;
+  while (ji + 1 < p.njobs && cta >= p.jobs[ji + 1].cta_begin) ++ji;
   const FinJob J = p.jobs[ji];
-  const int local = blockIdx.x - J.cta_begin;
+  const int local = cta - J.cta_begin;
   float ss = 0.f;
-  if (J.type == kJobSoftmaxBwd) {
+  if (J.type == kJobLossMean) {
+    // mean loss = sum(loss_row) * loss_scale   (F.cross_entropy mean reduction, forensic_trainer.py:287)
+    double part = 0.0;
+    for (int i = threadIdx.x; i < J.rows; i += 256) part += static_cast<double>(J.src_f32[i]);
+    dred[threadIdx.x] = part;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+      if (threadIdx.x < o) dred[threadIdx.x] += dred[threadIdx.x + o];
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) p.state->loss = static_cast<float>(dred[0] * static_cast<double>(p.state->loss_scale));
+    __syncthreads();
+  } else if (J.type == kJobSoftmaxBwd) {
     // dgate[j] = alpha[j] * (draw[j] - sum_j' alpha[j'] draw[j'])       (softmax backward of deep_truth_classifier.py:64)
     const int k = local;
     const float* al = J.aux + static_cast<size_t>(k) * J.cols;
@@ -877,36 +911,37 @@ __global__ void __launch_bounds__(256) finalize_kernel(FinParams p) {
   if (threadIdx.x == 0) {
     float tot = 0.f;
     for (int w = 0; w < 8; ++w) tot += red[w];
-    p.slots[p.slot_base + blockIdx.x] = tot;
-    __threadfence();
-    const unsigned int old = atomicAdd(&p.state->fin_counter, 1u);
-    is_last = (old == gridDim.x - 1) ? 1 : 0;
+    p.slots[p.slot_base + cta] = tot;
+    is_last = 0;
+    if (p.elect_last) {
+      __threadfence();
+      const unsigned int old = atomicAdd(&p.state->fin_counter, 1u);
+      is_last = (old == static_cast<unsigned int>(ncta) - 1) ? 1 : 0;
+    }
   }
   __syncthreads();
   if (!is_last) return;
-  // ---- last CTA: global norm (fixed-order, double accumulation), mean loss, step bookkeeping ----
+  // ---- last CTA (stand-alone launches only): global norm, mean loss, step bookkeeping ----
   __threadfence();
-  double part = 0.0;
-  for (int i = threadIdx.x; i < p.total_slots; i += 256) part += static_cast<double>(__ldcg(p.slots + i));
+  const double tot = block_reduce_slots(p.slots, p.total_slots, dred);
   double lsum = 0.0;
-  if (p.loss_row)
-    for (int i = threadIdx.x; i < p.B; i += 256) lsum += static_cast<double>(__ldcg(p.loss_row + i));
-  __shared__ double dred[2][256];
-  dred[0][threadIdx.x] = part; dred[1][threadIdx.x] = lsum;
-  __syncthreads();
-  for (int o = 128; o > 0; o >>= 1) {
-    if (threadIdx.x < o) {
-      dred[0][threadIdx.x] += dred[0][threadIdx.x + o];
-      dred[1][threadIdx.x] += dred[1][threadIdx.x + o];
-    }
+  if (p.loss_row) {
+    double part = 0.0;
+    for (int i = threadIdx.x; i < p.B; i += 256) part += static_cast<double>(__ldcg(p.loss_row + i));
+    dred[threadIdx.x] = part;
     __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+      if (threadIdx.x < o) dred[threadIdx.x] += dred[threadIdx.x + o];
+      __syncthreads();
+    }
+    lsum = dred[0];
   }
   if (threadIdx.x == 0) {
     DevState* S = p.state;
-    const float norm = static_cast<float>(sqrt(dred[0][0]));
+    const float norm = static_cast<float>(sqrt(tot));
     S->grad_norm = norm;
-    S->clip_coef = (S->max_norm > 0.f) ? fminf(1.0f, S->max_norm / (norm + 1e-6f)) : 1.0f;
-    if (p.loss_row) S->loss = static_cast<float>(dred[1][0] * static_cast<double>(S->loss_scale));
+    S->clip_coef = clip_coef_of(S->max_norm, norm);
+    if (p.loss_row) S->loss = static_cast<float>(lsum * static_cast<double>(S->loss_scale));
     if (p.update_step) {
       S->step += 1;
       S->bc1 = 1.0f - powf(S->beta1, static_cast<float>(S->step));
@@ -914,6 +949,12 @@ __global__ void __launch_bounds__(256) finalize_kernel(FinParams p) {
     }
     S->fin_counter = 0u;
   }
+}
+
+__global__ void __launch_bounds__(256) finalize_kernel(FinParams p) {
+  griddep_wait();
+  griddep_launch();
+  finalize_cta(p, static_cast<int>(blockIdx.x), static_cast<int>(gridDim.x));
 }
 
 }  // namespace fnd
