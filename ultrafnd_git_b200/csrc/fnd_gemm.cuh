@@ -206,7 +206,8 @@ fnd_gemm_kernel(const __grid_constant__ GemmTableP tbl, RunCtx ctx, const __grid
   if (kVariant == 1 && static_cast<int>(blockIdx.x) >= tbl.gemm_ctas) {
     griddep_wait();
     griddep_launch();
-    if (threadIdx.x < 256) finalize_cta(fin, static_cast<int>(blockIdx.x) - tbl.gemm_ctas, static_cast<int>(gridDim.x) - tbl.gemm_ctas);
+    // the election counter is shared by every CTA of the launch (tiles and finalize CTAs)
+    if (threadIdx.x < 256) finalize_cta(fin, static_cast<int>(blockIdx.x) - tbl.gemm_ctas, static_cast<int>(gridDim.x));
     return;
   }
   const GemmProblem* probs = tbl.p;
@@ -507,6 +508,16 @@ fnd_gemm_kernel(const __grid_constant__ GemmTableP tbl, RunCtx ctx, const __grid
       if (epi_tid == 0)
         E.sumsq_slots[local] = ((red_smem[0] + red_smem[1]) + (red_smem[2] + red_smem[3])) +
                                ((red_smem[4] + red_smem[5]) + (red_smem[6] + red_smem[7]));
+    }
+    if (kVariant == 1 && fin.elect_last && ew == 0) {
+      // fused step: the last CTA of the launch (tile or finalize CTA alike) turns the slots into the gradient norm
+      int last = 0;
+      if (lane == 0) {
+        __threadfence();
+        last = (atomicAdd(&fin.state->fin_counter, 1u) == gridDim.x - 1) ? 1 : 0;
+      }
+      last = __shfl_sync(0xffffffffu, last, 0);
+      if (last) warp_publish_norm(fin);
     }
   }
 

@@ -23,12 +23,7 @@ struct AdamWParams {
   size_t rp_begin, rp_end;       // element range inside the arena
   int rp_cols, rp_pitch;
   __nv_bfloat16* rp_hi; __nv_bfloat16* rp_lo;
-  DevState* state;
-  // Fused step: the gradient norm has not been reduced yet — `slots` holds the per-CTA sums of squares left by the
-  // wgrad / finalize CTAs. Every CTA reduces them itself (identical fixed order => identical coefficient), takes
-  // optimizer step t = state->step + 1, and the LAST CTA to finish publishes norm / clip coefficient / step.
-  const float* slots;            // null: state->{clip_coef, bc1, bc2} were published by an earlier kernel
-  int nslots;
+  const DevState* state;
 };
 
 __device__ __forceinline__ void shadow_store4(const AdamWParams& a, size_t i, const float4& x) {
@@ -55,21 +50,11 @@ __device__ __forceinline__ void shadow_store4(const AdamWParams& a, size_t i, co
 __global__ void __launch_bounds__(256) adamw_kernel(AdamWParams a) {
   griddep_wait();
   griddep_launch();
-  DevState* S = a.state;
-  const float lr = S->lr, b1 = S->beta1, b2 = S->beta2, eps = S->eps;
-  float coef = S->clip_coef, bc1 = S->bc1, bc2 = S->bc2, norm = 0.f;
-  int t = S->step;
-  if (a.slots) {
-    __shared__ double dred[256];
-    norm = static_cast<float>(sqrt(block_reduce_slots(a.slots, a.nslots, dred)));
-    coef = clip_coef_of(S->max_norm, norm);
-    t += 1;
-    bc1 = 1.0f - powf(b1, static_cast<float>(t));
-    bc2 = 1.0f - powf(b2, static_cast<float>(t));
-  }
+  const DevState* S = a.state;
+  const float coef = S->clip_coef, lr = S->lr, b1 = S->beta1, b2 = S->beta2, eps = S->eps;
   const float decay = 1.0f - lr * S->weight_decay;
-  const float step_size = lr / bc1;
-  const float inv_sqrt_bc2 = rsqrtf(bc2);
+  const float step_size = lr / S->bc1;
+  const float inv_sqrt_bc2 = rsqrtf(S->bc2);
   const uint64_t pol = l2_policy_evict_first();
   for (size_t i = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 4; i < a.n;
        i += static_cast<size_t>(gridDim.x) * blockDim.x * 4) {
@@ -91,18 +76,6 @@ __global__ void __launch_bounds__(256) adamw_kernel(AdamWParams a) {
     st_f4_policy(a.m + i, m, pol);
     st_f4_policy(a.v + i, v, pol);
     shadow_store4(a, i, p);
-  }
-  if (a.slots) {
-    // publish the step bookkeeping once every CTA has read the old state (all CTAs of this grid are co-resident or
-    // have finished by the time the counter completes)
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      const unsigned int old = atomicAdd(&S->fin_counter, 1u);
-      if (old == gridDim.x - 1) {
-        S->grad_norm = norm; S->clip_coef = coef; S->step = t; S->bc1 = bc1; S->bc2 = bc2;
-        S->fin_counter = 0u;
-      }
-    }
   }
 }
 

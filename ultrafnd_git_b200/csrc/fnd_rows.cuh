@@ -792,7 +792,7 @@ struct FinParams {
   DevState* state;
   int update_step;              // 1: advance optimizer step and publish bias corrections
   int elect_last;               // 1: the last CTA to finish reduces all slots to the gradient norm (stand-alone launches);
-                                // 0: slots only — the consumer (adamw_kernel / norm_finish_kernel) reduces them
+                                // 0: slots only — a later kernel reduces them
 };
 
 // Global gradient norm from the per-CTA sum-of-squares slots: fixed order, double accumulation; every thread of the
@@ -812,6 +812,37 @@ __device__ __forceinline__ double block_reduce_slots(const float* slots, int n, 
 }
 __device__ __forceinline__ float clip_coef_of(float max_norm, float norm) {
   return (max_norm > 0.f) ? fminf(1.0f, max_norm / (norm + 1e-6f)) : 1.0f;
+}
+
+// Called by ONE full warp of the last CTA of a launch (elected through state->fin_counter): reduces the per-CTA
+// sum-of-squares slots to the global gradient norm in a fixed order (lane-strided partial sums in double, xor
+// butterfly), so the result does not depend on which CTA happened to finish last; publishes norm, clip coefficient,
+// optionally the mean loss and the optimizer-step bookkeeping, and re-arms the counter.
+__device__ __forceinline__ void warp_publish_norm(const FinParams& p) {
+  const int lane = threadIdx.x & 31;
+  __threadfence();
+  double part = 0.0, lsum = 0.0;
+  for (int i = lane; i < p.total_slots; i += 32) part += static_cast<double>(__ldcg(p.slots + i));
+  if (p.loss_row)
+    for (int i = lane; i < p.B; i += 32) lsum += static_cast<double>(__ldcg(p.loss_row + i));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    part += __shfl_xor_sync(0xffffffffu, part, o);
+    lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
+  }
+  if (lane == 0) {
+    DevState* S = p.state;
+    const float norm = static_cast<float>(sqrt(part));
+    S->grad_norm = norm;
+    S->clip_coef = clip_coef_of(S->max_norm, norm);
+    if (p.loss_row) S->loss = static_cast<float>(lsum * static_cast<double>(S->loss_scale));
+    if (p.update_step) {
+      S->step += 1;
+      S->bc1 = 1.0f - powf(S->beta1, static_cast<float>(S->step));
+      S->bc2 = 1.0f - powf(S->beta2, static_cast<float>(S->step));
+    }
+    S->fin_counter = 0u;
+  }
 }
 
 // One finalize CTA (256 threads; `cta` = index among the finalize CTAs). Callable from any kernel whose block has
@@ -921,34 +952,8 @@ __device__ __forceinline__ void finalize_cta(const FinParams& p, int cta, int nc
   }
   __syncthreads();
   if (!is_last) return;
-  // ---- last CTA (stand-alone launches only): global norm, mean loss, step bookkeeping ----
-  __threadfence();
-  const double tot = block_reduce_slots(p.slots, p.total_slots, dred);
-  double lsum = 0.0;
-  if (p.loss_row) {
-    double part = 0.0;
-    for (int i = threadIdx.x; i < p.B; i += 256) part += static_cast<double>(__ldcg(p.loss_row + i));
-    dred[threadIdx.x] = part;
-    __syncthreads();
-    for (int o = 128; o > 0; o >>= 1) {
-      if (threadIdx.x < o) dred[threadIdx.x] += dred[threadIdx.x + o];
-      __syncthreads();
-    }
-    lsum = dred[0];
-  }
-  if (threadIdx.x == 0) {
-    DevState* S = p.state;
-    const float norm = static_cast<float>(sqrt(tot));
-    S->grad_norm = norm;
-    S->clip_coef = clip_coef_of(S->max_norm, norm);
-    if (p.loss_row) S->loss = static_cast<float>(lsum * static_cast<double>(S->loss_scale));
-    if (p.update_step) {
-      S->step += 1;
-      S->bc1 = 1.0f - powf(S->beta1, static_cast<float>(S->step));
-      S->bc2 = 1.0f - powf(S->beta2, static_cast<float>(S->step));
-    }
-    S->fin_counter = 0u;
-  }
+  // ---- last CTA of the launch: global norm, mean loss, step bookkeeping ----
+  if (threadIdx.x < 32) warp_publish_norm(p);
 }
 
 __global__ void __launch_bounds__(256) finalize_kernel(FinParams p) {
