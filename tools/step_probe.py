@@ -31,3 +31,17 @@ for i, n in enumerate(names):
     else:
         print(f"{n:12s} grid {g:4d} median us:", {l: round(float(d[:, j + 1].median()), 2) for j, l in enumerate(lab)},
               "max epi", round(float(d[:, 6].max()), 2))
+
+# ---- wgrad launch: per-problem CTA durations (tile CTAs only) ----
+i = names.index("wgrad_all")
+g = int((buf[i, :, 0] != 0).sum())
+t = buf[i, :g]
+dur = (t[:, 7] - t[:, 0]) / 1.965e3
+seg = [("pre.3", 16), ("pre.0", 16), ("dA", 4), ("fuse1", 32), ("fuse0", 512), ("qkv", 144), ("proj", 56)]
+o = 0
+print("wgrad per-problem CTA duration us (median / p90 / max) and phase medians [setup, first_full, mma, accum, epi0, epi_done]")
+for nm, n in seg:
+    d = dur[o:o + n]
+    ph = ((t[o:o + n, 1:7] - t[o:o + n, :1]) / 1.965e3).median(0).values
+    print(f"  {nm:6s} n={n:4d} {float(d.median()):6.2f} {float(d.quantile(0.9)):6.2f} {float(d.max()):6.2f}  ", [round(float(x), 2) for x in ph])
+    o += n

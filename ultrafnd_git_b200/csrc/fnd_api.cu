@@ -223,6 +223,11 @@ static int build_tables(Plan& P) {
       job(T, kJobColsumF32, P.n_asm_ctas, 3 * P.L.evstride, 3 * P.L.evstride, P.buf<float>("ev_partial"), nullptr, nullptr,
           nullptr, P.G("fusion.attn_tv.evidence_proj.0.weight"), 0, 1.0f);
     }
+    if (clf && fus) {   // fused step only: mean loss (the stand-alone finalize launches compute it in their last CTA)
+      job(T, kJobLossMean, B, 1, 1, P.buf<float>("loss_row"), nullptr, nullptr, nullptr, nullptr, 0, 1.0f);
+      T.host.back().cta_count = 1;
+      T.host.back().want_norm = 0;
+    }
     int c = 0;
     for (auto& j : T.host) { j.cta_begin = c; c += j.cta_count; }
     T.grid = c;
@@ -443,6 +448,7 @@ static AdamWParams adamw_params(const Plan& P) {
     a.rp_hi = P.sh_hi + P.L.n_shadow; a.rp_lo = P.sh_lo ? P.sh_lo + P.L.n_shadow : nullptr;
   }
   a.state = P.state();
+  a.slots = nullptr; a.nslots = 0;
   return a;
 }
 
@@ -723,7 +729,7 @@ int fnd_clip_adamw_step(void* plan, int norm_from_slots, void* stream) {
     float* slots = P.buf<float>("slots");
     const int nb = 148 * 4;
     FND_CUDA_OK(launch_k(sumsq_kernel, nb, 256, 0, st, take_pdl(P), P.grads, static_cast<size_t>(P.L.n_hot), slots + kSlotSumsq));
-    FND_CUDA_OK(launch_k(norm_finish_kernel, 1, 256, 0, st, take_pdl(P), slots + kSlotSumsq, nb, P.state(), 1));
+    FND_CUDA_OK(launch_k(norm_finish_kernel, 1, 32, 0, st, take_pdl(P), slots + kSlotSumsq, nb, P.state(), 1));
     mark(P, "grad_norm", st);
   } else {
     FND_CUDA_OK(launch_k(step_kernel, 1, 32, 0, st, take_pdl(P), P.state()));
@@ -736,7 +742,7 @@ int fnd_clip_adamw_step(void* plan, int norm_from_slots, void* stream) {
 }
 
 // ------------------------------- fused trainer step -------------------------------
-static int train_fwd_bwd_impl(void* plan, const fnd_inputs* in, int update_step, void* stream) {
+static int train_fwd_bwd_impl(void* plan, const fnd_inputs* in, int fused_optimizer, void* stream) {
   FND_PLAN(plan);
   if (!in || !in->labels) return -1;
   FND_OK(fusion_forward_impl(P, in, 1, true, st));
@@ -750,10 +756,17 @@ static int train_fwd_bwd_impl(void* plan, const fnd_inputs* in, int update_step,
   FND_OK(run_assemble_bwd(P, st));
   FND_OK(run_gemm(P, P.dg_qkv, 1, st, "dgrad_qkv"));
   // Weight gradients of every GEMM; the trailing CTAs of the same launch run the finalize jobs (bias / threshold /
-  // leaf / evidence reductions). Every CTA leaves its sum of squares in "slots" and the LAST CTA of the launch
-  // reduces them to the global norm, the clip coefficient, the mean loss and (fused step) the optimizer-step bookkeeping.
-  const FinParams f = fin_params(P, P.fin_all, P.wg_all.grid, P.total_slots, true, update_step, 1);
-  return run_gemm(P, P.wg_all, 1, st, "wgrad_all", &f, P.fin_all.grid);
+  // leaf / evidence reductions, mean loss). Every CTA leaves its sum of squares in "slots"; whoever consumes the
+  // gradients next reduces the slots to the global norm: adamw_kernel in the fused step (no election, fence or atomic
+  // on the tile CTAs' critical path — measured 10 us), norm_finish_kernel otherwise.
+  const FinParams f = fin_params(P, P.fin_all, P.wg_all.grid, P.total_slots, false, 0, 0);
+  FND_OK(run_gemm(P, P.wg_all, 1, st, "wgrad_all", &f, P.fin_all.grid));
+  if (!fused_optimizer) {
+    FND_SKIP(P);
+    FND_CUDA_OK(launch_k(norm_finish_kernel, 1, 32, 0, st, take_pdl(P), P.buf<float>("slots"), P.total_slots, P.state(), 0));
+    mark(P, "grad_norm", st);
+  }
+  return 0;
 }
 
 int fnd_train_fwd_bwd(void* plan, const fnd_inputs* in, void* stream) { return train_fwd_bwd_impl(plan, in, 0, stream); }
@@ -768,7 +781,9 @@ int fnd_train_step(void* plan, const fnd_inputs* in, void* stream) {
   P.pdl_next = true;        // continues the chain started by train_fwd_bwd_impl
   P.launch_seq = 16;
   FND_SKIP(P);
+  // AdamW reduces the norm slots itself (identical in every CTA), clips, steps and publishes the bookkeeping.
   AdamWParams a = adamw_params(P);
+  a.slots = P.buf<float>("slots"); a.nslots = P.total_slots;
   FND_CUDA_OK(launch_k(adamw_kernel, 148 * 8, 256, 0, st, take_pdl(P), a));
   mark(P, "adamw", st);
   return 0;
@@ -836,7 +851,7 @@ int fnd_launch_count(const void* plan, const char* entry) {
   if (e == "fusion_forward") return fusion_fwd + 1;
   if (e == "classifier_forward") return 3;
   if (e == "eval_step") return fusion_fwd + 1 + 2 + 1;
-  if (e == "train_fwd_bwd") return fusion_fwd + 2 + 1 + 4 + 1 + 1 + 1;       // ... wgrad(+finalize CTAs)
+  if (e == "train_fwd_bwd") return fusion_fwd + 2 + 1 + 4 + 1 + 1 + 1 + 1;   // ... wgrad(+finalize CTAs), grad_norm
   if (e == "clip_adamw_step") return 3;
   if (e == "train_step") return fusion_fwd + 2 + 1 + 4 + 1 + 1 + 1 + 1;       // ... wgrad(+finalize CTAs), adamw
   return -2;

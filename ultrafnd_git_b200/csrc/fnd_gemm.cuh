@@ -72,6 +72,7 @@ struct EpiParams {
   __nv_bfloat16* out_lo;
   int bf_pitch;
   float* sumsq_slots;                // per-CTA sum of v^2 (for the global gradient norm)
+  int plain_f32;                     // host-set: the epilogue is ONLY "store v as fp32 (+ sum of squares)", pitch % 8 == 0
 };
 
 struct alignas(128) GemmProblem {
@@ -206,7 +207,6 @@ fnd_gemm_kernel(const __grid_constant__ GemmTableP tbl, RunCtx ctx, const __grid
   if (kVariant == 1 && static_cast<int>(blockIdx.x) >= tbl.gemm_ctas) {
     griddep_wait();
     griddep_launch();
-    // the election counter is shared by every CTA of the launch (tiles and finalize CTAs)
     if (threadIdx.x < 256) finalize_cta(fin, static_cast<int>(blockIdx.x) - tbl.gemm_ctas, static_cast<int>(gridDim.x));
     return;
   }
@@ -401,6 +401,30 @@ fnd_gemm_kernel(const __grid_constant__ GemmTableP tbl, RunCtx ctx, const __grid
         a1 = E.aux[static_cast<size_t>(m) * 2 + 1];
       }
       if (epi_tid == 0) FND_STAMP(5);
+      if (E.plain_f32 && bn >= 64) {
+        // Store-only epilogue (weight gradients, dcat): 32 accumulator columns per tcgen05.ld, four 256-bit stores.
+        // Each warp of a lane quarter takes one contiguous half of the tile's columns.
+        const int c_end = (half + 1) * (bn >> 1);
+#pragma unroll 1
+        for (int c = half * (bn >> 1); c < c_end; c += 32) {
+          uint32_t r[32];
+          tmem_ld_32x32(taddr + c, r);
+          tmem_ld_wait();
+          if (!proceed || !row_ok) continue;
+          float* dst = E.out_f32 + static_cast<size_t>(m) * E.f32_pitch + nb + c;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            if (nb + c + q * 8 < PN) {
+              float v[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[q * 8 + j]);
+              st_f8(dst + q * 8, v);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) ss = fmaf(v[j], v[j], ss);
+            }
+          }
+        }
+      } else
 #pragma unroll 1
       for (int g = half; g < ngroups; g += 2) {
         uint32_t r[8];
@@ -508,16 +532,6 @@ fnd_gemm_kernel(const __grid_constant__ GemmTableP tbl, RunCtx ctx, const __grid
       if (epi_tid == 0)
         E.sumsq_slots[local] = ((red_smem[0] + red_smem[1]) + (red_smem[2] + red_smem[3])) +
                                ((red_smem[4] + red_smem[5]) + (red_smem[6] + red_smem[7]));
-    }
-    if (kVariant == 1 && fin.elect_last && ew == 0) {
-      // fused step: the last CTA of the launch (tile or finalize CTA alike) turns the slots into the gradient norm
-      int last = 0;
-      if (lane == 0) {
-        __threadfence();
-        last = (atomicAdd(&fin.state->fin_counter, 1u) == gridDim.x - 1) ? 1 : 0;
-      }
-      last = __shfl_sync(0xffffffffu, last, 0);
-      if (last) warp_publish_norm(fin);
     }
   }
 

@@ -80,6 +80,8 @@ inline int fill_problem(GemmProblem& p, const Operand& A, const Operand& B, int 
   p.hintA = hintA; p.hintB = hintB;
   p.splitk_ws = ws; p.splitk_ctr = ctr;
   p.epi = epi;
+  p.epi.plain_f32 = (epi.out_f32 && !epi.bias && !epi.aux && !epi.add_in && !epi.out_pre && !epi.act && !epi.gate_z &&
+                     !epi.out_hi && epi.drop_p == 0.f && (epi.f32_pitch & 7) == 0) ? 1 : 0;
   for (int h = 0; h < (ncombo == 3 ? 2 : 1); ++h) {
     const void* a = h ? static_cast<const void*>(A.lo) : static_cast<const void*>(A.hi);
     const void* b = h ? static_cast<const void*>(B.lo) : static_cast<const void*>(B.hi);

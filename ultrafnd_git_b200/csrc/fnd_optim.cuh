@@ -23,7 +23,12 @@ struct AdamWParams {
   size_t rp_begin, rp_end;       // element range inside the arena
   int rp_cols, rp_pitch;
   __nv_bfloat16* rp_hi; __nv_bfloat16* rp_lo;
-  const DevState* state;
+  DevState* state;
+  // Fused step: the gradient norm has not been reduced yet — `slots` holds the per-CTA sums of squares left by the
+  // wgrad / finalize CTAs. One warp of every CTA reduces them (same fixed order everywhere => identical coefficient),
+  // the CTA takes optimizer step t = state->step + 1, and the LAST CTA to finish publishes norm / coefficient / step.
+  const float* slots;            // null: state->{clip_coef, bc1, bc2} were published by an earlier kernel
+  int nslots;
 };
 
 __device__ __forceinline__ void shadow_store4(const AdamWParams& a, size_t i, const float4& x) {
@@ -47,14 +52,29 @@ __device__ __forceinline__ void shadow_store4(const AdamWParams& a, size_t i, co
   }
 }
 
-__global__ void __launch_bounds__(256) adamw_kernel(AdamWParams a) {
+__global__ void __launch_bounds__(256, 5) adamw_kernel(AdamWParams a) {
   griddep_wait();
   griddep_launch();
-  const DevState* S = a.state;
-  const float coef = S->clip_coef, lr = S->lr, b1 = S->beta1, b2 = S->beta2, eps = S->eps;
+  DevState* S = a.state;
+  const float lr = S->lr, b1 = S->beta1, b2 = S->beta2, eps = S->eps;
+  float coef = S->clip_coef, bc1 = S->bc1, bc2 = S->bc2, norm = 0.f;
+  int t = S->step;
+  if (a.slots) {
+    __shared__ float s_norm;
+    if (threadIdx.x < 32) {
+      const double ss = warp_reduce_slots<3>(a.slots, a.nslots);      // 3 in flight: keeps the kernel at 5 CTAs/SM
+      if (threadIdx.x == 0) s_norm = static_cast<float>(sqrt(ss));
+    }
+    __syncthreads();
+    norm = s_norm;
+    coef = clip_coef_of(S->max_norm, norm);
+    t += 1;
+    bc1 = 1.0f - powf(b1, static_cast<float>(t));
+    bc2 = 1.0f - powf(b2, static_cast<float>(t));
+  }
   const float decay = 1.0f - lr * S->weight_decay;
-  const float step_size = lr / S->bc1;
-  const float inv_sqrt_bc2 = rsqrtf(S->bc2);
+  const float step_size = lr / bc1;
+  const float inv_sqrt_bc2 = rsqrtf(bc2);
   const uint64_t pol = l2_policy_evict_first();
   for (size_t i = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 4; i < a.n;
        i += static_cast<size_t>(gridDim.x) * blockDim.x * 4) {
@@ -76,6 +96,18 @@ __global__ void __launch_bounds__(256) adamw_kernel(AdamWParams a) {
     st_f4_policy(a.m + i, m, pol);
     st_f4_policy(a.v + i, v, pol);
     shadow_store4(a, i, p);
+  }
+  if (a.slots) {
+    // Publish the step bookkeeping once every CTA has read the old state: a CTA bumps the counter after its last read
+    // of *S, so whoever completes the count knows nobody still needs the old values.
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const unsigned int old = atomicAdd(&S->fin_counter, 1u);
+      if (old == gridDim.x - 1) {
+        S->grad_norm = norm; S->clip_coef = coef; S->step = t; S->bc1 = bc1; S->bc2 = bc2;
+        S->fin_counter = 0u;
+      }
+    }
   }
 }
 
@@ -120,23 +152,17 @@ __global__ void step_kernel(DevState* S) {
   griddep_launch();
   if (threadIdx.x == 0 && blockIdx.x == 0) advance_step(S);
 }
-__global__ void __launch_bounds__(256) norm_finish_kernel(const float* __restrict__ slots, int nslots, DevState* S,
-                                                          int update_step) {
+// slots -> gradient norm + clip coefficient (+ optimizer-step bookkeeping): the consumer of the slots when no fused
+// AdamW follows (fnd_train_fwd_bwd) and after sumsq_kernel (gradients reduced across ranks).
+__global__ void __launch_bounds__(32) norm_finish_kernel(const float* __restrict__ slots, int nslots, DevState* S,
+                                                         int update_step) {
   griddep_wait();
   griddep_launch();
-  __shared__ double dred[256];
-  double part = 0.0;
-  for (int i = threadIdx.x; i < nslots; i += 256) part += static_cast<double>(slots[i]);
-  dred[threadIdx.x] = part;
-  __syncthreads();
-  for (int o = 128; o > 0; o >>= 1) {
-    if (threadIdx.x < o) dred[threadIdx.x] += dred[threadIdx.x + o];
-    __syncthreads();
-  }
+  const double ss = warp_reduce_slots(slots, nslots);
   if (threadIdx.x == 0) {
-    const float norm = static_cast<float>(sqrt(dred[0]));
+    const float norm = static_cast<float>(sqrt(ss));
     S->grad_norm = norm;
-    S->clip_coef = (S->max_norm > 0.f) ? fminf(1.0f, S->max_norm / (norm + 1e-6f)) : 1.0f;
+    S->clip_coef = clip_coef_of(S->max_norm, norm);
     if (update_step) advance_step(S);
   }
 }

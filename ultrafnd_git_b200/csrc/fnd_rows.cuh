@@ -792,7 +792,7 @@ struct FinParams {
   DevState* state;
   int update_step;              // 1: advance optimizer step and publish bias corrections
   int elect_last;               // 1: the last CTA to finish reduces all slots to the gradient norm (stand-alone launches);
-                                // 0: slots only — a later kernel reduces them
+                                // 0: slots only — the consumer (adamw_kernel / norm_finish_kernel) reduces them
 };
 
 // Global gradient norm from the per-CTA sum-of-squares slots: fixed order, double accumulation; every thread of the
@@ -814,38 +814,45 @@ __device__ __forceinline__ float clip_coef_of(float max_norm, float norm) {
   return (max_norm > 0.f) ? fminf(1.0f, max_norm / (norm + 1e-6f)) : 1.0f;
 }
 
-// Called by ONE full warp of the last CTA of a launch (elected through state->fin_counter): reduces the per-CTA
-// sum-of-squares slots to the global gradient norm in a fixed order (lane-strided partial sums in double, xor
-// butterfly), so the result does not depend on which CTA happened to finish last; publishes norm, clip coefficient,
-// optionally the mean loss and the optimizer-step bookkeeping, and re-arms the counter.
+// Sum of the per-CTA sum-of-squares slots by ONE full warp, in a fixed order (lane-strided 128-bit loads, eight in
+// flight per lane — a scalar dependent loop here cost ~10 us of L2 round trips, measured — then an xor butterfly in
+// double): every caller gets the bit-identical result. The slot buffer is zero beyond n (zeroed at bind, never
+// written), so whole float4s may be read.
+template <int kInflight = 8>
+__device__ __forceinline__ double warp_reduce_slots(const float* slots, int n) {
+  const int lane = threadIdx.x & 31;
+  double part = 0.0;
+  const int n4 = (n + 3) >> 2;
+#pragma unroll 1
+  for (int i0 = 0; i0 < n4; i0 += 32 * kInflight) {
+    float4 t[kInflight];
+#pragma unroll
+    for (int q = 0; q < kInflight; ++q) {
+      const int i = i0 + q * 32 + lane;
+      t[q] = i < n4 ? __ldcg(reinterpret_cast<const float4*>(slots) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int q = 0; q < kInflight; ++q)
+      part += (static_cast<double>(t[q].x) + static_cast<double>(t[q].y)) + (static_cast<double>(t[q].z) + static_cast<double>(t[q].w));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+  return part;
+}
+
+// Called by ONE full warp of the last CTA of a stand-alone finalize launch (elected through state->fin_counter):
+// publishes norm, clip coefficient, optionally the mean loss and the optimizer-step bookkeeping, re-arms the counter.
 __device__ __forceinline__ void warp_publish_norm(const FinParams& p) {
   const int lane = threadIdx.x & 31;
   __threadfence();
-  // 128-bit loads, eight in flight per lane: a scalar dependent loop here cost ~10 us of L2 round trips (measured).
-  // The slot buffer is zero beyond total_slots (zeroed at bind, never written), so whole float4s may be read.
-  double part = 0.0, lsum = 0.0;
-  const int n4 = (p.total_slots + 3) >> 2;
-#pragma unroll 1
-  for (int i0 = 0; i0 < n4; i0 += 256) {
-    float4 t[8];
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const int i = i0 + q * 32 + lane;
-      t[q] = i < n4 ? __ldcg(reinterpret_cast<const float4*>(p.slots) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-#pragma unroll
-    for (int q = 0; q < 8; ++q)
-      part += (static_cast<double>(t[q].x) + static_cast<double>(t[q].y)) + (static_cast<double>(t[q].z) + static_cast<double>(t[q].w));
-  }
+  const double part = warp_reduce_slots(p.slots, p.total_slots);
+  double lsum = 0.0;
   if (p.loss_row) {
 #pragma unroll 4
     for (int i = lane; i < p.B; i += 32) lsum += static_cast<double>(__ldcg(p.loss_row + i));
   }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    part += __shfl_xor_sync(0xffffffffu, part, o);
-    lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
-  }
+  for (int o = 16; o > 0; o >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
   if (lane == 0) {
     DevState* S = p.state;
     const float norm = static_cast<float>(sqrt(part));
