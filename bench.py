@@ -207,12 +207,17 @@ def run_b200_arm(args):
     fusion = CrossModalTransformer(precision=args.precision)
     clf = DeepTruthClassifier(precision=args.precision)
     fusion.train(); clf.train()
-    step = FusedStep(fusion, clf, B, precision=args.precision, use_graph=True)
+    # N > 1: identical replicas (rank 0's arena is broadcast), batch sharded by rank, and the optimizer step runs
+    # sharded over NVLink peer memory (csrc/fnd_dp.cuh). FND_DP=nccl selects the plain all-reduce + replicated AdamW
+    # path instead (kept as the comparison arm).
+    dp_mode = "single" if world == 1 else os.environ.get("FND_DP", "peer")
+    step = FusedStep(fusion, clf, B, precision=args.precision, use_graph=True,
+                     dp_group=dist.group.WORLD if dp_mode == "peer" else None)
     eng, plan, lib = step.engine, step.plan, step.engine.lib
     if world > 1:
-        # identical replicas: broadcast rank 0's arena, then rebuild the bf16 shadows
-        dist.broadcast(eng.params, src=0)
-        eng.refresh_shadows(eng.param_version())
+        if dp_mode != "peer":
+            dist.broadcast(eng.params, src=0)
+            eng.refresh_shadows(eng.param_version())
         check(lib.fnd_set_loss_scale(plan.handle, 1.0 / (B * world), eng.stream_ptr()), "fnd_set_loss_scale")
         eng.set_seed(eng.seed + rank)
 
@@ -230,6 +235,9 @@ def run_b200_arm(args):
         step.static_gather.copy_(idx_pool[i % pool], non_blocking=True)
         if world == 1:
             step.train_step(from_cache=True)
+        elif dp_mode == "peer":
+            step.train_fwd_bwd(from_cache=True)
+            step.dp_optimizer_step()
         else:
             step.train_fwd_bwd(from_cache=True)
             dist.all_reduce(eng.grads)
@@ -298,6 +306,9 @@ def run_b200_arm(args):
         stage_free[s].record(main)
         if world == 1:
             step.train_step(from_cache=False)
+        elif dp_mode == "peer":
+            step.train_fwd_bwd(from_cache=False)
+            step.dp_optimizer_step()
         else:
             step.train_fwd_bwd(from_cache=False)
             dist.all_reduce(eng.grads)
@@ -383,14 +394,14 @@ def run_b200_arm(args):
         cpu_baseline = {"value": n * B / dt, "unit": "samples/s", "cores": cores, "kind": "port",
                         "sample": f"{n} training steps at batch {B} in {dt:.1f} s (oracle/fnd_oracle.py on the host CPU)"}
 
-    launches_per_step = plan.launch_count("train_step") if world == 1 else plan.launch_count("train_fwd_bwd") + plan.launch_count("clip_adamw_step")
+    launches_per_step = plan.launch_count("train_step") if world == 1 else plan.launch_count("train_fwd_bwd") + 3
     line = {
         "metric": "train samples/sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16" if args.precision == "bf16" else "f32(bf16x3)", "data": "synthetic",
         "config": {"workload": f"fusion train step (fwd+CE+bwd+clip+AdamW), batch {B}/GPU, FakeSV-shaped synthetic features "
                                "(text 768, audio 128, visual 512, temporal 256, gnn 128, aux 2), random-init weights",
-                   "batch_per_gpu": B, "global_batch": B * world, "hidden": 512, "parallelism": f"dp{world}",
+                   "batch_per_gpu": B, "global_batch": B * world, "hidden": 512, "parallelism": f"dp{world}", "dp_optimizer": dp_mode,
                    "l2": "flushed between timed steps (256 MiB write); e2e leg un-flushed, per-step working set ~560 MB > 126 MB L2",
                    "cuda_graph": True, "final_loss": loss_after},
         "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,

@@ -129,6 +129,25 @@ int fnd_train_fwd_bwd(void* plan, const fnd_inputs* in, void* stream);
 int fnd_train_step(void* plan, const fnd_inputs* in, void* stream);
 int fnd_eval_step(void* plan, const fnd_inputs* in, void* stream);
 
+/* ---- data-parallel optimizer step over NVLink peer memory (batch-sharded replicas, one process per GPU) ----
+ * Replaces, for N ranks, "all-reduce the gradients, then clip_grad_norm_ + AdamW on every rank"
+ * (forensic_trainer.py:292-298 under a data-parallel wrapper): each rank reduces ITS 1/N slice of the gradient arena
+ * directly out of every peer's memory, the clip coefficient is formed from the N slice norms in rank order
+ * (bit-identical on all ranks), AdamW runs on the slice only (fp32 master / m / v stay sharded) and the refreshed
+ * bf16 operand shadows + the small fp32 parameters are stored into every rank's buffers.
+ * Every rank places params | grads | shadow_hi | shadow_lo | a 256-byte zeroed comm pad at the SAME byte offsets of
+ * one peer-mapped (symmetric) allocation; peer_bases[p] is rank p's base address as mapped into THIS process. The
+ * plan must already be bound (fnd_plan_bind) to this rank's slices. gred: local scratch of at least
+ * ceil(hot/world) rounded up to 1024 floats; slots: 1024 zeroed floats.
+ * fnd_dp_optimizer_step is stream-ordered and graph-capturable; every rank must call it once per fnd_train_fwd_bwd.
+ * After it, only the OWNER of a slice holds current fp32 master weights for it (fnd_dp_shard_range); gather the
+ * slices (e.g. one broadcast per rank) before reading a state_dict. */
+int fnd_dp_bind(void* plan, int rank, int world, const unsigned long long* peer_bases, long long off_params,
+                long long off_grads, long long off_shadow_hi, long long off_shadow_lo, long long off_pad, float* gred,
+                long long gred_elems, float* slots, long long slots_elems);
+int fnd_dp_shard_range(const void* plan, int rank, int world, long long* lo, long long* hi);
+int fnd_dp_optimizer_step(void* plan, void* stream);
+
 /* Per-kernel timing for benchmarks: between begin and end every kernel launch of this plan is followed by a
  * cudaEvent on `stream`; end synchronises and returns, per kernel name (64-byte slots in `names`), the summed
  * milliseconds between consecutive events. Not capturable; do not use around graph replays. */

@@ -1,0 +1,108 @@
+#!/usr/bin/env python3
+"""Multi-GPU parity of the peer-memory data-parallel step (csrc/fnd_dp.cuh). Run under torchrun, one rank per GPU:
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
+        tests/dp_peer_check.py [fp32|bf16]
+
+Every rank trains `STEPS` steps on its own slice of a global batch (dropout off) with train_fwd_bwd + dp_optimizer_step.
+Rank 0 then trains a SINGLE-GPU engine from the same initial weights on the whole global batch with fnd_train_step
+(the path the 1-GPU parity tests pin against the oracle) and compares: loss trajectory, gradient norm, and every
+parameter after the gather of the sharded master weights. Sums over ranks are taken in a different order than the
+single-GPU batch reduction, so agreement is to fp32 rounding, not bitwise."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch
+import torch.distributed as dist
+
+import bench
+from ultrafnd_git_b200.fused import FusedStep
+from ultrafnd_git_b200.modules import CrossModalTransformer, DeepTruthClassifier
+
+STEPS = 3
+B = 32
+
+
+def build(precision, seed=7):
+    torch.manual_seed(seed)
+    f, c = CrossModalTransformer(precision=precision), DeepTruthClassifier(precision=precision)
+    with torch.no_grad():      # exercise the NODE head (zero-init gates / leaves make its gradients trivially small)
+        g = torch.Generator().manual_seed(seed + 1)
+        for n, p in c.named_parameters():
+            if "gates" in n or "leaf_logits" in n:
+                p.add_(0.05 * torch.randn(p.shape, generator=g).to(p.device))
+    for m in list(f.modules()) + list(c.modules()):
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+    f.train(); c.train(); f._sync_dropout(); c._sync_dropout()
+    return f, c
+
+
+def main():
+    precision = sys.argv[1] if len(sys.argv) > 1 else "fp32"
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    use_graph = os.environ.get("FND_DP_GRAPH", "1") == "1"
+
+    f, c = build(precision)
+    step = FusedStep(f, c, B, precision=precision, use_graph=use_graph, dp_group=dist.group.WORLD)
+    eng, plan, lib = step.engine, step.plan, step.engine.lib
+    lib.fnd_set_loss_scale(plan.handle, 1.0 / (B * world), eng.stream_ptr())
+    init = eng.params.clone()
+    batches = [bench.synth_batch(B * world, 500 + s) for s in range(STEPS)]
+    losses, norms = [], []
+    for s in range(STEPS):
+        mine = {k: v[rank * B:(rank + 1) * B] for k, v in batches[s].items()}
+        step.load_batch({k: v.to(dev) for k, v in mine.items()})
+        step.train_fwd_bwd()
+        step.dp_optimizer_step()
+        st = plan.state()
+        t = torch.tensor([st["loss"]], device=dev, dtype=torch.float64)
+        dist.all_reduce(t)
+        losses.append(float(t.item())); norms.append(st["grad_norm"])
+    plan.check_error()
+    # bf16 shadows must be identical on every rank (they are what the next forward reads)
+    sh = eng.shadow_hi.view(torch.int16).to(torch.int64)
+    chk = torch.stack([sh.sum(), (sh * (torch.arange(sh.numel(), device=dev) % 8191)).sum()])
+    gathered = [torch.zeros_like(chk) for _ in range(world)]
+    dist.all_gather(gathered, chk)
+    assert all(torch.equal(g, gathered[0]) for g in gathered), f"shadow planes differ across ranks: {gathered}"
+    eng.gather_master()
+    dp_params = eng.params[:eng.n_hot].clone()
+    dist.barrier()
+    ok = True
+    if rank == 0:
+        f1, c1 = build(precision)
+        ref = FusedStep(f1, c1, B * world, precision=precision, use_graph=False)
+        ref.engine.params.copy_(init)
+        ref.engine.refresh_shadows(ref.engine.param_version())
+        rl, rn = [], []
+        for s in range(STEPS):
+            ref.load_batch({k: v.to(dev) for k, v in batches[s].items()})
+            ref.train_step()
+            st = ref.plan.state()
+            rl.append(st["loss"]); rn.append(st["grad_norm"])
+        ref.plan.check_error()
+        rp = ref.engine.params[:eng.n_hot]
+        tol = 2e-5 if precision == "fp32" else 2e-3
+        dl = max(abs(a - b) / abs(b) for a, b in zip(losses, rl))
+        dn = max(abs(a - b) / abs(b) for a, b in zip(norms, rn))
+        upd = (rp - init[:eng.n_hot]).abs().max().item()
+        dpar = (dp_params - rp).abs().max().item()
+        print(f"[dp_peer_check {precision} world={world} graph={use_graph}] losses {losses} vs {rl}; norms {norms} vs {rn}")
+        print(f"  max rel loss diff {dl:.2e}, norm diff {dn:.2e}; max |param diff| {dpar:.3e} (max update {upd:.3e})")
+        ok = dl < tol and dn < 10 * tol and dpar < 0.05 * upd + 1e-7
+        print("DP PEER CHECK", "OK" if ok else "FAILED")
+    flag = torch.tensor([1 if ok else 0], device=dev)
+    dist.broadcast(flag, src=0)
+    dist.destroy_process_group()
+    sys.exit(0 if int(flag.item()) else 1)
+
+
+if __name__ == "__main__":
+    main()

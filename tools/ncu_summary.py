@@ -18,7 +18,7 @@ import sys
 STEP_ORDER = ["prep", "gemm_proj", "gemm_qkv", "assemble_fwd", "gemm_fuse0", "gemm_fuse1", "gemm_pre0", "gemm_pre1", "head",
               "dgrad_pre1", "dgrad_pre0", "dgrad_fuse1", "dgrad_fuse0", "assemble_bwd", "dgrad_qkv", "wgrad_all", "adamw"]
 METRICS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
-           "dram__throughput.avg.pct_of_peak_sustained_elapsed",
+           "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
            "sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed",
            "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread",
            "lts__t_bytes.sum", "sm__throughput.avg.pct_of_peak_sustained_elapsed"]
@@ -27,11 +27,12 @@ UNIT_SCALE = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-3,
 
 def main():
     rep, out = sys.argv[1], sys.argv[2]
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv", "--metrics", ",".join(METRICS)],
-                         capture_output=True, text=True, check=True).stdout
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units, data = rows[0], rows[1], rows[2:]
     col = {h: i for i, h in enumerate(hdr)}
+    for h, i in list(col.items()):            # some metrics carry a section prefix ("TPC.TriageCompute.<metric>")
+        col.setdefault(h.split(".TriageCompute.")[-1], i)
 
     def val(r, name):
         if name not in col or r[col[name]] in ("", "n/a"):
@@ -59,7 +60,7 @@ def main():
         traffic.setdefault(n, []).append(rd + wr)
         out_rows.append([n, r[col["Kernel Name"]].split("(")[0], r[col["Grid Size"]], r[col["Block Size"]],
                          val(r, "gpu__time_duration.sum"), rd, wr,
-                         val(r, "dram__throughput.avg.pct_of_peak_sustained_elapsed"),
+                         val(r, "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"),
                          val(r, "sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed"),
                          val(r, "sm__warps_active.avg.pct_of_peak_sustained_active"),
                          val(r, "launch__registers_per_thread"), val(r, "lts__t_bytes.sum")])

@@ -789,6 +789,70 @@ int fnd_train_step(void* plan, const fnd_inputs* in, void* stream) {
   return 0;
 }
 
+// ------------------------------- data-parallel optimizer step over peer memory -------------------------------
+int fnd_dp_bind(void* plan, int rank, int world, const unsigned long long* peer_bases, long long off_params,
+                long long off_grads, long long off_shadow_hi, long long off_shadow_lo, long long off_pad, float* gred,
+                long long gred_elems, float* slots, long long slots_elems) {
+  Plan* PP = as_plan(plan);
+  if (!PP || !PP->bound) return -5;
+  Plan& P = *PP;
+  if (!peer_bases || !gred || !slots || world < 1 || world > kDpMaxWorld || rank < 0 || rank >= world) return -1;
+  if (!P.m || !P.v) return -6;
+  DpParams d;
+  memset(&d, 0, sizeof(d));
+  d.rank = rank; d.world = world;
+  for (int p = 0; p < world; ++p) {
+    uint8_t* base = reinterpret_cast<uint8_t*>(static_cast<uintptr_t>(peer_bases[p]));
+    if (!base) return -2;
+    d.params[p] = reinterpret_cast<float*>(base + off_params);
+    d.grads[p] = reinterpret_cast<const float*>(base + off_grads);
+    d.sh_hi[p] = reinterpret_cast<__nv_bfloat16*>(base + off_shadow_hi);
+    d.sh_lo[p] = P.sh_lo ? reinterpret_cast<__nv_bfloat16*>(base + off_shadow_lo) : nullptr;
+    d.pad[p] = reinterpret_cast<unsigned int*>(base + off_pad);
+  }
+  // the plan must already be bound to THIS rank's slices of the symmetric buffer
+  if (d.params[rank] != P.params || d.grads[rank] != P.grads || d.sh_hi[rank] != P.sh_hi || (P.sh_lo && d.sh_lo[rank] != P.sh_lo))
+    return -3;
+  const size_t n = static_cast<size_t>(P.L.n_hot);
+  size_t per = (n + world - 1) / world;
+  per = (per + 1023) / 1024 * 1024;
+  d.shard_lo = per * rank < n ? per * rank : n;
+  d.shard_hi = d.shard_lo + per < n ? d.shard_lo + per : n;
+  if (gred_elems < static_cast<long long>(per) || slots_elems < 1024) return -4;
+  d.gred = gred; d.slots = slots;
+  d.a = adamw_params(P);
+  P.dp = d;
+  P.dp_bound = true;
+  return 0;
+}
+
+int fnd_dp_shard_range(const void* plan, int rank, int world, long long* lo, long long* hi) {
+  if (!plan || !lo || !hi || world < 1 || rank < 0 || rank >= world) return -1;
+  const Plan* P = static_cast<const Plan*>(plan);
+  const size_t n = static_cast<size_t>(P->L.n_hot);
+  size_t per = (n + world - 1) / world;
+  per = (per + 1023) / 1024 * 1024;
+  const size_t l = per * rank < n ? per * rank : n;
+  *lo = static_cast<long long>(l);
+  *hi = static_cast<long long>(l + per < n ? l + per : n);
+  return 0;
+}
+
+int fnd_dp_optimizer_step(void* plan, void* stream) {
+  FND_PLAN(plan);
+  if (!P.dp_bound) return -7;
+  P.dp.a = adamw_params(P);
+  // ordinary (non-PDL) launches: these kernels spin on remote flags and must not become resident early
+  const int grid = 148 * 4;
+  FND_CUDA_OK(launch_k(dp_reduce_kernel, grid, 256, 0, st, false, P.dp));
+  mark(P, "dp_reduce", st);
+  FND_CUDA_OK(launch_k(dp_adamw_kernel, grid, 256, 0, st, false, P.dp));
+  mark(P, "dp_adamw", st);
+  FND_CUDA_OK(launch_k(dp_wait_kernel, 1, 32, 0, st, false, P.dp));
+  mark(P, "dp_wait", st);
+  return 0;
+}
+
 int fnd_eval_step(void* plan, const fnd_inputs* in, void* stream) {
   FND_PLAN(plan);
   if (!in) return -1;

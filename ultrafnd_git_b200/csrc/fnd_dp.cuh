@@ -1,0 +1,256 @@
+// fnd_dp.cuh — data-parallel optimizer step over NVLink peer memory (one process per GPU, batch-sharded replicas).
+//
+// The reference trains on one device (src/training/forensic_trainer.py:285-298); its clip_grad_norm_ + AdamW pair is
+// what this file replaces when the batch is sharded over N GPUs. Instead of "NCCL all-reduce of the 51 MB fp32 gradient,
+// then N identical AdamW passes over 357 MB each", the gradient exchange, the clip and the optimizer are ONE sharded
+// sequence over symmetric (peer-mapped) buffers:
+//
+//   dp_reduce_kernel   rank r sums ITS 1/N slice of the gradient arena straight out of every peer's memory (128-bit
+//                      P2P loads over NVLink/NVSwitch — a reduce-scatter without a staging copy), keeps the reduced
+//                      slice locally and publishes the slice's sum of squares to every peer;
+//   dp_adamw_kernel    every rank adds the N partial sums in rank order (bit-identical clip coefficient everywhere),
+//                      runs AdamW on its slice only (1/N of the 357 MB optimizer stream; fp32 master, m and v stay
+//                      sharded, ZeRO-1 style) and writes the refreshed bf16 operand shadows — the only copy of the
+//                      weights the forward/backward kernels read — plus the small fp32 parameters (biases, gates, ...)
+//                      into EVERY rank's buffers with P2P stores (the all-gather);
+//   dp_wait_kernel     blocks the stream until every peer's shadow writes have landed here.
+//
+// Cross-GPU ordering uses epoch flags in each rank's symmetric comm pad (st.release.sys / ld.acquire.sys): a flag
+// holds the number of the last step for which the event happened, so nothing is ever reset and a captured CUDA graph
+// can be replayed. All three kernels are ordinary stream-ordered launches; they only ever wait for events that peers
+// produce without needing anything further from this rank, so the sequence cannot deadlock as long as every rank
+// runs the same steps.
+#pragma once
+#include "fnd_optim.cuh"
+
+namespace fnd {
+
+constexpr int kDpMaxWorld = 8;
+// comm pad layout (uint32 words): [0,8) grads-ready epochs | [8,16) partial-ready | [16,24) shadows-written |
+// [24,32) float partial sums of squares | [32] local epoch counter | [33] local CTA counter
+constexpr int kPadGradsReady = 0, kPadPartialReady = 8, kPadDone = 16, kPadPartial = 24, kPadEpoch = 32, kPadCounter = 33;
+constexpr int kPadWords = 64;
+
+struct DpParams {
+  int rank, world;
+  const float* grads[kDpMaxWorld];        // gradient arena of every rank (peer-mapped)
+  float* params[kDpMaxWorld];             // fp32 parameter arena of every rank
+  __nv_bfloat16* sh_hi[kDpMaxWorld];      // bf16 operand shadows of every rank
+  __nv_bfloat16* sh_lo[kDpMaxWorld];      // residual planes (fp32x3 mode) or null
+  unsigned int* pad[kDpMaxWorld];         // comm pad of every rank
+  float* gred;                            // local: reduced gradient slice [shard_hi - shard_lo]
+  float* slots;                           // local: per-CTA sums of squares of dp_reduce_kernel
+  size_t shard_lo, shard_hi;              // this rank's slice of [0, n_hot), multiples of 4
+  AdamWParams a;                          // local p / m / v / state, shadow geometry
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ float4 ld_peer_f4(const float* p) {
+  float4 v;
+  asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+}
+// Spin until pad[base + p] >= epoch for every rank p (threads p < world of the calling warp), bounded like mbar_wait.
+__device__ __forceinline__ void dp_wait_all(const unsigned int* pad, int base, int world, unsigned int epoch, int* err) {
+  if (threadIdx.x < static_cast<unsigned>(world)) {
+    long long t0 = 0;
+    for (unsigned int spins = 1;; ++spins) {
+      // epochs only grow; the signed difference tolerates wrap-around
+      if (static_cast<int>(ld_acquire_sys(pad + base + threadIdx.x) - epoch) >= 0) break;
+      if ((spins & 63u) == 0u) {
+        const long long now = clock64();
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > 20000000000ll) {       // ~10 s: a peer died or ran a different sequence
+          if (err) atomicExch(err, 201);
+          break;
+        }
+      }
+    }
+  }
+  __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// 1. reduce-scatter out of peer memory + slice norm
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) dp_reduce_kernel(DpParams d) {
+  __shared__ float red[8];
+  __shared__ int is_last;
+  unsigned int* mypad = d.pad[d.rank];
+  const unsigned int epoch = mypad[kPadEpoch] + 1u;
+  // my gradients are complete (stream order: the backward kernels precede this launch): tell every peer
+  if (blockIdx.x == 0 && threadIdx.x < static_cast<unsigned>(d.world)) {
+    __threadfence_system();
+    st_release_sys(d.pad[threadIdx.x] + kPadGradsReady + d.rank, epoch);
+  }
+  dp_wait_all(mypad, kPadGradsReady, d.world, epoch, &d.a.state->err);
+
+  float ss = 0.f;
+  const size_t n4 = (d.shard_hi - d.shard_lo) >> 2;
+  for (size_t i4 = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i4 < n4;
+       i4 += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t i = d.shard_lo + i4 * 4;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 t[kDpMaxWorld];
+#pragma unroll
+    for (int p = 0; p < kDpMaxWorld; ++p)
+      if (p < d.world) t[p] = ld_peer_f4(d.grads[p] + i);           // all peers in flight, summed in rank order
+#pragma unroll
+    for (int p = 0; p < kDpMaxWorld; ++p)
+      if (p < d.world) { acc.x += t[p].x; acc.y += t[p].y; acc.z += t[p].z; acc.w += t[p].w; }
+    *reinterpret_cast<float4*>(d.gred + i4 * 4) = acc;
+    ss += (acc.x * acc.x + acc.y * acc.y) + (acc.z * acc.z + acc.w * acc.w);
+  }
+  ss = warp_sum(ss);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tot = 0.f;
+    for (int w = 0; w < 8; ++w) tot += red[w];
+    d.slots[blockIdx.x] = tot;
+    __threadfence();
+    is_last = (atomicAdd(mypad + kPadCounter, 1u) == gridDim.x - 1) ? 1 : 0;
+  }
+  __syncthreads();
+  if (!is_last) return;
+  // last CTA: this rank's partial sum of squares (fixed order) -> every peer
+  if (threadIdx.x < 32) {
+    __threadfence();
+    const double part = warp_reduce_slots(d.slots, static_cast<int>(gridDim.x));
+    if (threadIdx.x == 0) mypad[kPadCounter] = 0u;
+    if (threadIdx.x < static_cast<unsigned>(d.world)) {
+      reinterpret_cast<float*>(d.pad[threadIdx.x])[kPadPartial + d.rank] = static_cast<float>(part);
+      __threadfence_system();
+      st_release_sys(d.pad[threadIdx.x] + kPadPartialReady + d.rank, epoch);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// 2. clip + AdamW on the slice, shadows / small parameters written to every rank
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void dp_publish4(const DpParams& d, size_t i, const float4& x) {
+  const AdamWParams& a = d.a;
+  if (i < a.n_shadow) {
+    // bf16 operand copy (hi [, lo]) of a GEMM weight -> all ranks
+    const uint32_t h0 = pack_bf16x2(x.x, x.y), h1 = pack_bf16x2(x.z, x.w);
+    uint32_t l0 = 0, l1 = 0;
+    if (a.sh_lo) {
+      const __nv_bfloat162 a2 = *reinterpret_cast<const __nv_bfloat162*>(&h0), b2 = *reinterpret_cast<const __nv_bfloat162*>(&h1);
+      l0 = pack_bf16x2(x.x - __low2float(a2), x.y - __high2float(a2));
+      l1 = pack_bf16x2(x.z - __low2float(b2), x.w - __high2float(b2));
+    }
+#pragma unroll
+    for (int p = 0; p < kDpMaxWorld; ++p) {
+      if (p < d.world) {
+        *reinterpret_cast<uint2*>(d.sh_hi[p] + i) = make_uint2(h0, h1);
+        if (a.sh_lo) *reinterpret_cast<uint2*>(d.sh_lo[p] + i) = make_uint2(l0, l1);
+      }
+    }
+  } else {
+    // small fp32 parameters (biases, gates, thresholds, leaf tables, evidence MLPs) are read as fp32 by the kernels
+#pragma unroll
+    for (int p = 0; p < kDpMaxWorld; ++p)
+      if (p < d.world && p != d.rank) *reinterpret_cast<float4*>(d.params[p] + i) = x;
+  }
+  if (i + 4 > a.rp_begin && i < a.rp_end) {
+    // re-pitched pre.0.weight shadow (+ its fp32 aux columns, which the epilogue reads from the arena)
+    const float xs[4] = {x.x, x.y, x.z, x.w};
+    const size_t rp_off = static_cast<size_t>(a.rp_hi - a.sh_hi);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const size_t e = i + q;
+      if (e >= a.rp_begin && e < a.rp_end) {
+        const size_t r = (e - a.rp_begin) / a.rp_cols, c = (e - a.rp_begin) % a.rp_cols;
+        __nv_bfloat16 h, l;
+        split_bf16(xs[q], h, l);
+        for (int p = 0; p < d.world; ++p) {
+          d.sh_hi[p][rp_off + r * a.rp_pitch + c] = h;
+          if (a.sh_lo) d.sh_lo[p][rp_off + r * a.rp_pitch + c] = l;
+          if (c >= static_cast<size_t>(a.rp_cols - 2) && p != d.rank) d.params[p][e] = xs[q];
+        }
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) dp_adamw_kernel(DpParams d) {
+  __shared__ float s_norm;
+  __shared__ int is_last;
+  unsigned int* mypad = d.pad[d.rank];
+  const unsigned int epoch = mypad[kPadEpoch] + 1u;
+  DevState* S = d.a.state;
+  dp_wait_all(mypad, kPadPartialReady, d.world, epoch, &S->err);
+  if (threadIdx.x == 0) {
+    double tot = 0.0;
+    for (int p = 0; p < d.world; ++p) tot += static_cast<double>(reinterpret_cast<volatile float*>(mypad)[kPadPartial + p]);
+    s_norm = static_cast<float>(sqrt(tot));
+  }
+  __syncthreads();
+  const float norm = s_norm;
+  const float coef = clip_coef_of(S->max_norm, norm);
+  const float lr = S->lr, b1 = S->beta1, b2 = S->beta2, eps = S->eps;
+  const int t = S->step + 1;
+  const float bc1 = 1.0f - powf(b1, static_cast<float>(t)), bc2 = 1.0f - powf(b2, static_cast<float>(t));
+  const float decay = 1.0f - lr * S->weight_decay;
+  const float step_size = lr / bc1;
+  const float inv_sqrt_bc2 = rsqrtf(bc2);
+  const AdamWParams& a = d.a;
+  const uint64_t pol = l2_policy_evict_first();
+  const size_t n4 = (d.shard_hi - d.shard_lo) >> 2;
+  for (size_t i4 = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i4 < n4;
+       i4 += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t i = d.shard_lo + i4 * 4;
+    float4 p = ld_f4_policy(a.p + i, pol);
+    const float4 g4 = *reinterpret_cast<const float4*>(d.gred + i4 * 4);
+    float4 m = ld_f4_policy(a.m + i, pol);
+    float4 v = ld_f4_policy(a.v + i, pol);
+    float* pp = &p.x; float* mp = &m.x; float* vp = &v.x; const float* gp = &g4.x;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float g = gp[q] * coef;
+      pp[q] *= decay;
+      mp[q] = b1 * mp[q] + (1.0f - b1) * g;
+      vp[q] = b2 * vp[q] + (1.0f - b2) * g * g;
+      const float denom = sqrtf(vp[q]) * inv_sqrt_bc2 + eps;
+      pp[q] -= step_size * (mp[q] / denom);
+    }
+    st_f4_policy(a.p + i, p, pol);
+    st_f4_policy(a.m + i, m, pol);
+    st_f4_policy(a.v + i, v, pol);
+    dp_publish4(d, i, p);
+  }
+  // every P2P store of this CTA is ordered before its counter bump; the last CTA tells the peers
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = (atomicAdd(mypad + kPadCounter, 1u) == gridDim.x - 1) ? 1 : 0;
+  __syncthreads();
+  if (!is_last) return;
+  if (threadIdx.x == 0) {
+    S->grad_norm = norm; S->clip_coef = coef; S->step = t; S->bc1 = bc1; S->bc2 = bc2;
+    mypad[kPadCounter] = 0u;
+  }
+  if (threadIdx.x < static_cast<unsigned>(d.world)) {
+    __threadfence_system();
+    st_release_sys(d.pad[threadIdx.x] + kPadDone + d.rank, epoch);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// 3. wait for every peer's shadow / parameter writes, then advance the local epoch
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32) dp_wait_kernel(DpParams d) {
+  unsigned int* mypad = d.pad[d.rank];
+  const unsigned int epoch = mypad[kPadEpoch] + 1u;
+  dp_wait_all(mypad, kPadDone, d.world, epoch, &d.a.state->err);
+  if (threadIdx.x == 0) mypad[kPadEpoch] = epoch;
+}
+
+}  // namespace fnd

@@ -9,6 +9,7 @@
 #include "../../include/fnd_b200.h"
 #include "fnd_gemm_host.h"
 #include "fnd_optim.cuh"
+#include "fnd_dp.cuh"
 #include <cstdlib>
 #include <map>
 #include <string>
@@ -204,6 +205,8 @@ struct Plan {
   int dbg_launch = 0;            // probe builds: index of the next launch's stamp region
   bool pdl_next = false;         // the next launch may carry the programmatic-serialization attribute
   int launch_limit = -1, launch_seq = 0;   // debug: issue only the first `launch_limit` launches of an entry point
+  bool dp_bound = false;         // fnd_dp_bind succeeded: dp holds the peer-mapped buffers of every rank
+  DpParams dp;
   bool profiling = false;
   std::vector<std::pair<const char*, cudaEvent_t>> marks;
 

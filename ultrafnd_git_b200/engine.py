@@ -219,6 +219,7 @@ class Engine:
         self.seed = 0x5EED5EED
         self._shadow_version: Optional[int] = None
         self.attached: list = []          # weakrefs to the nn.Modules whose parameters live in this arena
+        self.symm: Optional[dict] = None  # peer-mapped buffers of the data-parallel optimizer step (enable_symmetric)
         self._alloc_device_buffers()
 
     def param_version(self) -> int:
@@ -247,6 +248,85 @@ class Engine:
             self.adam_v = torch.zeros(self.n_hot, dtype=torch.float32, device=self.device)
             for p in self.plans.values():
                 p.bind()
+
+    # ---------------------------------------------------------------- data parallel over peer memory
+    def enable_symmetric(self, group=None) -> None:
+        """Move params / grads / bf16 shadows into ONE peer-mapped (symmetric) allocation shared with the other ranks
+        of ``group`` and bind the sharded optimizer step (csrc/fnd_dp.cuh). torch.distributed's symmetric-memory
+        allocator is plumbing here: it hands out the CUDA VMM mapping of every peer's buffer; all data movement is done
+        by this library's kernels. Call once, after the modules are attached and before any plan is used for training.
+        Raises if peer mapping is unavailable — callers that want an all-reduce path must choose it explicitly."""
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        self.require_cuda()
+        self.enable_optimizer()
+        group = group if group is not None else dist.group.WORLD
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        if world > 8:
+            raise NotImplementedError("the peer-memory optimizer step supports up to 8 ranks (one NVSwitch domain)")
+
+        def up(x):
+            return (x + 255) // 256 * 256
+        off_p = 0
+        off_g = up(off_p + 4 * self.n_total)
+        off_h = up(off_g + 4 * self.n_hot)
+        off_l = up(off_h + 2 * self.n_shadow_buf)
+        off_pad = up(off_l + (2 * self.n_shadow_buf if self.mode == MODE_FP32X3 else 0))
+        total = off_pad + 256
+        buf = symm.empty(total, dtype=torch.uint8, device=self.device)
+        buf.zero_()
+        hdl = symm.rendezvous(buf, group)
+        new_p = buf[off_p: off_p + 4 * self.n_total].view(torch.float32)
+        new_g = buf[off_g: off_g + 4 * self.n_hot].view(torch.float32)
+        new_h = buf[off_h: off_h + 2 * self.n_shadow_buf].view(torch.bfloat16)
+        new_l = buf[off_l: off_l + 2 * self.n_shadow_buf].view(torch.bfloat16) if self.mode == MODE_FP32X3 else None
+        new_p.copy_(self.params)
+        new_h.copy_(self.shadow_hi)
+        if new_l is not None:
+            new_l.copy_(self.shadow_lo)
+        self.params, self.grads, self.shadow_hi, self.shadow_lo = new_p, new_g, new_h, new_l
+        with torch.no_grad():
+            for ref in self.attached:
+                m = ref()
+                if m is not None and getattr(m, "_engine", None) is self:
+                    for name, p in m.named_parameters():
+                        p.data = self.view(m._prefix + name)
+        self.plans.clear()
+        self._shadow_version = None
+        per = ((self.n_hot + world - 1) // world + 1023) // 1024 * 1024
+        self.symm = {"buf": buf, "handle": hdl, "rank": rank, "world": world, "group": group,
+                     "offsets": (off_p, off_g, off_h, off_l, off_pad),
+                     "peer_bases": [int(x) for x in hdl.buffer_ptrs],
+                     "gred": torch.zeros(per, dtype=torch.float32, device=self.device),
+                     "slots": torch.zeros(1024, dtype=torch.float32, device=self.device)}
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group)          # every rank's pad is zeroed and mapped before anyone signals
+
+    def dp_bind(self, plan: "Plan") -> None:
+        s = self.symm
+        bases = (ctypes.c_ulonglong * s["world"])(*s["peer_bases"])
+        off_p, off_g, off_h, off_l, off_pad = s["offsets"]
+        check(self.lib.fnd_dp_bind(plan.handle, s["rank"], s["world"], bases, off_p, off_g, off_h, off_l, off_pad,
+                                   s["gred"].data_ptr(), s["gred"].numel(), s["slots"].data_ptr(), s["slots"].numel()),
+              "fnd_dp_bind")
+
+    def shard_range(self, rank: int) -> Tuple[int, int]:
+        lo, hi = ctypes.c_longlong(), ctypes.c_longlong()
+        check(self.lib.fnd_dp_shard_range(self.any_plan().handle, rank, self.symm["world"], ctypes.byref(lo), ctypes.byref(hi)),
+              "fnd_dp_shard_range")
+        return lo.value, hi.value
+
+    def gather_master(self) -> None:
+        """After sharded optimizer steps only the owner of a slice holds current fp32 master weights: broadcast every
+        slice from its owner so that ``state_dict()`` / checkpoints see the full model on every rank."""
+        import torch.distributed as dist
+        s = getattr(self, "symm", None)
+        if s is None:
+            return
+        for r in range(s["world"]):
+            lo, hi = self.shard_range(r)
+            if hi > lo:
+                dist.broadcast(self.params[lo:hi], src=dist.get_global_rank(s["group"], r), group=s["group"])
 
     def view(self, name: str) -> torch.Tensor:
         p = self.index[name]

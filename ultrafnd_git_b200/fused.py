@@ -59,11 +59,17 @@ class FusedStep:
     """Runs fnd_train_step / fnd_eval_step for a (fusion, classifier) pair at a fixed batch size."""
 
     def __init__(self, fusion: CrossModalTransformer, clf: DeepTruthClassifier, batch: int,
-                 precision: Optional[str] = None, use_graph: bool = True):
+                 precision: Optional[str] = None, use_graph: bool = True, dp_group=None):
+        """dp_group: a torch.distributed process group (one rank per GPU of one NVSwitch domain). When given, rank 0's
+        parameters are broadcast, the arena moves into peer-mapped memory and ``dp_optimizer_step`` becomes available."""
         self.fusion, self.clf = fusion, clf
         self.engine = pair_modules(fusion, clf, precision)
         self.engine.require_cuda()
         self.engine.enable_optimizer()
+        if dp_group is not None and self.engine.symm is None:
+            import torch.distributed as dist
+            dist.broadcast(self.engine.params, src=dist.get_global_rank(dp_group, 0), group=dp_group)
+            self.engine.enable_symmetric(dp_group)
         self.batch = batch
         self.plan = self.engine.plan(batch)
         self.use_graph = use_graph
@@ -165,6 +171,24 @@ class FusedStep:
         """Forward + loss + backward only (gradients left in the arena for an all-reduce)."""
         self._launch("train_fwd_bwd", from_cache)
         self.plan.forward_id += 1
+
+    def dp_optimizer_step(self) -> None:
+        """Sharded clip + AdamW over NVLink peer memory (Engine.enable_symmetric must have been called): the gradients
+        left by train_fwd_bwd on every rank are reduce-scattered, the slice is updated and the bf16 shadows are written
+        to all ranks. Replayed from a CUDA graph together with nothing else (the kernels spin on peer flags)."""
+        if not getattr(self, "_dp_bound", False):
+            self.engine.dp_bind(self.plan)
+            self._dp_bound = True
+        if not self.use_graph:
+            check(self.engine.lib.fnd_dp_optimizer_step(self.plan.handle, self.engine.stream_ptr()), "fnd_dp_optimizer_step")
+            return
+        g = self._graphs.get("dp_opt")
+        if g is None:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                check(self.engine.lib.fnd_dp_optimizer_step(self.plan.handle, self.engine.stream_ptr()), "fnd_dp_optimizer_step")
+            self._graphs["dp_opt"] = g
+        g.replay()
 
     def optimizer_step(self, norm_from_slots: bool = False) -> None:
         check(self.engine.lib.fnd_clip_adamw_step(self.plan.handle, int(norm_from_slots), self.engine.stream_ptr()),
