@@ -236,8 +236,7 @@ def run_b200_arm(args):
         if world == 1:
             step.train_step(from_cache=True)
         elif dp_mode == "peer":
-            step.train_fwd_bwd(from_cache=True)
-            step.dp_optimizer_step()
+            step.train_step_dp(from_cache=True)
         else:
             step.train_fwd_bwd(from_cache=True)
             dist.all_reduce(eng.grads)
@@ -307,8 +306,7 @@ def run_b200_arm(args):
         if world == 1:
             step.train_step(from_cache=False)
         elif dp_mode == "peer":
-            step.train_fwd_bwd(from_cache=False)
-            step.dp_optimizer_step()
+            step.train_step_dp(from_cache=False)
         else:
             step.train_fwd_bwd(from_cache=False)
             dist.all_reduce(eng.grads)

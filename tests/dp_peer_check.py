@@ -59,8 +59,11 @@ def main():
     for s in range(STEPS):
         mine = {k: v[rank * B:(rank + 1) * B] for k, v in batches[s].items()}
         step.load_batch({k: v.to(dev) for k, v in mine.items()})
-        step.train_fwd_bwd()
-        step.dp_optimizer_step()
+        if s % 2 == 0:
+            step.train_step_dp()                 # one graph per rank
+        else:
+            step.train_fwd_bwd()                 # the two halves as separate calls
+            step.dp_optimizer_step()
         st = plan.state()
         t = torch.tensor([st["loss"]], device=dev, dtype=torch.float64)
         dist.all_reduce(t)
@@ -94,9 +97,18 @@ def main():
         dn = max(abs(a - b) / abs(b) for a, b in zip(norms, rn))
         upd = (rp - init[:eng.n_hot]).abs().max().item()
         dpar = (dp_params - rp).abs().max().item()
+        # Adam's first steps move every element by ~lr * g/(|g| + eps): elements whose gradient is ~eps are sensitive
+        # to the summation order of the per-rank partial gradients, so the bf16 criterion is the relative L2 error of the
+        # whole update and the fraction of outliers; fp32 mode is also held to a max-norm bound.
+        rel_l2 = ((dp_params - rp).double().norm() / (rp - init[:eng.n_hot]).double().norm()).item()
+        outliers = ((dp_params - rp).abs() > 0.1 * upd).double().mean().item()
         print(f"[dp_peer_check {precision} world={world} graph={use_graph}] losses {losses} vs {rl}; norms {norms} vs {rn}")
-        print(f"  max rel loss diff {dl:.2e}, norm diff {dn:.2e}; max |param diff| {dpar:.3e} (max update {upd:.3e})")
-        ok = dl < tol and dn < 10 * tol and dpar < 0.05 * upd + 1e-7
+        print(f"  max rel loss diff {dl:.2e}, norm diff {dn:.2e}; max |param diff| {dpar:.3e} (max update {upd:.3e}); "
+              f"update rel-L2 err {rel_l2:.2e}; outlier fraction {outliers:.2e}")
+        if precision == "fp32":
+            ok = dl < tol and dn < 10 * tol and dpar < 0.05 * upd + 1e-7 and rel_l2 < 1e-3
+        else:
+            ok = dl < tol and dn < 10 * tol and rel_l2 < 2e-2 and outliers < 1e-3
         print("DP PEER CHECK", "OK" if ok else "FAILED")
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.broadcast(flag, src=0)

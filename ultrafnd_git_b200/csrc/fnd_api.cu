@@ -177,6 +177,24 @@ static int build_tables(Plan& P) {
     }
     return 0;
   };
+  {
+    // data-parallel overlap: fuse_mlp.0 alone, and everything else
+    P.wg_f0.kind = 2;
+    FND_OK(wg(P.wg_f0, tb.act("dz_f0", 0, 2 * H, true), tb.act("fused_cat", 0, catw, true), 2 * H, catw,
+              P.G("fusion.fuse_mlp.0.weight"), catw));
+    GemmTable& T = P.wg_rest;
+    T.kind = 2;
+    FND_OK(wg(T, tb.act("dz_p1", 0, H, true), tb.act("xp1", 0, H, true), H, H, P.G("clf.pre.3.weight"), H));
+    FND_OK(wg(T, tb.act("dz_p0", 0, H, true), tb.act("fusedbf", 0, H, true), H, H, P.G("clf.pre.0.weight"), p0w));
+    FND_OK(wg(T, tb.act("dFbf", 0, kDFCols, true), tb.act("hbf", 0, H, true), P.TD + 2, H, P.buf<float>("dAraw"), H));
+    FND_OK(wg(T, tb.act("dz_f1", 0, H, true), tb.act("h1", 0, 2 * H, true), H, 2 * H, P.G("fusion.fuse_mlp.3.weight"), 2 * H));
+    for (int g = 0; g < 4; ++g)
+      FND_OK(wg(T, tb.act("dQ", qg[g].q_col, 9 * H, true), tb.act("pbf", qg[g].in_col, 5 * H, true), qg[g].n, H,
+                P.G(std::string(qg[g].first) + ".weight"), H));
+    for (int i = 0; i < P.nmod; ++i)
+      FND_OK(wg(T, tb.act("dP", i * H, 5 * H, true), tb.act("xbf", P.xoff[i], P.dsum, true), H, P.xdim[i],
+                P.G(std::string("fusion.") + pn[i] + ".weight"), P.xdim[i]));
+  }
   FND_OK(build_wg(P.wg_all, true, true));
   FND_OK(build_wg(P.wg_clf, true, false));
   FND_OK(build_wg(P.wg_fus, false, true));
@@ -238,7 +256,7 @@ static int build_tables(Plan& P) {
 
   // ---------------- finish: CTA prefixes, slots, upload ----------------
   GemmTable* all[] = {&P.fwd_proj, &P.fwd_qkv, &P.fwd_f0, &P.fwd_f1, &P.fwd_p0, &P.fwd_p1, &P.dg_p1, &P.dg_p0_fused,
-                      &P.dg_p0_split, &P.dg_f1, &P.dg_f0, &P.dg_qkv, &P.wg_all, &P.wg_clf, &P.wg_fus};
+                      &P.dg_p0_split, &P.dg_f1, &P.dg_f0, &P.dg_qkv, &P.wg_all, &P.wg_clf, &P.wg_fus, &P.wg_f0, &P.wg_rest};
   for (GemmTable* T : all) T->grid = finish_table(T->host.data(), static_cast<int>(T->host.size()));
   // gradient-norm slots: fused-step wgrad CTAs first (the dAraw problem writes none: its slots stay 0)
   float* slots = P.buf<float>("slots");
@@ -572,7 +590,7 @@ int fnd_plan_bind(void* plan, void* workspace, float* params, float* grads, floa
   P.sh_lo = P.ncombo == 3 ? static_cast<__nv_bfloat16*>(shadow_lo) : nullptr;
   FND_CUDA_OK(cudaMemsetAsync(P.ws, 0, static_cast<size_t>(P.ws_bytes), st));
   GemmTable* all[] = {&P.fwd_proj, &P.fwd_qkv, &P.fwd_f0, &P.fwd_f1, &P.fwd_p0, &P.fwd_p1, &P.dg_p1, &P.dg_p0_fused,
-                      &P.dg_p0_split, &P.dg_f1, &P.dg_f0, &P.dg_qkv, &P.wg_all, &P.wg_clf, &P.wg_fus};
+                      &P.dg_p0_split, &P.dg_f1, &P.dg_f0, &P.dg_qkv, &P.wg_all, &P.wg_clf, &P.wg_fus, &P.wg_f0, &P.wg_rest};
   for (GemmTable* T : all) T->host.clear();
   P.fin_all.host.clear(); P.fin_clf.host.clear(); P.fin_fus.host.clear();
   FND_OK(build_tables(P));
@@ -742,9 +760,16 @@ int fnd_clip_adamw_step(void* plan, int norm_from_slots, void* stream) {
 }
 
 // ------------------------------- fused trainer step -------------------------------
-static int train_fwd_bwd_impl(void* plan, const fnd_inputs* in, int fused_optimizer, void* stream) {
+// data-parallel tail (defined with the other fnd_dp_* entry points below). Its kernels are ordinary (non-PDL) launches:
+// they spin on remote flags and must not become resident early.
+static const int kDpGrid = 148 * 4;
+static int dp_tail(Plan& P, bool early_done, cudaStream_t st);
+
+static int train_fwd_bwd_impl(void* plan, const fnd_inputs* in, int fused_optimizer, void* stream, void* side_stream = nullptr) {
   FND_PLAN(plan);
   if (!in || !in->labels) return -1;
+  cudaStream_t side = reinterpret_cast<cudaStream_t>(side_stream);
+  const bool overlap = side_stream != nullptr && P.dp_bound;
   FND_OK(fusion_forward_impl(P, in, 1, true, st));
   FND_OK(classifier_gemms_impl(P, 1, st));
   HeadParams h = head_params(P, 1);
@@ -752,9 +777,27 @@ static int train_fwd_bwd_impl(void* plan, const fnd_inputs* in, int fused_optimi
   FND_OK(run_gemm(P, P.dg_p1, 1, st, "dgrad_pre1"));
   FND_OK(run_gemm(P, P.dg_p0_fused, 1, st, "dgrad_pre0"));
   FND_OK(run_gemm(P, P.dg_f1, 1, st, "dgrad_fuse1"));
+  if (overlap) {
+    // Data-parallel step with overlap: the fuse_mlp.0 weight gradient (65 % of all gradient bytes) needs only dz_f0
+    // and fused_cat, so it is produced NOW and its cross-rank reduction runs on the side stream under the rest of
+    // the backward pass (fork / join through two events; capturable).
+    FND_OK(run_gemm(P, P.wg_f0, 1, st, "wgrad_fuse0"));
+    FND_CUDA_OK(cudaEventRecord(P.ev_fork, st));
+    FND_CUDA_OK(cudaStreamWaitEvent(side, P.ev_fork, 0));
+    P.dp.a = adamw_params(P);
+    FND_CUDA_OK(launch_k(dp_reduce_kernel, kDpGrid, 256, 0, side, false, P.dp, 0, 1, 0));
+    FND_CUDA_OK(cudaEventRecord(P.ev_join, side));
+    P.pdl_next = false;
+  }
   FND_OK(run_gemm(P, P.dg_f0, 1, st, "dgrad_fuse0"));
   FND_OK(run_assemble_bwd(P, st));
   FND_OK(run_gemm(P, P.dg_qkv, 1, st, "dgrad_qkv"));
+  if (overlap) {
+    const FinParams f = fin_params(P, P.fin_all, P.wg_rest.grid, P.total_slots, false, 0, 0);
+    FND_OK(run_gemm(P, P.wg_rest, 1, st, "wgrad_rest", &f, P.fin_all.grid));
+    FND_CUDA_OK(cudaStreamWaitEvent(st, P.ev_join, 0));
+    return dp_tail(P, true, st);
+  }
   // Weight gradients of every GEMM; the trailing CTAs of the same launch run the finalize jobs (bias / threshold /
   // leaf / evidence reductions, mean loss). Every CTA leaves its sum of squares in "slots"; whoever consumes the
   // gradients next reduces the slots to the global norm: adamw_kernel in the fused step (no election, fence or atomic
@@ -770,6 +813,15 @@ static int train_fwd_bwd_impl(void* plan, const fnd_inputs* in, int fused_optimi
 }
 
 int fnd_train_fwd_bwd(void* plan, const fnd_inputs* in, void* stream) { return train_fwd_bwd_impl(plan, in, 0, stream); }
+
+int fnd_train_step_dp(void* plan, const fnd_inputs* in, void* stream, void* side_stream) {
+  Plan* PP = as_plan(plan);
+  if (!PP || !PP->bound) return -5;
+  if (!PP->dp_bound) return -7;
+  if (side_stream) return train_fwd_bwd_impl(plan, in, 0, stream, side_stream);
+  FND_OK(train_fwd_bwd_impl(plan, in, 0, stream));
+  return fnd_dp_optimizer_step(plan, stream);
+}
 
 int fnd_train_step(void* plan, const fnd_inputs* in, void* stream) {
   {
@@ -790,6 +842,22 @@ int fnd_train_step(void* plan, const fnd_inputs* in, void* stream) {
 }
 
 // ------------------------------- data-parallel optimizer step over peer memory -------------------------------
+// The hot arena [0, n_hot) is cut into three ranges — before / inside / after fuse_mlp.0.weight — and every rank owns an
+// equal share (rounded to 1024 elements) of EACH range, so that the early (fuse_mlp.0) reduction is balanced over ranks.
+static void dp_segments(const Plan& P, int rank, int world, size_t (&lo)[kDpMaxSeg], size_t (&hi)[kDpMaxSeg]) {
+  const size_t a0 = static_cast<size_t>(P.L.at("fusion.fuse_mlp.0.weight"));
+  const size_t a1 = a0 + static_cast<size_t>(2 * P.H) * (P.nslots * P.H);
+  const size_t rb[kDpMaxSeg][2] = {{a0, a1}, {0, a0}, {a1, static_cast<size_t>(P.L.n_hot)}};
+  for (int s = 0; s < kDpMaxSeg; ++s) {
+    const size_t n = rb[s][1] - rb[s][0];
+    size_t per = (n + world - 1) / world;
+    per = (per + 1023) / 1024 * 1024;
+    const size_t l = per * rank < n ? per * rank : n;
+    lo[s] = rb[s][0] + l;
+    hi[s] = rb[s][0] + (l + per < n ? l + per : n);
+  }
+}
+
 int fnd_dp_bind(void* plan, int rank, int world, const unsigned long long* peer_bases, long long off_params,
                 long long off_grads, long long off_shadow_hi, long long off_shadow_lo, long long off_pad, float* gred,
                 long long gred_elems, float* slots, long long slots_elems) {
@@ -813,44 +881,50 @@ int fnd_dp_bind(void* plan, int rank, int world, const unsigned long long* peer_
   // the plan must already be bound to THIS rank's slices of the symmetric buffer
   if (d.params[rank] != P.params || d.grads[rank] != P.grads || d.sh_hi[rank] != P.sh_hi || (P.sh_lo && d.sh_lo[rank] != P.sh_lo))
     return -3;
-  const size_t n = static_cast<size_t>(P.L.n_hot);
-  size_t per = (n + world - 1) / world;
-  per = (per + 1023) / 1024 * 1024;
-  d.shard_lo = per * rank < n ? per * rank : n;
-  d.shard_hi = d.shard_lo + per < n ? d.shard_lo + per : n;
-  if (gred_elems < static_cast<long long>(per) || slots_elems < 1024) return -4;
+  d.nseg = kDpMaxSeg;
+  dp_segments(P, rank, world, d.seg_lo, d.seg_hi);
+  size_t off = 0;
+  for (int s = 0; s < kDpMaxSeg; ++s) { d.seg_goff[s] = off; off += d.seg_hi[s] - d.seg_lo[s]; }
+  if (gred_elems < static_cast<long long>(off) || slots_elems < 1024) return -4;
   d.gred = gred; d.slots = slots;
   d.a = adamw_params(P);
   P.dp = d;
   P.dp_bound = true;
+  if (!P.ev_fork) {
+    FND_CUDA_OK(cudaEventCreateWithFlags(&P.ev_fork, cudaEventDisableTiming));
+    FND_CUDA_OK(cudaEventCreateWithFlags(&P.ev_join, cudaEventDisableTiming));
+  }
   return 0;
 }
 
-int fnd_dp_shard_range(const void* plan, int rank, int world, long long* lo, long long* hi) {
-  if (!plan || !lo || !hi || world < 1 || rank < 0 || rank >= world) return -1;
+int fnd_dp_shard_ranges(const void* plan, int rank, int world, long long* lo3, long long* hi3) {
+  if (!plan || !lo3 || !hi3 || world < 1 || rank < 0 || rank >= world) return -1;
   const Plan* P = static_cast<const Plan*>(plan);
-  const size_t n = static_cast<size_t>(P->L.n_hot);
-  size_t per = (n + world - 1) / world;
-  per = (per + 1023) / 1024 * 1024;
-  const size_t l = per * rank < n ? per * rank : n;
-  *lo = static_cast<long long>(l);
-  *hi = static_cast<long long>(l + per < n ? l + per : n);
+  size_t lo[kDpMaxSeg], hi[kDpMaxSeg];
+  dp_segments(*P, rank, world, lo, hi);
+  for (int s = 0; s < kDpMaxSeg; ++s) { lo3[s] = static_cast<long long>(lo[s]); hi3[s] = static_cast<long long>(hi[s]); }
+  return kDpMaxSeg;
+}
+
+static int dp_tail(Plan& P, bool early_done, cudaStream_t st) {
+  P.dp.a = adamw_params(P);
+  if (!early_done) {
+    FND_CUDA_OK(launch_k(dp_reduce_kernel, kDpGrid, 256, 0, st, false, P.dp, 0, 1, 0));
+    mark(P, "dp_reduce_early", st);
+  }
+  FND_CUDA_OK(launch_k(dp_reduce_kernel, kDpGrid, 256, 0, st, false, P.dp, 1, kDpMaxSeg, 1));
+  mark(P, "dp_reduce", st);
+  FND_CUDA_OK(launch_k(dp_adamw_kernel, kDpGrid, 256, 0, st, false, P.dp));
+  mark(P, "dp_adamw", st);
+  FND_CUDA_OK(launch_k(dp_wait_kernel, 1, 32, 0, st, false, P.dp));
+  mark(P, "dp_wait", st);
   return 0;
 }
 
 int fnd_dp_optimizer_step(void* plan, void* stream) {
   FND_PLAN(plan);
   if (!P.dp_bound) return -7;
-  P.dp.a = adamw_params(P);
-  // ordinary (non-PDL) launches: these kernels spin on remote flags and must not become resident early
-  const int grid = 148 * 4;
-  FND_CUDA_OK(launch_k(dp_reduce_kernel, grid, 256, 0, st, false, P.dp));
-  mark(P, "dp_reduce", st);
-  FND_CUDA_OK(launch_k(dp_adamw_kernel, grid, 256, 0, st, false, P.dp));
-  mark(P, "dp_adamw", st);
-  FND_CUDA_OK(launch_k(dp_wait_kernel, 1, 32, 0, st, false, P.dp));
-  mark(P, "dp_wait", st);
-  return 0;
+  return dp_tail(P, false, st);
 }
 
 int fnd_eval_step(void* plan, const fnd_inputs* in, void* stream) {

@@ -7,7 +7,10 @@
 //
 //   dp_reduce_kernel   rank r sums ITS 1/N slice of the gradient arena straight out of every peer's memory (128-bit
 //                      P2P loads over NVLink/NVSwitch — a reduce-scatter without a staging copy), keeps the reduced
-//                      slice locally and publishes the slice's sum of squares to every peer;
+//                      slice locally and publishes the slice's sum of squares to every peer. It runs twice per step:
+//                      once for the fuse_mlp.0 weight gradient (65 % of all gradient bytes), which is complete two
+//                      thirds of the way through the backward pass and is reduced on a side stream UNDER the rest of
+//                      the backward, and once for everything else;
 //   dp_adamw_kernel    every rank adds the N partial sums in rank order (bit-identical clip coefficient everywhere),
 //                      runs AdamW on its slice only (1/N of the 357 MB optimizer stream; fp32 master, m and v stay
 //                      sharded, ZeRO-1 style) and writes the refreshed bf16 operand shadows — the only copy of the
@@ -26,9 +29,12 @@
 namespace fnd {
 
 constexpr int kDpMaxWorld = 8;
-// comm pad layout (uint32 words): [0,8) grads-ready epochs | [8,16) partial-ready | [16,24) shadows-written |
-// [24,32) float partial sums of squares | [32] local epoch counter | [33] local CTA counter
-constexpr int kPadGradsReady = 0, kPadPartialReady = 8, kPadDone = 16, kPadPartial = 24, kPadEpoch = 32, kPadCounter = 33;
+constexpr int kDpMaxSeg = 3;
+// comm pad layout (uint32 words): [0,8) early-gradients-ready epochs | [8,16) all-gradients-ready | [16,24) partial
+// norms ready | [24,32) shadows written | [32,40) float partial sums of squares | [40] local epoch counter |
+// [41] local CTA counter | [42] float: this rank's partial of the early segment
+constexpr int kPadReadyEarly = 0, kPadReadyLate = 8, kPadPartialReady = 16, kPadDone = 24, kPadPartial = 32, kPadEpoch = 40,
+              kPadCounter = 41, kPadPartialEarly = 42;
 constexpr int kPadWords = 64;
 
 struct DpParams {
@@ -40,7 +46,11 @@ struct DpParams {
   unsigned int* pad[kDpMaxWorld];         // comm pad of every rank
   float* gred;                            // local: reduced gradient slice [shard_hi - shard_lo]
   float* slots;                           // local: per-CTA sums of squares of dp_reduce_kernel
-  size_t shard_lo, shard_hi;              // this rank's slice of [0, n_hot), multiples of 4
+  // This rank's slice of [0, n_hot): one piece of each of (up to) three arena ranges — segment 0 is its share of the
+  // "early" range (fuse_mlp.0.weight), segments 1 and 2 its shares of the ranges before and after it. gred holds the
+  // reduced pieces back to back (seg_goff).
+  int nseg;
+  size_t seg_lo[kDpMaxSeg], seg_hi[kDpMaxSeg], seg_goff[kDpMaxSeg];
   AdamWParams a;                          // local p / m / v / state, shadow geometry
 };
 
@@ -80,33 +90,39 @@ __device__ __forceinline__ void dp_wait_all(const unsigned int* pad, int base, i
 // ---------------------------------------------------------------------------------------------------------------
 // 1. reduce-scatter out of peer memory + slice norm
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) dp_reduce_kernel(DpParams d) {
+// Segments [s0, s1) of this rank's slice. `late` = 0: the early launch (flag bank kPadReadyEarly; leaves its partial
+// sum of squares in the local pad); 1: the late launch (bank kPadReadyLate; adds the early partial and publishes the sum).
+__global__ void __launch_bounds__(256) dp_reduce_kernel(DpParams d, int s0, int s1, int late) {
   __shared__ float red[8];
   __shared__ int is_last;
   unsigned int* mypad = d.pad[d.rank];
   const unsigned int epoch = mypad[kPadEpoch] + 1u;
-  // my gradients are complete (stream order: the backward kernels precede this launch): tell every peer
+  const int bank = late ? kPadReadyLate : kPadReadyEarly;
+  // the gradients these segments cover are complete on this rank (stream/event order): tell every peer
   if (blockIdx.x == 0 && threadIdx.x < static_cast<unsigned>(d.world)) {
     __threadfence_system();
-    st_release_sys(d.pad[threadIdx.x] + kPadGradsReady + d.rank, epoch);
+    st_release_sys(d.pad[threadIdx.x] + bank + d.rank, epoch);
   }
-  dp_wait_all(mypad, kPadGradsReady, d.world, epoch, &d.a.state->err);
+  dp_wait_all(mypad, bank, d.world, epoch, &d.a.state->err);
 
   float ss = 0.f;
-  const size_t n4 = (d.shard_hi - d.shard_lo) >> 2;
-  for (size_t i4 = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i4 < n4;
-       i4 += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const size_t i = d.shard_lo + i4 * 4;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    float4 t[kDpMaxWorld];
+  for (int sg = s0; sg < s1; ++sg) {
+    const size_t n4 = (d.seg_hi[sg] - d.seg_lo[sg]) >> 2;
+    float* out = d.gred + d.seg_goff[sg];
+    for (size_t i4 = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i4 < n4;
+         i4 += static_cast<size_t>(gridDim.x) * blockDim.x) {
+      const size_t i = d.seg_lo[sg] + i4 * 4;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 t[kDpMaxWorld];
 #pragma unroll
-    for (int p = 0; p < kDpMaxWorld; ++p)
-      if (p < d.world) t[p] = ld_peer_f4(d.grads[p] + i);           // all peers in flight, summed in rank order
+      for (int p = 0; p < kDpMaxWorld; ++p)
+        if (p < d.world) t[p] = ld_peer_f4(d.grads[p] + i);           // all peers in flight, summed in rank order
 #pragma unroll
-    for (int p = 0; p < kDpMaxWorld; ++p)
-      if (p < d.world) { acc.x += t[p].x; acc.y += t[p].y; acc.z += t[p].z; acc.w += t[p].w; }
-    *reinterpret_cast<float4*>(d.gred + i4 * 4) = acc;
-    ss += (acc.x * acc.x + acc.y * acc.y) + (acc.z * acc.z + acc.w * acc.w);
+      for (int p = 0; p < kDpMaxWorld; ++p)
+        if (p < d.world) { acc.x += t[p].x; acc.y += t[p].y; acc.z += t[p].z; acc.w += t[p].w; }
+      *reinterpret_cast<float4*>(out + i4 * 4) = acc;
+      ss += (acc.x * acc.x + acc.y * acc.y) + (acc.z * acc.z + acc.w * acc.w);
+    }
   }
   ss = warp_sum(ss);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
@@ -120,13 +136,17 @@ __global__ void __launch_bounds__(256) dp_reduce_kernel(DpParams d) {
   }
   __syncthreads();
   if (!is_last) return;
-  // last CTA: this rank's partial sum of squares (fixed order) -> every peer
+  // last CTA: this launch's sum of squares (fixed order)
   if (threadIdx.x < 32) {
     __threadfence();
     const double part = warp_reduce_slots(d.slots, static_cast<int>(gridDim.x));
     if (threadIdx.x == 0) mypad[kPadCounter] = 0u;
-    if (threadIdx.x < static_cast<unsigned>(d.world)) {
-      reinterpret_cast<float*>(d.pad[threadIdx.x])[kPadPartial + d.rank] = static_cast<float>(part);
+    if (!late) {
+      if (threadIdx.x == 0) reinterpret_cast<float*>(mypad)[kPadPartialEarly] = static_cast<float>(part);
+    } else if (threadIdx.x < static_cast<unsigned>(d.world)) {
+      // early + late partial of this rank -> every peer (the early launch finished before this one started)
+      const float both = static_cast<float>(part + static_cast<double>(reinterpret_cast<volatile float*>(mypad)[kPadPartialEarly]));
+      reinterpret_cast<float*>(d.pad[threadIdx.x])[kPadPartial + d.rank] = both;
       __threadfence_system();
       st_release_sys(d.pad[threadIdx.x] + kPadPartialReady + d.rank, epoch);
     }
@@ -204,12 +224,14 @@ __global__ void __launch_bounds__(256) dp_adamw_kernel(DpParams d) {
   const float inv_sqrt_bc2 = rsqrtf(bc2);
   const AdamWParams& a = d.a;
   const uint64_t pol = l2_policy_evict_first();
-  const size_t n4 = (d.shard_hi - d.shard_lo) >> 2;
+  for (int sg = 0; sg < d.nseg; ++sg) {
+  const size_t n4 = (d.seg_hi[sg] - d.seg_lo[sg]) >> 2;
+  const float* gsrc = d.gred + d.seg_goff[sg];
   for (size_t i4 = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i4 < n4;
        i4 += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const size_t i = d.shard_lo + i4 * 4;
+    const size_t i = d.seg_lo[sg] + i4 * 4;
     float4 p = ld_f4_policy(a.p + i, pol);
-    const float4 g4 = *reinterpret_cast<const float4*>(d.gred + i4 * 4);
+    const float4 g4 = *reinterpret_cast<const float4*>(gsrc + i4 * 4);
     float4 m = ld_f4_policy(a.m + i, pol);
     float4 v = ld_f4_policy(a.v + i, pol);
     float* pp = &p.x; float* mp = &m.x; float* vp = &v.x; const float* gp = &g4.x;
@@ -226,6 +248,7 @@ __global__ void __launch_bounds__(256) dp_adamw_kernel(DpParams d) {
     st_f4_policy(a.m + i, m, pol);
     st_f4_policy(a.v + i, v, pol);
     dp_publish4(d, i, p);
+  }
   }
   // every P2P store of this CTA is ordered before its counter bump; the last CTA tells the peers
   __threadfence_system();

@@ -293,7 +293,7 @@ class Engine:
                         p.data = self.view(m._prefix + name)
         self.plans.clear()
         self._shadow_version = None
-        per = ((self.n_hot + world - 1) // world + 1023) // 1024 * 1024
+        per = (self.n_hot + world - 1) // world + 3 * 1024          # three pieces, each rounded up to 1024 elements
         self.symm = {"buf": buf, "handle": hdl, "rank": rank, "world": world, "group": group,
                      "offsets": (off_p, off_g, off_h, off_l, off_pad),
                      "peer_bases": [int(x) for x in hdl.buffer_ptrs],
@@ -310,11 +310,12 @@ class Engine:
                                    s["gred"].data_ptr(), s["gred"].numel(), s["slots"].data_ptr(), s["slots"].numel()),
               "fnd_dp_bind")
 
-    def shard_range(self, rank: int) -> Tuple[int, int]:
-        lo, hi = ctypes.c_longlong(), ctypes.c_longlong()
-        check(self.lib.fnd_dp_shard_range(self.any_plan().handle, rank, self.symm["world"], ctypes.byref(lo), ctypes.byref(hi)),
-              "fnd_dp_shard_range")
-        return lo.value, hi.value
+    def shard_ranges(self, rank: int) -> List[Tuple[int, int]]:
+        lo, hi = (ctypes.c_longlong * 3)(), (ctypes.c_longlong * 3)()
+        n = self.lib.fnd_dp_shard_ranges(self.any_plan().handle, rank, self.symm["world"], lo, hi)
+        if n < 0:
+            raise _lib.FndError(f"fnd_dp_shard_ranges: {n}")
+        return [(lo[i], hi[i]) for i in range(n)]
 
     def gather_master(self) -> None:
         """After sharded optimizer steps only the owner of a slice holds current fp32 master weights: broadcast every
@@ -324,9 +325,9 @@ class Engine:
         if s is None:
             return
         for r in range(s["world"]):
-            lo, hi = self.shard_range(r)
-            if hi > lo:
-                dist.broadcast(self.params[lo:hi], src=dist.get_global_rank(s["group"], r), group=s["group"])
+            for lo, hi in self.shard_ranges(r):
+                if hi > lo:
+                    dist.broadcast(self.params[lo:hi], src=dist.get_global_rank(s["group"], r), group=s["group"])
 
     def view(self, name: str) -> torch.Tensor:
         p = self.index[name]

@@ -8,6 +8,7 @@ them) or, alternatively, gathers each batch from a device-resident feature cache
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import Dict, Optional
 
 import torch
@@ -73,6 +74,8 @@ class FusedStep:
         self.batch = batch
         self.plan = self.engine.plan(batch)
         self.use_graph = use_graph
+        self.dp_overlap = os.environ.get("FND_DP_OVERLAP", "1") != "0"   # reduce fuse_mlp.0's gradient under the backward
+        self._side_stream: Optional[torch.cuda.Stream] = None
         self._graphs: Dict[str, torch.cuda.CUDAGraph] = {}
         dev = self.engine.device
         d = self.engine.dims
@@ -136,6 +139,14 @@ class FusedStep:
     # ------------------------------------------------------------------ launches
     def _run(self, entry: str, inp: FndInputs) -> None:
         lib, h = self.engine.lib, self.plan.handle
+        if entry == "train_step_dp":      # forward + backward + the sharded peer-memory optimizer step
+            side = None
+            if self.dp_overlap:
+                if self._side_stream is None:
+                    self._side_stream = torch.cuda.Stream(self.engine.device)
+                side = self._side_stream.cuda_stream
+            check(lib.fnd_train_step_dp(h, ctypes.byref(inp), self.engine.stream_ptr(), side), "fnd_train_step_dp")
+            return
         fn = {"train_step": lib.fnd_train_step, "train_fwd_bwd": lib.fnd_train_fwd_bwd, "eval_step": lib.fnd_eval_step}[entry]
         check(fn(h, ctypes.byref(inp), self.engine.stream_ptr()), "fnd_" + entry)
 
@@ -165,6 +176,15 @@ class FusedStep:
     def train_step(self, from_cache: bool = False) -> None:
         """One optimizer step on the batch currently in the static buffers (or gathered from the cache)."""
         self._launch("train_step", from_cache)
+        self.plan.forward_id += 1
+
+    def train_step_dp(self, from_cache: bool = False) -> None:
+        """One data-parallel optimizer step (every rank calls it with its own batch slice): forward + backward +
+        peer-memory reduce-scatter / sharded AdamW / shadow all-gather, ONE CUDA graph per rank."""
+        if not getattr(self, "_dp_bound", False):
+            self.engine.dp_bind(self.plan)
+            self._dp_bound = True
+        self._launch("train_step_dp", from_cache)
         self.plan.forward_id += 1
 
     def train_fwd_bwd(self, from_cache: bool = False) -> None:
