@@ -785,7 +785,8 @@ static int train_fwd_bwd_impl(void* plan, const fnd_inputs* in, int fused_optimi
     FND_CUDA_OK(cudaEventRecord(P.ev_fork, st));
     FND_CUDA_OK(cudaStreamWaitEvent(side, P.ev_fork, 0));
     P.dp.a = adamw_params(P);
-    FND_CUDA_OK(launch_k(dp_reduce_kernel, kDpGrid, 256, 0, side, false, P.dp, 0, 1, 0));
+    // one CTA per SM: leaves room for the backward's GEMM CTAs on every SM (see dp_reduce_kernel)
+    FND_CUDA_OK(launch_k(dp_reduce_kernel, 148, 256, 0, side, false, P.dp, 0, 1, 0));
     FND_CUDA_OK(cudaEventRecord(P.ev_join, side));
     P.pdl_next = false;
   }
@@ -908,11 +909,8 @@ int fnd_dp_shard_ranges(const void* plan, int rank, int world, long long* lo3, l
 
 static int dp_tail(Plan& P, bool early_done, cudaStream_t st) {
   P.dp.a = adamw_params(P);
-  if (!early_done) {
-    FND_CUDA_OK(launch_k(dp_reduce_kernel, kDpGrid, 256, 0, st, false, P.dp, 0, 1, 0));
-    mark(P, "dp_reduce_early", st);
-  }
-  FND_CUDA_OK(launch_k(dp_reduce_kernel, kDpGrid, 256, 0, st, false, P.dp, 1, kDpMaxSeg, 1));
+  if (early_done) FND_CUDA_OK(launch_k(dp_reduce_kernel, kDpGrid, 256, 0, st, false, P.dp, 1, kDpMaxSeg, 1));
+  else FND_CUDA_OK(launch_k(dp_reduce_kernel, kDpGrid, 256, 0, st, false, P.dp, 0, kDpMaxSeg, 2));
   mark(P, "dp_reduce", st);
   FND_CUDA_OK(launch_k(dp_adamw_kernel, kDpGrid, 256, 0, st, false, P.dp));
   mark(P, "dp_adamw", st);

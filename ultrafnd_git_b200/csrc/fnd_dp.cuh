@@ -91,8 +91,11 @@ __device__ __forceinline__ void dp_wait_all(const unsigned int* pad, int base, i
 // 1. reduce-scatter out of peer memory + slice norm
 // ---------------------------------------------------------------------------------------------------------------
 // Segments [s0, s1) of this rank's slice. `late` = 0: the early launch (flag bank kPadReadyEarly; leaves its partial
-// sum of squares in the local pad); 1: the late launch (bank kPadReadyLate; adds the early partial and publishes the sum).
-__global__ void __launch_bounds__(256) dp_reduce_kernel(DpParams d, int s0, int s1, int late) {
+// sum of squares in the local pad); 1: the late launch (bank kPadReadyLate; adds the early partial and publishes the
+// sum); 2: a single launch over all segments (no early launch happened this step).
+// Register-capped at 64: the early launch runs UNDER the backward GEMMs (one 256-thread CTA per SM, no shared memory),
+// and a GEMM CTA (320 threads x 152 registers, 213 KB smem) must still fit next to it on every SM.
+__global__ void __launch_bounds__(256, 4) dp_reduce_kernel(DpParams d, int s0, int s1, int late) {
   __shared__ float red[8];
   __shared__ int is_last;
   unsigned int* mypad = d.pad[d.rank];
@@ -145,7 +148,8 @@ __global__ void __launch_bounds__(256) dp_reduce_kernel(DpParams d, int s0, int 
       if (threadIdx.x == 0) reinterpret_cast<float*>(mypad)[kPadPartialEarly] = static_cast<float>(part);
     } else if (threadIdx.x < static_cast<unsigned>(d.world)) {
       // early + late partial of this rank -> every peer (the early launch finished before this one started)
-      const float both = static_cast<float>(part + static_cast<double>(reinterpret_cast<volatile float*>(mypad)[kPadPartialEarly]));
+      const float early = late == 1 ? reinterpret_cast<volatile float*>(mypad)[kPadPartialEarly] : 0.f;
+      const float both = static_cast<float>(part + static_cast<double>(early));
       reinterpret_cast<float*>(d.pad[threadIdx.x])[kPadPartial + d.rank] = both;
       __threadfence_system();
       st_release_sys(d.pad[threadIdx.x] + kPadPartialReady + d.rank, epoch);
