@@ -786,7 +786,7 @@ static int train_fwd_bwd_impl(void* plan, const fnd_inputs* in, int fused_optimi
     FND_CUDA_OK(cudaStreamWaitEvent(side, P.ev_fork, 0));
     P.dp.a = adamw_params(P);
     // one CTA per SM: leaves room for the backward's GEMM CTAs on every SM (see dp_reduce_kernel)
-    FND_CUDA_OK(launch_k(dp_reduce_kernel, 148, 256, 0, side, false, P.dp, 0, 1, 0));
+    FND_CUDA_OK(launch_k(dp_reduce_kernel, 148, 128, 0, side, false, P.dp, 0, 1, 0));
     FND_CUDA_OK(cudaEventRecord(P.ev_join, side));
     P.pdl_next = false;
   }

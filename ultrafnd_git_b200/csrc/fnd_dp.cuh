@@ -90,12 +90,45 @@ __device__ __forceinline__ void dp_wait_all(const unsigned int* pad, int base, i
 // ---------------------------------------------------------------------------------------------------------------
 // 1. reduce-scatter out of peer memory + slice norm
 // ---------------------------------------------------------------------------------------------------------------
+// One segment: W = padded world size, U = independent float4 per thread and iteration.
+template <int W, int U>
+__device__ __forceinline__ float dp_reduce_segment(const DpParams& d, int sg) {
+  const size_t n4 = (d.seg_hi[sg] - d.seg_lo[sg]) >> 2;
+  float* out = d.gred + d.seg_goff[sg];
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  float ss = 0.f;
+  for (size_t i4 = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i4 < n4; i4 += stride * U) {
+    float4 t[U][W];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const size_t j4 = i4 + u * stride;
+#pragma unroll
+      for (int p = 0; p < W; ++p)
+        if (p < d.world && j4 < n4) t[u][p] = ld_peer_f4(d.grads[p] + d.seg_lo[sg] + j4 * 4);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const size_t j4 = i4 + u * stride;
+      if (j4 < n4) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int p = 0; p < W; ++p)      // summed in rank order
+          if (p < d.world) { acc.x += t[u][p].x; acc.y += t[u][p].y; acc.z += t[u][p].z; acc.w += t[u][p].w; }
+        *reinterpret_cast<float4*>(out + j4 * 4) = acc;
+        ss += (acc.x * acc.x + acc.y * acc.y) + (acc.z * acc.z + acc.w * acc.w);
+      }
+    }
+  }
+  return ss;
+}
+
 // Segments [s0, s1) of this rank's slice. `late` = 0: the early launch (flag bank kPadReadyEarly; leaves its partial
 // sum of squares in the local pad); 1: the late launch (bank kPadReadyLate; adds the early partial and publishes the
 // sum); 2: a single launch over all segments (no early launch happened this step).
-// Register-capped at 64: the early launch runs UNDER the backward GEMMs (one 256-thread CTA per SM, no shared memory),
-// and a GEMM CTA (320 threads x 152 registers, 213 KB smem) must still fit next to it on every SM.
-__global__ void __launch_bounds__(256, 4) dp_reduce_kernel(DpParams d, int s0, int s1, int late) {
+// The early launch runs UNDER the backward GEMMs: ONE 128-thread CTA per SM and no shared memory, so that a GEMM CTA
+// (320 threads x 152 registers, 213 KB smem) still fits next to it on every SM. The late launch has the GPU to itself
+// (256-thread CTAs, several per SM).
+__global__ void __launch_bounds__(256) dp_reduce_kernel(DpParams d, int s0, int s1, int late) {
   __shared__ float red[8];
   __shared__ int is_last;
   unsigned int* mypad = d.pad[d.rank];
@@ -110,29 +143,17 @@ __global__ void __launch_bounds__(256, 4) dp_reduce_kernel(DpParams d, int s0, i
 
   float ss = 0.f;
   for (int sg = s0; sg < s1; ++sg) {
-    const size_t n4 = (d.seg_hi[sg] - d.seg_lo[sg]) >> 2;
-    float* out = d.gred + d.seg_goff[sg];
-    for (size_t i4 = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i4 < n4;
-         i4 += static_cast<size_t>(gridDim.x) * blockDim.x) {
-      const size_t i = d.seg_lo[sg] + i4 * 4;
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      float4 t[kDpMaxWorld];
-#pragma unroll
-      for (int p = 0; p < kDpMaxWorld; ++p)
-        if (p < d.world) t[p] = ld_peer_f4(d.grads[p] + i);           // all peers in flight, summed in rank order
-#pragma unroll
-      for (int p = 0; p < kDpMaxWorld; ++p)
-        if (p < d.world) { acc.x += t[p].x; acc.y += t[p].y; acc.z += t[p].z; acc.w += t[p].w; }
-      *reinterpret_cast<float4*>(out + i4 * 4) = acc;
-      ss += (acc.x * acc.x + acc.y * acc.y) + (acc.z * acc.z + acc.w * acc.w);
-    }
+    // eight 128-bit peer loads in flight per thread whatever the world size (NVLink latency x bandwidth needs MBs in flight)
+    if (d.world <= 2) ss += dp_reduce_segment<2, 4>(d, sg);
+    else if (d.world <= 4) ss += dp_reduce_segment<4, 2>(d, sg);
+    else ss += dp_reduce_segment<8, 1>(d, sg);
   }
   ss = warp_sum(ss);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
   __syncthreads();
   if (threadIdx.x == 0) {
     float tot = 0.f;
-    for (int w = 0; w < 8; ++w) tot += red[w];
+    for (int w = 0; w < static_cast<int>(blockDim.x >> 5); ++w) tot += red[w];
     d.slots[blockIdx.x] = tot;
     __threadfence();
     is_last = (atomicAdd(mypad + kPadCounter, 1u) == gridDim.x - 1) ? 1 : 0;
