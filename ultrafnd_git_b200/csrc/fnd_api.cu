@@ -764,6 +764,7 @@ int fnd_clip_adamw_step(void* plan, int norm_from_slots, void* stream) {
 // they spin on remote flags and must not become resident early.
 static const int kDpGrid = 148 * 4;
 static int dp_tail(Plan& P, bool early_done, cudaStream_t st);
+static void dp_segments(const Plan& P, int rank, int world, size_t (&lo)[kDpMaxSeg], size_t (&hi)[kDpMaxSeg]);
 
 static int train_fwd_bwd_impl(void* plan, const fnd_inputs* in, int fused_optimizer, void* stream, void* side_stream = nullptr) {
   FND_PLAN(plan);
@@ -784,9 +785,16 @@ static int train_fwd_bwd_impl(void* plan, const fnd_inputs* in, int fused_optimi
     FND_OK(run_gemm(P, P.wg_f0, 1, st, "wgrad_fuse0"));
     FND_CUDA_OK(cudaEventRecord(P.ev_fork, st));
     FND_CUDA_OK(cudaStreamWaitEvent(side, P.ev_fork, 0));
-    P.dp.a = adamw_params(P);
-    // one CTA per SM: leaves room for the backward's GEMM CTAs on every SM (see dp_reduce_kernel)
-    FND_CUDA_OK(launch_k(dp_reduce_kernel, 148, 128, 0, side, false, P.dp, 0, 1, 0));
+    // push every peer's piece of this gradient into its staging slot for this rank (copy engines, no SMs)
+    for (int p = 0; p < P.dp.world; ++p) {
+      if (p == P.dp.rank) continue;
+      size_t lo[kDpMaxSeg], hi[kDpMaxSeg];
+      dp_segments(P, p, P.dp.world, lo, hi);
+      if (hi[0] > lo[0])
+        FND_CUDA_OK(cudaMemcpyAsync(P.dp.stage[p] + static_cast<size_t>(P.dp.rank) * P.dp.piece_cap, P.grads + lo[0],
+                                    (hi[0] - lo[0]) * sizeof(float), cudaMemcpyDeviceToDevice, side));
+    }
+    FND_CUDA_OK(launch_k(dp_signal_kernel, 1, 32, 0, side, false, P.dp, static_cast<int>(kPadReadyEarly)));
     FND_CUDA_OK(cudaEventRecord(P.ev_join, side));
     P.pdl_next = false;
   }
@@ -859,9 +867,17 @@ static void dp_segments(const Plan& P, int rank, int world, size_t (&lo)[kDpMaxS
   }
 }
 
+int fnd_dp_stage_elems(const void* plan, int world) {
+  if (!plan || world < 1 || world > kDpMaxWorld) return -1;
+  const Plan* P = static_cast<const Plan*>(plan);
+  size_t lo[kDpMaxSeg], hi[kDpMaxSeg];
+  dp_segments(*P, 0, world, lo, hi);          // rank 0's piece is the largest (pieces are rounded up to 1024)
+  return static_cast<int>((hi[0] - lo[0]) * world);
+}
+
 int fnd_dp_bind(void* plan, int rank, int world, const unsigned long long* peer_bases, long long off_params,
-                long long off_grads, long long off_shadow_hi, long long off_shadow_lo, long long off_pad, float* gred,
-                long long gred_elems, float* slots, long long slots_elems) {
+                long long off_grads, long long off_shadow_hi, long long off_shadow_lo, long long off_pad,
+                long long off_stage, float* gred, long long gred_elems, float* slots, long long slots_elems) {
   Plan* PP = as_plan(plan);
   if (!PP || !PP->bound) return -5;
   Plan& P = *PP;
@@ -878,6 +894,12 @@ int fnd_dp_bind(void* plan, int rank, int world, const unsigned long long* peer_
     d.sh_hi[p] = reinterpret_cast<__nv_bfloat16*>(base + off_shadow_hi);
     d.sh_lo[p] = P.sh_lo ? reinterpret_cast<__nv_bfloat16*>(base + off_shadow_lo) : nullptr;
     d.pad[p] = reinterpret_cast<unsigned int*>(base + off_pad);
+    d.stage[p] = reinterpret_cast<float*>(base + off_stage);
+  }
+  {
+    size_t lo0[kDpMaxSeg], hi0[kDpMaxSeg];
+    dp_segments(P, 0, world, lo0, hi0);
+    d.piece_cap = hi0[0] - lo0[0];
   }
   // the plan must already be bound to THIS rank's slices of the symmetric buffer
   if (d.params[rank] != P.params || d.grads[rank] != P.grads || d.sh_hi[rank] != P.sh_hi || (P.sh_lo && d.sh_lo[rank] != P.sh_lo))
@@ -909,8 +931,7 @@ int fnd_dp_shard_ranges(const void* plan, int rank, int world, long long* lo3, l
 
 static int dp_tail(Plan& P, bool early_done, cudaStream_t st) {
   P.dp.a = adamw_params(P);
-  if (early_done) FND_CUDA_OK(launch_k(dp_reduce_kernel, kDpGrid, 256, 0, st, false, P.dp, 1, kDpMaxSeg, 1));
-  else FND_CUDA_OK(launch_k(dp_reduce_kernel, kDpGrid, 256, 0, st, false, P.dp, 0, kDpMaxSeg, 2));
+  FND_CUDA_OK(launch_k(dp_reduce_kernel, kDpGrid, 256, 0, st, false, P.dp, early_done ? 1 : 0));
   mark(P, "dp_reduce", st);
   FND_CUDA_OK(launch_k(dp_adamw_kernel, kDpGrid, 256, 0, st, false, P.dp));
   mark(P, "dp_adamw", st);

@@ -5,12 +5,14 @@
 // then N identical AdamW passes over 357 MB each", the gradient exchange, the clip and the optimizer are ONE sharded
 // sequence over symmetric (peer-mapped) buffers:
 //
-//   dp_reduce_kernel   rank r sums ITS 1/N slice of the gradient arena straight out of every peer's memory (128-bit
-//                      P2P loads over NVLink/NVSwitch — a reduce-scatter without a staging copy), keeps the reduced
-//                      slice locally and publishes the slice's sum of squares to every peer. It runs twice per step:
-//                      once for the fuse_mlp.0 weight gradient (65 % of all gradient bytes), which is complete two
-//                      thirds of the way through the backward pass and is reduced on a side stream UNDER the rest of
-//                      the backward, and once for everything else;
+//   (copy engines)     the fuse_mlp.0 weight gradient (65 % of all gradient bytes) is complete two thirds of the way
+//                      through the backward pass: each rank PUSHES the pieces its peers own into their staging
+//                      buffers with cudaMemcpyAsync on a side stream (DMA engines over NVLink, no SM is taken from
+//                      the backward kernels) and then raises a flag (dp_signal_kernel);
+//   dp_reduce_kernel   rank r sums ITS 1/N slice of the gradient arena: the pushed pieces out of local staging, the
+//                      rest straight out of every peer's memory (128-bit P2P loads over NVLink/NVSwitch — a
+//                      reduce-scatter without a staging copy), keeps the reduced slice locally and publishes the
+//                      slice's sum of squares to every peer;
 //   dp_adamw_kernel    every rank adds the N partial sums in rank order (bit-identical clip coefficient everywhere),
 //                      runs AdamW on its slice only (1/N of the 357 MB optimizer stream; fp32 master, m and v stay
 //                      sharded, ZeRO-1 style) and writes the refreshed bf16 operand shadows — the only copy of the
@@ -44,6 +46,8 @@ struct DpParams {
   __nv_bfloat16* sh_hi[kDpMaxWorld];      // bf16 operand shadows of every rank
   __nv_bfloat16* sh_lo[kDpMaxWorld];      // residual planes (fp32x3 mode) or null
   unsigned int* pad[kDpMaxWorld];         // comm pad of every rank
+  float* stage[kDpMaxWorld];              // staging buffer of every rank: [world][piece_cap] pushed segment-0 pieces
+  size_t piece_cap;                       // elements per staging slot
   float* gred;                            // local: reduced gradient slice [shard_hi - shard_lo]
   float* slots;                           // local: per-CTA sums of squares of dp_reduce_kernel
   // This rank's slice of [0, n_hot): one piece of each of (up to) three arena ranges — segment 0 is its share of the
@@ -91,9 +95,17 @@ __device__ __forceinline__ void dp_wait_all(const unsigned int* pad, int base, i
 // 1. reduce-scatter out of peer memory + slice norm
 // ---------------------------------------------------------------------------------------------------------------
 // One segment: W = padded world size, U = independent float4 per thread and iteration.
+// `staged`: the peers' contributions were pushed into this rank's staging buffer (segment 0 of an overlapped step).
 template <int W, int U>
-__device__ __forceinline__ float dp_reduce_segment(const DpParams& d, int sg) {
+__device__ __forceinline__ float dp_reduce_segment(const DpParams& d, int sg, bool staged) {
   const size_t n4 = (d.seg_hi[sg] - d.seg_lo[sg]) >> 2;
+  const float* src[W];
+#pragma unroll
+  for (int p = 0; p < W; ++p) {
+    src[p] = nullptr;
+    if (p < d.world)
+      src[p] = (staged && p != d.rank) ? d.stage[d.rank] + static_cast<size_t>(p) * d.piece_cap : d.grads[p] + d.seg_lo[sg];
+  }
   float* out = d.gred + d.seg_goff[sg];
   const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
   float ss = 0.f;
@@ -104,7 +116,7 @@ __device__ __forceinline__ float dp_reduce_segment(const DpParams& d, int sg) {
       const size_t j4 = i4 + u * stride;
 #pragma unroll
       for (int p = 0; p < W; ++p)
-        if (p < d.world && j4 < n4) t[u][p] = ld_peer_f4(d.grads[p] + d.seg_lo[sg] + j4 * 4);
+        if (p < d.world && j4 < n4) t[u][p] = ld_peer_f4(src[p] + j4 * 4);
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
@@ -122,56 +134,58 @@ __device__ __forceinline__ float dp_reduce_segment(const DpParams& d, int sg) {
   return ss;
 }
 
-// Segments [s0, s1) of this rank's slice. `late` = 0: the early launch (flag bank kPadReadyEarly; leaves its partial
-// sum of squares in the local pad); 1: the late launch (bank kPadReadyLate; adds the early partial and publishes the
-// sum); 2: a single launch over all segments (no early launch happened this step).
-// The early launch runs UNDER the backward GEMMs: ONE 128-thread CTA per SM and no shared memory, so that a GEMM CTA
-// (320 threads x 152 registers, 213 KB smem) still fits next to it on every SM. The late launch has the GPU to itself
-// (256-thread CTAs, several per SM).
-__global__ void __launch_bounds__(256) dp_reduce_kernel(DpParams d, int s0, int s1, int late) {
+// Raised on the side stream once this rank's pushes have been issued AND completed (stream order after the copies).
+__global__ void __launch_bounds__(32) dp_signal_kernel(DpParams d, int bank) {
+  unsigned int* mypad = d.pad[d.rank];
+  const unsigned int epoch = mypad[kPadEpoch] + 1u;
+  if (threadIdx.x < static_cast<unsigned>(d.world)) {
+    __threadfence_system();
+    st_release_sys(d.pad[threadIdx.x] + bank + d.rank, epoch);
+  }
+}
+
+// All segments of this rank's slice. `staged` != 0: segment 0 comes out of local staging (its pieces were pushed by the
+// peers during the backward pass; wait for their kPadReadyEarly flags too).
+__global__ void __launch_bounds__(256) dp_reduce_kernel(DpParams d, int staged) {
   __shared__ float red[8];
   __shared__ int is_last;
   unsigned int* mypad = d.pad[d.rank];
   const unsigned int epoch = mypad[kPadEpoch] + 1u;
-  const int bank = late ? kPadReadyLate : kPadReadyEarly;
-  // the gradients these segments cover are complete on this rank (stream/event order): tell every peer
+  // all of this rank's gradients are complete (stream order): tell every peer
   if (blockIdx.x == 0 && threadIdx.x < static_cast<unsigned>(d.world)) {
     __threadfence_system();
-    st_release_sys(d.pad[threadIdx.x] + bank + d.rank, epoch);
+    st_release_sys(d.pad[threadIdx.x] + kPadReadyLate + d.rank, epoch);
   }
-  dp_wait_all(mypad, bank, d.world, epoch, &d.a.state->err);
+  if (staged) dp_wait_all(mypad, kPadReadyEarly, d.world, epoch, &d.a.state->err);
+  dp_wait_all(mypad, kPadReadyLate, d.world, epoch, &d.a.state->err);
 
   float ss = 0.f;
-  for (int sg = s0; sg < s1; ++sg) {
-    // eight 128-bit peer loads in flight per thread whatever the world size (NVLink latency x bandwidth needs MBs in flight)
-    if (d.world <= 2) ss += dp_reduce_segment<2, 4>(d, sg);
-    else if (d.world <= 4) ss += dp_reduce_segment<4, 2>(d, sg);
-    else ss += dp_reduce_segment<8, 1>(d, sg);
+  for (int sg = 0; sg < d.nseg; ++sg) {
+    const bool st = staged && sg == 0;
+    // eight 128-bit loads in flight per thread whatever the world size (NVLink latency x bandwidth needs MBs in flight)
+    if (d.world <= 2) ss += dp_reduce_segment<2, 4>(d, sg, st);
+    else if (d.world <= 4) ss += dp_reduce_segment<4, 2>(d, sg, st);
+    else ss += dp_reduce_segment<8, 1>(d, sg, st);
   }
   ss = warp_sum(ss);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
   __syncthreads();
   if (threadIdx.x == 0) {
     float tot = 0.f;
-    for (int w = 0; w < static_cast<int>(blockDim.x >> 5); ++w) tot += red[w];
+    for (int w = 0; w < 8; ++w) tot += red[w];
     d.slots[blockIdx.x] = tot;
     __threadfence();
     is_last = (atomicAdd(mypad + kPadCounter, 1u) == gridDim.x - 1) ? 1 : 0;
   }
   __syncthreads();
   if (!is_last) return;
-  // last CTA: this launch's sum of squares (fixed order)
+  // last CTA: this rank's sum of squares (fixed order) -> every peer
   if (threadIdx.x < 32) {
     __threadfence();
     const double part = warp_reduce_slots(d.slots, static_cast<int>(gridDim.x));
     if (threadIdx.x == 0) mypad[kPadCounter] = 0u;
-    if (!late) {
-      if (threadIdx.x == 0) reinterpret_cast<float*>(mypad)[kPadPartialEarly] = static_cast<float>(part);
-    } else if (threadIdx.x < static_cast<unsigned>(d.world)) {
-      // early + late partial of this rank -> every peer (the early launch finished before this one started)
-      const float early = late == 1 ? reinterpret_cast<volatile float*>(mypad)[kPadPartialEarly] : 0.f;
-      const float both = static_cast<float>(part + static_cast<double>(early));
-      reinterpret_cast<float*>(d.pad[threadIdx.x])[kPadPartial + d.rank] = both;
+    if (threadIdx.x < static_cast<unsigned>(d.world)) {
+      reinterpret_cast<float*>(d.pad[threadIdx.x])[kPadPartial + d.rank] = static_cast<float>(part);
       __threadfence_system();
       st_release_sys(d.pad[threadIdx.x] + kPadPartialReady + d.rank, epoch);
     }

@@ -272,7 +272,11 @@ class Engine:
         off_h = up(off_g + 4 * self.n_hot)
         off_l = up(off_h + 2 * self.n_shadow_buf)
         off_pad = up(off_l + (2 * self.n_shadow_buf if self.mode == MODE_FP32X3 else 0))
-        total = off_pad + 256
+        off_stage = off_pad + 256
+        stage_elems = self.lib.fnd_dp_stage_elems(self.any_plan().handle, world)
+        if stage_elems < 0:
+            raise _lib.FndError(f"fnd_dp_stage_elems: {stage_elems}")
+        total = off_stage + 4 * stage_elems
         buf = symm.empty(total, dtype=torch.uint8, device=self.device)
         buf.zero_()
         hdl = symm.rendezvous(buf, group)
@@ -295,7 +299,7 @@ class Engine:
         self._shadow_version = None
         per = (self.n_hot + world - 1) // world + 3 * 1024          # three pieces, each rounded up to 1024 elements
         self.symm = {"buf": buf, "handle": hdl, "rank": rank, "world": world, "group": group,
-                     "offsets": (off_p, off_g, off_h, off_l, off_pad),
+                     "offsets": (off_p, off_g, off_h, off_l, off_pad, off_stage),
                      "peer_bases": [int(x) for x in hdl.buffer_ptrs],
                      "gred": torch.zeros(per, dtype=torch.float32, device=self.device),
                      "slots": torch.zeros(1024, dtype=torch.float32, device=self.device)}
@@ -305,8 +309,8 @@ class Engine:
     def dp_bind(self, plan: "Plan") -> None:
         s = self.symm
         bases = (ctypes.c_ulonglong * s["world"])(*s["peer_bases"])
-        off_p, off_g, off_h, off_l, off_pad = s["offsets"]
-        check(self.lib.fnd_dp_bind(plan.handle, s["rank"], s["world"], bases, off_p, off_g, off_h, off_l, off_pad,
+        off_p, off_g, off_h, off_l, off_pad, off_stage = s["offsets"]
+        check(self.lib.fnd_dp_bind(plan.handle, s["rank"], s["world"], bases, off_p, off_g, off_h, off_l, off_pad, off_stage,
                                    s["gred"].data_ptr(), s["gred"].numel(), s["slots"].data_ptr(), s["slots"].numel()),
               "fnd_dp_bind")
 
