@@ -177,3 +177,32 @@ def test_bench_reference_arm_emits_contract_json():
               "cpu_baseline", "e2e", "config"):
         assert k in line, k
     assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
+
+
+def test_dp_shard_ranges_partition_the_hot_arena():
+    """fnd_dp_shard_ranges (host-only): for every world size the per-rank ranges are disjoint, 4-element aligned and cover
+    [0, hot) exactly; segment 0 of every rank lies inside fuse_mlp.0.weight (the early-reduced range)."""
+    import ctypes
+    from ultrafnd_git_b200 import _lib, engine as E
+    lib = _lib.load()
+    dims = E.Dims()
+    cd = dims.to_c()
+    h = ctypes.c_void_p()
+    assert lib.fnd_plan_create(ctypes.byref(cd), 8, 0, ctypes.byref(h)) == 0
+    n_hot = lib.fnd_arena_hot_elems(ctypes.byref(cd))
+    table = {p.name: p for p in E.param_table(dims)}
+    f0 = table["fusion.fuse_mlp.0.weight"]
+    try:
+        for world in range(1, 9):
+            covered = np.zeros(n_hot, dtype=np.int8)
+            for rank in range(world):
+                lo, hi = (ctypes.c_longlong * 3)(), (ctypes.c_longlong * 3)()
+                assert lib.fnd_dp_shard_ranges(h, rank, world, lo, hi) == 3
+                for s in range(3):
+                    assert 0 <= lo[s] <= hi[s] <= n_hot and lo[s] % 4 == 0 and hi[s] % 4 == 0
+                    covered[lo[s]:hi[s]] += 1
+                assert f0.offset <= lo[0] and hi[0] <= f0.offset + f0.numel
+            assert (covered == 1).all(), f"world {world}: ranges must tile the hot arena exactly once"
+            assert lib.fnd_dp_stage_elems(h, world) >= world * ((f0.numel + world - 1) // world)
+    finally:
+        lib.fnd_plan_destroy(h)

@@ -10,8 +10,10 @@ What changes underneath:
   * the whole feature cache and the GCN embeddings live on the device as one matrix; a batch is a gather by row index
     inside the first kernel (no DataLoader / collate / .to(device) per step);
   * the six blocking D2H copies per step (:301-313) are replaced by device-side accumulation and ONE copy per epoch;
-  * with ``torch.distributed`` initialised, each global batch is sharded across ranks and gradients are all-reduced
-    (NCCL) between ``fnd_train_fwd_bwd`` and ``fnd_clip_adamw_step``.
+  * with ``torch.distributed`` initialised, each global batch is sharded across ranks; with the NCCL backend the
+    optimizer step is ``fnd_train_step_dp`` — gradient reduce-scatter out of NVLink peer memory, sharded AdamW, bf16
+    shadow all-gather (csrc/fnd_dp.cuh) — and ``FND_DP=nccl`` selects a plain gradient all-reduce between
+    ``fnd_train_fwd_bwd`` and ``fnd_clip_adamw_step`` instead.
 The data pipeline and graph construction stay the reference's (out of scope, SURVEY.md §2 #9,#14): pass a prebuilt
 ``cache`` dict, or have the reference importable as ``src.data_pipeline.fakesv_dataset``.
 """
@@ -162,8 +164,16 @@ class ForensicTrainer:
             raise RuntimeError("use_gnn=False with fusion.yaml use_gnn: true: the reference's fuse_mlp.0 is sized for 16 "
                                "slots and fails with a shape error; edit fusion.yaml as well")
         self.engine = pair_modules(self.fusion, self.clf, precision)
+        # Data parallel: identical replicas (rank 0's arena is broadcast), batches sharded by rank. With the NCCL backend
+        # the optimizer step runs sharded over NVLink peer memory (csrc/fnd_dp.cuh; FND_DP=nccl selects the plain
+        # gradient all-reduce + replicated AdamW instead).
+        self.dp_peer = False
         if self.dist:
             torch.distributed.broadcast(self.engine.params, src=0)
+            if torch.distributed.get_backend() == "nccl" and os.environ.get("FND_DP", "peer") == "peer":
+                self.engine.enable_optimizer()
+                self.engine.enable_symmetric(torch.distributed.group.WORLD)
+                self.dp_peer = True
         self.engine.set_hyper(lr=cfg.lr, weight_decay=cfg.weight_decay, max_norm=float(cfg.grad_clip or 0.0))
         self.engine.set_seed(cfg.seed + 1000003 * self.rank)
         self.use_graph = use_graph
@@ -268,11 +278,15 @@ class ForensicTrainer:
             gidx = order[start:start + bs]
             local = shard_indices(gidx, self.rank, self.world)
             if local.numel() == 0:
+                if self.dist and is_train:
+                    raise RuntimeError("data-parallel training needs at least one sample per rank in every global batch")
                 continue
             st = self._step_for(int(local.numel()), int(gidx.numel()))
             st.static_gather.copy_(local)
             if is_train:
-                if self.dist:
+                if self.dp_peer:
+                    st.train_step_dp(from_cache=True)
+                elif self.dist:
                     st.train_fwd_bwd(from_cache=True)
                     torch.distributed.all_reduce(st.engine.grads)
                     st.optimizer_step(norm_from_slots=False)
@@ -320,6 +334,8 @@ class ForensicTrainer:
             if val_auc > self.best_val_auc + 1e-4 and self.cfg.save_best:
                 self.best_val_auc = val_auc
                 self.no_improve = 0
+                if self.dp_peer:
+                    self.engine.gather_master()      # fp32 master weights are sharded between optimizer steps
                 if self.rank == 0:
                     torch.save({"fusion": {k: v.detach().cpu() for k, v in self.fusion.state_dict().items()},
                                 "clf": {k: v.detach().cpu() for k, v in self.clf.state_dict().items()},
