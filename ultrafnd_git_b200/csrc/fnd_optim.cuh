@@ -52,7 +52,7 @@ __device__ __forceinline__ void shadow_store4(const AdamWParams& a, size_t i, co
   }
 }
 
-__global__ void __launch_bounds__(256, 5) adamw_kernel(AdamWParams a) {
+__global__ void __launch_bounds__(256) adamw_kernel(AdamWParams a) {
   griddep_wait();
   griddep_launch();
   DevState* S = a.state;
@@ -60,10 +60,23 @@ __global__ void __launch_bounds__(256, 5) adamw_kernel(AdamWParams a) {
   float coef = S->clip_coef, bc1 = S->bc1, bc2 = S->bc2, norm = 0.f;
   int t = S->step;
   if (a.slots) {
+    // all 256 threads: one or two 128-bit loads each (one L2 round trip), fixed-order combine => identical everywhere
+    __shared__ double s_part[8];
     __shared__ float s_norm;
-    if (threadIdx.x < 32) {
-      const double ss = warp_reduce_slots<3>(a.slots, a.nslots);      // 3 in flight: keeps the kernel at 5 CTAs/SM
-      if (threadIdx.x == 0) s_norm = static_cast<float>(sqrt(ss));
+    double part = 0.0;
+    const int n4 = (a.nslots + 3) >> 2;                 // the slot buffer is zero beyond nslots
+    for (int i = threadIdx.x; i < n4; i += 256) {
+      const float4 t4 = __ldcg(reinterpret_cast<const float4*>(a.slots) + i);
+      part += (static_cast<double>(t4.x) + static_cast<double>(t4.y)) + (static_cast<double>(t4.z) + static_cast<double>(t4.w));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = part;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double tot = 0.0;
+      for (int w = 0; w < 8; ++w) tot += s_part[w];
+      s_norm = static_cast<float>(sqrt(tot));
     }
     __syncthreads();
     norm = s_norm;
