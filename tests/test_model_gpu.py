@@ -222,3 +222,56 @@ def test_backward_after_overwritten_forward_raises():
     module_forward(f, c, b2)
     with pytest.raises(RuntimeError, match="overwritten"):
         torch.nn.functional.cross_entropy(co1["logits"], b1["label"]).backward()
+
+
+@pytest.mark.parametrize("B", [200, 384])
+def test_large_batch_train_step_matches_oracle(B):
+    """Batches above 128 take the other code paths of the step (several M tiles, deep wgrad ring -> the one-CTA-per-SM
+    GEMM variant with finalize as a kernel of its own): one fused step vs the oracle's step, fp32 mode, dropout off."""
+    f, c, fus, clf = build_pair(42, True, "fp32", dropout_off=True)
+    f.train(); c.train(); f._sync_dropout(); c._sync_dropout()
+    batch = O.make_batch(B, seed=31)
+    step = FusedStep(f, c, B, precision="fp32", use_graph=False)
+    step.load_batch(to_cuda(batch))
+    step.train_step()
+    st = step.plan.state()
+    step.plan.check_error()
+    fo = {k: v.clone() for k, v in fus.items()}; co = {k: v.clone() for k, v in clf.items()}
+    ref = O.train_step(fo, co, batch, O.AdamWState(), dropout=0.0)
+    print(f"[B={B}] loss {st['loss']} vs {float(ref['loss'])}; norm {st['grad_norm']} vs {ref['grad_norm']}")
+    assert abs(st["loss"] - float(ref["loss"])) / float(ref["loss"]) < TOL["fp32"]
+    assert abs(st["grad_norm"] - ref["grad_norm"]) / ref["grad_norm"] < 2e-3
+    assert O.rel_err(step.logits().cpu(), ref["logits"]) < TOL["fp32"]
+    for name, mod, od in (("fuse_mlp.0.weight", f, fo), ("attn_tv.q.weight", f, fo), ("pre.0.weight", c, co), ("bypass.bias", c, co)):
+        got = dict(mod.named_parameters())[name].detach().cpu()
+        assert float((got - od[name]).abs().mean()) < 0.02 * 2e-4, name     # mean error << one lr-sized update
+
+
+def test_eval_forward_b1024_fp32_and_bf16_vs_reference_oracle():
+    """BASELINE.json configs[2]: inference-only eval forward, batch 1024, fp32 vs bf16 logits vs the reference
+    (oracle pinned to it): rel-err <= 1e-3 / 2e-2 and identical argmax predictions."""
+    B = 1024
+    batch = O.make_batch(B, seed=9)
+    ref = None
+    for precision in ("fp32", "bf16"):
+        f, c, fus, clf = build_pair(42, True, precision)
+        f.eval(); c.eval()
+        if ref is None:
+            with torch.no_grad():
+                ref = O.model_forward(fus, clf, batch)
+        step = FusedStep(f, c, B, precision=precision, use_graph=True)
+        step.load_batch(to_cuda(batch))
+        step.eval_step()
+        lg, pr = step.logits().cpu(), step.probs().cpu()
+        step.plan.check_error()
+        e = O.rel_err(lg, ref["logits"])
+        margin = (ref["logits"][:, 0] - ref["logits"][:, 1]).abs()
+        agree = (lg.argmax(-1) == ref["logits"].argmax(-1))
+        print(f"[eval B=1024/{precision}] logits rel-err {e:.2e}; argmax agreement {int(agree.sum())}/{B}; "
+              f"smallest reference margin among disagreements {float(margin[~agree].min()) if (~agree).any() else float('nan'):.2e}")
+        assert e < TOL[precision]
+        assert O.rel_err(pr, ref["probs"]) < TOL[precision]
+        # predictions identical; a flip is only tolerated on a numerical tie (|margin| below the stated tolerance of the logits)
+        assert bool(agree[margin > TOL[precision] * float(ref["logits"].abs().max())].all())
+        if precision == "fp32":
+            assert bool(agree.all())

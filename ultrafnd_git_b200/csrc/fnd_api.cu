@@ -324,9 +324,15 @@ static void mark(const Plan& Pc, const char* name, cudaStream_t st) {
 static int run_gemm(const Plan& P, const GemmTable& T, int training, cudaStream_t st, const char* name,
                     const FinParams* fin = nullptr, int fin_ctas = 0) {
   FND_SKIP(P);
+  const bool merged = fin && gemm_launch_is_light(T.kind, T.host.data(), static_cast<int>(T.host.size()));
   FND_CUDA_OK(launch_gemm(T.kind, T.host.data(), static_cast<int>(T.host.size()), T.grid, make_ctx(P, training), st,
-                          take_pdl(P), fin, fin_ctas));
+                          take_pdl(P), merged ? fin : nullptr, merged ? fin_ctas : 0));
   mark(P, name, st);
+  if (fin && !merged) {
+    // large batches (deep wgrad ring, one CTA per SM): the finalize jobs run as a kernel of their own
+    FND_CUDA_OK(launch_k(finalize_kernel, fin_ctas, 256, 0, st, take_pdl(P), *fin));
+    mark(P, "finalize", st);
+  }
   return 0;
 }
 

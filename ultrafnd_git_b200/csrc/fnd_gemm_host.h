@@ -128,6 +128,14 @@ inline int gemm_smem_bytes(const GemmProblem* host_table, int nprob) {
 
 // kind: 0 = forward (A K-major, B K-major); 1 = dgrad (A K-major, B MN-major); 2 = wgrad (both MN-major);
 // 3 = (A MN-major, B K-major). `host_table` is copied into the kernel's parameter space at launch.
+// The light variant (two CTAs per SM, trailing finalize CTAs) serves wgrad launches without split-K whose ring is
+// shallow enough for two CTAs to share an SM (contraction = batch <= 192).
+inline bool gemm_launch_is_light(int kind, const GemmProblem* host_table, int nprob) {
+  bool light = kind == 2 && gemm_smem_bytes(host_table, nprob) <= 100 * 1024;
+  for (int i = 0; i < nprob; ++i) light = light && host_table[i].splits == 1;
+  return light;
+}
+
 // `fin` (optional): finalize jobs run by `fin_ctas` trailing CTAs of the launch (light variant, see fnd_gemm.cuh).
 // The light variant is chosen for launches without split-K whose ring is shallow enough for two CTAs per SM.
 inline cudaError_t launch_gemm(int kind, const GemmProblem* host_table, int nprob, int grid, RunCtx ctx,
@@ -144,9 +152,8 @@ inline cudaError_t launch_gemm(int kind, const GemmProblem* host_table, int npro
   memset(&f, 0, sizeof(f));
   if (fin) f = *fin;
   const int smem = gemm_smem_bytes(host_table, nprob);
-  bool light = kind == 2 && smem <= 100 * 1024;
-  for (int i = 0; i < nprob; ++i) light = light && host_table[i].splits == 1;
-  if (!light && fin_ctas > 0) return cudaErrorInvalidValue;
+  if (!gemm_launch_is_light(kind, host_table, nprob) && fin_ctas > 0) return cudaErrorInvalidValue;
+  const bool light = gemm_launch_is_light(kind, host_table, nprob);
   if (light) return launch_k(fnd_gemm_kernel<1>, grid + fin_ctas, kGemmThreads, smem, st, pdl, t, ctx, f);
   return launch_k(fnd_gemm_kernel<0>, grid, kGemmThreads, smem, st, pdl, t, ctx, f);
 }
