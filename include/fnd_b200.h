@@ -131,30 +131,31 @@ int fnd_eval_step(void* plan, const fnd_inputs* in, void* stream);
 
 /* ---- data-parallel optimizer step over NVLink peer memory (batch-sharded replicas, one process per GPU) ----
  * Replaces, for N ranks, "all-reduce the gradients, then clip_grad_norm_ + AdamW on every rank"
- * (forensic_trainer.py:292-298 under a data-parallel wrapper): each rank reduces ITS 1/N slice of the gradient arena
- * directly out of every peer's memory, the clip coefficient is formed from the N slice norms in rank order
- * (bit-identical on all ranks), AdamW runs on the slice only (fp32 master / m / v stay sharded) and the refreshed
- * bf16 operand shadows + the small fp32 parameters are stored into every rank's buffers.
+ * (forensic_trainer.py:292-298 under a data-parallel wrapper). Every rank owns 1/N of the arena (its slice, three
+ * element ranges: fnd_dp_shard_ranges). Each rank stores the parts of its gradient that its peers own into their
+ * staging buffers (P2P stores over NVLink; bf16 on the wire when stage_bf16 = 1, summed in fp32), the owner adds the
+ * N pieces in rank order, the clip coefficient is formed from the N slice norms in rank order (bit-identical on all
+ * ranks), AdamW runs on the slice only (fp32 master / m / v stay sharded) and the refreshed bf16 operand shadows + the
+ * small fp32 parameters are stored into every rank's buffers.
  * Every rank places params | grads | shadow_hi | shadow_lo | a 256-byte zeroed comm pad | a staging region
- * (fnd_dp_stage_elems floats) at the SAME byte offsets of one peer-mapped (symmetric) allocation; peer_bases[p] is rank p's base address as mapped into THIS process. The
- * plan must already be bound (fnd_plan_bind) to this rank's slices. gred: local scratch of at least
- * ceil(hot/world) rounded up to 1024 floats; slots: 1024 zeroed floats.
+ * (fnd_dp_stage_bytes) at the SAME byte offsets of one peer-mapped (symmetric) allocation; peer_bases[p] is rank p's
+ * base address as mapped into THIS process. The plan must already be bound (fnd_plan_bind) to this rank's buffers.
+ * gred: local scratch of fnd_dp_stage_bytes / (world * elem size) floats; slots: 1024 zeroed floats.
  * fnd_dp_optimizer_step is stream-ordered and graph-capturable; every rank must call it once per fnd_train_fwd_bwd.
- * After it, only the OWNER of a slice holds current fp32 master weights for it (fnd_dp_shard_ranges); gather the
- * slices (e.g. one broadcast per rank) before reading a state_dict. */
+ * After it, only the OWNER of a slice holds current fp32 master weights for it; gather the slices (e.g. one broadcast
+ * per range) before reading a state_dict. */
 int fnd_dp_bind(void* plan, int rank, int world, const unsigned long long* peer_bases, long long off_params,
                 long long off_grads, long long off_shadow_hi, long long off_shadow_lo, long long off_pad,
-                long long off_stage, float* gred, long long gred_elems, float* slots, long long slots_elems);
-/* Floats the symmetric staging region (at off_stage) must hold: world slots of one rank's share of fuse_mlp.0.weight. */
-int fnd_dp_stage_elems(const void* plan, int world);
-/* The slice of [0, hot) rank `rank` owns: up to three element ranges (its shares of fuse_mlp.0.weight and of the
- * arena before / after it); returns the number of ranges written to lo3 / hi3. */
+                long long off_stage, int stage_bf16, float* gred, long long gred_elems, float* slots,
+                long long slots_elems);
+long long fnd_dp_stage_bytes(const void* plan, int world, int stage_bf16);
+/* The slice of [0, hot) rank `rank` owns: three element ranges (its shares of fuse_mlp.0/.3 weights and of the arena
+ * before / after them); returns the number of ranges written to lo3 / hi3. */
 int fnd_dp_shard_ranges(const void* plan, int rank, int world, long long* lo3, long long* hi3);
 int fnd_dp_optimizer_step(void* plan, void* stream);
-/* fnd_train_fwd_bwd + fnd_dp_optimizer_step as one call. With a non-NULL side_stream the fuse_mlp.0 weight gradient
- * (65 % of the gradient bytes) is produced early and its pieces are pushed to their owners' staging regions with
- * cudaMemcpyAsync on side_stream (copy engines) UNDER the rest of the backward pass (event fork / join; capturable
- * as one graph). */
+/* fnd_train_fwd_bwd + fnd_dp_optimizer_step as one call. With a non-NULL side_stream the fuse_mlp.0 / fuse_mlp.3 weight
+ * gradients (70 % of the gradient bytes) are produced early and pushed to their owners from side_stream UNDER the rest
+ * of the backward pass (event fork / join; capturable as one graph). */
 int fnd_train_step_dp(void* plan, const fnd_inputs* in, void* stream, void* side_stream);
 
 /* Per-kernel timing for benchmarks: between begin and end every kernel launch of this plan is followed by a

@@ -201,8 +201,8 @@ def test_dp_shard_ranges_partition_the_hot_arena():
                 for s in range(3):
                     assert 0 <= lo[s] <= hi[s] <= n_hot and lo[s] % 4 == 0 and hi[s] % 4 == 0
                     covered[lo[s]:hi[s]] += 1
-                assert f0.offset <= lo[0] and hi[0] <= f0.offset + f0.numel
+                assert f0.offset <= lo[0] and hi[0] <= table["clf.pre.0.weight"].offset
             assert (covered == 1).all(), f"world {world}: ranges must tile the hot arena exactly once"
-            assert lib.fnd_dp_stage_elems(h, world) >= world * ((f0.numel + world - 1) // world)
+            assert lib.fnd_dp_stage_bytes(h, world, 0) >= 4 * n_hot and lib.fnd_dp_stage_bytes(h, world, 1) * 2 == lib.fnd_dp_stage_bytes(h, world, 0)
     finally:
         lib.fnd_plan_destroy(h)

@@ -178,16 +178,16 @@ static int build_tables(Plan& P) {
     return 0;
   };
   {
-    // data-parallel overlap: fuse_mlp.0 alone, and everything else
-    P.wg_f0.kind = 2;
-    FND_OK(wg(P.wg_f0, tb.act("dz_f0", 0, 2 * H, true), tb.act("fused_cat", 0, catw, true), 2 * H, catw,
+    // data-parallel overlap: the early range (fuse_mlp.3, fuse_mlp.0), and everything else
+    P.wg_early.kind = 2;
+    FND_OK(wg(P.wg_early, tb.act("dz_f1", 0, H, true), tb.act("h1", 0, 2 * H, true), H, 2 * H, P.G("fusion.fuse_mlp.3.weight"), 2 * H));
+    FND_OK(wg(P.wg_early, tb.act("dz_f0", 0, 2 * H, true), tb.act("fused_cat", 0, catw, true), 2 * H, catw,
               P.G("fusion.fuse_mlp.0.weight"), catw));
     GemmTable& T = P.wg_rest;
     T.kind = 2;
     FND_OK(wg(T, tb.act("dz_p1", 0, H, true), tb.act("xp1", 0, H, true), H, H, P.G("clf.pre.3.weight"), H));
     FND_OK(wg(T, tb.act("dz_p0", 0, H, true), tb.act("fusedbf", 0, H, true), H, H, P.G("clf.pre.0.weight"), p0w));
     FND_OK(wg(T, tb.act("dFbf", 0, kDFCols, true), tb.act("hbf", 0, H, true), P.TD + 2, H, P.buf<float>("dAraw"), H));
-    FND_OK(wg(T, tb.act("dz_f1", 0, H, true), tb.act("h1", 0, 2 * H, true), H, 2 * H, P.G("fusion.fuse_mlp.3.weight"), 2 * H));
     for (int g = 0; g < 4; ++g)
       FND_OK(wg(T, tb.act("dQ", qg[g].q_col, 9 * H, true), tb.act("pbf", qg[g].in_col, 5 * H, true), qg[g].n, H,
                 P.G(std::string(qg[g].first) + ".weight"), H));
@@ -256,7 +256,7 @@ static int build_tables(Plan& P) {
 
   // ---------------- finish: CTA prefixes, slots, upload ----------------
   GemmTable* all[] = {&P.fwd_proj, &P.fwd_qkv, &P.fwd_f0, &P.fwd_f1, &P.fwd_p0, &P.fwd_p1, &P.dg_p1, &P.dg_p0_fused,
-                      &P.dg_p0_split, &P.dg_f1, &P.dg_f0, &P.dg_qkv, &P.wg_all, &P.wg_clf, &P.wg_fus, &P.wg_f0, &P.wg_rest};
+                      &P.dg_p0_split, &P.dg_f1, &P.dg_f0, &P.dg_qkv, &P.wg_all, &P.wg_clf, &P.wg_fus, &P.wg_early, &P.wg_rest};
   for (GemmTable* T : all) T->grid = finish_table(T->host.data(), static_cast<int>(T->host.size()));
   // gradient-norm slots: fused-step wgrad CTAs first (the dAraw problem writes none: its slots stay 0)
   float* slots = P.buf<float>("slots");
@@ -596,7 +596,7 @@ int fnd_plan_bind(void* plan, void* workspace, float* params, float* grads, floa
   P.sh_lo = P.ncombo == 3 ? static_cast<__nv_bfloat16*>(shadow_lo) : nullptr;
   FND_CUDA_OK(cudaMemsetAsync(P.ws, 0, static_cast<size_t>(P.ws_bytes), st));
   GemmTable* all[] = {&P.fwd_proj, &P.fwd_qkv, &P.fwd_f0, &P.fwd_f1, &P.fwd_p0, &P.fwd_p1, &P.dg_p1, &P.dg_p0_fused,
-                      &P.dg_p0_split, &P.dg_f1, &P.dg_f0, &P.dg_qkv, &P.wg_all, &P.wg_clf, &P.wg_fus, &P.wg_f0, &P.wg_rest};
+                      &P.dg_p0_split, &P.dg_f1, &P.dg_f0, &P.dg_qkv, &P.wg_all, &P.wg_clf, &P.wg_fus, &P.wg_early, &P.wg_rest};
   for (GemmTable* T : all) T->host.clear();
   P.fin_all.host.clear(); P.fin_clf.host.clear(); P.fin_fus.host.clear();
   FND_OK(build_tables(P));
@@ -770,6 +770,7 @@ int fnd_clip_adamw_step(void* plan, int norm_from_slots, void* stream) {
 // they spin on remote flags and must not become resident early.
 static const int kDpGrid = 148 * 4;
 static int dp_tail(Plan& P, bool early_done, cudaStream_t st);
+static int dp_push(Plan& P, int s0, int s1, int bank, int ctr, int grid, int block, cudaStream_t st);
 static void dp_segments(const Plan& P, int rank, int world, size_t (&lo)[kDpMaxSeg], size_t (&hi)[kDpMaxSeg]);
 
 static int train_fwd_bwd_impl(void* plan, const fnd_inputs* in, int fused_optimizer, void* stream, void* side_stream = nullptr) {
@@ -785,22 +786,15 @@ static int train_fwd_bwd_impl(void* plan, const fnd_inputs* in, int fused_optimi
   FND_OK(run_gemm(P, P.dg_p0_fused, 1, st, "dgrad_pre0"));
   FND_OK(run_gemm(P, P.dg_f1, 1, st, "dgrad_fuse1"));
   if (overlap) {
-    // Data-parallel step with overlap: the fuse_mlp.0 weight gradient (65 % of all gradient bytes) needs only dz_f0
-    // and fused_cat, so it is produced NOW and its cross-rank reduction runs on the side stream under the rest of
-    // the backward pass (fork / join through two events; capturable).
-    FND_OK(run_gemm(P, P.wg_f0, 1, st, "wgrad_fuse0"));
+    // Data-parallel step with overlap: the fuse_mlp.0 / fuse_mlp.3 weight gradients (70 % of all gradient bytes) need
+    // only dz_f0, dz_f1, h1 and fused_cat, so they are produced NOW and pushed to their owners from the side stream
+    // under the rest of the backward pass (fork / join through two events; capturable). The push uses ONE 128-thread
+    // CTA per SM and no shared memory, so a GEMM CTA (320 threads x 152 registers, 213 KB smem) still fits beside it.
+    FND_OK(run_gemm(P, P.wg_early, 1, st, "wgrad_early"));
     FND_CUDA_OK(cudaEventRecord(P.ev_fork, st));
     FND_CUDA_OK(cudaStreamWaitEvent(side, P.ev_fork, 0));
-    // push every peer's piece of this gradient into its staging slot for this rank (copy engines, no SMs)
-    for (int p = 0; p < P.dp.world; ++p) {
-      if (p == P.dp.rank) continue;
-      size_t lo[kDpMaxSeg], hi[kDpMaxSeg];
-      dp_segments(P, p, P.dp.world, lo, hi);
-      if (hi[0] > lo[0])
-        FND_CUDA_OK(cudaMemcpyAsync(P.dp.stage[p] + static_cast<size_t>(P.dp.rank) * P.dp.piece_cap, P.grads + lo[0],
-                                    (hi[0] - lo[0]) * sizeof(float), cudaMemcpyDeviceToDevice, side));
-    }
-    FND_CUDA_OK(launch_k(dp_signal_kernel, 1, 32, 0, side, false, P.dp, static_cast<int>(kPadReadyEarly)));
+    P.dp.a = adamw_params(P);
+    FND_OK(dp_push(P, 0, 1, kPadReadyEarly, kPadCounterEarly, 148, 128, side));
     FND_CUDA_OK(cudaEventRecord(P.ev_join, side));
     P.pdl_next = false;
   }
@@ -857,11 +851,12 @@ int fnd_train_step(void* plan, const fnd_inputs* in, void* stream) {
 }
 
 // ------------------------------- data-parallel optimizer step over peer memory -------------------------------
-// The hot arena [0, n_hot) is cut into three ranges — before / inside / after fuse_mlp.0.weight — and every rank owns an
-// equal share (rounded to 1024 elements) of EACH range, so that the early (fuse_mlp.0) reduction is balanced over ranks.
+// The hot arena [0, n_hot) is cut into three ranges — the "early" range fuse_mlp.0.weight + fuse_mlp.3.weight (adjacent
+// in the arena; their gradients are complete after dgrad_fuse1), the arena before it and the arena after it — and every
+// rank owns an equal share (rounded to 1024 elements) of EACH range, so that the early push is balanced over ranks.
 static void dp_segments(const Plan& P, int rank, int world, size_t (&lo)[kDpMaxSeg], size_t (&hi)[kDpMaxSeg]) {
   const size_t a0 = static_cast<size_t>(P.L.at("fusion.fuse_mlp.0.weight"));
-  const size_t a1 = a0 + static_cast<size_t>(2 * P.H) * (P.nslots * P.H);
+  const size_t a1 = static_cast<size_t>(P.L.at("clf.pre.0.weight"));
   const size_t rb[kDpMaxSeg][2] = {{a0, a1}, {0, a0}, {a1, static_cast<size_t>(P.L.n_hot)}};
   for (int s = 0; s < kDpMaxSeg; ++s) {
     const size_t n = rb[s][1] - rb[s][0];
@@ -872,18 +867,23 @@ static void dp_segments(const Plan& P, int rank, int world, size_t (&lo)[kDpMaxS
     hi[s] = rb[s][0] + (l + per < n ? l + per : n);
   }
 }
+// elements of the largest slice (rank 0's: shares are rounded up to 1024)
+static size_t dp_slot_cap(const Plan& P, int world) {
+  size_t lo[kDpMaxSeg], hi[kDpMaxSeg], n = 0;
+  dp_segments(P, 0, world, lo, hi);
+  for (int s = 0; s < kDpMaxSeg; ++s) n += hi[s] - lo[s];
+  return n;
+}
 
-int fnd_dp_stage_elems(const void* plan, int world) {
+long long fnd_dp_stage_bytes(const void* plan, int world, int bf16) {
   if (!plan || world < 1 || world > kDpMaxWorld) return -1;
   const Plan* P = static_cast<const Plan*>(plan);
-  size_t lo[kDpMaxSeg], hi[kDpMaxSeg];
-  dp_segments(*P, 0, world, lo, hi);          // rank 0's piece is the largest (pieces are rounded up to 1024)
-  return static_cast<int>((hi[0] - lo[0]) * world);
+  return static_cast<long long>(dp_slot_cap(*P, world)) * world * (bf16 ? 2 : 4);
 }
 
 int fnd_dp_bind(void* plan, int rank, int world, const unsigned long long* peer_bases, long long off_params,
                 long long off_grads, long long off_shadow_hi, long long off_shadow_lo, long long off_pad,
-                long long off_stage, float* gred, long long gred_elems, float* slots, long long slots_elems) {
+                long long off_stage, int stage_bf16, float* gred, long long gred_elems, float* slots, long long slots_elems) {
   Plan* PP = as_plan(plan);
   if (!PP || !PP->bound) return -5;
   Plan& P = *PP;
@@ -896,25 +896,23 @@ int fnd_dp_bind(void* plan, int rank, int world, const unsigned long long* peer_
     uint8_t* base = reinterpret_cast<uint8_t*>(static_cast<uintptr_t>(peer_bases[p]));
     if (!base) return -2;
     d.params[p] = reinterpret_cast<float*>(base + off_params);
-    d.grads[p] = reinterpret_cast<const float*>(base + off_grads);
     d.sh_hi[p] = reinterpret_cast<__nv_bfloat16*>(base + off_shadow_hi);
     d.sh_lo[p] = P.sh_lo ? reinterpret_cast<__nv_bfloat16*>(base + off_shadow_lo) : nullptr;
     d.pad[p] = reinterpret_cast<unsigned int*>(base + off_pad);
-    d.stage[p] = reinterpret_cast<float*>(base + off_stage);
-  }
-  {
-    size_t lo0[kDpMaxSeg], hi0[kDpMaxSeg];
-    dp_segments(P, 0, world, lo0, hi0);
-    d.piece_cap = hi0[0] - lo0[0];
+    d.stage[p] = base + off_stage;
+    dp_segments(P, p, world, d.seg_lo[p], d.seg_hi[p]);
+    size_t off = 0;
+    for (int s = 0; s < kDpMaxSeg; ++s) { d.seg_goff[p][s] = off; off += d.seg_hi[p][s] - d.seg_lo[p][s]; }
   }
   // the plan must already be bound to THIS rank's slices of the symmetric buffer
-  if (d.params[rank] != P.params || d.grads[rank] != P.grads || d.sh_hi[rank] != P.sh_hi || (P.sh_lo && d.sh_lo[rank] != P.sh_lo))
+  const float* my_grads = reinterpret_cast<const float*>(reinterpret_cast<uint8_t*>(static_cast<uintptr_t>(peer_bases[rank])) + off_grads);
+  if (d.params[rank] != P.params || my_grads != P.grads || d.sh_hi[rank] != P.sh_hi || (P.sh_lo && d.sh_lo[rank] != P.sh_lo))
     return -3;
+  d.grads = P.grads;
   d.nseg = kDpMaxSeg;
-  dp_segments(P, rank, world, d.seg_lo, d.seg_hi);
-  size_t off = 0;
-  for (int s = 0; s < kDpMaxSeg; ++s) { d.seg_goff[s] = off; off += d.seg_hi[s] - d.seg_lo[s]; }
-  if (gred_elems < static_cast<long long>(off) || slots_elems < 1024) return -4;
+  d.slot_cap = dp_slot_cap(P, world);
+  d.stage_bf16 = stage_bf16 ? 1 : 0;
+  if (gred_elems < static_cast<long long>(d.slot_cap) || slots_elems < 1024) return -4;
   d.gred = gred; d.slots = slots;
   d.a = adamw_params(P);
   P.dp = d;
@@ -935,9 +933,22 @@ int fnd_dp_shard_ranges(const void* plan, int rank, int world, long long* lo3, l
   return kDpMaxSeg;
 }
 
+static int dp_push(Plan& P, int s0, int s1, int bank, int ctr, int grid, int block, cudaStream_t st) {
+  if (P.dp.stage_bf16) FND_CUDA_OK(launch_k(dp_push_kernel<true>, grid, block, 0, st, false, P.dp, s0, s1, bank, ctr));
+  else FND_CUDA_OK(launch_k(dp_push_kernel<false>, grid, block, 0, st, false, P.dp, s0, s1, bank, ctr));
+  return 0;
+}
+
 static int dp_tail(Plan& P, bool early_done, cudaStream_t st) {
   P.dp.a = adamw_params(P);
-  FND_CUDA_OK(launch_k(dp_reduce_kernel, kDpGrid, 256, 0, st, false, P.dp, early_done ? 1 : 0));
+  if (!early_done) {
+    FND_OK(dp_push(P, 0, 1, kPadReadyEarly, kPadCounterEarly, kDpGrid, 256, st));
+    mark(P, "dp_push_early", st);
+  }
+  FND_OK(dp_push(P, 1, kDpMaxSeg, kPadReadyLate, kPadCounter, kDpGrid, 256, st));
+  mark(P, "dp_push", st);
+  if (P.dp.stage_bf16) FND_CUDA_OK(launch_k(dp_reduce_kernel<true>, kDpGrid, 256, 0, st, false, P.dp));
+  else FND_CUDA_OK(launch_k(dp_reduce_kernel<false>, kDpGrid, 256, 0, st, false, P.dp));
   mark(P, "dp_reduce", st);
   FND_CUDA_OK(launch_k(dp_adamw_kernel, kDpGrid, 256, 0, st, false, P.dp));
   mark(P, "dp_adamw", st);

@@ -3,16 +3,17 @@
 // The reference trains on one device (src/training/forensic_trainer.py:285-298); its clip_grad_norm_ + AdamW pair is
 // what this file replaces when the batch is sharded over N GPUs. Instead of "NCCL all-reduce of the 51 MB fp32 gradient,
 // then N identical AdamW passes over 357 MB each", the gradient exchange, the clip and the optimizer are ONE sharded
-// sequence over symmetric (peer-mapped) buffers:
+// sequence over symmetric (peer-mapped) buffers. Every rank owns 1/N of each of three arena ranges (its "slice"):
 //
-//   (copy engines)     the fuse_mlp.0 weight gradient (65 % of all gradient bytes) is complete two thirds of the way
-//                      through the backward pass: each rank PUSHES the pieces its peers own into their staging
-//                      buffers with cudaMemcpyAsync on a side stream (DMA engines over NVLink, no SM is taken from
-//                      the backward kernels) and then raises a flag (dp_signal_kernel);
-//   dp_reduce_kernel   rank r sums ITS 1/N slice of the gradient arena: the pushed pieces out of local staging, the
-//                      rest straight out of every peer's memory (128-bit P2P loads over NVLink/NVSwitch — a
-//                      reduce-scatter without a staging copy), keeps the reduced slice locally and publishes the
-//                      slice's sum of squares to every peer;
+//   dp_push_kernel     rank r stores, for every peer p, the part of ITS gradient that p owns into p's staging buffer
+//                      (slot r) with 128-bit P2P stores over NVLink/NVSwitch — the reduce-scatter's data movement,
+//                      sender-driven so that no handshake precedes it. It runs twice per step: for the fuse_mlp.0 /
+//                      fuse_mlp.3 weight gradients (70 % of all gradient bytes), which are complete two thirds of the way
+//                      through the backward pass and are pushed from a side stream UNDER the rest of the backward (one
+//                      small CTA per SM, so the backward's GEMM CTAs still fit), and for everything else at the end.
+//                      In bf16 mode the pieces travel as bf16 (the sum is taken in fp32);
+//   dp_reduce_kernel   rank r sums its own slice and the N-1 staged pieces in rank order (local memory only), keeps the
+//                      reduced slice and publishes the slice's sum of squares to every peer;
 //   dp_adamw_kernel    every rank adds the N partial sums in rank order (bit-identical clip coefficient everywhere),
 //                      runs AdamW on its slice only (1/N of the 357 MB optimizer stream; fp32 master, m and v stay
 //                      sharded, ZeRO-1 style) and writes the refreshed bf16 operand shadows — the only copy of the
@@ -20,11 +21,14 @@
 //                      into EVERY rank's buffers with P2P stores (the all-gather);
 //   dp_wait_kernel     blocks the stream until every peer's shadow writes have landed here.
 //
+// Measured on this pool's 8 x B200 NVSwitch box (tools/p2p_probe.py, all ranks active): P2P stores 548 GB/s per rank
+// and direction, P2P loads 480 GB/s, multimem.ld_reduce / multimem.st 550 GB/s on the limiting direction, copy-engine
+// pushes 198 GB/s — hence SM stores for the data movement, and pushes (not pulls) so the early part needs no handshake.
+//
 // Cross-GPU ordering uses epoch flags in each rank's symmetric comm pad (st.release.sys / ld.acquire.sys): a flag
 // holds the number of the last step for which the event happened, so nothing is ever reset and a captured CUDA graph
-// can be replayed. All three kernels are ordinary stream-ordered launches; they only ever wait for events that peers
-// produce without needing anything further from this rank, so the sequence cannot deadlock as long as every rank
-// runs the same steps.
+// can be replayed. The kernels only ever wait for events that peers produce without needing anything further from
+// this rank, so the sequence cannot deadlock as long as every rank runs the same steps.
 #pragma once
 #include "fnd_optim.cuh"
 
@@ -32,29 +36,30 @@ namespace fnd {
 
 constexpr int kDpMaxWorld = 8;
 constexpr int kDpMaxSeg = 3;
-// comm pad layout (uint32 words): [0,8) early-gradients-ready epochs | [8,16) all-gradients-ready | [16,24) partial
+// comm pad layout (uint32 words): [0,8) early pieces pushed (epochs) | [8,16) late pieces pushed | [16,24) partial
 // norms ready | [24,32) shadows written | [32,40) float partial sums of squares | [40] local epoch counter |
-// [41] local CTA counter | [42] float: this rank's partial of the early segment
+// [41] CTA counter of the main-stream kernels | [42] CTA counter of the early (side-stream) push
 constexpr int kPadReadyEarly = 0, kPadReadyLate = 8, kPadPartialReady = 16, kPadDone = 24, kPadPartial = 32, kPadEpoch = 40,
-              kPadCounter = 41, kPadPartialEarly = 42;
+              kPadCounter = 41, kPadCounterEarly = 42;
 constexpr int kPadWords = 64;
 
 struct DpParams {
   int rank, world;
-  const float* grads[kDpMaxWorld];        // gradient arena of every rank (peer-mapped)
-  float* params[kDpMaxWorld];             // fp32 parameter arena of every rank
+  const float* grads;                     // this rank's gradient arena
+  float* params[kDpMaxWorld];             // fp32 parameter arena of every rank (peer-mapped)
   __nv_bfloat16* sh_hi[kDpMaxWorld];      // bf16 operand shadows of every rank
   __nv_bfloat16* sh_lo[kDpMaxWorld];      // residual planes (fp32x3 mode) or null
   unsigned int* pad[kDpMaxWorld];         // comm pad of every rank
-  float* stage[kDpMaxWorld];              // staging buffer of every rank: [world][piece_cap] pushed segment-0 pieces
-  size_t piece_cap;                       // elements per staging slot
-  float* gred;                            // local: reduced gradient slice [shard_hi - shard_lo]
+  void* stage[kDpMaxWorld];               // staging buffer of every rank: [world slots][slot_cap] fp32 or bf16
+  size_t slot_cap;                        // elements per staging slot (>= the largest slice)
+  int stage_bf16;                         // 1: pieces travel as bf16
+  float* gred;                            // local: reduced gradient slice, segments back to back
   float* slots;                           // local: per-CTA sums of squares of dp_reduce_kernel
-  // This rank's slice of [0, n_hot): one piece of each of (up to) three arena ranges — segment 0 is its share of the
-  // "early" range (fuse_mlp.0.weight), segments 1 and 2 its shares of the ranges before and after it. gred holds the
-  // reduced pieces back to back (seg_goff).
+  // Slices: rank p owns [seg_lo[p][s], seg_hi[p][s]) of arena range s. Range 0 is the "early" one (fuse_mlp.0.weight and
+  // fuse_mlp.3.weight), ranges 1 and 2 the arena before and after it. Inside a staging slot / gred the three pieces of a
+  // slice lie back to back at seg_goff[p][s].
   int nseg;
-  size_t seg_lo[kDpMaxSeg], seg_hi[kDpMaxSeg], seg_goff[kDpMaxSeg];
+  size_t seg_lo[kDpMaxWorld][kDpMaxSeg], seg_hi[kDpMaxWorld][kDpMaxSeg], seg_goff[kDpMaxWorld][kDpMaxSeg];
   AdamWParams a;                          // local p / m / v / state, shadow geometry
 };
 
@@ -64,11 +69,6 @@ __device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) 
 __device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
   unsigned int v;
   asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ float4 ld_peer_f4(const float* p) {
-  float4 v;
-  asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
   return v;
 }
 // Spin until pad[base + p] >= epoch for every rank p (threads p < world of the calling warp), bounded like mbar_wait.
@@ -92,80 +92,100 @@ __device__ __forceinline__ void dp_wait_all(const unsigned int* pad, int base, i
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// 1. reduce-scatter out of peer memory + slice norm
+// 1a. push: this rank's contributions to every peer's slice -> that peer's staging slot for this rank
 // ---------------------------------------------------------------------------------------------------------------
-// One segment: W = padded world size, U = independent float4 per thread and iteration.
-// `staged`: the peers' contributions were pushed into this rank's staging buffer (segment 0 of an overlapped step).
-template <int W, int U>
-__device__ __forceinline__ float dp_reduce_segment(const DpParams& d, int sg, bool staged) {
-  const size_t n4 = (d.seg_hi[sg] - d.seg_lo[sg]) >> 2;
-  const float* src[W];
-#pragma unroll
-  for (int p = 0; p < W; ++p) {
-    src[p] = nullptr;
-    if (p < d.world)
-      src[p] = (staged && p != d.rank) ? d.stage[d.rank] + static_cast<size_t>(p) * d.piece_cap : d.grads[p] + d.seg_lo[sg];
-  }
-  float* out = d.gred + d.seg_goff[sg];
+// Segments [s0, s1); `bank` is the flag bank raised on every peer once all stores of this launch are globally visible;
+// `ctr` the pad word used to elect the last CTA (the early launch runs concurrently with main-stream kernels).
+template <bool BF16>
+__global__ void __launch_bounds__(256) dp_push_kernel(DpParams d, int s0, int s1, int bank, int ctr) {
+  __shared__ int is_last;
+  unsigned int* mypad = d.pad[d.rank];
+  const unsigned int epoch = mypad[kPadEpoch] + 1u;
   const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
-  float ss = 0.f;
-  for (size_t i4 = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i4 < n4; i4 += stride * U) {
-    float4 t[U][W];
+  const size_t tid = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  for (int sg = s0; sg < s1; ++sg) {
+    for (int q = 1; q < d.world; ++q) {
+      const int p = (d.rank + q) % d.world;            // start with a different peer on every rank: spreads the links
+      const size_t lo = d.seg_lo[p][sg], n4 = (d.seg_hi[p][sg] - lo) >> 2;
+      const float* src = d.grads + lo;
+      const size_t doff = static_cast<size_t>(d.rank) * d.slot_cap + d.seg_goff[p][sg];
+      // four independent 128-bit loads in flight per thread; the stores are fire-and-forget
+      for (size_t i4 = tid; i4 < n4; i4 += 4 * stride) {
+        float4 v[4];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const size_t j4 = i4 + u * stride;
+        for (int u = 0; u < 4; ++u)
+          if (i4 + u * stride < n4) v[u] = __ldcg(reinterpret_cast<const float4*>(src) + i4 + u * stride);
 #pragma unroll
-      for (int p = 0; p < W; ++p)
-        if (p < d.world && j4 < n4) t[u][p] = ld_peer_f4(src[p] + j4 * 4);
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const size_t j4 = i4 + u * stride;
-      if (j4 < n4) {
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-        for (int p = 0; p < W; ++p)      // summed in rank order
-          if (p < d.world) { acc.x += t[u][p].x; acc.y += t[u][p].y; acc.z += t[u][p].z; acc.w += t[u][p].w; }
-        *reinterpret_cast<float4*>(out + j4 * 4) = acc;
-        ss += (acc.x * acc.x + acc.y * acc.y) + (acc.z * acc.z + acc.w * acc.w);
+        for (int u = 0; u < 4; ++u) {
+          const size_t j4 = i4 + u * stride;
+          if (j4 < n4) {
+            if (BF16) {
+              __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(d.stage[p]) + doff;
+              *reinterpret_cast<uint2*>(dst + j4 * 4) = make_uint2(pack_bf16x2(v[u].x, v[u].y), pack_bf16x2(v[u].z, v[u].w));
+            } else {
+              float* dst = static_cast<float*>(d.stage[p]) + doff;
+              *reinterpret_cast<float4*>(dst + j4 * 4) = v[u];
+            }
+          }
+        }
       }
     }
   }
-  return ss;
-}
-
-// Raised on the side stream once this rank's pushes have been issued AND completed (stream order after the copies).
-__global__ void __launch_bounds__(32) dp_signal_kernel(DpParams d, int bank) {
-  unsigned int* mypad = d.pad[d.rank];
-  const unsigned int epoch = mypad[kPadEpoch] + 1u;
+  // every P2P store of this CTA is ordered before its counter bump; the last CTA raises the flag on every peer
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = (atomicAdd(mypad + ctr, 1u) == gridDim.x - 1) ? 1 : 0;
+  __syncthreads();
+  if (!is_last) return;
+  if (threadIdx.x == 0) mypad[ctr] = 0u;
   if (threadIdx.x < static_cast<unsigned>(d.world)) {
     __threadfence_system();
     st_release_sys(d.pad[threadIdx.x] + bank + d.rank, epoch);
   }
 }
 
-// All segments of this rank's slice. `staged` != 0: segment 0 comes out of local staging (its pieces were pushed by the
-// peers during the backward pass; wait for their kPadReadyEarly flags too).
-__global__ void __launch_bounds__(256) dp_reduce_kernel(DpParams d, int staged) {
+// ---------------------------------------------------------------------------------------------------------------
+// 1b. reduce: own slice + the staged pieces of every peer, in rank order (local memory only) + slice norm
+// ---------------------------------------------------------------------------------------------------------------
+template <bool BF16>
+__global__ void __launch_bounds__(256) dp_reduce_kernel(DpParams d) {
   __shared__ float red[8];
   __shared__ int is_last;
   unsigned int* mypad = d.pad[d.rank];
   const unsigned int epoch = mypad[kPadEpoch] + 1u;
-  // all of this rank's gradients are complete (stream order): tell every peer
-  if (blockIdx.x == 0 && threadIdx.x < static_cast<unsigned>(d.world)) {
-    __threadfence_system();
-    st_release_sys(d.pad[threadIdx.x] + kPadReadyLate + d.rank, epoch);
-  }
-  if (staged) dp_wait_all(mypad, kPadReadyEarly, d.world, epoch, &d.a.state->err);
+  dp_wait_all(mypad, kPadReadyEarly, d.world, epoch, &d.a.state->err);     // (own flags are raised by the own pushes)
   dp_wait_all(mypad, kPadReadyLate, d.world, epoch, &d.a.state->err);
-
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
   float ss = 0.f;
   for (int sg = 0; sg < d.nseg; ++sg) {
-    const bool st = staged && sg == 0;
-    // eight 128-bit loads in flight per thread whatever the world size (NVLink latency x bandwidth needs MBs in flight)
-    if (d.world <= 2) ss += dp_reduce_segment<2, 4>(d, sg, st);
-    else if (d.world <= 4) ss += dp_reduce_segment<4, 2>(d, sg, st);
-    else ss += dp_reduce_segment<8, 1>(d, sg, st);
+    const size_t lo = d.seg_lo[d.rank][sg], n4 = (d.seg_hi[d.rank][sg] - lo) >> 2;
+    const size_t goff = d.seg_goff[d.rank][sg];
+    float* out = d.gred + goff;
+    for (size_t i4 = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i4 < n4; i4 += stride) {
+      float4 t[kDpMaxWorld];
+#pragma unroll
+      for (int p = 0; p < kDpMaxWorld; ++p) {
+        if (p < d.world) {
+          if (p == d.rank) {
+            t[p] = __ldcg(reinterpret_cast<const float4*>(d.grads + lo) + i4);
+          } else if (BF16) {
+            const __nv_bfloat16* sp = static_cast<const __nv_bfloat16*>(d.stage[d.rank]) + static_cast<size_t>(p) * d.slot_cap + goff;
+            const uint2 raw = __ldcg(reinterpret_cast<const uint2*>(sp) + i4);
+            const __nv_bfloat162 a2 = *reinterpret_cast<const __nv_bfloat162*>(&raw.x), b2 = *reinterpret_cast<const __nv_bfloat162*>(&raw.y);
+            t[p] = make_float4(__low2float(a2), __high2float(a2), __low2float(b2), __high2float(b2));
+          } else {
+            const float* sp = static_cast<const float*>(d.stage[d.rank]) + static_cast<size_t>(p) * d.slot_cap + goff;
+            t[p] = __ldcg(reinterpret_cast<const float4*>(sp) + i4);
+          }
+        }
+      }
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int p = 0; p < kDpMaxWorld; ++p)      // summed in rank order
+        if (p < d.world) { acc.x += t[p].x; acc.y += t[p].y; acc.z += t[p].z; acc.w += t[p].w; }
+      *reinterpret_cast<float4*>(out + i4 * 4) = acc;
+      ss += (acc.x * acc.x + acc.y * acc.y) + (acc.z * acc.z + acc.w * acc.w);
+    }
   }
   ss = warp_sum(ss);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
@@ -264,11 +284,11 @@ __global__ void __launch_bounds__(256) dp_adamw_kernel(DpParams d) {
   const AdamWParams& a = d.a;
   const uint64_t pol = l2_policy_evict_first();
   for (int sg = 0; sg < d.nseg; ++sg) {
-  const size_t n4 = (d.seg_hi[sg] - d.seg_lo[sg]) >> 2;
-  const float* gsrc = d.gred + d.seg_goff[sg];
+  const size_t n4 = (d.seg_hi[d.rank][sg] - d.seg_lo[d.rank][sg]) >> 2;
+  const float* gsrc = d.gred + d.seg_goff[d.rank][sg];
   for (size_t i4 = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i4 < n4;
        i4 += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const size_t i = d.seg_lo[sg] + i4 * 4;
+    const size_t i = d.seg_lo[d.rank][sg] + i4 * 4;
     float4 p = ld_f4_policy(a.p + i, pol);
     const float4 g4 = *reinterpret_cast<const float4*>(gsrc + i4 * 4);
     float4 m = ld_f4_policy(a.m + i, pol);

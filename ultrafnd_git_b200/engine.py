@@ -273,10 +273,12 @@ class Engine:
         off_l = up(off_h + 2 * self.n_shadow_buf)
         off_pad = up(off_l + (2 * self.n_shadow_buf if self.mode == MODE_FP32X3 else 0))
         off_stage = off_pad + 256
-        stage_elems = self.lib.fnd_dp_stage_elems(self.any_plan().handle, world)
-        if stage_elems < 0:
-            raise _lib.FndError(f"fnd_dp_stage_elems: {stage_elems}")
-        total = off_stage + 4 * stage_elems
+        # gradients travel as bf16 in bf16 mode (summed in fp32 by the owner) unless FND_DP_GRAD=fp32; always fp32 in fp32 mode
+        stage_bf16 = int(self.mode == MODE_BF16 and os.environ.get("FND_DP_GRAD", "bf16") != "fp32")
+        stage_bytes = self.lib.fnd_dp_stage_bytes(self.any_plan().handle, world, stage_bf16)
+        if stage_bytes < 0:
+            raise _lib.FndError(f"fnd_dp_stage_bytes: {stage_bytes}")
+        total = off_stage + stage_bytes
         buf = symm.empty(total, dtype=torch.uint8, device=self.device)
         buf.zero_()
         hdl = symm.rendezvous(buf, group)
@@ -297,8 +299,8 @@ class Engine:
                         p.data = self.view(m._prefix + name)
         self.plans.clear()
         self._shadow_version = None
-        per = (self.n_hot + world - 1) // world + 3 * 1024          # three pieces, each rounded up to 1024 elements
-        self.symm = {"buf": buf, "handle": hdl, "rank": rank, "world": world, "group": group,
+        per = stage_bytes // (world * (2 if stage_bf16 else 4))      # elements of the largest slice
+        self.symm = {"buf": buf, "handle": hdl, "rank": rank, "world": world, "group": group, "stage_bf16": stage_bf16,
                      "offsets": (off_p, off_g, off_h, off_l, off_pad, off_stage),
                      "peer_bases": [int(x) for x in hdl.buffer_ptrs],
                      "gred": torch.zeros(per, dtype=torch.float32, device=self.device),
@@ -311,6 +313,7 @@ class Engine:
         bases = (ctypes.c_ulonglong * s["world"])(*s["peer_bases"])
         off_p, off_g, off_h, off_l, off_pad, off_stage = s["offsets"]
         check(self.lib.fnd_dp_bind(plan.handle, s["rank"], s["world"], bases, off_p, off_g, off_h, off_l, off_pad, off_stage,
+                                   s["stage_bf16"],
                                    s["gred"].data_ptr(), s["gred"].numel(), s["slots"].data_ptr(), s["slots"].numel()),
               "fnd_dp_bind")
 
