@@ -155,8 +155,11 @@ static int build_tables(Plan& P) {
   auto wg = [&](GemmTable& T, const Operand& dY, const Operand& X, int n_out, int k_in, float* dst, int pitch) -> int {
     EpiParams e = epi_zero();
     e.out_f32 = dst; e.f32_pitch = pitch;
+    // dAraw feeds finalize jobs that may run as trailing CTAs of the same launch: its tiles announce completion
+    if (dst == P.buf<float>("dAraw")) e.done_ctr = &P.state()->wg_done;
     return add_problem(P, T, dY, X, n_out, k_in, B, 128, 1, e, "", 0);
   };
+  const int dA_tiles = ceil_div(P.TD + 2, kGemmBM) * ceil_div(H, 128);
   auto build_wg = [&](GemmTable& T, bool clf, bool fus) -> int {
     T.kind = 2;
     if (clf) {
@@ -230,8 +233,10 @@ static int build_tables(Plan& P) {
           P.G("clf.node.trees.0.leaf_logits"), 0, 1.0f);
       job(T, kJobColsumF32, 1, 2 * H, 2 * H, P.buf<float>("dAraw") + static_cast<size_t>(P.TD) * H, nullptr, nullptr, nullptr,
           P.G("clf.bypass.weight"), 0, 1.0f);
+      T.host.back().wait_ctr = &P.state()->wg_done; T.host.back().wait_count = dA_tiles;
       job(T, kJobSoftmaxBwd, P.TD, H, H, P.buf<float>("dAraw"), nullptr, nullptr, P.buf<float>("alpha"),
           P.G("clf.node.trees.0.gates.0"), H, 1.0f);
+      T.host.back().wait_ctr = &P.state()->wg_done; T.host.back().wait_count = dA_tiles;
     }
     if (fus) {
       bfj(T, "dP", 0, P.nmod * H, 5 * H, P.G("fusion.text_proj.bias"));
@@ -354,6 +359,7 @@ static int run_prep(Plan& P, const fnd_inputs* in, int training, bool bump_clf, 
   pp.gates = P.W("clf.node.trees.0.gates.0"); pp.alpha = P.buf<float>("alpha");
   pp.TD = P.TD; pp.H = P.H;
   pp.rng = P.state()->rng; pp.bump_fusion = training ? 1 : 0; pp.bump_clf = (training && bump_clf) ? 1 : 0;
+  pp.wg_done = &P.state()->wg_done;
   FND_CUDA_OK(launch_k(prep_kernel, P.B + P.TD, kRowThreads, 0, st, take_pdl(P), pp));
   mark(P, "prep", st);
   return 0;
@@ -691,6 +697,7 @@ int fnd_classifier_forward(void* plan, const float* fused, const float* aux, int
     pp.out_hi = P.buf<__nv_bfloat16>("fusedbf_hi"); pp.out_lo = P.buf<__nv_bfloat16>("fusedbf_lo");
     pp.B = P.B; pp.gates = P.W("clf.node.trees.0.gates.0"); pp.alpha = P.buf<float>("alpha"); pp.TD = P.TD; pp.H = P.H;
     pp.rng = P.state()->rng; pp.bump_clf = training ? 1 : 0;
+    pp.wg_done = &P.state()->wg_done;
     FND_CUDA_OK(launch_k(prep_kernel, P.B + P.TD, kRowThreads, 0, st, take_pdl(P), pp));
   }
   FND_OK(classifier_gemms_impl(P, training, st));

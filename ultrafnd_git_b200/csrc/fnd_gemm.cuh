@@ -73,6 +73,7 @@ struct EpiParams {
   int bf_pitch;
   float* sumsq_slots;                // per-CTA sum of v^2 (for the global gradient norm)
   int plain_f32;                     // host-set: the epilogue is ONLY "store v as fp32 (+ sum of squares)", pitch % 8 == 0
+  unsigned int* done_ctr;            // non-null: bumped once per tile after its stores (consumers in the same launch wait on it)
 };
 
 struct alignas(128) GemmProblem {
@@ -523,6 +524,11 @@ fnd_gemm_kernel(const __grid_constant__ GemmTableP tbl, RunCtx ctx, const __grid
         const int old = atomicAdd(&ctr[1], 1);
         if (old == splits - 1) { ctr[0] = 0; ctr[1] = 0; }
       }
+    }
+    if (E.done_ctr) {
+      __threadfence();
+      epi_named_barrier();
+      if (epi_tid == 0) atomicAdd(E.done_ctr, 1u);
     }
     if (E.sumsq_slots) {
       // every epilogue thread takes part => fixed order, deterministic

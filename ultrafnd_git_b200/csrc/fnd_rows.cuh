@@ -40,7 +40,9 @@ struct DevState {
   int err;                // device error flag
   float loss_scale;       // d(loss)/d(row loss): 1 / global batch
   unsigned int fin_counter;   // finalize kernel last-CTA election
-  int pad[3];
+  unsigned int wg_done;       // tiles of the head-gradient wgrad problem (dAraw) finished in the current step: finalize
+                              // jobs that consume dAraw run in the SAME launch and wait for it (zeroed by prep_kernel)
+  int pad[2];
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -97,6 +99,7 @@ struct PrepParams {
   const float* gates;         // [TD, H] fp32 (master)
   float* alpha;               // [TD, H]
   int TD, H;
+  unsigned int* wg_done;      // DevState.wg_done, re-armed by block 0
   uint32_t* rng;              // DevState.rng; salts bumped by block 0 (a forward starts here)
   int bump_fusion, bump_clf;
 };
@@ -109,6 +112,7 @@ __global__ void __launch_bounds__(kRowThreads) prep_kernel(PrepParams p) {
   if (b == 0 && threadIdx.x == 0 && p.rng) {
     if (p.bump_fusion) p.rng[2] += 1u;
     if (p.bump_clf) p.rng[3] += 1u;
+    if (p.wg_done) *p.wg_done = 0u;
   }
   if (b < p.B) {
     const long long src = p.gather ? p.gather[b] : static_cast<long long>(b);
@@ -780,6 +784,8 @@ struct FinJob {
   float scale;
   int cta_begin, cta_count;     // 64 columns per CTA (softmax-bwd: one row per CTA; loss mean: one CTA)
   int want_norm;                // include outputs in the gradient norm
+  const unsigned int* wait_ctr; // non-null: the job's source is written by tile CTAs of the same launch — wait until
+  int wait_count;               //           *wait_ctr >= wait_count (those tiles have lower block indices: resident first)
 };
 struct FinParams {
   const FinJob* jobs;
@@ -880,6 +886,21 @@ __device__ __forceinline__ void finalize_cta(const FinParams& p, int cta, int nc
   const FinJob J = p.jobs[ji];
   const int local = cta - J.cta_begin;
   float ss = 0.f;
+  if (J.wait_ctr) {
+    if (threadIdx.x == 0) {
+      long long t0 = 0;
+      for (unsigned int spins = 1;; ++spins) {
+        if (*reinterpret_cast<const volatile unsigned int*>(J.wait_ctr) >= static_cast<unsigned int>(J.wait_count)) break;
+        if ((spins & 255u) == 0u) {
+          const long long now = clock64();
+          if (t0 == 0) t0 = now;
+          else if (now - t0 > 4000000000ll) { atomicExch(&p.state->err, 105); break; }
+        }
+      }
+      __threadfence();
+    }
+    __syncthreads();
+  }
   if (J.type == kJobLossMean) {
     // mean loss = sum(loss_row) * loss_scale   (F.cross_entropy mean reduction, forensic_trainer.py:287)
     double part = 0.0;
