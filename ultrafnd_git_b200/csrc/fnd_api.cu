@@ -795,13 +795,14 @@ static int train_fwd_bwd_impl(void* plan, const fnd_inputs* in, int fused_optimi
   if (overlap) {
     // Data-parallel step with overlap: the fuse_mlp.0 / fuse_mlp.3 weight gradients (70 % of all gradient bytes) need
     // only dz_f0, dz_f1, h1 and fused_cat, so they are produced NOW and pushed to their owners from the side stream
-    // under the rest of the backward pass (fork / join through two events; capturable). The push uses ONE 128-thread
-    // CTA per SM and no shared memory, so a GEMM CTA (320 threads x 152 registers, 213 KB smem) still fits beside it.
+    // under the rest of the backward pass (fork / join through two events; capturable). The push uses ONE 256-thread
+    // CTA per SM (64 registers, no shared memory), so a GEMM CTA (320 threads x 152 registers, 213 KB smem) still fits
+    // beside it.
     FND_OK(run_gemm(P, P.wg_early, 1, st, "wgrad_early"));
     FND_CUDA_OK(cudaEventRecord(P.ev_fork, st));
     FND_CUDA_OK(cudaStreamWaitEvent(side, P.ev_fork, 0));
     P.dp.a = adamw_params(P);
-    FND_OK(dp_push(P, 0, 1, kPadReadyEarly, kPadCounterEarly, 148, 128, side));
+    FND_OK(dp_push(P, 0, 1, kPadReadyEarly, kPadCounterEarly, 148, 256, side));
     FND_CUDA_OK(cudaEventRecord(P.ev_join, side));
     P.pdl_next = false;
   }

@@ -97,7 +97,7 @@ __device__ __forceinline__ void dp_wait_all(const unsigned int* pad, int base, i
 // Segments [s0, s1); `bank` is the flag bank raised on every peer once all stores of this launch are globally visible;
 // `ctr` the pad word used to elect the last CTA (the early launch runs concurrently with main-stream kernels).
 template <bool BF16>
-__global__ void __launch_bounds__(256) dp_push_kernel(DpParams d, int s0, int s1, int bank, int ctr) {
+__global__ void __launch_bounds__(256, 4) dp_push_kernel(DpParams d, int s0, int s1, int bank, int ctr) {
   __shared__ int is_last;
   unsigned int* mypad = d.pad[d.rank];
   const unsigned int epoch = mypad[kPadEpoch] + 1u;
@@ -215,45 +215,55 @@ __global__ void __launch_bounds__(256) dp_reduce_kernel(DpParams d) {
 // ---------------------------------------------------------------------------------------------------------------
 // 2. clip + AdamW on the slice, shadows / small parameters written to every rank
 // ---------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void dp_publish4(const DpParams& d, size_t i, const float4& x) {
+// Eight consecutive updated parameters [i, i+8) -> every rank: bf16 shadow (one 128-bit store per destination), or the
+// fp32 values themselves for the small parameters the kernels read from the arena.
+__device__ __forceinline__ void dp_publish8(const DpParams& d, size_t i, const float (&x)[8]) {
   const AdamWParams& a = d.a;
   if (i < a.n_shadow) {
-    // bf16 operand copy (hi [, lo]) of a GEMM weight -> all ranks
-    const uint32_t h0 = pack_bf16x2(x.x, x.y), h1 = pack_bf16x2(x.z, x.w);
-    uint32_t l0 = 0, l1 = 0;
+    uint4 h, l = make_uint4(0, 0, 0, 0);
+    h.x = pack_bf16x2(x[0], x[1]); h.y = pack_bf16x2(x[2], x[3]); h.z = pack_bf16x2(x[4], x[5]); h.w = pack_bf16x2(x[6], x[7]);
     if (a.sh_lo) {
-      const __nv_bfloat162 a2 = *reinterpret_cast<const __nv_bfloat162*>(&h0), b2 = *reinterpret_cast<const __nv_bfloat162*>(&h1);
-      l0 = pack_bf16x2(x.x - __low2float(a2), x.y - __high2float(a2));
-      l1 = pack_bf16x2(x.z - __low2float(b2), x.w - __high2float(b2));
+      const uint32_t hh[4] = {h.x, h.y, h.z, h.w};
+      uint32_t ll[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&hh[q]);
+        ll[q] = pack_bf16x2(x[2 * q] - __low2float(h2), x[2 * q + 1] - __high2float(h2));
+      }
+      l = make_uint4(ll[0], ll[1], ll[2], ll[3]);
     }
 #pragma unroll
-    for (int p = 0; p < kDpMaxWorld; ++p) {
-      if (p < d.world) {
-        *reinterpret_cast<uint2*>(d.sh_hi[p] + i) = make_uint2(h0, h1);
-        if (a.sh_lo) *reinterpret_cast<uint2*>(d.sh_lo[p] + i) = make_uint2(l0, l1);
+    for (int q = 0; q < kDpMaxWorld; ++q) {
+      if (q < d.world) {
+        const int p = (d.rank + q) % d.world;           // own copy first, then a different peer order on every rank
+        *reinterpret_cast<uint4*>(d.sh_hi[p] + i) = h;
+        if (a.sh_lo) *reinterpret_cast<uint4*>(d.sh_lo[p] + i) = l;
       }
     }
   } else {
-    // small fp32 parameters (biases, gates, thresholds, leaf tables, evidence MLPs) are read as fp32 by the kernels
 #pragma unroll
-    for (int p = 0; p < kDpMaxWorld; ++p)
-      if (p < d.world && p != d.rank) *reinterpret_cast<float4*>(d.params[p] + i) = x;
+    for (int q = 1; q < kDpMaxWorld; ++q) {
+      if (q < d.world) {
+        const int p = (d.rank + q) % d.world;
+        *reinterpret_cast<float4*>(d.params[p] + i) = make_float4(x[0], x[1], x[2], x[3]);
+        *reinterpret_cast<float4*>(d.params[p] + i + 4) = make_float4(x[4], x[5], x[6], x[7]);
+      }
+    }
   }
-  if (i + 4 > a.rp_begin && i < a.rp_end) {
+  if (i + 8 > a.rp_begin && i < a.rp_end) {
     // re-pitched pre.0.weight shadow (+ its fp32 aux columns, which the epilogue reads from the arena)
-    const float xs[4] = {x.x, x.y, x.z, x.w};
     const size_t rp_off = static_cast<size_t>(a.rp_hi - a.sh_hi);
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
+    for (int q = 0; q < 8; ++q) {
       const size_t e = i + q;
       if (e >= a.rp_begin && e < a.rp_end) {
         const size_t r = (e - a.rp_begin) / a.rp_cols, c = (e - a.rp_begin) % a.rp_cols;
-        __nv_bfloat16 h, l;
-        split_bf16(xs[q], h, l);
+        __nv_bfloat16 hb, lb;
+        split_bf16(x[q], hb, lb);
         for (int p = 0; p < d.world; ++p) {
-          d.sh_hi[p][rp_off + r * a.rp_pitch + c] = h;
-          if (a.sh_lo) d.sh_lo[p][rp_off + r * a.rp_pitch + c] = l;
-          if (c >= static_cast<size_t>(a.rp_cols - 2) && p != d.rank) d.params[p][e] = xs[q];
+          d.sh_hi[p][rp_off + r * a.rp_pitch + c] = hb;
+          if (a.sh_lo) d.sh_lo[p][rp_off + r * a.rp_pitch + c] = lb;
+          if (c >= static_cast<size_t>(a.rp_cols - 2) && p != d.rank) d.params[p][e] = x[q];
         }
       }
     }
@@ -282,32 +292,53 @@ __global__ void __launch_bounds__(256) dp_adamw_kernel(DpParams d) {
   const float step_size = lr / bc1;
   const float inv_sqrt_bc2 = rsqrtf(bc2);
   const AdamWParams& a = d.a;
-  const uint64_t pol = l2_policy_evict_first();
   for (int sg = 0; sg < d.nseg; ++sg) {
-  const size_t n4 = (d.seg_hi[d.rank][sg] - d.seg_lo[d.rank][sg]) >> 2;
-  const float* gsrc = d.gred + d.seg_goff[d.rank][sg];
-  for (size_t i4 = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i4 < n4;
-       i4 += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const size_t i = d.seg_lo[d.rank][sg] + i4 * 4;
-    float4 p = ld_f4_policy(a.p + i, pol);
-    const float4 g4 = *reinterpret_cast<const float4*>(gsrc + i4 * 4);
-    float4 m = ld_f4_policy(a.m + i, pol);
-    float4 v = ld_f4_policy(a.v + i, pol);
-    float* pp = &p.x; float* mp = &m.x; float* vp = &v.x; const float* gp = &g4.x;
+    const size_t n8 = (d.seg_hi[d.rank][sg] - d.seg_lo[d.rank][sg]) >> 3;      // slices are multiples of 1024 elements...
+    const size_t rem = (d.seg_hi[d.rank][sg] - d.seg_lo[d.rank][sg]) & 7;      // ...except the last rank's tail
+    const float* gsrc = d.gred + d.seg_goff[d.rank][sg];
+    for (size_t i8 = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i8 < n8 + (rem ? 1 : 0);
+         i8 += static_cast<size_t>(gridDim.x) * blockDim.x) {
+      const size_t i = d.seg_lo[d.rank][sg] + i8 * 8;
+      float p[8], g[8], m[8], v[8];
+      if (i8 < n8) {
+        ldcg_f8(a.p + i, p); ldcg_f8(gsrc + i8 * 8, g); ldcg_f8(a.m + i, m); ldcg_f8(a.v + i, v);
+      } else {                                   // 4-element tail (arena ranges are multiples of 4)
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const float g = gp[q] * coef;
-      pp[q] *= decay;
-      mp[q] = b1 * mp[q] + (1.0f - b1) * g;
-      vp[q] = b2 * vp[q] + (1.0f - b2) * g * g;
-      const float denom = sqrtf(vp[q]) * inv_sqrt_bc2 + eps;
-      pp[q] -= step_size * (mp[q] / denom);
+        for (int q = 0; q < 8; ++q) {
+          const bool ok = q < static_cast<int>(rem);
+          p[q] = ok ? a.p[i + q] : 0.f; g[q] = ok ? gsrc[i8 * 8 + q] : 0.f; m[q] = ok ? a.m[i + q] : 0.f; v[q] = ok ? a.v[i + q] : 0.f;
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float gq = g[q] * coef;
+        p[q] *= decay;
+        m[q] = b1 * m[q] + (1.0f - b1) * gq;
+        v[q] = b2 * v[q] + (1.0f - b2) * gq * gq;
+        const float denom = sqrtf(v[q]) * inv_sqrt_bc2 + eps;
+        p[q] -= step_size * (m[q] / denom);
+      }
+      if (i8 < n8) {
+        st_f8(a.p + i, p); st_f8(a.m + i, m); st_f8(a.v + i, v);
+        dp_publish8(d, i, p);
+      } else {
+        for (int q = 0; q < static_cast<int>(rem); ++q) { a.p[i + q] = p[q]; a.m[i + q] = m[q]; a.v[i + q] = v[q]; }
+        // tail: element-wise publication
+        for (int q = 0; q < static_cast<int>(rem); ++q) {
+          const size_t e = i + q;
+          for (int pr = 0; pr < d.world; ++pr) {
+            if (e < a.n_shadow) {
+              __nv_bfloat16 hb, lb;
+              split_bf16(p[q], hb, lb);
+              d.sh_hi[pr][e] = hb;
+              if (a.sh_lo) d.sh_lo[pr][e] = lb;
+            } else if (pr != d.rank) {
+              d.params[pr][e] = p[q];
+            }
+          }
+        }
+      }
     }
-    st_f4_policy(a.p + i, p, pol);
-    st_f4_policy(a.m + i, m, pol);
-    st_f4_policy(a.v + i, v, pol);
-    dp_publish4(d, i, p);
-  }
   }
   // every P2P store of this CTA is ordered before its counter bump; the last CTA tells the peers
   __threadfence_system();
