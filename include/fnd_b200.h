@@ -139,15 +139,16 @@ int fnd_eval_step(void* plan, const fnd_inputs* in, void* stream);
  * small fp32 parameters are stored into every rank's buffers.
  * Every rank places params | grads | shadow_hi | shadow_lo | a 256-byte zeroed comm pad | a staging region
  * (fnd_dp_stage_bytes) at the SAME byte offsets of one peer-mapped (symmetric) allocation; peer_bases[p] is rank p's
- * base address as mapped into THIS process. The plan must already be bound (fnd_plan_bind) to this rank's buffers.
+ * base address as mapped into THIS process; multicast_base (0 = none) is the NVSwitch multicast mapping of the same
+ * allocation — when given, the all-gather uses one multimem.st per 16 bytes instead of one store per peer. The plan must already be bound (fnd_plan_bind) to this rank's buffers.
  * gred: local scratch of fnd_dp_stage_bytes / (world * elem size) floats; slots: 1024 zeroed floats.
  * fnd_dp_optimizer_step is stream-ordered and graph-capturable; every rank must call it once per fnd_train_fwd_bwd.
  * After it, only the OWNER of a slice holds current fp32 master weights for it; gather the slices (e.g. one broadcast
  * per range) before reading a state_dict. */
 int fnd_dp_bind(void* plan, int rank, int world, const unsigned long long* peer_bases, long long off_params,
                 long long off_grads, long long off_shadow_hi, long long off_shadow_lo, long long off_pad,
-                long long off_stage, int stage_bf16, float* gred, long long gred_elems, float* slots,
-                long long slots_elems);
+                long long off_stage, int stage_bf16, unsigned long long multicast_base, float* gred,
+                long long gred_elems, float* slots, long long slots_elems);
 long long fnd_dp_stage_bytes(const void* plan, int world, int stage_bf16);
 /* The slice of [0, hot) rank `rank` owns: three element ranges (its shares of fuse_mlp.0/.3 weights and of the arena
  * before / after them); returns the number of ranges written to lo3 / hi3. */

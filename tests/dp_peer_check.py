@@ -60,6 +60,8 @@ def main():
         mine = {k: v[rank * B:(rank + 1) * B] for k, v in batches[s].items()}
         step.load_batch({k: v.to(dev) for k, v in mine.items()})
         if s % 2 == 0:
+            step.dp_overlap = (s == 2)           # step 2: early push from the side stream under the backward
+            step._graphs.pop("train_step_dp/static", None)
             step.train_step_dp()                 # one graph per rank
         else:
             step.train_fwd_bwd()                 # the two halves as separate calls

@@ -780,7 +780,8 @@ static int dp_tail(Plan& P, bool early_done, cudaStream_t st);
 static int dp_push(Plan& P, int s0, int s1, int bank, int ctr, int grid, int block, cudaStream_t st);
 static void dp_segments(const Plan& P, int rank, int world, size_t (&lo)[kDpMaxSeg], size_t (&hi)[kDpMaxSeg]);
 
-static int train_fwd_bwd_impl(void* plan, const fnd_inputs* in, int fused_optimizer, void* stream, void* side_stream = nullptr) {
+static int train_fwd_bwd_impl(void* plan, const fnd_inputs* in, int fused_optimizer, void* stream, void* side_stream = nullptr,
+                              bool skip_norm = false) {
   FND_PLAN(plan);
   if (!in || !in->labels) return -1;
   cudaStream_t side = reinterpret_cast<cudaStream_t>(side_stream);
@@ -821,7 +822,7 @@ static int train_fwd_bwd_impl(void* plan, const fnd_inputs* in, int fused_optimi
   // on the tile CTAs' critical path — measured 10 us), norm_finish_kernel otherwise.
   const FinParams f = fin_params(P, P.fin_all, P.wg_all.grid, P.total_slots, false, 0, 0);
   FND_OK(run_gemm(P, P.wg_all, 1, st, "wgrad_all", &f, P.fin_all.grid));
-  if (!fused_optimizer) {
+  if (!fused_optimizer && !skip_norm) {
     FND_SKIP(P);
     FND_CUDA_OK(launch_k(norm_finish_kernel, 1, 32, 0, st, take_pdl(P), P.buf<float>("slots"), P.total_slots, P.state(), 0));
     mark(P, "grad_norm", st);
@@ -836,7 +837,7 @@ int fnd_train_step_dp(void* plan, const fnd_inputs* in, void* stream, void* side
   if (!PP || !PP->bound) return -5;
   if (!PP->dp_bound) return -7;
   if (side_stream) return train_fwd_bwd_impl(plan, in, 0, stream, side_stream);
-  FND_OK(train_fwd_bwd_impl(plan, in, 0, stream));
+  FND_OK(train_fwd_bwd_impl(plan, in, 0, stream, nullptr, /*skip_norm: the reduced gradient's norm is what counts*/ true));
   return fnd_dp_optimizer_step(plan, stream);
 }
 
@@ -891,7 +892,8 @@ long long fnd_dp_stage_bytes(const void* plan, int world, int bf16) {
 
 int fnd_dp_bind(void* plan, int rank, int world, const unsigned long long* peer_bases, long long off_params,
                 long long off_grads, long long off_shadow_hi, long long off_shadow_lo, long long off_pad,
-                long long off_stage, int stage_bf16, float* gred, long long gred_elems, float* slots, long long slots_elems) {
+                long long off_stage, int stage_bf16, unsigned long long multicast_base, float* gred, long long gred_elems,
+                float* slots, long long slots_elems) {
   Plan* PP = as_plan(plan);
   if (!PP || !PP->bound) return -5;
   Plan& P = *PP;
@@ -917,6 +919,12 @@ int fnd_dp_bind(void* plan, int rank, int world, const unsigned long long* peer_
   if (d.params[rank] != P.params || my_grads != P.grads || d.sh_hi[rank] != P.sh_hi || (P.sh_lo && d.sh_lo[rank] != P.sh_lo))
     return -3;
   d.grads = P.grads;
+  if (multicast_base) {
+    uint8_t* mc = reinterpret_cast<uint8_t*>(static_cast<uintptr_t>(multicast_base));
+    d.mc_params = reinterpret_cast<float*>(mc + off_params);
+    d.mc_sh_hi = reinterpret_cast<__nv_bfloat16*>(mc + off_shadow_hi);
+    d.mc_sh_lo = P.sh_lo ? reinterpret_cast<__nv_bfloat16*>(mc + off_shadow_lo) : nullptr;
+  }
   d.nseg = kDpMaxSeg;
   d.slot_cap = dp_slot_cap(P, world);
   d.stage_bf16 = stage_bf16 ? 1 : 0;
@@ -949,14 +957,11 @@ static int dp_push(Plan& P, int s0, int s1, int bank, int ctr, int grid, int blo
 
 static int dp_tail(Plan& P, bool early_done, cudaStream_t st) {
   P.dp.a = adamw_params(P);
-  if (!early_done) {
-    FND_OK(dp_push(P, 0, 1, kPadReadyEarly, kPadCounterEarly, kDpGrid, 256, st));
-    mark(P, "dp_push_early", st);
-  }
-  FND_OK(dp_push(P, 1, kDpMaxSeg, kPadReadyLate, kPadCounter, kDpGrid, 256, st));
+  // without an early push, ONE launch moves all three ranges (it raises the late flags; the early bank is not used)
+  FND_OK(dp_push(P, early_done ? 1 : 0, kDpMaxSeg, kPadReadyLate, kPadCounter, kDpGrid, 256, st));
   mark(P, "dp_push", st);
-  if (P.dp.stage_bf16) FND_CUDA_OK(launch_k(dp_reduce_kernel<true>, kDpGrid, 256, 0, st, false, P.dp));
-  else FND_CUDA_OK(launch_k(dp_reduce_kernel<false>, kDpGrid, 256, 0, st, false, P.dp));
+  if (P.dp.stage_bf16) FND_CUDA_OK(launch_k(dp_reduce_kernel<true>, kDpGrid, 256, 0, st, false, P.dp, early_done ? 1 : 0));
+  else FND_CUDA_OK(launch_k(dp_reduce_kernel<false>, kDpGrid, 256, 0, st, false, P.dp, early_done ? 1 : 0));
   mark(P, "dp_reduce", st);
   FND_CUDA_OK(launch_k(dp_adamw_kernel, kDpGrid, 256, 0, st, false, P.dp));
   mark(P, "dp_adamw", st);

@@ -50,6 +50,10 @@ struct DpParams {
   __nv_bfloat16* sh_hi[kDpMaxWorld];      // bf16 operand shadows of every rank
   __nv_bfloat16* sh_lo[kDpMaxWorld];      // residual planes (fp32x3 mode) or null
   unsigned int* pad[kDpMaxWorld];         // comm pad of every rank
+  // NVSwitch multicast mappings of the same buffers (one store lands on every rank; null when the fabric has no multicast)
+  float* mc_params;
+  __nv_bfloat16* mc_sh_hi;
+  __nv_bfloat16* mc_sh_lo;
   void* stage[kDpMaxWorld];               // staging buffer of every rank: [world slots][slot_cap] fp32 or bf16
   size_t slot_cap;                        // elements per staging slot (>= the largest slice)
   int stage_bf16;                         // 1: pieces travel as bf16
@@ -147,13 +151,14 @@ __global__ void __launch_bounds__(256, 4) dp_push_kernel(DpParams d, int s0, int
 // ---------------------------------------------------------------------------------------------------------------
 // 1b. reduce: own slice + the staged pieces of every peer, in rank order (local memory only) + slice norm
 // ---------------------------------------------------------------------------------------------------------------
+// `early_used`: segment 0 was pushed by a separate (early) launch with its own flag bank.
 template <bool BF16>
-__global__ void __launch_bounds__(256) dp_reduce_kernel(DpParams d) {
+__global__ void __launch_bounds__(256) dp_reduce_kernel(DpParams d, int early_used) {
   __shared__ float red[8];
   __shared__ int is_last;
   unsigned int* mypad = d.pad[d.rank];
   const unsigned int epoch = mypad[kPadEpoch] + 1u;
-  dp_wait_all(mypad, kPadReadyEarly, d.world, epoch, &d.a.state->err);     // (own flags are raised by the own pushes)
+  if (early_used) dp_wait_all(mypad, kPadReadyEarly, d.world, epoch, &d.a.state->err);   // (own flags: raised by the own pushes)
   dp_wait_all(mypad, kPadReadyLate, d.world, epoch, &d.a.state->err);
   const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
   float ss = 0.f;
@@ -215,6 +220,12 @@ __global__ void __launch_bounds__(256) dp_reduce_kernel(DpParams d) {
 // ---------------------------------------------------------------------------------------------------------------
 // 2. clip + AdamW on the slice, shadows / small parameters written to every rank
 // ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void multimem_st16(void* mc, const uint4& v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc), "f"(__uint_as_float(v.x)),
+               "f"(__uint_as_float(v.y)), "f"(__uint_as_float(v.z)), "f"(__uint_as_float(v.w))
+               : "memory");
+}
+
 // Eight consecutive updated parameters [i, i+8) -> every rank: bf16 shadow (one 128-bit store per destination), or the
 // fp32 values themselves for the small parameters the kernels read from the arena.
 __device__ __forceinline__ void dp_publish8(const DpParams& d, size_t i, const float (&x)[8]) {
@@ -232,14 +243,24 @@ __device__ __forceinline__ void dp_publish8(const DpParams& d, size_t i, const f
       }
       l = make_uint4(ll[0], ll[1], ll[2], ll[3]);
     }
+    if (d.mc_sh_hi) {
+      // one multicast store: the switch replicates it into every rank's shadow (this rank's included)
+      multimem_st16(d.mc_sh_hi + i, h);
+      if (a.sh_lo) multimem_st16(d.mc_sh_lo + i, l);
+    } else {
 #pragma unroll
-    for (int q = 0; q < kDpMaxWorld; ++q) {
-      if (q < d.world) {
-        const int p = (d.rank + q) % d.world;           // own copy first, then a different peer order on every rank
-        *reinterpret_cast<uint4*>(d.sh_hi[p] + i) = h;
-        if (a.sh_lo) *reinterpret_cast<uint4*>(d.sh_lo[p] + i) = l;
+      for (int q = 0; q < kDpMaxWorld; ++q) {
+        if (q < d.world) {
+          const int p = (d.rank + q) % d.world;           // own copy first, then a different peer order on every rank
+          *reinterpret_cast<uint4*>(d.sh_hi[p] + i) = h;
+          if (a.sh_lo) *reinterpret_cast<uint4*>(d.sh_lo[p] + i) = l;
+        }
       }
     }
+  } else if (d.mc_params) {
+    // (rewrites this rank's own copy with the same values)
+    multimem_st16(d.mc_params + i, make_uint4(__float_as_uint(x[0]), __float_as_uint(x[1]), __float_as_uint(x[2]), __float_as_uint(x[3])));
+    multimem_st16(d.mc_params + i + 4, make_uint4(__float_as_uint(x[4]), __float_as_uint(x[5]), __float_as_uint(x[6]), __float_as_uint(x[7])));
   } else {
 #pragma unroll
     for (int q = 1; q < kDpMaxWorld; ++q) {

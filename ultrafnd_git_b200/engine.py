@@ -303,6 +303,8 @@ class Engine:
         self.symm = {"buf": buf, "handle": hdl, "rank": rank, "world": world, "group": group, "stage_bf16": stage_bf16,
                      "offsets": (off_p, off_g, off_h, off_l, off_pad, off_stage),
                      "peer_bases": [int(x) for x in hdl.buffer_ptrs],
+                     # NVSwitch multicast mapping (0 when unsupported, or when disabled with FND_DP_MULTICAST=0)
+                     "multicast": int(getattr(hdl, "multicast_ptr", 0) or 0) if os.environ.get("FND_DP_MULTICAST", "1") != "0" else 0,
                      "gred": torch.zeros(per, dtype=torch.float32, device=self.device),
                      "slots": torch.zeros(1024, dtype=torch.float32, device=self.device)}
         torch.cuda.synchronize(self.device)
@@ -313,7 +315,7 @@ class Engine:
         bases = (ctypes.c_ulonglong * s["world"])(*s["peer_bases"])
         off_p, off_g, off_h, off_l, off_pad, off_stage = s["offsets"]
         check(self.lib.fnd_dp_bind(plan.handle, s["rank"], s["world"], bases, off_p, off_g, off_h, off_l, off_pad, off_stage,
-                                   s["stage_bf16"],
+                                   s["stage_bf16"], s["multicast"],
                                    s["gred"].data_ptr(), s["gred"].numel(), s["slots"].data_ptr(), s["slots"].numel()),
               "fnd_dp_bind")
 

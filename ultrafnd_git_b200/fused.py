@@ -74,7 +74,10 @@ class FusedStep:
         self.batch = batch
         self.plan = self.engine.plan(batch)
         self.use_graph = use_graph
-        self.dp_overlap = os.environ.get("FND_DP_OVERLAP", "1") != "0"   # reduce fuse_mlp.0's gradient under the backward
+        # FND_DP_OVERLAP=1: push the fuse_mlp.0/.3 gradients from a side stream under the rest of the backward pass.
+        # Off by default: on this pool's NVSwitch boxes the one-CTA-per-SM push that fits beside the backward's GEMM CTAs
+        # reaches ~160 GB/s and finishes after the backward, while the full-grid push that follows it takes 40 us.
+        self.dp_overlap = os.environ.get("FND_DP_OVERLAP", "0") == "1"
         self._side_stream: Optional[torch.cuda.Stream] = None
         self._graphs: Dict[str, torch.cuda.CUDAGraph] = {}
         dev = self.engine.device
