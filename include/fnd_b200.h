@@ -157,7 +157,13 @@ int fnd_dp_optimizer_step(void* plan, void* stream);
 /* fnd_train_fwd_bwd + fnd_dp_optimizer_step as one call. With a non-NULL side_stream the fuse_mlp.0 / fuse_mlp.3 weight
  * gradients (70 % of the gradient bytes) are produced early and pushed to their owners from side_stream UNDER the rest
  * of the backward pass (event fork / join; capturable as one graph). */
-int fnd_train_step_dp(void* plan, const fnd_inputs* in, void* stream, void* side_stream);
+int fnd_train_step_dp(void* plan, const fnd_inputs* in, void* stream, void* side_stream, int flags);
+/* flags (need side_stream): 1 = early push as described above; 2 = DEFER the optimizer update + all-gather of the
+ * fuse_mlp.0/.3 slice (70 % of the all-gather bytes): the next fnd_train_step_dp applies it from side_stream under its
+ * first four kernels and joins before gemm_fuse0. While an update is pending the fuse_mlp shadows are one step old:
+ * call fnd_dp_flush (every rank) before anything else reads the model — an evaluation pass, a learning-rate or
+ * hyper-parameter change, gathering the master weights. fnd_dp_optimizer_step flushes by itself. */
+int fnd_dp_flush(void* plan, void* stream);
 
 /* Per-kernel timing for benchmarks: between begin and end every kernel launch of this plan is followed by a
  * cudaEvent on `stream`; end synchronises and returns, per kernel name (64-byte slots in `names`), the summed

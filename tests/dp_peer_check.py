@@ -22,7 +22,7 @@ import bench
 from ultrafnd_git_b200.fused import FusedStep
 from ultrafnd_git_b200.modules import CrossModalTransformer, DeepTruthClassifier
 
-STEPS = 3
+STEPS = 4
 B = 32
 
 
@@ -61,6 +61,7 @@ def main():
         step.load_batch({k: v.to(dev) for k, v in mine.items()})
         if s % 2 == 0:
             step.dp_overlap = (s == 2)           # step 2: early push from the side stream under the backward
+            step.dp_defer = True                 # fuse_mlp update deferred to the next step / the flush
             step._graphs.pop("train_step_dp/static", None)
             step.train_step_dp()                 # one graph per rank
         else:

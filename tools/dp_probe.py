@@ -57,8 +57,9 @@ def timed(fn, reps=50):
     return float(t.item())
 
 
-for ov in (False, True):
-    step.dp_overlap = ov
+for ov in (False, "defer"):
+    step.dp_overlap = False
+    step.dp_defer = ov == "defer"
     step.use_graph = False
     for _ in range(3):
         step.train_step_dp()

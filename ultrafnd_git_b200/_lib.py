@@ -134,7 +134,8 @@ def _signatures() -> Dict[str, tuple]:
                                  _c_void_p, ll, _c_void_p, ll]),
         "fnd_dp_stage_bytes": (ll, [_c_void_p, _c_int, _c_int]),
         "fnd_dp_shard_ranges": (_c_int, [_c_void_p, _c_int, _c_int, P(ll), P(ll)]),
-        "fnd_train_step_dp": (_c_int, [_c_void_p, P(FndInputs), _c_void_p, _c_void_p]),
+        "fnd_train_step_dp": (_c_int, [_c_void_p, P(FndInputs), _c_void_p, _c_void_p, _c_int]),
+        "fnd_dp_flush": (_c_int, [_c_void_p, _c_void_p]),
         "fnd_dp_optimizer_step": (_c_int, [_c_void_p, _c_void_p]),
         "fnd_profile_begin": (_c_int, [_c_void_p, _c_void_p]),
         "fnd_profile_end": (_c_int, [_c_void_p, _c_void_p, ctypes.c_char_p, P(_c_float), _c_int, P(_c_int)]),

@@ -482,13 +482,20 @@ static AdamWParams adamw_params(const Plan& P) {
   return a;
 }
 
-static int fusion_forward_impl(Plan& P, const fnd_inputs* in, int training, bool bump_clf, cudaStream_t st) {
+static int fusion_forward_impl(Plan& P, const fnd_inputs* in, int training, bool bump_clf, cudaStream_t st,
+                               bool join_deferred = false) {
   P.last_training = training;
   P.dbg_launch = 0;
   FND_OK(run_prep(P, in, training, bump_clf, st));
   FND_OK(run_gemm(P, P.fwd_proj, training, st, "gemm_proj"));
   FND_OK(run_gemm(P, P.fwd_qkv, training, st, "gemm_qkv"));
   FND_OK(run_assemble_fwd(P, st));
+  if (join_deferred) {
+    // the deferred all-gather of the fuse_mlp shadows (side stream) must have landed before gemm_fuse0 reads them —
+    // including its PDL-early weight loads, hence an ordinary launch
+    FND_CUDA_OK(cudaStreamWaitEvent(st, P.ev_join2, 0));
+    P.pdl_next = false;
+  }
   FND_OK(run_gemm(P, P.fwd_f0, training, st, "gemm_fuse0"));
   FND_OK(run_gemm(P, P.fwd_f1, training, st, "gemm_fuse1"));
   return 0;
@@ -776,17 +783,33 @@ int fnd_clip_adamw_step(void* plan, int norm_from_slots, void* stream) {
 // data-parallel tail (defined with the other fnd_dp_* entry points below). Its kernels are ordinary (non-PDL) launches:
 // they spin on remote flags and must not become resident early.
 static const int kDpGrid = 148 * 4;
-static int dp_tail(Plan& P, bool early_done, cudaStream_t st);
+static int dp_tail(Plan& P, bool early_done, bool defer, cudaStream_t st);
+static int dp_deferred(Plan& P, int grid, cudaStream_t st);
 static int dp_push(Plan& P, int s0, int s1, int bank, int ctr, int grid, int block, cudaStream_t st);
 static void dp_segments(const Plan& P, int rank, int world, size_t (&lo)[kDpMaxSeg], size_t (&hi)[kDpMaxSeg]);
 
+// dp_flags (data-parallel step only): bit 0 = push the early gradient range from the side stream under the backward,
+// bit 1 = defer the optimizer update / all-gather of that range to the next step (see fnd_dp.cuh).
 static int train_fwd_bwd_impl(void* plan, const fnd_inputs* in, int fused_optimizer, void* stream, void* side_stream = nullptr,
-                              bool skip_norm = false) {
+                              bool skip_norm = false, int dp_flags = 0) {
   FND_PLAN(plan);
   if (!in || !in->labels) return -1;
   cudaStream_t side = reinterpret_cast<cudaStream_t>(side_stream);
-  const bool overlap = side_stream != nullptr && P.dp_bound;
-  FND_OK(fusion_forward_impl(P, in, 1, true, st));
+  const bool overlap = side_stream != nullptr && P.dp_bound && (dp_flags & 1);
+  const bool defer = side_stream != nullptr && P.dp_bound && (dp_flags & 2);
+  if (P.dp_bound && (dp_flags || skip_norm)) {
+    // A deferred update of the previous step: run it on the side stream under the first four kernels of this forward
+    // pass (one CTA per SM, so their GEMM CTAs still fit), or right here when there is no side stream.
+    if (side_stream) {
+      FND_CUDA_OK(cudaEventRecord(P.ev_fork2, st));
+      FND_CUDA_OK(cudaStreamWaitEvent(side, P.ev_fork2, 0));
+      FND_OK(dp_deferred(P, 148, side));
+      FND_CUDA_OK(cudaEventRecord(P.ev_join2, side));
+    } else {
+      FND_OK(dp_deferred(P, kDpGrid, st));
+    }
+  }
+  FND_OK(fusion_forward_impl(P, in, 1, true, st, P.dp_bound && (dp_flags || skip_norm) && side_stream != nullptr));
   FND_OK(classifier_gemms_impl(P, 1, st));
   HeadParams h = head_params(P, 1);
   FND_OK((run_head<true, true, true>(P, h, st)));
@@ -814,7 +837,7 @@ static int train_fwd_bwd_impl(void* plan, const fnd_inputs* in, int fused_optimi
     const FinParams f = fin_params(P, P.fin_all, P.wg_rest.grid, P.total_slots, false, 0, 0);
     FND_OK(run_gemm(P, P.wg_rest, 1, st, "wgrad_rest", &f, P.fin_all.grid));
     FND_CUDA_OK(cudaStreamWaitEvent(st, P.ev_join, 0));
-    return dp_tail(P, true, st);
+    return dp_tail(P, true, defer, st);
   }
   // Weight gradients of every GEMM; the trailing CTAs of the same launch run the finalize jobs (bias / threshold /
   // leaf / evidence reductions, mean loss). Every CTA leaves its sum of squares in "slots"; whoever consumes the
@@ -832,13 +855,18 @@ static int train_fwd_bwd_impl(void* plan, const fnd_inputs* in, int fused_optimi
 
 int fnd_train_fwd_bwd(void* plan, const fnd_inputs* in, void* stream) { return train_fwd_bwd_impl(plan, in, 0, stream); }
 
-int fnd_train_step_dp(void* plan, const fnd_inputs* in, void* stream, void* side_stream) {
+int fnd_train_step_dp(void* plan, const fnd_inputs* in, void* stream, void* side_stream, int flags) {
   Plan* PP = as_plan(plan);
   if (!PP || !PP->bound) return -5;
   if (!PP->dp_bound) return -7;
-  if (side_stream) return train_fwd_bwd_impl(plan, in, 0, stream, side_stream);
-  FND_OK(train_fwd_bwd_impl(plan, in, 0, stream, nullptr, /*skip_norm: the reduced gradient's norm is what counts*/ true));
-  return fnd_dp_optimizer_step(plan, stream);
+  if (!side_stream) flags = 0;
+  if (flags & 1) return train_fwd_bwd_impl(plan, in, 0, stream, side_stream, true, flags);
+  // (skip_norm: the reduced gradient's norm is what counts)
+  FND_OK(train_fwd_bwd_impl(plan, in, 0, stream, side_stream, true, flags));
+  Plan& P = *PP;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  P.pdl_next = false;
+  return dp_tail(P, false, (flags & 2) != 0, st);
 }
 
 int fnd_train_step(void* plan, const fnd_inputs* in, void* stream) {
@@ -936,6 +964,8 @@ int fnd_dp_bind(void* plan, int rank, int world, const unsigned long long* peer_
   if (!P.ev_fork) {
     FND_CUDA_OK(cudaEventCreateWithFlags(&P.ev_fork, cudaEventDisableTiming));
     FND_CUDA_OK(cudaEventCreateWithFlags(&P.ev_join, cudaEventDisableTiming));
+    FND_CUDA_OK(cudaEventCreateWithFlags(&P.ev_fork2, cudaEventDisableTiming));
+    FND_CUDA_OK(cudaEventCreateWithFlags(&P.ev_join2, cudaEventDisableTiming));
   }
   return 0;
 }
@@ -955,7 +985,16 @@ static int dp_push(Plan& P, int s0, int s1, int bank, int ctr, int grid, int blo
   return 0;
 }
 
-static int dp_tail(Plan& P, bool early_done, cudaStream_t st) {
+// The deferred (range 0) optimizer launch + the wait for every peer's deferred shadows. No-op on the device when nothing
+// is pending.
+static int dp_deferred(Plan& P, int grid, cudaStream_t st) {
+  P.dp.a = adamw_params(P);
+  FND_CUDA_OK(launch_k(dp_adamw_kernel, grid, 256, 0, st, false, P.dp, 0, 1, 1, static_cast<int>(kPadCounterEarly)));
+  FND_CUDA_OK(launch_k(dp_wait_kernel, 1, 32, 0, st, false, P.dp, 1));
+  return 0;
+}
+
+static int dp_tail(Plan& P, bool early_done, bool defer, cudaStream_t st) {
   P.dp.a = adamw_params(P);
   // without an early push, ONE launch moves all three ranges (it raises the late flags; the early bank is not used)
   FND_OK(dp_push(P, early_done ? 1 : 0, kDpMaxSeg, kPadReadyLate, kPadCounter, kDpGrid, 256, st));
@@ -963,9 +1002,10 @@ static int dp_tail(Plan& P, bool early_done, cudaStream_t st) {
   if (P.dp.stage_bf16) FND_CUDA_OK(launch_k(dp_reduce_kernel<true>, kDpGrid, 256, 0, st, false, P.dp, early_done ? 1 : 0));
   else FND_CUDA_OK(launch_k(dp_reduce_kernel<false>, kDpGrid, 256, 0, st, false, P.dp, early_done ? 1 : 0));
   mark(P, "dp_reduce", st);
-  FND_CUDA_OK(launch_k(dp_adamw_kernel, kDpGrid, 256, 0, st, false, P.dp));
+  FND_CUDA_OK(launch_k(dp_adamw_kernel, kDpGrid, 256, 0, st, false, P.dp, defer ? 1 : 0, static_cast<int>(kDpMaxSeg), 0,
+                       static_cast<int>(kPadCounter)));
   mark(P, "dp_adamw", st);
-  FND_CUDA_OK(launch_k(dp_wait_kernel, 1, 32, 0, st, false, P.dp));
+  FND_CUDA_OK(launch_k(dp_wait_kernel, 1, 32, 0, st, false, P.dp, 0));
   mark(P, "dp_wait", st);
   return 0;
 }
@@ -973,7 +1013,14 @@ static int dp_tail(Plan& P, bool early_done, cudaStream_t st) {
 int fnd_dp_optimizer_step(void* plan, void* stream) {
   FND_PLAN(plan);
   if (!P.dp_bound) return -7;
-  return dp_tail(P, false, st);
+  FND_OK(dp_deferred(P, kDpGrid, st));          // a deferred update of an earlier step must land first
+  return dp_tail(P, false, false, st);
+}
+
+int fnd_dp_flush(void* plan, void* stream) {
+  FND_PLAN(plan);
+  if (!P.dp_bound) return -7;
+  return dp_deferred(P, kDpGrid, st);
 }
 
 int fnd_eval_step(void* plan, const fnd_inputs* in, void* stream) {

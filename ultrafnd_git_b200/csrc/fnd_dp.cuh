@@ -21,6 +21,13 @@
 //                      into EVERY rank's buffers with P2P stores (the all-gather);
 //   dp_wait_kernel     blocks the stream until every peer's shadow writes have landed here.
 //
+// Deferred update (optional): 70 % of the all-gather bytes belong to fuse_mlp.0 / fuse_mlp.3, whose weights are first
+// read by the FIFTH kernel of the next forward pass. With deferral the optimizer step above covers only the other two
+// ranges; the fuse_mlp slice is updated and all-gathered by a second dp_adamw_kernel launch that the NEXT training step
+// starts on a side stream and joins right before gemm_fuse0 — the all-gather runs under prep / projections / q-k-v /
+// assemble instead of on the critical path. fnd_dp_flush applies a pending deferred update immediately (before an
+// evaluation pass, a learning-rate change or a state_dict read).
+//
 // Measured on this pool's 8 x B200 NVSwitch box (tools/p2p_probe.py, all ranks active): P2P stores 548 GB/s per rank
 // and direction, P2P loads 480 GB/s, multimem.ld_reduce / multimem.st 550 GB/s on the limiting direction, copy-engine
 // pushes 198 GB/s — hence SM stores for the data movement, and pushes (not pulls) so the early part needs no handshake.
@@ -39,8 +46,9 @@ constexpr int kDpMaxSeg = 3;
 // comm pad layout (uint32 words): [0,8) early pieces pushed (epochs) | [8,16) late pieces pushed | [16,24) partial
 // norms ready | [24,32) shadows written | [32,40) float partial sums of squares | [40] local epoch counter |
 // [41] CTA counter of the main-stream kernels | [42] CTA counter of the early (side-stream) push
+// [43] pending: epoch whose deferred (range 0) update has not been applied yet, 0 = none | [48,56) deferred shadows written
 constexpr int kPadReadyEarly = 0, kPadReadyLate = 8, kPadPartialReady = 16, kPadDone = 24, kPadPartial = 32, kPadEpoch = 40,
-              kPadCounter = 41, kPadCounterEarly = 42;
+              kPadCounter = 41, kPadCounterEarly = 42, kPadPending = 43, kPadDoneDeferred = 48;
 constexpr int kPadWords = 64;
 
 struct DpParams {
@@ -291,29 +299,50 @@ __device__ __forceinline__ void dp_publish8(const DpParams& d, size_t i, const f
   }
 }
 
-__global__ void __launch_bounds__(256) dp_adamw_kernel(DpParams d) {
+// mode 0: the step's optimizer launch over segments [s0, s1): waits for the partial norms, forms the clip coefficient,
+//         publishes norm / coefficient / step, raises kPadDone; when s0 > 0 it marks range 0 as pending (deferred).
+// mode 1: the deferred launch over segment 0 (next step's side stream, or fnd_dp_flush): no-op unless pending; uses the
+//         coefficient and bias corrections published by the mode-0 launch of the same optimizer step; raises
+//         kPadDoneDeferred (always) and clears the pending mark. `ctr` = pad word used to elect the last CTA.
+__global__ void __launch_bounds__(256) dp_adamw_kernel(DpParams d, int s0, int s1, int mode, int ctr) {
   __shared__ float s_norm;
   __shared__ int is_last;
   unsigned int* mypad = d.pad[d.rank];
-  const unsigned int epoch = mypad[kPadEpoch] + 1u;
   DevState* S = d.a.state;
-  dp_wait_all(mypad, kPadPartialReady, d.world, epoch, &S->err);
-  if (threadIdx.x == 0) {
-    double tot = 0.0;
-    for (int p = 0; p < d.world; ++p) tot += static_cast<double>(reinterpret_cast<volatile float*>(mypad)[kPadPartial + p]);
-    s_norm = static_cast<float>(sqrt(tot));
-  }
-  __syncthreads();
-  const float norm = s_norm;
-  const float coef = clip_coef_of(S->max_norm, norm);
+  unsigned int epoch;
+  float norm = 0.f, coef, bc1, bc2;
+  int t = 0;
   const float lr = S->lr, b1 = S->beta1, b2 = S->beta2, eps = S->eps;
-  const int t = S->step + 1;
-  const float bc1 = 1.0f - powf(b1, static_cast<float>(t)), bc2 = 1.0f - powf(b2, static_cast<float>(t));
+  if (mode == 0) {
+    epoch = mypad[kPadEpoch] + 1u;
+    dp_wait_all(mypad, kPadPartialReady, d.world, epoch, &S->err);
+    if (threadIdx.x == 0) {
+      double tot = 0.0;
+      for (int p = 0; p < d.world; ++p) tot += static_cast<double>(reinterpret_cast<volatile float*>(mypad)[kPadPartial + p]);
+      s_norm = static_cast<float>(sqrt(tot));
+    }
+    __syncthreads();
+    norm = s_norm;
+    coef = clip_coef_of(S->max_norm, norm);
+    t = S->step + 1;
+    bc1 = 1.0f - powf(b1, static_cast<float>(t));
+    bc2 = 1.0f - powf(b2, static_cast<float>(t));
+  } else {
+    // kPadDoneDeferred flags mean "this rank has no deferred update pending for epochs <= value": raise them with the
+    // last completed epoch whether or not there was work (every rank runs this launch at the same points)
+    epoch = mypad[kPadEpoch];
+    if (mypad[kPadPending] == 0u) {          // nothing deferred (first step, or already flushed): uniform over the grid
+      if (blockIdx.x == 0 && threadIdx.x < static_cast<unsigned>(d.world))
+        st_release_sys(d.pad[threadIdx.x] + kPadDoneDeferred + d.rank, epoch);
+      return;
+    }
+    coef = S->clip_coef; bc1 = S->bc1; bc2 = S->bc2;
+  }
   const float decay = 1.0f - lr * S->weight_decay;
   const float step_size = lr / bc1;
   const float inv_sqrt_bc2 = rsqrtf(bc2);
   const AdamWParams& a = d.a;
-  for (int sg = 0; sg < d.nseg; ++sg) {
+  for (int sg = s0; sg < s1; ++sg) {
     const size_t n8 = (d.seg_hi[d.rank][sg] - d.seg_lo[d.rank][sg]) >> 3;      // slices are multiples of 1024 elements...
     const size_t rem = (d.seg_hi[d.rank][sg] - d.seg_lo[d.rank][sg]) & 7;      // ...except the last rank's tail
     const float* gsrc = d.gred + d.seg_goff[d.rank][sg];
@@ -364,24 +393,36 @@ __global__ void __launch_bounds__(256) dp_adamw_kernel(DpParams d) {
   // every P2P store of this CTA is ordered before its counter bump; the last CTA tells the peers
   __threadfence_system();
   __syncthreads();
-  if (threadIdx.x == 0) is_last = (atomicAdd(mypad + kPadCounter, 1u) == gridDim.x - 1) ? 1 : 0;
+  if (threadIdx.x == 0) is_last = (atomicAdd(mypad + ctr, 1u) == gridDim.x - 1) ? 1 : 0;
   __syncthreads();
   if (!is_last) return;
   if (threadIdx.x == 0) {
-    S->grad_norm = norm; S->clip_coef = coef; S->step = t; S->bc1 = bc1; S->bc2 = bc2;
-    mypad[kPadCounter] = 0u;
+    if (mode == 0) {
+      S->grad_norm = norm; S->clip_coef = coef; S->step = t; S->bc1 = bc1; S->bc2 = bc2;
+      mypad[kPadPending] = s0 > 0 ? epoch : 0u;
+    } else {
+      mypad[kPadPending] = 0u;
+    }
+    mypad[ctr] = 0u;
   }
   if (threadIdx.x < static_cast<unsigned>(d.world)) {
     __threadfence_system();
-    st_release_sys(d.pad[threadIdx.x] + kPadDone + d.rank, epoch);
+    st_release_sys(d.pad[threadIdx.x] + (mode == 0 ? kPadDone : kPadDoneDeferred) + d.rank, epoch);
   }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
 // 3. wait for every peer's shadow / parameter writes, then advance the local epoch
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(32) dp_wait_kernel(DpParams d) {
+// deferred = 0: end of an optimizer step (waits kPadDone for the running epoch, then advances the local epoch);
+// deferred = 1: after a deferred launch (waits until every peer's deferred shadows of the LAST COMPLETED epoch are here;
+//               trivially satisfied when nothing was deferred, because every rank defers or flushes in lockstep).
+__global__ void __launch_bounds__(32) dp_wait_kernel(DpParams d, int deferred) {
   unsigned int* mypad = d.pad[d.rank];
+  if (deferred) {
+    dp_wait_all(mypad, kPadDoneDeferred, d.world, mypad[kPadEpoch], &d.a.state->err);
+    return;
+  }
   const unsigned int epoch = mypad[kPadEpoch] + 1u;
   dp_wait_all(mypad, kPadDone, d.world, epoch, &d.a.state->err);
   if (threadIdx.x == 0) mypad[kPadEpoch] = epoch;

@@ -199,7 +199,8 @@ struct Plan {
   GemmTable fwd_proj, fwd_qkv, fwd_f0, fwd_f1, fwd_p0, fwd_p1;
   GemmTable dg_p1, dg_p0_fused, dg_p0_split, dg_f1, dg_f0, dg_qkv;
   GemmTable wg_all, wg_clf, wg_fus, wg_early, wg_rest;
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;   // data-parallel overlap: side-stream fork / join
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;   // data-parallel overlap: side-stream fork / join (early push)
+  cudaEvent_t ev_fork2 = nullptr, ev_join2 = nullptr; // ... and for the deferred update at the start of a step
   FinTable fin_all, fin_clf, fin_fus;
   int total_slots = 0;
   // optional per-kernel timing (bench/profiling only): an event is recorded after every launch

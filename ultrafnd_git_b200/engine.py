@@ -220,6 +220,8 @@ class Engine:
         self._shadow_version: Optional[int] = None
         self.attached: list = []          # weakrefs to the nn.Modules whose parameters live in this arena
         self.symm: Optional[dict] = None  # peer-mapped buffers of the data-parallel optimizer step (enable_symmetric)
+        self._dp_pending = False          # a deferred fuse_mlp update of the last train_step_dp has not been applied yet
+        self._dp_plan: Optional["Plan"] = None
         self._alloc_device_buffers()
 
     def param_version(self) -> int:
@@ -326,6 +328,12 @@ class Engine:
             raise _lib.FndError(f"fnd_dp_shard_ranges: {n}")
         return [(lo[i], hi[i]) for i in range(n)]
 
+    def dp_flush(self) -> None:
+        """Apply a pending deferred data-parallel update now (every rank must call this at the same point)."""
+        if self._dp_pending and self._dp_plan is not None:
+            check(self.lib.fnd_dp_flush(self._dp_plan.handle, self.stream_ptr()), "fnd_dp_flush")
+        self._dp_pending = False
+
     def gather_master(self) -> None:
         """After sharded optimizer steps only the owner of a slice holds current fp32 master weights: broadcast every
         slice from its owner so that ``state_dict()`` / checkpoints see the full model on every rank."""
@@ -333,6 +341,7 @@ class Engine:
         s = getattr(self, "symm", None)
         if s is None:
             return
+        self.dp_flush()
         for r in range(s["world"]):
             for lo, hi in self.shard_ranges(r):
                 if hi > lo:
@@ -412,6 +421,7 @@ class Engine:
             self.refresh_shadows(version)
 
     def set_hyper(self, **kw) -> None:
+        self.dp_flush()
         self.hyper.update(kw)
         for p in self.plans.values():
             h = self.hyper
@@ -419,6 +429,7 @@ class Engine:
                                          h["max_norm"], self.stream_ptr()), "fnd_set_hyper")
 
     def set_lr(self, lr: float) -> None:
+        self.dp_flush()
         self.hyper["lr"] = lr
         for p in self.plans.values():
             check(self.lib.fnd_set_lr(p.handle, lr, self.stream_ptr()), "fnd_set_lr")

@@ -78,6 +78,9 @@ class FusedStep:
         # Off by default: on this pool's NVSwitch boxes the one-CTA-per-SM push that fits beside the backward's GEMM CTAs
         # reaches ~160 GB/s and finishes after the backward, while the full-grid push that follows it takes 40 us.
         self.dp_overlap = os.environ.get("FND_DP_OVERLAP", "0") == "1"
+        # FND_DP_DEFER=0 disables the deferred update + all-gather of the fuse_mlp slice (applied by the next step under
+        # its first four kernels; flushed automatically before any other entry point, lr change or state_dict read).
+        self.dp_defer = os.environ.get("FND_DP_DEFER", "1") != "0"
         self._side_stream: Optional[torch.cuda.Stream] = None
         self._graphs: Dict[str, torch.cuda.CUDAGraph] = {}
         dev = self.engine.device
@@ -143,12 +146,13 @@ class FusedStep:
     def _run(self, entry: str, inp: FndInputs) -> None:
         lib, h = self.engine.lib, self.plan.handle
         if entry == "train_step_dp":      # forward + backward + the sharded peer-memory optimizer step
+            flags = (1 if self.dp_overlap else 0) | (2 if self.dp_defer else 0)
             side = None
-            if self.dp_overlap:
+            if flags:
                 if self._side_stream is None:
                     self._side_stream = torch.cuda.Stream(self.engine.device)
                 side = self._side_stream.cuda_stream
-            check(lib.fnd_train_step_dp(h, ctypes.byref(inp), self.engine.stream_ptr(), side), "fnd_train_step_dp")
+            check(lib.fnd_train_step_dp(h, ctypes.byref(inp), self.engine.stream_ptr(), side, flags), "fnd_train_step_dp")
             return
         fn = {"train_step": lib.fnd_train_step, "train_fwd_bwd": lib.fnd_train_fwd_bwd, "eval_step": lib.fnd_eval_step}[entry]
         check(fn(h, ctypes.byref(inp), self.engine.stream_ptr()), "fnd_" + entry)
@@ -157,6 +161,8 @@ class FusedStep:
         inp = self._inp_cache if from_cache else self._inp_static
         if inp is None:
             raise RuntimeError("attach_cache() first")
+        if entry != "train_step_dp":
+            self.engine.dp_flush()        # a deferred data-parallel update must land before anything else reads the model
         if not self.use_graph:
             self._run(entry, inp)
             return
@@ -187,7 +193,9 @@ class FusedStep:
         if not getattr(self, "_dp_bound", False):
             self.engine.dp_bind(self.plan)
             self._dp_bound = True
+        self.engine._dp_plan = self.plan
         self._launch("train_step_dp", from_cache)
+        self.engine._dp_pending = self.dp_defer
         self.plan.forward_id += 1
 
     def train_fwd_bwd(self, from_cache: bool = False) -> None:
