@@ -78,9 +78,11 @@ class FusedStep:
         # Off by default: on this pool's NVSwitch boxes the one-CTA-per-SM push that fits beside the backward's GEMM CTAs
         # reaches ~160 GB/s and finishes after the backward, while the full-grid push that follows it takes 40 us.
         self.dp_overlap = os.environ.get("FND_DP_OVERLAP", "0") == "1"
-        # FND_DP_DEFER=0 disables the deferred update + all-gather of the fuse_mlp slice (applied by the next step under
-        # its first four kernels; flushed automatically before any other entry point, lr change or state_dict read).
-        self.dp_defer = os.environ.get("FND_DP_DEFER", "1") != "0"
+        # FND_DP_DEFER=1: defer the update + all-gather of the fuse_mlp slice to the next step's side stream (under its
+        # first four kernels; flushed automatically before any other entry point, lr change or state_dict read). Off by
+        # default: measured on 8 GPUs the side-stream kernel slows the latency-bound forward chain as much as it saves
+        # (321 vs 316 us/step), like the early push.
+        self.dp_defer = os.environ.get("FND_DP_DEFER", "0") == "1"
         self._side_stream: Optional[torch.cuda.Stream] = None
         self._graphs: Dict[str, torch.cuda.CUDAGraph] = {}
         dev = self.engine.device
