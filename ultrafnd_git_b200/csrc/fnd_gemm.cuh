@@ -72,7 +72,8 @@ struct EpiParams {
   __nv_bfloat16* out_lo;
   int bf_pitch;
   float* sumsq_slots;                // per-CTA sum of v^2 (for the global gradient norm)
-  int plain_f32;                     // host-set: the epilogue is ONLY "store v as fp32 (+ sum of squares)", pitch % 8 == 0
+  int plain_f32;                     // host-set: the epilogue is ONLY "store v as fp32 (+ sum of squares)", pitch % 8 == 0;
+                                     // 2 = additionally the operand ring is large enough to stage the tile for coalesced stores
   unsigned int* done_ctr;            // non-null: bumped once per tile after its stores (consumers in the same launch wait on it)
 };
 
@@ -402,8 +403,45 @@ fnd_gemm_kernel(const __grid_constant__ GemmTableP tbl, RunCtx ctx, const __grid
         a1 = E.aux[static_cast<size_t>(m) * 2 + 1];
       }
       if (epi_tid == 0) FND_STAMP(5);
-      if (E.plain_f32 && bn >= 64) {
-        // Store-only epilogue (weight gradients, dcat): 32 accumulator columns per tcgen05.ld, four 256-bit stores.
+      if (E.plain_f32 == 2 && bn >= 64) {
+        // Store-only epilogue (weight gradients, dcat), coalesced: a thread owns a ROW of the accumulator, so storing
+        // straight from registers makes every warp-level store touch 32 different 128-byte lines (two LSU wavefronts
+        // per lane: the 780-tile wgrad launch was LSU-bound, ncu). Instead each warp transposes its 32x32 block through
+        // shared memory (the operand ring is dead once the accumulator is complete) and writes 4 full rows x 128 B
+        // per instruction.
+        constexpr int kStgPitch = 36;                                  // floats per staged row (16-byte aligned, conflict-free)
+        float* stg = reinterpret_cast<float*>(smem) + ew * (32 * kStgPitch);
+        const int c_end = (half + 1) * (bn >> 1);
+        const int rsub = lane >> 3, csub = (lane & 7) * 4;
+#pragma unroll 1
+        for (int c = half * (bn >> 1); c < c_end; c += 32) {
+          uint32_t r[32];
+          tmem_ld_32x32(taddr + c, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 v4 = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]),
+                                          __uint_as_float(r[4 * q + 3]));
+            *reinterpret_cast<float4*>(stg + lane * kStgPitch + 4 * q) = v4;
+            if (proceed && row_ok && nb + c + 4 * q < PN)
+              ss = fmaf(v4.x, v4.x, fmaf(v4.y, v4.y, fmaf(v4.z, v4.z, fmaf(v4.w, v4.w, ss))));
+          }
+          __syncwarp();
+          const int n = nb + c + csub;
+          if (proceed && n < PN) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const int rr = k * 4 + rsub;
+              const int mm = tm * kGemmBM + lane_grp * 32 + rr;
+              if (mm < PM)
+                *reinterpret_cast<float4*>(E.out_f32 + static_cast<size_t>(mm) * E.f32_pitch + n) =
+                    *reinterpret_cast<const float4*>(stg + rr * kStgPitch + csub);
+            }
+          }
+          __syncwarp();
+        }
+      } else if (E.plain_f32 && bn >= 64) {
+        // Store-only epilogue, direct: 32 accumulator columns per tcgen05.ld, four 256-bit stores per thread.
         // Each warp of a lane quarter takes one contiguous half of the tile's columns.
         const int c_end = (half + 1) * (bn >> 1);
 #pragma unroll 1
