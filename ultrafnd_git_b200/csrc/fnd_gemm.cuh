@@ -204,7 +204,7 @@ __device__ __forceinline__ float epi_group(const EpiParams& E, const EpiCtx& X, 
 //             k-loop), and the trailing CTAs [gemm_ctas, gridDim.x) run the finalize jobs (bias / threshold / leaf /
 //             evidence gradient reductions, fnd_rows.cuh) concurrently with the tiles instead of in a kernel of their own.
 template <int kVariant>
-__global__ void __launch_bounds__(kGemmThreads, kVariant == 1 ? 3 : 1)
+__global__ void __launch_bounds__(kGemmThreads, kVariant == 1 ? 2 : 1)
 fnd_gemm_kernel(const __grid_constant__ GemmTableP tbl, RunCtx ctx, const __grid_constant__ FinParams fin) {
   if (kVariant == 1 && static_cast<int>(blockIdx.x) >= tbl.gemm_ctas) {
     griddep_wait();
