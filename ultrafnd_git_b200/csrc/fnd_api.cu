@@ -148,7 +148,8 @@ static int build_tables(Plan& P) {
     e.out_lo = P.buf<__nv_bfloat16>("dP_lo") ? P.buf<__nv_bfloat16>("dP_lo") + qg[g].in_col : nullptr;
     e.bf_pitch = 5 * H;
     FND_OK(add_problem(P, P.dg_qkv, tb.act("dQ", qg[g].q_col, 9 * H, false),
-                       tb.weight(std::string(qg[g].first) + ".weight", H, true), B, H, qg[g].n, P.cfg_dg_qkv.bn, 1, e, "", 1));
+                       tb.weight(std::string(qg[g].first) + ".weight", H, true), B, H, qg[g].n, P.cfg_dg_qkv.bn,
+                       P.cfg_dg_qkv.splits, e, "dgqkv" + std::to_string(g), 1));
   }
 
   // ---------------- wgrad (dW[N_out, K_in] = dY^T X; both operands MN-major; contraction = batch) -------------

@@ -167,8 +167,9 @@ inline GemmCfg pick_cfg(int B, const std::vector<std::pair<int, int>>& nk, bool 
   }
   const int ctas = ctas_at(c.bn);
   const long long per_cta = static_cast<long long>(kb) * ncombo * (kGemmStageBytesA + c.bn * kGemmBK * 2);
-  if (allow_split && nk.size() == 1 && per_cta > 600 * 1024) {
-    int sp = static_cast<int>(per_cta / (256 * 1024));
+  // (a CTA ingests ~55 GB/s through TMA in 128-byte rows; the split-K exchange costs ~2.5 us = ~140 KB of streaming)
+  if (allow_split && per_cta > 400 * 1024) {
+    int sp = static_cast<int>(per_cta / (128 * 1024));
     if (sp > 148 / ctas) sp = 148 / ctas;
     if (sp > 16) sp = 16;
     if (sp > c.bn / 2) sp = c.bn / 2;
@@ -294,7 +295,7 @@ inline void carve(Plan& P) {
     P.cfg_dg_pre = pick_cfg(P.B, {{Hh, Hh}}, true, nc, false);
     P.cfg_dg_f1 = pick_cfg(P.B, {{2 * Hh, Hh}}, true, nc, true);
     P.cfg_dg_f0 = pick_cfg(P.B, {{cat, 2 * Hh}}, true, nc, true);
-    P.cfg_dg_qkv = pick_cfg(P.B, {{Hh, 2 * Hh}, {Hh, 3 * Hh}, {Hh, 2 * Hh}, {Hh, 2 * Hh}}, true, nc, false);
+    P.cfg_dg_qkv = pick_cfg(P.B, {{Hh, 2 * Hh}, {Hh, 3 * Hh}, {Hh, 2 * Hh}, {Hh, 2 * Hh}}, true, nc, true);
     auto split_bufs = [&](const char* tag, const GemmCfg& c, int N) {
       if (c.splits <= 1) return;
       plan_add(P, std::string("splitws_") + tag, static_cast<long long>(splitk_ws_floats(P.B, N, c.bn, c.splits)) * 4);
@@ -304,6 +305,7 @@ inline void carve(Plan& P) {
     split_bufs("f1", P.cfg_f1, Hh);
     split_bufs("dgf1", P.cfg_dg_f1, 2 * Hh);
     split_bufs("dgf0", P.cfg_dg_f0, cat);
+    for (int g = 0; g < 4; ++g) split_bufs(("dgqkv" + std::to_string(g)).c_str(), P.cfg_dg_qkv, Hh);
   }
   if (getenv("FND_DEBUG_STAMPS")) plan_add(P, "dbg", 8LL * 8 * 1024 * 40);     // clock64 stamps of the row kernels (probes)
   // per-CTA sum-of-squares slots (wgrad CTAs + finalize CTAs); generous upper bound, zero-initialised at bind
