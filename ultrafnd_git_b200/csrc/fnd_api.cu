@@ -111,7 +111,8 @@ static int build_tables(Plan& P) {
     EpiParams e = epi_zero();
     e.gate_z = P.buf<float>("z_p0"); e.gate_pitch = H; e.gate_p = d.clf_dropout; e.gate_stream = kStreamPre0;
     e.out_hi = P.buf<__nv_bfloat16>("dz_p0_hi"); e.out_lo = P.buf<__nv_bfloat16>("dz_p0_lo"); e.bf_pitch = H;
-    FND_OK(add_problem(P, P.dg_p1, tb.act("dz_p1", 0, H, false), tb.weight("clf.pre.3.weight", H, true), B, H, H, P.cfg_dg_pre.bn, 1, e, "", 1));
+    FND_OK(add_problem(P, P.dg_p1, tb.act("dz_p1", 0, H, false), tb.weight("clf.pre.3.weight", H, true), B, H, H, P.cfg_dg_pre.bn,
+                       P.cfg_dg_pre.splits, e, "dgp1", 1));
   }
   for (int fusedpath = 0; fusedpath < 2; ++fusedpath) {
     GemmTable& T = fusedpath ? P.dg_p0_fused : P.dg_p0_split;
@@ -123,7 +124,8 @@ static int build_tables(Plan& P) {
     } else {
       e.out_f32 = P.buf<float>("dfused"); e.f32_pitch = H;
     }
-    FND_OK(add_problem(P, T, tb.act("dz_p0", 0, H, false), tb.weight_rp(true), B, H, H, P.cfg_dg_pre.bn, 1, e, "", 1));
+    FND_OK(add_problem(P, T, tb.act("dz_p0", 0, H, false), tb.weight_rp(true), B, H, H, P.cfg_dg_pre.bn, P.cfg_dg_pre.splits, e,
+                       fusedpath ? "dgp0f" : "dgp0s", 1));
   }
   {
     P.dg_f1.kind = 1;

@@ -175,6 +175,10 @@ inline GemmCfg pick_cfg(int B, const std::vector<std::pair<int, int>>& nk, bool 
     if (sp > c.bn / 2) sp = c.bn / 2;
     if (sp > kb) sp = kb;
     c.splits = sp < 1 ? 1 : sp;
+  } else if (allow_split && ctas <= 16 && kb >= 8) {
+    // a handful of wide (MN-major B: >= 64 columns) tiles: four splits shorten both the operand stream and the
+    // per-CTA epilogue (the fix-up is spread over the splits) by more than the exchange costs (measured)
+    c.splits = 4;
   }
   return c;
 }
@@ -292,7 +296,7 @@ inline void carve(Plan& P) {
     P.cfg_f0 = pick_cfg(P.B, {{2 * Hh, cat}}, false, nc, true);
     P.cfg_f1 = pick_cfg(P.B, {{Hh, 2 * Hh}}, false, nc, true);
     P.cfg_pre = pick_cfg(P.B, {{Hh, Hh}}, false, nc, false);
-    P.cfg_dg_pre = pick_cfg(P.B, {{Hh, Hh}}, true, nc, false);
+    P.cfg_dg_pre = pick_cfg(P.B, {{Hh, Hh}}, true, nc, true);
     P.cfg_dg_f1 = pick_cfg(P.B, {{2 * Hh, Hh}}, true, nc, true);
     P.cfg_dg_f0 = pick_cfg(P.B, {{cat, 2 * Hh}}, true, nc, true);
     P.cfg_dg_qkv = pick_cfg(P.B, {{Hh, 2 * Hh}, {Hh, 3 * Hh}, {Hh, 2 * Hh}, {Hh, 2 * Hh}}, true, nc, true);
@@ -305,6 +309,9 @@ inline void carve(Plan& P) {
     split_bufs("f1", P.cfg_f1, Hh);
     split_bufs("dgf1", P.cfg_dg_f1, 2 * Hh);
     split_bufs("dgf0", P.cfg_dg_f0, cat);
+    split_bufs("dgp1", P.cfg_dg_pre, Hh);
+    split_bufs("dgp0f", P.cfg_dg_pre, Hh);
+    split_bufs("dgp0s", P.cfg_dg_pre, Hh);
     for (int g = 0; g < 4; ++g) split_bufs(("dgqkv" + std::to_string(g)).c_str(), P.cfg_dg_qkv, Hh);
   }
   if (getenv("FND_DEBUG_STAMPS")) plan_add(P, "dbg", 8LL * 8 * 1024 * 40);     // clock64 stamps of the row kernels (probes)
