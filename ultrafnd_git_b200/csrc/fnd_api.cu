@@ -468,6 +468,16 @@ static int run_finalize(Plan& P, const FinTable& T, int slot_base, int total_slo
   return 0;
 }
 
+// one persistent wave: as many CTAs as are resident at once
+static int adamw_grid() {
+  static int g = 0;
+  if (!g) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, adamw_kernel, 256, 0) != cudaSuccess || per_sm < 1) per_sm = 4;
+    g = 148 * per_sm;
+  }
+  return g;
+}
 static AdamWParams adamw_params(const Plan& P) {
   AdamWParams a;
   memset(&a, 0, sizeof(a));
@@ -777,7 +787,7 @@ int fnd_clip_adamw_step(void* plan, int norm_from_slots, void* stream) {
     mark(P, "step_bookkeeping", st);
   }
   AdamWParams a = adamw_params(P);
-  FND_CUDA_OK(launch_k(adamw_kernel, 148 * 8, 256, 0, st, take_pdl(P), a));
+  FND_CUDA_OK(launch_k(adamw_kernel, adamw_grid(), 256, 0, st, take_pdl(P), a));
   mark(P, "adamw", st);
   return 0;
 }
@@ -885,7 +895,7 @@ int fnd_train_step(void* plan, const fnd_inputs* in, void* stream) {
   // AdamW reduces the norm slots itself (identical in every CTA), clips, steps and publishes the bookkeeping.
   AdamWParams a = adamw_params(P);
   a.slots = P.buf<float>("slots"); a.nslots = P.total_slots;
-  FND_CUDA_OK(launch_k(adamw_kernel, 148 * 8, 256, 0, st, take_pdl(P), a));
+  FND_CUDA_OK(launch_k(adamw_kernel, adamw_grid(), 256, 0, st, take_pdl(P), a));
   mark(P, "adamw", st);
   return 0;
 }

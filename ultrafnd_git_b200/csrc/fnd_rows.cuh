@@ -182,6 +182,12 @@ __device__ __forceinline__ float2 ld2(const float* p) { return __ldg(reinterpret
 
 template <int CH>   // CH = H / 512 chunks of 2 consecutive elements per thread
 __global__ void __launch_bounds__(kRowThreads) assemble_fwd_kernel(AssembleParams p) {
+  // static data (evidence-gate MLP parameters, cold after the optimizer streamed through L2): pull them in while the
+  // predecessor is still running
+  for (int k = 0; k < 3; ++k) {
+    for (int j = threadIdx.x * 32; j < 3 * p.H; j += kRowThreads * 32) prefetch_l2(p.ev[k].w1 + j);
+    for (int j = threadIdx.x * 32; j < p.H; j += kRowThreads * 32) { prefetch_l2(p.ev[k].b1 + j); prefetch_l2(p.ev[k].w2 + j); }
+  }
   griddep_wait();
   griddep_launch();
   __shared__ float red[8 * 9];
@@ -289,6 +295,10 @@ struct AssembleBwdParams {
 
 template <int CH>
 __global__ void __launch_bounds__(kRowThreads) assemble_bwd_kernel(AssembleBwdParams p) {
+  for (int k = 0; k < 3; ++k) {
+    for (int j = threadIdx.x * 32; j < 3 * p.H; j += kRowThreads * 32) prefetch_l2(p.ev[k].w1 + j);
+    for (int j = threadIdx.x * 32; j < p.H; j += kRowThreads * 32) { prefetch_l2(p.ev[k].b1 + j); prefetch_l2(p.ev[k].w2 + j); }
+  }
   griddep_wait();
   griddep_launch();
   __shared__ float red[8 * 6];
