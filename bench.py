@@ -409,6 +409,11 @@ def run_b200_arm(args):
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,
         "kernels_ms": {k: round(v, 5) for k, v in sorted(kernels.items(), key=lambda kv: -kv[1])},
+        # whole-step fractions: 74.57 MFLOP/sample of tensor work; 459 MB/step of compulsory HBM traffic
+        # (weights twice, wgrad, AdamW) + 3.6 kB/sample of inputs, per GPU
+        "step_roofline": {"tensor_frac": B * 74.57e6 / (total_ms / K / 1e3) / (peaks["bf16_tflops"] * 1e12),
+                          "hbm_frac": (B * 3604 + 459e6) / (total_ms / K / 1e3) / (peaks["hbm_gbs"] * 1e9),
+                          "note": "at batch 128 the step is a 17-kernel latency chain + the AdamW stream (DESIGN.md §4)"},
     }
     print(json.dumps(line), flush=True)
     if world > 1:

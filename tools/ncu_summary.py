@@ -35,7 +35,7 @@ def main():
         col.setdefault(h.split(".TriageCompute.")[-1], i)
 
     def val(r, name):
-        if name not in col or r[col[name]] in ("", "n/a"):
+        if name not in col or r[col[name]] in ("", "n/a", "no data"):
             return None
         return float(r[col[name]].replace(",", "")) * UNIT_SCALE.get(units[col[name]], 1.0)
 
