@@ -1,7 +1,6 @@
 // fnd_gemm_host.h — host-side construction of GemmProblem tables and the grouped launch.
 #pragma once
 #include "fnd_gemm.cuh"
-#include "fnd_wgrad.cuh"
 #include "fnd_tmap.h"
 #include <cstdlib>
 #include <utility>
@@ -115,7 +114,7 @@ inline int finish_table(GemmProblem* probs, int n) {
 inline cudaError_t init_gemm_attrs() {
   cudaError_t e = cudaFuncSetAttribute(fnd_gemm_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes);
   if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(fnd_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmemBytes);
+  return cudaFuncSetAttribute(fnd_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes);
 }
 
 // Dynamic shared memory one launch of `host_table` needs: header + the deepest ring among its problems (+ align slack).
@@ -130,12 +129,11 @@ inline int gemm_smem_bytes(const GemmProblem* host_table, int nprob) {
 
 // kind: 0 = forward (A K-major, B K-major); 1 = dgrad (A K-major, B MN-major); 2 = wgrad (both MN-major);
 // 3 = (A MN-major, B K-major). `host_table` is copied into the kernel's parameter space at launch.
-// The persistent wgrad kernel (fnd_wgrad.cuh: two resident CTAs per SM walking the tile list, trailing finalize CTAs)
-// serves wgrad launches without split-K whose contraction (= batch) is at most 3 k-blocks (<= 192), 128-wide tiles.
+// The light variant (two CTAs per SM, trailing finalize CTAs) serves wgrad launches without split-K whose ring is
+// shallow enough for two CTAs to share an SM (contraction = batch <= 192).
 inline bool gemm_launch_is_light(int kind, const GemmProblem* host_table, int nprob) {
-  bool light = kind == 2;
-  for (int i = 0; i < nprob; ++i)
-    light = light && host_table[i].splits == 1 && host_table[i].kb_total <= 3 && host_table[i].bn == 128;
+  bool light = kind == 2 && gemm_smem_bytes(host_table, nprob) <= 100 * 1024;
+  for (int i = 0; i < nprob; ++i) light = light && host_table[i].splits == 1;
   return light;
 }
 
@@ -157,10 +155,7 @@ inline cudaError_t launch_gemm(int kind, const GemmProblem* host_table, int npro
   const int smem = gemm_smem_bytes(host_table, nprob);
   if (!gemm_launch_is_light(kind, host_table, nprob) && fin_ctas > 0) return cudaErrorInvalidValue;
   const bool light = gemm_launch_is_light(kind, host_table, nprob);
-  if (light) {
-    t.gemm_ctas = grid < kWgMaxCtas ? grid : kWgMaxCtas;        // resident tile CTAs; `grid` = number of tiles
-    return launch_k(fnd_wgrad_kernel, t.gemm_ctas + fin_ctas, kGemmThreads, kWgSmemBytes, st, pdl, t, ctx, f, grid);
-  }
+  if (light) return launch_k(fnd_gemm_kernel<1>, grid + fin_ctas, kGemmThreads, smem, st, pdl, t, ctx, f);
   return launch_k(fnd_gemm_kernel<0>, grid, kGemmThreads, smem, st, pdl, t, ctx, f);
 }
 
