@@ -392,7 +392,12 @@ def run_b200_arm(args):
         cpu_baseline = {"value": n * B / dt, "unit": "samples/s", "cores": cores, "kind": "port",
                         "sample": f"{n} training steps at batch {B} in {dt:.1f} s (oracle/fnd_oracle.py on the host CPU)"}
 
-    launches_per_step = plan.launch_count("train_step") if world == 1 else plan.launch_count("train_fwd_bwd") + 3
+    if world == 1:
+        launches_per_step = plan.launch_count("train_step")
+    elif dp_mode == "peer":      # forward+backward without the local-norm kernel, then push / reduce / adamw / wait
+        launches_per_step = plan.launch_count("train_fwd_bwd") - 1 + 4
+    else:                        # NCCL arm: + sumsq, norm, adamw (the all-reduce itself is NCCL's kernel)
+        launches_per_step = plan.launch_count("train_fwd_bwd") + plan.launch_count("clip_adamw_step")
     line = {
         "metric": "train samples/sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
