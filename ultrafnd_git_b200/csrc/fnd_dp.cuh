@@ -342,49 +342,56 @@ __global__ void __launch_bounds__(256) dp_adamw_kernel(DpParams d, int s0, int s
   const float step_size = lr / bc1;
   const float inv_sqrt_bc2 = rsqrtf(bc2);
   const AdamWParams& a = d.a;
+  const uint64_t pol = l2_policy_evict_first();      // optimizer streams must not push the weights / activations out of L2
+  auto update4 = [&](size_t i, const float* gsrc4, float (&out)[4]) {
+    float4 p = ld_f4_policy(a.p + i, pol);
+    const float4 g4 = __ldcg(reinterpret_cast<const float4*>(gsrc4));
+    float4 m = ld_f4_policy(a.m + i, pol);
+    float4 v = ld_f4_policy(a.v + i, pol);
+    float* pp = &p.x; float* mp = &m.x; float* vp = &v.x; const float* gp = &g4.x;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float gq = gp[q] * coef;
+      pp[q] *= decay;
+      mp[q] = b1 * mp[q] + (1.0f - b1) * gq;
+      vp[q] = b2 * vp[q] + (1.0f - b2) * gq * gq;
+      const float denom = sqrtf(vp[q]) * inv_sqrt_bc2 + eps;
+      pp[q] -= step_size * (mp[q] / denom);
+      out[q] = pp[q];
+    }
+    st_f4_policy(a.p + i, p, pol);
+    st_f4_policy(a.m + i, m, pol);
+    st_f4_policy(a.v + i, v, pol);
+  };
   for (int sg = s0; sg < s1; ++sg) {
-    const size_t n8 = (d.seg_hi[d.rank][sg] - d.seg_lo[d.rank][sg]) >> 3;      // slices are multiples of 1024 elements...
-    const size_t rem = (d.seg_hi[d.rank][sg] - d.seg_lo[d.rank][sg]) & 7;      // ...except the last rank's tail
+    const size_t len = d.seg_hi[d.rank][sg] - d.seg_lo[d.rank][sg];
+    const size_t n8 = len >> 3;                                    // slices are multiples of 1024 elements ...
+    const bool tail4 = (len & 7) != 0;                             // ... except the last rank's (a multiple of 4)
     const float* gsrc = d.gred + d.seg_goff[d.rank][sg];
-    for (size_t i8 = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i8 < n8 + (rem ? 1 : 0);
+    for (size_t i8 = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i8 < n8;
          i8 += static_cast<size_t>(gridDim.x) * blockDim.x) {
       const size_t i = d.seg_lo[d.rank][sg] + i8 * 8;
-      float p[8], g[8], m[8], v[8];
-      if (i8 < n8) {
-        ldcg_f8(a.p + i, p); ldcg_f8(gsrc + i8 * 8, g); ldcg_f8(a.m + i, m); ldcg_f8(a.v + i, v);
-      } else {                                   // 4-element tail (arena ranges are multiples of 4)
+      float lo4[4], hi4[4];
+      update4(i, gsrc + i8 * 8, lo4);
+      update4(i + 4, gsrc + i8 * 8 + 4, hi4);
+      const float x[8] = {lo4[0], lo4[1], lo4[2], lo4[3], hi4[0], hi4[1], hi4[2], hi4[3]};
+      dp_publish8(d, i, x);
+    }
+    if (tail4 && blockIdx.x == 0 && threadIdx.x == 0) {
+      const size_t i = d.seg_lo[d.rank][sg] + n8 * 8;
+      float t4[4];
+      update4(i, gsrc + n8 * 8, t4);
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const bool ok = q < static_cast<int>(rem);
-          p[q] = ok ? a.p[i + q] : 0.f; g[q] = ok ? gsrc[i8 * 8 + q] : 0.f; m[q] = ok ? a.m[i + q] : 0.f; v[q] = ok ? a.v[i + q] : 0.f;
-        }
-      }
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const float gq = g[q] * coef;
-        p[q] *= decay;
-        m[q] = b1 * m[q] + (1.0f - b1) * gq;
-        v[q] = b2 * v[q] + (1.0f - b2) * gq * gq;
-        const float denom = sqrtf(v[q]) * inv_sqrt_bc2 + eps;
-        p[q] -= step_size * (m[q] / denom);
-      }
-      if (i8 < n8) {
-        st_f8(a.p + i, p); st_f8(a.m + i, m); st_f8(a.v + i, v);
-        dp_publish8(d, i, p);
-      } else {
-        for (int q = 0; q < static_cast<int>(rem); ++q) { a.p[i + q] = p[q]; a.m[i + q] = m[q]; a.v[i + q] = v[q]; }
-        // tail: element-wise publication
-        for (int q = 0; q < static_cast<int>(rem); ++q) {
-          const size_t e = i + q;
-          for (int pr = 0; pr < d.world; ++pr) {
-            if (e < a.n_shadow) {
-              __nv_bfloat16 hb, lb;
-              split_bf16(p[q], hb, lb);
-              d.sh_hi[pr][e] = hb;
-              if (a.sh_lo) d.sh_lo[pr][e] = lb;
-            } else if (pr != d.rank) {
-              d.params[pr][e] = p[q];
-            }
+      for (int q = 0; q < 4; ++q) {                                // element-wise publication of the 4-element tail
+        const size_t e = i + q;
+        for (int pr = 0; pr < d.world; ++pr) {
+          if (e < a.n_shadow) {
+            __nv_bfloat16 hb, lb;
+            split_bf16(t4[q], hb, lb);
+            d.sh_hi[pr][e] = hb;
+            if (a.sh_lo) d.sh_lo[pr][e] = lb;
+          } else if (pr != d.rank) {
+            d.params[pr][e] = t4[q];
           }
         }
       }
