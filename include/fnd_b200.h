@@ -69,6 +69,10 @@ void fnd_plan_destroy(void* plan);
 size_t fnd_plan_workspace_bytes(const void* plan);
 int fnd_plan_bind(void* plan, void* workspace, float* params, float* grads, float* adam_m, float* adam_v,
                   void* shadow_hi, void* shadow_lo, void* stream);
+/* Optional, BEFORE fnd_plan_bind: a bf16 buffer of fnd_arena_hot_elems elements that the weight-gradient kernels fill
+ * with bf16 copies of the GEMM-weight gradients (same element offsets as the gradient arena; pre.0.weight excluded).
+ * The data-parallel step reduces this mirror through the NVSwitch (fnd_dp_bind). NULL = no mirror. 256-byte aligned. */
+int fnd_plan_set_grad_mirror(void* plan, void* grads_bf16);
 /* Byte offset / element count of a named workspace buffer ("fused", "fusion_logits", "rowstat", "logits",
  * "probs", "loss_row", "dlogits", "dfused", "state", "fused_cat_hi", ...); returns -1 if unknown. */
 long long fnd_plan_buffer_offset(const void* plan, const char* name);
@@ -140,15 +144,18 @@ int fnd_eval_step(void* plan, const fnd_inputs* in, void* stream);
  * Every rank places params | grads | shadow_hi | shadow_lo | a 256-byte zeroed comm pad | a staging region
  * (fnd_dp_stage_bytes) at the SAME byte offsets of one peer-mapped (symmetric) allocation; peer_bases[p] is rank p's
  * base address as mapped into THIS process; multicast_base (0 = none) is the NVSwitch multicast mapping of the same
- * allocation — when given, the all-gather uses one multimem.st per 16 bytes instead of one store per peer. The plan must already be bound (fnd_plan_bind) to this rank's buffers.
+ * allocation — when given, the all-gather uses one multimem.st per 16 bytes instead of one store per peer, and with
+ * off_grads_bf16 >= -1 the reduce-scatter becomes ONE multimem.ld_reduce kernel (in-switch sum over all gradient arenas;
+ * off_grads_bf16 >= 0 is the offset of the bf16 gradient mirror given to fnd_plan_set_grad_mirror, read instead of the
+ * fp32 arena for the GEMM weights; -2 keeps the store-based exchange through the staging region). The plan must already be bound (fnd_plan_bind) to this rank's buffers.
  * gred: local scratch of fnd_dp_stage_bytes / (world * elem size) floats; slots: 1024 zeroed floats.
  * fnd_dp_optimizer_step is stream-ordered and graph-capturable; every rank must call it once per fnd_train_fwd_bwd.
  * After it, only the OWNER of a slice holds current fp32 master weights for it; gather the slices (e.g. one broadcast
  * per range) before reading a state_dict. */
 int fnd_dp_bind(void* plan, int rank, int world, const unsigned long long* peer_bases, long long off_params,
                 long long off_grads, long long off_shadow_hi, long long off_shadow_lo, long long off_pad,
-                long long off_stage, int stage_bf16, unsigned long long multicast_base, float* gred,
-                long long gred_elems, float* slots, long long slots_elems);
+                long long off_stage, int stage_bf16, unsigned long long multicast_base, long long off_grads_bf16,
+                float* gred, long long gred_elems, float* slots, long long slots_elems);
 long long fnd_dp_stage_bytes(const void* plan, int world, int stage_bf16);
 /* The slice of [0, hot) rank `rank` owns: three element ranges (its shares of fuse_mlp.0/.3 weights and of the arena
  * before / after them); returns the number of ranges written to lo3 / hi3. */

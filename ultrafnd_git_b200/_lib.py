@@ -112,6 +112,7 @@ def _signatures() -> Dict[str, tuple]:
         "fnd_plan_destroy": (None, [_c_void_p]),
         "fnd_plan_workspace_bytes": (_c_size_t, [_c_void_p]),
         "fnd_plan_bind": (_c_int, [_c_void_p] * 9),
+        "fnd_plan_set_grad_mirror": (_c_int, [_c_void_p, _c_void_p]),
         "fnd_plan_buffer_offset": (ll, [_c_void_p, ctypes.c_char_p]),
         "fnd_plan_buffer_bytes": (ll, [_c_void_p, ctypes.c_char_p]),
         "fnd_set_hyper": (_c_int, [_c_void_p, _c_float, _c_float, _c_float, _c_float, _c_float, _c_float, _c_void_p]),
@@ -130,7 +131,7 @@ def _signatures() -> Dict[str, tuple]:
         "fnd_eval_step": (_c_int, [_c_void_p, P(FndInputs), _c_void_p]),
         "fnd_launch_count": (_c_int, [_c_void_p, ctypes.c_char_p]),
         "fnd_debug_set_launch_limit": (_c_int, [_c_void_p, _c_int]),
-        "fnd_dp_bind": (_c_int, [_c_void_p, _c_int, _c_int, P(ctypes.c_ulonglong), ll, ll, ll, ll, ll, ll, _c_int, ctypes.c_ulonglong,
+        "fnd_dp_bind": (_c_int, [_c_void_p, _c_int, _c_int, P(ctypes.c_ulonglong), ll, ll, ll, ll, ll, ll, _c_int, ctypes.c_ulonglong, ll,
                                  _c_void_p, ll, _c_void_p, ll]),
         "fnd_dp_stage_bytes": (ll, [_c_void_p, _c_int, _c_int]),
         "fnd_dp_shard_ranges": (_c_int, [_c_void_p, _c_int, _c_int, P(ll), P(ll)]),

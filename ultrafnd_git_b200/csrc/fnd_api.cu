@@ -160,6 +160,9 @@ static int build_tables(Plan& P) {
     e.out_f32 = dst; e.f32_pitch = pitch;
     // dAraw feeds finalize jobs that may run as trailing CTAs of the same launch: its tiles announce completion
     if (dst == P.buf<float>("dAraw")) e.done_ctr = &P.state()->wg_done;
+    // bf16 mirror of the weight gradients (same element offsets as the gradient arena); pre.0.weight's rows (pitch 514)
+    // are not 16-byte aligned in bf16 and stay fp32-only
+    if (P.grads_bf && dst >= P.grads && dst < P.grads + P.L.n_hot && (pitch & 7) == 0) e.out_bf = P.grads_bf + (dst - P.grads);
     return add_problem(P, T, dY, X, n_out, k_in, B, 128, 1, e, "", 0);
   };
   const int dA_tiles = ceil_div(P.TD + 2, kGemmBM) * ceil_div(H, 128);
@@ -605,6 +608,14 @@ long long fnd_plan_buffer_bytes(const void* plan, const char* name) {
   return it == P->bufs.end() ? -1 : it->second.bytes;
 }
 
+int fnd_plan_set_grad_mirror(void* plan, void* grads_bf16) {
+  Plan* PP = as_plan(plan);
+  if (!PP) return -1;
+  if (reinterpret_cast<uintptr_t>(grads_bf16) & 255) return -3;
+  PP->grads_bf = static_cast<__nv_bfloat16*>(grads_bf16);
+  return 0;
+}
+
 int fnd_plan_bind(void* plan, void* workspace, float* params, float* grads, float* adam_m, float* adam_v, void* shadow_hi,
                   void* shadow_lo, void* stream) {
   Plan* PP = as_plan(plan);
@@ -933,8 +944,8 @@ long long fnd_dp_stage_bytes(const void* plan, int world, int bf16) {
 
 int fnd_dp_bind(void* plan, int rank, int world, const unsigned long long* peer_bases, long long off_params,
                 long long off_grads, long long off_shadow_hi, long long off_shadow_lo, long long off_pad,
-                long long off_stage, int stage_bf16, unsigned long long multicast_base, float* gred, long long gred_elems,
-                float* slots, long long slots_elems) {
+                long long off_stage, int stage_bf16, unsigned long long multicast_base, long long off_grads_bf16,
+                float* gred, long long gred_elems, float* slots, long long slots_elems) {
   Plan* PP = as_plan(plan);
   if (!PP || !PP->bound) return -5;
   Plan& P = *PP;
@@ -965,6 +976,16 @@ int fnd_dp_bind(void* plan, int rank, int world, const unsigned long long* peer_
     d.mc_params = reinterpret_cast<float*>(mc + off_params);
     d.mc_sh_hi = reinterpret_cast<__nv_bfloat16*>(mc + off_shadow_hi);
     d.mc_sh_lo = P.sh_lo ? reinterpret_cast<__nv_bfloat16*>(mc + off_shadow_lo) : nullptr;
+    // pull mode (off_grads_bf16 >= -1): the reduce-scatter is one multimem.ld_reduce kernel over the gradient arenas; a
+    // non-negative offset names the bf16 gradient mirror every rank keeps in the symmetric allocation
+    if (off_grads_bf16 >= -1) {
+      d.mc_grads = reinterpret_cast<const float*>(mc + off_grads);
+      if (off_grads_bf16 >= 0) {
+        uint8_t* mine = reinterpret_cast<uint8_t*>(static_cast<uintptr_t>(peer_bases[rank]));
+        if (reinterpret_cast<__nv_bfloat16*>(mine + off_grads_bf16) != P.grads_bf) return -8;   // plan not bound with this mirror
+        d.mc_grads_bf = reinterpret_cast<const __nv_bfloat16*>(mc + off_grads_bf16);
+      }
+    }
   }
   d.nseg = kDpMaxSeg;
   d.slot_cap = dp_slot_cap(P, world);
@@ -1009,12 +1030,18 @@ static int dp_deferred(Plan& P, int grid, cudaStream_t st) {
 
 static int dp_tail(Plan& P, bool early_done, bool defer, cudaStream_t st) {
   P.dp.a = adamw_params(P);
-  // without an early push, ONE launch moves all three ranges (it raises the late flags; the early bank is not used)
-  FND_OK(dp_push(P, early_done ? 1 : 0, kDpMaxSeg, kPadReadyLate, kPadCounter, kDpGrid, 256, st));
-  mark(P, "dp_push", st);
-  if (P.dp.stage_bf16) FND_CUDA_OK(launch_k(dp_reduce_kernel<true>, kDpGrid, 256, 0, st, false, P.dp, early_done ? 1 : 0));
-  else FND_CUDA_OK(launch_k(dp_reduce_kernel<false>, kDpGrid, 256, 0, st, false, P.dp, early_done ? 1 : 0));
-  mark(P, "dp_reduce", st);
+  if (P.dp.mc_grads && !early_done) {
+    // NVSwitch multicast available: the reduce-scatter is one in-switch-reduction kernel
+    FND_CUDA_OK(launch_k(dp_pull_kernel, kDpGrid, 256, 0, st, false, P.dp));
+    mark(P, "dp_pull", st);
+  } else {
+    // without an early push, ONE launch moves all three ranges (it raises the late flags; the early bank is not used)
+    FND_OK(dp_push(P, early_done ? 1 : 0, kDpMaxSeg, kPadReadyLate, kPadCounter, kDpGrid, 256, st));
+    mark(P, "dp_push", st);
+    if (P.dp.stage_bf16) FND_CUDA_OK(launch_k(dp_reduce_kernel<true>, kDpGrid, 256, 0, st, false, P.dp, early_done ? 1 : 0));
+    else FND_CUDA_OK(launch_k(dp_reduce_kernel<false>, kDpGrid, 256, 0, st, false, P.dp, early_done ? 1 : 0));
+    mark(P, "dp_reduce", st);
+  }
   FND_CUDA_OK(launch_k(dp_adamw_kernel, kDpGrid, 256, 0, st, false, P.dp, defer ? 1 : 0, static_cast<int>(kDpMaxSeg), 0,
                        static_cast<int>(kPadCounter)));
   mark(P, "dp_adamw", st);

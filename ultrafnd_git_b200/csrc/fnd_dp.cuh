@@ -62,6 +62,8 @@ struct DpParams {
   float* mc_params;
   __nv_bfloat16* mc_sh_hi;
   __nv_bfloat16* mc_sh_lo;
+  const float* mc_grads;                  // multicast view of the gradient arenas (pull mode: in-switch reduction)
+  const __nv_bfloat16* mc_grads_bf;       // ... and of their bf16 mirrors (null: reduce the fp32 gradients)
   void* stage[kDpMaxWorld];               // staging buffer of every rank: [world slots][slot_cap] fp32 or bf16
   size_t slot_cap;                        // elements per staging slot (>= the largest slice)
   int stage_bf16;                         // 1: pieces travel as bf16
@@ -153,6 +155,82 @@ __global__ void __launch_bounds__(256, 4) dp_push_kernel(DpParams d, int s0, int
   if (threadIdx.x < static_cast<unsigned>(d.world)) {
     __threadfence_system();
     st_release_sys(d.pad[threadIdx.x] + bank + d.rank, epoch);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// 1'. pull: the whole reduce-scatter as ONE kernel when the fabric has multicast — every rank reads its slice through
+//     the NVSwitch with multimem.ld_reduce, which fetches the same address from all N gradient arenas and returns the
+//     sum (accumulated in fp32 inside the switch). No staging, no sender-side kernel, one flag round. GEMM-weight
+//     gradients are read from the bf16 mirror when there is one (half the wire bytes; the sum comes back rounded to
+//     bf16), everything else — and everything in fp32 mode — from the fp32 arenas.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) dp_pull_kernel(DpParams d) {
+  __shared__ float red[8];
+  __shared__ int is_last;
+  unsigned int* mypad = d.pad[d.rank];
+  const unsigned int epoch = mypad[kPadEpoch] + 1u;
+  // all of this rank's gradients are complete (stream order): tell every peer, then wait for all of them
+  if (blockIdx.x == 0 && threadIdx.x < static_cast<unsigned>(d.world)) {
+    __threadfence_system();
+    st_release_sys(d.pad[threadIdx.x] + kPadReadyLate + d.rank, epoch);
+  }
+  dp_wait_all(mypad, kPadReadyLate, d.world, epoch, &d.a.state->err);
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  const size_t rp0 = d.a.rp_begin, rp1 = d.a.rp_end, nsh = d.a.n_shadow;
+  float ss = 0.f;
+  for (int sg = 0; sg < d.nseg; ++sg) {
+    const size_t lo = d.seg_lo[d.rank][sg], n8 = (d.seg_hi[d.rank][sg] - lo) >> 3;
+    float* out = d.gred + d.seg_goff[d.rank][sg];
+    for (size_t i8 = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i8 < n8; i8 += stride) {
+      const size_t i = lo + i8 * 8;
+      float v[8];
+      // mirrored: a GEMM weight other than pre.0.weight (tensor boundaries are multiples of 64 elements)
+      const bool mirrored = d.mc_grads_bf != nullptr && i < nsh && !(i >= rp0 && i < rp1);
+      if (mirrored) {
+        uint32_t r0, r1, r2, r3;
+        asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f32.v4.bf16x2 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "l"(d.mc_grads_bf + i) : "memory");
+        const uint32_t rr[4] = {r0, r1, r2, r3};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&rr[q]);
+          v[2 * q] = __low2float(h2); v[2 * q + 1] = __high2float(h2);
+        }
+      } else {
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+          asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+                       : "=f"(v[4 * h]), "=f"(v[4 * h + 1]), "=f"(v[4 * h + 2]), "=f"(v[4 * h + 3])
+                       : "l"(d.mc_grads + i + 4 * h) : "memory");
+      }
+      *reinterpret_cast<float4*>(out + i8 * 8) = make_float4(v[0], v[1], v[2], v[3]);
+      *reinterpret_cast<float4*>(out + i8 * 8 + 4) = make_float4(v[4], v[5], v[6], v[7]);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) ss = fmaf(v[q], v[q], ss);
+    }
+  }
+  ss = warp_sum(ss);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tot = 0.f;
+    for (int w = 0; w < 8; ++w) tot += red[w];
+    d.slots[blockIdx.x] = tot;
+    __threadfence();
+    is_last = (atomicAdd(mypad + kPadCounter, 1u) == gridDim.x - 1) ? 1 : 0;
+  }
+  __syncthreads();
+  if (!is_last) return;
+  if (threadIdx.x < 32) {
+    __threadfence();
+    const double part = warp_reduce_slots(d.slots, static_cast<int>(gridDim.x));
+    if (threadIdx.x == 0) mypad[kPadCounter] = 0u;
+    if (threadIdx.x < static_cast<unsigned>(d.world)) {
+      reinterpret_cast<float*>(d.pad[threadIdx.x])[kPadPartial + d.rank] = static_cast<float>(part);
+      __threadfence_system();
+      st_release_sys(d.pad[threadIdx.x] + kPadPartialReady + d.rank, epoch);
+    }
   }
 }
 

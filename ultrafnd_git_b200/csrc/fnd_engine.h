@@ -200,6 +200,7 @@ struct Plan {
   uint8_t* ws = nullptr;
   float *params = nullptr, *grads = nullptr, *m = nullptr, *v = nullptr;
   __nv_bfloat16 *sh_hi = nullptr, *sh_lo = nullptr;
+  __nv_bfloat16* grads_bf = nullptr;   // optional bf16 mirror of the GEMM-weight gradients (fnd_plan_set_grad_mirror)
   // tables
   GemmTable fwd_proj, fwd_qkv, fwd_f0, fwd_f1, fwd_p0, fwd_p1;
   GemmTable dg_p1, dg_p0_fused, dg_p0_split, dg_f1, dg_f0, dg_qkv;

@@ -75,6 +75,8 @@ struct EpiParams {
   int plain_f32;                     // host-set: the epilogue is ONLY "store v as fp32 (+ sum of squares)", pitch % 8 == 0;
                                      // 2 = additionally the operand ring is large enough to stage the tile for coalesced stores
   unsigned int* done_ctr;            // non-null: bumped once per tile after its stores (consumers in the same launch wait on it)
+  __nv_bfloat16* out_bf;             // store-only epilogues: also store bf16(v) at the same [m * f32_pitch + n] offsets (the
+                                     // bf16 gradient mirror that the data-parallel step reduces through the NVSwitch)
 };
 
 struct alignas(128) GemmProblem {
@@ -433,9 +435,12 @@ fnd_gemm_kernel(const __grid_constant__ GemmTableP tbl, RunCtx ctx, const __grid
             for (int k = 0; k < 8; ++k) {
               const int rr = k * 4 + rsub;
               const int mm = tm * kGemmBM + lane_grp * 32 + rr;
-              if (mm < PM)
-                *reinterpret_cast<float4*>(E.out_f32 + static_cast<size_t>(mm) * E.f32_pitch + n) =
-                    *reinterpret_cast<const float4*>(stg + rr * kStgPitch + csub);
+              if (mm < PM) {
+                const float4 v4 = *reinterpret_cast<const float4*>(stg + rr * kStgPitch + csub);
+                const size_t o = static_cast<size_t>(mm) * E.f32_pitch + n;
+                *reinterpret_cast<float4*>(E.out_f32 + o) = v4;
+                if (E.out_bf) *reinterpret_cast<uint2*>(E.out_bf + o) = make_uint2(pack_bf16x2(v4.x, v4.y), pack_bf16x2(v4.z, v4.w));
+              }
             }
           }
           __syncwarp();
@@ -458,6 +463,9 @@ fnd_gemm_kernel(const __grid_constant__ GemmTableP tbl, RunCtx ctx, const __grid
 #pragma unroll
               for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[q * 8 + j]);
               st_f8(dst + q * 8, v);
+              if (E.out_bf)
+                *reinterpret_cast<uint4*>(E.out_bf + (dst - E.out_f32) + q * 8) =
+                    make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
 #pragma unroll
               for (int j = 0; j < 8; ++j) ss = fmaf(v[j], v[j], ss);
             }

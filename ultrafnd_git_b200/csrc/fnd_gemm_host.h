@@ -83,6 +83,7 @@ inline int fill_problem(GemmProblem& p, const Operand& A, const Operand& B, int 
   p.epi.plain_f32 = (epi.out_f32 && !epi.bias && !epi.aux && !epi.add_in && !epi.out_pre && !epi.act && !epi.gate_z &&
                      !epi.out_hi && epi.drop_p == 0.f && (epi.f32_pitch & 7) == 0) ? 1 : 0;
   if (p.epi.plain_f32 && p.nstages * p.stage_bytes >= kGemmEpiWarps * 32 * 36 * 4) p.epi.plain_f32 = 2;   // room to stage the tile
+  if (!p.epi.plain_f32 || bn < 64) p.epi.out_bf = nullptr;    // the bf16 mirror is written by the store-only epilogues only
   for (int h = 0; h < (ncombo == 3 ? 2 : 1); ++h) {
     const void* a = h ? static_cast<const void*>(A.lo) : static_cast<const void*>(A.hi);
     const void* b = h ? static_cast<const void*>(B.lo) : static_cast<const void*>(B.hi);

@@ -122,6 +122,8 @@ class Plan:
 
     def bind(self) -> None:
         e = self.engine
+        check(self.lib.fnd_plan_set_grad_mirror(self.handle, e.grads_bf.data_ptr() if e.grads_bf is not None else None),
+              "fnd_plan_set_grad_mirror")
         check(self.lib.fnd_plan_bind(self.handle, self._ws_base, e.params.data_ptr(), e.grads.data_ptr(),
                                      e.adam_m.data_ptr() if e.adam_m is not None else None,
                                      e.adam_v.data_ptr() if e.adam_v is not None else None,
@@ -220,6 +222,7 @@ class Engine:
         self._shadow_version: Optional[int] = None
         self.attached: list = []          # weakrefs to the nn.Modules whose parameters live in this arena
         self.symm: Optional[dict] = None  # peer-mapped buffers of the data-parallel optimizer step (enable_symmetric)
+        self.grads_bf: Optional[torch.Tensor] = None   # bf16 mirror of the GEMM-weight gradients (pull-mode exchange)
         self._dp_pending = False          # a deferred fuse_mlp update of the last train_step_dp has not been applied yet
         self._dp_plan: Optional["Plan"] = None
         self._alloc_device_buffers()
@@ -280,7 +283,11 @@ class Engine:
         stage_bytes = self.lib.fnd_dp_stage_bytes(self.any_plan().handle, world, stage_bf16)
         if stage_bytes < 0:
             raise _lib.FndError(f"fnd_dp_stage_bytes: {stage_bytes}")
-        total = off_stage + stage_bytes
+        # pull mode (NVSwitch multicast): the reduce-scatter is one multimem.ld_reduce kernel; in bf16 mode the GEMM-weight
+        # gradients are reduced from a bf16 mirror that the wgrad kernels write (FND_DP_PULL=0: store-based exchange)
+        want_pull = os.environ.get("FND_DP_PULL", "1") != "0"
+        off_gbf = up(off_stage + stage_bytes)
+        total = off_gbf + (2 * self.n_hot if (want_pull and stage_bf16) else 0)
         buf = symm.empty(total, dtype=torch.uint8, device=self.device)
         buf.zero_()
         hdl = symm.rendezvous(buf, group)
@@ -293,6 +300,9 @@ class Engine:
         if new_l is not None:
             new_l.copy_(self.shadow_lo)
         self.params, self.grads, self.shadow_hi, self.shadow_lo = new_p, new_g, new_h, new_l
+        multicast = int(getattr(hdl, "multicast_ptr", 0) or 0) if os.environ.get("FND_DP_MULTICAST", "1") != "0" else 0
+        pull = bool(multicast) and want_pull
+        self.grads_bf = buf[off_gbf: off_gbf + 2 * self.n_hot].view(torch.bfloat16) if (pull and stage_bf16) else None
         with torch.no_grad():
             for ref in self.attached:
                 m = ref()
@@ -306,7 +316,9 @@ class Engine:
                      "offsets": (off_p, off_g, off_h, off_l, off_pad, off_stage),
                      "peer_bases": [int(x) for x in hdl.buffer_ptrs],
                      # NVSwitch multicast mapping (0 when unsupported, or when disabled with FND_DP_MULTICAST=0)
-                     "multicast": int(getattr(hdl, "multicast_ptr", 0) or 0) if os.environ.get("FND_DP_MULTICAST", "1") != "0" else 0,
+                     "multicast": multicast,
+                     # -2: store-based exchange; -1: pull from the fp32 arenas; >= 0: pull, offset of the bf16 mirror
+                     "off_grads_bf16": (off_gbf if stage_bf16 else -1) if pull else -2,
                      "gred": torch.zeros(per, dtype=torch.float32, device=self.device),
                      "slots": torch.zeros(1024, dtype=torch.float32, device=self.device)}
         torch.cuda.synchronize(self.device)
@@ -317,7 +329,7 @@ class Engine:
         bases = (ctypes.c_ulonglong * s["world"])(*s["peer_bases"])
         off_p, off_g, off_h, off_l, off_pad, off_stage = s["offsets"]
         check(self.lib.fnd_dp_bind(plan.handle, s["rank"], s["world"], bases, off_p, off_g, off_h, off_l, off_pad, off_stage,
-                                   s["stage_bf16"], s["multicast"],
+                                   s["stage_bf16"], s["multicast"], s["off_grads_bf16"],
                                    s["gred"].data_ptr(), s["gred"].numel(), s["slots"].data_ptr(), s["slots"].numel()),
               "fnd_dp_bind")
 
@@ -367,6 +379,8 @@ class Engine:
         self.plans.clear()
         self.adam_m = self.adam_v = None
         self.grads = self.shadow_hi = self.shadow_lo = None
+        self.grads_bf = None
+        self.symm = None
         self._shadow_version = None
         self._alloc_device_buffers()
 
