@@ -45,3 +45,27 @@ def test_forward_batch_api_matches_fused_eval():
     st.static_gather.copy_(torch.as_tensor(tr.te_idx)[batch["index"]].cuda())
     st.eval_step(from_cache=True)
     assert torch.allclose(st.logits(), out["logits"], atol=1e-5, rtol=1e-4)
+
+
+def test_resume_continues_bit_for_bit(tmp_path):
+    """save_resume / load_resume: two epochs + save + one epoch == load into a fresh trainer + one epoch,
+    bitwise (same dropout salts, optimizer step count, Adam moments, shuffle order)."""
+    cache = synthetic_cache(n=300, seed=5)
+    cfg = TrainConfig(data_root="unused", ocr_phrase_pkl=None, out_dir=str(tmp_path), batch_size=32, epochs=0, lr=3e-4)
+    a = ForensicTrainer(cfg, cache=cache)
+    for ep in (1, 2):
+        a.epoch = ep
+        a._epoch_loop("train")
+    path = os.path.join(str(tmp_path), "resume.pt")
+    a.save_resume(path)
+    a.epoch = 3
+    la, _ = a._epoch_loop("train")
+    pa = a.engine.params.clone()
+    b = ForensicTrainer(cfg, cache=cache)
+    b.load_resume(path)
+    assert b.epoch == 2
+    b.epoch = 3
+    lb, _ = b._epoch_loop("train")
+    assert la == lb
+    assert torch.equal(pa, b.engine.params)
+    assert a._last_step.plan.state()["step"] == b._last_step.plan.state()["step"] > 0

@@ -180,6 +180,7 @@ class ForensicTrainer:
         self.precision = precision
         self._steps: Dict[int, FusedStep] = {}
         self._last_step: Optional[FusedStep] = None
+        self._resume_state: Optional[torch.Tensor] = None
 
         feats = {"text_features": torch.as_tensor(np.asarray(cache["text"])),
                  "audio_features": torch.as_tensor(np.asarray(cache["audio"])),
@@ -247,6 +248,15 @@ class ForensicTrainer:
             check(st.engine.lib.fnd_set_loss_scale(st.plan.handle, 1.0 / global_batch, st.engine.stream_ptr()),
                   "fnd_set_loss_scale")
             st._global_batch = global_batch
+        if self._last_step is None and self._resume_state is not None:
+            # resuming: the saved DevState (optimizer step, bias corrections, dropout salts, hyper-parameters) seeds
+            # the first plan that runs
+            dst = st.plan.buffer("state", torch.float32, (22,))
+            keep_scale = dst[17:18].clone()
+            dst.copy_(self._resume_state.to(self.device))
+            dst[17:18].copy_(keep_scale)
+            dst[16:17].zero_(); dst[18:20].zero_()        # error flag, election / intra-launch counters
+            self._resume_state = None
         if self._last_step is not None and self._last_step is not st:
             # optimizer step count / bias corrections / dropout salts live in each plan's DevState: carry them over
             src = self._last_step.plan.buffer("state", torch.float32, (22,))
@@ -349,6 +359,47 @@ class ForensicTrainer:
                         print(f"↳ Early stopping (no val AUC improvement for {self.cfg.early_stop_patience} epochs)")
                     break
         return self.best_val_auc
+
+    # ------------------------------------------------------------------ full resume
+    def save_resume(self, path: str) -> None:
+        """Everything needed to continue training bit-for-bit: fp32 master weights, Adam moments, the device-side step
+        state (optimizer step count, dropout salts), learning rate, epoch and early-stopping bookkeeping. The reference
+        only saves the best weights (forensic_trainer.py:352-361) and cannot resume. Every rank must call this (the
+        sharded data-parallel state is gathered first); rank 0 writes."""
+        eng = self.engine
+        if self.dp_peer:
+            eng.gather_master()
+            for r in range(self.world):                      # Adam moments are sharded like the master weights
+                for lo, hi in eng.shard_ranges(r):
+                    if hi > lo:
+                        torch.distributed.broadcast(eng.adam_m[lo:hi], src=r)
+                        torch.distributed.broadcast(eng.adam_v[lo:hi], src=r)
+        else:
+            eng.dp_flush()
+        dev_state = (self._last_step.plan.buffer("state", torch.float32, (22,)).cpu().clone()
+                     if self._last_step is not None else self._resume_state)
+        if self.rank == 0:
+            torch.save({"params": eng.params.detach().cpu(),
+                        "adam_m": eng.adam_m.cpu() if eng.adam_m is not None else None,
+                        "adam_v": eng.adam_v.cpu() if eng.adam_v is not None else None,
+                        "dev_state": dev_state, "lr": self.lr, "epoch": self.epoch, "best_val_auc": self.best_val_auc,
+                        "no_improve": self.no_improve, "cfg": dict(self.cfg.__dict__)}, path)
+
+    def load_resume(self, path: str) -> None:
+        ck = torch.load(path, map_location="cpu")
+        eng = self.engine
+        eng.enable_optimizer()
+        with torch.no_grad():
+            eng.params.copy_(ck["params"].to(self.device))
+            if ck.get("adam_m") is not None:
+                eng.adam_m.copy_(ck["adam_m"].to(self.device))
+                eng.adam_v.copy_(ck["adam_v"].to(self.device))
+        eng.refresh_shadows(eng.param_version())
+        self.lr = float(ck["lr"]); eng.set_lr(self.lr)
+        self.epoch = int(ck["epoch"]); self.best_val_auc = float(ck["best_val_auc"]); self.no_improve = int(ck["no_improve"])
+        self._resume_state = ck["dev_state"]
+        self._steps.clear()
+        self._last_step = None
 
     def test(self) -> Dict[str, float]:
         if os.path.exists(self.ckpt_path):
