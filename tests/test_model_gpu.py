@@ -275,3 +275,49 @@ def test_eval_forward_b1024_fp32_and_bf16_vs_reference_oracle():
         assert bool(agree[margin > TOL[precision] * float(ref["logits"].abs().max())].all())
         if precision == "fp32":
             assert bool(agree.all())
+
+
+def test_hidden_1024_forward_and_gradients_match_oracle(tmp_path):
+    """hidden_dim is a YAML knob of the reference (fusion.yaml:2, classifier.yaml:3): the 1024-wide instantiations of
+    the row kernels / GEMM tables against the (shape-generic) oracle, fp32 mode."""
+    fy, cy = tmp_path / "fusion.yaml", tmp_path / "classifier.yaml"
+    fy.write_text("hidden_dim: 1024\ndropout: 0.0\nuse_gnn: true\ngnn_dim: 128\n")
+    cy.write_text("input_dim: 1024\nhidden_dim: 1024\ndropout: 0.0\nnum_classes: 2\nuse_aux: true\naux_dim: 2\n"
+                  "node_trees: 6\nnode_depth: 4\nnode_tau: 10.0\ntemperature: 1.0\n")
+    torch.manual_seed(5)
+    f = CrossModalTransformer(config_path=str(fy), precision="fp32")
+    c = DeepTruthClassifier(config_path=str(cy), precision="fp32")
+    assert f.hidden == 1024 and f.fused_dim == 16 * 1024
+    with torch.no_grad():
+        g = torch.Generator().manual_seed(6)
+        for n, p in c.named_parameters():
+            if "gates" in n or "leaf_logits" in n:
+                p.add_(0.05 * torch.randn(p.shape, generator=g).to(p.device))
+    for m in list(f.modules()) + list(c.modules()):
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+    f.train(); c.train(); f._sync_dropout(); c._sync_dropout()
+    B = 24
+    batch = O.make_batch(B, seed=21)
+    step = FusedStep(f, c, B, precision="fp32", use_graph=False)
+    fus = {k: v.detach().cpu().clone() for k, v in f.state_dict().items()}
+    clf = {k: v.detach().cpu().clone() for k, v in c.state_dict().items()}
+    step.load_batch(to_cuda(batch))
+    step.train_fwd_bwd()
+    st = step.plan.state()
+    step.plan.check_error()
+    out, gf, gc = O.loss_and_grads(fus, clf, batch, dropout=0.0)
+    print(f"[H=1024] loss {st['loss']} vs {float(out['loss'])}; logits rel-err {O.rel_err(step.logits().cpu(), out['logits']):.2e}")
+    assert abs(st["loss"] - float(out["loss"])) / float(out["loss"]) < TOL["fp32"]
+    assert O.rel_err(step.logits().cpu(), out["logits"]) < TOL["fp32"]
+    assert O.rel_err(step.fused().cpu(), out["fused"]) < TOL["fp32"]
+    eng = step.engine
+    worst = 0.0
+    for prefix, grads in (("fusion", gf), ("clf", gc)):
+        for k, gref in grads.items():
+            if float(gref.norm()) == 0:
+                continue
+            e = O.rel_err(eng.grad_view(f"{prefix}.{k}").cpu(), gref)
+            worst = max(worst, e)
+            assert e < 5 * TOL["fp32"], (prefix, k, e)
+    print(f"[H=1024] worst per-parameter gradient rel-err {worst:.2e}")
