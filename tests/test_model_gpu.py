@@ -321,3 +321,53 @@ def test_hidden_1024_forward_and_gradients_match_oracle(tmp_path):
             worst = max(worst, e)
             assert e < 5 * TOL["fp32"], (prefix, k, e)
     print(f"[H=1024] worst per-parameter gradient rel-err {worst:.2e}")
+
+
+def test_no_gnn_no_aux_configuration_matches_oracle(tmp_path):
+    """fusion.yaml use_gnn: false (15 slots in fused_cat) and classifier.yaml use_aux: false (no rank-2 aux update,
+    plain K = 512 pre.0): the other shape of the tables, against the oracle, fp32 mode."""
+    fy, cy = tmp_path / "fusion.yaml", tmp_path / "classifier.yaml"
+    fy.write_text("hidden_dim: 512\ndropout: 0.0\nuse_gnn: false\ngnn_dim: 128\n")
+    cy.write_text("input_dim: 512\nhidden_dim: 512\ndropout: 0.0\nnum_classes: 2\nuse_aux: false\naux_dim: 2\n"
+                  "node_trees: 6\nnode_depth: 4\nnode_tau: 10.0\ntemperature: 1.0\n")
+    torch.manual_seed(8)
+    f = CrossModalTransformer(config_path=str(fy), precision="fp32")
+    c = DeepTruthClassifier(config_path=str(cy), precision="fp32")
+    assert f.fused_dim == 15 * 512 and "gnn_proj.weight" not in f.state_dict()
+    with torch.no_grad():
+        g = torch.Generator().manual_seed(9)
+        for n, p in c.named_parameters():
+            if "gates" in n or "leaf_logits" in n:
+                p.add_(0.05 * torch.randn(p.shape, generator=g).to(p.device))
+    for m in list(f.modules()) + list(c.modules()):
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+    f.train(); c.train(); f._sync_dropout(); c._sync_dropout()
+    B = 20
+    batch = O.make_batch(B, seed=22)
+    ob = dict(batch); ob["gnn_feat"] = None; ob["aux"] = None          # what the oracle (= the reference) sees
+    step = FusedStep(f, c, B, precision="fp32", use_graph=False)
+    fus = {k: v.detach().cpu().clone() for k, v in f.state_dict().items()}
+    clf = {k: v.detach().cpu().clone() for k, v in c.state_dict().items()}
+    step.load_batch(to_cuda(batch))
+    step.train_fwd_bwd()
+    st = step.plan.state()
+    step.plan.check_error()
+    fk, ck = O.trainable_keys()
+    fl = {k: v.clone().requires_grad_(k in fk) for k, v in fus.items()}
+    cl = {k: v.clone().requires_grad_(k in ck) for k, v in clf.items()}
+    feats = {k: ob[k] for k in O.FEAT_KEYS}
+    fo = O.fusion_forward(fl, feats, dropout=0.0)
+    co = O.classifier_forward(cl, fo["fused"], None, dropout=0.0)
+    loss = torch.nn.functional.cross_entropy(co["logits"], batch["label"])
+    loss.backward()
+    print(f"[no gnn/aux] loss {st['loss']} vs {float(loss)}; logits rel-err {O.rel_err(step.logits().cpu(), co['logits'].detach()):.2e}")
+    assert abs(st["loss"] - float(loss)) / float(loss) < TOL["fp32"]
+    assert O.rel_err(step.logits().cpu(), co["logits"].detach()) < TOL["fp32"]
+    eng = step.engine
+    for prefix, params in (("fusion", fl), ("clf", cl)):
+        for k, p in params.items():
+            if p.grad is None or float(p.grad.norm()) == 0:
+                continue
+            e = O.rel_err(eng.grad_view(f"{prefix}.{k}").cpu(), p.grad)
+            assert e < 5 * TOL["fp32"], (prefix, k, e)
