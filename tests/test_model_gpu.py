@@ -361,8 +361,8 @@ def test_no_gnn_no_aux_configuration_matches_oracle(tmp_path):
     co = O.classifier_forward(cl, fo["fused"], None, dropout=0.0)
     loss = torch.nn.functional.cross_entropy(co["logits"], batch["label"])
     loss.backward()
-    print(f"[no gnn/aux] loss {st['loss']} vs {float(loss)}; logits rel-err {O.rel_err(step.logits().cpu(), co['logits'].detach()):.2e}")
-    assert abs(st["loss"] - float(loss)) / float(loss) < TOL["fp32"]
+    print(f"[no gnn/aux] loss {st['loss']} vs {loss.item()}; logits rel-err {O.rel_err(step.logits().cpu(), co['logits'].detach()):.2e}")
+    assert abs(st["loss"] - loss.item()) / loss.item() < TOL["fp32"]
     assert O.rel_err(step.logits().cpu(), co["logits"].detach()) < TOL["fp32"]
     eng = step.engine
     for prefix, params in (("fusion", fl), ("clf", cl)):
