@@ -273,9 +273,8 @@ def run_b200_arm(args):
     loss_after = plan.state()["loss"]
 
     # ---- timed region 2: end to end through the public API (pinned host batch -> H2D -> step -> loss D2H) ----
-    stage_host = [step.host_staging() for _ in range(2)]
-    stage_dev = [torch.empty_like(step.static_in) for _ in range(2)]
-    lab_dev = [torch.empty_like(step.static_labels) for _ in range(2)]
+    # double-buffered feeding: the copy stream lands batch i+1 in one of the step's two input sets while the graph of
+    # batch i reads the other
     packed = []
     for hb in host_batches:
         st = step.host_staging()
@@ -294,23 +293,24 @@ def run_b200_arm(args):
     def e2e_step(i):
         s = i % 2
         src = packed[i % pool]
+        dst_in, dst_lab = step.input_set(s)
         with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(stage_free[s])
-            stage_dev[s].copy_(src["inputs"], non_blocking=True)
-            lab_dev[s].copy_(src["labels"], non_blocking=True)
+            copy_stream.wait_event(stage_free[s])          # the step that last read this input set has been enqueued and finished
+            dst_in.copy_(src["inputs"], non_blocking=True)
+            dst_lab.copy_(src["labels"], non_blocking=True)
             h2d_done[s].record(copy_stream)
         main.wait_event(h2d_done[s])
-        step.static_in.copy_(stage_dev[s], non_blocking=True)
-        step.static_labels.copy_(lab_dev[s], non_blocking=True)
-        stage_free[s].record(main)
         if world == 1:
-            step.train_step(from_cache=False)
+            step.train_step(from_cache=False, input_set=s)
         elif dp_mode == "peer":
-            step.train_step_dp(from_cache=False)
+            step.train_step_dp(from_cache=False, input_set=s)
         else:
+            if s == 1:                                     # the NCCL arm only has graphs over input set 0
+                step.static_in.copy_(dst_in, non_blocking=True); step.static_labels.copy_(dst_lab, non_blocking=True)
             step.train_fwd_bwd(from_cache=False)
             dist.all_reduce(eng.grads)
             step.optimizer_step(norm_from_slots=False)
+        stage_free[s].record(main)
         loss_host[i:i + 1].copy_(loss_view, non_blocking=True)
 
     for i in range(W):

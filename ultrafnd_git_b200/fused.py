@@ -98,22 +98,33 @@ class FusedStep:
         self.static_labels = torch.zeros(batch, dtype=torch.int64, device=dev)
         self.static_gather = torch.zeros(batch, dtype=torch.int64, device=dev)
         self._inp_static = self._make_static_inputs()
+        # A second input set for double-buffered host feeding: the H2D copy of batch i+1 lands in one set while the
+        # graph of batch i reads the other (no device-to-device staging copy on the critical path).
+        self.alt_in = torch.zeros_like(self.static_in)
+        self.alt_labels = torch.zeros_like(self.static_labels)
+        self._inp_alt = self._make_static_inputs(self.alt_in, self.alt_labels)
         self._inp_cache: Optional[FndInputs] = None
         self._cache: Optional[DeviceCache] = None
         self.engine.refresh_shadows(self.engine.param_version())
 
     # ------------------------------------------------------------------ inputs
-    def _make_static_inputs(self) -> FndInputs:
+    def _make_static_inputs(self, buf: Optional[torch.Tensor] = None, labels: Optional[torch.Tensor] = None) -> FndInputs:
+        buf = self.static_in if buf is None else buf
+        labels = self.static_labels if labels is None else labels
         inp = FndInputs()
-        base = self.static_in.data_ptr()
+        base = buf.data_ptr()
         for i in range(5):
             inp.x[i] = base + 4 * self.in_off[i]
             inp.pitch[i] = self.in_pitch
         inp.aux = base + 4 * self.aux_off
         inp.aux_pitch = self.in_pitch
-        inp.labels = self.static_labels.data_ptr()
+        inp.labels = labels.data_ptr()
         inp.gather = None
         return inp
+
+    def input_set(self, which: int):
+        """(inputs, labels) device buffers of input set 0 / 1 (layout of host_staging())."""
+        return (self.static_in, self.static_labels) if which == 0 else (self.alt_in, self.alt_labels)
 
     def host_staging(self) -> Dict[str, torch.Tensor]:
         """Pinned host buffers with the static device buffers' layout (for the end-to-end path)."""
@@ -159,8 +170,8 @@ class FusedStep:
         fn = {"train_step": lib.fnd_train_step, "train_fwd_bwd": lib.fnd_train_fwd_bwd, "eval_step": lib.fnd_eval_step}[entry]
         check(fn(h, ctypes.byref(inp), self.engine.stream_ptr()), "fnd_" + entry)
 
-    def _launch(self, entry: str, from_cache: bool) -> None:
-        inp = self._inp_cache if from_cache else self._inp_static
+    def _launch(self, entry: str, from_cache: bool, input_set: int = 0) -> None:
+        inp = self._inp_cache if from_cache else (self._inp_static if input_set == 0 else self._inp_alt)
         if inp is None:
             raise RuntimeError("attach_cache() first")
         if entry != "train_step_dp":
@@ -168,7 +179,7 @@ class FusedStep:
         if not self.use_graph:
             self._run(entry, inp)
             return
-        key = entry + ("/cache" if from_cache else "/static")
+        key = entry + ("/cache" if from_cache else ("/static" if input_set == 0 else "/alt"))
         g = self._graphs.get(key)
         if g is None:
             # warm-up on a side stream (first launches set function attributes), then capture
@@ -184,19 +195,19 @@ class FusedStep:
             self._graphs[key] = g
         g.replay()
 
-    def train_step(self, from_cache: bool = False) -> None:
-        """One optimizer step on the batch currently in the static buffers (or gathered from the cache)."""
-        self._launch("train_step", from_cache)
+    def train_step(self, from_cache: bool = False, input_set: int = 0) -> None:
+        """One optimizer step on the batch currently in the static buffers of `input_set` (or gathered from the cache)."""
+        self._launch("train_step", from_cache, input_set)
         self.plan.forward_id += 1
 
-    def train_step_dp(self, from_cache: bool = False) -> None:
+    def train_step_dp(self, from_cache: bool = False, input_set: int = 0) -> None:
         """One data-parallel optimizer step (every rank calls it with its own batch slice): forward + backward +
         peer-memory reduce-scatter / sharded AdamW / shadow all-gather, ONE CUDA graph per rank."""
         if not getattr(self, "_dp_bound", False):
             self.engine.dp_bind(self.plan)
             self._dp_bound = True
         self.engine._dp_plan = self.plan
-        self._launch("train_step_dp", from_cache)
+        self._launch("train_step_dp", from_cache, input_set)
         self.engine._dp_pending = self.dp_defer
         self.plan.forward_id += 1
 
