@@ -135,8 +135,44 @@ def save_case(name, seed, perturb, batch, dist, steps=0):
     print(f"wrote {path}: {os.path.getsize(path) / 1024:.1f} KiB, eval loss {float(rec['eval.loss']):.6f}")
 
 
+def save_large(name, seed, batch, data_seed):
+    """BASELINE.json configs[1]/[2] at full size (train batch 128, eval batch 1024): inputs are NOT stored (7 MB) — they
+    are regenerated from ``O.make_batch(batch, seed=data_seed)`` — only the reference's outputs are."""
+    torch.manual_seed(0)
+    fusion, clf, fus_p, clf_p = build_reference(seed, True)
+    b = O.make_batch(batch, seed=data_seed)
+    rec = {"meta_seed": np.array(seed), "meta_batch": np.array(batch), "meta_data_seed": np.array(data_seed),
+           "in_checksum": np.array([float(sum(v.double().sum() for v in b.values()))])}
+    fusion.eval(); clf.eval()
+    with torch.no_grad():
+        fo, co, loss = ref_forward(fusion, clf, b)
+    rec["eval.logits"] = co["logits"].numpy()
+    rec["eval.probs"] = co["probs"].numpy()
+    rec["eval.fused_rowsum"] = fo["fused"].double().sum(-1).numpy()
+    rec["eval.loss"] = np.array(float(loss))
+    for k, v in fo["forensic"].items():
+        rec["eval.forensic." + k] = v.numpy()
+    fusion.train(); clf.train()
+    set_dropout(fusion, 0.0); set_dropout(clf, 0.0)
+    params = list(fusion.parameters()) + list(clf.parameters())
+    fo, co, loss = ref_forward(fusion, clf, b)
+    loss.backward()
+    rec["train.loss"] = np.array(float(loss))
+    rec["train.grad_norm"] = np.array(float(torch.sqrt(sum((p.grad.double() ** 2).sum() for p in params if p.grad is not None))))
+    for prefix, mod in (("fusion", fusion), ("clf", clf)):
+        for k, p in mod.named_parameters():
+            if p.grad is not None:
+                rec[f"gnorm.{prefix}.{k}"] = np.array(float(p.grad.double().norm()))
+    os.makedirs(os.path.join(OUT, "large"), exist_ok=True)
+    path = os.path.join(OUT, "large", name + ".npz")
+    np.savez_compressed(path, **rec)
+    print(f"wrote {path}: {os.path.getsize(path) / 1024:.1f} KiB, eval loss {float(rec['eval.loss']):.6f}")
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
     save_case("eval_smoke_b4", seed=42, perturb=False, batch=4, dist="smoke")
     save_case("trained_cache_b16", seed=42, perturb=True, batch=16, dist="cache")
     save_case("train3_smoke_b8", seed=43, perturb=True, batch=8, dist="smoke", steps=3)
+    save_large("train_b128", seed=42, batch=128, data_seed=31)
+    save_large("eval_b1024", seed=42, batch=1024, data_seed=9)

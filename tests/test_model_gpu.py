@@ -371,3 +371,67 @@ def test_no_gnn_no_aux_configuration_matches_oracle(tmp_path):
                 continue
             e = O.rel_err(eng.grad_view(f"{prefix}.{k}").cpu(), p.grad)
             assert e < 5 * TOL["fp32"], (prefix, k, e)
+
+
+def _load_large(name):
+    z = np.load(os.path.join(GOLD, "large", name + ".npz"))
+    batch = O.make_batch(int(z["meta_batch"]), seed=int(z["meta_data_seed"]))
+    return z, batch
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_eval_b1024_against_reference_outputs(precision):
+    """BASELINE.json configs[2] against outputs of the UNMODIFIED reference itself (tests/golden/large/eval_b1024.npz):
+    logits rel-err <= 1e-3 (fp32 mode) / 2e-2 (bf16), identical argmax wherever the reference's margin is not a tie."""
+    z, batch = _load_large("eval_b1024")
+    f, c, _, _ = build_pair(int(z["meta_seed"]), True, precision)
+    f.eval(); c.eval()
+    B = int(z["meta_batch"])
+    step = FusedStep(f, c, B, precision=precision, use_graph=True)
+    step.load_batch(to_cuda(batch))
+    step.eval_step()
+    step.plan.check_error()
+    ref_logits = torch.from_numpy(z["eval.logits"])
+    lg = step.logits().cpu()
+    assert O.rel_err(lg, ref_logits) < TOL[precision]
+    assert O.rel_err(step.probs().cpu(), torch.from_numpy(z["eval.probs"])) < TOL[precision]
+    assert O.rel_err(step.fused().cpu().double().sum(-1), torch.from_numpy(z["eval.fused_rowsum"])) < TOL[precision]
+    rs = step.plan.buffer("rowstat", torch.float32, (B, 16)).cpu()
+    for col, key in ((0, "semantic_conflict"), (1, "emotion_intensity"), (2, "temporal_delay")):
+        assert O.rel_err(rs[:, col], torch.from_numpy(z["eval.forensic." + key])) < TOL[precision], key
+    margin = (ref_logits[:, 0] - ref_logits[:, 1]).abs()
+    agree = lg.argmax(-1) == ref_logits.argmax(-1)
+    assert bool(agree[margin > TOL[precision] * float(ref_logits.abs().max())].all())
+    if precision == "fp32":
+        assert bool(agree.all())
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_train_b128_against_reference_outputs(precision):
+    """BASELINE.json configs[1] (the bench batch) against the reference's own loss and per-parameter gradient norms
+    (tests/golden/large/train_b128.npz), dropout off."""
+    z, batch = _load_large("train_b128")
+    f, c, _, _ = build_pair(int(z["meta_seed"]), True, precision, dropout_off=True)
+    f.train(); c.train(); f._sync_dropout(); c._sync_dropout()
+    B = int(z["meta_batch"])
+    step = FusedStep(f, c, B, precision=precision, use_graph=True)
+    step.load_batch(to_cuda(batch))
+    step.train_fwd_bwd()
+    st = step.plan.state()
+    step.plan.check_error()
+    tol = TOL[precision]
+    assert abs(st["loss"] - float(z["train.loss"])) / float(z["train.loss"]) < tol
+    assert abs(st["grad_norm"] - float(z["train.grad_norm"])) / float(z["train.grad_norm"]) < max(tol, 2e-3)
+    eng = step.engine
+    worst = 0.0
+    for key in z.files:
+        if not key.startswith("gnorm."):
+            continue
+        name = key[len("gnorm."):]
+        ref = float(z[key])
+        if ref == 0.0:
+            continue
+        got = float(eng.grad_view(name).double().norm())
+        worst = max(worst, abs(got - ref) / ref)
+        assert abs(got - ref) / ref < (5e-4 if precision == "fp32" else 5e-2), (name, got, ref)
+    print(f"[train_b128/{precision}] loss {st['loss']} vs {float(z['train.loss'])}; worst gradient-norm rel-err {worst:.2e}")

@@ -116,3 +116,35 @@ def test_explicit_dropout_masks_are_applied():
         # fuse0 fully dropped => fused = gelu(bias of fuse_mlp.3)
         expect = torch.nn.functional.gelu(fus["fuse_mlp.3.bias"]).expand(B, -1)
     assert O.rel_err(out["fused"], expect) < 1e-6
+
+
+# ---- full-size cases (BASELINE.json configs[1] train batch 128, configs[2] eval batch 1024): reference OUTPUTS only ----
+LARGE = os.path.join(GOLD, "large")
+
+
+def load_large(name):
+    z = np.load(os.path.join(LARGE, name + ".npz"))
+    fus, clf = O.init_params(int(z["meta_seed"]))
+    O.perturb_node_head(clf)
+    batch = O.make_batch(int(z["meta_batch"]), seed=int(z["meta_data_seed"]))
+    chk = float(sum(v.double().sum() for v in batch.values()))
+    assert abs(chk - float(z["in_checksum"][0])) <= 1e-9 * max(1.0, abs(chk)), "regenerated inputs differ from the fixture's"
+    return z, fus, clf, batch
+
+
+@pytest.mark.parametrize("name", ["train_b128", "eval_b1024"])
+def test_full_size_oracle_matches_reference(name):
+    z, fus, clf, batch = load_large(name)
+    with torch.no_grad():
+        out = O.model_forward(fus, clf, batch, masks=None)
+    assert O.rel_err(out["logits"], torch.from_numpy(z["eval.logits"])) < 1e-5
+    assert O.rel_err(out["probs"], torch.from_numpy(z["eval.probs"])) < 2e-6
+    assert O.rel_err(out["fused"].double().sum(-1), torch.from_numpy(z["eval.fused_rowsum"])) < 1e-5
+    assert torch.equal(out["logits"].argmax(-1), torch.from_numpy(z["eval.logits"]).argmax(-1))
+    assert abs(float(out["loss"]) - float(z["eval.loss"])) < 1e-6
+    out2, gf, gc = O.loss_and_grads(fus, clf, batch, dropout=0.0)
+    assert abs(float(out2["loss"]) - float(z["train.loss"])) < 1e-6
+    for prefix, grads in (("fusion", gf), ("clf", gc)):
+        for k, g in grads.items():
+            ref = float(z[f"gnorm.{prefix}.{k}"])
+            assert abs(float(g.double().norm()) - ref) <= 2e-5 * ref + 1e-12, (prefix, k)
