@@ -19,7 +19,10 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     out_dir = os.path.join(tempfile.gettempdir(), "fnd_dp_trainer_check")
-    cache = synthetic_cache(n=640, seed=3)
+    # n and batch size deliberately NOT divisible by the world size; 449 training rows = 7 x 64 + 1, so in the last global
+    # batch every rank but 0 has an empty shard and runs the zero-weight padding step
+    cache = synthetic_cache(n=642, seed=3)
+    assert len(cache["split"][0]) == 449
     cfg = TrainConfig(data_root="unused", ocr_phrase_pkl=None, out_dir=out_dir, batch_size=64, epochs=3, lr=5e-4)
     tr = ForensicTrainer(cfg, cache=cache)
     assert tr.dp_peer, "expected the peer-memory optimizer step with the NCCL backend"
@@ -36,6 +39,11 @@ def main():
         return all(torch.equal(p, parts[0]) for p in parts)
     ok = same_everywhere(eng.shadow_hi) and same_everywhere(eng.params[:eng.n_hot])
     res = tr.test()
+    # every rank must report the same numbers (metrics are gathered, never rank-local)
+    t = torch.tensor([best, res["test_auc"], res["test_loss"]], dtype=torch.float64, device=dev)
+    parts = [torch.zeros_like(t) for _ in range(world)]
+    dist.all_gather(parts, t)
+    ok = ok and all(torch.equal(p, parts[0]) for p in parts)
     if rank == 0:
         print(f"[dp_trainer_check world={world}] best val auc {best:.3f}, test auc {res['test_auc']:.3f}, replicas identical: {ok}")
     good = ok and best > 0.9 and res["test_auc"] > 0.85

@@ -136,3 +136,50 @@ def test_sharded_optimizer_equals_replicated_optimizer():
     mp.spawn(_zero1_worker, args=(2, port, ret), nprocs=2, join=True)
     assert ret["norm_err"] < 1e-12, ret["norm_err"]
     assert ret["equal"] is True or ret["equal"] < 1e-9, ret["equal"]
+
+
+# ------------------------------------------------------------------------------------------------------------
+# Epoch bookkeeping under data parallelism with n and batch_size NOT divisible by the world size:
+# ragged shards are always gathered, every rank ends up with the same rows, the same mean-of-batch-means loss
+# (forensic_trainer.py:301,316) and therefore the same early-stopping / checkpoint decisions.
+# ------------------------------------------------------------------------------------------------------------
+def _ragged_worker(rank, world, port, ret):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from ultrafnd_git_b200.trainer import gather_ragged, mean_of_batch_means, shard_indices
+    n, bs = 23, 5                                  # 5 batches: 5,5,5,5,3 -> shards 3/2, ..., 2/1
+    g = torch.Generator().manual_seed(3)
+    row_loss = torch.rand(n, generator=g)           # "loss of sample i" as every rank would compute it
+    order = torch.randperm(n, generator=g)
+    cap = (n + world - 1) // world + (n + bs - 1) // bs + 1
+    loss_rows, ids, bid = torch.zeros(cap), torch.zeros(cap, dtype=torch.int64), torch.zeros(cap, dtype=torch.int64)
+    done = nb = 0
+    for bno, s0 in enumerate(range(0, n, bs)):
+        gidx = order[s0:s0 + bs]
+        nb += 1
+        local = shard_indices(gidx, rank, world)
+        k = local.numel()
+        loss_rows[done:done + k] = row_loss[local]
+        ids[done:done + k] = local
+        bid[done:done + k] = bno
+        done += k
+    (lr, ii, bb), total = gather_ragged([loss_rows, ids, bid], done, world)
+    mine = mean_of_batch_means(lr, bb, nb)
+    want = float(torch.stack([row_loss[order[s0:s0 + bs]].double().mean() for s0 in range(0, n, bs)]).mean())
+    ret[rank] = (total, sorted(ii.tolist()) == list(range(n)), mine, want, float(row_loss.mean()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_ragged_epoch_gather_is_identical_on_every_rank():
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_ragged_worker, args=(2, port, ret), nprocs=2, join=True)
+    (t0, ok0, m0, want, rowmean), (t1, ok1, m1, _, _) = ret[0], ret[1]
+    assert t0 == t1 == 23 and ok0 and ok1
+    assert m0 == m1, "ranks must agree bit-for-bit (same rows, same order)"
+    assert abs(m0 - want) < 1e-6
+    assert abs(want - rowmean) > 1e-4, "case must distinguish mean-of-batch-means from the per-row mean"

@@ -15,7 +15,7 @@ def test_fit_and_test_on_synthetic_cache(tmp_path):
     cfg = TrainConfig(data_root="unused", ocr_phrase_pkl=None, out_dir=str(tmp_path), batch_size=64, epochs=4, lr=5e-4)
     tr = ForensicTrainer(cfg, cache=cache)
     assert tuple(tr.cache["gnn_Z"].shape) == (600, 128)
-    l0, m0 = tr._epoch_loop("val")
+    l0, m0 = tr._epoch_loop(tr.val_loader, "val")
     best = tr.fit()
     l1, m1 = tr._epoch_loop("val")
     print(f"val loss {l0:.4f} -> {l1:.4f}; val auc {m0['auc']:.3f} -> {m1['auc']:.3f}; best {best:.3f}")
@@ -69,3 +69,76 @@ def test_resume_continues_bit_for_bit(tmp_path):
     assert la == lb
     assert torch.equal(pa, b.engine.params)
     assert a._last_step.plan.state()["step"] == b._last_step.plan.state()["step"] > 0
+
+
+def test_fit_after_load_resume_continues_the_run(tmp_path):
+    """fit() after load_resume() must continue with epoch+1 (same shuffle seeds, the StepLR value of an
+    uninterrupted run, early-stopping counters kept) — three epochs in one go == two epochs, save, fresh process state,
+    load, fit to three."""
+    cache = synthetic_cache(n=300, seed=6)
+    mk = lambda d, e: TrainConfig(data_root="unused", ocr_phrase_pkl=None, out_dir=os.path.join(str(tmp_path), d),
+                                  batch_size=32, epochs=e, lr=3e-4)
+    a = ForensicTrainer(mk("a", 3), cache=cache)
+    a.fit()
+    b = ForensicTrainer(mk("b", 2), cache=cache)
+    b.fit()
+    path = os.path.join(str(tmp_path), "resume.pt")
+    b.save_resume(path)
+    c = ForensicTrainer(mk("c", 3), cache=cache)
+    c.load_resume(path)
+    assert c.epoch == 2
+    c.fit()
+    assert c.epoch == 3 and abs(c.lr - 3e-4 * 0.7) < 1e-12 and abs(a.lr - c.lr) < 1e-12
+    assert torch.equal(a.engine.params, c.engine.params)
+    assert a.best_val_auc == c.best_val_auc and a.no_improve == c.no_improve
+
+
+def test_epoch_loss_is_mean_of_batch_means():
+    """forensic_trainer.py:301,316: the epoch loss is np.mean of the per-batch mean losses (differs from the per-row mean
+    when the last batch is short); _epoch_loop keeps the reference's (loader, split) signature."""
+    cache = synthetic_cache(n=200, seed=7)        # val split = 30 rows; batch 16 -> batches of 16 and 14
+    cfg = TrainConfig(data_root="unused", ocr_phrase_pkl=None, out_dir="/tmp/fnd_out_bm", batch_size=16, epochs=0)
+    tr = ForensicTrainer(cfg, cache=cache)
+    loss, m = tr._epoch_loop(tr.val_loader, "val")
+    tr.fusion.eval(); tr.clf.eval()
+    per_batch = []
+    with torch.no_grad():
+        for batch in tr.val_loader:
+            out = tr._forward_batch(batch, "val")
+            per_batch.append(float(torch.nn.functional.cross_entropy(out["logits"], out["y"])))
+    assert len(per_batch) == 2
+    assert abs(loss - float(np.mean(per_batch))) < 1e-5
+    assert tr._epoch_loop("val")[0] == loss
+
+
+def test_paired_modules_backward_matches_fused_step():
+    """trainer._forward_batch(...) followed by loss.backward() (module-level autograd over the PAIRED
+    modules) must work and give the fused step's gradients."""
+    cache = synthetic_cache(n=128, seed=8)
+    cfg = TrainConfig(data_root="unused", ocr_phrase_pkl=None, out_dir="/tmp/fnd_out_pb", batch_size=16, epochs=0)
+    tr = ForensicTrainer(cfg, cache=cache, precision="fp32")
+    for m in list(tr.fusion.modules()) + list(tr.clf.modules()):
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+    tr.fusion.train(); tr.clf.train(); tr.fusion._sync_dropout(); tr.clf._sync_dropout()
+    batch = next(iter(tr.val_loader))
+    out = tr._forward_batch(batch, "val")
+    loss = torch.nn.functional.cross_entropy(out["logits"], out["y"])
+    loss.backward()
+    g_mod = {n: p.grad.clone() for n, p in list(tr.fusion.named_parameters()) + list(tr.clf.named_parameters())
+             if p.grad is not None}
+    assert "fuse_mlp.0.weight" in g_mod and "pre.0.weight" in g_mod
+    st = tr._step_for(len(batch["label"]))
+    st.static_gather.copy_(torch.as_tensor(tr.va_idx)[batch["index"]].cuda())
+    st.train_fwd_bwd(from_cache=True)
+    eng = tr.engine
+    worst = 0.0
+    for prefix, mod in (("fusion.", tr.fusion), ("clf.", tr.clf)):
+        for n, p in mod.named_parameters():
+            if p.grad is None:
+                continue
+            ref = eng.grad_view(prefix + n)
+            err = float((p.grad - ref).norm() / (ref.norm() + 1e-12))
+            worst = max(worst, err)
+    assert abs(float(loss) - st.plan.state()["loss"]) < 1e-5
+    assert worst < 1e-4, worst

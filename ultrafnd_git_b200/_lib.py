@@ -20,6 +20,8 @@ _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 _REPO_DIR = os.path.dirname(_PKG_DIR)
 LIB_PATH = os.path.join(_PKG_DIR, "libfnd_b200.so")
 HEADER_PATH = os.path.join(_REPO_DIR, "include", "fnd_b200.h")
+SEQ_HEADER_PATH = os.path.join(_REPO_DIR, "include", "fnd_seq_b200.h")
+HEADER_PATHS = [HEADER_PATH, SEQ_HEADER_PATH]
 CSRC_DIR = os.path.join(_PKG_DIR, "csrc")
 
 NVCC_FLAGS = [
@@ -31,11 +33,11 @@ NVCC_FLAGS = [
 
 
 def _sources() -> List[str]:
-    return [os.path.join(CSRC_DIR, "fnd_api.cu")]
+    return [os.path.join(CSRC_DIR, "fnd_api.cu"), os.path.join(CSRC_DIR, "fnd_seq_api.cu")]
 
 
 def _deps() -> List[str]:
-    out = [HEADER_PATH]
+    out = list(HEADER_PATHS)
     for fn in sorted(os.listdir(CSRC_DIR)):
         if fn.endswith((".cu", ".cuh", ".h")):
             out.append(os.path.join(CSRC_DIR, fn))
@@ -54,7 +56,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB_PATH
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + _sources()
+    cmd = [nvcc] + NVCC_FLAGS + ["--threads", "2"] + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + _sources()
     proc = subprocess.run(cmd, cwd=_REPO_DIR, capture_output=True, text=True)
     if proc.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + proc.stdout + proc.stderr)
@@ -64,12 +66,15 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 def declared_symbols() -> List[str]:
-    """Every function name declared in include/fnd_b200.h."""
-    with open(HEADER_PATH, "r", encoding="utf-8") as f:
-        src = f.read()
-    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    src = re.sub(r"//[^\n]*", "", src)
-    return sorted(set(re.findall(r"\b(fnd_[a-z0-9_]+)\s*\(", src)))
+    """Every function name declared in include/fnd_b200.h and include/fnd_seq_b200.h."""
+    names = set()
+    for path in HEADER_PATHS:
+        with open(path, "r", encoding="utf-8") as f:
+            src = f.read()
+        src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+        src = re.sub(r"//[^\n]*", "", src)
+        names.update(re.findall(r"\b(fnd_[a-z0-9_]+)\s*\(", src))
+    return sorted(names)
 
 
 _lib: Optional[ctypes.CDLL] = None
@@ -142,6 +147,17 @@ def _signatures() -> Dict[str, tuple]:
         "fnd_profile_end": (_c_int, [_c_void_p, _c_void_p, ctypes.c_char_p, P(_c_float), _c_int, P(_c_int)]),
         "fnd_export_dropout_mask": (_c_int, [_c_void_p, _c_int, _c_void_p, ll, _c_void_p]),
         "fnd_check_error": (_c_int, [_c_void_p, _c_void_p]),
+        # ---- sequence front-end (include/fnd_seq_b200.h)
+        "fnd_seq_init": (_c_int, []),
+        "fnd_seq_cast_bf16": (_c_int, [_c_void_p, _c_void_p, ll, _c_void_p]),
+        "fnd_seq_linear": (_c_int, [_c_void_p, _c_int, _c_void_p, _c_int, _c_void_p, _c_void_p, _c_int, _c_int, _c_void_p, _c_int,
+                                    _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_void_p, _c_void_p]),
+        "fnd_seq_layernorm": (_c_int, [_c_void_p, _c_int, _c_void_p, _c_void_p, _c_float, _c_void_p, _c_int, _c_int, _c_int, _c_void_p]),
+        "fnd_seq_coattn_forward": (_c_int, [_c_void_p, _c_int, _c_int, _c_void_p, _c_int, _c_int, _c_void_p, _c_int, _c_int,
+                                            _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_float, _c_void_p, _c_int,
+                                            _c_void_p, _c_void_p, _c_void_p]),
+        "fnd_seq_masked_mean_pool": (_c_int, [_c_void_p, _c_int, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p, _c_int,
+                                              _c_void_p, _c_int, _c_void_p]),
         "fnd_gemm_scratch_bytes": (_c_size_t, [_c_int] * 4),
         "fnd_gemm_bf16_probe": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_void_p, _c_void_p, _c_int, _c_int,
                                          _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,
@@ -165,9 +181,9 @@ def load() -> ctypes.CDLL:
     sigs = _signatures()
     for name in declared_symbols():
         if not hasattr(lib, name):
-            raise RuntimeError(f"libfnd_b200.so does not export {name} declared in include/fnd_b200.h")
+            raise RuntimeError(f"libfnd_b200.so does not export {name} declared in include/*.h")
         if name not in sigs:
-            raise RuntimeError(f"{name} is declared in include/fnd_b200.h but has no ctypes signature in _lib.py")
+            raise RuntimeError(f"{name} is declared in include/*.h but has no ctypes signature in _lib.py")
         fn = getattr(lib, name)
         fn.restype, fn.argtypes = sigs[name]
     _lib = lib

@@ -254,7 +254,7 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
 // under key (seed, stream). Dropout keeps element i iff word(i & 3) of counter (i >> 2) >= p * 2^32,
 // so forward and backward regenerate identical masks from (seed, stream, element index) alone.
 // ------------------------------------------------------------------------------------------
-__device__ __noinline__ uint4 philox4x32_10(uint64_t ctr, uint32_t key0, uint32_t key1, uint32_t stream) {
+static __device__ __noinline__ uint4 philox4x32_10(uint64_t ctr, uint32_t key0, uint32_t key1, uint32_t stream) {
   uint32_t c0 = static_cast<uint32_t>(ctr), c1 = static_cast<uint32_t>(ctr >> 32), c2 = stream, c3 = 0x5eedf17du;
   uint32_t k0 = key0, k1 = key1;
 #pragma unroll

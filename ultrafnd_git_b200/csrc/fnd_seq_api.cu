@@ -1,0 +1,149 @@
+// fnd_seq_api.cu — C-ABI of the sequence front-end (see include/fnd_seq_b200.h for the contract of every entry point).
+#include "../../include/fnd_seq_b200.h"
+#include "fnd_seq_attn.cuh"
+#include "fnd_seq_gemm.cuh"
+#include "fnd_seq_rows.cuh"
+#include "fnd_tmap.h"
+#include <math.h>
+
+using namespace fnd;
+
+#define SEQ_CUDA_OK(expr)                                        \
+  do {                                                           \
+    cudaError_t _e = (expr);                                     \
+    if (_e != cudaSuccess) return -1000 - static_cast<int>(_e);  \
+  } while (0)
+
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+static int seq_num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;
+  }
+  return n;
+}
+
+extern "C" {
+
+int fnd_seq_init(void) {
+  static bool done = false;
+  if (done) return 0;
+  SEQ_CUDA_OK(cudaFuncSetAttribute(seq_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   kSeqGemmRingBudget + kSeqGemmHeader + 1024));
+  SEQ_CUDA_OK(cudaFuncSetAttribute(seq_attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBytes));
+  done = true;
+  return 0;
+}
+
+int fnd_seq_cast_bf16(const float* x, void* y_bf16, long long n, void* stream) {
+  if (!x || !y_bf16 || n < 0 || (n & 7) || !aligned16(x) || !aligned16(y_bf16)) return -1;
+  if (n == 0) return 0;
+  const size_t n8 = static_cast<size_t>(n) >> 3;
+  const int grid = static_cast<int>(n8 / 256 + 1 < static_cast<size_t>(seq_num_sms()) * 8 ? n8 / 256 + 1 : static_cast<size_t>(seq_num_sms()) * 8);
+  seq_cast_bf16_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, static_cast<__nv_bfloat16*>(y_bf16), n8);
+  SEQ_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int fnd_seq_linear(const void* a_bf16, int a_pitch, const void* w_bf16, int w_pitch, const float* bias,
+                   const void* resid_bf16, int resid_pitch, int act, void* out_bf16, int out_pitch, float* out_f32,
+                   int f32_pitch, int M, int N, int K, int* err_flag, void* stream) {
+  if (!a_bf16 || !w_bf16 || (!out_bf16 && !out_f32) || M <= 0 || N <= 0 || K <= 0) return -1;
+  if ((N & 7) || (K & 7) || (a_pitch & 7) || (w_pitch & 7) || a_pitch < K || w_pitch < K) return -2;
+  if (out_bf16 && ((out_pitch & 7) || out_pitch < N || !aligned16(out_bf16))) return -3;
+  if (out_f32 && ((f32_pitch & 3) || f32_pitch < N || !aligned16(out_f32))) return -3;
+  if (resid_bf16 && ((resid_pitch & 7) || resid_pitch < N || !aligned16(resid_bf16))) return -3;
+  if (bias && !aligned16(bias)) return -3;
+  { int r = fnd_seq_init(); if (r) return r; }
+  SeqGemmParams P;
+  memset(&P, 0, sizeof(P));
+  P.M = M; P.N = N; P.K = K;
+  P.tiles_m = cdiv(M, kSeqGemmBM);
+  // widest tile that still gives every SM work; 256 columns keep one UMMA busy for 128 cycles
+  int bn = 256;
+  const int sms = seq_num_sms();
+  if (N % 256 != 0 && N <= 128) bn = N <= 64 ? 64 : 128;
+  while (bn > 64 && P.tiles_m * cdiv(N, bn) < sms) bn >>= 1;
+  P.bn = bn;
+  P.tiles_n = cdiv(N, bn);
+  P.kblocks = cdiv(K, kSeqGemmBK);
+  P.stage_bytes = kSeqGemmBM * kSeqGemmBK * 2 + bn * kSeqGemmBK * 2;
+  P.nstages = kSeqGemmRingBudget / P.stage_bytes;
+  if (P.nstages > kSeqGemmMaxStages) P.nstages = kSeqGemmMaxStages;
+  P.bias = bias;
+  P.resid = static_cast<const __nv_bfloat16*>(resid_bf16); P.resid_pitch = resid_pitch;
+  P.act = act;
+  P.out_bf = static_cast<__nv_bfloat16*>(out_bf16); P.out_pitch = out_pitch;
+  P.out_f32 = out_f32; P.f32_pitch = f32_pitch;
+  P.err = err_flag;
+  int r = encode_bf16_2d(&P.tmA, a_bf16, K, M, a_pitch, 64, kSeqGemmBM);
+  if (r) return r;
+  r = encode_bf16_2d(&P.tmB, w_bf16, K, N, w_pitch, 64, bn);
+  if (r) return r;
+  const int ntiles = P.tiles_m * P.tiles_n;
+  const int grid = ntiles < sms ? ntiles : sms;
+  const size_t smem = static_cast<size_t>(P.nstages) * P.stage_bytes + kSeqGemmHeader + 1024;
+  seq_gemm_kernel<<<grid, kSeqGemmThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(P);
+  SEQ_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int fnd_seq_layernorm(const void* x_bf16, int x_pitch, const float* gamma, const float* beta, float eps, void* y_bf16,
+                      int y_pitch, int M, int d, void* stream) {
+  if (!x_bf16 || !gamma || !beta || !y_bf16 || M <= 0 || d <= 0) return -1;
+  if ((d & 7) || d > kLnMaxChunks * 256 || (x_pitch & 7) || (y_pitch & 7) || x_pitch < d || y_pitch < d) return -2;
+  if (!aligned16(x_bf16) || !aligned16(y_bf16) || !aligned16(gamma) || !aligned16(beta)) return -3;
+  LnParams P{static_cast<const __nv_bfloat16*>(x_bf16), x_pitch, gamma, beta, eps, static_cast<__nv_bfloat16*>(y_bf16), y_pitch, M, d};
+  seq_layernorm_kernel<<<cdiv(M, 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(P);
+  SEQ_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int fnd_seq_coattn_forward(const void* q_bf16, int q_pitch, int q_col0, const void* k_bf16, int k_pitch, int k_col0,
+                           const void* v_bf16, int v_pitch, int v_col0, const int* kv_len, const unsigned char* kv_mask,
+                           int B, int H, int Lq, int Lk, float scale, void* out_bf16, int out_pitch, float* lse,
+                           int* err_flag, void* stream) {
+  if (!q_bf16 || !k_bf16 || !v_bf16 || !out_bf16 || B <= 0 || H <= 0 || Lq <= 0 || Lk <= 0) return -1;
+  if ((q_pitch & 7) || (k_pitch & 7) || (v_pitch & 7) || (out_pitch & 7) || (q_col0 & 7) || (k_col0 & 7) || (v_col0 & 7)) return -2;
+  if (q_col0 + H * kAttnD > q_pitch || k_col0 + H * kAttnD > k_pitch || v_col0 + H * kAttnD > v_pitch || H * kAttnD > out_pitch) return -2;
+  if (!aligned16(out_bf16) || !(scale > 0.f) || H > 65535 || B > 65535) return -3;
+  { int r = fnd_seq_init(); if (r) return r; }
+  AttnParams P;
+  memset(&P, 0, sizeof(P));
+  int r = encode_bf16_3d(&P.tmQ, q_bf16, static_cast<uint64_t>(q_pitch), Lq, B, q_pitch, kAttnBQ);
+  if (r) return r;
+  r = encode_bf16_3d(&P.tmK, k_bf16, static_cast<uint64_t>(k_pitch), Lk, B, k_pitch, kAttnBK);
+  if (r) return r;
+  r = encode_bf16_3d(&P.tmV, v_bf16, static_cast<uint64_t>(v_pitch), Lk, B, v_pitch, kAttnBK);
+  if (r) return r;
+  P.B = B; P.H = H; P.Lq = Lq; P.Lk = Lk;
+  P.q_col0 = q_col0; P.k_col0 = k_col0; P.v_col0 = v_col0;
+  P.kv_len = kv_len; P.kv_mask = kv_mask;
+  P.scale = scale;
+  P.scale_log2 = scale * 1.44269504088896340736f;
+  P.out = static_cast<__nv_bfloat16*>(out_bf16); P.out_pitch = out_pitch;
+  P.lse = lse;
+  P.err = err_flag;
+  dim3 grid(static_cast<unsigned>(cdiv(Lq, kAttnBQ)), static_cast<unsigned>(H), static_cast<unsigned>(B));
+  seq_attn_fwd_kernel<<<grid, kAttnThreads, kAttnSmemBytes, reinterpret_cast<cudaStream_t>(stream)>>>(P);
+  SEQ_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int fnd_seq_masked_mean_pool(const void* x_bf16, int x_pitch, const unsigned char* mask, const int* len, int B, int L,
+                             int d, float* out_f32, int f32_pitch, void* out_bf16, int bf_pitch, void* stream) {
+  if (!x_bf16 || (!out_f32 && !out_bf16) || B <= 0 || L <= 0 || d <= 0) return -1;
+  if ((d & 7) || (x_pitch & 7) || x_pitch < d || !aligned16(x_bf16) || B > 65535) return -2;
+  PoolParams P{static_cast<const __nv_bfloat16*>(x_bf16), x_pitch, mask, len, B, L, d, out_f32, f32_pitch,
+               static_cast<__nv_bfloat16*>(out_bf16), bf_pitch};
+  dim3 grid(static_cast<unsigned>(cdiv(d, 64)), static_cast<unsigned>(B));
+  seq_masked_mean_pool_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(P);
+  SEQ_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // extern "C"

@@ -42,4 +42,22 @@ inline int encode_bf16_2d(CUtensorMap* out, const void* base, uint64_t inner, ui
   return r == CUDA_SUCCESS ? 0 : -100 - static_cast<int>(r);
 }
 
+// 3-D bf16 tensor [batch][rows][cols] over a row-major [batch * rows, pitch] matrix: dim0 = `cols` contiguous elements,
+// dim1 = `rows` (stride pitch), dim2 = `batch` (stride rows * pitch). Box = 64 x box_rows x 1, 128-byte swizzle. Rows
+// past `rows` are zero-filled PER SAMPLE, so a tile that overhangs a sequence never sees the next sample's tokens.
+inline int encode_bf16_3d(CUtensorMap* out, const void* base, uint64_t cols, uint64_t rows, uint64_t batch,
+                          uint64_t pitch_elems, uint32_t box_rows) {
+  PFN_encodeTiled fn = get_encode_fn();
+  if (!fn) return -1;
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (pitch_elems * 2) % 16 != 0) return -2;
+  cuuint64_t dims[3] = {cols, rows, batch};
+  cuuint64_t strides[2] = {pitch_elems * 2, rows * pitch_elems * 2};
+  cuuint32_t box[3] = {64, box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -100 - static_cast<int>(r);
+}
+
 }  // namespace fnd

@@ -117,8 +117,20 @@ class Plan:
         self.workspace = torch.zeros(nbytes + 256, dtype=torch.uint8, device=engine.device)
         self._ws_base = (self.workspace.data_ptr() + 255) // 256 * 256
         self._ws_shift = self._ws_base - self.workspace.data_ptr()
-        self.forward_id = 0
+        # Activation generations: the fusion stage and the classifier stage save their activations in disjoint workspace
+        # buffers, so each has its own counter (a paired classifier forward must not invalidate the fusion forward that
+        # fed it). The fused entry points overwrite both.
+        self.fusion_id = 0
+        self.clf_id = 0
         self.bind()
+
+    @property
+    def forward_id(self) -> int:
+        return self.fusion_id + self.clf_id
+
+    def bump_all(self) -> None:
+        self.fusion_id += 1
+        self.clf_id += 1
 
     def bind(self) -> None:
         e = self.engine

@@ -198,7 +198,7 @@ class FusedStep:
     def train_step(self, from_cache: bool = False, input_set: int = 0) -> None:
         """One optimizer step on the batch currently in the static buffers of `input_set` (or gathered from the cache)."""
         self._launch("train_step", from_cache, input_set)
-        self.plan.forward_id += 1
+        self.plan.bump_all()
 
     def train_step_dp(self, from_cache: bool = False, input_set: int = 0) -> None:
         """One data-parallel optimizer step (every rank calls it with its own batch slice): forward + backward +
@@ -209,12 +209,12 @@ class FusedStep:
         self.engine._dp_plan = self.plan
         self._launch("train_step_dp", from_cache, input_set)
         self.engine._dp_pending = self.dp_defer
-        self.plan.forward_id += 1
+        self.plan.bump_all()
 
     def train_fwd_bwd(self, from_cache: bool = False) -> None:
         """Forward + loss + backward only (gradients left in the arena for an all-reduce)."""
         self._launch("train_fwd_bwd", from_cache)
-        self.plan.forward_id += 1
+        self.plan.bump_all()
 
     def dp_optimizer_step(self) -> None:
         """Sharded clip + AdamW over NVLink peer memory (Engine.enable_symmetric must have been called): the gradients
@@ -240,7 +240,7 @@ class FusedStep:
 
     def eval_step(self, from_cache: bool = False) -> None:
         self._launch("eval_step", from_cache)
-        self.plan.forward_id += 1
+        self.plan.bump_all()
 
     # ------------------------------------------------------------------ results (zero-copy views of the workspace)
     def logits(self) -> torch.Tensor:

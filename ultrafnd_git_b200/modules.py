@@ -136,13 +136,13 @@ class _FusionFn(torch.autograd.Function):
         inp, keep = E.make_inputs(feats, use_gnn=eng.dims.use_gnn)
         training = bool(module.training and (eng.dims.fusion_dropout > 0))
         check(eng.lib.fnd_fusion_forward(plan.handle, ctypes.byref(inp), int(training), eng.stream_ptr()), "fnd_fusion_forward")
-        plan.forward_id += 1
+        plan.fusion_id += 1
         H = eng.dims.hidden
         fused = plan.buffer("fused", torch.float32, (B, H)).clone()
         logits = plan.buffer("fusion_logits", torch.float32, (B, 2)).clone()
         rs = plan.buffer("rowstat", torch.float32, (B, 16))
         sc, emo, delay = rs[:, 0].clone(), rs[:, 1].clone(), rs[:, 2].clone()
-        ctx.module, ctx.plan, ctx.fid, ctx.nparams = module, plan, plan.forward_id, len(params)
+        ctx.module, ctx.plan, ctx.fid, ctx.nparams = module, plan, plan.fusion_id, len(params)
         ctx.mark_non_differentiable(logits, sc, emo, delay)
         return fused, logits, sc, emo, delay
 
@@ -150,7 +150,7 @@ class _FusionFn(torch.autograd.Function):
     def backward(ctx, dfused, *_unused):
         module, plan = ctx.module, ctx.plan
         eng: E.Engine = module._engine
-        if plan.forward_id != ctx.fid:
+        if plan.fusion_id != ctx.fid:
             raise RuntimeError("CrossModalTransformer backward: the activations saved in this batch size's plan were "
                                "overwritten by a later forward; run backward before the next forward of the same batch size")
         dfused = dfused.to(torch.float32).contiguous()
@@ -208,10 +208,21 @@ class CrossModalTransformer(_EngineModule):
         if p != self._engine.dims.fusion_dropout:
             self._engine.set_dropout(fusion_p=p)
 
+    def attach_sequence_frontend(self, frontend) -> None:
+        """Tier B hook: with a ``SequenceFrontEnd`` attached, ``forward`` accepts 3-D feature
+        tensors (B, L, D_in) (+ optional ``<key>_mask``) and pools them to the (B, D) vectors first; 2-D inputs behave
+        exactly as before. Kept out of ``state_dict`` (the reference's checkpoint schema has no such entries)."""
+        object.__setattr__(self, "_seq_frontend", frontend)
+
     def forward(self, feats: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
         eng = self._engine
         eng.require_cuda()
         self._sync_dropout()
+        if feats["text_features"].dim() == 3:
+            fe = getattr(self, "_seq_frontend", None)
+            if fe is None:
+                raise RuntimeError("3-D (sequence) features need a SequenceFrontEnd: call attach_sequence_frontend() first")
+            feats = fe.forward_features(feats)
 
         def prep(x: torch.Tensor) -> torch.Tensor:
             if x.requires_grad:
@@ -272,10 +283,10 @@ class _ClassifierFn(torch.autograd.Function):
         check(eng.lib.fnd_classifier_forward(plan.handle, fused_c.data_ptr(), aux_c.data_ptr() if aux_c is not None else None,
                                              aux_c.shape[1] if aux_c is not None else 0, int(training), eng.stream_ptr()),
               "fnd_classifier_forward")
-        plan.forward_id += 1
+        plan.clf_id += 1
         logits = plan.buffer("logits", torch.float32, (B, 2)).clone()
         probs = plan.buffer("probs", torch.float32, (B, 2)).clone()
-        ctx.module, ctx.plan, ctx.fid = module, plan, plan.forward_id
+        ctx.module, ctx.plan, ctx.fid = module, plan, plan.clf_id
         ctx.mark_non_differentiable(probs)
         return logits, probs
 
@@ -283,7 +294,7 @@ class _ClassifierFn(torch.autograd.Function):
     def backward(ctx, dlogits, _dprobs):
         module, plan = ctx.module, ctx.plan
         eng: E.Engine = module._engine
-        if plan.forward_id != ctx.fid:
+        if plan.clf_id != ctx.fid:
             raise RuntimeError("DeepTruthClassifier backward: the activations saved in this batch size's plan were "
                                "overwritten by a later forward; run backward before the next forward of the same batch size")
         dlogits = dlogits.to(torch.float32).contiguous()

@@ -106,6 +106,37 @@ def shard_indices(global_idx: torch.Tensor, rank: int, world: int) -> torch.Tens
     return global_idx[rank::world] if world > 1 else global_idx
 
 
+def gather_ragged(tensors: List[torch.Tensor], count: int, world: int, group=None) -> Tuple[List[torch.Tensor], int]:
+    """All-gather the first ``count`` rows of every tensor from every rank when the counts differ between ranks: the
+    counts are exchanged first, shards are padded to the longest one (the buffers must have at least that many rows)
+    and the padding is cut away again. Returns (rank-major concatenations, total rows); identical on every rank."""
+    dev = tensors[0].device
+    cnt = torch.tensor([count], dtype=torch.int64, device=dev)
+    cnts = [torch.zeros_like(cnt) for _ in range(world)]
+    torch.distributed.all_gather(cnts, cnt, group=group)
+    cnts = [int(c.item()) for c in cnts]
+    m = max(max(cnts), 1)
+    out = []
+    for t in tensors:
+        if t.shape[0] < m:
+            t = torch.cat([t, t.new_zeros((m - t.shape[0],) + tuple(t.shape[1:]))])
+        mine = t[:m].contiguous()
+        parts = [torch.empty_like(mine) for _ in range(world)]
+        torch.distributed.all_gather(parts, mine, group=group)
+        out.append(torch.cat([p[:c] for p, c in zip(parts, cnts)]))
+    return out, sum(cnts)
+
+
+def mean_of_batch_means(loss_rows: torch.Tensor, batch_id: torch.Tensor, nbatches: int) -> float:
+    """np.mean over batches of the per-batch mean loss (forensic_trainer.py:301,316) from per-row losses and the global
+    batch number of every row; differs from the per-row mean whenever the last batch is short."""
+    sums = torch.zeros(nbatches, device=loss_rows.device, dtype=torch.float64).index_add_(0, batch_id, loss_rows.double())
+    cnt = torch.zeros(nbatches, device=loss_rows.device, dtype=torch.float64).index_add_(
+        0, batch_id, torch.ones_like(loss_rows, dtype=torch.float64))
+    seen = cnt > 0
+    return float((sums[seen] / cnt[seen]).mean().cpu())
+
+
 class CachedTensorDataset(torch.utils.data.Dataset):
     """API-compatibility view of one split (forensic_trainer.py:60-83); the fused loops do not use it."""
 
@@ -181,6 +212,7 @@ class ForensicTrainer:
         self._steps: Dict[int, FusedStep] = {}
         self._last_step: Optional[FusedStep] = None
         self._resume_state: Optional[torch.Tensor] = None
+        self._resumed = False
 
         feats = {"text_features": torch.as_tensor(np.asarray(cache["text"])),
                  "audio_features": torch.as_tensor(np.asarray(cache["audio"])),
@@ -237,17 +269,21 @@ class ForensicTrainer:
                 "forensic": fo.get("forensic", {})}
 
     # ------------------------------------------------------------------ fused epoch loop
-    def _step_for(self, batch: int, global_batch: Optional[int] = None) -> FusedStep:
+    def _step_for(self, batch: int, loss_scale: Optional[float] = None) -> FusedStep:
+        """The fused step for a per-rank batch size. ``loss_scale`` = d(mean loss)/d(row loss): 1/len(global batch) under
+        data parallelism (a SUM of the rank gradients is then the single-process gradient), 0 for a padding step (a rank
+        whose shard of a short last batch is empty still takes part in the collective optimizer step, contributing zero)."""
         st = self._steps.get(batch)
         if st is None:
             st = FusedStep(self.fusion, self.clf, batch, precision=self.precision, use_graph=self.use_graph)
             st.attach_cache(self.dcache)
+            st._loss_scale = 1.0 / batch
             self._steps[batch] = st
-        if self.dist and global_batch is not None and getattr(st, "_global_batch", None) != global_batch:
+        if loss_scale is not None and st._loss_scale != loss_scale:
             from ._lib import check
-            check(st.engine.lib.fnd_set_loss_scale(st.plan.handle, 1.0 / global_batch, st.engine.stream_ptr()),
+            check(st.engine.lib.fnd_set_loss_scale(st.plan.handle, float(loss_scale), st.engine.stream_ptr()),
                   "fnd_set_loss_scale")
-            st._global_batch = global_batch
+            st._loss_scale = loss_scale
         if self._last_step is None and self._resume_state is not None:
             # resuming: the saved DevState (optimizer step, bias corrections, dropout salts, hyper-parameters) seeds
             # the first plan that runs
@@ -267,7 +303,16 @@ class ForensicTrainer:
         self._last_step = st
         return st
 
-    def _epoch_loop(self, split: str) -> Tuple[float, Dict[str, float]]:
+    def _epoch_loop(self, loader, split: Optional[str] = None) -> Tuple[float, Dict[str, float]]:
+        """forensic_trainer.py:273-330 with the reference's signature ``_epoch_loop(loader, split)``. The loader argument
+        is accepted for call compatibility; batches are gathered on the device from the resident feature cache in the
+        loader's order for val/test (sequential) and in a seeded per-epoch permutation for train (the reference's
+        ``shuffle=True`` draws from torch's global CPU RNG, which cannot be reproduced bit-for-bit anyway).
+        ``_epoch_loop("train")`` (split only) is accepted too.
+        Returns (mean of the per-batch mean losses — forensic_trainer.py:301,316 —, metrics over the whole split);
+        under data parallelism every rank returns the same global values."""
+        if split is None:
+            split = loader
         is_train = split == "train"
         idx_np = {"train": self.tr_idx, "val": self.va_idx}.get(split, self.te_idx)
         n = len(idx_np)
@@ -279,20 +324,30 @@ class ForensicTrainer:
         order = order.to(self.device)
         bs = self.cfg.batch_size
         # device-side epoch buffers: one D2H copy at the end instead of six per step (forensic_trainer.py:301-313)
-        loss_rows = torch.empty(n, device=self.device)
-        p1 = torch.empty(n, device=self.device)
-        ys = torch.empty(n, dtype=torch.int64, device=self.device)
-        forensic = torch.empty(n, 3, device=self.device)
+        cap = (n + self.world - 1) // self.world + (n + bs - 1) // max(bs, 1) + 1
+        loss_rows = torch.zeros(cap, device=self.device)
+        p1 = torch.zeros(cap, device=self.device)
+        ys = torch.zeros(cap, dtype=torch.int64, device=self.device)
+        bid = torch.zeros(cap, dtype=torch.int64, device=self.device)       # global batch number of every row
+        forensic = torch.zeros(cap, 3, device=self.device)
         done = 0
-        for start in range(0, n, bs):
+        nbatches = 0
+        for bno, start in enumerate(range(0, n, bs)):
             gidx = order[start:start + bs]
+            nbatches += 1
             local = shard_indices(gidx, self.rank, self.world)
-            if local.numel() == 0:
-                if self.dist and is_train:
-                    raise RuntimeError("data-parallel training needs at least one sample per rank in every global batch")
-                continue
-            st = self._step_for(int(local.numel()), int(gidx.numel()))
-            st.static_gather.copy_(local)
+            k = int(local.numel())
+            if k == 0:
+                # short last batch (the reference keeps it: drop_last=False) with fewer samples than ranks: this rank has
+                # nothing to evaluate, but a data-parallel optimizer step is collective, so it runs one padding row with
+                # loss weight 0 (zero gradient contribution) instead of leaving the other ranks waiting
+                if not (self.dist and is_train):
+                    continue
+                st = self._step_for(1, 0.0)
+                st.static_gather.copy_(gidx[:1])
+            else:
+                st = self._step_for(k, 1.0 / int(gidx.numel()) if self.dist else None)
+                st.static_gather.copy_(local)
             if is_train:
                 if self.dp_peer:
                     st.train_step_dp(from_cache=True)
@@ -304,24 +359,24 @@ class ForensicTrainer:
                     st.train_step(from_cache=True)
             else:
                 st.eval_step(from_cache=True)
-            k = int(local.numel())
+            if k == 0:
+                continue
             loss_rows[done:done + k] = st.loss_rows()
             p1[done:done + k] = st.probs()[:, 1]
             ys[done:done + k] = self.dcache.labels[local]
+            bid[done:done + k] = bno
             forensic[done:done + k] = st.plan.buffer("rowstat", torch.float32, (k, 16))[:, :3]
             done += k
         if is_train and self._last_step is not None:
             self._last_step.mark_params_updated()
             self._last_step.plan.check_error()
-        loss_rows, p1, ys, forensic = loss_rows[:done], p1[:done], ys[:done], forensic[:done]
         if self.dist:
-            def gather(t):
-                parts = [torch.empty_like(t) for _ in range(self.world)]
-                torch.distributed.all_gather(parts, t)       # equal shard sizes: global batches are split evenly
-                return torch.cat(parts)
-            if n % self.world == 0 and bs % self.world == 0:
-                loss_rows, p1, ys, forensic = gather(loss_rows), gather(p1), gather(ys), gather(forensic)
-        loss_mean = float(loss_rows.mean().cpu()) if done else 0.0
+            # ALWAYS gather (shard sizes may differ by a few rows), so that every rank computes the same loss / AUC and
+            # takes the same checkpoint and early-stopping decisions
+            (loss_rows, p1, ys, bid, forensic), done = gather_ragged([loss_rows, p1, ys, bid, forensic], done, self.world)
+        else:
+            loss_rows, p1, ys, bid, forensic = loss_rows[:done], p1[:done], ys[:done], bid[:done], forensic[:done]
+        loss_mean = mean_of_batch_means(loss_rows, bid, nbatches) if done else 0.0
         f = forensic.cpu().numpy()
         metrics = aggregate_epoch_metrics(ys.cpu().numpy(), p1.cpu().numpy(),
                                           {"semantic_conflict": f[:, 0], "emotion_intensity": f[:, 1],
@@ -329,28 +384,43 @@ class ForensicTrainer:
         return loss_mean, metrics
 
     def fit(self) -> float:
-        self.no_improve = 0
-        for epoch in range(1, self.cfg.epochs + 1):
+        """forensic_trainer.py:332-369. After ``load_resume`` it continues with the epoch after the saved one (same
+        shuffle seeds, learning-rate schedule and early-stopping counters as an uninterrupted run)."""
+        if not self._resumed:
+            self.no_improve = 0
+        self._resumed = False
+        for epoch in range(self.epoch + 1, self.cfg.epochs + 1):
             self.epoch = epoch
-            tr_loss, tr_m = self._epoch_loop("train")
-            va_loss, va_m = self._epoch_loop("val")
-            if epoch % 3 == 0:                       # StepLR(step_size=3, gamma=0.7), stepped once per epoch
-                self.lr *= 0.7
+            tr_loss, tr_m = self._epoch_loop(self.train_loader, "train")
+            va_loss, va_m = self._epoch_loop(self.val_loader, "val")
+            # StepLR(step_size=3, gamma=0.7), stepped once per epoch (forensic_trainer.py:177,341); closed form so that a
+            # resumed run lands on the same value
+            lr = self.cfg.lr * (0.7 ** (epoch // 3))
+            if lr != self.lr:
+                self.lr = lr
                 self.engine.set_lr(self.lr)
             if self.rank == 0:
                 print(f"[Epoch {epoch:02d}] train_loss={tr_loss:.4f} | ", end=""); pretty_print("train", tr_m)
                 print(f"           val_loss={va_loss:.4f} | ", end=""); pretty_print("val", va_m)
             val_auc = float(va_m.get("auc", 0.5))
+            if self.dist:
+                # identical on every rank by construction (same gathered rows); rank 0's value is authoritative so that a
+                # last-bit difference can never split the ranks between "save" (a collective) and "stop"
+                t = torch.tensor([val_auc], dtype=torch.float64, device=self.device)
+                torch.distributed.broadcast(t, src=0)
+                val_auc = float(t.item())
             if val_auc > self.best_val_auc + 1e-4 and self.cfg.save_best:
                 self.best_val_auc = val_auc
                 self.no_improve = 0
                 if self.dp_peer:
                     self.engine.gather_master()      # fp32 master weights are sharded between optimizer steps
                 if self.rank == 0:
+                    tmp = self.ckpt_path + ".tmp"
                     torch.save({"fusion": {k: v.detach().cpu() for k, v in self.fusion.state_dict().items()},
                                 "clf": {k: v.detach().cpu() for k, v in self.clf.state_dict().items()},
                                 "gnn": self.gnn.state_dict() if (self.cfg.use_gnn and self.gnn is not None) else None,
-                                "cfg": dict(self.cfg.__dict__)}, self.ckpt_path)
+                                "cfg": dict(self.cfg.__dict__)}, tmp)
+                    os.replace(tmp, self.ckpt_path)  # readers never see a partial file
                     print(f"  ↳ saved best checkpoint to {self.ckpt_path} (val_auc={self.best_val_auc:.3f})")
             else:
                 self.no_improve += 1
@@ -398,10 +468,13 @@ class ForensicTrainer:
         self.lr = float(ck["lr"]); eng.set_lr(self.lr)
         self.epoch = int(ck["epoch"]); self.best_val_auc = float(ck["best_val_auc"]); self.no_improve = int(ck["no_improve"])
         self._resume_state = ck["dev_state"]
+        self._resumed = True
         self._steps.clear()
         self._last_step = None
 
     def test(self) -> Dict[str, float]:
+        if self.dist:
+            torch.distributed.barrier()          # rank 0's best.pt (written + renamed in fit) is complete before anyone reads
         if os.path.exists(self.ckpt_path):
             ck = torch.load(self.ckpt_path, map_location="cpu")
             self.fusion.load_state_dict(ck["fusion"])
@@ -409,7 +482,7 @@ class ForensicTrainer:
             if self.cfg.use_gnn and ck.get("gnn") is not None and self.gnn is not None:
                 self.gnn.load_state_dict(ck["gnn"])
             self.engine.refresh_shadows(self.engine.param_version())
-        ts_loss, m = self._epoch_loop("test")
+        ts_loss, m = self._epoch_loop(self.test_loader, "test")
         if self.rank == 0:
             print(f"[Test] loss={ts_loss:.4f} | ", end=""); pretty_print("test", m)
         return {"test_loss": ts_loss, "test_acc": m.get("accuracy", 0.0), "test_auc": m.get("auc", 0.5),
