@@ -180,7 +180,8 @@ class ForensicTrainer:
             raw = FakeSVRawDataset(cfg.data_root)
             cache = build_gnn_cache_from_raw_dataset(raw, ocr_phrase_pkl=cfg.ocr_phrase_pkl, text_dim=768, audio_dim=128,
                                                      visual_dim=512, temporal_dim=256, seed=cfg.seed)
-        self.cache = cache
+        self.cache = dict(cache)         # shallow copy: _build_gnn adds "gnn_Z" without mutating the caller's dict
+        cache = self.cache
         self.tr_idx, self.va_idx, self.te_idx = (np.asarray(x) for x in cache["split"])
         if "gnn_Z" not in cache or cache["gnn_Z"] is None:
             self._build_gnn()
