@@ -58,6 +58,13 @@ int fnd_seq_coattn_forward(const void* q_bf16, int q_pitch, int q_col0, const vo
 int fnd_seq_masked_mean_pool(const void* x_bf16, int x_pitch, const unsigned char* mask, const int* len, int B, int L,
                              int d, float* out_f32, int f32_pitch, void* out_bf16, int bf_pitch, void* stream);
 
+/* Probe aid (tools/seq_probe.py): while `stamps` is non-NULL, fnd_seq_coattn_forward launches an instrumented build in
+ * which one softmax thread per CTA accumulates clock64() cycles per phase of its key-block loop into
+ * stamps[cta * 8 + phase] (0 wait for S, 1 TMEM load, 2 mask + row max, 3 exp2 + pack, 4 P store + fence, 5 previous
+ * P V product, 6 rescale, 7 loop / item epilogue). `stamps` must hold 8 * 2 * (number of SMs) entries. NULL restores the
+ * production kernel. Not for use around graph capture. */
+int fnd_seq_debug_attn_stamps(long long* stamps);
+
 #ifdef __cplusplus
 }
 #endif

@@ -330,6 +330,33 @@ def train_step(fus: Params, clf: Params, batch: Dict[str, Tensor], opt: AdamWSta
     return out
 
 
+class TorchStep:
+    """The reference's OWN step machinery around the restated forward — leaf parameters, ``F.cross_entropy``,
+    ``loss.backward()``, ``nn.utils.clip_grad_norm_(params, 5.0)`` and ``torch.optim.AdamW(lr=2e-4, weight_decay=1e-4)``
+    exactly as src/training/forensic_trainer.py:173-177,286-298 drives them — on any device. Used as the timed CPU
+    baseline of bench.py (no per-step parameter clones, torch's own multi-tensor optimizer: what the reference runs)
+    and, on ``cuda``, as the same-box "stock PyTorch eager" bar. ``AdamWState`` above stays the
+    spelled-out arithmetic that the golden trajectories pin; tests/test_oracle_golden.py checks the two agree."""
+
+    def __init__(self, fus: Params, clf: Params, device: str = "cpu", lr: float = 2e-4, weight_decay: float = 1e-4,
+                 grad_clip: float = 5.0):
+        fk, ck = trainable_keys()
+        self.fus = {k: v.detach().to(device).clone().requires_grad_(k in fk) for k, v in fus.items()}
+        self.clf = {k: v.detach().to(device).clone().requires_grad_(k in ck) for k, v in clf.items()}
+        self.params = [self.fus[k] for k in fk] + [self.clf[k] for k in ck]
+        self.opt = torch.optim.AdamW(self.params, lr=lr, weight_decay=weight_decay)
+        self.clip = grad_clip
+
+    def step(self, batch: Dict[str, Tensor], dropout: float = 0.1, masks: Optional[Dict[str, Tensor]] = None) -> Dict[str, Tensor]:
+        out = model_forward(self.fus, self.clf, batch, dropout, masks)
+        self.opt.zero_grad(set_to_none=True)
+        out["loss"].backward()
+        if self.clip and self.clip > 0:
+            out["grad_norm"] = torch.nn.utils.clip_grad_norm_(self.params, max_norm=self.clip)
+        self.opt.step()
+        return out
+
+
 def rel_err(a: Tensor, b: Tensor) -> float:
     """Norm-wise relative error ||a-b|| / ||b|| used by every parity test."""
     a, b = a.double().flatten(), b.double().flatten()

@@ -11,7 +11,7 @@ import torch
 from ultrafnd_git_b200 import seq_ops as S
 
 
-def timeit(fn, reps=20, warm=3):
+def timeit(fn, reps=int(os.environ.get('SEQ_PROBE_REPS', '20')), warm=int(os.environ.get('SEQ_PROBE_WARM', '3'))):
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
@@ -59,6 +59,21 @@ def main():
     ms = timeit(lambda: S.masked_mean_pool(at, B, Lt)); rec("pool text", ms, 0.0, 2.0 * B * Lt * d)
     xin = torch.randn(B * Lt, 768, device=dev, generator=g)
     ms = timeit(lambda: S.cast_bf16(xin)); rec("cast text fp32->bf16", ms, 0.0, 6.0 * B * Lt * 768)
+    if os.environ.get("SEQ_PROBE_STAMPS"):
+        from ultrafnd_git_b200 import _lib
+        lib = _lib.load()
+        st = torch.zeros(2 * 148 * 8 + 64, dtype=torch.int64, device=dev)
+        lib.fnd_seq_debug_attn_stamps(st.data_ptr())
+        S.coattn_forward(qkv_t, qkv_f, qkv_f, B, H, Lt, Lf, 0, d, 2 * d, out=at, err=err)
+        torch.cuda.synchronize()
+        lib.fnd_seq_debug_attn_stamps(None)
+        v = st[:2 * 148 * 8].view(-1, 8).double().cpu()
+        nb = B * H * ((Lt + 127) // 128) * ((Lf + 63) // 64) / (2 * 148)
+        names = ["wait S", "tmem ld S", "mask+max+xchg", "exp2+pack", "P store+fence", "prev PV add", "rescale", "loop/epilogue"]
+        print(f"attention phase cycles per key block (softmax warp 2 lane 0, mean over {v.shape[0]} CTAs, {nb:.1f} blocks/CTA):")
+        for i, n in enumerate(names):
+            print(f"   {n:16s} {float(v[:, i].mean()) / nb:8.1f}")
+        print(f"   {'total':16s} {float(v.sum(1).mean()) / nb:8.1f}")
     torch.cuda.synchronize()
     print(f"seq_probe B={B} Lt={Lt} Lf={Lf} d={d} heads={H}  err={int(err.item())}")
     for name, ms, tf, gbs in rows:

@@ -149,6 +149,7 @@ def _signatures() -> Dict[str, tuple]:
         "fnd_check_error": (_c_int, [_c_void_p, _c_void_p]),
         # ---- sequence front-end (include/fnd_seq_b200.h)
         "fnd_seq_init": (_c_int, []),
+        "fnd_seq_debug_attn_stamps": (_c_int, [_c_void_p]),
         "fnd_seq_cast_bf16": (_c_int, [_c_void_p, _c_void_p, ll, _c_void_p]),
         "fnd_seq_linear": (_c_int, [_c_void_p, _c_int, _c_void_p, _c_int, _c_void_p, _c_void_p, _c_int, _c_int, _c_void_p, _c_int,
                                     _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_void_p, _c_void_p]),

@@ -134,6 +134,24 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const void* tmap, ui
       : "memory");
 }
 
+// TMA store: shared memory (in the tensor map's box / swizzle layout) -> global, clipped at the tensor bounds. Bulk-group
+// completion: commit after issuing, wait_read<N> until at most N groups still READ shared memory, wait<N> until at most
+// N groups are incomplete (writes visible).
+__device__ __forceinline__ void tma_store_2d(const void* tmap, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void tma_store_wait() {
+  asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+
 // ------------------------------------------------------------------------------------------
 // tcgen05: TMEM allocation, MMA, commit, TMEM load
 // ------------------------------------------------------------------------------------------
@@ -203,6 +221,49 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t saddr, uint32_
   d |= 2ull << 61;
   return d;
 }
+// The same descriptor split into its two 32-bit words. The MMA-issuing thread runs scalar, dependent code: building the
+// 64-bit descriptor from scratch for every instruction (shifts / masks in 64-bit arithmetic) cost ~40 instructions per
+// tcgen05.mma and made the issue loop, not the tensor pipe, the bottleneck (ncu: softmax warps waiting on the S tile).
+// The high word is constant per operand layout; the low word is (address >> 4) | (lbo >> 4) << 16, so advancing the
+// operand by `bytes` is a 32-bit add of (bytes >> 4).
+__device__ __forceinline__ uint32_t smem_desc_hi_sw128(uint32_t sbo_bytes) {
+  return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);
+}
+__device__ __forceinline__ uint32_t smem_desc_lo(uint32_t saddr, uint32_t lbo_bytes) {
+  return ((saddr & 0x3FFFFu) >> 4) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+}
+__device__ __forceinline__ uint64_t desc64(uint32_t lo, uint32_t hi) {
+  uint64_t d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
+  return d;
+}
+// Single-probe wait helpers for the hot issue loops: spin on try_wait (the instruction itself blocks for a hardware
+// time slice), fall back to the bounded wait only after many failed probes.
+__device__ __forceinline__ bool mbar_wait_fast(uint64_t* bar, uint32_t parity, int* err, int code) {
+#pragma unroll 1
+  for (int i = 0; i < 4096; ++i)
+    if (mbar_try_wait(bar, parity)) return true;
+  return mbar_wait(bar, parity, err, code);
+}
+// explicit shared-state-space accesses by 32-bit shared address (generic LD/ST on shared pointers cost an extra
+// address-space resolve on the LSU path)
+__device__ __forceinline__ void sts_v4(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint4 lds_v4(uint32_t saddr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_f32(uint32_t saddr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(saddr), "f"(v) : "memory");
+}
+__device__ __forceinline__ float lds_f32(uint32_t saddr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr) : "memory");
+  return v;
+}
+
 // Instruction descriptor for kind::f16 with bf16 A/B and fp32 D.
 //   [4,6) D fmt (1 = f32)  [7,10) A fmt (1 = bf16)  [10,13) B fmt  [15] A major (1 = MN)  [16] B major
 //   [17,23) N >> 3   [24,29) M >> 4

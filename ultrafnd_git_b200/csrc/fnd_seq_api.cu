@@ -27,14 +27,21 @@ static int seq_num_sms() {
   return n;
 }
 
+static long long* g_attn_stamps = nullptr;      // probe aid (fnd_seq_debug_attn_stamps)
+
 extern "C" {
+
+int fnd_seq_debug_attn_stamps(long long* stamps) {
+  g_attn_stamps = stamps;
+  return 0;
+}
 
 int fnd_seq_init(void) {
   static bool done = false;
   if (done) return 0;
-  SEQ_CUDA_OK(cudaFuncSetAttribute(seq_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   kSeqGemmRingBudget + kSeqGemmHeader + 1024));
-  SEQ_CUDA_OK(cudaFuncSetAttribute(seq_attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBytes));
+  SEQ_CUDA_OK(cudaFuncSetAttribute(seq_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSeqGemmSmemMax));
+  SEQ_CUDA_OK(cudaFuncSetAttribute(seq_attn_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBytes));
+  SEQ_CUDA_OK(cudaFuncSetAttribute(seq_attn_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBytes));
   done = true;
   return 0;
 }
@@ -72,7 +79,8 @@ int fnd_seq_linear(const void* a_bf16, int a_pitch, const void* w_bf16, int w_pi
   P.tiles_n = cdiv(N, bn);
   P.kblocks = cdiv(K, kSeqGemmBK);
   P.stage_bytes = kSeqGemmBM * kSeqGemmBK * 2 + bn * kSeqGemmBK * 2;
-  P.nstages = kSeqGemmRingBudget / P.stage_bytes;
+  const int rbuf_bytes = (resid_bf16 && out_bf16) ? 2 * kSeqGemmStageOutBytes : 0;      // residual slabs, prefetched two ahead
+  P.nstages = (kSeqGemmRingBudget - rbuf_bytes) / P.stage_bytes;
   if (P.nstages > kSeqGemmMaxStages) P.nstages = kSeqGemmMaxStages;
   P.bias = bias;
   P.resid = static_cast<const __nv_bfloat16*>(resid_bf16); P.resid_pitch = resid_pitch;
@@ -84,9 +92,17 @@ int fnd_seq_linear(const void* a_bf16, int a_pitch, const void* w_bf16, int w_pi
   if (r) return r;
   r = encode_bf16_2d(&P.tmB, w_bf16, K, N, w_pitch, 64, bn);
   if (r) return r;
+  if (out_bf16) {
+    r = encode_bf16_2d(&P.tmC, out_bf16, N, M, out_pitch, 64, kSeqGemmBM);
+    if (r) return r;
+  }
+  if (resid_bf16) {
+    r = encode_bf16_2d(&P.tmR, resid_bf16, N, M, resid_pitch, 64, kSeqGemmBM);
+    if (r) return r;
+  }
   const int ntiles = P.tiles_m * P.tiles_n;
   const int grid = ntiles < sms ? ntiles : sms;
-  const size_t smem = static_cast<size_t>(P.nstages) * P.stage_bytes + kSeqGemmHeader + 1024;
+  const size_t smem = static_cast<size_t>(P.nstages) * P.stage_bytes + 2 * kSeqGemmStageOutBytes + rbuf_bytes + kSeqGemmHeader + 1024;
   seq_gemm_kernel<<<grid, kSeqGemmThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(P);
   SEQ_CUDA_OK(cudaGetLastError());
   return 0;
@@ -98,7 +114,11 @@ int fnd_seq_layernorm(const void* x_bf16, int x_pitch, const float* gamma, const
   if ((d & 7) || d > kLnMaxChunks * 256 || (x_pitch & 7) || (y_pitch & 7) || x_pitch < d || y_pitch < d) return -2;
   if (!aligned16(x_bf16) || !aligned16(y_bf16) || !aligned16(gamma) || !aligned16(beta)) return -3;
   LnParams P{static_cast<const __nv_bfloat16*>(x_bf16), x_pitch, gamma, beta, eps, static_cast<__nv_bfloat16*>(y_bf16), y_pitch, M, d};
-  seq_layernorm_kernel<<<cdiv(M, 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(P);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (d <= 256) seq_layernorm_kernel<1><<<cdiv(M, 8), 256, 0, st>>>(P);
+  else if (d <= 512) seq_layernorm_kernel<2><<<cdiv(M, 8), 256, 0, st>>>(P);
+  else if (d <= 1024) seq_layernorm_kernel<4><<<cdiv(M, 8), 256, 0, st>>>(P);
+  else seq_layernorm_kernel<8><<<cdiv(M, 8), 256, 0, st>>>(P);
   SEQ_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -128,8 +148,13 @@ int fnd_seq_coattn_forward(const void* q_bf16, int q_pitch, int q_col0, const vo
   P.out = static_cast<__nv_bfloat16*>(out_bf16); P.out_pitch = out_pitch;
   P.lse = lse;
   P.err = err_flag;
-  dim3 grid(static_cast<unsigned>(cdiv(Lq, kAttnBQ)), static_cast<unsigned>(H), static_cast<unsigned>(B));
-  seq_attn_fwd_kernel<<<grid, kAttnThreads, kAttnSmemBytes, reinterpret_cast<cudaStream_t>(stream)>>>(P);
+  // persistent: two resident CTAs per SM walk the (sample, head, query-tile) work list
+  const long long nwork = static_cast<long long>(cdiv(Lq, kAttnBQ)) * H * B;
+  if (nwork > 0x7fffffffLL) return -3;
+  const int grid = nwork < 2LL * seq_num_sms() ? static_cast<int>(nwork) : 2 * seq_num_sms();
+  P.dbg = g_attn_stamps;
+  if (g_attn_stamps) seq_attn_fwd_kernel<true><<<grid, kAttnThreads, kAttnSmemBytes, reinterpret_cast<cudaStream_t>(stream)>>>(P);
+  else seq_attn_fwd_kernel<false><<<grid, kAttnThreads, kAttnSmemBytes, reinterpret_cast<cudaStream_t>(stream)>>>(P);
   SEQ_CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -8,7 +8,8 @@
 //   * tiles are 128 x BN with BN up to 256 (UMMA 128 x 256 x 16: one instruction keeps the tensor pipe busy for 128
 //     cycles while reading 12 KB of shared memory — within the 128 B/clk shared-memory port),
 //   * TWO accumulators live in TMEM (2 x BN columns, up to all 512), so the MMA warp starts tile i+1 while the four
-//     epilogue warps drain tile i (tcgen05.ld -> bias / residual / activation -> packed bf16 256-bit stores),
+//     epilogue warps drain tile i (tcgen05.ld -> bias / residual / activation -> bf16 into a swizzled staging buffer ->
+//     TMA store; the residual slab is TMA-loaded into the same buffer),
 //   * operands arrive by TMA (SWIZZLE_128B) through a 4..8-stage ring that runs ahead across tile boundaries,
 //   * consecutive tile ids share the A panel (m-major order), so the co-resident CTAs re-read A from L2, not HBM.
 // TMA zero-fills out-of-bounds rows, stores are row-masked: any M, any K that is a multiple of 8, N a multiple of 8.
@@ -25,10 +26,15 @@ constexpr int kSeqGemmBK = 64;
 constexpr int kSeqGemmMaxStages = 8;
 constexpr int kSeqGemmThreads = 192;             // warp0 TMA, warp1 MMA + TMEM owner, warps 2..5 epilogue
 constexpr int kSeqGemmHeader = 1024;
-constexpr int kSeqGemmRingBudget = 200 * 1024;
+constexpr int kSeqGemmRingBudget = 192 * 1024;
+constexpr int kSeqGemmStageOutBytes = kSeqGemmBM * 64 * 2;    // one 128 x 64 bf16 output slab
+constexpr int kSeqGemmSmemMax = kSeqGemmRingBudget + 2 * kSeqGemmStageOutBytes + kSeqGemmHeader + 1024;   // residual buffers come out of the ring budget
+
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
 struct alignas(64) SeqGemmParams {
   CUtensorMap tmA, tmB;
+  CUtensorMap tmC, tmR;                          // bf16 output / residual, box 64 x 128 (valid when out_bf / resid are set)
   int M, N, K;
   int bn;                                        // 64 / 128 / 256
   int tiles_m, tiles_n, kblocks, nstages, stage_bytes;
@@ -50,8 +56,11 @@ __global__ void __launch_bounds__(kSeqGemmThreads, 1) seq_gemm_kernel(const __gr
   uint64_t* empty_bar = full_bar + kSeqGemmMaxStages;
   uint64_t* tfull_bar = empty_bar + kSeqGemmMaxStages;     // [2] accumulator complete
   uint64_t* tempty_bar = tfull_bar + 2;                    // [2] accumulator drained
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* rfull_bar = tempty_bar + 2;                    // [2] residual slab landed in the staging buffer
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rfull_bar + 2);
   uint8_t* ring = smem + kSeqGemmHeader;
+  uint8_t* stage = ring + P.nstages * P.stage_bytes;       // 2 x 16 KB output staging (128 rows x 64 bf16, SWIZZLE_128B)
+  uint8_t* rbuf = stage + 2 * kSeqGemmStageOutBytes;       // 2 x 16 KB residual slabs (only when P.resid; host sizes the ring)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int bn = P.bn, nstages = P.nstages, stage_bytes = P.stage_bytes, kblocks = P.kblocks;
@@ -61,11 +70,13 @@ __global__ void __launch_bounds__(kSeqGemmThreads, 1) seq_gemm_kernel(const __gr
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&P.tmA);
     tma_prefetch_desc(&P.tmB);
+    if (P.out_bf) tma_prefetch_desc(&P.tmC);
+    if (P.resid) tma_prefetch_desc(&P.tmR);
   }
   if (warp == 1) {
     if (lane == 0) {
       for (int s = 0; s < nstages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-      for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 128); }
+      for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 128); mbar_init(&rfull_bar[a], 1); }
       fence_mbar_init();
     }
     __syncwarp();
@@ -81,120 +92,204 @@ __global__ void __launch_bounds__(kSeqGemmThreads, 1) seq_gemm_kernel(const __gr
     // ================= TMA producer: runs ahead across tile boundaries =================
     if (lane == 0) {
       const uint32_t tx = static_cast<uint32_t>(stage_bytes);
-      int it = 0;
+      int s = 0;
+      uint32_t ph = 1u;                          // parity to wait for on empty_bar (fresh barrier: passes)
       bool ok = true;
+#pragma unroll 1
       for (int tile = blockIdx.x; tile < ntiles && ok; tile += gridDim.x) {
         const int tm = tile / P.tiles_n, tn = tile - tm * P.tiles_n;
-        for (int kb = 0; kb < kblocks; ++kb, ++it) {
-          const int s = it % nstages;
-          const uint32_t ph = static_cast<uint32_t>(it / nstages) & 1u;
-          ok = mbar_wait(&empty_bar[s], ph ^ 1u, P.err, FND_DEV_TIMEOUT_PRODUCER);
+        const int am = tm * kSeqGemmBM, bnr = tn * bn;
+#pragma unroll 1
+        for (int kb = 0; kb < kblocks; ++kb) {
+          ok = mbar_wait_fast(&empty_bar[s], ph, P.err, FND_DEV_TIMEOUT_PRODUCER);
           if (!ok) break;
           mbar_arrive_expect_tx(&full_bar[s], tx);
           uint8_t* sA = ring + s * stage_bytes;
-          tma_load_2d(sA, &P.tmA, &full_bar[s], kb * kSeqGemmBK, tm * kSeqGemmBM, kEvictNormal);
-          tma_load_2d(sA + kSeqGemmBM * kSeqGemmBK * 2, &P.tmB, &full_bar[s], kb * kSeqGemmBK, tn * bn, kEvictLast);
+          tma_load_2d(sA, &P.tmA, &full_bar[s], kb * kSeqGemmBK, am, kEvictNormal);
+          tma_load_2d(sA + kSeqGemmBM * kSeqGemmBK * 2, &P.tmB, &full_bar[s], kb * kSeqGemmBK, bnr, kEvictLast);
+          if (++s == nstages) { s = 0; ph ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
-    // ================= MMA issuer =================
-    if (lane == 0) {
+    // ================= MMA issuer (lean loop: incremental stage / parity, 32-bit descriptor arithmetic; warp-uniform
+    // control flow with ONE elected lane around the issue, so operands reach the uniform datapath without
+    // divergence-safe conversion loops) =================
+    {
       const uint32_t idesc = make_idesc_bf16(kSeqGemmBM, bn, 0, 0);
-      int it = 0, lt = 0;
+      const uint32_t dhi = smem_desc_hi_sw128(1024);
+      const uint32_t a_lo0 = smem_desc_lo(smem_u32(ring), 16);
+      const uint32_t b_off = (kSeqGemmBM * kSeqGemmBK * 2) >> 4;
+      const uint32_t stage_step = static_cast<uint32_t>(stage_bytes) >> 4;
+      int s = 0, lt = 0;
+      uint32_t ph = 0u;
       bool ok = true;
+#pragma unroll 1
       for (int tile = blockIdx.x; tile < ntiles && ok; tile += gridDim.x, ++lt) {
         const int ab = lt & 1;
         const uint32_t aph = static_cast<uint32_t>(lt >> 1) & 1u;
-        ok = mbar_wait(&tempty_bar[ab], aph ^ 1u, P.err, FND_DEV_TIMEOUT_MMA);
+        ok = mbar_wait_fast(&tempty_bar[ab], aph ^ 1u, P.err, FND_DEV_TIMEOUT_MMA);
         if (!ok) break;
         tc_fence_after_sync();
         const uint32_t tacc = tmem_base + static_cast<uint32_t>(ab * bn);
-        for (int kb = 0; kb < kblocks; ++kb, ++it) {
-          const int s = it % nstages;
-          const uint32_t ph = static_cast<uint32_t>(it / nstages) & 1u;
-          ok = mbar_wait(&full_bar[s], ph, P.err, FND_DEV_TIMEOUT_MMA);
+#pragma unroll 1
+        for (int kb = 0; kb < kblocks; ++kb) {
+          ok = mbar_wait_fast(&full_bar[s], ph, P.err, FND_DEV_TIMEOUT_MMA);
           if (!ok) break;
           tc_fence_after_sync();
-          const uint32_t aBase = smem_u32(ring + s * stage_bytes);
-          const uint32_t bBase = aBase + kSeqGemmBM * kSeqGemmBK * 2;
-#pragma unroll
-          for (int k = 0; k < kSeqGemmBK / 16; ++k) {
-            const uint64_t ad = make_smem_desc_sw128(aBase + k * 32, 16, 1024);
-            const uint64_t bd = make_smem_desc_sw128(bBase + k * 32, 16, 1024);
-            umma_f16(tacc, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+          const uint32_t al = a_lo0 + static_cast<uint32_t>(s) * stage_step;
+          const uint32_t bl = al + b_off;
+          if (elect_one()) {
+            umma_f16(tacc, desc64(al, dhi), desc64(bl, dhi), idesc, kb != 0 ? 1u : 0u);
+            umma_f16(tacc, desc64(al + 2, dhi), desc64(bl + 2, dhi), idesc, 1u);
+            umma_f16(tacc, desc64(al + 4, dhi), desc64(bl + 4, dhi), idesc, 1u);
+            umma_f16(tacc, desc64(al + 6, dhi), desc64(bl + 6, dhi), idesc, 1u);
+            umma_commit(&empty_bar[s]);
+            if (kb == kblocks - 1) umma_commit(&tfull_bar[ab]);
           }
-          umma_commit(&empty_bar[s]);
+          __syncwarp();
+          if (++s == nstages) { s = 0; ph ^= 1u; }
         }
-        umma_commit(&tfull_bar[ab]);
       }
     }
   } else {
     // ================= epilogue: warps 2..5, TMEM lane quarter = warp % 4 =================
     const int q = warp & 3;
     const int row = q * 32 + lane;
+    const int epi_tid = threadIdx.x - 64;
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
     int lt = 0;
+    uint32_t slab_ctr = 0;                                   // 64-column slabs staged so far (selects the staging buffer)
+    // Residual slabs are prefetched TWO slabs ahead into their own buffers (they do not depend on the accumulator, so
+    // the first two are requested before the first tile's MMAs have even finished): a load issued on demand cost a full
+    // L2/HBM round trip per slab and made the epilogue, not the MMA, the pace of the residual GEMMs.
+    int pf_tile = blockIdx.x, pf_c = 0;
+    uint32_t pf_n = 0;
+    auto pf_issue = [&]() {
+      if (pf_tile >= ntiles) return;
+      const int ptm = pf_tile / P.tiles_n, ptn = pf_tile - ptm * P.tiles_n;
+      const uint32_t b = pf_n & 1u;
+      mbar_arrive_expect_tx(&rfull_bar[b], kSeqGemmStageOutBytes);
+      tma_load_2d(rbuf + b * kSeqGemmStageOutBytes, &P.tmR, &rfull_bar[b], ptn * bn + pf_c, ptm * kSeqGemmBM, kEvictFirst);
+      ++pf_n;
+      pf_c += 64;
+      if (pf_c >= bn || ptn * bn + pf_c >= P.N) { pf_c = 0; pf_tile += gridDim.x; }
+    };
+    if (P.resid && P.out_bf && epi_tid == 0) { pf_issue(); pf_issue(); }
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++lt) {
       const int tm = tile / P.tiles_n, tn = tile - tm * P.tiles_n;
       const int ab = lt & 1;
       const uint32_t aph = static_cast<uint32_t>(lt >> 1) & 1u;
       const bool ok = mbar_wait(&tfull_bar[ab], aph, P.err, FND_DEV_TIMEOUT_EPILOGUE);
       tc_fence_after_sync();
-      const int m = tm * kSeqGemmBM + row;
-      const bool row_ok = ok && m < P.M;
+      const int m0 = tm * kSeqGemmBM;
+      const int m = m0 + row;
       const uint32_t taddr = tmem_base + lane_addr + static_cast<uint32_t>(ab * bn);
       const int nb = tn * bn;
+      if (P.out_bf) {
+        // ---- bf16 output: 64-column slabs go through a swizzled shared-memory staging buffer and leave by TMA store.
+        // A thread owns an accumulator ROW; storing rows straight from registers would make every warp-level store touch
+        // 32 different 128-byte lines (LSU-bound: measured 20 K cycles per 128x256 tile against 8 K cycles of MMA). The
+        // residual slab arrives the same way (TMA load into the staging buffer, read back by the owning thread). ----
 #pragma unroll 1
-      for (int c = 0; c < bn; c += 32) {
-        uint32_t r[32];
-        tmem_ld_32x32(taddr + c, r);
-        tmem_ld_wait();
-        const int n0 = nb + c;
-        if (!row_ok || n0 >= P.N) continue;
-        float v[32];
+        for (int c = 0; c < bn; c += 64) {
+          const int n0 = nb + c;
+          if (n0 >= P.N) break;                              // tile-uniform
+          const uint32_t sb = slab_ctr & 1u;
+          uint8_t* stg = stage + sb * kSeqGemmStageOutBytes;
+          if (epi_tid == 0) tma_store_wait_read<1>();        // the store issued two slabs ago has drained this buffer
+          epi_bar_sync();
+          if (P.resid) mbar_wait(&rfull_bar[sb], (slab_ctr >> 1) & 1u, P.err, FND_DEV_TIMEOUT_EPILOGUE);
+          const uint8_t* rrow = rbuf + sb * kSeqGemmStageOutBytes + row * 128;
+          uint32_t r0[32], r1[32];
+          tmem_ld_32x32(taddr + c, r0);
+          tmem_ld_32x32(taddr + c + 32, r1);
+          tmem_ld_wait();
+          uint8_t* prow = stg + row * 128;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        const int ncols = min(32, P.N - n0);              // multiple of 8
-        if (P.bias) {
+          for (int ch = 0; ch < 8; ++ch) {                   // 8 chunks of 8 columns
+            float v[8];
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            if (j < ncols) {
-              const float4 b4 = __ldg(reinterpret_cast<const float4*>(P.bias + n0 + j));
-              v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+            for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(ch < 4 ? r0[ch * 8 + j] : r1[(ch - 4) * 8 + j]);
+            const int n = n0 + ch * 8;
+            if (P.bias && n < P.N) {
+              const float4 b0 = __ldg(reinterpret_cast<const float4*>(P.bias + n));
+              const float4 b1 = __ldg(reinterpret_cast<const float4*>(P.bias + n + 4));
+              v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+              v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
             }
-          }
-        }
-        if (P.resid) {
-          const __nv_bfloat16* rp = P.resid + static_cast<size_t>(m) * P.resid_pitch + n0;
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            if (j < ncols) {
-              const uint4 u = __ldg(reinterpret_cast<const uint4*>(rp + j));
+            uint4* slot = reinterpret_cast<uint4*>(prow + ((ch ^ (row & 7)) << 4));
+            if (P.resid) {
+              const uint4 u = *reinterpret_cast<const uint4*>(rrow + ((ch ^ (row & 7)) << 4));
               const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
               for (int t = 0; t < 4; ++t) {
                 const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&w[t]);
-                v[j + 2 * t] += __low2float(h2);
-                v[j + 2 * t + 1] += __high2float(h2);
+                v[2 * t] += __low2float(h2);
+                v[2 * t + 1] += __high2float(h2);
+              }
+            }
+            if (P.act == 1) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] = gelu_erf(v[j]);
+            }
+            *slot = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+          }
+          fence_proxy_async_smem();
+          epi_bar_sync();
+          if (epi_tid == 0) {
+            if (ok) {
+              tma_store_2d(&P.tmC, stg, n0, m0);             // rows >= M and columns >= N are clipped by the tensor map
+              tma_store_commit();
+            }
+            if (P.resid) pf_issue();                         // every thread has read this residual buffer: refill it
+          }
+          ++slab_ctr;
+        }
+      }
+      if (P.out_f32) {
+        // ---- fp32 output (the small pooled-head GEMMs): direct row stores ----
+        const bool row_ok = ok && m < P.M;
+#pragma unroll 1
+        for (int c = 0; c < bn; c += 32) {
+          uint32_t r[32];
+          tmem_ld_32x32(taddr + c, r);
+          tmem_ld_wait();
+          const int n0 = nb + c;
+          if (!row_ok || n0 >= P.N) continue;
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          const int ncols = min(32, P.N - n0);              // multiple of 8
+          if (P.bias) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              if (j < ncols) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(P.bias + n0 + j));
+                v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
               }
             }
           }
-        }
-        if (P.act == 1) {
+          if (P.resid) {
+            const __nv_bfloat16* rp = P.resid + static_cast<size_t>(m) * P.resid_pitch + n0;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
-        }
-        if (P.out_bf) {
-          __nv_bfloat16* op = P.out_bf + static_cast<size_t>(m) * P.out_pitch + n0;
+            for (int j = 0; j < 32; j += 8) {
+              if (j < ncols) {
+                const uint4 u = __ldg(reinterpret_cast<const uint4*>(rp + j));
+                const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            if (j < ncols)
-              *reinterpret_cast<uint4*>(op + j) = make_uint4(pack_bf16x2(v[j], v[j + 1]), pack_bf16x2(v[j + 2], v[j + 3]),
-                                                             pack_bf16x2(v[j + 4], v[j + 5]), pack_bf16x2(v[j + 6], v[j + 7]));
+                for (int t = 0; t < 4; ++t) {
+                  const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&w[t]);
+                  v[j + 2 * t] += __low2float(h2);
+                  v[j + 2 * t + 1] += __high2float(h2);
+                }
+              }
+            }
           }
-        }
-        if (P.out_f32) {
+          if (P.act == 1) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+          }
           float* op = P.out_f32 + static_cast<size_t>(m) * P.f32_pitch + n0;
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
@@ -202,10 +297,11 @@ __global__ void __launch_bounds__(kSeqGemmThreads, 1) seq_gemm_kernel(const __gr
           }
         }
       }
-      // every column of this accumulator is in registers / stored: hand it back to the MMA warp
+      // every column of this accumulator is in registers / staged: hand it back to the MMA warp
       tc_fence_before_sync();
       mbar_arrive(&tempty_bar[ab]);
     }
+    if (epi_tid == 0) tma_store_wait<0>();                   // all output tiles written before the CTA retires
   }
 
   tc_fence_before_sync();

@@ -37,16 +37,17 @@ struct LnParams {
   __nv_bfloat16* y; int y_pitch;
   int M, d;
 };
+template <int kChunks>                           // 8-element chunks per lane: d <= kChunks * 256
 __global__ void __launch_bounds__(256) seq_layernorm_kernel(const LnParams P) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * 8 + warp;
   if (row >= P.M) return;
   const __nv_bfloat16* xr = P.x + static_cast<size_t>(row) * P.x_pitch;
   const int nchunk = P.d >> 3;                   // 8-element chunks in the row
-  float v[kLnMaxChunks][8];
+  float v[kChunks][8];
   float sum = 0.f;
 #pragma unroll
-  for (int c = 0; c < kLnMaxChunks; ++c) {
+  for (int c = 0; c < kChunks; ++c) {
     const int ch = c * 32 + lane;
     if (ch < nchunk) {
       unpack_bf16x8(__ldcg(reinterpret_cast<const uint4*>(xr + ch * 8)), v[c]);
@@ -57,7 +58,7 @@ __global__ void __launch_bounds__(256) seq_layernorm_kernel(const LnParams P) {
   const float mean = warp_sum(sum) / static_cast<float>(P.d);
   float sq = 0.f;
 #pragma unroll
-  for (int c = 0; c < kLnMaxChunks; ++c) {
+  for (int c = 0; c < kChunks; ++c) {
     if (c * 32 + lane < nchunk) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -69,7 +70,7 @@ __global__ void __launch_bounds__(256) seq_layernorm_kernel(const LnParams P) {
   const float rstd = rsqrtf(warp_sum(sq) / static_cast<float>(P.d) + P.eps);
   __nv_bfloat16* yr = P.y + static_cast<size_t>(row) * P.y_pitch;
 #pragma unroll
-  for (int c = 0; c < kLnMaxChunks; ++c) {
+  for (int c = 0; c < kChunks; ++c) {
     const int ch = c * 32 + lane;
     if (ch < nchunk) {
       const float4 g0 = ldg_f4(P.gamma + ch * 8), g1 = ldg_f4(P.gamma + ch * 8 + 4);
@@ -107,6 +108,7 @@ __global__ void __launch_bounds__(256) seq_masked_mean_pool_kernel(const PoolPar
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   float cnt = 0.f;
   const bool col_ok = col < P.d;
+#pragma unroll 4
   for (int l = ty; l < L; l += 32) {
     const float w = mrow ? (mrow[l] ? 1.f : 0.f) : 1.f;
     cnt += w;
