@@ -137,10 +137,13 @@ def algorithmic_work(name, B, H=512, n_hot=12746240, n_gemm=12715008, dsum=1792)
 # CPU arm: the oracle port (torch CPU ops, all host threads)
 # ------------------------------------------------------------------------------------------------------------
 def cpu_oracle_steps(batch, steps, warmup, budget_s=None):
+    """The oracle port driven exactly like the reference drives its modules (forensic_trainer.py:286-298): leaf
+    parameters, F.cross_entropy, backward, clip_grad_norm_(5.0), torch.optim.AdamW — O.TorchStep; no per-step parameter
+    clones (round 1's port cloned 53 MB per step and measured 12 % slower than the real reference on the same CPU)."""
     from oracle import fnd_oracle as O
     torch.set_num_threads(os.cpu_count() or 1)
     fus, clf = O.init_params(42)
-    opt = O.AdamWState()
+    ts = O.TorchStep(fus, clf, device="cpu")
     pool = [synth_batch(batch, 100 + i) for i in range(4)]
     gen = torch.Generator().manual_seed(0)
 
@@ -150,16 +153,42 @@ def cpu_oracle_steps(batch, steps, warmup, budget_s=None):
         return {"fuse0": m((batch, 1024), 0.1), "fuse1": m((batch, 512), 0.1), "pre0": m((batch, 512), 0.1),
                 "pre1": m((batch, 512), 0.1), "tree": m((batch, 6, 2), 0.3)}
     for i in range(warmup):
-        O.train_step(fus, clf, pool[i % 4], opt, dropout=0.1, masks=masks())
+        ts.step(pool[i % 4], dropout=0.1, masks=masks())
     t0 = time.perf_counter()
     done = 0
     for i in range(steps):
-        O.train_step(fus, clf, pool[i % 4], opt, dropout=0.1, masks=masks())
+        ts.step(pool[i % 4], dropout=0.1, masks=masks())
         done += 1
         if budget_s is not None and time.perf_counter() - t0 > budget_s:
             break
     dt = time.perf_counter() - t0
     return done, dt, torch.get_num_threads()
+
+
+def gpu_eager_steps(batch, steps, warmup, dev):
+    """Same-box bar: the oracle's restated forward run EAGERLY on the B200 by stock
+    PyTorch (ATen / cuBLAS kernels, autograd, clip_grad_norm_, torch.optim.AdamW) — what a device-patched reference
+    would execute. A baseline, never the product path."""
+    from oracle import fnd_oracle as O
+    fus, clf = O.init_params(42)
+    ts = O.TorchStep(fus, clf, device=str(dev))
+    pool = [{k: v.to(dev) for k, v in synth_batch(batch, 100 + i).items()} for i in range(4)]
+
+    def masks():
+        def m(shape, p):
+            return (torch.rand(shape, device=dev) >= p).float() / (1.0 - p)
+        return {"fuse0": m((batch, 1024), 0.1), "fuse1": m((batch, 512), 0.1), "pre0": m((batch, 512), 0.1),
+                "pre1": m((batch, 512), 0.1), "tree": m((batch, 6, 2), 0.3)}
+    for i in range(warmup):
+        ts.step(pool[i % 4], dropout=0.1, masks=masks())
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        ts.step(pool[i % 4], dropout=0.1, masks=masks())
+    e1.record()
+    torch.cuda.synchronize()
+    return steps * batch / (e0.elapsed_time(e1) / 1e3)
 
 
 def run_reference_arm(args):
@@ -175,13 +204,177 @@ def run_reference_arm(args):
         "config": {"workload": f"fusion train step (fwd+CE+bwd+clip+AdamW), batch {args.batch}, FakeSV-shaped synthetic features",
                    "batch_per_gpu": args.batch, "hidden": 512, "device": "host CPU"},
         "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": "port",
-                         "sample": f"{steps} full training steps at batch {args.batch} (oracle/fnd_oracle.py, torch CPU ops; "
+                         "sample": f"{steps} full training steps at batch {args.batch} (oracle/fnd_oracle.py TorchStep: restated forward + "
+                                   "the reference's own backward / clip_grad_norm_ / torch.optim.AdamW, torch CPU ops; "
                                    "the reference is pure Python on ATen and /root/reference does not travel)"},
         "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
 
+
+
+# ------------------------------------------------------------------------------------------------------------
+# Extra measurement legs of the B200 arm (rank 0, N = 1): BASELINE.json configs[2] (eval forward, batch 1024, fp32 vs
+# bf16), the fp32-mode training step, the drop-in trainer's own epoch loop, and the stock-PyTorch eager bar
+# ------------------------------------------------------------------------------------------------------------
+def _timed_graph_steps(step, fn, idx_pool, flush_buf, K, W):
+    for i in range(W):
+        step.static_gather.copy_(idx_pool[i % len(idx_pool)], non_blocking=True)
+        fn()
+    torch.cuda.synchronize()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    for i in range(K):
+        step.static_gather.copy_(idx_pool[(W + i) % len(idx_pool)], non_blocking=True)
+        flush_buf.zero_()
+        evs[i][0].record()
+        fn()
+        evs[i][1].record()
+    torch.cuda.synchronize()
+    return sum(a.elapsed_time(b) for a, b in evs) / K
+
+
+def extra_single_gpu_legs(dev, flush_buf, K=30, W=5):
+    from ultrafnd_git_b200.fused import FusedStep, DeviceCache, FEATURE_KEYS
+    from ultrafnd_git_b200.modules import CrossModalTransformer, DeepTruthClassifier
+    out = {}
+
+    def make(precision, B, pool=4, train=True):
+        torch.manual_seed(42)
+        f, c = CrossModalTransformer(precision=precision), DeepTruthClassifier(precision=precision)
+        f.train(train); c.train(train)
+        st = FusedStep(f, c, B, precision=precision, use_graph=True)
+        hb = [synth_batch(B, 3000 + i) for i in range(pool)]
+        cache = DeviceCache({k: torch.cat([b[k] for b in hb]) for k in FEATURE_KEYS}, torch.cat([b["aux"] for b in hb]),
+                            torch.cat([b["label"] for b in hb]), dev)
+        st.attach_cache(cache)
+        idx = torch.stack([torch.arange(i * B, (i + 1) * B) for i in range(pool)]).to(dev)
+        return st, idx
+    # ---- configs[2]: inference-only eval forward, batch 1024, fp32 (bf16x3 tensor-core mode) vs bf16 ----
+    ev = {}
+    for prec in ("bf16", "fp32"):
+        st, idx = make(prec, 1024, pool=2, train=False)
+        ms = _timed_graph_steps(st, lambda: st.eval_step(from_cache=True), idx, flush_buf, K, W)
+        st.plan.check_error()
+        ev[prec] = {"samples_per_s": 1024 / (ms / 1e3), "ms_per_step": ms}
+        del st
+    out["eval_b1024"] = {"workload": "eval forward (fusion + classifier + row losses), batch 1024, inputs resident, CUDA graph, L2 flushed",
+                         "bf16": ev["bf16"], "f32_bf16x3": ev["fp32"], "flops_per_sample": 25.47e6}
+    # ---- fp32-mode (bf16x3) training step at the benchmark batch ----
+    st, idx = make("fp32", 128)
+    ms = _timed_graph_steps(st, lambda: st.train_step(from_cache=True), idx, flush_buf, K, W)
+    st.plan.check_error()
+    out["train_f32_bf16x3"] = {"samples_per_s": 128 / (ms / 1e3), "ms_per_step": ms, "batch": 128,
+                               "note": "every GEMM as three bf16 tensor-core products (fp32-equivalent results)"}
+    del st
+    # ---- the drop-in ForensicTrainer's own epoch loop (public API: trainer._epoch_loop / fit), device cache ----
+    try:
+        from ultrafnd_git_b200.trainer import ForensicTrainer, TrainConfig, synthetic_cache
+        import tempfile
+        cache = synthetic_cache(n=128 * 48, seed=1)
+        cache["gnn_Z"] = torch.randn(len(cache["labels"]), 128)
+        cfg = TrainConfig(data_root="unused", ocr_phrase_pkl=None, out_dir=tempfile.mkdtemp(prefix="fnd_bench_"), batch_size=128,
+                          epochs=1, save_best=False)
+        tr = ForensicTrainer(cfg, cache=cache, precision="bf16")
+        tr.epoch = 1
+        tr._epoch_loop(tr.train_loader, "train")
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        tr.epoch = 2
+        tr._epoch_loop(tr.train_loader, "train")
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        out["trainer_epoch"] = {"samples_per_s": len(tr.tr_idx) / dt, "rows": int(len(tr.tr_idx)), "batch": 128, "seconds": dt,
+                                "note": "ForensicTrainer._epoch_loop('train') wall clock incl. per-epoch metrics gather + sklearn on the host"}
+        del tr
+    except Exception as e:      # noqa: BLE001 - reported, never fatal for the headline
+        out["trainer_epoch"] = {"error": f"{type(e).__name__}: {str(e)[:160]}"}
+    # ---- stock PyTorch eager on the same B200 (baseline only) ----
+    try:
+        v = gpu_eager_steps(128, 30, 5, dev)
+        out["gpu_eager_baseline"] = {"value": v, "unit": "samples/s", "kind": "oracle forward + torch autograd / clip_grad_norm_ / "
+                                     "torch.optim.AdamW, eager ATen + cuBLAS kernels on this GPU, fp32, batch 128 (baseline only)"}
+    except Exception as e:      # noqa: BLE001
+        out["gpu_eager_baseline"] = {"error": f"{type(e).__name__}: {str(e)[:160]}"}
+    return out
+
+
+def dp_parity_check(world, rank, dev, precision, batch):
+    """Driver-visible parity of the benchmarked data-parallel configuration (same precision, same wire format, same DP
+    flags as the timed step): 4 dropout-off steps on `world` ranks against the single-GPU fused step on the concatenated
+    global batch from the same initial weights. Tolerances (bf16: north_star's 2e-2; fp32 mode: 1e-3) apply to the loss,
+    the gradient norm and the relative L2 error of the whole parameter update; bf16 shadows must be bit-identical on
+    every rank. Every rank calls this; the dict is meaningful on rank 0."""
+    import torch.distributed as dist
+    from ultrafnd_git_b200.fused import FusedStep
+    from ultrafnd_git_b200.modules import CrossModalTransformer, DeepTruthClassifier
+    steps = 4
+    B = max(8, min(batch, 1024 // world))
+
+    def build():
+        torch.manual_seed(7)
+        f, c = CrossModalTransformer(precision=precision), DeepTruthClassifier(precision=precision)
+        with torch.no_grad():
+            g = torch.Generator().manual_seed(8)
+            for n, p in c.named_parameters():
+                if "gates" in n or "leaf_logits" in n:
+                    p.add_(0.05 * torch.randn(p.shape, generator=g).to(p.device))
+        for m in list(f.modules()) + list(c.modules()):
+            if isinstance(m, torch.nn.Dropout):
+                m.p = 0.0
+        f.train(); c.train(); f._sync_dropout(); c._sync_dropout()
+        return f, c
+    f, c = build()
+    step = FusedStep(f, c, B, precision=precision, use_graph=True, dp_group=dist.group.WORLD)
+    eng, plan = step.engine, step.plan
+    eng.lib.fnd_set_loss_scale(plan.handle, 1.0 / (B * world), eng.stream_ptr())
+    init = eng.params.clone()
+    batches = [synth_batch(B * world, 500 + s) for s in range(steps)]
+    losses, norms = [], []
+    for s_ in range(steps):
+        mine = {k: v[rank * B:(rank + 1) * B] for k, v in batches[s_].items()}
+        step.load_batch({k: v.to(dev) for k, v in mine.items()})
+        step.train_step_dp()
+        st = plan.state()
+        t = torch.tensor([st["loss"]], device=dev, dtype=torch.float64)
+        dist.all_reduce(t)
+        losses.append(float(t.item())); norms.append(st["grad_norm"])
+    plan.check_error()
+    sh = eng.shadow_hi.view(torch.int16).to(torch.int64)
+    chk = torch.stack([sh.sum(), (sh * (torch.arange(sh.numel(), device=dev) % 8191)).sum()])
+    gathered = [torch.zeros_like(chk) for _ in range(world)]
+    dist.all_gather(gathered, chk)
+    shadows_identical = all(torch.equal(g, gathered[0]) for g in gathered)
+    eng.gather_master()
+    dp_params = eng.params[:eng.n_hot].clone()
+    dist.barrier()
+    res = None
+    if rank == 0:
+        f1, c1 = build()
+        ref = FusedStep(f1, c1, B * world, precision=precision, use_graph=False)
+        ref.engine.params.copy_(init)
+        ref.engine.refresh_shadows(ref.engine.param_version())
+        rl, rn = [], []
+        for s_ in range(steps):
+            ref.load_batch({k: v.to(dev) for k, v in batches[s_].items()})
+            ref.train_step()
+            st = ref.plan.state()
+            rl.append(st["loss"]); rn.append(st["grad_norm"])
+        ref.plan.check_error()
+        rp = ref.engine.params[:eng.n_hot]
+        upd = rp - init[:eng.n_hot]
+        tol = 2e-2 if precision == "bf16" else 1e-3
+        loss_rel = max(abs(a - b) / abs(b) for a, b in zip(losses, rl))
+        norm_rel = max(abs(a - b) / abs(b) for a, b in zip(norms, rn))
+        rel_l2 = float((dp_params - rp).double().norm() / upd.double().norm())
+        outliers = float(((dp_params - rp).abs() > 0.1 * float(upd.abs().max())).double().mean())
+        wire = "bf16" if eng.symm["stage_bf16"] else "fp32"
+        res = {"steps": steps, "batch_per_gpu": B, "global_batch": B * world, "precision": precision, "wire": wire,
+               "loss_rel": loss_rel, "norm_rel": norm_rel, "update_rel_l2": rel_l2, "outliers": outliers,
+               "shadows_identical": bool(shadows_identical), "tolerance": tol,
+               "ok": bool(shadows_identical and loss_rel < tol and norm_rel < tol and rel_l2 < tol and outliers < 1e-3)}
+    dist.barrier()
+    return res
 
 # ------------------------------------------------------------------------------------------------------------
 # B200 arm
@@ -371,10 +564,22 @@ def run_b200_arm(args):
     if world > 1:
         dist.barrier()
 
+    # ---- driver-visible parity of the data-parallel configuration just timed (every rank takes part) ----
+    dp_parity = None
+    if world > 1 and dp_mode == "peer" and not args.no_dp_parity:
+        try:
+            dp_parity = dp_parity_check(world, rank, dev, args.precision, B)
+        except Exception as e:          # noqa: BLE001 - reported in the JSON line
+            dp_parity = {"ok": False, "error": f"{type(e).__name__}: {str(e)[:200]}"}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
+
+    extras = {}
+    if world == 1 and not args.no_extras:
+        extras = extra_single_gpu_legs(dev, flush_buf)
 
     # ---- roofline of the dominant kernel ----
     peaks = measured_peaks()
@@ -401,6 +606,7 @@ def run_b200_arm(args):
         if os.path.exists(tr):
             with open(tr) as f:
                 roofline["traffic"] = json.load(f).get(dom)
+            roofline["traffic_source"] = "committed ncu --set full capture (profiles/traffic.json, profiles/r01_step_traffic.json), not measured in this run"
 
     # ---- CPU baseline (bounded sample of the same workload, oracle port) ----
     cpu_baseline = None
@@ -433,6 +639,16 @@ def run_b200_arm(args):
         "kernels_ms": {k: round(v, 5) for k, v in sorted(kernels.items(), key=lambda kv: -kv[1])},
         # whole-step fractions: 74.57 MFLOP/sample of tensor work; 459 MB/step of compulsory HBM traffic
         # (weights twice, wgrad, AdamW) + 3.6 kB/sample of inputs, per GPU
+        "dp_parity": dp_parity,
+        # the reference's own co-attention (ForensicCoAttention, vector-level): its tensor-core work is the grouped q/k/v
+        # projection launch (+ its dgrad / share of wgrad); fraction of the measured bf16 peak while that launch runs
+        "coattn_tensor_frac": ({"kernel": "gemm_qkv (9 stacked q/k/v projections of the 3 ForensicCoAttention blocks)",
+                                "flops": 2.0 * B * 9 * 512 * 512, "ms": kernels.get("gemm_qkv"),
+                                "frac_of_measured_bf16_peak": (2.0 * B * 9 * 512 * 512 / (kernels["gemm_qkv"] / 1e3) / (peaks["bf16_tflops"] * 1e12))
+                                if kernels.get("gemm_qkv") else None,
+                                "note": "latency-bound at batch 128 (4.7 MB of weights, 0.6 GFLOP); the sequence-level co-attention "
+                                        "of north_star is measured by `bench.py --workload stress`"} if kernels else None),
+        **extras,
         "step_roofline": {"tensor_frac": B * 74.57e6 / (total_ms / K / 1e3) / (peaks["bf16_tflops"] * 1e12),
                           "hbm_frac": (B * 3604 + 459e6) / (total_ms / K / 1e3) / (peaks["hbm_gbs"] * 1e9),
                           "note": "at batch 128 the step is a 17-kernel latency chain + the AdamW stream (DESIGN.md §4)"},
@@ -447,11 +663,24 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
-    ap.add_argument("--batch", type=int, default=128, help="per-GPU batch (BASELINE.json configs[1]: 128)")
+    ap.add_argument("--batch", type=int, default=None, help="per-GPU batch (train: 128 = BASELINE.json configs[1]; stress: 32)")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the eval / fp32 / trainer / eager-GPU legs (N = 1)")
+    ap.add_argument("--no-dp-parity", action="store_true", help="skip the data-parallel parity check (N > 1)")
+    ap.add_argument("--workload", default="train", choices=["train", "stress"],
+                    help="train: BASELINE.json configs[1] (default, the headline); stress: configs[4], the sequence front-end")
     args = ap.parse_args()
+    if args.batch is None:
+        args.batch = 128 if args.workload == "train" else 32
+    if args.workload == "stress":
+        import bench_stress
+        if args.impl == "reference":
+            bench_stress.run_reference_arm(args)
+        else:
+            bench_stress.run_b200_arm(args)
+        return
     if args.impl == "reference":
         if args.steps > 60:
             args.steps = 60        # bounded sample: ~0.1-0.2 s per CPU step

@@ -163,6 +163,8 @@ static int build_tables(Plan& P) {
     // bf16 mirror of the weight gradients (same element offsets as the gradient arena); pre.0.weight's rows (pitch 514)
     // are not 16-byte aligned in bf16 and stay fp32-only
     if (P.grads_bf && dst >= P.grads && dst < P.grads + P.L.n_hot && (pitch & 7) == 0) e.out_bf = P.grads_bf + (dst - P.grads);
+    // eligible for the data-parallel fused push (routed store-only epilogue): a GEMM weight in the arena with 16-byte rows
+    if (dst >= P.grads && dst < P.grads + P.L.n_hot && (pitch & 63) == 0 && (k_in & 63) == 0) e.routed = 1;
     return add_problem(P, T, dY, X, n_out, k_in, B, 128, 1, e, "", 0);
   };
   const int dA_tiles = ceil_div(P.TD + 2, kGemmBM) * ceil_div(H, 128);
@@ -299,6 +301,7 @@ static int upload_tables(Plan& P, cudaStream_t st) {
 static inline RunCtx make_ctx(const Plan& P, int training) {
   DevState* S = P.state();
   RunCtx c;
+  memset(&c, 0, sizeof(c));
   c.err = &S->err;
   c.rng = S->rng;
   c.training = training;
@@ -333,10 +336,12 @@ static void mark(const Plan& Pc, const char* name, cudaStream_t st) {
   P.marks.emplace_back(name, ev);
 }
 static int run_gemm(const Plan& P, const GemmTable& T, int training, cudaStream_t st, const char* name,
-                    const FinParams* fin = nullptr, int fin_ctas = 0) {
+                    const FinParams* fin = nullptr, int fin_ctas = 0, const DpRoute* route = nullptr) {
   FND_SKIP(P);
   const bool merged = fin && gemm_launch_is_light(T.kind, T.host.data(), static_cast<int>(T.host.size()));
-  FND_CUDA_OK(launch_gemm(T.kind, T.host.data(), static_cast<int>(T.host.size()), T.grid, make_ctx(P, training), st,
+  RunCtx ctx = make_ctx(P, training);
+  if (route) ctx.route = *route;
+  FND_CUDA_OK(launch_gemm(T.kind, T.host.data(), static_cast<int>(T.host.size()), T.grid, ctx, st,
                           take_pdl(P), merged ? fin : nullptr, merged ? fin_ctas : 0));
   mark(P, name, st);
   if (fin && !merged) {
@@ -821,6 +826,11 @@ static int train_fwd_bwd_impl(void* plan, const fnd_inputs* in, int fused_optimi
   cudaStream_t side = reinterpret_cast<cudaStream_t>(side_stream);
   const bool overlap = side_stream != nullptr && P.dp_bound && (dp_flags & 1);
   const bool defer = side_stream != nullptr && P.dp_bound && (dp_flags & 2);
+  // bit 2: fused push — the weight-gradient launch's epilogue stores each tile into its owner's staging slot (bf16 wire
+  // format, merged-finalize light launch only; not combined with the early push)
+  const bool fused_push = P.dp_bound && (dp_flags & 4) && !overlap && P.dp.stage_bf16 && P.dp.world > 1 && !P.dp.mc_grads &&
+                          gemm_launch_is_light(P.wg_all.kind, P.wg_all.host.data(), static_cast<int>(P.wg_all.host.size()));
+  P.dp_fused_now = fused_push;
   if (P.dp_bound && (dp_flags || skip_norm)) {
     // A deferred update of the previous step: run it on the side stream under the first four kernels of this forward
     // pass (one CTA per SM, so their GEMM CTAs still fit), or right here when there is no side stream.
@@ -868,7 +878,7 @@ static int train_fwd_bwd_impl(void* plan, const fnd_inputs* in, int fused_optimi
   // gradients next reduces the slots to the global norm: adamw_kernel in the fused step (no election, fence or atomic
   // on the tile CTAs' critical path — measured 10 us), norm_finish_kernel otherwise.
   const FinParams f = fin_params(P, P.fin_all, P.wg_all.grid, P.total_slots, false, 0, 0);
-  FND_OK(run_gemm(P, P.wg_all, 1, st, "wgrad_all", &f, P.fin_all.grid));
+  FND_OK(run_gemm(P, P.wg_all, 1, st, "wgrad_all", &f, P.fin_all.grid, fused_push ? &P.dp_route : nullptr));
   if (!fused_optimizer && !skip_norm) {
     FND_SKIP(P);
     FND_CUDA_OK(launch_k(norm_finish_kernel, 1, 32, 0, st, take_pdl(P), P.buf<float>("slots"), P.total_slots, P.state(), 0));
@@ -883,7 +893,7 @@ int fnd_train_step_dp(void* plan, const fnd_inputs* in, void* stream, void* side
   Plan* PP = as_plan(plan);
   if (!PP || !PP->bound) return -5;
   if (!PP->dp_bound) return -7;
-  if (!side_stream) flags = 0;
+  if (!side_stream) flags &= 4;      // overlap / deferral need the side stream; the fused push (bit 2) does not
   if (flags & 1) return train_fwd_bwd_impl(plan, in, 0, stream, side_stream, true, flags);
   // (skip_norm: the reduced gradient's norm is what counts)
   FND_OK(train_fwd_bwd_impl(plan, in, 0, stream, side_stream, true, flags));
@@ -995,6 +1005,29 @@ int fnd_dp_bind(void* plan, int rank, int world, const unsigned long long* peer_
   d.a = adamw_params(P);
   P.dp = d;
   P.dp_bound = true;
+  {
+    // routing table of the fused push (fnd_gemm.cuh: DpRoute); same geometry as dp_segments
+    DpRoute r;
+    memset(&r, 0, sizeof(r));
+    r.rank = rank; r.world = world;
+    r.grads = P.grads;
+    r.slot_cap = static_cast<uint32_t>(d.slot_cap);
+    const size_t a0 = static_cast<size_t>(P.L.at("fusion.fuse_mlp.0.weight")), a1 = static_cast<size_t>(P.L.at("clf.pre.0.weight"));
+    r.a0 = static_cast<uint32_t>(a0); r.a1 = static_cast<uint32_t>(a1);
+    const size_t rb[kDpMaxSeg][2] = {{a0, a1}, {0, a0}, {a1, static_cast<size_t>(P.L.n_hot)}};
+    for (int s = 0; s < kDpMaxSeg; ++s) {
+      const size_t n = rb[s][1] - rb[s][0];
+      size_t per = (n + world - 1) / world;
+      per = (per + 1023) / 1024 * 1024;
+      r.r_lo[s] = static_cast<uint32_t>(rb[s][0]);
+      r.per[s] = static_cast<uint32_t>(per);
+    }
+    for (int p = 0; p < world; ++p) {
+      r.stage[p] = static_cast<__nv_bfloat16*>(d.stage[p]);
+      for (int s = 0; s < kDpMaxSeg; ++s) r.goff[p][s] = static_cast<uint32_t>(d.seg_goff[p][s]);
+    }
+    P.dp_route = r;
+  }
   if (!P.ev_fork) {
     FND_CUDA_OK(cudaEventCreateWithFlags(&P.ev_fork, cudaEventDisableTiming));
     FND_CUDA_OK(cudaEventCreateWithFlags(&P.ev_join, cudaEventDisableTiming));
@@ -1034,12 +1067,23 @@ static int dp_tail(Plan& P, bool early_done, bool defer, cudaStream_t st) {
     // NVSwitch multicast available: the reduce-scatter is one in-switch-reduction kernel
     FND_CUDA_OK(launch_k(dp_pull_kernel, kDpGrid, 256, 0, st, false, P.dp));
     mark(P, "dp_pull", st);
+  } else if (P.dp_fused_now) {
+    // fused push: the wgrad epilogue already delivered the GEMM-weight tiles; push the two un-routed arena intervals
+    // (pre.0.weight and the non-GEMM parameters), raise the flags, reduce all N staged pieces
+    const size_t r0 = static_cast<size_t>(P.L.at("clf.pre.0.weight"));
+    // (with aux_dim == 0 pre.0.weight has 16-byte rows and is routed like every other GEMM weight: empty interval)
+    const size_t r0e = P.d.aux_dim ? r0 + static_cast<size_t>(P.H) * (P.H + P.d.aux_dim) : r0;
+    FND_CUDA_OK(launch_k(dp_push_residual_kernel, 148, 256, 0, st, false, P.dp, r0, (r0e + 63) / 64 * 64,
+                         static_cast<size_t>(P.L.n_shadow), static_cast<size_t>(P.L.n_hot)));
+    mark(P, "dp_push_residual", st);
+    FND_CUDA_OK(launch_k(dp_reduce_kernel<true>, kDpGrid, 256, 0, st, false, P.dp, 0, 1));
+    mark(P, "dp_reduce", st);
   } else {
     // without an early push, ONE launch moves all three ranges (it raises the late flags; the early bank is not used)
     FND_OK(dp_push(P, early_done ? 1 : 0, kDpMaxSeg, kPadReadyLate, kPadCounter, kDpGrid, 256, st));
     mark(P, "dp_push", st);
-    if (P.dp.stage_bf16) FND_CUDA_OK(launch_k(dp_reduce_kernel<true>, kDpGrid, 256, 0, st, false, P.dp, early_done ? 1 : 0));
-    else FND_CUDA_OK(launch_k(dp_reduce_kernel<false>, kDpGrid, 256, 0, st, false, P.dp, early_done ? 1 : 0));
+    if (P.dp.stage_bf16) FND_CUDA_OK(launch_k(dp_reduce_kernel<true>, kDpGrid, 256, 0, st, false, P.dp, early_done ? 1 : 0, 0));
+    else FND_CUDA_OK(launch_k(dp_reduce_kernel<false>, kDpGrid, 256, 0, st, false, P.dp, early_done ? 1 : 0, 0));
     mark(P, "dp_reduce", st);
   }
   FND_CUDA_OK(launch_k(dp_adamw_kernel, kDpGrid, 256, 0, st, false, P.dp, defer ? 1 : 0, static_cast<int>(kDpMaxSeg), 0,

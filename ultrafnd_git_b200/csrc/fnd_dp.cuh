@@ -159,6 +159,52 @@ __global__ void __launch_bounds__(256, 4) dp_push_kernel(DpParams d, int s0, int
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// 1a'. residual push of the FUSED mode: the weight-gradient GEMM's epilogue has already stored every GEMM-weight tile
+//      into its owner's staging slot (fnd_gemm.cuh, DpRoute); what is left are the two arena intervals that launch does
+//      not route — pre.0.weight (row pitch 514: not 16-byte aligned) and the small non-GEMM parameters behind the
+//      shadows (biases, gates, thresholds, leaf tables, evidence MLPs; written by the finalize CTAs) — about 2 % of the
+//      gradient. They are pushed here, to EVERY owner including this rank itself (the fused reduce reads all N pieces
+//      from staging), as bf16; the last CTA then raises the "late" flags, which also cover the epilogue's stores (that
+//      launch has completed: ordinary stream order).
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256, 4) dp_push_residual_kernel(DpParams d, size_t lo0, size_t hi0, size_t lo1, size_t hi1) {
+  __shared__ int is_last;
+  unsigned int* mypad = d.pad[d.rank];
+  const unsigned int epoch = mypad[kPadEpoch] + 1u;
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  const size_t tid = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  for (int sg = 0; sg < d.nseg; ++sg) {
+    for (int q = 0; q < d.world; ++q) {
+      const int p = (d.rank + q) % d.world;
+      for (int iv = 0; iv < 2; ++iv) {
+        const size_t a = iv ? lo1 : lo0, b = iv ? hi1 : hi0;
+        const size_t lo = d.seg_lo[p][sg] > a ? d.seg_lo[p][sg] : a;
+        const size_t hi = d.seg_hi[p][sg] < b ? d.seg_hi[p][sg] : b;
+        if (hi <= lo) continue;
+        const size_t n4 = (hi - lo) >> 2;                        // interval and segment bounds are multiples of 64
+        const float* src = d.grads + lo;
+        __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(d.stage[p]) + static_cast<size_t>(d.rank) * d.slot_cap + d.seg_goff[p][sg] +
+                             (lo - d.seg_lo[p][sg]);
+        for (size_t i4 = tid; i4 < n4; i4 += stride) {
+          const float4 v = __ldcg(reinterpret_cast<const float4*>(src) + i4);
+          *reinterpret_cast<uint2*>(dst + i4 * 4) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+        }
+      }
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = (atomicAdd(mypad + kPadCounter, 1u) == gridDim.x - 1) ? 1 : 0;
+  __syncthreads();
+  if (!is_last) return;
+  if (threadIdx.x == 0) mypad[kPadCounter] = 0u;
+  if (threadIdx.x < static_cast<unsigned>(d.world)) {
+    __threadfence_system();
+    st_release_sys(d.pad[threadIdx.x] + kPadReadyLate + d.rank, epoch);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // 1'. pull: the whole reduce-scatter as ONE kernel when the fabric has multicast — every rank reads its slice through
 //     the NVSwitch with multimem.ld_reduce, which fetches the same address from all N gradient arenas and returns the
 //     sum (accumulated in fp32 inside the switch). No staging, no sender-side kernel, one flag round. GEMM-weight
@@ -238,8 +284,9 @@ __global__ void __launch_bounds__(256) dp_pull_kernel(DpParams d) {
 // 1b. reduce: own slice + the staged pieces of every peer, in rank order (local memory only) + slice norm
 // ---------------------------------------------------------------------------------------------------------------
 // `early_used`: segment 0 was pushed by a separate (early) launch with its own flag bank.
+// `own_from_stage` (fused mode): this rank's own piece lies in its staging slot too (bf16), not in the gradient arena.
 template <bool BF16>
-__global__ void __launch_bounds__(256) dp_reduce_kernel(DpParams d, int early_used) {
+__global__ void __launch_bounds__(256) dp_reduce_kernel(DpParams d, int early_used, int own_from_stage) {
   __shared__ float red[8];
   __shared__ int is_last;
   unsigned int* mypad = d.pad[d.rank];
@@ -257,7 +304,7 @@ __global__ void __launch_bounds__(256) dp_reduce_kernel(DpParams d, int early_us
 #pragma unroll
       for (int p = 0; p < kDpMaxWorld; ++p) {
         if (p < d.world) {
-          if (p == d.rank) {
+          if (p == d.rank && !own_from_stage) {
             t[p] = __ldcg(reinterpret_cast<const float4*>(d.grads + lo) + i4);
           } else if (BF16) {
             const __nv_bfloat16* sp = static_cast<const __nv_bfloat16*>(d.stage[d.rank]) + static_cast<size_t>(p) * d.slot_cap + goff;

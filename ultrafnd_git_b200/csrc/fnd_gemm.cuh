@@ -77,7 +77,30 @@ struct EpiParams {
   unsigned int* done_ctr;            // non-null: bumped once per tile after its stores (consumers in the same launch wait on it)
   __nv_bfloat16* out_bf;             // store-only epilogues: also store bf16(v) at the same [m * f32_pitch + n] offsets (the
                                      // bf16 gradient mirror that the data-parallel step reduces through the NVSwitch)
+  int routed;                        // host-set: out_f32 lies in the gradient arena (pitch % 8 == 0); with an active DpRoute the
+                                     // store-only epilogue sends each row segment straight to its OWNER's staging slot
 };
+
+// Data-parallel routing of weight-gradient tiles (fused reduce-scatter push, bf16 on the wire). The hot arena [0, n_hot)
+// is cut into three ranges (0: [a0, a1), 1: [0, a0), 2: [a1, n_hot)); rank p owns elements [p * per[s], (p+1) * per[s]) of
+// range s (per[s] a multiple of 1024) and keeps, for every source rank q, a staging slot of slot_cap bf16 elements in
+// which its piece of range s starts at goff[p][s]. A 64-element row segment of a weight gradient (64-aligned in the
+// arena) therefore has exactly one owner. world == 0: routing off.
+struct DpRoute {
+  int rank, world;
+  const float* grads;                // this rank's gradient arena (arena index = pointer difference)
+  __nv_bfloat16* stage[8];           // staging buffer of every rank (peer-mapped)
+  uint32_t slot_cap;
+  uint32_t a0, a1;
+  uint32_t r_lo[3], per[3];
+  uint32_t goff[8][3];
+};
+__device__ __forceinline__ __nv_bfloat16* dp_route_dst(const DpRoute& R, uint32_t i) {
+  const int s = (i >= R.a0) ? (i < R.a1 ? 0 : 2) : 1;
+  const uint32_t rel = i - R.r_lo[s];
+  const uint32_t owner = rel / R.per[s];
+  return R.stage[owner] + (static_cast<size_t>(R.rank) * R.slot_cap + R.goff[owner][s] + (rel - owner * R.per[s]));
+}
 
 struct alignas(128) GemmProblem {
   CUtensorMap tmA[2];                // [0] hi, [1] lo
@@ -100,6 +123,7 @@ struct RunCtx {
   const uint32_t* rng;               // [0] seed lo, [1] seed hi, [2] fusion salt, [3] classifier salt
   int training;                      // 0: every dropout (forward masks and backward gates) is the identity
   long long* dbg;                    // optional [grid][8] clock64 stamps (probe builds only; null in production)
+  DpRoute route;                     // data-parallel fused push (weight-gradient launch only; world == 0 otherwise)
 };
 #define FND_STAMP(i) do { if (ctx.dbg) ctx.dbg[static_cast<size_t>(blockIdx.x) * 8 + (i)] = clock64(); } while (0)
 
@@ -405,7 +429,50 @@ fnd_gemm_kernel(const __grid_constant__ GemmTableP tbl, RunCtx ctx, const __grid
         a1 = E.aux[static_cast<size_t>(m) * 2 + 1];
       }
       if (epi_tid == 0) FND_STAMP(5);
-      if (E.plain_f32 == 2 && bn >= 64) {
+      if (kVariant == 1 && E.routed && ctx.route.world > 1 && E.plain_f32 == 2 && bn >= 64) {
+        // Data-parallel fused push: the reduce-scatter's data movement happens HERE. Each warp packs its 32 rows x 64
+        // columns of the accumulator to bf16 through shared memory and stores every row segment (128 contiguous bytes,
+        // 8 lanes x 16 B) into the staging slot of the rank that OWNS that arena range — over NVLink for 7 of 8 segments
+        // on 8 GPUs, locally for its own. The fp32 gradient is never written to HBM and no separate push kernel re-reads it.
+        constexpr int kRowB = 144;                                       // staged row: 64 bf16 + 16 B pad (conflict-free)
+        uint8_t* stg = smem + ew * (32 * kRowB);
+        const uint32_t base_idx = static_cast<uint32_t>(E.out_f32 - ctx.route.grads);
+        const int cw = bn >> 1;                                          // columns per warp: 64 (bn 128) or 32 (bn 64)
+        const int rsub = lane >> 3, ch8 = lane & 7;
+#pragma unroll 1
+        for (int c = half * cw; c < (half + 1) * cw; c += 64) {
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            if (hh * 32 < cw) {
+              uint32_t r[32];
+              tmem_ld_32x32(taddr + c + hh * 32, r);
+              tmem_ld_wait();
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                *reinterpret_cast<uint4*>(stg + lane * kRowB + hh * 64 + q * 16) =
+                    make_uint4(pack_bf16x2(__uint_as_float(r[8 * q]), __uint_as_float(r[8 * q + 1])),
+                               pack_bf16x2(__uint_as_float(r[8 * q + 2]), __uint_as_float(r[8 * q + 3])),
+                               pack_bf16x2(__uint_as_float(r[8 * q + 4]), __uint_as_float(r[8 * q + 5])),
+                               pack_bf16x2(__uint_as_float(r[8 * q + 6]), __uint_as_float(r[8 * q + 7])));
+            }
+          }
+          __syncwarp();
+          const int n = nb + c + ch8 * 8;
+          if (proceed && n < PN && ch8 * 8 < cw) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const int rr = k * 4 + rsub;
+              const int mm = tm * kGemmBM + lane_grp * 32 + rr;
+              if (mm < PM) {
+                const uint4 v4 = *reinterpret_cast<const uint4*>(stg + rr * kRowB + ch8 * 16);
+                __nv_bfloat16* dst = dp_route_dst(ctx.route, base_idx + static_cast<uint32_t>(mm) * E.f32_pitch + nb + c);
+                *reinterpret_cast<uint4*>(dst + ch8 * 8) = v4;
+              }
+            }
+          }
+          __syncwarp();
+        }
+      } else if (E.plain_f32 == 2 && bn >= 64) {
         // Store-only epilogue (weight gradients, dcat), coalesced: a thread owns a ROW of the accumulator, so storing
         // straight from registers makes every warp-level store touch 32 different 128-byte lines (two LSU wavefronts
         // per lane: the 780-tile wgrad launch was LSU-bound, ncu). Instead each warp transposes its 32x32 block through

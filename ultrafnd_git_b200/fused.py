@@ -83,6 +83,9 @@ class FusedStep:
         # default: measured on 8 GPUs the side-stream kernel slows the latency-bound forward chain as much as it saves
         # (321 vs 316 us/step), like the early push.
         self.dp_defer = os.environ.get("FND_DP_DEFER", "0") == "1"
+        # FND_DP_FUSED=1 (default; bf16 wire format only): the weight-gradient launch's epilogue stores every tile straight
+        # into its owner's staging slot over NVLink (no separate push kernel, the fp32 gradient never touches HBM).
+        self.dp_fused = os.environ.get("FND_DP_FUSED", "1") == "1"
         self._side_stream: Optional[torch.cuda.Stream] = None
         self._graphs: Dict[str, torch.cuda.CUDAGraph] = {}
         dev = self.engine.device
@@ -161,11 +164,12 @@ class FusedStep:
         if entry == "train_step_dp":      # forward + backward + the sharded peer-memory optimizer step
             flags = (1 if self.dp_overlap else 0) | (2 if self.dp_defer else 0)
             side = None
+            fused = 4 if (self.dp_fused and not self.dp_overlap) else 0
             if flags:
                 if self._side_stream is None:
                     self._side_stream = torch.cuda.Stream(self.engine.device)
                 side = self._side_stream.cuda_stream
-            check(lib.fnd_train_step_dp(h, ctypes.byref(inp), self.engine.stream_ptr(), side, flags), "fnd_train_step_dp")
+            check(lib.fnd_train_step_dp(h, ctypes.byref(inp), self.engine.stream_ptr(), side, flags | fused), "fnd_train_step_dp")
             return
         fn = {"train_step": lib.fnd_train_step, "train_fwd_bwd": lib.fnd_train_fwd_bwd, "eval_step": lib.fnd_eval_step}[entry]
         check(fn(h, ctypes.byref(inp), self.engine.stream_ptr()), "fnd_" + entry)
