@@ -23,7 +23,7 @@ from ultrafnd_git_b200.fused import FusedStep
 from ultrafnd_git_b200.modules import CrossModalTransformer, DeepTruthClassifier
 
 STEPS = 4
-B = 32
+B = int(os.environ.get("FND_DP_CHECK_BATCH", "32"))      # 32: small-batch fallback (un-fused push); 128: fused push active
 
 
 def build(precision, seed=7):

@@ -10,13 +10,15 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("precision", ["fp32", "bf16"])
-def test_dp_peer_matches_single_gpu(precision):
+@pytest.mark.parametrize("precision,batch", [("fp32", 32), ("bf16", 32), ("bf16", 128)])
+def test_dp_peer_matches_single_gpu(precision, batch):
+    """batch 128 in bf16 mode exercises the fused push (wgrad epilogue -> owners' staging slots); batch 32 the fallback."""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (run under gpurun --gpus 2)")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
            "--master-port", "29517", os.path.join(ROOT, "tests", "dp_peer_check.py"), precision]
-    r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600)
+    env = dict(os.environ, FND_DP_CHECK_BATCH=str(batch))
+    r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600, env=env)
     print(r.stdout[-3000:], r.stderr[-3000:])
     assert r.returncode == 0
 

@@ -828,8 +828,12 @@ static int train_fwd_bwd_impl(void* plan, const fnd_inputs* in, int fused_optimi
   const bool defer = side_stream != nullptr && P.dp_bound && (dp_flags & 2);
   // bit 2: fused push — the weight-gradient launch's epilogue stores each tile into its owner's staging slot (bf16 wire
   // format, merged-finalize light launch only; not combined with the early push)
-  const bool fused_push = P.dp_bound && (dp_flags & 4) && !overlap && P.dp.stage_bf16 && P.dp.world > 1 && !P.dp.mc_grads &&
-                          gemm_launch_is_light(P.wg_all.kind, P.wg_all.host.data(), static_cast<int>(P.wg_all.host.size()));
+  bool fused_push = P.dp_bound && (dp_flags & 4) && !overlap && P.dp.stage_bf16 && P.dp.world > 1 && !P.dp.mc_grads &&
+                    gemm_launch_is_light(P.wg_all.kind, P.wg_all.host.data(), static_cast<int>(P.wg_all.host.size()));
+  // every routed problem must take the staged store-only epilogue (its dead operand ring holds the 36 KB of staging;
+  // not the case for very small batches, whose k-loop is a single partial block)
+  for (const auto& g : P.wg_all.host)
+    if (g.epi.routed && !(g.epi.plain_f32 == 2 && g.bn >= 64)) fused_push = false;
   P.dp_fused_now = fused_push;
   if (P.dp_bound && (dp_flags || skip_norm)) {
     // A deferred update of the previous step: run it on the side stream under the first four kernels of this forward

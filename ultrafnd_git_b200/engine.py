@@ -373,6 +373,26 @@ class Engine:
                 if hi > lo:
                     dist.broadcast(self.params[lo:hi], src=dist.get_global_rank(s["group"], r), group=s["group"])
 
+    def gather_reduced_grads(self) -> torch.Tensor:
+        """The REDUCED gradient of the last data-parallel step as one [n_hot] fp32 tensor on every rank (test / bench
+        support: after fnd_train_step_dp each rank only holds the reduced values of its own slice, segments back to
+        back in ``symm["gred"]``)."""
+        import torch.distributed as dist
+        s = self.symm
+        if s is None:
+            raise RuntimeError("enable_symmetric() first")
+        out = torch.zeros(self.n_hot, dtype=torch.float32, device=self.device)
+        for r in range(s["world"]):
+            off = 0
+            for lo, hi in self.shard_ranges(r):
+                n = hi - lo
+                if n > 0:
+                    if r == s["rank"]:
+                        out[lo:hi].copy_(s["gred"][off:off + n])
+                    dist.broadcast(out[lo:hi], src=dist.get_global_rank(s["group"], r), group=s["group"])
+                off += n
+        return out
+
     def view(self, name: str) -> torch.Tensor:
         p = self.index[name]
         return self.params[p.offset: p.offset + p.numel].view(p.shape)
