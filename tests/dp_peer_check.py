@@ -111,7 +111,9 @@ def main():
         if precision == "fp32":
             ok = dl < tol and dn < 10 * tol and dpar < 0.05 * upd + 1e-7 and rel_l2 < 1e-3
         else:
-            ok = dl < tol and dn < 10 * tol and rel_l2 < 2e-2 and outliers < 1e-3
+            # floor of this metric in bf16 mode with an fp32 wire (no exchange rounding at all): rel-L2 1.6e-2, outliers 8e-4
+            # at batch 128 (profiles/r02_dp_wire_floor.txt); the bf16 wire adds ~1e-3 / ~5e-4 on top
+            ok = dl < tol and dn < 10 * tol and rel_l2 < 2e-2 and outliers < 3e-3
         print("DP PEER CHECK", "OK" if ok else "FAILED")
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.broadcast(flag, src=0)

@@ -169,8 +169,51 @@ def save_large(name, seed, batch, data_seed):
     print(f"wrote {path}: {os.path.getsize(path) / 1024:.1f} KiB, eval loss {float(rec['eval.loss']):.6f}")
 
 
+from tests.golden.gcn_common import gcn_inputs  # noqa: E402  (shared with the tests)
+
+
+def save_gcn(name, n, seed):
+    """the reference's OWN SimpleGCN / build_adj_from_ocr / pre-train loop (forensic_trainer.py:25-53,
+    113-132,184-224) on a synthetic post graph, dropout 0 so the result is deterministic (the reference draws its
+    dropout(0.2) masks from torch's CPU RNG, which no other implementation can replay). Inputs and initial weights are
+    regenerated from seeds by the test; only a strided sample of gnn_Z, its row norms and the adjacency degrees are stored."""
+    from src.training.forensic_trainer import SimpleGCN, build_adj_from_ocr
+    X, ocr = gcn_inputs(n, seed)
+    adj = build_adj_from_ocr(ocr, thresh=0.12)
+    torch.manual_seed(seed)
+    gnn = SimpleGCN(in_dim=416, hid=256, out_dim=128, dropout=0.0)
+    head = nn.Linear(128, 1)
+    init = {k: v.detach().clone() for k, v in list(gnn.state_dict().items())}
+    head_init = {k: v.detach().clone() for k, v in head.state_dict().items()}
+    Xt, At = torch.from_numpy(X), torch.from_numpy(adj)
+    opt = torch.optim.Adam(gnn.parameters(), lr=1e-3, weight_decay=1e-4)          # _pretrain_gnn, forensic_trainer.py:213-224
+    target = At.sum(dim=-1, keepdim=True) / max(1.0, At.shape[0])
+    losses = []
+    for _ in range(2):
+        gnn.train()
+        Z = gnn(Xt, At)
+        loss = F.mse_loss(torch.sigmoid(head(Z)), target)
+        opt.zero_grad(); loss.backward(); opt.step()
+        losses.append(float(loss))
+    with torch.no_grad():
+        Z = gnn(Xt, At)
+    out = {"n": np.array(n), "seed": np.array(seed), "degree": adj.sum(-1).astype(np.float32), "edges": np.array(adj.sum()),
+           "pretrain_losses": np.array(losses), "Z_rows": Z[::16].numpy(), "Z_row_norm": Z.norm(dim=1).numpy(),
+           "Z_fro": np.array(float(Z.double().norm()))}
+    for k, v in init.items():
+        out["init." + k] = v.numpy()
+    for k, v in head_init.items():
+        out["head." + k] = v.numpy()
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print(f"{name}: n={n} edges={int(adj.sum())} max degree={int(adj.sum(-1).max())} pretrain losses {losses} |Z|={float(Z.norm()):.4f}")
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
+    if len(sys.argv) > 1 and sys.argv[1] == "gcn":
+        save_gcn("gcn_n512", 512, 21)
+        save_gcn("gcn_n5504", 5504, 22)
+        sys.exit(0)
     save_case("eval_smoke_b4", seed=42, perturb=False, batch=4, dist="smoke")
     save_case("trained_cache_b16", seed=42, perturb=True, batch=16, dist="cache")
     save_case("train3_smoke_b8", seed=43, perturb=True, batch=8, dist="smoke", steps=3)

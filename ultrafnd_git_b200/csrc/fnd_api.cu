@@ -1077,7 +1077,7 @@ static int dp_tail(Plan& P, bool early_done, bool defer, cudaStream_t st) {
     const size_t r0 = static_cast<size_t>(P.L.at("clf.pre.0.weight"));
     // (with aux_dim == 0 pre.0.weight has 16-byte rows and is routed like every other GEMM weight: empty interval)
     const size_t r0e = P.d.aux_dim ? r0 + static_cast<size_t>(P.H) * (P.H + P.d.aux_dim) : r0;
-    FND_CUDA_OK(launch_k(dp_push_residual_kernel, 148, 256, 0, st, false, P.dp, r0, (r0e + 63) / 64 * 64,
+    FND_CUDA_OK(launch_k(dp_push_residual_kernel, 32, 256, 0, st, false, P.dp, r0, (r0e + 63) / 64 * 64,
                          static_cast<size_t>(P.L.n_shadow), static_cast<size_t>(P.L.n_hot)));
     mark(P, "dp_push_residual", st);
     FND_CUDA_OK(launch_k(dp_reduce_kernel<true>, kDpGrid, 256, 0, st, false, P.dp, 0, 1));

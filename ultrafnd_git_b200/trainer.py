@@ -30,6 +30,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .fused import DeviceCache, FusedStep, FEATURE_KEYS
+from .gcn import SimpleGCN, build_gnn_embeddings
 from .metrics import aggregate_epoch_metrics, pretty_print
 from .modules import CrossModalTransformer, DeepTruthClassifier, pair_modules
 
@@ -52,28 +53,6 @@ class TrainConfig:
     save_best: bool = True
     grad_clip: float = 5.0
     early_stop_patience: int = 3
-
-
-class SimpleGCN(nn.Module):
-    """Two-layer dense GCN (forensic_trainer.py:25-53): z = lin2(Â · drop(gelu(lin1(Â x)))), Â = D^-1/2 (A+I) D^-1/2.
-    Runs once at start-up to produce the constant ``gnn_Z`` table; plain torch on the GPU (not a hot-path kernel)."""
-
-    def __init__(self, in_dim: int, hid: int = 128, out_dim: int = 128, dropout: float = 0.3):
-        super().__init__()
-        self.lin1 = nn.Linear(in_dim, hid)
-        self.lin2 = nn.Linear(hid, out_dim)
-        self.drop = nn.Dropout(dropout)
-
-    @staticmethod
-    def normalise(adj: torch.Tensor) -> torch.Tensor:
-        a_hat = adj + torch.eye(adj.shape[0], device=adj.device, dtype=adj.dtype)
-        d = (a_hat.sum(-1) + 1e-9).pow(-0.5)
-        return d[:, None] * a_hat * d[None, :]
-
-    def forward(self, x: torch.Tensor, adj: torch.Tensor) -> torch.Tensor:
-        a = self.normalise(adj)
-        h = self.drop(F.gelu(self.lin1(a @ x)))
-        return self.lin2(a @ h)
 
 
 def build_adj_from_ocr(ocr_sets, thresh: float = 0.12) -> np.ndarray:
@@ -231,7 +210,9 @@ class ForensicTrainer:
     # ------------------------------------------------------------------ start-up stages (not the hot path)
     def _build_gnn(self) -> None:
         """forensic_trainer.py:184-224: compact node features, OCR-Jaccard graph, 2-epoch degree-regression pre-train,
-        then a constant embedding table."""
+        then a constant embedding table — on the library's tensor-core GEMM (gcn.py: one adjacency GEMM per Â·x, Â never
+        materialised; no cuBLAS). FND_GNN_Z_DROPOUT=1 reproduces the reference's quirk of leaving the GCN in train mode
+        (dropout 0.2 active) while the cached table is computed; the default computes it deterministically."""
         c, cfg = self.cache, self.cfg
         T, A, V, U = (np.asarray(c[k]) for k in ("text", "audio", "visual", "temporal"))
         X = np.concatenate([T[:, :192], A[:, :32], V[:, :128], U[:, :64]], axis=1).astype(np.float32)
@@ -240,17 +221,10 @@ class ForensicTrainer:
         self.X = torch.from_numpy(X).to(self.device)
         self.Adj = torch.from_numpy(adj).to(self.device)
         self.gnn = SimpleGCN(self.X.shape[1], hid=2 * cfg.gnn_dim, out_dim=cfg.gnn_dim, dropout=0.2).to(self.device)
-        if cfg.use_gnn:
-            opt = torch.optim.Adam(self.gnn.parameters(), lr=1e-3, weight_decay=1e-4)
-            target = self.Adj.sum(-1, keepdim=True) / max(1.0, self.Adj.shape[0])
-            head = nn.Linear(cfg.gnn_dim, 1, device=self.device)
-            for _ in range(2):
-                self.gnn.train()
-                loss = F.mse_loss(torch.sigmoid(head(self.gnn(self.X, self.Adj))), target)
-                opt.zero_grad(); loss.backward(); opt.step()
+        head = nn.Linear(cfg.gnn_dim, 1).to(self.device)          # constructed even when unused: same RNG consumption
+        self.cache["gnn_Z"] = build_gnn_embeddings(self.X, self.Adj, self.gnn, head, pretrain=bool(cfg.use_gnn), epochs=2,
+                                                   z_dropout=os.environ.get("FND_GNN_Z_DROPOUT", "0") == "1")
         self.gnn.eval()
-        with torch.no_grad():
-            self.cache["gnn_Z"] = self.gnn(self.X, self.Adj).detach()
 
     def _build_dataloaders(self):
         mk = lambda idx, shuf: torch.utils.data.DataLoader(CachedTensorDataset(self.cache, idx),
