@@ -287,6 +287,7 @@ class _ClassifierFn(torch.autograd.Function):
         logits = plan.buffer("logits", torch.float32, (B, 2)).clone()
         probs = plan.buffer("probs", torch.float32, (B, 2)).clone()
         ctx.module, ctx.plan, ctx.fid = module, plan, plan.clf_id
+        ctx.need_daux = bool(aux is not None and aux.requires_grad)
         ctx.mark_non_differentiable(probs)
         return logits, probs
 
@@ -300,10 +301,21 @@ class _ClassifierFn(torch.autograd.Function):
         dlogits = dlogits.to(torch.float32).contiguous()
         check(eng.lib.fnd_classifier_backward(plan.handle, dlogits.data_ptr(), eng.stream_ptr()), "fnd_classifier_backward")
         B = dlogits.shape[0]
-        dfused = plan.buffer("dfused", torch.float32, (B, eng.dims.hidden)).clone()
+        H = eng.dims.hidden
+        dfused = plan.buffer("dfused", torch.float32, (B, H)).clone()
+        daux = None
+        if ctx.need_daux:
+            # d loss / d aux = dz_pre0 . W_pre0[:, H:H+aux_dim] (deep_truth_classifier.py:142-146: aux is concatenated behind
+            # fused). dz_pre0 is the backward's own intermediate (bf16 hi [+ lo in fp32 mode]); two output columns, so a
+            # broadcast-multiply-reduce rather than a GEMM.
+            dz = plan.buffer("dz_p0_hi", torch.bfloat16, (B, H)).float()
+            if eng.mode == E.MODE_FP32X3:
+                dz = dz + plan.buffer("dz_p0_lo", torch.bfloat16, (B, H)).float()
+            w_aux = module.pre[0].weight.detach()[:, H:H + eng.dims.aux_dim]
+            daux = (dz[:, :, None] * w_aux[None, :, :]).sum(dim=1)
         flat = eng.grads.clone()
         grads = tuple(eng.grad_view(module._prefix + n, flat) for n in module._param_names)
-        return (None, dfused, None) + grads
+        return (None, dfused, daux) + grads
 
 
 class DeepTruthClassifier(_EngineModule):
@@ -367,14 +379,27 @@ class DeepTruthClassifier(_EngineModule):
                 raise RuntimeError(f"mat1 and mat2 shapes cannot be multiplied ({fused.shape[0]}x{self.hidden} and "
                                    f"{self.hidden + self.aux_dim}x{self.hidden}): aux is required when use_aux=True")
             aux = aux.to(eng.device, dtype=torch.float32)
-            if aux.requires_grad:
-                raise NotImplementedError("gradients w.r.t. aux are not produced by this drop-in")
         else:
             aux = None
         params = tuple(self.parameters())
         logits, probs = _ClassifierFn.apply(self, fused, aux, *params)
         t = torch.clamp(self.temperature.detach(), min=0.5, max=5.0)
         return {"logits": logits, "probs": probs, "temperature": t}
+
+    def feature_importance(self, fused: torch.Tensor, aux: Optional[torch.Tensor] = None, class_idx: int = 1,
+                           aggregate: bool = True) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+        """Gradient x Input importance (deep_truth_classifier.py:189-211): |d logits[:, class_idx].sum() / d x * x| with
+        x = [fused | aux]. Returns (per-input importance (B, F[+A]), its batch mean (F[+A],) when ``aggregate``). The input
+        gradients come from the library's own backward (``dfused`` crosses the C ABI; d/d aux from its dz_pre0)."""
+        dev = self._engine.device
+        fused = fused.detach().to(dev, dtype=torch.float32).requires_grad_(True)
+        aux = aux.detach().to(dev, dtype=torch.float32).requires_grad_(True) if (aux is not None and self.use_aux) else None
+        logits = self.forward(fused, aux)["logits"]
+        logits[:, class_idx].sum().backward()
+        x = torch.cat([fused, aux], dim=-1) if aux is not None else fused
+        grad = torch.cat([fused.grad, aux.grad], dim=-1) if aux is not None else fused.grad
+        imp = (grad.detach() * x.detach()).abs()
+        return (imp, imp.mean(dim=0)) if aggregate else (imp, None)
 
     @torch.no_grad()
     def predict_proba(self, fused: torch.Tensor, aux: Optional[torch.Tensor] = None) -> torch.Tensor:
