@@ -208,8 +208,58 @@ def save_gcn(name, n, seed):
     print(f"{name}: n={n} edges={int(adj.sum())} max degree={int(adj.sum(-1).max())} pretrain losses {losses} |Z|={float(Z.norm()):.4f}")
 
 
+def save_trainer_epochs(name, n=300, seed=9, batch_size=32, epochs=2):
+    """the reference's REAL ForensicTrainer (its __init__, _build_gnn, _forward_batch, _epoch_loop and
+    metrics code, forensic_trainer.py:139-330) on a synthetic feature cache. Only the out-of-scope data pipeline is
+    replaced (FakeSVRawDataset / build_gnn_cache_from_raw_dataset return the synthetic cache). Deterministic set-up:
+    weights from O.init_params(42) (+ perturbed NODE head), every dropout p = 0, and the train loader iterates in the
+    seeded per-epoch permutation the drop-in trainer uses (the reference's shuffle=True draws from the global CPU RNG).
+    Stored: the reference's gnn_Z table (it carries the reference's dropout draw, so the test injects it), per-epoch
+    train / val (loss, metrics) and the optimizer trajectory's final loss."""
+    import src.training.forensic_trainer as RT
+    from ultrafnd_git_b200.trainer import synthetic_cache
+    cache = synthetic_cache(n=n, seed=seed)
+    RT.FakeSVRawDataset = lambda root: None
+    RT.build_gnn_cache_from_raw_dataset = lambda raw, **kw: cache
+    outdir = "/tmp/fnd_golden_trainer"
+    cfg = RT.TrainConfig(data_root="unused", ocr_phrase_pkl=None, out_dir=outdir, batch_size=batch_size, epochs=epochs, lr=2e-4,
+                         weight_decay=1e-4, seed=42, use_mps=False, use_gnn=True, save_best=False)
+    tr = RT.ForensicTrainer(cfg)
+    fus_p, clf_p = O.init_params(42)
+    O.perturb_node_head(clf_p)
+    tr.fusion.load_state_dict(fus_p, strict=True)
+    tr.clf.load_state_dict(clf_p, strict=True)
+    for m in (tr.fusion, tr.clf, tr.gnn):
+        set_dropout(m, 0.0)
+    out = {"n": np.array(n), "seed": np.array(seed), "batch_size": np.array(batch_size), "gnn_Z": tr.cache["gnn_Z"].numpy()}
+    tr_ds = tr.train_loader.dataset
+    for ep in range(1, epochs + 1):
+        g = torch.Generator().manual_seed(cfg.seed * 7919 + ep)
+        order = torch.randperm(len(tr_ds), generator=g).tolist()
+        loader = torch.utils.data.DataLoader(tr_ds, batch_size=batch_size, sampler=order, drop_last=False)
+        tl, tm = tr._epoch_loop(loader, "train")
+        vl, vm = tr._epoch_loop(tr.val_loader, "val")
+        out[f"ep{ep}.train_loss"] = np.array(tl); out[f"ep{ep}.val_loss"] = np.array(vl)
+        for k, v in tm.items():
+            if np.isscalar(v):
+                out[f"ep{ep}.train.{k}"] = np.array(float(v))
+        for k, v in vm.items():
+            if np.isscalar(v):
+                out[f"ep{ep}.val.{k}"] = np.array(float(v))
+        print(f"{name}: epoch {ep} train loss {tl:.6f} val loss {vl:.6f} val auc {vm.get('auc')}")
+    tl, tm = tr._epoch_loop(tr.test_loader, "test")
+    out["test_loss"] = np.array(tl)
+    for k, v in tm.items():
+        if np.isscalar(v):
+            out[f"test.{k}"] = np.array(float(v))
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
+    if len(sys.argv) > 1 and sys.argv[1] == "trainer":
+        save_trainer_epochs("trainer_epochs_n300")
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "gcn":
         save_gcn("gcn_n512", 512, 21)
         save_gcn("gcn_n5504", 5504, 22)

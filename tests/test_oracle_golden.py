@@ -13,7 +13,7 @@ import torch
 from oracle import fnd_oracle as O
 
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
-CASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLD, "*.npz")) if not os.path.basename(p).startswith("gcn_"))
+CASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLD, "*.npz")) if not os.path.basename(p).startswith(("gcn_", "trainer_")))
 STRIDE = 997
 
 

@@ -142,3 +142,44 @@ def test_paired_modules_backward_matches_fused_step():
             worst = max(worst, err)
     assert abs(float(loss.detach()) - st.plan.state()["loss"]) < 1e-5
     assert worst < 1e-4, worst
+
+
+def test_epochs_match_reference_trainer():
+    """two training epochs + validation + test of the drop-in trainer against the REFERENCE's own
+    ForensicTrainer (its real __init__ / _forward_batch / _epoch_loop / metrics on the same synthetic cache; fixture
+    tests/golden/trainer_epochs_n300.npz from tests/golden/make_golden.py trainer): per-epoch mean-of-batch-means losses
+    and every scalar metric of aggregate_epoch_metrics. fp32 mode, dropout off, same per-epoch sample order, the
+    reference's gnn_Z table injected. Losses to 1e-3 relative (north_star fp32 tolerance); count-based metrics may move by
+    one borderline sample."""
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "trainer_epochs_n300.npz"))
+    from oracle import fnd_oracle as O
+    cache = synthetic_cache(n=int(g["n"]), seed=int(g["seed"]))
+    cache["gnn_Z"] = torch.from_numpy(g["gnn_Z"])
+    cfg = TrainConfig(data_root="unused", ocr_phrase_pkl=None, out_dir="/tmp/fnd_out_epochs", batch_size=int(g["batch_size"]),
+                      epochs=2, lr=2e-4, weight_decay=1e-4, seed=42, use_gnn=True, save_best=False)
+    tr = ForensicTrainer(cfg, cache=cache, precision="fp32")
+    fus_p, clf_p = O.init_params(42)
+    O.perturb_node_head(clf_p)
+    tr.fusion.load_state_dict(fus_p); tr.clf.load_state_dict(clf_p)
+    for m in list(tr.fusion.modules()) + list(tr.clf.modules()):
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+    tr.fusion._sync_dropout(); tr.clf._sync_dropout()
+    tr.engine.refresh_shadows(tr.engine.param_version())
+    for ep in (1, 2):
+        tr.epoch = ep
+        tl, tm = tr._epoch_loop(tr.train_loader, "train")
+        vl, vm = tr._epoch_loop(tr.val_loader, "val")
+        ref_t, ref_v = float(g[f"ep{ep}.train_loss"]), float(g[f"ep{ep}.val_loss"])
+        print(f"epoch {ep}: train loss {tl:.6f} (reference {ref_t:.6f}), val loss {vl:.6f} (reference {ref_v:.6f})")
+        assert abs(tl - ref_t) <= 1e-3 * ref_t and abs(vl - ref_v) <= 1e-3 * ref_v
+        for split, m in (("train", tm), ("val", vm)):
+            for k, v in m.items():
+                key = f"ep{ep}.{split}.{k}"
+                if key in g.files and np.isscalar(v):
+                    assert abs(float(v) - float(g[key])) <= 0.02 + 1e-3 * abs(float(g[key])), (key, v, float(g[key]))
+    sl, sm = tr._epoch_loop(tr.test_loader, "test")
+    assert abs(sl - float(g["test_loss"])) <= 1e-3 * float(g["test_loss"])
+    for k, v in sm.items():
+        if f"test.{k}" in g.files and np.isscalar(v):
+            assert abs(float(v) - float(g[f"test.{k}"])) <= 0.02 + 1e-3 * abs(float(g[f"test.{k}"]))
