@@ -37,10 +37,10 @@ int fnd_seq_linear(const void* a_bf16, int a_pitch, const void* w_bf16, int w_pi
                    const void* resid_bf16, int resid_pitch, int act, void* out_bf16, int out_pitch, float* out_f32,
                    int f32_pitch, int M, int N, int K, int* err_flag, void* stream);
 
-/* y = LayerNorm(x) over the last dimension (biased variance, eps inside the sqrt, affine gamma / beta in fp32).
- * d a multiple of 8, d <= 2048. */
-int fnd_seq_layernorm(const void* x_bf16, int x_pitch, const float* gamma, const float* beta, float eps, void* y_bf16,
-                      int y_pitch, int M, int d, void* stream);
+/* y = LayerNorm(x + resid) over the last dimension (resid may be NULL: plain LayerNorm; biased variance, eps inside the
+ * sqrt, affine gamma / beta in fp32). d a multiple of 8, d <= 2048. */
+int fnd_seq_layernorm(const void* x_bf16, int x_pitch, const void* resid_bf16, int resid_pitch, const float* gamma,
+                      const float* beta, float eps, void* y_bf16, int y_pitch, int M, int d, void* stream);
 
 /* Multi-head cross-attention forward, head dimension 64:
  *   out[b,q,h,:] = softmax_k(Q[b,q,h,:] . K[b,k,h,:] * scale + key_padding_mask[b,k]) V[b,k,h,:]

@@ -55,7 +55,9 @@ def main():
     ms = timeit(lambda: S.coattn_forward(qkv_t, qkv_f, qkv_f, B, H, Lt, Lf, 0, d, 2 * d, out=at, err=err)); rec("attn text<-frames", ms, 4.0 * B * Lt * Lf * d)
     ms = timeit(lambda: S.coattn_forward(qkv_f, qkv_t, qkv_t, B, H, Lf, Lt, 0, d, 2 * d, out=af, err=err)); rec("attn frames<-text", ms, 4.0 * B * Lt * Lf * d)
     ms = timeit(lambda: S.linear(at, wo, bo, resid=xt, out=yt, err=err)); rec("out_proj text +resid", ms, 2.0 * B * Lt * d * d)
+    ms = timeit(lambda: S.linear(at, wo, bo, out=yt, err=err)); rec("out_proj text (no resid)", ms, 2.0 * B * Lt * d * d)
     ms = timeit(lambda: S.layernorm(yt, ones, zeros, out=at)); rec("layernorm text", ms, 0.0, 4.0 * B * Lt * d)
+    ms = timeit(lambda: S.layernorm(yt, ones, zeros, out=at, resid=xt)); rec("layernorm text (x + resid)", ms, 0.0, 6.0 * B * Lt * d)
     ms = timeit(lambda: S.masked_mean_pool(at, B, Lt)); rec("pool text", ms, 0.0, 2.0 * B * Lt * d)
     xin = torch.randn(B * Lt, 768, device=dev, generator=g)
     ms = timeit(lambda: S.cast_bf16(xin)); rec("cast text fp32->bf16", ms, 0.0, 6.0 * B * Lt * 768)
@@ -78,7 +80,7 @@ def main():
     print(f"seq_probe B={B} Lt={Lt} Lf={Lf} d={d} heads={H}  err={int(err.item())}")
     for name, ms, tf, gbs in rows:
         print(f"  {name:44s} {ms * 1e3:9.1f} us  {tf:8.1f} TFLOP/s  {gbs:8.1f} GB/s")
-    tot = sum(r[1] for r in rows[:5]) + rows[4][1] * Lf / Lt + rows[5][1] * (1 + Lf / Lt)
+    tot = sum(r[1] for r in rows[:5]) + rows[4][1] * Lf / Lt + rows[6][1] * (1 + Lf / Lt)
     fl = B * 2.0 * (2.0 * (2.0 * Lt * d * d + 2.0 * Lf * d * d + 2.0 * Lt * Lf * d))
     print(f"  one bidirectional layer (sum of parts): {tot * 1e3:.1f} us, {fl / tot / 1e9:.1f} TFLOP/s")
 

@@ -153,7 +153,8 @@ def _signatures() -> Dict[str, tuple]:
         "fnd_seq_cast_bf16": (_c_int, [_c_void_p, _c_void_p, ll, _c_void_p]),
         "fnd_seq_linear": (_c_int, [_c_void_p, _c_int, _c_void_p, _c_int, _c_void_p, _c_void_p, _c_int, _c_int, _c_void_p, _c_int,
                                     _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_void_p, _c_void_p]),
-        "fnd_seq_layernorm": (_c_int, [_c_void_p, _c_int, _c_void_p, _c_void_p, _c_float, _c_void_p, _c_int, _c_int, _c_int, _c_void_p]),
+        "fnd_seq_layernorm": (_c_int, [_c_void_p, _c_int, _c_void_p, _c_int, _c_void_p, _c_void_p, _c_float, _c_void_p, _c_int, _c_int,
+                                       _c_int, _c_void_p]),
         "fnd_seq_coattn_forward": (_c_int, [_c_void_p, _c_int, _c_int, _c_void_p, _c_int, _c_int, _c_void_p, _c_int, _c_int,
                                             _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_float, _c_void_p, _c_int,
                                             _c_void_p, _c_void_p, _c_void_p]),

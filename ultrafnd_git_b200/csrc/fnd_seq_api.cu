@@ -108,17 +108,23 @@ int fnd_seq_linear(const void* a_bf16, int a_pitch, const void* w_bf16, int w_pi
   return 0;
 }
 
-int fnd_seq_layernorm(const void* x_bf16, int x_pitch, const float* gamma, const float* beta, float eps, void* y_bf16,
-                      int y_pitch, int M, int d, void* stream) {
+int fnd_seq_layernorm(const void* x_bf16, int x_pitch, const void* resid_bf16, int resid_pitch, const float* gamma,
+                      const float* beta, float eps, void* y_bf16, int y_pitch, int M, int d, void* stream) {
   if (!x_bf16 || !gamma || !beta || !y_bf16 || M <= 0 || d <= 0) return -1;
   if ((d & 7) || d > kLnMaxChunks * 256 || (x_pitch & 7) || (y_pitch & 7) || x_pitch < d || y_pitch < d) return -2;
+  if (resid_bf16 && ((resid_pitch & 7) || resid_pitch < d || !aligned16(resid_bf16))) return -2;
   if (!aligned16(x_bf16) || !aligned16(y_bf16) || !aligned16(gamma) || !aligned16(beta)) return -3;
-  LnParams P{static_cast<const __nv_bfloat16*>(x_bf16), x_pitch, gamma, beta, eps, static_cast<__nv_bfloat16*>(y_bf16), y_pitch, M, d};
+  LnParams P{static_cast<const __nv_bfloat16*>(x_bf16), x_pitch, static_cast<const __nv_bfloat16*>(resid_bf16), resid_pitch,
+             gamma, beta, eps, static_cast<__nv_bfloat16*>(y_bf16), y_pitch, M, d};
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (d <= 256) seq_layernorm_kernel<1><<<cdiv(M, 8), 256, 0, st>>>(P);
-  else if (d <= 512) seq_layernorm_kernel<2><<<cdiv(M, 8), 256, 0, st>>>(P);
-  else if (d <= 1024) seq_layernorm_kernel<4><<<cdiv(M, 8), 256, 0, st>>>(P);
-  else seq_layernorm_kernel<8><<<cdiv(M, 8), 256, 0, st>>>(P);
+  // resident warps walk the row list (gamma / beta stay in registers): a few waves of CTAs, never more than the rows need
+  const int want = cdiv(M, 8);
+  const int cap = seq_num_sms() * (d <= 512 ? 4 : 2);
+  const int grid = want < cap ? want : cap;
+  if (d <= 256) seq_layernorm_kernel<1><<<grid, 256, 0, st>>>(P);
+  else if (d <= 512) seq_layernorm_kernel<2><<<grid, 256, 0, st>>>(P);
+  else if (d <= 1024) seq_layernorm_kernel<4><<<grid, 256, 0, st>>>(P);
+  else seq_layernorm_kernel<8><<<grid, 256, 0, st>>>(P);
   SEQ_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -148,10 +154,10 @@ int fnd_seq_coattn_forward(const void* q_bf16, int q_pitch, int q_col0, const vo
   P.out = static_cast<__nv_bfloat16*>(out_bf16); P.out_pitch = out_pitch;
   P.lse = lse;
   P.err = err_flag;
-  // persistent: two resident CTAs per SM walk the (sample, head, query-tile) work list
+  // persistent: one resident CTA per SM walks the (sample, head, query-tile) work list
   const long long nwork = static_cast<long long>(cdiv(Lq, kAttnBQ)) * H * B;
   if (nwork > 0x7fffffffLL) return -3;
-  const int grid = nwork < 2LL * seq_num_sms() ? static_cast<int>(nwork) : 2 * seq_num_sms();
+  const int grid = nwork < 1LL * seq_num_sms() ? static_cast<int>(nwork) : seq_num_sms();
   P.dbg = g_attn_stamps;
   if (g_attn_stamps) seq_attn_fwd_kernel<true><<<grid, kAttnThreads, kAttnSmemBytes, reinterpret_cast<cudaStream_t>(stream)>>>(P);
   else seq_attn_fwd_kernel<false><<<grid, kAttnThreads, kAttnSmemBytes, reinterpret_cast<cudaStream_t>(stream)>>>(P);

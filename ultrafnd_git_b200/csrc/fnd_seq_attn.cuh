@@ -2,19 +2,20 @@
 //
 //   O[b, q, h, :] = softmax_k( Q[b,q,h,:] . K[b,k,h,:] * scale + key_padding_mask[b,k] ) V[b,k,h,:]       d_k = 64
 //
-// One CTA owns one (sample, head, 128-query tile) and walks the key/value sequence in blocks of 64:
+// One CTA owns one (sample, head, 128-query tile) at a time and walks the key/value sequence in blocks of 128:
 //   warp 0      TMA producer: Q tile once, then K_j / V_j tiles (SWIZZLE_128B, 3-D maps: rows past the sequence end of
 //               THIS sample are zero-filled) through a 3-stage ring
-//   warp 1      one elected thread issues tcgen05.mma:  S_j = Q K_j^T (128x64x64, into one of two TMEM S buffers — S_{j+1}
+//   warp 1      one elected thread issues tcgen05.mma:  S_j = Q K_j^T (128x128x64, into one of two TMEM S buffers — S_{j+1}
 //               is issued BEFORE P_j V_j so the tensor pipe works while the softmax warps are busy) and
-//               T_j = P_j V_j (128x64x64, P from shared memory, V MN-major, into one of two TMEM buffers)
-//   warps 2..9  softmax: two threads per query row (each owns half of the block's 64 key columns and half of the 64 output
+//               T_j = P_j V_j (128x64x128, P from shared memory, V MN-major, into one of two TMEM buffers)
+//   warps 2..9  softmax: two threads per query row (each owns half of the block's 128 key columns and half of the 64 output
 //               columns; the row maximum is exchanged through shared memory) — tcgen05.ld of the S row, key-padding mask,
 //               running max / sum (online softmax, exp2 with the scale folded in, packed f32x2 arithmetic), P_j as bf16
 //               into swizzled shared memory for the next MMA, O accumulated in REGISTERS (acc = acc * alpha_j + T_{j-1}:
 //               no TMEM read-modify-write correction pass)
-// TMEM: 2 x 64 (S) + 2 x 64 (T) = 256 columns and ~98 KB of shared memory per CTA -> two CTAs per SM, whose MMA / softmax
-// phases interleave on the SM. A query row with no valid key yields zeros (LSE = -inf).
+// 128-key blocks halve the issue groups and barrier rounds per key (the block cadence was set by the MMA-issuing warp and
+// by fixed synchronisation, profiles/r02_attn_phase_stamps.txt). TMEM: 2 x 128 (S) + 2 x 64 (T) columns, ~181 KB of
+// shared memory: one persistent CTA per SM. A query row with no valid key yields zeros (LSE = -inf).
 //
 // No counterpart in the reference (the reference's "co-attention" is a per-sample sigmoid gate,
 // src/models/fusion/cross_modal_transformer.py:39-55); checked against the self-oracle oracle/seq_oracle.py.
@@ -24,15 +25,15 @@
 namespace fnd {
 
 constexpr int kAttnBQ = 128;                 // query rows per CTA
-constexpr int kAttnBK = 64;                  // keys per block
+constexpr int kAttnBK = 128;                 // keys per block (two 64-key panels)
 constexpr int kAttnD = 64;                   // head dimension
 constexpr int kAttnStages = 3;
 constexpr int kAttnThreads = 320;             // warp 0 TMA, warp 1 MMA + TMEM owner, warps 2..9 softmax (two per TMEM lane quarter)
-constexpr int kAttnTmemCols = 256;
+constexpr int kAttnTmemCols = 512;           // S: 2 x 128 columns, T: 2 x 64 columns (power-of-two allocation)
 constexpr int kAttnQBytes = kAttnBQ * kAttnD * 2;        // 16 KB
-constexpr int kAttnPBytes = kAttnBQ * kAttnBK * 2;       // 16 KB
-constexpr int kAttnKBytes = kAttnBK * kAttnD * 2;        // 8 KB
-constexpr int kAttnSmemBytes = 1024 /*align*/ + 4096 /*barriers + row-statistics exchange*/ + kAttnQBytes + 2 * kAttnPBytes + kAttnStages * 2 * kAttnKBytes;
+constexpr int kAttnPBytes = kAttnBQ * kAttnBK * 2;       // 32 KB: two K-major panels of 128 rows x 64 keys
+constexpr int kAttnKBytes = kAttnBK * kAttnD * 2;        // 16 KB
+constexpr int kAttnSmemBytes = 1024 /*align*/ + 4096 /*barriers + row-statistics exchange*/ + 2 * kAttnQBytes + 2 * kAttnPBytes + kAttnStages * 2 * kAttnKBytes;
 
 struct alignas(64) AttnParams {
   CUtensorMap tmQ, tmK, tmV;                 // 3-D [batch][rows][cols] maps (fnd_tmap.h: encode_bf16_3d)
@@ -100,12 +101,12 @@ __device__ __forceinline__ float ex2_approx(float x) {
     }                                                        \
   } while (0)
 template <bool kDbg>
-__global__ void __launch_bounds__(kAttnThreads, 2) seq_attn_fwd_kernel(const __grid_constant__ AttnParams P) {
+__global__ void __launch_bounds__(kAttnThreads, 1) seq_attn_fwd_kernel(const __grid_constant__ AttnParams P) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* q_full = reinterpret_cast<uint64_t*>(smem);
-  uint64_t* q_empty = q_full + 1;
-  uint64_t* kv_full = q_empty + 1;
+  uint64_t* q_full = reinterpret_cast<uint64_t*>(smem);     // [2]: the Q tile is double-buffered (next item's tile is
+  uint64_t* q_empty = q_full + 2;                            //      prefetched a whole item ahead)
+  uint64_t* kv_full = q_empty + 2;
   uint64_t* kv_empty = kv_full + kAttnStages;
   uint64_t* s_full = kv_empty + kAttnStages;
   uint64_t* s_free = s_full + 2;
@@ -115,7 +116,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2) seq_attn_fwd_kernel(const __g
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_free + 2);
   float* xchg = reinterpret_cast<float*>(smem + 1024);       // [2 blocks][2 halves][128 rows] row maxima + [2][128] row sums
   uint8_t* sQ = smem + 4096;
-  uint8_t* sP = sQ + kAttnQBytes;
+  uint8_t* sP = sQ + 2 * kAttnQBytes;
   uint8_t* sKV = sP + 2 * kAttnPBytes;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -139,8 +140,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2) seq_attn_fwd_kernel(const __g
   }
   if (warp == 1) {
     if (lane == 0) {
-      mbar_init(q_full, 1);
-      mbar_init(q_empty, 1);
+      for (int i = 0; i < 2; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); }
       for (int s = 0; s < kAttnStages; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
       for (int i = 0; i < 2; ++i) {
         mbar_init(&s_full[i], 1);
@@ -172,11 +172,11 @@ __global__ void __launch_bounds__(kAttnThreads, 2) seq_attn_fwd_kernel(const __g
         const int nblk = item_nblk(w);
         if (nblk == 0) continue;
         const int qt = w % nqt, h = (w / nqt) % P.H, b = w / (nqt * P.H);
-        // the previous item's last S = Q K^T has retired before its Q tile is overwritten
-        ok = mbar_wait_fast(q_empty, (qn & 1u) ^ 1u, P.err, FND_DEV_TIMEOUT_PRODUCER);
+        // the last S = Q K^T of the item that used this Q buffer (two items ago) has retired before it is overwritten
+        ok = mbar_wait_fast(&q_empty[qn & 1u], ((qn >> 1) & 1u) ^ 1u, P.err, FND_DEV_TIMEOUT_PRODUCER);
         if (!ok) break;
-        mbar_arrive_expect_tx(q_full, kAttnQBytes);
-        tma_load_3d(sQ, &P.tmQ, q_full, P.q_col0 + h * kAttnD, qt * kAttnBQ, b, kEvictFirst);
+        mbar_arrive_expect_tx(&q_full[qn & 1u], kAttnQBytes);
+        tma_load_3d(sQ + (qn & 1u) * kAttnQBytes, &P.tmQ, &q_full[qn & 1u], P.q_col0 + h * kAttnD, qt * kAttnBQ, b, kEvictFirst);
         ++qn;
         const int kc = P.k_col0 + h * kAttnD, vc = P.v_col0 + h * kAttnD;
 #pragma unroll 1
@@ -206,7 +206,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2) seq_attn_fwd_kernel(const __g
     uint32_t gs = 0, gp = 0;                                               // blocks whose S / P V have been issued (global)
     int ss = 0; uint32_t sph = 0u;                                         // kv stage / parity of the S stream
     int ps = 0;                                                            // kv stage of the P V stream
-    uint32_t qn = 0;
+    uint32_t qn = 0, qcur = 0;                                             // items started by the S stream; Q buffer in use
     auto issue_s = [&](bool last_of_item) {
       ok = ok && mbar_wait_fast(&kv_full[ss], sph, P.err, FND_DEV_TIMEOUT_MMA);
       ok = ok && mbar_wait_fast(&s_free[gs & 1u], ((gs >> 1) & 1u) ^ 1u, P.err, FND_DEV_TIMEOUT_MMA);
@@ -216,24 +216,43 @@ __global__ void __launch_bounds__(kAttnThreads, 2) seq_attn_fwd_kernel(const __g
       if (ok && elect_one()) {
 #pragma unroll
         for (int k = 0; k < kAttnD / 16; ++k)
-          umma_f16(tS, desc64(q_lo + 2 * k, dhi), desc64(kl + 2 * k, dhi), idesc_s, k != 0 ? 1u : 0u);
+          umma_f16(tS, desc64(q_lo + qcur * (kAttnQBytes >> 4) + 2 * k, dhi), desc64(kl + 2 * k, dhi), idesc_s, k != 0 ? 1u : 0u);
         umma_commit(&s_full[gs & 1u]);
-        if (last_of_item) umma_commit(q_empty);                            // the Q tile may be replaced once this retires
+        if (last_of_item) umma_commit(&q_empty[qcur]);                     // this Q buffer may be refilled once this retires
       }
       __syncwarp();
       ++gs;
       if (++ss == kAttnStages) { ss = 0; sph ^= 1u; }
     };
+    // The S stream runs ONE BLOCK AHEAD of the P V stream, across item boundaries too: while the softmax warps work on the
+    // last block of an item, S of the next item's first block is already issued (its Q tile was requested when the last S
+    // of this item retired), so an item change costs no tensor-pipe bubble.
+    int ws = blockIdx.x, js = 0, ns = 0;                                   // S stream: item, block, blocks of that item
+    auto s_next_item = [&]() {                                             // advance to the next non-empty item (ns = 0: none left)
+      for (; ws < nwork; ws += gridDim.x) {
+        ns = item_nblk(ws);
+        if (ns > 0) return;
+      }
+      ns = 0;
+    };
+    auto s_step = [&]() {                                                  // issue S for (ws, js), advance the S stream
+      if (ns == 0) return;
+      if (js == 0) {
+        qcur = qn & 1u;
+        ok = ok && mbar_wait_fast(&q_full[qcur], (qn >> 1) & 1u, P.err, FND_DEV_TIMEOUT_MMA);
+        ++qn;
+      }
+      issue_s(js + 1 == ns);
+      if (++js == ns) { js = 0; ws += gridDim.x; s_next_item(); }
+    };
+    s_next_item();
+    s_step();
 #pragma unroll 1
     for (int w = blockIdx.x; w < nwork && ok; w += gridDim.x) {
       const int nblk = item_nblk(w);
-      if (nblk == 0) continue;
-      ok = mbar_wait_fast(q_full, qn & 1u, P.err, FND_DEV_TIMEOUT_MMA);
-      ++qn;
-      issue_s(nblk == 1);
 #pragma unroll 1
       for (int j = 0; j < nblk && ok; ++j) {
-        if (j + 1 < nblk) issue_s(j + 2 == nblk);                          // S runs one block ahead of P V
+        s_step();                                                          // S of the block after this one (same or next item)
         const uint32_t par = (gp >> 1) & 1u;
         ok = ok && mbar_wait_fast(&p_full[gp & 1u], par, P.err, FND_DEV_TIMEOUT_MMA);
         ok = ok && mbar_wait_fast(&o_free[gp & 1u], par ^ 1u, P.err, FND_DEV_TIMEOUT_MMA);
@@ -244,8 +263,8 @@ __global__ void __launch_bounds__(kAttnThreads, 2) seq_attn_fwd_kernel(const __g
         const uint32_t tO = tmem_base + 2 * kAttnBK + (gp & 1u) * kAttnD;
         if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < kAttnBK / 16; ++k)
-            umma_f16(tO, desc64(pl + 2 * k, dhi), desc64(vl + 128 * k, dhi), idesc_o, k != 0 ? 1u : 0u);
+          for (int k = 0; k < kAttnBK / 16; ++k)       // keys 0..63 from P panel 0, 64..127 from panel 1 (16 KB apart)
+            umma_f16(tO, desc64(pl + (k >> 2) * (kAttnPBytes >> 5) + 2 * (k & 3), dhi), desc64(vl + 128 * k, dhi), idesc_o, k != 0 ? 1u : 0u);
           umma_commit(&o_full[gp & 1u]);
           umma_commit(&kv_empty[ps]);
         }
@@ -285,11 +304,12 @@ __global__ void __launch_bounds__(kAttnThreads, 2) seq_attn_fwd_kernel(const __g
       for (int i = 0; i < 16; ++i) acc[i] = add_f32x2(acc[i], pack_u32x2(r[2 * i], r[2 * i + 1]));
     };
 
+    // (sample, head, query tile) of the current item, advanced incrementally (no integer divisions on the item path)
+    int qt = blockIdx.x % nqt, h = (blockIdx.x / nqt) % P.H, b = blockIdx.x / (nqt * P.H);
 #pragma unroll 1
     for (int w = blockIdx.x; w < nwork; w += gridDim.x) {
-      const int qt = w % nqt, h = (w / nqt) % P.H, b = w / (nqt * P.H);
       int kv_len = P.Lk;
-      if (P.kv_len) kv_len = min(max(P.kv_len[b], 0), P.Lk);
+      if (P.kv_len) kv_len = min(max(__ldg(P.kv_len + b), 0), P.Lk);
       const int nblk = (kv_len + kAttnBK - 1) / kAttnBK;
       const int qi = qt * kAttnBQ + row;
       const unsigned char* mrow = P.kv_mask ? P.kv_mask + static_cast<size_t>(b) * P.Lk : nullptr;
@@ -304,32 +324,45 @@ __global__ void __launch_bounds__(kAttnThreads, 2) seq_attn_fwd_kernel(const __g
         ok = ok && mbar_wait_fast(&s_full[g & 1u], (g >> 1) & 1u, P.err, FND_DEV_TIMEOUT_EPILOGUE);
         ATTN_STAMP(0);                             // wait for S
         tc_fence_after_sync();
-        uint32_t r[32];
-        tmem_ld_32x32(tmem_base + lane_addr + (g & 1u) * kAttnBK + half * 32, r);
-        tmem_ld_wait();
+        float s[64];
+        {
+          uint32_t r[32];
+          tmem_ld_32x32(tmem_base + lane_addr + (g & 1u) * kAttnBK + half * 64, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) s[i] = __uint_as_float(r[i]);
+          tmem_ld_32x32(tmem_base + lane_addr + (g & 1u) * kAttnBK + half * 64 + 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) s[32 + i] = __uint_as_float(r[i]);
+        }
         tc_fence_before_sync();
         __syncwarp();
         if (lane == 0) mbar_arrive(&s_free[g & 1u]);
         ATTN_STAMP(1);                             // TMEM load of S + release
-        float s[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) s[i] = __uint_as_float(r[i]);
 
-        // ---- key-padding mask of this thread's 32 columns as a validity word (warp-cooperative: one ballot) ----
-        const int k0 = j * kAttnBK + half * 32;
-        if (mrow || k0 + 32 > kv_len) {
-          const int kc = k0 + lane;
-          const uint32_t valid = __ballot_sync(0xffffffffu, kc < kv_len && (!mrow || mrow[kc] != 0));
-          if (valid != 0xffffffffu) {
+        // ---- key-padding mask of this thread's 64 columns as two validity words (warp-cooperative: two ballots) ----
+        const int k0 = j * kAttnBK + half * 64;
+        if (mrow || k0 + 64 > kv_len) {
+          const int ka = k0 + lane, kb = ka + 32;
+          const uint32_t va = __ballot_sync(0xffffffffu, ka < kv_len && (!mrow || mrow[ka] != 0));
+          const uint32_t vb = __ballot_sync(0xffffffffu, kb < kv_len && (!mrow || mrow[kb] != 0));
+          if ((va & vb) != 0xffffffffu) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) s[i] = ((valid >> i) & 1u) ? s[i] : -INFINITY;
+            for (int i = 0; i < 32; ++i) {
+              s[i] = ((va >> i) & 1u) ? s[i] : -INFINITY;
+              s[32 + i] = ((vb >> i) & 1u) ? s[32 + i] : -INFINITY;
+            }
           }
         }
-        // ---- row maximum: 3-input max tree over 32 columns, then the other half's maximum ----
+        // ---- row maximum: 3-input max tree over 64 columns (four independent chains), then the other half's maximum ----
         float m0 = fmax3(s[0], s[1], s[2]), m1 = fmax3(s[3], s[4], s[5]), m2 = fmax3(s[6], s[7], s[8]), m3 = fmax3(s[9], s[10], s[11]);
-        m0 = fmax3(m0, s[12], s[13]); m1 = fmax3(m1, s[14], s[15]); m2 = fmax3(m2, s[16], s[17]); m3 = fmax3(m3, s[18], s[19]);
-        m0 = fmax3(m0, s[20], s[21]); m1 = fmax3(m1, s[22], s[23]); m2 = fmax3(m2, s[24], s[25]); m3 = fmax3(m3, s[26], s[27]);
-        m0 = fmax3(m0, s[28], s[29]); m1 = fmax3(m1, s[30], s[31]);
+#pragma unroll
+        for (int i = 12; i < 60; i += 8) {
+          m0 = fmax3(m0, s[i], s[i + 1]); m1 = fmax3(m1, s[i + 2], s[i + 3]);
+          m2 = fmax3(m2, s[i + 4], s[i + 5]); m3 = fmax3(m3, s[i + 6], s[i + 7]);
+        }
+        m0 = fmax3(m0, s[60], s[61]); m1 = fmax3(m1, s[62], s[63]);
         float mx = fmaxf(fmax3(m0, m1, m2), m3);
         const uint32_t xc = xchg_s + (g & 1u) * 1024u + static_cast<uint32_t>(row * 4);
         sts_f32(xc + half * 512, mx);
@@ -342,10 +375,10 @@ __global__ void __launch_bounds__(kAttnThreads, 2) seq_attn_fwd_kernel(const __g
         const float alpha = ex2_approx(off_run - off);                        // off_run = -inf -> 0; unchanged maximum -> exactly 1
         off_run = off_new;
         const uint64_t noff = pack_f32x2(-off, -off);
-        uint32_t pk[16];
+        uint32_t pk[32];
         uint64_t ps0 = 0ull, ps1 = 0ull;
 #pragma unroll
-        for (int i = 0; i < 32; i += 4) {
+        for (int i = 0; i < 64; i += 4) {
           float x0, x1, x2, x3;
           unpack_f32x2(fma_f32x2(pack_f32x2(s[i], s[i + 1]), sl2, noff), x0, x1);
           unpack_f32x2(fma_f32x2(pack_f32x2(s[i + 2], s[i + 3]), sl2, noff), x2, x3);
@@ -361,13 +394,13 @@ __global__ void __launch_bounds__(kAttnThreads, 2) seq_attn_fwd_kernel(const __g
           l_part = fmaf(l_part, alpha, a0 + a1);
         }
         ATTN_STAMP(3);                             // exp2 + row sum + bf16 pack
-        // ---- P -> shared memory in the SWIZZLE_128B K-major layout the MMA descriptor expects:
-        //      row r at r*128 B, 16-byte chunk c stored at chunk (c ^ (r & 7)); this thread owns chunks half*4 .. half*4+3 ----
+        // ---- P -> shared memory in the SWIZZLE_128B K-major layout the MMA descriptor expects: this thread's 64 keys are
+        //      one full 128-byte row of panel `half`: row r at r*128 B, 16-byte chunk c stored at chunk (c ^ (r & 7)) ----
         {
-          const uint32_t prow = sP_s + (g & 1u) * kAttnPBytes + static_cast<uint32_t>(row * 128);
+          const uint32_t prow = sP_s + (g & 1u) * kAttnPBytes + static_cast<uint32_t>(half * (kAttnPBytes >> 1) + row * 128);
 #pragma unroll
-          for (int c = 0; c < 4; ++c)
-            sts_v4(prow + static_cast<uint32_t>(((half * 4 + c) ^ (row & 7)) << 4), pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+          for (int c = 0; c < 8; ++c)
+            sts_v4(prow + static_cast<uint32_t>((c ^ (row & 7)) << 4), pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
         }
         fence_proxy_async_smem();
         __syncwarp();
@@ -405,6 +438,11 @@ __global__ void __launch_bounds__(kAttnThreads, 2) seq_attn_fwd_kernel(const __g
         }
         if (P.lse && half == 0)
           P.lse[(static_cast<size_t>(b) * P.H + h) * P.Lq + qi] = (l_run > 0.f) ? fmaf(off_run, 0.69314718055994531f, __logf(l_run)) : -INFINITY;
+      }
+      qt += static_cast<int>(gridDim.x);
+      while (qt >= nqt) {
+        qt -= nqt;
+        if (++h == P.H) { h = 0; ++b; }
       }
     }
     if (kDbg && dbg_on) {

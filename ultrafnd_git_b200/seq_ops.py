@@ -76,15 +76,18 @@ def linear(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
 
 
 def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5,
-              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+              out: Optional[torch.Tensor] = None, resid: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """LayerNorm(x + resid) over the last dimension (resid optional)."""
     dev = _need_cuda(x)
     x2 = _as2d(x)
     M, d = x2.shape
     if out is None:
         out = torch.empty(x.shape, dtype=torch.bfloat16, device=dev)
     o2 = _as2d(out)
-    check(_lib.load().fnd_seq_layernorm(x2.data_ptr(), x2.stride(0), gamma.data_ptr(), beta.data_ptr(), float(eps),
-                                        o2.data_ptr(), o2.stride(0), M, d, _stream(dev)), "fnd_seq_layernorm")
+    r2 = _as2d(resid) if resid is not None else None
+    check(_lib.load().fnd_seq_layernorm(x2.data_ptr(), x2.stride(0), _ptr(r2), r2.stride(0) if r2 is not None else 0,
+                                        gamma.data_ptr(), beta.data_ptr(), float(eps), o2.data_ptr(), o2.stride(0), M, d,
+                                        _stream(dev)), "fnd_seq_layernorm")
     return out
 
 
