@@ -203,6 +203,14 @@ int fnd_gemm_bf16(const void* a_hi, const void* a_lo, int a_pitch, int a_mn, con
                   int b_pitch, int b_mn, float* c, int c_pitch, int M, int N, int K, int bn, int splits, int ncombo,
                   void* scratch, size_t scratch_bytes, void* stream);
 
+/* Stream-ordered variant (plain bf16 operands, ncombo = 1): no synchronisation, no host read-back; a device-side
+ * timeout is reported through `err_flag` (device int, optional — else the flag inside `scratch`). `scratch` must stay
+ * untouched until the launch has completed. Used for the weight-gradient GEMMs of the sequence front-end
+ * (dW[N,K] = dY[M,N]^T X[M,K]: a_mn = b_mn = 1, nothing is transposed in memory). */
+int fnd_gemm_bf16_async(const void* a_hi, int a_pitch, int a_mn, const void* b_hi, int b_pitch, int b_mn, float* c,
+                        int c_pitch, int M, int N, int K, int bn, int splits, void* scratch, size_t scratch_bytes,
+                        int* err_flag, void* stream);
+
 /* Probe variant: launches the kernel `reps` times back to back and, when `stamps` is non-NULL, has every CTA record
  * eight clock64() stamps into stamps[cta*8 + i] (0 start, 1 setup done, 2 first operands landed, 3 last MMA issued,
  * 4 accumulator ready, 5 split-K exchange done, 6 epilogue done, 7 all warps done). Used by tools/gemm_probe.py. */

@@ -58,12 +58,47 @@ int fnd_seq_coattn_forward(const void* q_bf16, int q_pitch, int q_col0, const vo
 int fnd_seq_masked_mean_pool(const void* x_bf16, int x_pitch, const unsigned char* mask, const int* len, int B, int L,
                              int d, float* out_f32, int f32_pitch, void* out_bf16, int bf_pitch, void* stream);
 
-/* Probe aid (tools/seq_probe.py): while `stamps` is non-NULL, fnd_seq_coattn_forward launches an instrumented build in
- * which one softmax thread per CTA accumulates clock64() cycles per phase of its key-block loop into
- * stamps[cta * 8 + phase] (0 wait for S, 1 TMEM load, 2 mask + row max, 3 exp2 + pack, 4 P store + fence, 5 previous
- * P V product, 6 rescale, 7 loop / item epilogue). `stamps` must hold 8 * 2 * (number of SMs) entries. NULL restores the
- * production kernel. Not for use around graph capture. */
+/* Reserved probe hook (round-2 phase-stamp builds of the attention kernel used it; profiles/r02_attn_phase_stamps.txt).
+ * The production kernel carries no instrumentation: the call is accepted and ignored. */
 int fnd_seq_debug_attn_stamps(long long* stamps);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Backward pass. Activation gradients travel as bf16 matrices, parameter gradients are fp32. Workspaces are caller-owned
+ * device buffers (16-byte aligned) of at least the size the matching *_workspace() query returns; nothing is allocated.
+ * ---------------------------------------------------------------------------------------------------------------- */
+
+/* Fused attention backward (head dimension 64). Given the forward's inputs, its output `o`, its logsumexp `lse`
+ * ([B, H, Lq], from fnd_seq_coattn_forward) and the output gradient `d_o` ([B*Lq, do_pitch], head h at columns 64 h):
+ *   P = exp(S * scale - lse),  dP = dO V^T,  dS = P o (dP - rowsum(dO o O)),
+ *   dq = scale * dS K,  dk = scale * dS^T Q,  dv = P^T dO        (masked keys / rows without a valid key: exact zeros)
+ * dq / dk / dv are written as bf16 at columns col0 + 64 h of their matrices ([B*Lq | B*Lk, pitch]; so a fused d[Q|K|V]
+ * buffer is filled in place). Three launches: a row prologue and two tcgen05 kernels (csrc/fnd_seq_attn_bwd.cuh);
+ * deterministic (no atomics). */
+size_t fnd_seq_coattn_backward_workspace(int B, int H, int Lq);
+int fnd_seq_coattn_backward(const void* q_bf16, int q_pitch, int q_col0, const void* k_bf16, int k_pitch, int k_col0,
+                            const void* v_bf16, int v_pitch, int v_col0, const void* o_bf16, int o_pitch,
+                            const void* do_bf16, int do_pitch, const float* lse, const int* kv_len,
+                            const unsigned char* kv_mask, int B, int H, int Lq, int Lk, float scale, void* dq_bf16,
+                            int dq_pitch, int dq_col0, void* dk_bf16, int dk_pitch, int dk_col0, void* dv_bf16,
+                            int dv_pitch, int dv_col0, void* workspace, size_t workspace_bytes, int* err_flag,
+                            void* stream);
+
+/* LayerNorm backward. t = the forward INPUT of the LayerNorm (x + resid already summed), dy = upstream gradient.
+ * dt (bf16) = gradient w.r.t. t; dgamma / dbeta (fp32 [d] each, ADJACENT: dbeta == dgamma + d) are overwritten.
+ * Partial sums are reduced in a fixed order (deterministic). */
+size_t fnd_seq_layernorm_backward_workspace(int M, int d);
+int fnd_seq_layernorm_backward(const void* t_bf16, int t_pitch, const void* dy_bf16, int dy_pitch, const float* gamma,
+                               float eps, void* dt_bf16, int dt_pitch, float* dgamma, float* dbeta, int M, int d,
+                               void* workspace, size_t workspace_bytes, void* stream);
+
+/* out[n] = sum_m x[m, n] (fp32; bias gradients). N a multiple of 8. Fixed-order reduction. */
+size_t fnd_seq_colsum_workspace(int M, int N);
+int fnd_seq_colsum(const void* x_bf16, int x_pitch, int M, int N, float* out, void* workspace, size_t workspace_bytes,
+                   void* stream);
+
+/* Backward of fnd_seq_masked_mean_pool: dx[b,l,:] = m[b,l] / max(sum_l m[b,l], 1e-6) * dpooled[b,:] (bf16). */
+int fnd_seq_masked_mean_pool_backward(const float* dpooled, int dp_pitch, const unsigned char* mask, const int* len, int B,
+                                      int L, int d, void* dx_bf16, int dx_pitch, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,125 @@
+"""GPU tests of the sequence front-end's BACKWARD kernels (Tier B) against torch autograd over the SELF-ORACLE
+oracle/seq_oracle.py.
+
+PARITY UNPINNED BY THE REFERENCE (the reference has no sequence attention / LayerNorm); the checker is
+autograd over the plain-PyTorch restatement, evaluated in fp32 on the same bf16-rounded inputs the kernels read.
+Tolerance (BASELINE.json north_star, bf16): rel-err <= 2e-2, written at each assert. All calls go through the C ABI
+(include/fnd_seq_b200.h) via ultrafnd_git_b200/seq_ops.py.
+"""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import seq_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+BF16_TOL = 2e-2
+
+
+def _rel(a, b):
+    return O.rel_err(a.detach().float().cpu(), b.detach().float().cpu())
+
+
+def _attn_case(B, H, Lq, Lk, seed, lens=None, scatter=False):
+    from ultrafnd_git_b200 import seq_ops as S
+    d = H * 64
+    g = torch.Generator().manual_seed(seed)
+    q = torch.randn(B, Lq, d, generator=g).bfloat16()
+    k = torch.randn(B, Lk, d, generator=g).bfloat16()
+    v = torch.randn(B, Lk, d, generator=g).bfloat16()
+    d_o = torch.randn(B, Lq, d, generator=g).bfloat16()
+    mask = torch.ones(B, Lk, dtype=torch.bool)
+    if lens is not None:
+        mask = torch.arange(Lk)[None, :] < torch.tensor(lens)[:, None]
+    if scatter:
+        mask[-1] &= torch.rand(Lk, generator=g) < 0.6
+        mask[-1, 0] = True
+    # checker: autograd over the restated attention, fp32, same bf16-rounded operands
+    qf, kf, vf = (t.float().requires_grad_(True) for t in (q, k, v))
+    o_ref, _ = O.attention_only(qf, kf, vf, mask, H)
+    o_ref.backward(d_o.float())
+    dev = torch.device("cuda")
+    err = S.new_err_flag(dev)
+    qc, kc, vc, doc = (t.cuda().view(-1, d) for t in (q, k, v, d_o))
+    mask_u8 = mask.to(torch.uint8).cuda().contiguous()
+    pos = torch.arange(1, Lk + 1, dtype=torch.int32)
+    kv_len = (mask.to(torch.int32) * pos).amax(dim=1).to(torch.int32).cuda()
+    lse = torch.empty(B, H, Lq, dtype=torch.float32, device=dev)
+    o = S.coattn_forward(qc, kc, vc, B, H, Lq, Lk, kv_len=kv_len, kv_mask=mask_u8, lse=lse, err=err)
+    dq = torch.full((B * Lq, d), float("nan"), dtype=torch.bfloat16, device=dev)
+    dk = torch.full((B * Lk, d), float("nan"), dtype=torch.bfloat16, device=dev)
+    dv = torch.full((B * Lk, d), float("nan"), dtype=torch.bfloat16, device=dev)
+    S.coattn_backward(qc, kc, vc, o, doc, lse, B, H, Lq, Lk, dq, dk, dv, kv_len=kv_len, kv_mask=mask_u8, err=err)
+    torch.cuda.synchronize()
+    assert int(err.item()) == 0
+    return (_rel(o.view(B, Lq, d), o_ref), _rel(dq.view(B, Lq, d), qf.grad), _rel(dk.view(B, Lk, d), kf.grad),
+            _rel(dv.view(B, Lk, d), vf.grad), dk.view(B, Lk, d), dv.view(B, Lk, d), mask)
+
+
+@pytest.mark.parametrize("B,H,Lq,Lk,lens,scatter", [
+    (2, 2, 100, 83, None, False),                  # single ragged tile on both sides
+    (3, 4, 300, 260, [260, 17, 0], True),          # several tiles, prefix lengths, an EMPTY key sequence, a scattered mask
+    (2, 3, 513, 700, [700, 129], False),           # tile / block remainders of one row
+    (2, 16, 1024, 512, None, False),               # the stress shape's tile counts
+])
+def test_coattn_backward_matches_autograd(B, H, Lq, Lk, lens, scatter):
+    eo, eq, ek, ev, dk, dv, mask = _attn_case(B, H, Lq, Lk, seed=B * 1000 + Lq + Lk, lens=lens, scatter=scatter)
+    print(f"attn bwd B={B} H={H} Lq={Lq} Lk={Lk}: O {eo:.2e} dQ {eq:.2e} dK {ek:.2e} dV {ev:.2e}")
+    assert eo < BF16_TOL and eq < BF16_TOL and ek < BF16_TOL and ev < BF16_TOL      # north_star bf16 tolerance 2e-2
+    # masked keys receive EXACT zeros (never NaN, never a stale buffer value)
+    dead = ~mask.cuda()
+    assert torch.all(dk[dead] == 0) and torch.all(dv[dead] == 0)
+    assert torch.isfinite(dk.float()).all() and torch.isfinite(dv.float()).all()
+
+
+def test_layernorm_backward_matches_autograd():
+    from ultrafnd_git_b200 import seq_ops as S
+    g = torch.Generator().manual_seed(3)
+    for M, d in ((50, 256), (1000, 1024), (7, 2048), (33, 64), (4099, 512)):
+        t = (torch.randn(M, d, generator=g) * 2 + 0.5).bfloat16()
+        dy = torch.randn(M, d, generator=g).bfloat16()
+        w = (1 + 0.1 * torch.randn(d, generator=g))
+        b = 0.1 * torch.randn(d, generator=g)
+        tf = t.float().requires_grad_(True)
+        wf, bf = w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+        F.layer_norm(tf, (d,), wf, bf, 1e-5).backward(dy.float())
+        dt, dg, db = S.layernorm_backward(t.cuda(), dy.cuda(), w.cuda(), 1e-5)
+        e = (_rel(dt, tf.grad), _rel(dg, wf.grad), _rel(db, bf.grad))
+        print(f"layernorm bwd M={M} d={d}: dt {e[0]:.2e} dgamma {e[1]:.2e} dbeta {e[2]:.2e}")
+        assert e[0] < 5e-3 and e[1] < 1e-4 and e[2] < 1e-4      # dt: one bf16 rounding; dgamma / dbeta: fp32 sums
+
+
+def test_pool_backward_colsum_wgrad():
+    from ultrafnd_git_b200 import seq_ops as S
+    g = torch.Generator().manual_seed(9)
+    B, L, d = 5, 83, 320
+    x = torch.randn(B, L, d, generator=g)
+    m = torch.rand(B, L, generator=g) < 0.7
+    m[2] = False                                    # a sample without any valid token: gradient 0 (clamp_min path)
+    dp = torch.randn(B, d, generator=g)
+    xf = x.clone().requires_grad_(True)
+    O.masked_mean(xf, m).backward(dp)
+    dx = S.masked_mean_pool_backward(dp.cuda(), B, L, mask=m.to(torch.uint8).cuda().contiguous())
+    e = _rel(dx.view(B, L, d), xf.grad)
+    print(f"pool bwd: {e:.2e}")
+    assert e < 5e-3                                 # bf16 output rounding
+    for M, N in ((1000, 1024), (37, 64), (20000, 3072)):
+        y = torch.randn(M, N, generator=g).bfloat16()
+        s = S.colsum(y.cuda())
+        e = _rel(s, y.float().sum(0))
+        print(f"colsum M={M} N={N}: {e:.2e}")
+        assert e < 1e-5
+    err = S.new_err_flag(torch.device("cuda"))
+    for M, N, K in ((4096, 1024, 1024), (512, 64, 128), (8192, 3072, 1024), (664, 512, 4096)):
+        dy = torch.randn(M, N, generator=g).bfloat16()
+        xx = torch.randn(M, K, generator=g).bfloat16()
+        dw = S.wgrad(dy.cuda(), xx.cuda(), err=err)
+        ref = dy.float().t() @ xx.float()
+        torch.cuda.synchronize()
+        assert int(err.item()) == 0
+        e = _rel(dw, ref)
+        print(f"wgrad M={M} N={N} K={K}: {e:.2e}")
+        assert e < 1e-4                             # same bf16 operands, fp32 accumulation

@@ -160,6 +160,21 @@ def _signatures() -> Dict[str, tuple]:
                                             _c_void_p, _c_void_p, _c_void_p]),
         "fnd_seq_masked_mean_pool": (_c_int, [_c_void_p, _c_int, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p, _c_int,
                                               _c_void_p, _c_int, _c_void_p]),
+        "fnd_seq_coattn_backward_workspace": (_c_size_t, [_c_int] * 3),
+        "fnd_seq_coattn_backward": (_c_int, [_c_void_p, _c_int, _c_int, _c_void_p, _c_int, _c_int, _c_void_p, _c_int, _c_int,
+                                             _c_void_p, _c_int, _c_void_p, _c_int, _c_void_p, _c_void_p, _c_void_p,
+                                             _c_int, _c_int, _c_int, _c_int, _c_float,
+                                             _c_void_p, _c_int, _c_int, _c_void_p, _c_int, _c_int, _c_void_p, _c_int, _c_int,
+                                             _c_void_p, _c_size_t, _c_void_p, _c_void_p]),
+        "fnd_seq_layernorm_backward_workspace": (_c_size_t, [_c_int] * 2),
+        "fnd_seq_layernorm_backward": (_c_int, [_c_void_p, _c_int, _c_void_p, _c_int, _c_void_p, _c_float, _c_void_p, _c_int,
+                                                _c_void_p, _c_void_p, _c_int, _c_int, _c_void_p, _c_size_t, _c_void_p]),
+        "fnd_seq_colsum_workspace": (_c_size_t, [_c_int] * 2),
+        "fnd_seq_colsum": (_c_int, [_c_void_p, _c_int, _c_int, _c_int, _c_void_p, _c_void_p, _c_size_t, _c_void_p]),
+        "fnd_seq_masked_mean_pool_backward": (_c_int, [_c_void_p, _c_int, _c_void_p, _c_void_p, _c_int, _c_int, _c_int,
+                                                       _c_void_p, _c_int, _c_void_p]),
+        "fnd_gemm_bf16_async": (_c_int, [_c_void_p, _c_int, _c_int, _c_void_p, _c_int, _c_int, _c_void_p, _c_int,
+                                         _c_int, _c_int, _c_int, _c_int, _c_int, _c_void_p, _c_size_t, _c_void_p, _c_void_p]),
         "fnd_gemm_scratch_bytes": (_c_size_t, [_c_int] * 4),
         "fnd_gemm_bf16_probe": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_void_p, _c_void_p, _c_int, _c_int,
                                          _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,

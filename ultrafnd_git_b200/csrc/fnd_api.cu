@@ -1190,7 +1190,15 @@ size_t fnd_gemm_scratch_bytes(int M, int N, int bn, int splits) {
 
 static int gemm_bf16_impl(const void* a_hi, const void* a_lo, int a_pitch, int a_mn, const void* b_hi, const void* b_lo,
                           int b_pitch, int b_mn, float* c, int c_pitch, int M, int N, int K, int bn, int splits, int ncombo,
-                          void* scratch, size_t scratch_bytes, void* stream, long long* stamps, int reps);
+                          void* scratch, size_t scratch_bytes, void* stream, long long* stamps, int reps, bool sync = true,
+                          int* user_err = nullptr);
+
+int fnd_gemm_bf16_async(const void* a_hi, int a_pitch, int a_mn, const void* b_hi, int b_pitch, int b_mn, float* c,
+                        int c_pitch, int M, int N, int K, int bn, int splits, void* scratch, size_t scratch_bytes,
+                        int* err_flag, void* stream) {
+  return gemm_bf16_impl(a_hi, nullptr, a_pitch, a_mn, b_hi, nullptr, b_pitch, b_mn, c, c_pitch, M, N, K, bn, splits, 1,
+                        scratch, scratch_bytes, stream, nullptr, 1, false, err_flag);
+}
 
 int fnd_gemm_bf16(const void* a_hi, const void* a_lo, int a_pitch, int a_mn, const void* b_hi, const void* b_lo,
                   int b_pitch, int b_mn, float* c, int c_pitch, int M, int N, int K, int bn, int splits, int ncombo,
@@ -1209,7 +1217,8 @@ int fnd_gemm_bf16_probe(const void* a_hi, const void* a_lo, int a_pitch, int a_m
 
 static int gemm_bf16_impl(const void* a_hi, const void* a_lo, int a_pitch, int a_mn, const void* b_hi, const void* b_lo,
                           int b_pitch, int b_mn, float* c, int c_pitch, int M, int N, int K, int bn, int splits, int ncombo,
-                          void* scratch, size_t scratch_bytes, void* stream, long long* stamps, int reps) {
+                          void* scratch, size_t scratch_bytes, void* stream, long long* stamps, int reps, bool sync,
+                          int* user_err) {
   if (!a_hi || !b_hi || !c || !scratch) return -1;
   if (scratch_bytes < fnd_gemm_scratch_bytes(M, N, bn, splits)) return -2;
   if ((reinterpret_cast<uintptr_t>(scratch) & 255) != 0) return -3;
@@ -1235,10 +1244,11 @@ static int gemm_bf16_impl(const void* a_hi, const void* a_lo, int a_pitch, int a
   const int grid = finish_table(&hp, 1);
   FND_CUDA_OK(init_gemm_attrs());
   FND_CUDA_OK(cudaMemsetAsync(derr, 0, 256 + ctr_bytes, st));
-  RunCtx ctx{derr, nullptr, 0, stamps};
+  RunCtx ctx{user_err ? user_err : derr, nullptr, 0, stamps};
   const int kind = (a_mn ? (b_mn ? 2 : 3) : (b_mn ? 1 : 0));
   (void)dtab;
   for (int r = 0; r < (reps < 1 ? 1 : reps); ++r) FND_CUDA_OK(launch_gemm(kind, &hp, 1, grid, ctx, st));
+  if (!sync) return 0;
   int herr = 0;
   FND_CUDA_OK(cudaMemcpyAsync(&herr, derr, sizeof(int), cudaMemcpyDeviceToHost, st));
   FND_CUDA_OK(cudaStreamSynchronize(st));

@@ -1,10 +1,13 @@
 // fnd_seq_api.cu — C-ABI of the sequence front-end (see include/fnd_seq_b200.h for the contract of every entry point).
 #include "../../include/fnd_seq_b200.h"
 #include "fnd_seq_attn.cuh"
+#include "fnd_seq_attn_bwd.cuh"
+#include "fnd_seq_bwd_rows.cuh"
 #include "fnd_seq_gemm.cuh"
 #include "fnd_seq_rows.cuh"
 #include "fnd_tmap.h"
 #include <math.h>
+#include <stdlib.h>
 
 using namespace fnd;
 
@@ -40,8 +43,16 @@ int fnd_seq_init(void) {
   static bool done = false;
   if (done) return 0;
   SEQ_CUDA_OK(cudaFuncSetAttribute(seq_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSeqGemmSmemMax));
-  SEQ_CUDA_OK(cudaFuncSetAttribute(seq_attn_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBytes));
-  SEQ_CUDA_OK(cudaFuncSetAttribute(seq_attn_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBytes));
+  SEQ_CUDA_OK(cudaFuncSetAttribute(seq_attn_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBytes));
+  SEQ_CUDA_OK(cudaFuncSetAttribute(seq_attn_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBytes));
+  SEQ_CUDA_OK(cudaFuncSetAttribute(seq_attn_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBytes));
+  SEQ_CUDA_OK(cudaFuncSetAttribute(seq_attn_fwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBytes));
+  SEQ_CUDA_OK(cudaFuncSetAttribute(seq_attn_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmemBytes));
+  SEQ_CUDA_OK(cudaFuncSetAttribute(seq_attn_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmemBytes));
+  SEQ_CUDA_OK(cudaFuncSetAttribute(seq_layernorm_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 2 * 256 * 4));
+  SEQ_CUDA_OK(cudaFuncSetAttribute(seq_layernorm_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 2 * 512 * 4));
+  SEQ_CUDA_OK(cudaFuncSetAttribute(seq_layernorm_bwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 2 * 1024 * 4));
+  SEQ_CUDA_OK(cudaFuncSetAttribute(seq_layernorm_bwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 2 * 2048 * 4));
   done = true;
   return 0;
 }
@@ -155,12 +166,23 @@ int fnd_seq_coattn_forward(const void* q_bf16, int q_pitch, int q_col0, const vo
   P.lse = lse;
   P.err = err_flag;
   // persistent: one resident CTA per SM walks the (sample, head, query-tile) work list
-  const long long nwork = static_cast<long long>(cdiv(Lq, kAttnBQ)) * H * B;
+  const long long nwork = static_cast<long long>(cdiv(Lq, kAttnItemQ)) * H * B;
   if (nwork > 0x7fffffffLL) return -3;
   const int grid = nwork < 1LL * seq_num_sms() ? static_cast<int>(nwork) : seq_num_sms();
-  P.dbg = g_attn_stamps;
-  if (g_attn_stamps) seq_attn_fwd_kernel<true><<<grid, kAttnThreads, kAttnSmemBytes, reinterpret_cast<cudaStream_t>(stream)>>>(P);
-  else seq_attn_fwd_kernel<false><<<grid, kAttnThreads, kAttnSmemBytes, reinterpret_cast<cudaStream_t>(stream)>>>(P);
+  // experiment knobs (tools/attn_probe.py sweeps them); the defaults are the measured best
+  int poly = kAttnDefaultPoly, skew = kAttnDefaultSkewNs;
+  if (const char* e = getenv("FND_ATTN_POLY")) { poly = atoi(e); if (poly < 0 || poly > 3) poly = kAttnDefaultPoly; }
+  if (const char* e = getenv("FND_ATTN_SKEW_NS")) { skew = atoi(e); if (skew < 0) skew = 0; }
+  P.skew_ns = skew;
+  P.pingpong = kAttnDefaultPingPong;
+  if (const char* e = getenv("FND_ATTN_PINGPONG")) P.pingpong = atoi(e) != 0;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  switch (poly) {
+    case 0: seq_attn_fwd_kernel<0><<<grid, kAttnThreads, kAttnSmemBytes, st>>>(P); break;
+    case 1: seq_attn_fwd_kernel<1><<<grid, kAttnThreads, kAttnSmemBytes, st>>>(P); break;
+    case 2: seq_attn_fwd_kernel<2><<<grid, kAttnThreads, kAttnSmemBytes, st>>>(P); break;
+    default: seq_attn_fwd_kernel<3><<<grid, kAttnThreads, kAttnSmemBytes, st>>>(P); break;
+  }
   SEQ_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -174,6 +196,161 @@ int fnd_seq_masked_mean_pool(const void* x_bf16, int x_pitch, const unsigned cha
   dim3 grid(static_cast<unsigned>(cdiv(d, 64)), static_cast<unsigned>(B));
   seq_masked_mean_pool_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(P);
   SEQ_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------- backward pass
+
+static int ln_bwd_grid(int M, int d) {
+  const int want = cdiv(M, 8);
+  const int cap = seq_num_sms() * (d <= 512 ? 2 : 1);
+  return want < cap ? want : cap;
+}
+
+size_t fnd_seq_layernorm_backward_workspace(int M, int d) {
+  if (M <= 0 || d <= 0) return 0;
+  return static_cast<size_t>(ln_bwd_grid(M, d)) * 2 * d * sizeof(float);
+}
+
+int fnd_seq_layernorm_backward(const void* t_bf16, int t_pitch, const void* dy_bf16, int dy_pitch, const float* gamma,
+                               float eps, void* dt_bf16, int dt_pitch, float* dgamma, float* dbeta, int M, int d,
+                               void* workspace, size_t workspace_bytes, void* stream) {
+  if (!t_bf16 || !dy_bf16 || !gamma || !dt_bf16 || !dgamma || !dbeta || !workspace || M <= 0 || d <= 0) return -1;
+  if ((d & 7) || d > kLnMaxChunks * 256 || (t_pitch & 7) || (dy_pitch & 7) || (dt_pitch & 7) || t_pitch < d || dy_pitch < d || dt_pitch < d) return -2;
+  if (!aligned16(t_bf16) || !aligned16(dy_bf16) || !aligned16(dt_bf16) || !aligned16(gamma) || !aligned16(workspace) || !aligned16(dgamma) || !aligned16(dbeta)) return -3;
+  if (dbeta != dgamma + d) return -3;             // the two gradients are reduced as ONE 2d-wide row: pass adjacent buffers
+  if (workspace_bytes < fnd_seq_layernorm_backward_workspace(M, d)) return -4;
+  { int r = fnd_seq_init(); if (r) return r; }
+  LnBwdParams P{static_cast<const __nv_bfloat16*>(t_bf16), t_pitch, static_cast<const __nv_bfloat16*>(dy_bf16), dy_pitch, gamma, eps,
+                static_cast<__nv_bfloat16*>(dt_bf16), dt_pitch, static_cast<float*>(workspace), M, d};
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int grid = ln_bwd_grid(M, d);
+  const size_t smem = static_cast<size_t>(8) * 2 * d * sizeof(float);
+  if (d <= 256) seq_layernorm_bwd_kernel<1><<<grid, 256, smem, st>>>(P);
+  else if (d <= 512) seq_layernorm_bwd_kernel<2><<<grid, 256, smem, st>>>(P);
+  else if (d <= 1024) seq_layernorm_bwd_kernel<4><<<grid, 256, smem, st>>>(P);
+  else seq_layernorm_bwd_kernel<8><<<grid, 256, smem, st>>>(P);
+  SEQ_CUDA_OK(cudaGetLastError());
+  seq_reduce_partials_kernel<<<cdiv(2 * d, 4 * 256), 256, 0, st>>>(static_cast<const float*>(workspace), grid, 2 * d, dgamma);
+  SEQ_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+static int colsum_slices(int M) {
+  const int want = cdiv(M, 64);
+  const int cap = seq_num_sms() * 2;
+  return want < cap ? want : cap;
+}
+
+size_t fnd_seq_colsum_workspace(int M, int N) {
+  if (M <= 0 || N <= 0) return 0;
+  return static_cast<size_t>(colsum_slices(M)) * N * sizeof(float);
+}
+
+int fnd_seq_colsum(const void* x_bf16, int x_pitch, int M, int N, float* out, void* workspace, size_t workspace_bytes,
+                   void* stream) {
+  if (!x_bf16 || !out || !workspace || M <= 0 || N <= 0) return -1;
+  if ((N & 7) || (x_pitch & 7) || x_pitch < N || !aligned16(x_bf16) || !aligned16(out) || !aligned16(workspace)) return -2;
+  if (workspace_bytes < fnd_seq_colsum_workspace(M, N)) return -4;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int slices = colsum_slices(M);
+  ColsumParams P{static_cast<const __nv_bfloat16*>(x_bf16), x_pitch, M, N, static_cast<float*>(workspace)};
+  dim3 grid(static_cast<unsigned>(cdiv(N, 256)), static_cast<unsigned>(slices));
+  seq_colsum_kernel<<<grid, 256, 0, st>>>(P);
+  SEQ_CUDA_OK(cudaGetLastError());
+  seq_reduce_partials_kernel<<<cdiv(N, 4 * 256), 256, 0, st>>>(static_cast<const float*>(workspace), slices, N, out);
+  SEQ_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int fnd_seq_masked_mean_pool_backward(const float* dpooled, int dp_pitch, const unsigned char* mask, const int* len, int B,
+                                      int L, int d, void* dx_bf16, int dx_pitch, void* stream) {
+  if (!dpooled || !dx_bf16 || B <= 0 || L <= 0 || d <= 0) return -1;
+  if ((d & 7) || (dx_pitch & 7) || dx_pitch < d || (dp_pitch & 3) || dp_pitch < d || !aligned16(dx_bf16) || !aligned16(dpooled)) return -2;
+  PoolBwdParams P{dpooled, dp_pitch, mask, len, B, L, d, static_cast<__nv_bfloat16*>(dx_bf16), dx_pitch};
+  const long long M = static_cast<long long>(B) * L;
+  const long long want = (M + 7) / 8;
+  const int cap = seq_num_sms() * 8;
+  const int grid = want < cap ? static_cast<int>(want) : cap;
+  seq_masked_mean_pool_bwd_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(P);
+  SEQ_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+size_t fnd_seq_coattn_backward_workspace(int B, int H, int Lq) {
+  if (B <= 0 || H <= 0 || Lq <= 0) return 0;
+  const size_t Lqp = static_cast<size_t>(cdiv(Lq, 64)) * 64;
+  return 2 * static_cast<size_t>(B) * H * Lqp * sizeof(float);
+}
+
+int fnd_seq_coattn_backward(const void* q_bf16, int q_pitch, int q_col0, const void* k_bf16, int k_pitch, int k_col0,
+                            const void* v_bf16, int v_pitch, int v_col0, const void* o_bf16, int o_pitch,
+                            const void* do_bf16, int do_pitch, const float* lse, const int* kv_len,
+                            const unsigned char* kv_mask, int B, int H, int Lq, int Lk, float scale, void* dq_bf16,
+                            int dq_pitch, int dq_col0, void* dk_bf16, int dk_pitch, int dk_col0, void* dv_bf16,
+                            int dv_pitch, int dv_col0, void* workspace, size_t workspace_bytes, int* err_flag,
+                            void* stream) {
+  if (!q_bf16 || !k_bf16 || !v_bf16 || !o_bf16 || !do_bf16 || !lse || !dq_bf16 || !dk_bf16 || !dv_bf16 || !workspace) return -1;
+  if (B <= 0 || H <= 0 || Lq <= 0 || Lk <= 0 || H > 65535 || B > 65535 || !(scale > 0.f)) return -1;
+  const int pitches[8] = {q_pitch, k_pitch, v_pitch, o_pitch, do_pitch, dq_pitch, dk_pitch, dv_pitch};
+  for (int i = 0; i < 8; ++i) if (pitches[i] & 7) return -2;
+  const int col0s[6] = {q_col0, k_col0, v_col0, dq_col0, dk_col0, dv_col0};
+  for (int i = 0; i < 6; ++i) if (col0s[i] & 7) return -2;
+  const int hd = H * kAttnD;
+  if (q_col0 + hd > q_pitch || k_col0 + hd > k_pitch || v_col0 + hd > v_pitch || hd > o_pitch || hd > do_pitch ||
+      dq_col0 + hd > dq_pitch || dk_col0 + hd > dk_pitch || dv_col0 + hd > dv_pitch) return -2;
+  if (!aligned16(dq_bf16) || !aligned16(dk_bf16) || !aligned16(dv_bf16) || !aligned16(o_bf16) || !aligned16(do_bf16) || !aligned16(workspace)) return -3;
+  if (workspace_bytes < fnd_seq_coattn_backward_workspace(B, H, Lq)) return -4;
+  { int r = fnd_seq_init(); if (r) return r; }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int Lqp = cdiv(Lq, 64) * 64;
+  float* Dp = static_cast<float*>(workspace);
+  float* lse2p = Dp + static_cast<size_t>(B) * H * Lqp;
+  {
+    AttnBwdPrepParams R{static_cast<const __nv_bfloat16*>(o_bf16), o_pitch, static_cast<const __nv_bfloat16*>(do_bf16), do_pitch, lse, B, H, Lq, Lqp, Dp, lse2p};
+    const long long rows = static_cast<long long>(B) * Lqp;
+    const long long want = (rows + 7) / 8;
+    const int cap = seq_num_sms() * 8;
+    seq_attn_bwd_prep_kernel<<<want < cap ? static_cast<int>(want) : cap, 256, 0, st>>>(R);
+    SEQ_CUDA_OK(cudaGetLastError());
+  }
+  const int sms = seq_num_sms();
+  AttnBwdParams P;
+  memset(&P, 0, sizeof(P));
+  P.B = B; P.H = H; P.Lq = Lq; P.Lk = Lk; P.Lqp = Lqp;
+  P.kv_len = kv_len; P.kv_mask = kv_mask;
+  P.scale = scale; P.scale_log2 = scale * 1.44269504088896340736f;
+  P.lse2p = lse2p; P.Dp = Dp;
+  P.err = err_flag;
+  int r;
+  // ---- dQ: resident Q / dO tiles (128 rows), streamed K / V blocks (64 rows) ----
+  if ((r = encode_bf16_3d(&P.tmR0, q_bf16, static_cast<uint64_t>(q_pitch), Lq, B, q_pitch, kAttnBQ))) return r;
+  if ((r = encode_bf16_3d(&P.tmR1, do_bf16, static_cast<uint64_t>(do_pitch), Lq, B, do_pitch, kAttnBQ))) return r;
+  if ((r = encode_bf16_3d(&P.tmS0, k_bf16, static_cast<uint64_t>(k_pitch), Lk, B, k_pitch, kBwdBlk))) return r;
+  if ((r = encode_bf16_3d(&P.tmS1, v_bf16, static_cast<uint64_t>(v_pitch), Lk, B, v_pitch, kBwdBlk))) return r;
+  P.r0_col0 = q_col0; P.r1_col0 = 0; P.s0_col0 = k_col0; P.s1_col0 = v_col0;
+  P.out0 = static_cast<__nv_bfloat16*>(dq_bf16); P.out0_pitch = dq_pitch; P.out0_col0 = dq_col0;
+  P.out1 = nullptr; P.out1_pitch = 0; P.out1_col0 = 0;
+  {
+    const long long nwork = static_cast<long long>(cdiv(Lq, kAttnItemQ)) * H * B;
+    if (nwork > 0x7fffffffLL) return -3;
+    seq_attn_bwd_kernel<false><<<nwork < sms ? static_cast<int>(nwork) : sms, kAttnThreads, kBwdSmemBytes, st>>>(P);
+    SEQ_CUDA_OK(cudaGetLastError());
+  }
+  // ---- dK / dV: resident K / V tiles, streamed Q / dO blocks ----
+  if ((r = encode_bf16_3d(&P.tmR0, k_bf16, static_cast<uint64_t>(k_pitch), Lk, B, k_pitch, kAttnBQ))) return r;
+  if ((r = encode_bf16_3d(&P.tmR1, v_bf16, static_cast<uint64_t>(v_pitch), Lk, B, v_pitch, kAttnBQ))) return r;
+  if ((r = encode_bf16_3d(&P.tmS0, q_bf16, static_cast<uint64_t>(q_pitch), Lq, B, q_pitch, kBwdBlk))) return r;
+  if ((r = encode_bf16_3d(&P.tmS1, do_bf16, static_cast<uint64_t>(do_pitch), Lq, B, do_pitch, kBwdBlk))) return r;
+  P.r0_col0 = k_col0; P.r1_col0 = v_col0; P.s0_col0 = q_col0; P.s1_col0 = 0;
+  P.out0 = static_cast<__nv_bfloat16*>(dk_bf16); P.out0_pitch = dk_pitch; P.out0_col0 = dk_col0;
+  P.out1 = static_cast<__nv_bfloat16*>(dv_bf16); P.out1_pitch = dv_pitch; P.out1_col0 = dv_col0;
+  {
+    const long long nwork = static_cast<long long>(cdiv(Lk, kAttnItemQ)) * H * B;
+    if (nwork > 0x7fffffffLL) return -3;
+    seq_attn_bwd_kernel<true><<<nwork < sms ? static_cast<int>(nwork) : sms, kAttnThreads, kBwdSmemBytes, st>>>(P);
+    SEQ_CUDA_OK(cudaGetLastError());
+  }
   return 0;
 }
 

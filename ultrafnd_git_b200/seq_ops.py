@@ -127,3 +127,96 @@ def masked_mean_pool(x: torch.Tensor, B: int, L: int, mask: Optional[torch.Tenso
     check(_lib.load().fnd_seq_masked_mean_pool(x2.data_ptr(), x2.stride(0), _ptr(mask), _ptr(length), B, L, d,
                                                out.data_ptr(), d, _ptr(obf), d, _stream(dev)), "fnd_seq_masked_mean_pool")
     return (out, obf) if want_bf16 else out
+
+
+# ----------------------------------------------------------------------------------------------------- backward pass
+def _workspace(nbytes: int, dev: torch.device) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=dev)
+
+
+def coattn_backward(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, o: torch.Tensor, d_o: torch.Tensor,
+                    lse: torch.Tensor, B: int, heads: int, Lq: int, Lk: int, dq: torch.Tensor, dk: torch.Tensor,
+                    dv: torch.Tensor, q_col0: int = 0, k_col0: int = 0, v_col0: int = 0, dq_col0: int = 0,
+                    dk_col0: int = 0, dv_col0: int = 0, kv_len: Optional[torch.Tensor] = None,
+                    kv_mask: Optional[torch.Tensor] = None, scale: Optional[float] = None,
+                    err: Optional[torch.Tensor] = None) -> None:
+    """Fused attention backward (fnd_seq_coattn_backward): fills dq / dk / dv (bf16, head h at col0 + 64 h) from the
+    forward's q / k / v / o / lse and the output gradient d_o."""
+    dev = _need_cuda(q, k, v, o, d_o, lse, dq, dk, dv)
+    q, k, v, o, d_o, dq, dk, dv = (_as2d(t) for t in (q, k, v, o, d_o, dq, dk, dv))
+    assert lse.dtype == torch.float32 and lse.is_contiguous() and lse.numel() == B * heads * Lq
+    if scale is None:
+        scale = 1.0 / math.sqrt(64.0)
+    lib = _lib.load()
+    ws = _workspace(lib.fnd_seq_coattn_backward_workspace(B, heads, Lq), dev)
+    check(lib.fnd_seq_coattn_backward(q.data_ptr(), q.stride(0), q_col0, k.data_ptr(), k.stride(0), k_col0, v.data_ptr(),
+                                      v.stride(0), v_col0, o.data_ptr(), o.stride(0), d_o.data_ptr(), d_o.stride(0),
+                                      lse.data_ptr(), _ptr(kv_len), _ptr(kv_mask), B, heads, Lq, Lk, float(scale),
+                                      dq.data_ptr(), dq.stride(0), dq_col0, dk.data_ptr(), dk.stride(0), dk_col0,
+                                      dv.data_ptr(), dv.stride(0), dv_col0, ws.data_ptr(), ws.numel(), _ptr(err),
+                                      _stream(dev)), "fnd_seq_coattn_backward")
+
+
+def layernorm_backward(t: torch.Tensor, dy: torch.Tensor, gamma: torch.Tensor, eps: float = 1e-5):
+    """Returns (dt bf16 [M, d], dgamma fp32 [d], dbeta fp32 [d]) for y = LayerNorm(t)."""
+    dev = _need_cuda(t, dy, gamma)
+    t2, dy2 = _as2d(t), _as2d(dy)
+    M, d = t2.shape
+    dt = torch.empty(M, d, dtype=torch.bfloat16, device=dev)
+    dgb = torch.empty(2, d, dtype=torch.float32, device=dev)
+    lib = _lib.load()
+    ws = _workspace(lib.fnd_seq_layernorm_backward_workspace(M, d), dev)
+    check(lib.fnd_seq_layernorm_backward(t2.data_ptr(), t2.stride(0), dy2.data_ptr(), dy2.stride(0), gamma.data_ptr(),
+                                         float(eps), dt.data_ptr(), d, dgb[0].data_ptr(), dgb[1].data_ptr(), M, d,
+                                         ws.data_ptr(), ws.numel(), _stream(dev)), "fnd_seq_layernorm_backward")
+    return dt, dgb[0], dgb[1]
+
+
+def colsum(x: torch.Tensor) -> torch.Tensor:
+    """fp32 column sums of a bf16 matrix (bias gradients)."""
+    dev = _need_cuda(x)
+    x2 = _as2d(x)
+    M, N = x2.shape
+    out = torch.empty(N, dtype=torch.float32, device=dev)
+    lib = _lib.load()
+    ws = _workspace(lib.fnd_seq_colsum_workspace(M, N), dev)
+    check(lib.fnd_seq_colsum(x2.data_ptr(), x2.stride(0), M, N, out.data_ptr(), ws.data_ptr(), ws.numel(), _stream(dev)),
+          "fnd_seq_colsum")
+    return out
+
+
+def masked_mean_pool_backward(dpooled: torch.Tensor, B: int, L: int, mask: Optional[torch.Tensor] = None,
+                              length: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """bf16 [B*L, d] gradient of the token states from the fp32 [B, d] gradient of the pooled vectors."""
+    dev = _need_cuda(dpooled)
+    dpooled = dpooled.contiguous().float()
+    d = dpooled.shape[1]
+    dx = torch.empty(B * L, d, dtype=torch.bfloat16, device=dev)
+    check(_lib.load().fnd_seq_masked_mean_pool_backward(dpooled.data_ptr(), d, _ptr(mask), _ptr(length), B, L, d,
+                                                        dx.data_ptr(), d, _stream(dev)), "fnd_seq_masked_mean_pool_backward")
+    return dx
+
+
+def wgrad(dy: torch.Tensor, x: torch.Tensor, err: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """dW[N, K] (fp32) = dy[M, N]^T @ x[M, K] on the tcgen05 GEMM (fnd_gemm_bf16_async: both operands are read in place with
+    the token dimension as the reduction — MN-major descriptors — so nothing is transposed in memory)."""
+    dev = _need_cuda(dy, x)
+    dy, x = _as2d(dy), _as2d(x)
+    M, N = dy.shape
+    K = x.shape[1]
+    assert x.shape[0] == M and dy.stride(1) == 1 and x.stride(1) == 1
+    if N % 64 or K % 64 or M % 8:
+        raise NotImplementedError("wgrad needs N, K multiples of 64 and M a multiple of 8 (pad the token dimension)")
+    lib = _lib.load()
+    bn = 128 if K % 128 == 0 else 64
+    tiles = ((N + 127) // 128) * (K // bn)
+    splits = 1
+    while tiles * splits * 2 <= 148 and M // (splits * 2) >= 1024:     # split the token reduction while every CTA stays co-resident
+        splits *= 2
+    out = torch.empty(N, K, dtype=torch.float32, device=dev)
+    nbytes = lib.fnd_gemm_scratch_bytes(N, K, bn, splits)
+    scratch = torch.zeros(nbytes + 256, dtype=torch.uint8, device=dev)
+    sp = (scratch.data_ptr() + 255) // 256 * 256
+    check(lib.fnd_gemm_bf16_async(dy.data_ptr(), dy.stride(0), 1, x.data_ptr(), x.stride(0), 1, out.data_ptr(), K,
+                                  N, K, M, bn, splits, sp, nbytes, _ptr(err), _stream(dev)), "fnd_gemm_bf16_async")
+    return out
