@@ -123,3 +123,52 @@ def test_pool_backward_colsum_wgrad():
         e = _rel(dw, ref)
         print(f"wgrad M={M} N={N} K={K}: {e:.2e}")
         assert e < 1e-4                             # same bf16 operands, fp32 accumulation
+
+
+def _frontend_grads(d_model, heads, lengths, batch, seed, full=False):
+    """(kernel grads, oracle grads, forward errors) of sum_s <y_s, w_s> for fixed random w_s."""
+    from ultrafnd_git_b200.seqfront import SequenceFrontEnd
+    streams, blocks = O.FAKESV_STREAMS, O.FAKESV_BLOCKS
+    p = O.init_params(streams, blocks, d_model, seed=seed)
+    data = O.make_batch(streams, lengths, batch, seed=seed + 1, full=full)
+    # the kernels read bf16 features and bf16 GEMM weights: hand the checker the same rounded values
+    for n in streams:
+        data[n] = data[n].bfloat16().float()
+    pr = {k: (v.bfloat16().float() if (k.endswith("weight") and v.dim() == 2) else v.clone()) for k, v in p.items()}
+    pr = {k: v.requires_grad_(True) for k, v in pr.items()}
+    g = torch.Generator().manual_seed(seed + 2)
+    w = {n: torch.randn(batch, streams[n][1], generator=g) for n in streams}
+    ref = O.forward(pr, data, streams, blocks, heads)
+    sum((ref[n] * w[n]).sum() for n in streams).backward()
+    fe = SequenceFrontEnd(d_model, heads, streams, blocks).cuda()
+    fe.load_state_dict({k: v for k, v in p.items()})
+    out = fe({k: v.cuda() for k, v in data.items()})
+    loss = sum((out[n] * w[n].cuda()).sum() for n in streams)
+    loss.backward()
+    torch.cuda.synchronize()
+    fe.check_error()
+    fwd = {n: _rel(out[n], ref[n]) for n in streams}
+    got = {k: v.grad for k, v in fe.named_parameters()}
+    return got, {k: v.grad for k, v in pr.items()}, fwd
+
+
+@pytest.mark.parametrize("d_model,heads,lengths,batch,full", [
+    (256, 4, {"text": 40, "frames": 83, "audio": 50, "c3d": 83}, 3, False),        # FakeSV-shaped, ragged, one scattered mask
+    (512, 8, {"text": 300, "frames": 83, "audio": 50, "c3d": 83}, 4, False),       # several query / key tiles
+    (128, 2, {"text": 130, "frames": 260, "audio": 64, "c3d": 16}, 2, True),       # full-length sequences
+])
+def test_frontend_backward_matches_oracle_autograd(d_model, heads, lengths, batch, full):
+    got, ref, fwd = _frontend_grads(d_model, heads, lengths, batch, seed=17 + d_model, full=full)
+    assert max(fwd.values()) < BF16_TOL
+    worst = ("", 0.0)
+    for k, gref in ref.items():
+        assert got[k] is not None, k
+        e = _rel(got[k], gref)
+        if e > worst[1]:
+            worst = (k, e)
+        assert torch.isfinite(got[k]).all(), k
+    errs = {k: _rel(got[k], ref[k]) for k in ref}
+    top = sorted(errs.items(), key=lambda kv: -kv[1])[:4]
+    print(f"front-end backward d={d_model}: worst parameter-gradient rel-err {worst[1]:.2e} ({worst[0]}); top: "
+          + ", ".join(f"{k} {v:.1e}" for k, v in top))
+    assert worst[1] < BF16_TOL                    # north_star bf16 tolerance 2e-2, every parameter gradient

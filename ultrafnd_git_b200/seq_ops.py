@@ -205,8 +205,8 @@ def wgrad(dy: torch.Tensor, x: torch.Tensor, err: Optional[torch.Tensor] = None)
     M, N = dy.shape
     K = x.shape[1]
     assert x.shape[0] == M and dy.stride(1) == 1 and x.stride(1) == 1
-    if N % 64 or K % 64 or M % 8:
-        raise NotImplementedError("wgrad needs N, K multiples of 64 and M a multiple of 8 (pad the token dimension)")
+    if N % 8 or K % 8:
+        raise NotImplementedError("wgrad needs N and K to be multiples of 8 (16-byte row pitches)")
     lib = _lib.load()
     bn = 128 if K % 128 == 0 else 64
     tiles = ((N + 127) // 128) * (K // bn)

@@ -13,8 +13,12 @@ carried over is the masked mean-pool, src/core_blocks/text_blocks.py:81-86.
     pool + head    : masked mean over valid tokens, Linear(d -> D_out) sized for CrossModalTransformer's inputs
 
 Parameter names equal oracle/seq_oracle.py's (``embed.<s>.*``, ``embed_ln.<s>.*``, ``blocks.<i>.<a|b>.{in_proj,out_proj,ln}.*``,
-``head.<s>.*``) so a state_dict moves between the two. Forward only (inference / feature extraction): the fused backward
-is not built yet, outputs carry no autograd graph. There is no CPU path: every op raises without CUDA.
+``head.<s>.*``) so a state_dict moves between the two. With gradients enabled the forward keeps its activations and the returned
+tensors carry ONE autograd node whose backward is the fused backward pass: attention backward (two tcgen05 kernels, P
+recomputed from the logsumexp), LayerNorm / pool backward row kernels, input-gradient GEMMs on the same persistent GEMM
+(transposed bf16 weight copies), weight-gradient GEMMs on the library GEMM with both operands read token-major in
+place, bias gradients as fixed-order column sums. Parameter gradients are fp32, activation gradients bf16; the input
+features receive no gradient (they are extracted offline). There is no CPU path: every op raises without CUDA.
 """
 from __future__ import annotations
 
@@ -70,6 +74,8 @@ class SequenceFrontEnd(nn.Module):
         self.blocks = nn.ModuleList([_CoBlock(d_model) for _ in self.block_pairs])
         self.head = nn.ModuleDict({n: nn.Linear(d_model, s[1]) for n, s in self.streams.items()})
         self._shadow: Dict[str, torch.Tensor] = {}
+        self._shadow_t: Dict[str, torch.Tensor] = {}
+        self._last_states: Dict[str, torch.Tensor] = {}
         self._shadow_version = None
         self._err: Optional[torch.Tensor] = None
 
@@ -83,8 +89,19 @@ class SequenceFrontEnd(nn.Module):
         if v != self._shadow_version:
             self._shadow = {k: p.detach().to(torch.bfloat16).contiguous() for k, p in self.named_parameters()
                             if k.endswith("weight") and p.dim() == 2}
+            self._shadow_t = {}
             self._shadow_version = v
         return self._shadow
+
+    def _weight_t(self, name: str) -> torch.Tensor:
+        """bf16 W^T ([in, out], row-major) of a GEMM weight: the input-gradient GEMM dX = dY W is then the same K-major
+        persistent GEMM as the forward. Built lazily (only a training step needs it), refreshed with the shadows."""
+        W = self._weights()
+        t = self._shadow_t.get(name)
+        if t is None:
+            t = W[name].t().contiguous()
+            self._shadow_t[name] = t
+        return t
 
     def check_error(self) -> None:
         if self._err is not None:
@@ -94,10 +111,22 @@ class SequenceFrontEnd(nn.Module):
                 raise RuntimeError(f"sequence front-end kernel reported device-side error code {code}")
 
     # ------------------------------------------------------------------ forward
-    @torch.no_grad()
     def forward(self, batch: Dict[str, torch.Tensor], return_states: bool = False) -> Dict[str, torch.Tensor]:
         """batch[name]: (B, L, D_in) fp32 or bf16; batch[name + "_mask"]: (B, L) bool, True = valid token (optional).
-        Returns {name: (B, D_out) fp32} (+ "pooled.<name>" / "state.<name>" with return_states)."""
+        Returns {name: (B, D_out) fp32} (+ "pooled.<name>" / "state.<name>" with return_states). When gradients are
+        enabled and a parameter requires them, the head outputs carry the fused backward (states / pooled never do)."""
+        params = [p for p in self.parameters()]
+        if torch.is_grad_enabled() and any(p.requires_grad for p in params):
+            names = list(self.streams)
+            ys = _SeqFrontFn.apply(self, batch, *params)
+            out = {n: y for n, y in zip(names, ys)}
+            if return_states:
+                out.update(self._last_states)
+            return out
+        with torch.no_grad():
+            return self._forward_impl(batch, return_states, None)
+
+    def _forward_impl(self, batch: Dict[str, torch.Tensor], return_states: bool, saved: Optional[dict]) -> Dict[str, torch.Tensor]:
         first = next(iter(self.streams))
         dev = batch[first].device
         if dev.type != "cuda":
@@ -128,17 +157,24 @@ class SequenceFrontEnd(nn.Module):
             xb = x.contiguous() if x.dtype == torch.bfloat16 else S.cast_bf16(x.to(torch.float32))
             y = S.linear(xb.view(B * L, -1), W[f"embed.{name}.weight"], self.embed[name].bias, err=err)
             X[name] = S.layernorm(y, self.embed_ln[name].weight, self.embed_ln[name].bias, self.eps)
+            if saved is not None:
+                saved[f"x.{name}"], saved[f"pre.{name}"] = xb.view(B * L, -1), y
         for i, (a, b) in enumerate(self.block_pairs):
             blk = self.blocks[i]
             (Ba, La), (Bb, Lb) = shape[a], shape[b]
             qkv_a = S.linear(X[a], W[f"blocks.{i}.a.in_proj.weight"], blk.a.in_proj.bias, err=err)      # [B*La, 3d]
             qkv_b = S.linear(X[b], W[f"blocks.{i}.b.in_proj.weight"], blk.b.in_proj.bias, err=err)
+            lse_a = torch.empty(Ba, H, La, dtype=torch.float32, device=dev) if saved is not None else None
+            lse_b = torch.empty(Bb, H, Lb, dtype=torch.float32, device=dev) if saved is not None else None
             att_a = S.coattn_forward(qkv_a, qkv_b, qkv_b, Ba, H, La, Lb, q_col0=0, k_col0=d, v_col0=2 * d,
-                                     kv_len=length[b], kv_mask=mask_u8[b], err=err)
+                                     kv_len=length[b], kv_mask=mask_u8[b], lse=lse_a, err=err)
             att_b = S.coattn_forward(qkv_b, qkv_a, qkv_a, Bb, H, Lb, La, q_col0=0, k_col0=d, v_col0=2 * d,
-                                     kv_len=length[a], kv_mask=mask_u8[a], err=err)
+                                     kv_len=length[a], kv_mask=mask_u8[a], lse=lse_b, err=err)
             ya = S.linear(att_a, W[f"blocks.{i}.a.out_proj.weight"], blk.a.out_proj.bias, resid=X[a], err=err)
             yb = S.linear(att_b, W[f"blocks.{i}.b.out_proj.weight"], blk.b.out_proj.bias, resid=X[b], err=err)
+            if saved is not None:
+                saved[f"blk.{i}"] = dict(xa=X[a], xb=X[b], qkv_a=qkv_a, qkv_b=qkv_b, att_a=att_a, att_b=att_b,
+                                         lse_a=lse_a, lse_b=lse_b, ya=ya, yb=yb)
             X[a] = S.layernorm(ya, blk.a.ln.weight, blk.a.ln.bias, self.eps)
             X[b] = S.layernorm(yb, blk.b.ln.weight, blk.b.ln.bias, self.eps)
         out: Dict[str, torch.Tensor] = {}
@@ -148,12 +184,71 @@ class SequenceFrontEnd(nn.Module):
             y = torch.empty(B, dout, dtype=torch.float32, device=dev)
             S.linear(pooled_bf, W[f"head.{name}.weight"], self.head[name].bias, out_f32=y, want_bf16=False, err=err)
             out[name] = y
+            if saved is not None:
+                saved[f"pooled.{name}"] = pooled_bf
             if return_states:
                 out["pooled." + name] = pooled
                 out["state." + name] = X[name].view(B, L, d)
+        if saved is not None:
+            saved["shape"], saved["mask_u8"], saved["length"] = shape, mask_u8, length
         return out
 
-    @torch.no_grad()
+    # ------------------------------------------------------------------ backward (called by _SeqFrontFn)
+    def _backward_impl(self, saved: dict, douts: Dict[str, Optional[torch.Tensor]]) -> Dict[str, torch.Tensor]:
+        """Parameter gradients (fp32, keyed like named_parameters()) from the gradients of the head outputs."""
+        err = self._err
+        d, H = self.d_model, self.heads
+        shape, mask_u8, length = saved["shape"], saved["mask_u8"], saved["length"]
+        dev = self._err.device
+        grads: Dict[str, torch.Tensor] = {}
+        dX: Dict[str, torch.Tensor] = {}
+        bf = torch.bfloat16
+        for name, (_din, dout, _key) in self.streams.items():
+            B, L = shape[name]
+            dy = douts.get(name)
+            if dy is None:
+                dy = torch.zeros(B, dout, dtype=torch.float32, device=dev)
+            dyb = S.cast_bf16(dy.contiguous().float()) if (B * dout) % 8 == 0 else dy.to(bf).contiguous()
+            grads[f"head.{name}.weight"] = S.wgrad(dyb, saved[f"pooled.{name}"], err=err)
+            grads[f"head.{name}.bias"] = S.colsum(dyb)
+            dpooled = torch.empty(B, d, dtype=torch.float32, device=dev)
+            S.linear(dyb, self._weight_t(f"head.{name}.weight"), None, out_f32=dpooled, want_bf16=False, err=err)
+            dX[name] = S.masked_mean_pool_backward(dpooled, B, L, mask=mask_u8[name], length=length[name])
+        for i in reversed(range(len(self.block_pairs))):
+            a, b = self.block_pairs[i]
+            blk, sv = self.blocks[i], saved[f"blk.{i}"]
+            (Ba, La), (Bb, Lb) = shape[a], shape[b]
+            dy_side, datt = {}, {}
+            for side, st, mod in (("a", a, blk.a), ("b", b, blk.b)):
+                pre = f"blocks.{i}.{side}"
+                dyv, dg, db = S.layernorm_backward(sv["y" + side], dX[st], mod.ln.weight, self.eps)
+                grads[pre + ".ln.weight"], grads[pre + ".ln.bias"] = dg, db
+                grads[pre + ".out_proj.bias"] = S.colsum(dyv)
+                grads[pre + ".out_proj.weight"] = S.wgrad(dyv, sv["att_" + side], err=err)
+                datt[side] = S.linear(dyv, self._weight_t(pre + ".out_proj.weight"), None, err=err)
+                dy_side[side] = dyv
+            dqkv_a = torch.empty(Ba * La, 3 * d, dtype=bf, device=dev)
+            dqkv_b = torch.empty(Bb * Lb, 3 * d, dtype=bf, device=dev)
+            # direction a <- b: queries from a's in_proj, keys / values from b's; and the reverse
+            S.coattn_backward(sv["qkv_a"], sv["qkv_b"], sv["qkv_b"], sv["att_a"], datt["a"], sv["lse_a"], Ba, H, La, Lb,
+                              dqkv_a, dqkv_b, dqkv_b, q_col0=0, k_col0=d, v_col0=2 * d, dq_col0=0, dk_col0=d, dv_col0=2 * d,
+                              kv_len=length[b], kv_mask=mask_u8[b], err=err)
+            S.coattn_backward(sv["qkv_b"], sv["qkv_a"], sv["qkv_a"], sv["att_b"], datt["b"], sv["lse_b"], Bb, H, Lb, La,
+                              dqkv_b, dqkv_a, dqkv_a, q_col0=0, k_col0=d, v_col0=2 * d, dq_col0=0, dk_col0=d, dv_col0=2 * d,
+                              kv_len=length[a], kv_mask=mask_u8[a], err=err)
+            for side, st, dq in (("a", a, dqkv_a), ("b", b, dqkv_b)):
+                pre = f"blocks.{i}.{side}"
+                grads[pre + ".in_proj.bias"] = S.colsum(dq)
+                grads[pre + ".in_proj.weight"] = S.wgrad(dq, sv["x" + side], err=err)
+                # dX = d[QKV] W_in + (residual branch: the LayerNorm input gradient)
+                dX[st] = S.linear(dq, self._weight_t(pre + ".in_proj.weight"), None, resid=dy_side[side], err=err)
+        for name in self.streams:
+            dpre, dg, db = S.layernorm_backward(saved[f"pre.{name}"], dX[name], self.embed_ln[name].weight, self.eps)
+            grads[f"embed_ln.{name}.weight"], grads[f"embed_ln.{name}.bias"] = dg, db
+            grads[f"embed.{name}.bias"] = S.colsum(dpre)
+            grads[f"embed.{name}.weight"] = S.wgrad(dpre, saved[f"x.{name}"], err=err)
+        return grads
+
     def forward_features(self, feats: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
         """Tier-A keyed view: ``feats[<feature key>]`` is a (B, L, D_in) sequence (+ optional ``<feature key>_mask``);
         returns the dict CrossModalTransformer.forward expects (2-D vectors under the same keys; other entries such as
@@ -179,3 +274,28 @@ class SequenceFrontEnd(nn.Module):
             La, Lb = lengths[a], lengths[b]
             f += batch * 2.0 * (2.0 * (2.0 * La * d * d + 2.0 * Lb * d * d + 2.0 * La * Lb * d))
         return f
+
+
+class _SeqFrontFn(torch.autograd.Function):
+    """One autograd node for the whole front-end: forward = the fused forward with activations kept, backward = the fused
+    backward (SequenceFrontEnd._backward_impl). Inputs after ``batch`` are the module's parameters in parameters() order so
+    that autograd routes the returned gradients into their ``.grad``."""
+
+    @staticmethod
+    def forward(ctx, module: "SequenceFrontEnd", batch, *params):
+        saved: dict = {}
+        with torch.no_grad():
+            out = module._forward_impl(batch, True, saved)
+        names = list(module.streams)
+        module._last_states = {k: v for k, v in out.items() if k.startswith(("pooled.", "state."))}
+        ctx.module, ctx.saved, ctx.names = module, saved, names
+        ctx.pnames = [k for k, _ in module.named_parameters()]
+        return tuple(out[n] for n in names)
+
+    @staticmethod
+    def backward(ctx, *douts):
+        module = ctx.module
+        with torch.no_grad():
+            grads = module._backward_impl(ctx.saved, {n: g for n, g in zip(ctx.names, douts)})
+        ctx.saved = None
+        return (None, None) + tuple(grads.get(k) for k in ctx.pnames)
