@@ -172,3 +172,102 @@ def test_frontend_backward_matches_oracle_autograd(d_model, heads, lengths, batc
     print(f"front-end backward d={d_model}: worst parameter-gradient rel-err {worst[1]:.2e} ({worst[0]}); top: "
           + ", ".join(f"{k} {v:.1e}" for k, v in top))
     assert worst[1] < BF16_TOL                    # north_star bf16 tolerance 2e-2, every parameter gradient
+
+
+def test_end_to_end_training_gradients_through_fusion_and_classifier():
+    """Sequences -> SequenceFrontEnd -> CrossModalTransformer -> DeepTruthClassifier -> cross-entropy, ONE backward.
+    The reference's fusion forward is not smooth (|a - b| interactions, evidence gates: a 1e-3 relative change of its
+    inputs moves its input gradients by 2-3 %, measured on the CPU oracle), so the chain is checked link by link at the
+    SAME evaluation point instead of end to end at two slightly different ones:
+      (1) loss against the all-oracle chain (bf16 tolerance);
+      (2) dL/d(pooled vectors) that the fusion backward hands to the front-end, against autograd over the restated
+          reference evaluated AT the front-end's own outputs;
+      (3) the front-end's parameter gradients against autograd over the self-oracle driven by that same upstream gradient."""
+    from oracle import fnd_oracle as FO
+    from ultrafnd_git_b200.modules import CrossModalTransformer, DeepTruthClassifier
+    from ultrafnd_git_b200.seqfront import SequenceFrontEnd
+    streams, blocks = O.FAKESV_STREAMS, O.FAKESV_BLOCKS
+    d_model, heads, B = 128, 2, 6
+    lengths = {"text": 40, "frames": 83, "audio": 50, "c3d": 83}
+    p = O.init_params(streams, blocks, d_model, seed=5)
+    data = O.make_batch(streams, lengths, B, seed=6)
+    for n in streams:
+        data[n] = data[n].bfloat16().float()
+    fus, clf = FO.init_params(42)
+    FO.perturb_node_head(clf)
+    tier_a = FO.make_batch(B, seed=8)
+    label, gnn, aux = tier_a["label"], tier_a["gnn_feat"], tier_a["aux"]
+    # ---- kernels: one forward, one backward through all three modules
+    f = CrossModalTransformer(precision="fp32"); c = DeepTruthClassifier(precision="fp32")
+    f.load_state_dict(fus); c.load_state_dict(clf)
+    for m in list(f.modules()) + list(c.modules()):
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+    f.train(); c.train(); f._sync_dropout(); c._sync_dropout()
+    fe = SequenceFrontEnd(d_model, heads, streams, blocks).cuda()
+    fe.load_state_dict(p)
+    seq_feats = {streams[n][2]: data[n].cuda() for n in streams}
+    for n in streams:
+        seq_feats[streams[n][2] + "_mask"] = data[n + "_mask"].cuda()
+    seq_feats["gnn_feat"] = gnn.cuda()
+    pooled = fe.forward_features(seq_feats)                 # what CrossModalTransformer.forward does for 3-D inputs
+    for n in streams:
+        pooled[streams[n][2]].retain_grad()
+    out = f(pooled)
+    loss = F.cross_entropy(c(out["fused"], aux.cuda())["logits"], label.cuda())
+    loss.backward()
+    torch.cuda.synchronize()
+    fe.check_error()
+    # ---- (1) + (2): restated reference at the front-end's own outputs
+    y_in = {streams[n][2]: pooled[streams[n][2]].detach().cpu().clone().requires_grad_(True) for n in streams}
+    feats = dict(y_in); feats["gnn_feat"] = gnn
+    fo = FO.fusion_forward({k: v.clone() for k, v in fus.items()}, feats, dropout=0.0)
+    co = FO.classifier_forward({k: v.clone() for k, v in clf.items()}, fo["fused"], aux, dropout=0.0)
+    loss_ref = F.cross_entropy(co["logits"], label)
+    loss_ref.backward()
+    e_loss = abs(float(loss.detach()) - float(loss_ref.detach())) / float(loss_ref.detach())
+    e_dy = {k: _rel(pooled[k].grad, y_in[k].grad) for k in y_in}
+    # ---- (3): self-oracle front-end driven by the kernels' upstream gradient
+    pr = {k: (v.bfloat16().float() if (k.endswith("weight") and v.dim() == 2) else v.clone()).requires_grad_(True) for k, v in p.items()}
+    ys = O.forward(pr, data, streams, blocks, heads)
+    torch.autograd.backward([ys[n] for n in streams], [pooled[streams[n][2]].grad.cpu() for n in streams])
+    errs = {k: _rel(v.grad, pr[k].grad) for k, v in fe.named_parameters()}
+    top = sorted(errs.items(), key=lambda kv: -kv[1])[:3]
+    print(f"end-to-end: loss {float(loss.detach()):.6f} vs {float(loss_ref.detach()):.6f} ({e_loss:.1e}); dL/d pooled "
+          + ", ".join(f"{k.split('_')[0]} {v:.1e}" for k, v in e_dy.items()) + "; front-end gradients top: "
+          + ", ".join(f"{k} {v:.1e}" for k, v in top))
+    assert e_loss < 1e-3                                   # Tier A in fp32 mode at identical inputs: north_star fp32 tolerance
+    assert max(e_dy.values()) < 5e-3                       # fp32-mode gradient bound used throughout (5x the logits tolerance)
+    assert max(errs.values()) < BF16_TOL                   # the front-end is bf16: north_star 2e-2
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-3), ("bf16", 2e-2)])
+def test_fusion_input_gradients_match_oracle(precision, tol):
+    """dL/d(text, audio, visual, temporal vectors) returned by CrossModalTransformer's backward (dX_m = dP_m W_m) against
+    autograd over the restated reference forward (cross_modal_transformer.py:141-198), same inputs on both sides."""
+    from oracle import fnd_oracle as FO
+    from ultrafnd_git_b200.modules import CrossModalTransformer, DeepTruthClassifier
+    B = 24
+    fus, clf = FO.init_params(42)
+    FO.perturb_node_head(clf)
+    batch = FO.make_batch(B, seed=31)
+    keys = ("text_features", "audio_features", "visual_features", "temporal_features")
+    ref_in = {k: batch[k].clone().requires_grad_(True) for k in keys}
+    feats = dict(ref_in); feats["gnn_feat"] = batch["gnn_feat"]
+    fo = FO.fusion_forward({k: v.clone() for k, v in fus.items()}, feats, dropout=0.0)
+    co = FO.classifier_forward({k: v.clone() for k, v in clf.items()}, fo["fused"], batch["aux"], dropout=0.0)
+    F.cross_entropy(co["logits"], batch["label"]).backward()
+    f = CrossModalTransformer(precision=precision); c = DeepTruthClassifier(precision=precision)
+    f.load_state_dict(fus); c.load_state_dict(clf)
+    for m in list(f.modules()) + list(c.modules()):
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+    f.train(); c.train(); f._sync_dropout(); c._sync_dropout()
+    got_in = {k: batch[k].cuda().requires_grad_(True) for k in keys}
+    gf = dict(got_in); gf["gnn_feat"] = batch["gnn_feat"].cuda()
+    out = f(gf)
+    F.cross_entropy(c(out["fused"], batch["aux"].cuda())["logits"], batch["label"].cuda()).backward()
+    torch.cuda.synchronize()
+    errs = {k: _rel(got_in[k].grad, ref_in[k].grad) for k in keys}
+    print(f"fusion input gradients [{precision}]: " + ", ".join(f"{k} {v:.1e}" for k, v in errs.items()))
+    assert max(errs.values()) < 5 * tol          # same bound the per-parameter gradient tests use (5x the logits tolerance)

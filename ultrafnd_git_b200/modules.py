@@ -157,7 +157,31 @@ class _FusionFn(torch.autograd.Function):
         check(eng.lib.fnd_fusion_backward(plan.handle, dfused.data_ptr(), None, eng.stream_ptr()), "fnd_fusion_backward")
         flat = eng.grads.clone()       # autograd may keep/accumulate the returned tensors; the arena is overwritten next step
         grads = tuple(eng.grad_view(module._prefix + n, flat) for n in module._param_names)
-        return (None, None, None, None, None, None) + grads
+        # Gradients w.r.t. the modality vectors (only when they come from a trainable SequenceFrontEnd): dX_m = dP_m W_m.
+        # dP (bf16, [B, 5H], the operand the projection wgrad reads) is still in the plan's workspace; the product runs
+        # on the library's persistent tcgen05 GEMM. The evidence scalars are computed under no_grad in the reference
+        # (cross_modal_transformer.py:153-164), so the projections are the only path back to the inputs.
+        dins = [None, None, None, None]
+        if any(ctx.needs_input_grad[1:5]):
+            from . import seq_ops as S
+            B, H = dfused.shape[0], eng.dims.hidden
+            planes = [plan.buffer("dP_hi", torch.bfloat16, (B, 5 * H))]
+            try:
+                planes.append(plan.buffer("dP_lo", torch.bfloat16, (B, 5 * H)))        # fp32 mode: dP = hi + lo
+            except KeyError:
+                pass
+            projs = (module.text_proj, module.audio_proj, module.visual_proj, module.temporal_proj)
+            for m, proj in enumerate(projs):
+                if not ctx.needs_input_grad[1 + m]:
+                    continue
+                wt = proj.weight.detach().to(torch.bfloat16).t().contiguous()          # [D_in, H]
+                dx = None
+                for dP in planes:
+                    part = torch.empty(B, wt.shape[0], dtype=torch.float32, device=dfused.device)
+                    S.linear(dP[:, m * H:(m + 1) * H], wt, None, out_f32=part, want_bf16=False)
+                    dx = part if dx is None else dx + part
+                dins[m] = dx
+        return (None, dins[0], dins[1], dins[2], dins[3], None) + grads
 
 
 class CrossModalTransformer(_EngineModule):
@@ -225,8 +249,8 @@ class CrossModalTransformer(_EngineModule):
             feats = fe.forward_features(feats)
 
         def prep(x: torch.Tensor) -> torch.Tensor:
-            if x.requires_grad:
-                raise NotImplementedError("gradients w.r.t. the input features are not produced by this drop-in")
+            # the four modality vectors may carry a graph (a trainable SequenceFrontEnd produced them): _FusionFn.backward
+            # returns dL/dx for them; gnn_feat never does
             return x.to(eng.device, dtype=torch.float32)
 
         t, a = prep(feats["text_features"]), prep(feats["audio_features"])
@@ -238,6 +262,8 @@ class CrossModalTransformer(_EngineModule):
                 # is a shape error there too (cross_modal_transformer.py:184,197; SURVEY.md §7 hard parts)
                 raise RuntimeError(f"mat1 and mat2 shapes cannot be multiplied ({t.shape[0]}x{15 * self.hidden} and "
                                    f"{self.fused_dim}x{2 * self.hidden}): gnn_feat is required when use_gnn=True")
+            if feats["gnn_feat"].requires_grad:
+                raise NotImplementedError("gradients w.r.t. gnn_feat are not produced by this drop-in")
             g = prep(feats["gnn_feat"])
         params = tuple(self.parameters())
         fused, logits, sc, emo, delay = _FusionFn.apply(self, t, a, v, u, g, *params)
