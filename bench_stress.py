@@ -221,6 +221,27 @@ def run_b200_arm(args):
     torch.cuda.synchronize()
     assert int(err.item()) == 0
 
+    # ---- fused attention backward alone, and one TRAINING step of the front-end (forward with activations kept +
+    #      fused backward through SequenceFrontEnd's autograd node; eager launches: the backward allocates its buffers) ----
+    d_at = torch.randn(B * LT, d, device=dev, generator=gg).bfloat16()
+    lse_t = torch.empty(B, H, LT, device=dev, dtype=torch.float32)
+    S.coattn_forward(qkv_t, qkv_f, qkv_f, B, H, LT, LF, 0, d, 2 * d, out=at, lse=lse_t, err=err)
+    dqkv_t, dqkv_f = torch.empty_like(qkv_t), torch.empty_like(qkv_f)
+    bwd_ms = _median_ms(lambda: S.coattn_backward(qkv_t, qkv_f, qkv_f, at, d_at, lse_t, B, H, LT, LF, dqkv_t, dqkv_f, dqkv_f,
+                                                  q_col0=0, k_col0=d, v_col0=2 * d, dq_col0=0, dk_col0=d, dv_col0=2 * d, err=err),
+                        reps=10, warm=2)
+    wts = {n: torch.randn(B, s_[1], device=dev, generator=gg) for n, s_ in STREAMS.items()}
+
+    def train_step():
+        for p_ in fe.parameters():
+            p_.grad = None
+        o = fe(resident[0])
+        sum((o[n] * wts[n]).sum() for n in STREAMS).backward()
+    train_ms = _median_ms(train_step, reps=max(3, min(K, 10)), warm=2, flush=flush_buf)
+    torch.cuda.synchronize()
+    fe.check_error()
+    assert int(err.item()) == 0
+
     peaks = bench.measured_peaks()
     layer_flops = B * 2.0 * (2.0 * (2.0 * LT * d * d + 2.0 * LF * d * d + 2.0 * LT * LF * d))
     peak = peaks["bf16_tflops"] * 1e12
@@ -263,6 +284,16 @@ def run_b200_arm(args):
         cpu_baseline = {"value": 2 * n / dt, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
                         "sample": f"{n} forward passes at batch 2 in {dt:.1f} s (self-oracle oracle/seq_oracle.py on the host CPU)"}
 
+    attn_fwd_flops = ops["attn_text_from_frames"][1]
+    kernels["attn_bwd_text_from_frames"] = {"ms": round(bwd_ms, 5), "tflops": 2.5 * attn_fwd_flops / (bwd_ms / 1e3) / 1e12,
+                                            "frac_of_measured_bf16_peak": 2.5 * attn_fwd_flops / (bwd_ms / 1e3) / peak,
+                                            "note": "row prologue + dQ kernel + dK/dV kernel; algorithmic FLOPs = 2.5x the forward's "
+                                                    "(the two-kernel split executes 3.5x: S and dP are recomputed in both)"}
+    fl_fwd = fe.flops({"text": LT, "frames": LF}, B)
+    train = {"ms_per_step": train_ms, "value": B / (train_ms / 1e3), "unit": "samples/s",
+             "tflops": 3.0 * fl_fwd / (train_ms / 1e3) / 1e12, "frac_of_measured_bf16_peak": 3.0 * fl_fwd / (train_ms / 1e3) / peak,
+             "note": "one rank: forward (activations kept) + fused backward of every front-end parameter (attention backward, LayerNorm / "
+                     "pool backward, dgrad + token-major wgrad GEMMs, bias column sums), eager launches, L2 flushed; FLOPs counted as 3x forward"}
     nlaunch = 2 * 3 + 8 + 2 * 2                       # cast+embed+LN per stream, block, pool+head per stream
     fl_total = fe.flops({"text": LT, "frames": LF}, B)
     line = {
@@ -276,7 +307,7 @@ def run_b200_arm(args):
         "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                 "ms_per_step": e2e_ms / KE, "note": "bound by the H2D copy of the fp32 features (PCIe)"},
         "gpu_launches": nlaunch * K, "clocks": clocks, "roofline": roofline, "coattn": coattn, "coattn_tensor_frac": coattn["frac_of_measured_bf16_peak"],
-        "cpu_baseline": cpu_baseline, "kernels": kernels,
+        "cpu_baseline": cpu_baseline, "kernels": kernels, "train": train,
         "step_tensor_frac": fl_total / (total_ms / K / 1e3) / peak,
     }
     print(json.dumps(line), flush=True)

@@ -96,6 +96,14 @@ size_t fnd_seq_colsum_workspace(int M, int N);
 int fnd_seq_colsum(const void* x_bf16, int x_pitch, int M, int N, float* out, void* workspace, size_t workspace_bytes,
                    void* stream);
 
+/* Weight gradient of a token-level nn.Linear: dw[n_out, k_in] (fp32) = dy[tokens, n_out]^T x[tokens, k_in]. Both operands are
+ * read token-major IN PLACE (MN-major UMMA descriptors on the persistent tcgen05 GEMM: nothing is transposed in memory); the
+ * token reduction is split into ranges whose partial tiles are summed in a fixed order (deterministic). n_out, k_in
+ * multiples of 8; dw dense (dw_pitch == k_in) whenever the plan splits (always, for tokens >= 2048). */
+size_t fnd_seq_wgrad_workspace(int tokens, int n_out, int k_in);
+int fnd_seq_wgrad(const void* dy_bf16, int dy_pitch, const void* x_bf16, int x_pitch, int tokens, int n_out, int k_in,
+                  float* dw, int dw_pitch, void* workspace, size_t workspace_bytes, int* err_flag, void* stream);
+
 /* Backward of fnd_seq_masked_mean_pool: dx[b,l,:] = m[b,l] / max(sum_l m[b,l], 1e-6) * dpooled[b,:] (bf16). */
 int fnd_seq_masked_mean_pool_backward(const float* dpooled, int dp_pitch, const unsigned char* mask, const int* len, int B,
                                       int L, int d, void* dx_bf16, int dx_pitch, void* stream);

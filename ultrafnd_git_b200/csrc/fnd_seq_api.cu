@@ -80,6 +80,7 @@ int fnd_seq_linear(const void* a_bf16, int a_pitch, const void* w_bf16, int w_pi
   SeqGemmParams P;
   memset(&P, 0, sizeof(P));
   P.M = M; P.N = N; P.K = K;
+  P.splits = 1; P.kb_per_split = cdiv(K, kSeqGemmBK);
   P.tiles_m = cdiv(M, kSeqGemmBM);
   // widest tile that still gives every SM work; 256 columns keep one UMMA busy for 128 cycles
   int bn = 256;
@@ -201,6 +202,74 @@ int fnd_seq_masked_mean_pool(const void* x_bf16, int x_pitch, const unsigned cha
 
 // ------------------------------------------------------------------------------------------------- backward pass
 
+// dW[N_out, K_in] = dY[tokens, N_out]^T X[tokens, K_in]: split plan shared by the workspace query and the launch
+static void wgrad_plan(int tokens, int n_out, int k_in, int* bn, int* splits, int* kb_per_split) {
+  *bn = (k_in % 256 == 0 || k_in > 256) ? 256 : (k_in > 64 ? 128 : 64);
+  const int tiles = cdiv(n_out, kSeqGemmBM) * cdiv(k_in, *bn);
+  const int kblocks = cdiv(tokens, kSeqGemmBK);
+  int s = cdiv(4 * seq_num_sms(), tiles);                 // >= 4 waves of items
+  const int smax = kblocks / 16 > 0 ? kblocks / 16 : 1;   // at least 16 k-blocks (1024 tokens) per item
+  if (s > smax) s = smax;
+  if (s < 1) s = 1;
+  *kb_per_split = cdiv(kblocks, s);
+  *splits = cdiv(kblocks, *kb_per_split);                 // every split non-empty
+}
+
+size_t fnd_seq_wgrad_workspace(int tokens, int n_out, int k_in) {
+  if (tokens <= 0 || n_out <= 0 || k_in <= 0) return 0;
+  int bn, splits, kbps;
+  wgrad_plan(tokens, n_out, k_in, &bn, &splits, &kbps);
+  return splits > 1 ? static_cast<size_t>(splits) * n_out * k_in * sizeof(float) : 16;
+}
+
+int fnd_seq_wgrad(const void* dy_bf16, int dy_pitch, const void* x_bf16, int x_pitch, int tokens, int n_out, int k_in,
+                  float* dw, int dw_pitch, void* workspace, size_t workspace_bytes, int* err_flag, void* stream) {
+  if (!dy_bf16 || !x_bf16 || !dw || !workspace || tokens <= 0 || n_out <= 0 || k_in <= 0) return -1;
+  if ((n_out & 7) || (k_in & 7) || (dy_pitch & 7) || (x_pitch & 7) || dy_pitch < n_out || x_pitch < k_in) return -2;
+  if ((dw_pitch & 3) || dw_pitch < k_in || !aligned16(dw) || !aligned16(workspace)) return -3;
+  if (workspace_bytes < fnd_seq_wgrad_workspace(tokens, n_out, k_in)) return -4;
+  { int r = fnd_seq_init(); if (r) return r; }
+  SeqGemmParams P;
+  memset(&P, 0, sizeof(P));
+  int bn;
+  wgrad_plan(tokens, n_out, k_in, &bn, &P.splits, &P.kb_per_split);
+  P.mn = 1;
+  P.M = n_out; P.N = k_in; P.K = tokens;
+  P.bn = bn;
+  P.tiles_m = cdiv(n_out, kSeqGemmBM);
+  P.tiles_n = cdiv(k_in, bn);
+  P.kblocks = cdiv(tokens, kSeqGemmBK);
+  P.stage_bytes = kSeqGemmBM * kSeqGemmBK * 2 + bn * kSeqGemmBK * 2;
+  P.nstages = kSeqGemmRingBudget / P.stage_bytes;
+  if (P.nstages > kSeqGemmMaxStages) P.nstages = kSeqGemmMaxStages;
+  P.err = err_flag;
+  const bool split = P.splits > 1;
+  // partial tiles are dense [n_out, k_in]; without a split the kernel writes dw directly
+  P.out_f32 = split ? static_cast<float*>(workspace) : dw;
+  P.f32_pitch = split ? k_in : dw_pitch;
+  P.split_stride = static_cast<long long>(n_out) * k_in;
+  if (!split && (dw_pitch & 3)) return -3;
+  int r = encode_bf16_2d(&P.tmA, dy_bf16, n_out, tokens, dy_pitch, 64, kSeqGemmBK);     // dY as [tokens][n_out]: MN-major A
+  if (r) return r;
+  r = encode_bf16_2d(&P.tmB, x_bf16, k_in, tokens, x_pitch, 64, kSeqGemmBK);            // X as [tokens][k_in]: MN-major B
+  if (r) return r;
+  const int sms = seq_num_sms();
+  const long long nitems = static_cast<long long>(P.tiles_m) * P.tiles_n * P.splits;
+  const int grid = nitems < sms ? static_cast<int>(nitems) : sms;
+  const size_t smem = static_cast<size_t>(P.nstages) * P.stage_bytes + 2 * kSeqGemmStageOutBytes + kSeqGemmHeader + 1024;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  seq_gemm_kernel<<<grid, kSeqGemmThreads, smem, st>>>(P);
+  SEQ_CUDA_OK(cudaGetLastError());
+  if (split) {
+    if (dw_pitch != k_in) return -3;                     // the fixed-order reduction writes a dense matrix
+    const long long n = static_cast<long long>(n_out) * k_in;
+    seq_reduce_partials_kernel<<<static_cast<unsigned>((n + 127) / 128), 256, 0, st>>>(static_cast<const float*>(workspace), P.splits,
+                                                                                          static_cast<int>(n), dw);
+    SEQ_CUDA_OK(cudaGetLastError());
+  }
+  return 0;
+}
+
 static int ln_bwd_grid(int M, int d) {
   const int want = cdiv(M, 8);
   const int cap = seq_num_sms() * (d <= 512 ? 2 : 1);
@@ -231,7 +300,7 @@ int fnd_seq_layernorm_backward(const void* t_bf16, int t_pitch, const void* dy_b
   else if (d <= 1024) seq_layernorm_bwd_kernel<4><<<grid, 256, smem, st>>>(P);
   else seq_layernorm_bwd_kernel<8><<<grid, 256, smem, st>>>(P);
   SEQ_CUDA_OK(cudaGetLastError());
-  seq_reduce_partials_kernel<<<cdiv(2 * d, 4 * 256), 256, 0, st>>>(static_cast<const float*>(workspace), grid, 2 * d, dgamma);
+  seq_reduce_partials_kernel<<<cdiv(2 * d, 128), 256, 0, st>>>(static_cast<const float*>(workspace), grid, 2 * d, dgamma);
   SEQ_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -258,7 +327,7 @@ int fnd_seq_colsum(const void* x_bf16, int x_pitch, int M, int N, float* out, vo
   dim3 grid(static_cast<unsigned>(cdiv(N, 256)), static_cast<unsigned>(slices));
   seq_colsum_kernel<<<grid, 256, 0, st>>>(P);
   SEQ_CUDA_OK(cudaGetLastError());
-  seq_reduce_partials_kernel<<<cdiv(N, 4 * 256), 256, 0, st>>>(static_cast<const float*>(workspace), slices, N, out);
+  seq_reduce_partials_kernel<<<cdiv(N, 128), 256, 0, st>>>(static_cast<const float*>(workspace), slices, N, out);
   SEQ_CUDA_OK(cudaGetLastError());
   return 0;
 }

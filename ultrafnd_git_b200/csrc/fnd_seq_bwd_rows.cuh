@@ -121,17 +121,32 @@ __global__ void __launch_bounds__(256) seq_layernorm_bwd_kernel(const LnBwdParam
   }
 }
 
-// out[i] = sum_p part[p][i] in index order (deterministic); n floats per partial row, 128-bit loads.
+// out[i] = sum_p part[p][i], fixed order (deterministic); n floats per partial row (multiple of 4), 128-bit loads.
+// A CTA owns 128 consecutive floats: 32 column lanes x 8 part lanes (part lane y adds parts y, y + 8, ...), then the eight
+// partial sums meet in shared memory in lane order. (One thread per column walking all parts serialised ~300 dependent
+// loads on two CTAs: 57 us per call for the 2 x 1024 LayerNorm gradients.)
 __global__ void __launch_bounds__(256) seq_reduce_partials_kernel(const float* __restrict__ part, int nparts, int n, float* __restrict__ out) {
-  const int i4 = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i4 * 4 >= n) return;
+  __shared__ float4 red[8][32];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int i4 = blockIdx.x * 32 + tx;
   float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (i4 * 4 < n) {
 #pragma unroll 4
-  for (int p = 0; p < nparts; ++p) {
-    const float4 v = ldcg_f4(part + static_cast<size_t>(p) * n + i4 * 4);
-    s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    for (int p = ty; p < nparts; p += 8) {
+      const float4 v = ldcg_f4(part + static_cast<size_t>(p) * n + i4 * 4);
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
   }
-  *reinterpret_cast<float4*>(out + i4 * 4) = s;
+  red[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && i4 * 4 < n) {
+#pragma unroll
+    for (int w = 1; w < 8; ++w) {
+      const float4 v = red[w][tx];
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    *reinterpret_cast<float4*>(out + i4 * 4) = s;
+  }
 }
 
 // Column sums of a bf16 matrix (bias gradients): part[blockIdx.y][n] = sum over this CTA's row slice of x[m][n].

@@ -47,6 +47,13 @@ struct alignas(64) SeqGemmParams {
   float* out_f32;                                // [M, f32_pitch] or null
   int f32_pitch;
   int* err;
+  // Weight-gradient mode (mn = 1): C[M,N] = sum_k A[k,m] B[k,n] with BOTH operands stored [K][rows] (rows contiguous) — dW =
+  // dY^T X read token-major in place (MN-major UMMA descriptors, 64 x 64 TMA boxes), fp32 output. The token reduction is cut
+  // into `splits` ranges of kb_per_split k-blocks; split s writes its partial tile to out_f32 + s * split_stride (summed in
+  // split order by seq_reduce_partials_kernel: deterministic), which turns 32..192 output tiles into >= 4 waves of items.
+  int mn;
+  int splits, kb_per_split;
+  long long split_stride;                        // floats between the partial outputs of consecutive splits
 };
 
 __global__ void __launch_bounds__(kSeqGemmThreads, 1) seq_gemm_kernel(const __grid_constant__ SeqGemmParams P) {
@@ -65,6 +72,8 @@ __global__ void __launch_bounds__(kSeqGemmThreads, 1) seq_gemm_kernel(const __gr
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int bn = P.bn, nstages = P.nstages, stage_bytes = P.stage_bytes, kblocks = P.kblocks;
   const int ntiles = P.tiles_m * P.tiles_n;
+  const int nitems = ntiles * P.splits;            // work item = (k-range split, tile); splits == 1 outside the wgrad mode
+  const bool mn = P.mn != 0;
   const uint32_t tmem_cols = static_cast<uint32_t>(2 * bn);
 
   if (warp == 0 && lane == 0) {
@@ -96,17 +105,28 @@ __global__ void __launch_bounds__(kSeqGemmThreads, 1) seq_gemm_kernel(const __gr
       uint32_t ph = 1u;                          // parity to wait for on empty_bar (fresh barrier: passes)
       bool ok = true;
 #pragma unroll 1
-      for (int tile = blockIdx.x; tile < ntiles && ok; tile += gridDim.x) {
+      for (int item = blockIdx.x; item < nitems && ok; item += gridDim.x) {
+        const int split = item / ntiles, tile = item - split * ntiles;
         const int tm = tile / P.tiles_n, tn = tile - tm * P.tiles_n;
         const int am = tm * kSeqGemmBM, bnr = tn * bn;
+        const int kb0 = split * P.kb_per_split, kb1 = min(kblocks, kb0 + P.kb_per_split);
 #pragma unroll 1
-        for (int kb = 0; kb < kblocks; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           ok = mbar_wait_fast(&empty_bar[s], ph, P.err, FND_DEV_TIMEOUT_PRODUCER);
           if (!ok) break;
           mbar_arrive_expect_tx(&full_bar[s], tx);
           uint8_t* sA = ring + s * stage_bytes;
-          tma_load_2d(sA, &P.tmA, &full_bar[s], kb * kSeqGemmBK, am, kEvictNormal);
-          tma_load_2d(sA + kSeqGemmBM * kSeqGemmBK * 2, &P.tmB, &full_bar[s], kb * kSeqGemmBK, bnr, kEvictLast);
+          uint8_t* sB = sA + kSeqGemmBM * kSeqGemmBK * 2;
+          if (!mn) {
+            tma_load_2d(sA, &P.tmA, &full_bar[s], kb * kSeqGemmBK, am, kEvictNormal);
+            tma_load_2d(sB, &P.tmB, &full_bar[s], kb * kSeqGemmBK, bnr, kEvictLast);
+          } else {
+            // 64 (rows, contiguous) x 64 (k) boxes: one 128-byte swizzle atom wide, 8 KB each, LBO = 8192 between atoms
+            tma_load_2d(sA, &P.tmA, &full_bar[s], am, kb * kSeqGemmBK, kEvictNormal);
+            tma_load_2d(sA + 8192, &P.tmA, &full_bar[s], am + 64, kb * kSeqGemmBK, kEvictNormal);
+            for (int ch = 0; ch < bn / 64; ++ch)
+              tma_load_2d(sB + ch * 8192, &P.tmB, &full_bar[s], bnr + ch * 64, kb * kSeqGemmBK, kEvictNormal);
+          }
           if (++s == nstages) { s = 0; ph ^= 1u; }
         }
       }
@@ -116,16 +136,20 @@ __global__ void __launch_bounds__(kSeqGemmThreads, 1) seq_gemm_kernel(const __gr
     // control flow with ONE elected lane around the issue, so operands reach the uniform datapath without
     // divergence-safe conversion loops) =================
     {
-      const uint32_t idesc = make_idesc_bf16(kSeqGemmBM, bn, 0, 0);
+      const uint32_t idesc = make_idesc_bf16(kSeqGemmBM, bn, mn ? 1 : 0, mn ? 1 : 0);
       const uint32_t dhi = smem_desc_hi_sw128(1024);
-      const uint32_t a_lo0 = smem_desc_lo(smem_u32(ring), 16);
+      const uint32_t a_lo0 = smem_desc_lo(smem_u32(ring), mn ? 8192 : 16);
       const uint32_t b_off = (kSeqGemmBM * kSeqGemmBK * 2) >> 4;
       const uint32_t stage_step = static_cast<uint32_t>(stage_bytes) >> 4;
+      // K-major: 16 contraction elements = 32 B inside the swizzled row; MN-major: 16 contraction rows of 128 B = 2048 B
+      const uint32_t kstep = mn ? 128u : 2u;
       int s = 0, lt = 0;
       uint32_t ph = 0u;
       bool ok = true;
 #pragma unroll 1
-      for (int tile = blockIdx.x; tile < ntiles && ok; tile += gridDim.x, ++lt) {
+      for (int item = blockIdx.x; item < nitems && ok; item += gridDim.x, ++lt) {
+        const int split = item / ntiles;
+        const int kb0 = split * P.kb_per_split, kb1 = min(kblocks, kb0 + P.kb_per_split);
         const int ab = lt & 1;
         const uint32_t aph = static_cast<uint32_t>(lt >> 1) & 1u;
         ok = mbar_wait_fast(&tempty_bar[ab], aph ^ 1u, P.err, FND_DEV_TIMEOUT_MMA);
@@ -133,19 +157,19 @@ __global__ void __launch_bounds__(kSeqGemmThreads, 1) seq_gemm_kernel(const __gr
         tc_fence_after_sync();
         const uint32_t tacc = tmem_base + static_cast<uint32_t>(ab * bn);
 #pragma unroll 1
-        for (int kb = 0; kb < kblocks; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           ok = mbar_wait_fast(&full_bar[s], ph, P.err, FND_DEV_TIMEOUT_MMA);
           if (!ok) break;
           tc_fence_after_sync();
           const uint32_t al = a_lo0 + static_cast<uint32_t>(s) * stage_step;
           const uint32_t bl = al + b_off;
           if (elect_one()) {
-            umma_f16(tacc, desc64(al, dhi), desc64(bl, dhi), idesc, kb != 0 ? 1u : 0u);
-            umma_f16(tacc, desc64(al + 2, dhi), desc64(bl + 2, dhi), idesc, 1u);
-            umma_f16(tacc, desc64(al + 4, dhi), desc64(bl + 4, dhi), idesc, 1u);
-            umma_f16(tacc, desc64(al + 6, dhi), desc64(bl + 6, dhi), idesc, 1u);
+            umma_f16(tacc, desc64(al, dhi), desc64(bl, dhi), idesc, kb != kb0 ? 1u : 0u);
+            umma_f16(tacc, desc64(al + kstep, dhi), desc64(bl + kstep, dhi), idesc, 1u);
+            umma_f16(tacc, desc64(al + 2 * kstep, dhi), desc64(bl + 2 * kstep, dhi), idesc, 1u);
+            umma_f16(tacc, desc64(al + 3 * kstep, dhi), desc64(bl + 3 * kstep, dhi), idesc, 1u);
             umma_commit(&empty_bar[s]);
-            if (kb == kblocks - 1) umma_commit(&tfull_bar[ab]);
+            if (kb == kb1 - 1) umma_commit(&tfull_bar[ab]);
           }
           __syncwarp();
           if (++s == nstages) { s = 0; ph ^= 1u; }
@@ -165,7 +189,7 @@ __global__ void __launch_bounds__(kSeqGemmThreads, 1) seq_gemm_kernel(const __gr
     // L2/HBM round trip per slab and made the epilogue, not the MMA, the pace of the residual GEMMs.
     int pf_tile = blockIdx.x, pf_c = 0;
     uint32_t pf_n = 0;
-    auto pf_issue = [&]() {
+    auto pf_issue = [&]() {                                 // (residuals never occur in the wgrad mode: items == tiles here)
       if (pf_tile >= ntiles) return;
       const int ptm = pf_tile / P.tiles_n, ptn = pf_tile - ptm * P.tiles_n;
       const uint32_t b = pf_n & 1u;
@@ -176,7 +200,8 @@ __global__ void __launch_bounds__(kSeqGemmThreads, 1) seq_gemm_kernel(const __gr
       if (pf_c >= bn || ptn * bn + pf_c >= P.N) { pf_c = 0; pf_tile += gridDim.x; }
     };
     if (P.resid && P.out_bf && epi_tid == 0) { pf_issue(); pf_issue(); }
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++lt) {
+    for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++lt) {
+      const int split = item / ntiles, tile = item - split * ntiles;
       const int tm = tile / P.tiles_n, tn = tile - tm * P.tiles_n;
       const int ab = lt & 1;
       const uint32_t aph = static_cast<uint32_t>(lt >> 1) & 1u;
@@ -290,7 +315,7 @@ __global__ void __launch_bounds__(kSeqGemmThreads, 1) seq_gemm_kernel(const __gr
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
           }
-          float* op = P.out_f32 + static_cast<size_t>(m) * P.f32_pitch + n0;
+          float* op = P.out_f32 + static_cast<size_t>(split) * P.split_stride + static_cast<size_t>(m) * P.f32_pitch + n0;
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             if (j < ncols) *reinterpret_cast<float4*>(op + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);

@@ -198,8 +198,8 @@ def masked_mean_pool_backward(dpooled: torch.Tensor, B: int, L: int, mask: Optio
 
 
 def wgrad(dy: torch.Tensor, x: torch.Tensor, err: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """dW[N, K] (fp32) = dy[M, N]^T @ x[M, K] on the tcgen05 GEMM (fnd_gemm_bf16_async: both operands are read in place with
-    the token dimension as the reduction — MN-major descriptors — so nothing is transposed in memory)."""
+    """dW[N, K] (fp32) = dy[M, N]^T @ x[M, K] on the persistent tcgen05 GEMM (fnd_seq_wgrad): both operands are read in place
+    with the token dimension as the reduction — MN-major descriptors — so nothing is transposed in memory."""
     dev = _need_cuda(dy, x)
     dy, x = _as2d(dy), _as2d(x)
     M, N = dy.shape
@@ -208,15 +208,8 @@ def wgrad(dy: torch.Tensor, x: torch.Tensor, err: Optional[torch.Tensor] = None)
     if N % 8 or K % 8:
         raise NotImplementedError("wgrad needs N and K to be multiples of 8 (16-byte row pitches)")
     lib = _lib.load()
-    bn = 128 if K % 128 == 0 else 64
-    tiles = ((N + 127) // 128) * (K // bn)
-    splits = 1
-    while tiles * splits * 2 <= 148 and M // (splits * 2) >= 1024:     # split the token reduction while every CTA stays co-resident
-        splits *= 2
     out = torch.empty(N, K, dtype=torch.float32, device=dev)
-    nbytes = lib.fnd_gemm_scratch_bytes(N, K, bn, splits)
-    scratch = torch.zeros(nbytes + 256, dtype=torch.uint8, device=dev)
-    sp = (scratch.data_ptr() + 255) // 256 * 256
-    check(lib.fnd_gemm_bf16_async(dy.data_ptr(), dy.stride(0), 1, x.data_ptr(), x.stride(0), 1, out.data_ptr(), K,
-                                  N, K, M, bn, splits, sp, nbytes, _ptr(err), _stream(dev)), "fnd_gemm_bf16_async")
+    ws = _workspace(lib.fnd_seq_wgrad_workspace(M, N, K), dev)
+    check(lib.fnd_seq_wgrad(dy.data_ptr(), dy.stride(0), x.data_ptr(), x.stride(0), M, N, K, out.data_ptr(), K,
+                            ws.data_ptr(), ws.numel(), _ptr(err), _stream(dev)), "fnd_seq_wgrad")
     return out
