@@ -108,6 +108,17 @@ int fnd_seq_wgrad(const void* dy_bf16, int dy_pitch, const void* x_bf16, int x_p
 int fnd_seq_masked_mean_pool_backward(const float* dpooled, int dp_pitch, const unsigned char* mask, const int* len, int B,
                                       int L, int d, void* dx_bf16, int dx_pitch, void* stream);
 
+/* Optimizer step of the front-end over one flat fp32 range (parameters, gradients, Adam moments at the same offsets):
+ * out4[0] = sum of squares of g (fixed-order reduction); then clip_grad_norm_(max_norm) + torch.optim.AdamW semantics
+ * (decoupled weight decay, bias corrections 1 - beta^step) in ONE pass: g is read as g * grad_scale (1 / world after a
+ * summing all-reduce) * min(1, max_norm / (sqrt(sumsq) * grad_scale + 1e-6)). n a multiple of 4, step >= 1, max_norm <= 0
+ * disables clipping. The trainer the reference uses for its own parameters: src/training/forensic_trainer.py:173-177,292-298. */
+size_t fnd_seq_grad_sumsq_workspace(long long n);
+int fnd_seq_grad_sumsq(const float* g, long long n, float* out4, void* workspace, size_t workspace_bytes, void* stream);
+int fnd_seq_adamw_step(float* w, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                       float eps, float weight_decay, int step, float max_norm, float grad_scale, const float* sumsq,
+                       void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -3,6 +3,7 @@
 Tolerances are BASELINE.json's: logits/loss rel-err <= 1e-3 in fp32 mode and <= 2e-2 in bf16 mode, argmax identical.
 """
 import glob
+import math
 import os
 
 import numpy as np
@@ -152,12 +153,12 @@ def test_fused_train_steps_match_reference(precision):
             assert float(diff.max()) <= max_bound and float(diff.mean()) <= mean_bound, (prefix, k, float(diff.max()), float(diff.mean()))
 
 
-@pytest.mark.parametrize("precision", ["fp32"])
-def test_train_mode_with_dropout_matches_oracle_given_same_masks(precision):
-    """Dropout ON: export the Philox keep-masks the next forward will draw, replay them in the CPU oracle."""
+@pytest.mark.parametrize("precision,B", [("fp32", 16), ("bf16", 128)])
+def test_train_mode_with_dropout_matches_oracle_given_same_masks(precision, B):
+    """Dropout ON: export the Philox keep-masks the next forward will draw, replay them in the CPU oracle.
+    ("bf16", 128) is the BENCHMARKED regime (BASELINE.json configs[1]: bf16 operands, dropout on, batch 128)."""
     f, c, fus, clf = build_pair(42, True, precision)
     f.train(); c.train()
-    B = 16
     batch = O.make_batch(B, seed=77)
     step = FusedStep(f, c, B, precision=precision, use_graph=False)
     masks = {k: v.cpu() for k, v in step.plan.dropout_masks().items()}
@@ -165,20 +166,39 @@ def test_train_mode_with_dropout_matches_oracle_given_same_masks(precision):
         keep = float((masks[k] > 0).float().mean())
         vals = torch.unique(masks[k]).tolist()
         assert all(v == 0.0 or abs(v - 1.0 / (1.0 - p)) < 1e-6 for v in vals), vals
-        assert abs(keep - (1.0 - p)) < (0.25 if k == "tree" else 0.05), (k, keep)
+        # keep-rate within five binomial standard deviations of 1 - p for THIS mask's element count (tree masks are small:
+        # B x trees x 2), plus the 16-bit threshold's quantisation
+        n = masks[k].numel()
+        bound = 5.0 * math.sqrt(p * (1.0 - p) / n) + 2.0 / 65536.0
+        assert abs(keep - (1.0 - p)) < bound, (k, keep, n, bound)
     step.load_batch(to_cuda(batch))
     step.train_fwd_bwd()
     st = step.plan.state()
     out, gf, gc = O.loss_and_grads(fus, clf, batch, dropout=0.1, masks=masks)
-    print(f"[dropout/{precision}] loss {st['loss']} vs oracle {float(out['loss'])}")
+    print(f"[dropout/{precision}/B={B}] loss {st['loss']} vs oracle {float(out['loss'])}")
     assert abs(st["loss"] - float(out["loss"])) / float(out["loss"]) < TOL[precision]
     eng = step.engine
+    worst = ("", 0.0)
+    total = math.sqrt(sum(float(g.norm()) ** 2 for grads in (gf, gc) for g in grads.values()))
+    floor = 1e-4 * total
     for prefix, grads in (("fusion", gf), ("clf", gc)):
         for k, g in grads.items():
             got = eng.grad_view(f"{prefix}.{k}").cpu()
-            if float(g.norm()) == 0:
+            gn = float(g.norm())
+            if gn == 0:
                 continue
-            assert O.rel_err(got, g) < 5 * TOL[precision], (prefix, k, O.rel_err(got, g))
+            if gn < floor:
+                # Vanishing gradients (the evidence-gate MLPs at batch 128: |g| ~ 1e-7 .. 1e-5 against a total norm of 0.29,
+                # a batch sum that cancels almost completely): a RELATIVE error of such a tensor measures rounding noise —
+                # fp32 mode reproduces them to 2e-3, bf16 operands to 8e-2 .. 0.18. They are held to an ABSOLUTE bound at
+                # the scale below which a gradient cannot move the step: 5 x tol x 1e-4 of the total gradient norm.
+                assert float((got - g).norm()) < 5 * TOL[precision] * floor, (prefix, k, float((got - g).norm()), gn)
+                continue
+            e = O.rel_err(got, g)
+            if e > worst[1]:
+                worst = (f"{prefix}.{k}", e)
+            assert e < 5 * TOL[precision], (prefix, k, e)
+    print(f"[dropout/{precision}/B={B}] worst per-parameter gradient rel-err {worst[1]:.2e} ({worst[0]}); total norm {total:.4f}")
     # a second forward draws different masks
     m2 = step.plan.dropout_masks()
     assert not torch.equal(m2["fuse0"].cpu(), masks["fuse0"])

@@ -271,3 +271,74 @@ def test_fusion_input_gradients_match_oracle(precision, tol):
     errs = {k: _rel(got_in[k].grad, ref_in[k].grad) for k in keys}
     print(f"fusion input gradients [{precision}]: " + ", ".join(f"{k} {v:.1e}" for k, v in errs.items()))
     assert max(errs.values()) < 5 * tol          # same bound the per-parameter gradient tests use (5x the logits tolerance)
+
+
+def test_flat_adamw_matches_torch_clip_and_adamw():
+    """fnd_seq_grad_sumsq + fnd_seq_adamw_step against torch.nn.utils.clip_grad_norm_ + torch.optim.AdamW on the SAME gradients
+    (three steps, clipping active in the first and inactive in the last), incl. the 1 / world gradient scale."""
+    from ultrafnd_git_b200 import seq_ops as S
+    g = torch.Generator().manual_seed(12)
+    n = 4 * 25_003
+    w0 = torch.randn(n, generator=g)
+    grads = [torch.randn(n, generator=g) * s for s in (3.0, 0.5, 0.001)]
+    lr, betas, eps, wd, max_norm, world = 3e-3, (0.9, 0.999), 1e-8, 1e-2, 5.0, 4
+    p = torch.nn.Parameter(w0.clone().double())
+    opt = torch.optim.AdamW([p], lr=lr, betas=betas, eps=eps, weight_decay=wd)
+    w = w0.clone().cuda()
+    m, v = torch.zeros_like(w), torch.zeros_like(w)
+    norms = []
+    for t, gr in enumerate(grads, 1):
+        p.grad = (gr.double() / world).clone()                 # the all-reduced SUM is gr; the mean is what the reference steps on
+        norms.append(float(torch.nn.utils.clip_grad_norm_([p], max_norm)))
+        opt.step()
+        gc = gr.cuda()
+        ss = S.grad_sumsq(gc)
+        S.adamw_step(w, gc, m, v, ss, t, lr, betas, eps, wd, max_norm, 1.0 / world)
+        torch.cuda.synchronize()
+        e_n = abs(float(ss[0].sqrt()) / world - norms[-1]) / norms[-1]
+        e_w = _rel(w, p.detach())
+        print(f"flat AdamW step {t}: grad norm {norms[-1]:.4f} (rel-err {e_n:.1e}), parameters rel-err {e_w:.1e}")
+        assert e_n < 1e-5 and e_w < 1e-6                        # fp32 arithmetic against an fp64 torch trajectory
+    assert norms[0] > max_norm > norms[-1]                      # both branches of the clip were exercised
+
+
+def test_sequence_trainer_flat_buffers_and_steps():
+    """SequenceTrainer: gradients land in the flat buffer bit-identically to the plain autograd path, the parameters are
+    views of the flat parameter buffer, and a few optimizer steps reduce a regression loss."""
+    from ultrafnd_git_b200.seqfront import SequenceFrontEnd, SequenceTrainer
+    streams, blocks = O.FAKESV_STREAMS, O.FAKESV_BLOCKS
+    d_model, heads, B = 128, 2, 4
+    lengths = {"text": 40, "frames": 83, "audio": 50, "c3d": 83}
+    p = O.init_params(streams, blocks, d_model, seed=3)
+    data = {k: v.cuda() for k, v in O.make_batch(streams, lengths, B, seed=4).items()}
+    g = torch.Generator().manual_seed(5)
+    target = {n: torch.randn(B, streams[n][1], generator=g).cuda() for n in streams}
+
+    def loss_of(fe):
+        out = fe(data)
+        return sum(((out[n] - target[n]) ** 2).mean() for n in streams)
+
+    fe_plain = SequenceFrontEnd(d_model, heads, streams, blocks).cuda(); fe_plain.load_state_dict(p)
+    loss_of(fe_plain).backward()
+    ref = {k: v.grad.clone() for k, v in fe_plain.named_parameters()}
+    fe = SequenceFrontEnd(d_model, heads, streams, blocks).cuda(); fe.load_state_dict(p)
+    tr = SequenceTrainer(fe, lr=2e-3, max_norm=5.0)
+    assert sum(len(b) for b in fe.grad_order()) == len(ref) and tr.n == sum(v.numel() for v in ref.values())
+    for k, q in fe.named_parameters():
+        o, n = tr.offset[k]
+        assert q.data_ptr() == tr.flat_w[o:o + n].data_ptr()
+    losses = []
+    for it in range(6):
+        tr.zero_grad()
+        loss = loss_of(fe)
+        loss.backward()
+        if it == 0:
+            for k in ref:
+                o, n = tr.offset[k]
+                assert torch.equal(tr.flat_g[o:o + n].view(ref[k].shape), ref[k]), k      # same kernels, same order: bit-identical
+        tr.step()
+        losses.append(float(loss.detach()))
+    torch.cuda.synchronize()
+    fe.check_error()
+    print("SequenceTrainer losses:", ", ".join(f"{x:.4f}" for x in losses), f"| grad norm {tr.grad_norm():.3f}")
+    assert losses[-1] < 0.9 * losses[0] and all(math.isfinite(x) for x in losses)

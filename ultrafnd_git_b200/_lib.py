@@ -173,6 +173,10 @@ def _signatures() -> Dict[str, tuple]:
         "fnd_seq_colsum": (_c_int, [_c_void_p, _c_int, _c_int, _c_int, _c_void_p, _c_void_p, _c_size_t, _c_void_p]),
         "fnd_seq_masked_mean_pool_backward": (_c_int, [_c_void_p, _c_int, _c_void_p, _c_void_p, _c_int, _c_int, _c_int,
                                                        _c_void_p, _c_int, _c_void_p]),
+        "fnd_seq_grad_sumsq_workspace": (_c_size_t, [ll]),
+        "fnd_seq_grad_sumsq": (_c_int, [_c_void_p, ll, _c_void_p, _c_void_p, _c_size_t, _c_void_p]),
+        "fnd_seq_adamw_step": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, ll, _c_float, _c_float, _c_float, _c_float,
+                                        _c_float, _c_int, _c_float, _c_float, _c_void_p, _c_void_p]),
         "fnd_seq_wgrad_workspace": (_c_size_t, [_c_int] * 3),
         "fnd_seq_wgrad": (_c_int, [_c_void_p, _c_int, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_void_p, _c_int,
                                    _c_void_p, _c_size_t, _c_void_p, _c_void_p]),

@@ -423,4 +423,44 @@ int fnd_seq_coattn_backward(const void* q_bf16, int q_pitch, int q_col0, const v
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------------- optimizer
+
+static int sumsq_grid(long long n4) {
+  const long long want = (n4 + 255) / 256;
+  const int cap = seq_num_sms() * 4;
+  return want < cap ? static_cast<int>(want > 0 ? want : 1) : cap;
+}
+
+size_t fnd_seq_grad_sumsq_workspace(long long n) {
+  if (n <= 0) return 0;
+  return static_cast<size_t>(sumsq_grid(n / 4)) * 4 * sizeof(float);
+}
+
+int fnd_seq_grad_sumsq(const float* g, long long n, float* out4, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!g || !out4 || !workspace || n <= 0 || (n & 3)) return -1;
+  if (!aligned16(g) || !aligned16(out4) || !aligned16(workspace)) return -3;
+  if (workspace_bytes < fnd_seq_grad_sumsq_workspace(n)) return -4;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int grid = sumsq_grid(n / 4);
+  seq_sumsq_kernel<<<grid, 256, 0, st>>>(g, n / 4, static_cast<float*>(workspace));
+  SEQ_CUDA_OK(cudaGetLastError());
+  seq_reduce_partials_kernel<<<1, 256, 0, st>>>(static_cast<const float*>(workspace), grid, 4, out4);
+  SEQ_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int fnd_seq_adamw_step(float* w, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                       float eps, float weight_decay, int step, float max_norm, float grad_scale, const float* sumsq,
+                       void* stream) {
+  if (!w || !g || !m || !v || !sumsq || n <= 0 || (n & 3) || step < 1) return -1;
+  if (!aligned16(w) || !aligned16(g) || !aligned16(m) || !aligned16(v)) return -3;
+  SeqAdamParams P{w, g, m, v, n / 4, lr, beta1, beta2, eps, weight_decay,
+                  1.f - powf(beta1, static_cast<float>(step)), 1.f - powf(beta2, static_cast<float>(step)), max_norm, grad_scale, sumsq};
+  const long long want = (n / 4 + 255) / 256;
+  const int cap = seq_num_sms() * 8;
+  seq_adamw_kernel<<<want < cap ? static_cast<int>(want) : cap, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(P);
+  SEQ_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 }  // extern "C"

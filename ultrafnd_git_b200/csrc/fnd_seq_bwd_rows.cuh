@@ -284,3 +284,68 @@ __global__ void __launch_bounds__(256) seq_attn_bwd_prep_kernel(const AttnBwdPre
 }
 
 }  // namespace fnd
+
+namespace fnd {
+
+// ---------------------------------------------------------------------------------------------------------------
+// Optimizer step of the sequence front-end over ONE flat fp32 parameter / gradient / moment range (the front-end's own
+// mirror of Tier A's flat-arena AdamW, csrc/fnd_optim.cuh): global-norm clip + decoupled-weight-decay Adam in one pass,
+// 128-bit accesses, 28 B of HBM traffic per parameter. Semantics = torch.nn.utils.clip_grad_norm_(max_norm) followed by
+// torch.optim.AdamW (what the reference's trainer uses for its own parameters, src/training/forensic_trainer.py:173-177,
+// 292-298); there is no reference optimizer for these parameters (the front-end does not exist there).
+// ---------------------------------------------------------------------------------------------------------------
+// part[blockIdx.x * 4] = sum of squares of this CTA's slice (three zero pads keep the 128-bit partial-sum reduction happy)
+__global__ void __launch_bounds__(256) seq_sumsq_kernel(const float* __restrict__ g, long long n4, float* __restrict__ part) {
+  __shared__ float red[8];
+  float s = 0.f;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 v = ldcg_f4(g + 4 * i);
+    s = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, s))));
+  }
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[w];
+    *reinterpret_cast<float4*>(part + 4 * static_cast<size_t>(blockIdx.x)) = make_float4(t, 0.f, 0.f, 0.f);
+  }
+}
+
+struct SeqAdamParams {
+  float* w; const float* g; float* m; float* v;
+  long long n4;                                  // number of float4 groups
+  float lr, beta1, beta2, eps, weight_decay, bc1, bc2, max_norm, grad_scale;
+  const float* sumsq;                            // device scalar: sum of squares of g BEFORE grad_scale
+};
+__global__ void __launch_bounds__(256) seq_adamw_kernel(const SeqAdamParams P) {
+  // clip coefficient of clip_grad_norm_: min(1, max_norm / (||g|| + 1e-6)), with ||g|| of the SCALED gradient
+  const float norm = sqrtf(__ldg(P.sumsq)) * P.grad_scale;
+  const float coef = (P.max_norm > 0.f) ? fminf(1.f, P.max_norm / (norm + 1e-6f)) : 1.f;
+  const float gs = P.grad_scale * coef;
+  const float decay = 1.f - P.lr * P.weight_decay;
+  const float step = P.lr / P.bc1;
+  const float inv_sqrt_bc2 = rsqrtf(P.bc2);
+  const uint64_t pol = l2_policy_evict_first();
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < P.n4; i += stride) {
+    const float4 g4 = ld_f4_policy(P.g + 4 * i, pol);
+    float4 w4 = ld_f4_policy(P.w + 4 * i, pol), m4 = ld_f4_policy(P.m + 4 * i, pol), v4 = ld_f4_policy(P.v + 4 * i, pol);
+    float* wp = &w4.x; float* mp = &m4.x; float* vp = &v4.x; const float* gp = &g4.x;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float gj = gp[j] * gs;
+      mp[j] = fmaf(P.beta1, mp[j], (1.f - P.beta1) * gj);
+      vp[j] = fmaf(P.beta2, vp[j], (1.f - P.beta2) * gj * gj);
+      const float denom = fmaf(sqrtf(vp[j]), inv_sqrt_bc2, P.eps);
+      wp[j] = fmaf(-step, __fdividef(mp[j], denom), wp[j] * decay);
+    }
+    st_f4_policy(P.w + 4 * i, w4, pol);
+    st_f4_policy(P.m + 4 * i, m4, pol);
+    st_f4_policy(P.v + 4 * i, v4, pol);
+  }
+}
+
+}  // namespace fnd

@@ -157,13 +157,17 @@ def coattn_backward(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, o: torch.
                                       _stream(dev)), "fnd_seq_coattn_backward")
 
 
-def layernorm_backward(t: torch.Tensor, dy: torch.Tensor, gamma: torch.Tensor, eps: float = 1e-5):
-    """Returns (dt bf16 [M, d], dgamma fp32 [d], dbeta fp32 [d]) for y = LayerNorm(t)."""
+def layernorm_backward(t: torch.Tensor, dy: torch.Tensor, gamma: torch.Tensor, eps: float = 1e-5,
+                       dgb: Optional[torch.Tensor] = None):
+    """Returns (dt bf16 [M, d], dgamma fp32 [d], dbeta fp32 [d]) for y = LayerNorm(t). ``dgb``: optional contiguous fp32
+    [2, d] destination for (dgamma, dbeta) (a slice of a flat gradient buffer)."""
     dev = _need_cuda(t, dy, gamma)
     t2, dy2 = _as2d(t), _as2d(dy)
     M, d = t2.shape
     dt = torch.empty(M, d, dtype=torch.bfloat16, device=dev)
-    dgb = torch.empty(2, d, dtype=torch.float32, device=dev)
+    if dgb is None:
+        dgb = torch.empty(2, d, dtype=torch.float32, device=dev)
+    assert dgb.is_contiguous() and dgb.dtype == torch.float32 and dgb.numel() == 2 * d
     lib = _lib.load()
     ws = _workspace(lib.fnd_seq_layernorm_backward_workspace(M, d), dev)
     check(lib.fnd_seq_layernorm_backward(t2.data_ptr(), t2.stride(0), dy2.data_ptr(), dy2.stride(0), gamma.data_ptr(),
@@ -172,12 +176,14 @@ def layernorm_backward(t: torch.Tensor, dy: torch.Tensor, gamma: torch.Tensor, e
     return dt, dgb[0], dgb[1]
 
 
-def colsum(x: torch.Tensor) -> torch.Tensor:
+def colsum(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """fp32 column sums of a bf16 matrix (bias gradients)."""
     dev = _need_cuda(x)
     x2 = _as2d(x)
     M, N = x2.shape
-    out = torch.empty(N, dtype=torch.float32, device=dev)
+    if out is None:
+        out = torch.empty(N, dtype=torch.float32, device=dev)
+    assert out.is_contiguous() and out.dtype == torch.float32 and out.numel() == N
     lib = _lib.load()
     ws = _workspace(lib.fnd_seq_colsum_workspace(M, N), dev)
     check(lib.fnd_seq_colsum(x2.data_ptr(), x2.stride(0), M, N, out.data_ptr(), ws.data_ptr(), ws.numel(), _stream(dev)),
@@ -197,7 +203,7 @@ def masked_mean_pool_backward(dpooled: torch.Tensor, B: int, L: int, mask: Optio
     return dx
 
 
-def wgrad(dy: torch.Tensor, x: torch.Tensor, err: Optional[torch.Tensor] = None) -> torch.Tensor:
+def wgrad(dy: torch.Tensor, x: torch.Tensor, err: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """dW[N, K] (fp32) = dy[M, N]^T @ x[M, K] on the persistent tcgen05 GEMM (fnd_seq_wgrad): both operands are read in place
     with the token dimension as the reduction — MN-major descriptors — so nothing is transposed in memory."""
     dev = _need_cuda(dy, x)
@@ -208,8 +214,33 @@ def wgrad(dy: torch.Tensor, x: torch.Tensor, err: Optional[torch.Tensor] = None)
     if N % 8 or K % 8:
         raise NotImplementedError("wgrad needs N and K to be multiples of 8 (16-byte row pitches)")
     lib = _lib.load()
-    out = torch.empty(N, K, dtype=torch.float32, device=dev)
+    if out is None:
+        out = torch.empty(N, K, dtype=torch.float32, device=dev)
+    assert out.is_contiguous() and out.dtype == torch.float32 and tuple(out.shape) == (N, K)
     ws = _workspace(lib.fnd_seq_wgrad_workspace(M, N, K), dev)
     check(lib.fnd_seq_wgrad(dy.data_ptr(), dy.stride(0), x.data_ptr(), x.stride(0), M, N, K, out.data_ptr(), K,
                             ws.data_ptr(), ws.numel(), _ptr(err), _stream(dev)), "fnd_seq_wgrad")
     return out
+
+
+def grad_sumsq(g: torch.Tensor, out4: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out4[0] = sum of squares of the flat fp32 gradient range (fixed-order reduction); stays on the device."""
+    dev = _need_cuda(g)
+    assert g.is_contiguous() and g.dtype == torch.float32 and g.numel() % 4 == 0
+    if out4 is None:
+        out4 = torch.empty(4, dtype=torch.float32, device=dev)
+    lib = _lib.load()
+    ws = _workspace(lib.fnd_seq_grad_sumsq_workspace(g.numel()), dev)
+    check(lib.fnd_seq_grad_sumsq(g.data_ptr(), g.numel(), out4.data_ptr(), ws.data_ptr(), ws.numel(), _stream(dev)), "fnd_seq_grad_sumsq")
+    return out4
+
+
+def adamw_step(w: torch.Tensor, g: torch.Tensor, m: torch.Tensor, v: torch.Tensor, sumsq: torch.Tensor, step: int, lr: float,
+               betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 1e-2, max_norm: float = 0.0, grad_scale: float = 1.0) -> None:
+    """clip_grad_norm_(max_norm) + torch.optim.AdamW semantics over one flat fp32 range, in place (fnd_seq_adamw_step)."""
+    dev = _need_cuda(w, g, m, v, sumsq)
+    n = w.numel()
+    assert all(t.is_contiguous() and t.dtype == torch.float32 and t.numel() == n for t in (w, g, m, v)) and n % 4 == 0
+    check(_lib.load().fnd_seq_adamw_step(w.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), n, float(lr), float(betas[0]),
+                                         float(betas[1]), float(eps), float(weight_decay), int(step), float(max_norm),
+                                         float(grad_scale), sumsq.data_ptr(), _stream(dev)), "fnd_seq_adamw_step")

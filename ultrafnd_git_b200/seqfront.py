@@ -194,8 +194,38 @@ class SequenceFrontEnd(nn.Module):
         return out
 
     # ------------------------------------------------------------------ backward (called by _SeqFrontFn)
+    def grad_order(self) -> List[Tuple[str, ...]]:
+        """Parameter names in the order the backward pass PRODUCES their gradients, grouped into buckets (heads, then the
+        blocks from last to first, then the embeddings): a flat gradient buffer laid out this way lets a data-parallel
+        trainer all-reduce each bucket as one contiguous range while the rest of the backward is still running.
+        LayerNorm (weight, bias) pairs are adjacent: their gradients are reduced as one 2d-wide row."""
+        buckets: List[Tuple[str, ...]] = []
+        heads: List[str] = []
+        for name in self.streams:
+            heads += [f"head.{name}.weight", f"head.{name}.bias"]
+        buckets.append(tuple(heads))
+        for i in reversed(range(len(self.block_pairs))):
+            b: List[str] = []
+            for side in ("a", "b"):
+                pre = f"blocks.{i}.{side}"
+                b += [pre + ".ln.weight", pre + ".ln.bias", pre + ".out_proj.bias", pre + ".out_proj.weight"]
+            for side in ("a", "b"):
+                pre = f"blocks.{i}.{side}"
+                b += [pre + ".in_proj.bias", pre + ".in_proj.weight"]
+            buckets.append(tuple(b))
+        emb: List[str] = []
+        for name in self.streams:
+            emb += [f"embed_ln.{name}.weight", f"embed_ln.{name}.bias", f"embed.{name}.bias", f"embed.{name}.weight"]
+        buckets.append(tuple(emb))
+        return buckets
+
     def _backward_impl(self, saved: dict, douts: Dict[str, Optional[torch.Tensor]]) -> Dict[str, torch.Tensor]:
-        """Parameter gradients (fp32, keyed like named_parameters()) from the gradients of the head outputs."""
+        """Parameter gradients (fp32, keyed like named_parameters()) from the gradients of the head outputs. With a gradient
+        sink attached (``SequenceTrainer``) every gradient is written straight into the sink's flat buffer and the sink is
+        told when a bucket of ``grad_order()`` is complete."""
+        sink = getattr(self, "_grad_sink", None)
+        dst = (lambda k: sink.grad_view(k)) if sink is not None else (lambda k: None)
+        done = (lambda i: sink.bucket_done(i)) if sink is not None else (lambda i: None)
         err = self._err
         d, H = self.d_model, self.heads
         shape, mask_u8, length = saved["shape"], saved["mask_u8"], saved["length"]
@@ -209,22 +239,23 @@ class SequenceFrontEnd(nn.Module):
             if dy is None:
                 dy = torch.zeros(B, dout, dtype=torch.float32, device=dev)
             dyb = S.cast_bf16(dy.contiguous().float()) if (B * dout) % 8 == 0 else dy.to(bf).contiguous()
-            grads[f"head.{name}.weight"] = S.wgrad(dyb, saved[f"pooled.{name}"], err=err)
-            grads[f"head.{name}.bias"] = S.colsum(dyb)
+            grads[f"head.{name}.weight"] = S.wgrad(dyb, saved[f"pooled.{name}"], err=err, out=dst(f"head.{name}.weight"))
+            grads[f"head.{name}.bias"] = S.colsum(dyb, out=dst(f"head.{name}.bias"))
             dpooled = torch.empty(B, d, dtype=torch.float32, device=dev)
             S.linear(dyb, self._weight_t(f"head.{name}.weight"), None, out_f32=dpooled, want_bf16=False, err=err)
             dX[name] = S.masked_mean_pool_backward(dpooled, B, L, mask=mask_u8[name], length=length[name])
-        for i in reversed(range(len(self.block_pairs))):
+        done(0)
+        for bi, i in enumerate(reversed(range(len(self.block_pairs)))):
             a, b = self.block_pairs[i]
             blk, sv = self.blocks[i], saved[f"blk.{i}"]
             (Ba, La), (Bb, Lb) = shape[a], shape[b]
             dy_side, datt = {}, {}
             for side, st, mod in (("a", a, blk.a), ("b", b, blk.b)):
                 pre = f"blocks.{i}.{side}"
-                dyv, dg, db = S.layernorm_backward(sv["y" + side], dX[st], mod.ln.weight, self.eps)
+                dyv, dg, db = S.layernorm_backward(sv["y" + side], dX[st], mod.ln.weight, self.eps, dgb=dst(pre + ".ln"))
                 grads[pre + ".ln.weight"], grads[pre + ".ln.bias"] = dg, db
-                grads[pre + ".out_proj.bias"] = S.colsum(dyv)
-                grads[pre + ".out_proj.weight"] = S.wgrad(dyv, sv["att_" + side], err=err)
+                grads[pre + ".out_proj.bias"] = S.colsum(dyv, out=dst(pre + ".out_proj.bias"))
+                grads[pre + ".out_proj.weight"] = S.wgrad(dyv, sv["att_" + side], err=err, out=dst(pre + ".out_proj.weight"))
                 datt[side] = S.linear(dyv, self._weight_t(pre + ".out_proj.weight"), None, err=err)
                 dy_side[side] = dyv
             dqkv_a = torch.empty(Ba * La, 3 * d, dtype=bf, device=dev)
@@ -238,15 +269,18 @@ class SequenceFrontEnd(nn.Module):
                               kv_len=length[a], kv_mask=mask_u8[a], err=err)
             for side, st, dq in (("a", a, dqkv_a), ("b", b, dqkv_b)):
                 pre = f"blocks.{i}.{side}"
-                grads[pre + ".in_proj.bias"] = S.colsum(dq)
-                grads[pre + ".in_proj.weight"] = S.wgrad(dq, sv["x" + side], err=err)
+                grads[pre + ".in_proj.bias"] = S.colsum(dq, out=dst(pre + ".in_proj.bias"))
+                grads[pre + ".in_proj.weight"] = S.wgrad(dq, sv["x" + side], err=err, out=dst(pre + ".in_proj.weight"))
                 # dX = d[QKV] W_in + (residual branch: the LayerNorm input gradient)
                 dX[st] = S.linear(dq, self._weight_t(pre + ".in_proj.weight"), None, resid=dy_side[side], err=err)
+            done(1 + bi)
         for name in self.streams:
-            dpre, dg, db = S.layernorm_backward(saved[f"pre.{name}"], dX[name], self.embed_ln[name].weight, self.eps)
+            dpre, dg, db = S.layernorm_backward(saved[f"pre.{name}"], dX[name], self.embed_ln[name].weight, self.eps,
+                                                dgb=dst(f"embed_ln.{name}"))
             grads[f"embed_ln.{name}.weight"], grads[f"embed_ln.{name}.bias"] = dg, db
-            grads[f"embed.{name}.bias"] = S.colsum(dpre)
-            grads[f"embed.{name}.weight"] = S.wgrad(dpre, saved[f"x.{name}"], err=err)
+            grads[f"embed.{name}.bias"] = S.colsum(dpre, out=dst(f"embed.{name}.bias"))
+            grads[f"embed.{name}.weight"] = S.wgrad(dpre, saved[f"x.{name}"], err=err, out=dst(f"embed.{name}.weight"))
+        done(1 + len(self.block_pairs))
         return grads
 
     def forward_features(self, feats: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
@@ -299,3 +333,100 @@ class _SeqFrontFn(torch.autograd.Function):
             grads = module._backward_impl(ctx.saved, {n: g for n, g in zip(ctx.names, douts)})
         ctx.saved = None
         return (None, None) + tuple(grads.get(k) for k in ctx.pnames)
+
+
+class SequenceTrainer:
+    """Optimizer + data-parallel gradient exchange for a ``SequenceFrontEnd`` (self-oracle scope like the module itself).
+
+    Parameters, gradients and both Adam moments live in ONE flat fp32 buffer each, laid out in the order the backward pass
+    produces the gradients (``SequenceFrontEnd.grad_order``): the module's ``nn.Parameter``s are re-pointed at views of the
+    flat parameter buffer, the backward kernels write their results straight into the flat gradient buffer, and the step is
+    two launches over the whole range (fixed-order gradient norm; clip + AdamW, ``fnd_seq_adamw_step``) — the same shape as
+    Tier A's flat-arena optimizer. Data parallel (one process per GPU, batch sharded by rank): each bucket of the flat
+    gradient (heads | block N-1 | ... | block 0 | embeddings) is handed to an NCCL all-reduce THE MOMENT the backward has
+    finished writing it (async on NCCL's own stream), so the exchange of everything but the last bucket runs under the
+    rest of the backward — north_star's "NCCL gradient allreduce overlapped with backward", here for the parameters the
+    reference does not have. The sum is divided by the world size inside the optimizer kernel.
+    Semantics: ``torch.nn.utils.clip_grad_norm_(max_norm)`` + ``torch.optim.AdamW`` (what the reference's trainer applies to
+    its own parameters, src/training/forensic_trainer.py:173-177,292-298); checked against exactly those two torch calls."""
+
+    def __init__(self, frontend: SequenceFrontEnd, lr: float = 3e-4, betas: Tuple[float, float] = (0.9, 0.999), eps: float = 1e-8,
+                 weight_decay: float = 1e-2, max_norm: float = 5.0, process_group=None):
+        self.fe = frontend
+        self.lr, self.betas, self.eps, self.weight_decay, self.max_norm = lr, betas, eps, weight_decay, max_norm
+        self.group = process_group
+        self.world = 1
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            self.world = torch.distributed.get_world_size(process_group)
+        params = dict(frontend.named_parameters())
+        dev = next(iter(params.values())).device
+        if dev.type != "cuda":
+            raise RuntimeError("SequenceTrainer needs the module on a CUDA device: no CPU fallback exists")
+        self.buckets = frontend.grad_order()
+        self.offset: Dict[str, Tuple[int, int]] = {}
+        self.bucket_range: List[Tuple[int, int]] = []
+        off = 0
+        for names in self.buckets:
+            start = off
+            for k in names:
+                n = params[k].numel()
+                if n % 4:
+                    raise NotImplementedError(f"{k}: parameter sizes must be multiples of 4 (16-byte aligned flat views)")
+                self.offset[k] = (off, n)
+                off += n
+            self.bucket_range.append((start, off))
+        missing = set(params) - set(self.offset)
+        assert not missing, missing
+        self.n = off
+        self.flat_w = torch.empty(off, dtype=torch.float32, device=dev)
+        self.flat_g = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.m = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.v = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.sumsq = torch.zeros(4, dtype=torch.float32, device=dev)
+        with torch.no_grad():
+            for k, p in params.items():
+                o, n = self.offset[k]
+                self.flat_w[o:o + n].copy_(p.detach().reshape(-1))
+                p.data = self.flat_w[o:o + n].view(p.shape)
+        if self.world > 1:                         # identical replicas: rank 0's parameters everywhere
+            torch.distributed.broadcast(self.flat_w, src=0, group=process_group)
+        frontend._shadow_version = None
+        frontend._grad_sink = self
+        self.step_count = 0
+        self._works: List = []
+        self._shapes = {k: tuple(v.shape) for k, v in params.items()}
+
+    # ---- gradient sink interface (called from SequenceFrontEnd._backward_impl)
+    def grad_view(self, key: str) -> torch.Tensor:
+        """Destination of one gradient inside the flat buffer; "<prefix>.ln" / "embed_ln.<stream>" name a LayerNorm's
+        (gamma, beta) pair as one [2, d] row pair."""
+        if key + ".weight" in self.offset and key + ".bias" in self.offset and key not in self.offset:
+            o, n = self.offset[key + ".weight"]
+            assert self.offset[key + ".bias"][0] == o + n
+            return self.flat_g[o:o + 2 * n].view(2, n)
+        o, n = self.offset[key]
+        return self.flat_g[o:o + n].view(self._shapes[key])
+
+    def bucket_done(self, i: int) -> None:
+        if self.world > 1:
+            a, b = self.bucket_range[i]
+            self._works.append(torch.distributed.all_reduce(self.flat_g[a:b], group=self.group, async_op=True))
+
+    # ---- one optimizer step over the flat range (call after loss.backward())
+    def step(self) -> None:
+        for w in self._works:
+            w.wait()                               # the current stream waits for the bucket all-reduces; the host does not
+        self._works = []
+        self.step_count += 1
+        S.grad_sumsq(self.flat_g, self.sumsq)
+        S.adamw_step(self.flat_w, self.flat_g, self.m, self.v, self.sumsq, self.step_count, self.lr, self.betas, self.eps,
+                     self.weight_decay, self.max_norm, 1.0 / self.world)
+        self.fe._shadow_version = None             # the bf16 operand copies are stale now
+
+    def zero_grad(self) -> None:
+        for p in self.fe.parameters():
+            p.grad = None
+
+    def grad_norm(self) -> float:
+        """Global gradient norm the last step() clipped against (reads the device scalar: synchronises)."""
+        return float(self.sumsq[0].sqrt().item()) / self.world
