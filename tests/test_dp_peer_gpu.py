@@ -31,3 +31,14 @@ def test_dp_trainer_two_gpus():
     r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600)
     print(r.stdout[-3000:], r.stderr[-3000:])
     assert r.returncode == 0
+
+
+def test_dp_sequence_trainer_two_gpus():
+    """Sequence front-end (Tier B, self-oracle scope): 2-rank SequenceTrainer vs a single-GPU replica on the whole batch."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run under gpurun --gpus 2)")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29523", os.path.join(ROOT, "tests", "dp_seq_check.py")]
+    r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600)
+    print(r.stdout[-3000:], r.stderr[-3000:])
+    assert r.returncode == 0

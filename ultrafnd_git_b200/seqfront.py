@@ -351,12 +351,14 @@ class SequenceTrainer:
     its own parameters, src/training/forensic_trainer.py:173-177,292-298); checked against exactly those two torch calls."""
 
     def __init__(self, frontend: SequenceFrontEnd, lr: float = 3e-4, betas: Tuple[float, float] = (0.9, 0.999), eps: float = 1e-8,
-                 weight_decay: float = 1e-2, max_norm: float = 5.0, process_group=None):
+                 weight_decay: float = 1e-2, max_norm: float = 5.0, process_group=None, world: Optional[int] = None):
         self.fe = frontend
         self.lr, self.betas, self.eps, self.weight_decay, self.max_norm = lr, betas, eps, weight_decay, max_norm
         self.group = process_group
         self.world = 1
-        if torch.distributed.is_available() and torch.distributed.is_initialized():
+        if world is not None:
+            self.world = int(world)                # world=1 inside an initialised process group: a local, un-exchanged replica
+        elif torch.distributed.is_available() and torch.distributed.is_initialized():
             self.world = torch.distributed.get_world_size(process_group)
         params = dict(frontend.named_parameters())
         dev = next(iter(params.values())).device
