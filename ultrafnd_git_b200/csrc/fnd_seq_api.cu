@@ -391,6 +391,8 @@ int fnd_seq_coattn_backward(const void* q_bf16, int q_pitch, int q_col0, const v
   P.scale = scale; P.scale_log2 = scale * 1.44269504088896340736f;
   P.lse2p = lse2p; P.Dp = Dp;
   P.err = err_flag;
+  P.pingpong = kAttnBwdDefaultPingPong;
+  if (const char* e = getenv("FND_ATTN_BWD_PINGPONG")) P.pingpong = atoi(e) != 0;
   int r;
   // ---- dQ: resident Q / dO tiles (128 rows), streamed K / V blocks (64 rows) ----
   if ((r = encode_bf16_3d(&P.tmR0, q_bf16, static_cast<uint64_t>(q_pitch), Lq, B, q_pitch, kAttnBQ))) return r;

@@ -26,6 +26,7 @@ constexpr int kBwdTileBytes = kAttnBQ * kAttnD * 2;      // 16 KB: a resident 12
 constexpr int kBwdBlkBytes = kBwdBlk * kAttnD * 2;       // 8 KB: a streamed 64 x 64 tile
 constexpr int kBwdStageBytes = 2 * kBwdBlkBytes + 1024;  // two streamed tiles + 64 lse2 + 64 D values (dK/dV kernel); 1024-aligned for SWIZZLE_128B
 constexpr int kBwdSmemBytes = 1024 + 1024 + 2 * 4 * kBwdTileBytes + kBwdStages * kBwdStageBytes;
+constexpr int kAttnBwdDefaultPingPong = 1;              // FND_ATTN_BWD_PINGPONG overrides
 constexpr int kBwdTmemS = 0, kBwdTmemDP = 128, kBwdTmemAcc0 = 256, kBwdTmemAcc1 = 384;
 
 struct alignas(64) AttnBwdParams {
@@ -42,6 +43,7 @@ struct alignas(64) AttnBwdParams {
   __nv_bfloat16* out0; int out0_pitch; int out0_col0;   // dQ | dK
   __nv_bfloat16* out1; int out1_pitch; int out1_col0;   // -  | dV
   int* err;
+  int pingpong;                              // 1: the two warpgroups take turns in the exp2 section (as in the forward kernel)
 };
 
 __device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
@@ -271,6 +273,8 @@ __global__ void __launch_bounds__(kAttnThreads, 1) seq_attn_bwd_kernel(const __g
     const uint32_t sS_s = smem_u32(sS);
     bool ok = true;
     uint32_t g = 0, ip = 0;
+    const bool pingpong = P.pingpong != 0;       // exp2-section token, see fnd_seq_attn.cuh
+    if (pingpong && t == 1) named_bar_arrive(1, 256);
 #pragma unroll 1
     for (int w = blockIdx.x; w < nwork; w += gridDim.x) {
       const int rt = w % nrt, h = (w / nrt) % P.H, b = w / (nrt * P.H);
@@ -308,6 +312,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) seq_attn_bwd_kernel(const __g
         tmem_ld_32x32(tD + 32, reinterpret_cast<uint32_t(&)[32]>(dp[32]));
         tmem_ld_wait();
         uint32_t pk[kBwdBlk / 2], dk[kBwdBlk / 2];
+        if (pingpong) named_bar_sync(1 + t, 256);
         if (kDkv) {
           // columns = the block's 64 queries: lse2 / D per column from the ring stage (broadcast 128-bit loads)
           const uint32_t stat = sS_s + stage * kBwdStageBytes + 2 * kBwdBlkBytes;
@@ -355,6 +360,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) seq_attn_bwd_kernel(const __g
           }
           tmem_st_32x32(tS, dk);                                 // dS over this row of S
         }
+        if (pingpong) named_bar_arrive(2 - t, 256);
         tmem_st_wait();
         tc_fence_before_sync();
         __syncwarp();
@@ -410,6 +416,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) seq_attn_bwd_kernel(const __g
         }
       }
     }
+    if (pingpong && t == 0) named_bar_sync(1, 256);
   }
 
   tc_fence_before_sync();
