@@ -131,7 +131,7 @@ int fnd_seq_layernorm(const void* x_bf16, int x_pitch, const void* resid_bf16, i
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   // resident warps walk the row list (gamma / beta stay in registers): a few waves of CTAs, never more than the rows need
   const int want = cdiv(M, 8);
-  const int cap = seq_num_sms() * (d <= 512 ? 4 : 2);
+  const int cap = seq_num_sms() * (d <= 1024 ? 4 : 2);
   const int grid = want < cap ? want : cap;
   if (d <= 256) seq_layernorm_kernel<1><<<grid, 256, 0, st>>>(P);
   else if (d <= 512) seq_layernorm_kernel<2><<<grid, 256, 0, st>>>(P);
