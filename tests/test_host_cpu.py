@@ -206,3 +206,29 @@ def test_dp_shard_ranges_partition_the_hot_arena():
             assert lib.fnd_dp_stage_bytes(h, world, 0) >= 4 * n_hot and lib.fnd_dp_stage_bytes(h, world, 1) * 2 == lib.fnd_dp_stage_bytes(h, world, 0)
     finally:
         lib.fnd_plan_destroy(h)
+
+
+def test_sequence_frontend_host_logic_and_no_cpu_fallback():
+    """Tier B host side (no GPU): parameter names equal the self-oracle's, the gradient production order covers every
+    parameter exactly once with LayerNorm (weight, bias) pairs adjacent (the backward reduces them as one row pair), and
+    both the module and its trainer refuse to compute on the CPU (no fallback)."""
+    from oracle import seq_oracle as SO
+    from ultrafnd_git_b200.seqfront import SequenceFrontEnd, SequenceTrainer
+    fe = SequenceFrontEnd(128, 2)
+    names = [k for k, _ in fe.named_parameters()]
+    shapes = SO.param_shapes(SO.FAKESV_STREAMS, SO.FAKESV_BLOCKS, 128)
+    assert sorted(names) == sorted(shapes) and all(tuple(dict(fe.named_parameters())[k].shape) == shapes[k] for k in names)
+    order = [k for bucket in fe.grad_order() for k in bucket]
+    assert sorted(order) == sorted(names) and len(set(order)) == len(order)
+    assert len(fe.grad_order()) == 2 + len(fe.block_pairs)                # heads | one bucket per block | embeddings
+    for i, k in enumerate(order):
+        if (".ln." in k or k.startswith("embed_ln.")) and k.endswith(".weight"):
+            assert order[i + 1] == k[:-len("weight")] + "bias", (k, order[i + 1])
+    assert all(dict(fe.named_parameters())[k].numel() % 4 == 0 for k in names)      # 16-byte aligned flat views
+    batch = SO.make_batch(SO.FAKESV_STREAMS, {"text": 8, "frames": 8, "audio": 8, "c3d": 8}, 2)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        fe(batch)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        SequenceTrainer(fe)
+    with pytest.raises(NotImplementedError):
+        SequenceFrontEnd(100, 2)                                           # head dimension must be 64
