@@ -158,6 +158,8 @@ int fnd_seq_coattn_forward(const void* q_bf16, int q_pitch, int q_col0, const vo
   if (r) return r;
   r = encode_bf16_3d(&P.tmV, v_bf16, static_cast<uint64_t>(v_pitch), Lk, B, v_pitch, kAttnBK);
   if (r) return r;
+  r = encode_bf16_3d(&P.tmO, out_bf16, static_cast<uint64_t>(H) * kAttnD, Lq, B, out_pitch, kAttnBQ);
+  if (r) return r;
   P.B = B; P.H = H; P.Lq = Lq; P.Lk = Lk;
   P.q_col0 = q_col0; P.k_col0 = k_col0; P.v_col0 = v_col0;
   P.kv_len = kv_len; P.kv_mask = kv_mask;

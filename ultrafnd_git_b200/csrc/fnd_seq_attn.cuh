@@ -41,7 +41,8 @@ constexpr int kAttnThreads = 384;            // warps 0..7 softmax (two warpgrou
 constexpr int kAttnTmemCols = 512;
 constexpr int kAttnQBytes = kAttnBQ * kAttnD * 2;        // 16 KB per tile
 constexpr int kAttnKBytes = kAttnBK * kAttnD * 2;        // 16 KB
-constexpr int kAttnSmemBytes = 1024 /*align*/ + 1024 /*barriers*/ + 2 * 2 * kAttnQBytes + kAttnStages * 2 * kAttnKBytes;
+constexpr int kAttnOutBytes = kAttnBQ * kAttnD * 2;      // 16 KB: one 128 x 64 bf16 output tile staged for its TMA store
+constexpr int kAttnSmemBytes = 1024 /*align*/ + 1024 /*barriers*/ + 2 * 2 * kAttnQBytes + kAttnStages * 2 * kAttnKBytes + 2 * kAttnOutBytes;
 constexpr int kAttnTmemS = 0, kAttnTmemO = 256, kAttnTmemP = 384;
 constexpr float kAttnLazyLog2 = 8.f;         // rescale only when the row maximum grew by more than this (log2 units)
 constexpr int kAttnDefaultPoly = 0;           // FND_ATTN_POLY overrides (0..3 of every 4 pairs on the FMA pipe)
@@ -50,6 +51,7 @@ constexpr int kAttnDefaultPingPong = 1;       // FND_ATTN_PINGPONG overrides
 
 struct alignas(64) AttnParams {
   CUtensorMap tmQ, tmK, tmV;                 // 3-D [batch][rows][cols] maps (fnd_tmap.h: encode_bf16_3d), box 64 x 128 x 1
+  CUtensorMap tmO;                           // the output the same way: rows >= Lq of a tile are clipped by the store
   int B, H, Lq, Lk;
   int q_col0, k_col0, v_col0;                // first column of head 0 inside the Q / K / V matrices
   const int* kv_len;                         // [B] valid prefix length of the key sequence, or null (= Lk)
@@ -184,6 +186,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) seq_attn_fwd_kernel(const __g
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_free + 2);
   uint8_t* sQ = smem + 1024;                                 // [2 buffers][2 tiles][128 x 64]
   uint8_t* sKV = sQ + 2 * 2 * kAttnQBytes;                   // [stages][K | V]
+  uint8_t* sOut = sKV + kAttnStages * 2 * kAttnKBytes;       // [2 tiles][128 x 64 bf16, SWIZZLE_128B]: output staging
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // Work items w = (sample, head, 256-query tile), query tile fastest: the CTAs running at the same time read the same
@@ -202,6 +205,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) seq_attn_fwd_kernel(const __g
     tma_prefetch_desc(&P.tmQ);
     tma_prefetch_desc(&P.tmK);
     tma_prefetch_desc(&P.tmV);
+    tma_prefetch_desc(&P.tmO);
   }
   if (warp == 9) {
     if (lane == 0) {
@@ -482,11 +486,14 @@ __global__ void __launch_bounds__(kAttnThreads, 1) seq_attn_fwd_kernel(const __g
         if (lane == 0) mbar_arrive(&p_full[t]);
       }
 
-      // ---- item epilogue: O / l -> bf16 -> global (one 128-byte row segment per thread) ----
+      // ---- item epilogue: O / l -> bf16 -> swizzled shared-memory tile -> ONE TMA store per tile. (Row stores straight
+      //      from registers made every warp-level store touch 32 different 128-byte lines: 256 LSU wavefronts per warp and
+      //      item, ~11 % of the softmax warps' time in ncu.) Rows past Lq are clipped by the tensor map. ----
+      uint32_t r[kAttnD];
+      float inv = 0.f;
       if (nblk > 0) {
         ok = ok && mbar_wait_fast(&o_full[t], ip & 1u, P.err, FND_DEV_TIMEOUT_EPILOGUE);
         tc_fence_after_sync();
-        uint32_t r[kAttnD];
         tmem_ld_32x32(tO, reinterpret_cast<uint32_t(&)[32]>(r[0]));
         tmem_ld_32x32(tO + 32, reinterpret_cast<uint32_t(&)[32]>(r[32]));
         tmem_ld_wait();
@@ -494,27 +501,33 @@ __global__ void __launch_bounds__(kAttnThreads, 1) seq_attn_fwd_kernel(const __g
         __syncwarp();
         if (lane == 0) mbar_arrive(&o_free[t]);
         ++ip;
-        if (qi < P.Lq) {
-          const float inv = (ok && l_run > 0.f) ? __fdividef(1.f, l_run) : 0.f;
-          __nv_bfloat16* op = P.out + (static_cast<size_t>(b) * P.Lq + qi) * P.out_pitch + h * kAttnD;
+        inv = (ok && l_run > 0.f) ? __fdividef(1.f, l_run) : 0.f;
+      } else {
 #pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            float o[8];
+        for (int i = 0; i < kAttnD; ++i) r[i] = 0u;       // no valid key at all: zeros
+      }
+      uint8_t* stg = sOut + t * kAttnOutBytes;
+      if (qd == 0 && lane == 0) tma_store_wait_read<0>();    // this tile's previous store has drained the staging buffer
+      named_bar_sync(3 + t, 128);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) o[i] = __uint_as_float(r[8 * c + i]) * inv;
-            *reinterpret_cast<uint4*>(op + 8 * c) = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]),
-                                                               pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
-          }
-        }
-      } else if (qi < P.Lq) {
-        __nv_bfloat16* op = P.out + (static_cast<size_t>(b) * P.Lq + qi) * P.out_pitch + h * kAttnD;
+      for (int c = 0; c < 8; ++c) {
+        float o[8];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(op + 8 * c) = make_uint4(0u, 0u, 0u, 0u);
+        for (int i = 0; i < 8; ++i) o[i] = __uint_as_float(r[8 * c + i]) * inv;
+        *reinterpret_cast<uint4*>(stg + row * 128 + ((c ^ (row & 7)) << 4)) =
+            make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+      }
+      fence_proxy_async_smem();
+      named_bar_sync(3 + t, 128);
+      if (qd == 0 && lane == 0) {
+        tma_store_3d(&P.tmO, stg, h * kAttnD, qt * kAttnItemQ + t * kAttnBQ, b);
+        tma_store_commit();
       }
       if (P.lse && qi < P.Lq)
         P.lse[(static_cast<size_t>(b) * P.H + h) * P.Lq + qi] = (l_run > 0.f) ? fmaf(m_run, 0.69314718055994531f, __logf(l_run)) : -INFINITY;
     }
     if (pingpong && t == 0) named_bar_sync(1, 256);
+    if (qd == 0 && lane == 0) tma_store_wait<0>();           // every output tile written before the CTA retires
   }
 
   tc_fence_before_sync();
