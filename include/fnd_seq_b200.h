@@ -58,8 +58,13 @@ int fnd_seq_coattn_forward(const void* q_bf16, int q_pitch, int q_col0, const vo
 int fnd_seq_masked_mean_pool(const void* x_bf16, int x_pitch, const unsigned char* mask, const int* len, int B, int L,
                              int d, float* out_f32, int f32_pitch, void* out_bf16, int bf_pitch, void* stream);
 
-/* Reserved probe hook (round-2 phase-stamp builds of the attention kernel used it; profiles/r02_attn_phase_stamps.txt).
- * The production kernel carries no instrumentation: the call is accepted and ignored. */
+/* Probe aid (tools/attn_stamps.py): while `stamps` is non-NULL, fnd_seq_coattn_forward records clock64() event stamps of
+ * its pipeline into stamps[(cta * 32 + step) * 16 + event] for the first 32 key-block steps of every CTA: softmax
+ * warpgroup t sees S (0 + 4t), holds S in registers (1 + 4t), enters the exp2 section (2 + 4t), publishes P (3 + 4t);
+ * the tile's MMA warp sees P (8 + 4t), has issued P V (9 + 4t), has issued the next Q K^T (10 + 4t). `stamps` must hold
+ * 16 * 32 * (number of SMs) entries. NULL (the default) disables it: the production path pays one predicate per event.
+ * FND_ATTN_DBG_NOEXP=1 additionally skips the exponentials (P = 0) to expose the pure pipeline latency. Not for use
+ * around graph capture. */
 int fnd_seq_debug_attn_stamps(long long* stamps);
 
 /* ------------------------------------------------------------------------------------------------------------------

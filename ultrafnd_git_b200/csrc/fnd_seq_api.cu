@@ -179,6 +179,8 @@ int fnd_seq_coattn_forward(const void* q_bf16, int q_pitch, int q_col0, const vo
   P.skew_ns = skew;
   P.pingpong = kAttnDefaultPingPong;
   if (const char* e = getenv("FND_ATTN_PINGPONG")) P.pingpong = atoi(e) != 0;
+  if (const char* e = getenv("FND_ATTN_DBG_NOEXP")) P.dbg_noexp = atoi(e) != 0;
+  P.dbg = g_attn_stamps;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   switch (poly) {
     case 0: seq_attn_fwd_kernel<0><<<grid, kAttnThreads, kAttnSmemBytes, st>>>(P); break;

@@ -13,17 +13,22 @@
 //   warps 4..7   the same for tile 1
 //   warp  8      TMA producer: the item's two Q tiles (double-buffered across items), then K_j / V_j (SWIZZLE_128B,
 //                3-D maps: rows past the sequence end of THIS sample are zero-filled) through a 3-stage ring
-//   warp  9      one elected thread issues tcgen05.mma: S_t = Q_t K_j^T (128x128x64) and O_t (+)= P_t V_j (128x64x128,
-//                A from TMEM, V MN-major), interleaved  PV_0(j) QK_0(j+1) PV_1(j) QK_1(j+1)  across item boundaries
-//   warps 10,11  idle (they complete the third warpgroup, which hands its registers to the softmax warpgroups)
+//   warps 9, 10  MMA issuers, ONE PER TILE (an elected thread each): S_t = Q_t K_j^T (128x128x64) and O_t (+)= P_t V_j
+//                (128x64x128, A from TMEM, V MN-major). Each warp follows its own tile's events with blocking waits —
+//                s_free_t(j) -> S_t(j+1),  p_full_t(j) -> P_t V(j) — so the tiles never wait for each other's turn in an
+//                issuing warp; the shared K / V / Q buffers are released by one tcgen05.commit arrival from each warp
+//   warp  11     idle (completes the third warpgroup, which hands its registers to the softmax warpgroups)
 // O accumulates in TMEM (the MMA's own accumulate flag). The running maximum is updated LAZILY: only when a row's new
 // maximum exceeds the one in use by more than 8 (log2 units) does the warp rescale its O rows in TMEM (tcgen05.ld / mul /
-// tcgen05.st between two MMAs that are ordered by the barriers anyway); otherwise the stale maximum stays — the
-// probabilities are then at most 2^8, harmless in bf16 / fp32, and the final normalisation and LSE are exact either way.
-// No barrier is needed for "S consumed" or "P consumed": QK_t(j+1) is issued after PV_t(j), whose issue waited for P_t(j),
-// which the softmax thread publishes after reading S_t(j); and s_full_t(j+1) implies PV_t(j) has retired (commit covers
-// all earlier MMAs). TMEM: S 2 x 128, O 2 x 64, P 2 x 64 (bf16 pairs) = 512 columns; shared memory 2 x 32 KB Q +
-// 3 x (16 + 16) KB K / V. A query row with no valid key yields zeros (LSE = -inf).
+// tcgen05.st); otherwise the stale maximum stays — the probabilities are then at most 2^8, harmless in bf16 / fp32, and
+// the final normalisation and LSE are exact either way.
+// S_t(j+1) is issued as soon as the softmax threads HOLD S_t(j) in registers (s_free), a whole softmax block before they
+// need it, so Q K^T (issue + execution + two barrier hops: ~1100 cycles by the event stamps, tools/attn_stamps.py) is off
+// their critical path; pv_done_t orders "P_t V(j) retired" before P_t / O_t are written for block j+1. Every wait except
+// the critical one is done ahead of time (an mbarrier try_wait costs ~90 cycles even on a completed phase). The two
+// warpgroups take turns in the MUFU-bound exp2 section (named-barrier token). TMEM: S 2 x 128, O 2 x 64, P 2 x 64 (bf16
+// pairs) = 512 columns; shared memory 2 x 32 KB Q + 3 x (16 + 16) KB K / V + 2 x 16 KB output staging. A query row with
+// no valid key yields zeros (LSE = -inf).
 //
 // No counterpart in the reference (the reference's "co-attention" is a per-sample sigmoid gate,
 // src/models/fusion/cross_modal_transformer.py:39-55); checked against the self-oracle oracle/seq_oracle.py.
@@ -37,7 +42,7 @@ constexpr int kAttnItemQ = 256;              // query rows per work item (two ti
 constexpr int kAttnBK = 128;                 // keys per block
 constexpr int kAttnD = 64;                   // head dimension
 constexpr int kAttnStages = 3;
-constexpr int kAttnThreads = 384;            // warps 0..7 softmax (two warpgroups), 8 TMA, 9 MMA + TMEM owner, 10..11 idle
+constexpr int kAttnThreads = 384;            // warps 0..7 softmax (two warpgroups), 8 TMA, 9 / 10 MMA (one per tile; 9 owns TMEM), 11 idle
 constexpr int kAttnTmemCols = 512;
 constexpr int kAttnQBytes = kAttnBQ * kAttnD * 2;        // 16 KB per tile
 constexpr int kAttnKBytes = kAttnBK * kAttnD * 2;        // 16 KB
@@ -64,7 +69,10 @@ struct alignas(64) AttnParams {
   int* err;
   int skew_ns;                               // start-up delay of softmax warpgroup 1 (experiment knob)
   int pingpong;                              // 1: the two softmax warpgroups take turns in the exp2 phase (named barriers)
+  int dbg_noexp;                             // probe: skip the exponentials (P = 0) to expose the pure pipeline latency
+  long long* dbg;                            // probe: [grid][32 steps][16 events] clock64 stamps (fnd_seq_debug_attn_stamps)
 };
+#define ATTN_EV(step, ev) do { if (P.dbg && (step) < 32u) P.dbg[(static_cast<size_t>(blockIdx.x) * 32 + (step)) * 16 + (ev)] = clock64(); } while (0)
 
 // packed fp32 pairs (sm_100: FFMA2 / FADD2 / FMUL2 issue two fp32 operations per instruction) and the 3-input maximum
 __device__ __forceinline__ uint64_t pack_f32x2(float a, float b) {
@@ -183,7 +191,9 @@ __global__ void __launch_bounds__(kAttnThreads, 1) seq_attn_fwd_kernel(const __g
   uint64_t* p_full = s_full + 2;
   uint64_t* o_full = p_full + 2;
   uint64_t* o_free = o_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_free + 2);
+  uint64_t* s_free = o_free + 2;                             // [2]: the softmax threads hold S_t in registers
+  uint64_t* pv_done = s_free + 2;                            // [2]: P_t V of the previous block has retired (P_t / O_t may be written)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
   uint8_t* sQ = smem + 1024;                                 // [2 buffers][2 tiles][128 x 64]
   uint8_t* sKV = sQ + 2 * 2 * kAttnQBytes;                   // [stages][K | V]
   uint8_t* sOut = sKV + kAttnStages * 2 * kAttnKBytes;       // [2 tiles][128 x 64 bf16, SWIZZLE_128B]: output staging
@@ -209,16 +219,18 @@ __global__ void __launch_bounds__(kAttnThreads, 1) seq_attn_fwd_kernel(const __g
   }
   if (warp == 9) {
     if (lane == 0) {
-      for (int i = 0; i < 2; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); }
+      for (int i = 0; i < 2; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 2); }      // "empty": one commit per MMA warp
       for (int s = 0; s < kAttnStages; ++s) {
-        mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1);
-        mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1);
+        mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 2);
+        mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 2);
       }
       for (int i = 0; i < 2; ++i) {
         mbar_init(&s_full[i], 1);
         mbar_init(&p_full[i], 4);                // one arrival per softmax warp of the tile (lane 0 after __syncwarp)
         mbar_init(&o_full[i], 1);
         mbar_init(&o_free[i], 4);
+        mbar_init(&s_free[i], 4);
+        mbar_init(&pv_done[i], 1);
       }
       fence_mbar_init();
     }
@@ -269,20 +281,30 @@ __global__ void __launch_bounds__(kAttnThreads, 1) seq_attn_fwd_kernel(const __g
           }
         }
       }
-    } else if (warp == 9) {
-      // ================= MMA issuer =================
-      // Warp-uniform control flow: every lane follows the barriers, ONE elected lane issues.
+    } else if (warp == 9 || warp == 10) {
+      // ================= MMA issuers: one warp PER TILE (warp 9: tile 0, warp 10: tile 1) =================
+      // Each warp runs its tile's own event sequence  s_free_t(g) -> S_t(g+1),  p_full_t(g) -> O_t += P_t V(g)  with blocking
+      // waits, so the two tiles never wait for each other inside an issuing warp (with ONE warp and a fixed issue order the
+      // event stamps showed a published P waiting ~2000 cycles for the other tile's turn). The K / V / Q buffers are shared:
+      // their "empty" barriers take one tcgen05.commit arrival from each warp. Warp-uniform control flow, ONE elected lane
+      // issues; everything but the critical barrier is waited for ahead of time (an mbarrier try_wait costs ~90 cycles even
+      // when the phase completed long ago).
+      const int t = warp - 9;
       const uint32_t idesc_s = make_idesc_bf16(kAttnBQ, kAttnBK, 0, 0);      // S = Q K^T : both K-major
       const uint32_t idesc_o = make_idesc_bf16(kAttnBQ, kAttnD, 0, 1);       // O += P V  : A from TMEM, V is [keys][d] = MN-major B
       const uint32_t dhi = smem_desc_hi_sw128(1024);
-      const uint32_t q_lo = smem_desc_lo(smem_u32(sQ), 16);
+      const uint32_t q_lo = smem_desc_lo(smem_u32(sQ), 16) + static_cast<uint32_t>(t) * (kAttnQBytes >> 4);
       const uint32_t k_lo = smem_desc_lo(smem_u32(sKV), 16);                 // + stage * (2 * kAttnKBytes >> 4)
       const uint32_t v_lo = smem_desc_lo(smem_u32(sKV + kAttnKBytes), 8192);
+      const uint32_t tS = tmem_base + kAttnTmemS + static_cast<uint32_t>(t) * kAttnBK;
+      const uint32_t tO = tmem_base + kAttnTmemO + static_cast<uint32_t>(t) * kAttnD;
+      const uint32_t tP = tmem_base + kAttnTmemP + static_cast<uint32_t>(t) * (kAttnBK / 2);
       bool ok = true;
-      // ---- S stream cursor: runs ONE BLOCK AHEAD of the P V stream, across item boundaries ----
+      // ---- S stream cursor: one block AHEAD of the P V stream, across item boundaries ----
       int ws = blockIdx.x, js = 0, ns = 0;                                   // item, block, blocks of that item
       int ks = 0; uint32_t kph = 0u;                                         // K stage / parity
       uint32_t qn = 0, qcur = 0;                                             // items started by the S stream; Q buffer in use
+      bool qk_ready = false;
       auto s_next_item = [&]() {                                             // advance to the next non-empty item (ns = 0: none left)
         for (; ws < nwork; ws += gridDim.x) {
           ns = item_nblk(ws);
@@ -290,71 +312,79 @@ __global__ void __launch_bounds__(kAttnThreads, 1) seq_attn_fwd_kernel(const __g
         }
         ns = 0;
       };
-      auto issue_qk = [&](int t) {                                           // S_t of block (ws, js); t = 1 advances the cursor
-        if (ns == 0) return;
-        if (t == 0) {
-          if (js == 0) {
-            qcur = qn & 1u;
-            ok = ok && mbar_wait_fast(&q_full[qcur], (qn >> 1) & 1u, P.err, FND_DEV_TIMEOUT_MMA);
-            ++qn;
-          }
-          ok = ok && mbar_wait_fast(&k_full[ks], kph, P.err, FND_DEV_TIMEOUT_MMA);
+      auto prepare_qk = [&]() {                                              // operand waits of the next S step, done early
+        if (ns == 0 || qk_ready) return;
+        if (js == 0) {
+          qcur = qn & 1u;
+          ok = ok && mbar_wait_fast(&q_full[qcur], (qn >> 1) & 1u, P.err, FND_DEV_TIMEOUT_MMA);
+          ++qn;
         }
+        ok = ok && mbar_wait_fast(&k_full[ks], kph, P.err, FND_DEV_TIMEOUT_MMA);
+        qk_ready = true;
+      };
+      auto issue_qk = [&]() {                                                // S_t of block (ws, js)
+        if (ns == 0) return;
+        prepare_qk();
         tc_fence_after_sync();
-        const uint32_t ql = q_lo + (qcur * 2u + static_cast<uint32_t>(t)) * (kAttnQBytes >> 4);
+        const uint32_t ql = q_lo + qcur * 2u * (kAttnQBytes >> 4);
         const uint32_t kl = k_lo + static_cast<uint32_t>(ks) * ((2 * kAttnKBytes) >> 4);
-        const uint32_t tS = tmem_base + kAttnTmemS + static_cast<uint32_t>(t) * kAttnBK;
         if (ok && elect_one()) {
 #pragma unroll
           for (int k = 0; k < kAttnD / 16; ++k)
             umma_f16(tS, desc64(ql + 2 * k, dhi), desc64(kl + 2 * k, dhi), idesc_s, k != 0 ? 1u : 0u);
           umma_commit(&s_full[t]);
-          if (t == 1) {
-            umma_commit(&k_empty[ks]);
-            if (js + 1 == ns) umma_commit(&q_empty[qcur]);                   // this Q buffer may be refilled once this retires
-          }
+          umma_commit(&k_empty[ks]);                                         // second arrival comes from the other tile's warp
+          if (js + 1 == ns) umma_commit(&q_empty[qcur]);                     // this Q buffer may be refilled once both tiles are through
         }
         __syncwarp();
-        if (t == 1) {
-          if (++ks == kAttnStages) { ks = 0; kph ^= 1u; }
-          if (++js == ns) { js = 0; ws += gridDim.x; s_next_item(); }
+        if (++ks == kAttnStages) { ks = 0; kph ^= 1u; }
+        if (++js == ns) { js = 0; ws += gridDim.x; s_next_item(); }
+        qk_ready = false;
+      };
+      // ---- P V stream cursor ----
+      int pw = blockIdx.x, pj = 0, pn = 0;
+      uint32_t pg = 0u, pi = 0u;                                             // global step / non-empty item count
+      int vs = 0; uint32_t vph = 0u;
+      auto pv_next_item = [&]() {
+        for (; pw < nwork; pw += gridDim.x) {
+          pn = item_nblk(pw);
+          if (pn > 0) return;
         }
+        pn = 0;
       };
       s_next_item();
-      issue_qk(0);
-      issue_qk(1);
-      uint32_t gp = 0, ip = 0;                                               // P V steps / non-empty items so far
-      int vs = 0; uint32_t vph = 0u;
+      pv_next_item();
+      issue_qk();                                                            // S_t of the first block
 #pragma unroll 1
-      for (int w = blockIdx.x; w < nwork && ok; w += gridDim.x) {
-        const int nblk = item_nblk(w);
-        if (nblk == 0) continue;
-#pragma unroll 1
-        for (int j = 0; j < nblk && ok; ++j) {
-#pragma unroll
-          for (int t = 0; t < 2; ++t) {
-            ok = ok && mbar_wait_fast(&p_full[t], gp & 1u, P.err, FND_DEV_TIMEOUT_MMA);
-            if (j == 0) ok = ok && mbar_wait_fast(&o_free[t], (ip & 1u) ^ 1u, P.err, FND_DEV_TIMEOUT_MMA);
-            if (t == 0) ok = ok && mbar_wait_fast(&v_full[vs], vph, P.err, FND_DEV_TIMEOUT_MMA);
-            if (!ok) break;
-            tc_fence_after_sync();
-            const uint32_t vl = v_lo + static_cast<uint32_t>(vs) * ((2 * kAttnKBytes) >> 4);
-            const uint32_t tO = tmem_base + kAttnTmemO + static_cast<uint32_t>(t) * kAttnD;
-            const uint32_t tP = tmem_base + kAttnTmemP + static_cast<uint32_t>(t) * (kAttnBK / 2);
-            if (elect_one()) {
-#pragma unroll
-              for (int k = 0; k < kAttnBK / 16; ++k)
-                umma_f16_ts(tO, tP + 8 * k, desc64(vl + 128 * k, dhi), idesc_o, (j != 0 || k != 0) ? 1u : 0u);
-              if (j + 1 == nblk) umma_commit(&o_full[t]);
-              if (t == 1) umma_commit(&v_empty[vs]);
-            }
-            __syncwarp();
-            issue_qk(t);                                                     // S_t of the NEXT block (same or next item)
-          }
-          ++gp;
-          if (++vs == kAttnStages) { vs = 0; vph ^= 1u; }
+      while (ok && pn != 0) {
+        // S_t(g+1) as soon as the softmax threads HOLD S_t(g) in registers: a whole softmax block before they need it
+        if (ns != 0) {
+          prepare_qk();
+          ok = ok && mbar_wait_fast(&s_free[t], pg & 1u, P.err, FND_DEV_TIMEOUT_MMA);
+          issue_qk();
+          if (lane == 0) ATTN_EV(pg, 10 + 4 * t);
         }
-        ++ip;
+        // O_t (+)= P_t V(g): V and (at an item start) the drained O are waited for before the critical wait on P
+        const int j = pj;
+        ok = ok && mbar_wait_fast(&v_full[vs], vph, P.err, FND_DEV_TIMEOUT_MMA);
+        if (j == 0) ok = ok && mbar_wait_fast(&o_free[t], (pi & 1u) ^ 1u, P.err, FND_DEV_TIMEOUT_MMA);
+        ok = ok && mbar_wait_fast(&p_full[t], pg & 1u, P.err, FND_DEV_TIMEOUT_MMA);
+        if (lane == 0) ATTN_EV(pg, 8 + 4 * t);
+        tc_fence_after_sync();
+        const uint32_t vl = v_lo + static_cast<uint32_t>(vs) * ((2 * kAttnKBytes) >> 4);
+        if (ok && elect_one()) {
+#pragma unroll
+          for (int k = 0; k < kAttnBK / 16; ++k)
+            umma_f16_ts(tO, tP + 8 * k, desc64(vl + 128 * k, dhi), idesc_o, (j != 0 || k != 0) ? 1u : 0u);
+          umma_commit(&pv_done[t]);
+          if (j + 1 == pn) umma_commit(&o_full[t]);
+          umma_commit(&v_empty[vs]);                                         // second arrival comes from the other tile's warp
+        }
+        __syncwarp();
+        if (lane == 0) ATTN_EV(pg, 9 + 4 * t);
+        ++pg;
+        if (++vs == kAttnStages) { vs = 0; vph ^= 1u; }
+        if (++pj == pn) { pj = 0; ++pi; pw += gridDim.x; pv_next_item(); }
       }
     }
   } else {
@@ -393,11 +423,17 @@ __global__ void __launch_bounds__(kAttnThreads, 1) seq_attn_fwd_kernel(const __g
 #pragma unroll 1
       for (int j = 0; j < nblk; ++j, ++g) {
         ok = ok && mbar_wait_fast(&s_full[t], g & 1u, P.err, FND_DEV_TIMEOUT_EPILOGUE);
+        if (qd == 0 && lane == 0) ATTN_EV(g, 0 + 4 * t);
         tc_fence_after_sync();
         float s[kAttnBK];
 #pragma unroll
         for (int c = 0; c < kAttnBK / 32; ++c) tmem_ld_32x32(tS + 32 * c, reinterpret_cast<uint32_t(&)[32]>(s[32 * c]));
         tmem_ld_wait();
+        // the whole S row is in registers: the MMA warp may overwrite S_t with the next block's scores right away
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_free[t]);
+        if (qd == 0 && lane == 0) ATTN_EV(g, 1 + 4 * t);
 
         // ---- key-padding mask of the block's 128 columns as four validity words (warp-cooperative ballots) ----
         const int k0 = j * kAttnBK;
@@ -423,6 +459,12 @@ __global__ void __launch_bounds__(kAttnThreads, 1) seq_attn_fwd_kernel(const __g
         m0 = fmax3(m0, s[124], s[125]); m1 = fmax3(m1, s[126], s[127]);
         const float mx = fmaxf(fmax3(m0, m1, m2), m3);
         const float m_new = fmaxf(m_run, mx * P.scale_log2);                  // scale_log2 > 0: max commutes with the scaling
+        if (j > 0) {
+          // P_t V of block j-1 must have retired before P_t is overwritten / O_t rescaled (issued a whole softmax block ago).
+          // For j == 0 the item epilogue's o_full wait covered it.
+          ok = ok && mbar_wait_fast(&pv_done[t], (g - 1u) & 1u, P.err, FND_DEV_TIMEOUT_EPILOGUE);
+          tc_fence_after_sync();
+        }
         if (j == 0) {
           m_run = m_new;                                                      // O is overwritten by the first P V: nothing to rescale
         } else if (__any_sync(0xffffffffu, m_new - m_run > kAttnLazyLog2)) {
@@ -472,7 +514,14 @@ __global__ void __launch_bounds__(kAttnThreads, 1) seq_attn_fwd_kernel(const __g
           }
         };
         if (pingpong) named_bar_sync(1 + t, 256);
-        if (kPoly == 0 || masked_blk) exp_block(IntTag<0>{});   // a masked score must give exactly 0: MUFU throughout
+        if (qd == 0 && lane == 0) ATTN_EV(g, 2 + 4 * t);
+        if (P.dbg_noexp) {
+          uint32_t z[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) z[i] = __float_as_uint(s[i]) & 0u;
+#pragma unroll
+          for (int c = 0; c < kAttnBK / 32; ++c) tmem_st_32x16(tP + 16 * c, z);
+        } else if (kPoly == 0 || masked_blk) exp_block(IntTag<0>{});   // a masked score must give exactly 0: MUFU throughout
         else exp_block(IntTag<kPoly>{});
         if (pingpong) named_bar_arrive(2 - t, 256);
         {
@@ -484,6 +533,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) seq_attn_fwd_kernel(const __g
         tc_fence_before_sync();
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[t]);
+        if (qd == 0 && lane == 0) ATTN_EV(g, 3 + 4 * t);
       }
 
       // ---- item epilogue: O / l -> bf16 -> swizzled shared-memory tile -> ONE TMA store per tile. (Row stores straight
