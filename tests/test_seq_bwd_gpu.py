@@ -125,10 +125,11 @@ def test_pool_backward_colsum_wgrad():
         assert e < 1e-4                             # same bf16 operands, fp32 accumulation
 
 
-def _frontend_grads(d_model, heads, lengths, batch, seed, full=False):
+def _frontend_grads(d_model, heads, lengths, batch, seed, full=False, streams=None, blocks=None):
     """(kernel grads, oracle grads, forward errors) of sum_s <y_s, w_s> for fixed random w_s."""
     from ultrafnd_git_b200.seqfront import SequenceFrontEnd
-    streams, blocks = O.FAKESV_STREAMS, O.FAKESV_BLOCKS
+    streams = O.FAKESV_STREAMS if streams is None else streams
+    blocks = O.FAKESV_BLOCKS if blocks is None else blocks
     p = O.init_params(streams, blocks, d_model, seed=seed)
     data = O.make_batch(streams, lengths, batch, seed=seed + 1, full=full)
     # the kernels read bf16 features and bf16 GEMM weights: hand the checker the same rounded values
@@ -172,6 +173,18 @@ def test_frontend_backward_matches_oracle_autograd(d_model, heads, lengths, batc
     print(f"front-end backward d={d_model}: worst parameter-gradient rel-err {worst[1]:.2e} ({worst[0]}); top: "
           + ", ".join(f"{k} {v:.1e}" for k, v in top))
     assert worst[1] < BF16_TOL                    # north_star bf16 tolerance 2e-2, every parameter gradient
+
+
+def test_frontend_backward_at_the_stress_shape():
+    """BASELINE.json configs[4] shape (1024 text tokens x 512 frames, hidden 1024, 16 heads), batch 2, full-length
+    sequences: every parameter gradient of the front-end against autograd over the self-oracle."""
+    streams = {"text": (768, 768, "text_features"), "frames": (4096, 512, "visual_features")}
+    got, ref, fwd = _frontend_grads(1024, 16, {"text": 1024, "frames": 512}, 2, seed=99, full=True, streams=streams,
+                                    blocks=(("text", "frames"),))
+    errs = {k: _rel(got[k], ref[k]) for k in ref}
+    top = sorted(errs.items(), key=lambda kv: -kv[1])[:3]
+    print(f"front-end backward, stress shape: forward {max(fwd.values()):.2e}; parameter gradients top: " + ", ".join(f"{k} {v:.1e}" for k, v in top))
+    assert max(fwd.values()) < BF16_TOL and max(errs.values()) < BF16_TOL        # north_star bf16 tolerance 2e-2
 
 
 def test_end_to_end_training_gradients_through_fusion_and_classifier():
