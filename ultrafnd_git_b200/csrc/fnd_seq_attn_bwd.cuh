@@ -93,8 +93,8 @@ __global__ void __launch_bounds__(kAttnThreads, 1) seq_attn_bwd_kernel(const __g
   }
   if (warp == 9) {
     if (lane == 0) {
-      for (int i = 0; i < 2; ++i) { mbar_init(&r_full[i], 1); mbar_init(&r_empty[i], 1); }
-      for (int s = 0; s < kBwdStages; ++s) { mbar_init(&st_full[s], 1); mbar_init(&st_empty[s], 1); }
+      for (int i = 0; i < 2; ++i) { mbar_init(&r_full[i], 1); mbar_init(&r_empty[i], 2); }      // "empty": one commit per MMA warp
+      for (int s = 0; s < kBwdStages; ++s) { mbar_init(&st_full[s], 1); mbar_init(&st_empty[s], 2); }
       for (int i = 0; i < 2; ++i) {
         mbar_init(&s_full[i], 1);
         mbar_init(&p_full[i], 4);
@@ -154,18 +154,28 @@ __global__ void __launch_bounds__(kAttnThreads, 1) seq_attn_bwd_kernel(const __g
           }
         }
       }
-    } else if (warp == 9) {
-      // ================= MMA issuer =================
+    } else if (warp == 9 || warp == 10) {
+      // ================= MMA issuers: one warp PER TILE (warp 9: tile 0, warp 10: tile 1), as in the forward kernel =================
+      // Each warp follows its own tile:  S_t, dP_t of the first block;  then per block  p_full_t -> accumulating GEMMs ->
+      // S_t, dP_t of the next block. The operand waits of the next block are done BEFORE the critical wait on p_full (an
+      // mbarrier try_wait costs ~90 cycles even on a completed phase). Shared buffers (resident tiles, ring stages) are
+      // released by one tcgen05.commit arrival from each warp.
+      const int t = warp - 9;
       const uint32_t idesc_s = make_idesc_bf16(kAttnBQ, kBwdBlk, 0, 0);      // S / dP: 128 x 64 x 64, both operands K-major
       const uint32_t idesc_a = make_idesc_bf16(kAttnBQ, kAttnD, 0, 1);       // accumulators: A from TMEM, B MN-major [rows][d]
       const uint32_t dhi = smem_desc_hi_sw128(1024);
-      const uint32_t r_lo = smem_desc_lo(smem_u32(sR), 16);
+      const uint32_t r_lo = smem_desc_lo(smem_u32(sR), 16) + static_cast<uint32_t>(t) * (kBwdTileBytes >> 4);
       const uint32_t s_lo = smem_desc_lo(smem_u32(sS), 16);                  // K-major view of a streamed tile
       const uint32_t s_mn = smem_desc_lo(smem_u32(sS), 8192);                // MN-major view of the same tile
+      const uint32_t tS = tmem_base + kBwdTmemS + static_cast<uint32_t>(t) * kBwdBlk;
+      const uint32_t tD = tmem_base + kBwdTmemDP + static_cast<uint32_t>(t) * kBwdBlk;
+      const uint32_t tA0 = tmem_base + kBwdTmemAcc0 + static_cast<uint32_t>(t) * kAttnD;
+      const uint32_t tA1 = tmem_base + kBwdTmemAcc1 + static_cast<uint32_t>(t) * kAttnD;
       bool ok = true;
       int ws = blockIdx.x, js = 0, ns = 0;
       int ks = 0; uint32_t kph = 0u;
       uint32_t rn = 0, rcur = 0;
+      bool s_ready = false;
       auto s_next_item = [&]() {
         for (; ws < nwork; ws += gridDim.x) {
           ns = item_nblk(ws);
@@ -173,41 +183,40 @@ __global__ void __launch_bounds__(kAttnThreads, 1) seq_attn_bwd_kernel(const __g
         }
         ns = 0;
       };
-      // S_t = R0_t S0^T and dP_t = R1_t S1^T of block (ws, js); t = 1 advances the cursor
-      auto issue_s = [&](int t) {
-        if (ns == 0) return;
-        if (t == 0) {
-          if (js == 0) {
-            rcur = rn & 1u;
-            ok = ok && mbar_wait_fast(&r_full[rcur], (rn >> 1) & 1u, P.err, FND_DEV_TIMEOUT_MMA);
-            ++rn;
-          }
-          ok = ok && mbar_wait_fast(&st_full[ks], kph, P.err, FND_DEV_TIMEOUT_MMA);
+      auto prepare_s = [&]() {                                               // operand waits of the next S / dP step
+        if (ns == 0 || s_ready) return;
+        if (js == 0) {
+          rcur = rn & 1u;
+          ok = ok && mbar_wait_fast(&r_full[rcur], (rn >> 1) & 1u, P.err, FND_DEV_TIMEOUT_MMA);
+          ++rn;
         }
+        ok = ok && mbar_wait_fast(&st_full[ks], kph, P.err, FND_DEV_TIMEOUT_MMA);
+        s_ready = true;
+      };
+      // S_t = R0_t S0^T and dP_t = R1_t S1^T of block (ws, js)
+      auto issue_s = [&]() {
+        if (ns == 0) return;
+        prepare_s();
         tc_fence_after_sync();
-        const uint32_t a0 = r_lo + (rcur * 4u + static_cast<uint32_t>(t)) * (kBwdTileBytes >> 4);
+        const uint32_t a0 = r_lo + rcur * 4u * (kBwdTileBytes >> 4);
         const uint32_t a1 = a0 + 2u * (kBwdTileBytes >> 4);
         const uint32_t b0 = s_lo + static_cast<uint32_t>(ks) * (kBwdStageBytes >> 4);
         const uint32_t b1 = b0 + (kBwdBlkBytes >> 4);
-        const uint32_t tS = tmem_base + kBwdTmemS + static_cast<uint32_t>(t) * kBwdBlk;
-        const uint32_t tD = tmem_base + kBwdTmemDP + static_cast<uint32_t>(t) * kBwdBlk;
         if (ok && elect_one()) {
 #pragma unroll
           for (int k = 0; k < kAttnD / 16; ++k) umma_f16(tS, desc64(a0 + 2 * k, dhi), desc64(b0 + 2 * k, dhi), idesc_s, k != 0 ? 1u : 0u);
 #pragma unroll
           for (int k = 0; k < kAttnD / 16; ++k) umma_f16(tD, desc64(a1 + 2 * k, dhi), desc64(b1 + 2 * k, dhi), idesc_s, k != 0 ? 1u : 0u);
           umma_commit(&s_full[t]);
-          if (t == 1 && js + 1 == ns) umma_commit(&r_empty[rcur]);
+          if (js + 1 == ns) umma_commit(&r_empty[rcur]);                     // second arrival: the other tile's warp
         }
         __syncwarp();
-        if (t == 1) {
-          if (++ks == kBwdStages) { ks = 0; kph ^= 1u; }
-          if (++js == ns) { js = 0; ws += gridDim.x; s_next_item(); }
-        }
+        if (++ks == kBwdStages) { ks = 0; kph ^= 1u; }
+        if (++js == ns) { js = 0; ws += gridDim.x; s_next_item(); }
+        s_ready = false;
       };
       s_next_item();
-      issue_s(0);
-      issue_s(1);
+      issue_s();
       uint32_t gp = 0, ip = 0;
       int vs = 0;
 #pragma unroll 1
@@ -216,42 +225,34 @@ __global__ void __launch_bounds__(kAttnThreads, 1) seq_attn_bwd_kernel(const __g
         if (nblk == 0) continue;
 #pragma unroll 1
         for (int j = 0; j < nblk && ok; ++j) {
+          prepare_s();                                                       // next block's operands: off the critical path
+          if (j == 0) ok = ok && mbar_wait_fast(&o_free[t], (ip & 1u) ^ 1u, P.err, FND_DEV_TIMEOUT_MMA);
+          ok = ok && mbar_wait_fast(&p_full[t], gp & 1u, P.err, FND_DEV_TIMEOUT_MMA);
+          if (!ok) break;
+          tc_fence_after_sync();
+          const uint32_t bm = s_mn + static_cast<uint32_t>(vs) * (kBwdStageBytes >> 4);
+          const uint32_t acc = (j != 0) ? 1u : 0u;
+          if (elect_one()) {
+            if (kDkv) {
+              // dV_t += P^T_t dO_i   (P^T over the S^T columns, dO_i = streamed tile 1)
+              // dK_t += dS^T_t Q_i   (dS^T over the dP^T columns, Q_i = streamed tile 0)
 #pragma unroll
-          for (int t = 0; t < 2; ++t) {
-            ok = ok && mbar_wait_fast(&p_full[t], gp & 1u, P.err, FND_DEV_TIMEOUT_MMA);
-            if (j == 0) ok = ok && mbar_wait_fast(&o_free[t], (ip & 1u) ^ 1u, P.err, FND_DEV_TIMEOUT_MMA);
-            if (!ok) break;
-            tc_fence_after_sync();
-            const uint32_t bm = s_mn + static_cast<uint32_t>(vs) * (kBwdStageBytes >> 4);
-            const uint32_t acc = (j != 0) ? 1u : 0u;
-            if (elect_one()) {
-              if (kDkv) {
-                // dV_t += P^T_t dO_i   (P^T over the S^T columns, dO_i = streamed tile 1)
-                // dK_t += dS^T_t Q_i   (dS^T over the dP^T columns, Q_i = streamed tile 0)
-                const uint32_t tPT = tmem_base + kBwdTmemS + static_cast<uint32_t>(t) * kBwdBlk;
-                const uint32_t tDS = tmem_base + kBwdTmemDP + static_cast<uint32_t>(t) * kBwdBlk;
-                const uint32_t tDK = tmem_base + kBwdTmemAcc0 + static_cast<uint32_t>(t) * kAttnD;
-                const uint32_t tDV = tmem_base + kBwdTmemAcc1 + static_cast<uint32_t>(t) * kAttnD;
+              for (int k = 0; k < kBwdBlk / 16; ++k)
+                umma_f16_ts(tA1, tS + 8 * k, desc64(bm + (kBwdBlkBytes >> 4) + 128 * k, dhi), idesc_a, (acc | (k != 0)) ? 1u : 0u);
 #pragma unroll
-                for (int k = 0; k < kBwdBlk / 16; ++k)
-                  umma_f16_ts(tDV, tPT + 8 * k, desc64(bm + (kBwdBlkBytes >> 4) + 128 * k, dhi), idesc_a, (acc | (k != 0)) ? 1u : 0u);
+              for (int k = 0; k < kBwdBlk / 16; ++k)
+                umma_f16_ts(tA0, tD + 8 * k, desc64(bm + 128 * k, dhi), idesc_a, (acc | (k != 0)) ? 1u : 0u);
+            } else {
+              // dQ_t += dS_t K_j     (dS over the S columns, K_j = streamed tile 0)
 #pragma unroll
-                for (int k = 0; k < kBwdBlk / 16; ++k)
-                  umma_f16_ts(tDK, tDS + 8 * k, desc64(bm + 128 * k, dhi), idesc_a, (acc | (k != 0)) ? 1u : 0u);
-              } else {
-                // dQ_t += dS_t K_j     (dS over the S columns, K_j = streamed tile 0)
-                const uint32_t tDS = tmem_base + kBwdTmemS + static_cast<uint32_t>(t) * kBwdBlk;
-                const uint32_t tDQ = tmem_base + kBwdTmemAcc0 + static_cast<uint32_t>(t) * kAttnD;
-#pragma unroll
-                for (int k = 0; k < kBwdBlk / 16; ++k)
-                  umma_f16_ts(tDQ, tDS + 8 * k, desc64(bm + 128 * k, dhi), idesc_a, (acc | (k != 0)) ? 1u : 0u);
-              }
-              if (j + 1 == nblk) umma_commit(&o_full[t]);
-              if (t == 1) umma_commit(&st_empty[vs]);
+              for (int k = 0; k < kBwdBlk / 16; ++k)
+                umma_f16_ts(tA0, tS + 8 * k, desc64(bm + 128 * k, dhi), idesc_a, (acc | (k != 0)) ? 1u : 0u);
             }
-            __syncwarp();
-            issue_s(t);
+            if (j + 1 == nblk) umma_commit(&o_full[t]);
+            umma_commit(&st_empty[vs]);                                      // second arrival: the other tile's warp
           }
+          __syncwarp();
+          issue_s();
           ++gp;
           if (++vs == kBwdStages) vs = 0;
         }
