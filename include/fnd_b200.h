@@ -128,9 +128,15 @@ int fnd_clip_adamw_step(void* plan, int norm_from_slots, void* stream);
  * fnd_train_fwd_bwd : forward + cross-entropy + full backward in one stream-ordered sequence; leaves the mean
  *                     loss / gradient norm in "state" and all gradients in the arena.
  * fnd_train_step    : fnd_train_fwd_bwd followed by fnd_clip_adamw_step(norm_from_slots = 1).
+ * fnd_train_step_overlap : fnd_train_step with the fuse_mlp.0 / fuse_mlp.3 weight gradients (70 % of the gradient
+ *                     bytes) launched on `side_stream` as soon as dgrad_fuse1 has produced their operands, so that
+ *                     their HBM write-back runs UNDER the latency-bound rest of the backward chain; the streams fork
+ *                     and join through events (capturable into one CUDA graph). Results are bit-identical to
+ *                     fnd_train_step (same tiles, same norm slots). side_stream NULL = fnd_train_step.
  * fnd_eval_step     : forward of both modules (+ row losses when labels are given), no dropout, nothing saved. */
 int fnd_train_fwd_bwd(void* plan, const fnd_inputs* in, void* stream);
 int fnd_train_step(void* plan, const fnd_inputs* in, void* stream);
+int fnd_train_step_overlap(void* plan, const fnd_inputs* in, void* stream, void* side_stream);
 int fnd_eval_step(void* plan, const fnd_inputs* in, void* stream);
 
 /* ---- data-parallel optimizer step over NVLink peer memory (batch-sharded replicas, one process per GPU) ----

@@ -26,6 +26,9 @@ extern "C" {
 /* One-time, per-device kernel attribute setup (opt-in shared-memory sizes). Call once outside graph capture; every
  * other entry point also calls it lazily. */
 int fnd_seq_init(void);
+/* Number of CTA pairs the 256 x 256 two-SM projection kernel (csrc/fnd_seq_gemm2.cuh) keeps resident (74 on a B200);
+ * 0 = that kernel is disabled (FND_SEQ_GEMM_PAIR=0) and fnd_seq_linear always takes the single-CTA kernel. */
+int fnd_seq_pair_clusters(void);
 
 /* y[i] = bf16(x[i]), n a multiple of 8 (feature tensors arrive as fp32: forensic_trainer.py:254-258 casts to fp32). */
 int fnd_seq_cast_bf16(const float* x, void* y_bf16, long long n, void* stream);
@@ -66,6 +69,11 @@ int fnd_seq_masked_mean_pool(const void* x_bf16, int x_pitch, const unsigned cha
  * FND_ATTN_DBG_NOEXP=1 additionally skips the exponentials (P = 0) to expose the pure pipeline latency. Not for use
  * around graph capture. */
 int fnd_seq_debug_attn_stamps(long long* stamps);
+/* Probe aid (tools/gemm2_stamps.py): device buffer of 16 int64 per CTA pair that the two-SM projection kernel fills with
+ * clock64 totals — MMA warp: [0] loop, [1] waiting for a drained accumulator, [2] waiting for operands, [3] issuing,
+ * [5] k-blocks; producer: [4] waiting for a free stage; epilogue: [6] loop, [7] waiting for an accumulator,
+ * [8..11] per-slab phases (buffer free, TMEM load, arithmetic + staging stores, fence + store issue). NULL = off. */
+int fnd_seq_debug_gemm_stamps(long long* stamps);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Backward pass. Activation gradients travel as bf16 matrices, parameter gradients are fp32. Workspaces are caller-owned

@@ -23,7 +23,10 @@ def _rel(a, b):
 
 
 @pytest.mark.parametrize("M,N,K,extras", [(100, 64, 128, False), (300, 384, 4096, True), (4096, 1024, 1024, True),
-                                           (37, 768, 256, True), (20000, 512, 512, False), (129, 1536, 512, True)])
+                                           (37, 768, 256, True), (20000, 512, 512, False), (129, 1536, 512, True),
+                                           # CTA-pair kernel (fnd_seq_gemm2.cuh: >= 74 tiles of 256 x 256): ragged M / N / K with
+                                           # every epilogue extra, and the stress shape's two projections
+                                           (19001, 320, 200, True), (18500, 576, 328, False), (32768, 1024, 1024, True), (16384, 3072, 1024, False)])
 def test_seq_linear_matches_torch(M, N, K, extras):
     from ultrafnd_git_b200 import seq_ops as S
     g = torch.Generator().manual_seed(M + N + K)
@@ -41,6 +44,8 @@ def test_seq_linear_matches_torch(M, N, K, extras):
     torch.cuda.synchronize()
     assert int(err.item()) == 0
     e32, e16 = _rel(of, ref), _rel(out, ref)
+    from ultrafnd_git_b200 import _lib
+    print(f"pair clusters {_lib.load().fnd_seq_pair_clusters()}", end=" ")
     print(f"seq_linear M={M} N={N} K={K}: fp32-out rel-err {e32:.2e}, bf16-out rel-err {e16:.2e}")
     assert e32 < 1e-4            # same bf16 operands, fp32 accumulation: only summation order differs
     assert e16 < 5e-3            # + one bf16 rounding of the output

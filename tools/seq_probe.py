@@ -52,6 +52,10 @@ def main():
 
     ms = timeit(lambda: S.linear(xt, w3, b3, out=qkv_t, err=err)); rec("in_proj text  [%d x %d x %d]" % (B * Lt, 3 * d, d), ms, 2.0 * B * Lt * 3 * d * d)
     ms = timeit(lambda: S.linear(xf, w3, b3, out=qkv_f, err=err)); rec("in_proj frames[%d x %d x %d]" % (B * Lf, 3 * d, d), ms, 2.0 * B * Lf * 3 * d * d)
+    # comparator only (never on the product path): the library GEMM on the same shapes, bias / residual not included
+    ms = timeit(lambda: torch.matmul(xt, w3.t(), out=qkv_t)); rec("  [cuBLAS via torch.matmul, same shape, no bias]", ms, 2.0 * B * Lt * 3 * d * d)
+    ms = timeit(lambda: torch.matmul(xf, w3.t(), out=qkv_f)); rec("  [cuBLAS frames shape]", ms, 2.0 * B * Lf * 3 * d * d)
+    ms = timeit(lambda: torch.matmul(xt, wo.t(), out=yt)); rec("  [cuBLAS out_proj shape, no residual]", ms, 2.0 * B * Lt * d * d)
     ms = timeit(lambda: S.coattn_forward(qkv_t, qkv_f, qkv_f, B, H, Lt, Lf, 0, d, 2 * d, out=at, err=err)); rec("attn text<-frames", ms, 4.0 * B * Lt * Lf * d)
     ms = timeit(lambda: S.coattn_forward(qkv_f, qkv_t, qkv_t, B, H, Lf, Lt, 0, d, 2 * d, out=af, err=err)); rec("attn frames<-text", ms, 4.0 * B * Lt * Lf * d)
     ms = timeit(lambda: S.linear(at, wo, bo, resid=xt, out=yt, err=err)); rec("out_proj text +resid", ms, 2.0 * B * Lt * d * d)

@@ -133,6 +133,7 @@ def _signatures() -> Dict[str, tuple]:
         "fnd_clip_adamw_step": (_c_int, [_c_void_p, _c_int, _c_void_p]),
         "fnd_train_fwd_bwd": (_c_int, [_c_void_p, P(FndInputs), _c_void_p]),
         "fnd_train_step": (_c_int, [_c_void_p, P(FndInputs), _c_void_p]),
+        "fnd_train_step_overlap": (_c_int, [_c_void_p, P(FndInputs), _c_void_p, _c_void_p]),
         "fnd_eval_step": (_c_int, [_c_void_p, P(FndInputs), _c_void_p]),
         "fnd_launch_count": (_c_int, [_c_void_p, ctypes.c_char_p]),
         "fnd_debug_set_launch_limit": (_c_int, [_c_void_p, _c_int]),
@@ -149,7 +150,9 @@ def _signatures() -> Dict[str, tuple]:
         "fnd_check_error": (_c_int, [_c_void_p, _c_void_p]),
         # ---- sequence front-end (include/fnd_seq_b200.h)
         "fnd_seq_init": (_c_int, []),
+        "fnd_seq_pair_clusters": (_c_int, []),
         "fnd_seq_debug_attn_stamps": (_c_int, [_c_void_p]),
+        "fnd_seq_debug_gemm_stamps": (_c_int, [_c_void_p]),
         "fnd_seq_cast_bf16": (_c_int, [_c_void_p, _c_void_p, ll, _c_void_p]),
         "fnd_seq_linear": (_c_int, [_c_void_p, _c_int, _c_void_p, _c_int, _c_void_p, _c_void_p, _c_int, _c_int, _c_void_p, _c_int,
                                     _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_void_p, _c_void_p]),

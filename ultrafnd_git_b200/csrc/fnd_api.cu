@@ -275,6 +275,14 @@ static int build_tables(Plan& P) {
   float* slots = P.buf<float>("slots");
   for (auto& g : P.wg_all.host)
     if (g.epi.out_f32 != P.buf<float>("dAraw")) g.epi.sumsq_slots = slots + g.cta_begin;
+  // the early / rest split of the same problems (fnd_train_step_overlap, data-parallel overlap) shares wg_all's slot
+  // layout: a problem's tiles write the slots its twin in wg_all owns
+  for (GemmTable* T : {&P.wg_early, &P.wg_rest})
+    for (auto& g : T->host) {
+      if (g.epi.out_f32 == P.buf<float>("dAraw")) continue;
+      for (const auto& a : P.wg_all.host)
+        if (a.epi.out_f32 == g.epi.out_f32 && a.cta_count == g.cta_count) g.epi.sumsq_slots = slots + a.cta_begin;
+    }
   P.total_slots = P.wg_all.grid + P.fin_all.grid;
   if (P.total_slots > kSlotSumsq || P.fin_all.grid > 16384 - kSlotScratch) return -31;
   return 0;
@@ -651,6 +659,12 @@ int fnd_plan_bind(void* plan, void* workspace, float* params, float* grads, floa
   hs.loss_scale = 1.0f / static_cast<float>(P.B);
   FND_CUDA_OK(cudaMemcpyAsync(P.state(), &hs, sizeof(hs), cudaMemcpyHostToDevice, st));
   FND_CUDA_OK(cudaStreamSynchronize(st));   // hs / host tables are stack or plan-owned pageable memory
+  if (!P.ev_fork) {                         // side-stream fork / join events (never created inside a capture)
+    FND_CUDA_OK(cudaEventCreateWithFlags(&P.ev_fork, cudaEventDisableTiming));
+    FND_CUDA_OK(cudaEventCreateWithFlags(&P.ev_join, cudaEventDisableTiming));
+    FND_CUDA_OK(cudaEventCreateWithFlags(&P.ev_fork2, cudaEventDisableTiming));
+    FND_CUDA_OK(cudaEventCreateWithFlags(&P.ev_join2, cudaEventDisableTiming));
+  }
   P.bound = true;
   return 0;
 }
@@ -825,6 +839,9 @@ static int train_fwd_bwd_impl(void* plan, const fnd_inputs* in, int fused_optimi
   if (!in || !in->labels) return -1;
   cudaStream_t side = reinterpret_cast<cudaStream_t>(side_stream);
   const bool overlap = side_stream != nullptr && P.dp_bound && (dp_flags & 1);
+  // single-GPU fused step with the fuse_mlp weight gradients on the side stream (fnd_train_step_overlap)
+  const bool early1 = side_stream != nullptr && fused_optimizer && dp_flags == 0 && !skip_norm && P.launch_limit < 0 &&
+                      gemm_launch_is_light(P.wg_rest.kind, P.wg_rest.host.data(), static_cast<int>(P.wg_rest.host.size()));
   const bool defer = side_stream != nullptr && P.dp_bound && (dp_flags & 2);
   // bit 2: fused push — the weight-gradient launch's epilogue stores each tile into its owner's staging slot (bf16 wire
   // format, merged-finalize light launch only; not combined with the early push)
@@ -868,9 +885,27 @@ static int train_fwd_bwd_impl(void* plan, const fnd_inputs* in, int fused_optimi
     FND_CUDA_OK(cudaEventRecord(P.ev_join, side));
     P.pdl_next = false;
   }
+  if (early1) {
+    // fork: dz_f0 / dz_f1 / h1 / fused_cat are complete; the side stream's launch is an ordinary (non-PDL) one
+    FND_CUDA_OK(cudaEventRecord(P.ev_fork, st));
+    FND_CUDA_OK(cudaStreamWaitEvent(side, P.ev_fork, 0));
+    const bool keep = P.pdl_next;
+    P.pdl_next = false;
+    FND_OK(run_gemm(P, P.wg_early, 1, side, "wgrad_early"));
+    FND_CUDA_OK(cudaEventRecord(P.ev_join, side));
+    P.pdl_next = keep;
+  }
   FND_OK(run_gemm(P, P.dg_f0, 1, st, "dgrad_fuse0"));
   FND_OK(run_assemble_bwd(P, st));
   FND_OK(run_gemm(P, P.dg_qkv, 1, st, "dgrad_qkv"));
+  if (early1) {
+    // the remaining weight gradients + finalize CTAs (slot layout of wg_all), then join before the optimizer
+    const FinParams f = fin_params(P, P.fin_all, P.wg_all.grid, P.total_slots, false, 0, 0);
+    FND_OK(run_gemm(P, P.wg_rest, 1, st, "wgrad_rest", &f, P.fin_all.grid));
+    FND_CUDA_OK(cudaStreamWaitEvent(st, P.ev_join, 0));
+    P.joined_side = true;
+    return 0;
+  }
   if (overlap) {
     const FinParams f = fin_params(P, P.fin_all, P.wg_rest.grid, P.total_slots, false, 0, 0);
     FND_OK(run_gemm(P, P.wg_rest, 1, st, "wgrad_rest", &f, P.fin_all.grid));
@@ -907,14 +942,17 @@ int fnd_train_step_dp(void* plan, const fnd_inputs* in, void* stream, void* side
   return dp_tail(P, false, (flags & 2) != 0, st);
 }
 
-int fnd_train_step(void* plan, const fnd_inputs* in, void* stream) {
+int fnd_train_step(void* plan, const fnd_inputs* in, void* stream) { return fnd_train_step_overlap(plan, in, stream, nullptr); }
+
+int fnd_train_step_overlap(void* plan, const fnd_inputs* in, void* stream, void* side_stream) {
   {
     Plan* PP = as_plan(plan);
     if (PP && PP->bound && (!PP->m || !PP->v)) return -6;
+    if (PP) PP->joined_side = false;
   }
-  FND_OK(train_fwd_bwd_impl(plan, in, 1, stream));
+  FND_OK(train_fwd_bwd_impl(plan, in, 1, stream, side_stream));
   FND_PLAN(plan);
-  P.pdl_next = true;        // continues the chain started by train_fwd_bwd_impl
+  P.pdl_next = !P.joined_side;   // continues the chain started by train_fwd_bwd_impl (an event wait breaks it)
   P.launch_seq = 16;
   FND_SKIP(P);
   // AdamW reduces the norm slots itself (identical in every CTA), clips, steps and publishes the bookkeeping.

@@ -4,6 +4,7 @@
 #include "fnd_seq_attn_bwd.cuh"
 #include "fnd_seq_bwd_rows.cuh"
 #include "fnd_seq_gemm.cuh"
+#include "fnd_seq_gemm2.cuh"
 #include "fnd_seq_rows.cuh"
 #include "fnd_tmap.h"
 #include <math.h>
@@ -30,6 +31,10 @@ static int seq_num_sms() {
   return n;
 }
 
+// Clusters of the CTA-pair GEMM that can be resident at once (one CTA per SM: normally 74); 0 = pair kernel unavailable.
+static int g_pair_clusters = 0;
+
+static long long* g_gemm_stamps = nullptr;      // probe aid (fnd_seq_debug_gemm_stamps)
 static long long* g_attn_stamps = nullptr;      // probe aid (fnd_seq_debug_attn_stamps)
 
 extern "C" {
@@ -39,10 +44,37 @@ int fnd_seq_debug_attn_stamps(long long* stamps) {
   return 0;
 }
 
+int fnd_seq_debug_gemm_stamps(long long* stamps) {
+  g_gemm_stamps = stamps;
+  return 0;
+}
+
 int fnd_seq_init(void) {
   static bool done = false;
   if (done) return 0;
   SEQ_CUDA_OK(cudaFuncSetAttribute(seq_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSeqGemmSmemMax));
+  SEQ_CUDA_OK(cudaFuncSetAttribute(seq_gemm2_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSeqGemmSmemMax));
+  SEQ_CUDA_OK(cudaFuncSetAttribute(seq_gemm2_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSeqGemmSmemMax));
+  SEQ_CUDA_OK(cudaFuncSetAttribute(seq_gemm2_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSeqGemmSmemMax));
+  SEQ_CUDA_OK(cudaFuncSetAttribute(seq_gemm2_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSeqGemmSmemMax));
+  {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(static_cast<unsigned>(seq_num_sms() & ~1), 1, 1);
+    cfg.blockDim = dim3(kSeqGemmThreads, 1, 1);
+    cfg.dynamicSmemBytes = kSeqGemmSmemMax;
+    cudaLaunchAttribute at;
+    at.id = cudaLaunchAttributeClusterDimension;
+    at.val.clusterDim.x = 2; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+    cfg.attrs = &at; cfg.numAttrs = 1;
+    int nc = 0;
+    if (cudaOccupancyMaxActiveClusters(&nc, seq_gemm2_kernel<1, false>, &cfg) != cudaSuccess || nc <= 0) {
+      cudaGetLastError();
+      nc = seq_num_sms() / 2;                  // one CTA per SM by shared memory: every SM pair holds one cluster
+    }
+    const char* e = getenv("FND_SEQ_GEMM_PAIR");
+    g_pair_clusters = (e && atoi(e) == 0) ? 0 : nc;
+  }
   SEQ_CUDA_OK(cudaFuncSetAttribute(seq_attn_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBytes));
   SEQ_CUDA_OK(cudaFuncSetAttribute(seq_attn_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBytes));
   SEQ_CUDA_OK(cudaFuncSetAttribute(seq_attn_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBytes));
@@ -55,6 +87,11 @@ int fnd_seq_init(void) {
   SEQ_CUDA_OK(cudaFuncSetAttribute(seq_layernorm_bwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 2 * 2048 * 4));
   done = true;
   return 0;
+}
+
+int fnd_seq_pair_clusters(void) {
+  { int r = fnd_seq_init(); if (r) return 0; }
+  return g_pair_clusters;
 }
 
 int fnd_seq_cast_bf16(const float* x, void* y_bf16, long long n, void* stream) {
@@ -81,6 +118,53 @@ int fnd_seq_linear(const void* a_bf16, int a_pitch, const void* w_bf16, int w_pi
   memset(&P, 0, sizeof(P));
   P.M = M; P.N = N; P.K = K;
   P.splits = 1; P.kb_per_split = cdiv(K, kSeqGemmBK);
+  // Large bf16-output problems: 256 x 256 tiles on CTA pairs (fnd_seq_gemm2.cuh) when there is at least one tile per pair
+  if (g_pair_clusters > 0 && out_bf16 && !out_f32 && N >= kSeqGemm2BN && (N & 63) == 0 &&
+      static_cast<long long>(cdiv(M, 2 * kSeqGemmBM)) * cdiv(N, kSeqGemm2BN) >= g_pair_clusters) {
+    P.bn = kSeqGemm2BN;
+    P.tiles_m = cdiv(M, 2 * kSeqGemmBM);
+    P.tiles_n = cdiv(N, kSeqGemm2BN);
+    // one 64-deep k-box per stage (six 32 KB stages, five beside the residual slabs); FND_SEQ_GEMM_KB=2 selects 128-deep
+    // stages for the residual-free GEMMs — measured no faster (fnd_seq_gemm2.cuh)
+    static const char* ekb = getenv("FND_SEQ_GEMM_KB");
+    const int kkb = (ekb && atoi(ekb) == 2 && !resid_bf16) ? 2 : 1;
+    P.kblocks = cdiv(K, kSeqGemmBK * kkb);
+    P.stage_bytes = kkb * kSeqGemm2StageBytes;
+    const int rbuf_bytes = resid_bf16 ? 2 * kSeqGemmStageOutBytes : 0;
+    P.nstages = (kSeqGemmRingBudget - rbuf_bytes) / P.stage_bytes;
+    if (P.nstages > kSeqGemmMaxStages) P.nstages = kSeqGemmMaxStages;
+    P.bias = bias;
+    P.resid = static_cast<const __nv_bfloat16*>(resid_bf16); P.resid_pitch = resid_pitch;
+    P.act = act;
+    P.out_bf = static_cast<__nv_bfloat16*>(out_bf16); P.out_pitch = out_pitch;
+    P.err = err_flag;
+    { static const char* e = getenv("FND_SEQ_DBG_MMAS"); P.dbg_mmas = e ? atoi(e) : 0; }
+    P.dbg = g_gemm_stamps;
+    int r = encode_bf16_2d(&P.tmA, a_bf16, K, M, a_pitch, 64, kSeqGemmBM);
+    if (r) return r;
+    r = encode_bf16_2d(&P.tmB, w_bf16, K, N, w_pitch, 64, kSeqGemm2BN / 2);
+    if (r) return r;
+    r = encode_bf16_2d(&P.tmC, out_bf16, N, M, out_pitch, 64, kSeqGemmBM);
+    if (r) return r;
+    if (resid_bf16) {
+      r = encode_bf16_2d(&P.tmR, resid_bf16, N, M, resid_pitch, 64, kSeqGemmBM);
+      if (r) return r;
+    }
+    const int ntiles = P.tiles_m * P.tiles_n;
+    const int nclusters = ntiles < g_pair_clusters ? ntiles : g_pair_clusters;
+    const size_t smem = static_cast<size_t>(P.nstages) * P.stage_bytes + 2 * kSeqGemmStageOutBytes + rbuf_bytes + kSeqGemmHeader + 1024;
+    const cudaStream_t st2 = reinterpret_cast<cudaStream_t>(stream);
+    const bool dbg = P.dbg != nullptr || P.dbg_mmas != 0;
+    if (kkb == 2) {
+      if (dbg) seq_gemm2_kernel<2, true><<<2 * nclusters, kSeqGemmThreads, smem, st2>>>(P);
+      else seq_gemm2_kernel<2, false><<<2 * nclusters, kSeqGemmThreads, smem, st2>>>(P);
+    } else {
+      if (dbg) seq_gemm2_kernel<1, true><<<2 * nclusters, kSeqGemmThreads, smem, st2>>>(P);
+      else seq_gemm2_kernel<1, false><<<2 * nclusters, kSeqGemmThreads, smem, st2>>>(P);
+    }
+    SEQ_CUDA_OK(cudaGetLastError());
+    return 0;
+  }
   P.tiles_m = cdiv(M, kSeqGemmBM);
   // widest tile that still gives every SM work; 256 columns keep one UMMA busy for 128 cycles
   int bn = 256;

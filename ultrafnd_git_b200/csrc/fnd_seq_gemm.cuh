@@ -54,6 +54,8 @@ struct alignas(64) SeqGemmParams {
   int mn;
   int splits, kb_per_split;
   long long split_stride;                        // floats between the partial outputs of consecutive splits
+  long long* dbg;                                // probe aid (fnd_seq_debug_gemm_stamps, pair kernel): 8 cycle counters per cluster
+  int dbg_mmas;                                  // probe aid (FND_SEQ_DBG_MMAS, pair kernel): issue only this many of the 4 UMMAs per k-block
 };
 
 __global__ void __launch_bounds__(kSeqGemmThreads, 1) seq_gemm_kernel(const __grid_constant__ SeqGemmParams P) {
@@ -226,6 +228,13 @@ __global__ void __launch_bounds__(kSeqGemmThreads, 1) seq_gemm_kernel(const __gr
           epi_bar_sync();
           if (P.resid) mbar_wait(&rfull_bar[sb], (slab_ctr >> 1) & 1u, P.err, FND_DEV_TIMEOUT_EPILOGUE);
           const uint8_t* rrow = rbuf + sb * kSeqGemmStageOutBytes + row * 128;
+          // the slab's 64 bias values, requested back to back BEFORE the accumulator load is waited for: loads left next to
+          // their use were issued one chunk at a time (ncu: the epilogue's top stalls were the FADDs behind them)
+          float4 bq[16];
+          if (P.bias) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) bq[i] = __ldg(reinterpret_cast<const float4*>(P.bias + min(n0 + 4 * i, P.N - 4)));
+          }
           uint32_t r0[32], r1[32];
           tmem_ld_32x32(taddr + c, r0);
           tmem_ld_32x32(taddr + c + 32, r1);
@@ -236,10 +245,8 @@ __global__ void __launch_bounds__(kSeqGemmThreads, 1) seq_gemm_kernel(const __gr
             float v[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(ch < 4 ? r0[ch * 8 + j] : r1[(ch - 4) * 8 + j]);
-            const int n = n0 + ch * 8;
-            if (P.bias && n < P.N) {
-              const float4 b0 = __ldg(reinterpret_cast<const float4*>(P.bias + n));
-              const float4 b1 = __ldg(reinterpret_cast<const float4*>(P.bias + n + 4));
+            if (P.bias) {                                    // (columns >= N are clipped by the TMA store)
+              const float4 b0 = bq[2 * ch], b1 = bq[2 * ch + 1];
               v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
               v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
             }

@@ -86,6 +86,8 @@ class FusedStep:
         # FND_DP_FUSED=1 (default; bf16 wire format only): the weight-gradient launch's epilogue stores every tile straight
         # into its owner's staging slot over NVLink (no separate push kernel, the fp32 gradient never touches HBM).
         self.dp_fused = os.environ.get("FND_DP_FUSED", "1") == "1"
+        # FND_WG_EARLY=1: single-GPU step with the fuse_mlp weight gradients launched early on a side stream
+        self.wg_early = os.environ.get("FND_WG_EARLY", "0") == "1"
         self._side_stream: Optional[torch.cuda.Stream] = None
         self._graphs: Dict[str, torch.cuda.CUDAGraph] = {}
         dev = self.engine.device
@@ -170,6 +172,13 @@ class FusedStep:
                     self._side_stream = torch.cuda.Stream(self.engine.device)
                 side = self._side_stream.cuda_stream
             check(lib.fnd_train_step_dp(h, ctypes.byref(inp), self.engine.stream_ptr(), side, flags | fused), "fnd_train_step_dp")
+            return
+        if entry == "train_step" and self.wg_early:
+            # fuse_mlp weight gradients on a side stream under the rest of the backward chain (fork / join inside the call)
+            if self._side_stream is None:
+                self._side_stream = torch.cuda.Stream(self.engine.device)
+            check(lib.fnd_train_step_overlap(h, ctypes.byref(inp), self.engine.stream_ptr(), self._side_stream.cuda_stream),
+                  "fnd_train_step_overlap")
             return
         fn = {"train_step": lib.fnd_train_step, "train_fwd_bwd": lib.fnd_train_fwd_bwd, "eval_step": lib.fnd_eval_step}[entry]
         check(fn(h, ctypes.byref(inp), self.engine.stream_ptr()), "fnd_" + entry)
