@@ -455,3 +455,29 @@ def test_train_b128_against_reference_outputs(precision):
         worst = max(worst, abs(got - ref) / ref)
         assert abs(got - ref) / ref < (5e-4 if precision == "fp32" else 5e-2), (name, got, ref)
     print(f"[train_b128/{precision}] loss {st['loss']} vs {float(z['train.loss'])}; worst gradient-norm rel-err {worst:.2e}")
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_train_step_overlap_is_bit_identical(use_graph):
+    """fnd_train_step_overlap (fuse_mlp weight gradients on a side stream under the rest of the backward chain) runs the same
+    tiles and writes the same norm slots as fnd_train_step: parameters, Adam moments and losses must be BIT-identical after
+    several steps with dropout on (forensic_trainer.py:285-298 is the step both replace)."""
+    batch = O.make_batch(128, seed=21)
+    res = []
+    for early in (False, True):
+        torch.manual_seed(3)
+        f, c = CrossModalTransformer(precision="bf16"), DeepTruthClassifier(precision="bf16")
+        f.train(); c.train()
+        st = FusedStep(f, c, 128, precision="bf16", use_graph=use_graph)
+        st.wg_early = early
+        st.load_batch({k: v.cuda() for k, v in batch.items()})
+        losses = []
+        for _ in range(4):
+            st.train_step()
+            losses.append(st.plan.state()["loss"])
+        st.plan.check_error()
+        eng = st.engine
+        res.append((losses, eng.params.clone(), eng.adam_m.clone(), eng.adam_v.clone()))
+    (l0, p0, m0, v0), (l1, p1, m1, v1) = res
+    assert l0 == l1
+    assert torch.equal(p0, p1) and torch.equal(m0, m1) and torch.equal(v0, v1)

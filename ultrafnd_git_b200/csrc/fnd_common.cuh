@@ -310,6 +310,9 @@ __device__ __forceinline__ uint64_t desc64(uint32_t lo, uint32_t hi) {
 // Single-probe wait helpers for the hot issue loops: spin on try_wait (the instruction itself blocks for a hardware
 // time slice), fall back to the bounded wait only after many failed probes.
 __device__ __forceinline__ bool mbar_wait_fast(uint64_t* bar, uint32_t parity, int* err, int code) {
+#ifndef FND_NO_TEST_WAIT
+  if (mbar_test_wait(bar, parity)) return true;      // phase already complete (the common case in a running pipeline)
+#endif
 #pragma unroll 1
   for (int i = 0; i < 4096; ++i)
     if (mbar_try_wait(bar, parity)) return true;

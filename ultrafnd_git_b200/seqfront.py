@@ -165,11 +165,14 @@ class SequenceFrontEnd(nn.Module):
             X[name] = S.layernorm(y, self.embed_ln[name].weight, self.embed_ln[name].bias, self.eps)
             if saved is not None:
                 saved[f"x.{name}"], saved[f"pre.{name}"] = xb.view(B * L, -1), y
+        # (Forward-only calls: with activations kept for the backward the second stream's allocations made the host stall in
+        # the caching allocator — measured 50-130 ms per eager step — so the training forward stays on one stream unless
+        # FND_SEQ_STREAMS_TRAIN=1.)
         # The two directions of a block only meet in the attention kernels (each needs BOTH [Q|K|V] projections): side a runs on
         # the current stream, side b on a second one, forked / joined by events (capturable: the block stays one CUDA graph).
         # Every kernel here is a persistent one-CTA-per-SM grid, so what this buys is the tails: the next kernel's CTAs start on
         # the SMs the previous one has already left (co-attention block at the stress shape: 0.616 -> 0.592 ms).
-        two = self.two_streams
+        two = self.two_streams and (saved is None or os.environ.get("FND_SEQ_STREAMS_TRAIN", "0") == "1")
         cur = torch.cuda.current_stream(dev)
         if two:
             if self._side is None or self._side.device != dev:
