@@ -92,7 +92,7 @@ static int build_tables(Plan& P) {
     e.out_pre = P.buf<float>("z_p0"); e.pre_pitch = H;
     e.act = 1; e.drop_p = d.clf_dropout; e.drop_stream = kStreamPre0;
     e.out_hi = P.buf<__nv_bfloat16>("xp1_hi"); e.out_lo = P.buf<__nv_bfloat16>("xp1_lo"); e.bf_pitch = H;
-    FND_OK(add_problem(P, P.fwd_p0, tb.act("fusedbf", 0, H, false), tb.weight_rp(false), B, H, H, P.cfg_pre.bn, 1, e, "", 1));
+    FND_OK(add_problem(P, P.fwd_p0, tb.act("fusedbf", 0, H, false), tb.weight_rp(false), B, H, H, P.cfg_pre.bn, P.cfg_pre.splits, e, "p0", 1));
   }
   {
     P.fwd_p1.kind = 0;
@@ -102,7 +102,7 @@ static int build_tables(Plan& P) {
     e.act = 1; e.drop_p = d.clf_dropout; e.drop_stream = kStreamPre1;
     e.out_f32 = P.buf<float>("h"); e.f32_pitch = H;
     e.out_hi = P.buf<__nv_bfloat16>("hbf_hi"); e.out_lo = P.buf<__nv_bfloat16>("hbf_lo"); e.bf_pitch = H;
-    FND_OK(add_problem(P, P.fwd_p1, tb.act("xp1", 0, H, false), tb.weight("clf.pre.3.weight", H, false), B, H, H, P.cfg_pre.bn, 1, e, "", 1));
+    FND_OK(add_problem(P, P.fwd_p1, tb.act("xp1", 0, H, false), tb.weight("clf.pre.3.weight", H, false), B, H, H, P.cfg_pre.bn, P.cfg_pre.splits, e, "p1", 1));
   }
 
   // ---------------- dgrad (A = dY K-major, B = W viewed MN-major) ----------------

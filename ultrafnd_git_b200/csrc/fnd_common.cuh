@@ -216,6 +216,15 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+// 32 bytes from a shared::cluster address (a peer CTA's shared memory, see mapa_shared)
+__device__ __forceinline__ void ld_cluster_f8(uint32_t cluster_addr, float (&v)[8]) {
+  asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(cluster_addr) : "memory");
+  asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "r"(cluster_addr + 16u) : "memory");
+}
 // shared::cluster address of the same shared-memory location in CTA `rank` of the cluster
 __device__ __forceinline__ uint32_t mapa_shared(uint32_t saddr, uint32_t rank) {
   uint32_t r;

@@ -148,7 +148,8 @@ struct GemmCfg { int bn = 64; int splits = 1; };
 // in one wave of 148 CTAs (more SMs streaming weights, shorter epilogue per CTA). Long-K problems (K >= 2048) take
 // 128-wide tiles instead so the activation panel is re-read by few CTAs, and are split along K (one CTA per SM, see
 // fnd_gemm.cuh) when a CTA would otherwise stream more than ~600 KB by itself.
-inline GemmCfg pick_cfg(int B, const std::vector<std::pair<int, int>>& nk, bool b_mn, int ncombo, bool allow_split) {
+inline GemmCfg pick_cfg(int B, const std::vector<std::pair<int, int>>& nk, bool b_mn, int ncombo, bool allow_split,
+                        int cluster_split = 0) {
   const int tm = ceil_div(B, kGemmBM);
   int kmax = 0;
   for (auto& p : nk) kmax = p.second > kmax ? p.second : kmax;
@@ -179,6 +180,14 @@ inline GemmCfg pick_cfg(int B, const std::vector<std::pair<int, int>>& nk, bool 
     // a handful of wide (MN-major B: >= 64 columns) tiles: four splits shorten both the operand stream and the
     // per-CTA epilogue (the fix-up is spread over the splits) by more than the exchange costs (measured)
     c.splits = 4;
+  }
+  if (c.splits == 1 && cluster_split > 1 && kb >= 8) {
+    // Cluster split-K (fnd_gemm.cuh: partial tiles exchanged through distributed shared memory, ~1 us instead of the ~2.5 us
+    // L2 rendezvous): a latency-chain GEMM whose 32 CTAs each stream the whole 128 x K activation panel becomes 128 CTAs
+    // that stream a quarter of it. Narrowest tile whose split grid still fits one wave.
+    const int cands[4] = {16, 32, 64, 128};
+    for (int i = b_mn ? 2 : 0; i < 4; ++i)
+      if (ctas_at(cands[i]) * cluster_split <= 148) { c.bn = cands[i]; c.splits = cluster_split; break; }
   }
   return c;
 }
@@ -295,11 +304,14 @@ inline void carve(Plan& P) {
     const int Hh = P.H, cat = P.nslots * P.H, nc = P.ncombo;
     std::vector<std::pair<int, int>> proj, qkv = {{2 * Hh, Hh}, {3 * Hh, Hh}, {2 * Hh, Hh}, {2 * Hh, Hh}};
     for (int i = 0; i < P.nmod; ++i) proj.push_back({Hh, P.xdim[i]});
+    // (measured and not kept: cluster split-K x2 for the projections, 19.6 -> 21.0 us, and x4 with 128-column tiles for the
+    //  q/k/v launch, 14.5 -> 25.4 us — their 80 / 144 narrow-tile CTAs already spread the panel over the chip)
     P.cfg_proj = pick_cfg(P.B, proj, false, nc, false);
     P.cfg_qkv = pick_cfg(P.B, qkv, false, nc, false);
     P.cfg_f0 = pick_cfg(P.B, {{2 * Hh, cat}}, false, nc, true);
-    P.cfg_f1 = pick_cfg(P.B, {{Hh, 2 * Hh}}, false, nc, true);
-    P.cfg_pre = pick_cfg(P.B, {{Hh, Hh}}, false, nc, false);
+    const int csk = cluster_splitk_enabled() ? 4 : 0;
+    P.cfg_f1 = pick_cfg(P.B, {{Hh, 2 * Hh}}, false, nc, true, csk);
+    P.cfg_pre = pick_cfg(P.B, {{Hh, Hh}}, false, nc, false, csk);
     P.cfg_dg_pre = pick_cfg(P.B, {{Hh, Hh}}, true, nc, true);
     P.cfg_dg_f1 = pick_cfg(P.B, {{2 * Hh, Hh}}, true, nc, true);
     P.cfg_dg_f0 = pick_cfg(P.B, {{cat, 2 * Hh}}, true, nc, true);
@@ -311,6 +323,8 @@ inline void carve(Plan& P) {
     };
     split_bufs("f0", P.cfg_f0, 2 * Hh);
     split_bufs("f1", P.cfg_f1, Hh);
+    split_bufs("p0", P.cfg_pre, Hh);
+    split_bufs("p1", P.cfg_pre, Hh);
     split_bufs("dgf1", P.cfg_dg_f1, 2 * Hh);
     split_bufs("dgf0", P.cfg_dg_f0, cat);
     split_bufs("dgp1", P.cfg_dg_pre, Hh);

@@ -139,6 +139,8 @@ struct GemmTableP {
   int nprob;
   int a_mn, b_mn;     // 0: K-major, 1: MN-major
   int gemm_ctas;      // CTAs [gemm_ctas, gridDim.x) of a kVariant == 1 launch run finalize jobs instead of a tile
+  int cluster_k;      // 1: the launch's clusters are the k-splits of a tile (cluster size == splits of every problem): the
+                      //    split-K partials are exchanged through distributed shared memory instead of an L2 workspace
 };
 
 struct EpiCtx {
@@ -349,6 +351,7 @@ fnd_gemm_kernel(const __grid_constant__ GemmTableP tbl, RunCtx ctx, const __grid
       }
     }
     __syncwarp();
+    if (kVariant == 0 && tbl.cluster_k && splits > 1) { cluster_arrive(); cluster_wait(); cluster_arrive(); cluster_wait(); }
   } else if (warp == 1) {
     // ================= MMA issuer =================
     if (lane == 0) {
@@ -379,6 +382,7 @@ fnd_gemm_kernel(const __grid_constant__ GemmTableP tbl, RunCtx ctx, const __grid
       FND_STAMP(3);
     }
     __syncwarp();
+    if (kVariant == 0 && tbl.cluster_k && splits > 1) { cluster_arrive(); cluster_wait(); cluster_arrive(); cluster_wait(); }
   } else {
     // ================= epilogue (warps 2..9) =================
     // Deliberately ROLLED (8 columns per iteration, #pragma unroll 1): a fully unrolled epilogue was ~100 KB of
@@ -551,6 +555,66 @@ fnd_gemm_kernel(const __grid_constant__ GemmTableP tbl, RunCtx ctx, const __grid
         for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[j]);
         ss += epi_group(E, X, v, m, n0, PN, a0, a1);
       }
+    } else if (kVariant == 0 && tbl.cluster_k) {
+      // ---- split-K inside a cluster: the `splits` CTAs of a tile ARE the cluster (rank == split). Each CTA parks its partial
+      // tile in its own shared memory (the operand ring is dead: every MMA has retired), one cluster barrier replaces the
+      // fence + atomic-counter rendezvous, and every split sums its share of the tile straight out of its peers' shared
+      // memory (ld.shared::cluster) in the same fixed split order as the L2 path below — bit-identical results, no
+      // workspace round trip through L2. A second cluster barrier keeps every CTA's partial alive until its peers have read it.
+      float* const part = reinterpret_cast<float*>(smem);            // [group][row][8]
+#pragma unroll 1
+      for (int g = half; g < ngroups; g += 2) {
+        uint32_t r[8];
+        tmem_ld_32x8(taddr + g * 8, r);
+        tmem_ld_wait();
+        float* dst = part + (static_cast<size_t>(g) * kGemmBM + row) * 8;
+        *reinterpret_cast<uint4*>(dst) = make_uint4(r[0], r[1], r[2], r[3]);
+        *reinterpret_cast<uint4*>(dst + 4) = make_uint4(r[4], r[5], r[6], r[7]);
+      }
+      cluster_arrive();
+      cluster_wait();
+      if (epi_tid == 0) FND_STAMP(5);
+      const int nunits = ngroups * 4;
+      const uint32_t part_u32 = smem_u32(part);
+#pragma unroll 1
+      for (int u = split + ew * splits; u < nunits; u += kGemmEpiWarps * splits) {
+        const int g = u >> 2, q = u & 3;
+        const int urow = q * 32 + lane;
+        const int um = tm * kGemmBM + urow;
+        const int n0 = nb + g * 8;
+        const uint32_t off = part_u32 + static_cast<uint32_t>((g * kGemmBM + urow) * 32);
+        float v[8];
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) v[jj] = 0.f;
+#pragma unroll 1
+        for (int s2 = 0; s2 < splits; s2 += 4) {                     // four peers in flight, summed in split order
+          float t[4][8];
+#pragma unroll
+          for (int qq = 0; qq < 4; ++qq) {
+            const bool okq = s2 + qq < splits;
+            ld_cluster_f8(mapa_shared(off, static_cast<uint32_t>(okq ? s2 + qq : s2)), t[qq]);
+            if (!okq) {
+#pragma unroll
+              for (int jj = 0; jj < 8; ++jj) t[qq][jj] = 0.f;
+            }
+          }
+#pragma unroll
+          for (int qq = 0; qq < 4; ++qq) {
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) v[jj] += t[qq][jj];
+          }
+        }
+        if (!proceed || um >= PM || n0 >= PN) continue;
+        float a0 = 0.f, a1 = 0.f;
+        if (E.aux) {
+          a0 = E.aux[static_cast<size_t>(um) * 2];
+          a1 = E.aux[static_cast<size_t>(um) * 2 + 1];
+        }
+        ss += epi_group(E, X, v, um, n0, PN, a0, a1);
+      }
+      __syncwarp();
+      cluster_arrive();
+      cluster_wait();
     } else if (kVariant == 0) {
       // ---- split-K: publish this CTA's partial tile, wait for the other splits, finish a share of the tile ----
       // partial layout [split][group][row][8]: a warp's 32 rows of one group are 1 KB contiguous, so both the write

@@ -44,6 +44,35 @@ inline cudaError_t launch_k(void (*kern)(KArgs...), int grid, int block, size_t 
   cfg.numAttrs = (pdl && pdl_enabled()) ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kern, KArgs(std::forward<Args>(args))...);
 }
+// The same launch with thread-block clusters of `cluster` consecutive CTAs (grid must be a multiple of it).
+template <class... KArgs, class... Args>
+inline cudaError_t launch_k_cluster(void (*kern)(KArgs...), int grid, int block, size_t smem, cudaStream_t st, bool pdl,
+                                    int cluster, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(static_cast<unsigned>(grid), 1, 1);
+  cfg.blockDim = dim3(static_cast<unsigned>(block), 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[2];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = static_cast<unsigned>(cluster);
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = (pdl && pdl_enabled()) ? 2 : 1;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(std::forward<Args>(args))...);
+}
+inline bool cluster_splitk_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("FND_CLUSTER_SPLITK");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
+}
 
 // Fills one problem; returns 0 or a negative error. `cta_begin` is assigned by the caller (finish_table).
 inline int fill_problem(GemmProblem& p, const Operand& A, const Operand& B, int M, int N, int K, int bn, int splits,
@@ -156,7 +185,21 @@ inline cudaError_t launch_gemm(int kind, const GemmProblem* host_table, int npro
   const int smem = gemm_smem_bytes(host_table, nprob);
   if (!gemm_launch_is_light(kind, host_table, nprob) && fin_ctas > 0) return cudaErrorInvalidValue;
   const bool light = gemm_launch_is_light(kind, host_table, nprob);
+  t.cluster_k = 0;
   if (light) return launch_k(fnd_gemm_kernel<1>, grid + fin_ctas, kGemmThreads, smem, st, pdl, t, ctx, f);
+  // (16-CTA clusters for the 16 k-splits of gemm_fuse0 — non-portable size — were measured too: no change in the step.)
+  // Split-K launches whose problems all use the same 2 / 4 / 8 splits run as clusters of the k-splits of a tile and exchange
+  // their partial tiles through distributed shared memory (every problem's CTA count is a multiple of its splits, so the
+  // clusters line up with the tiles); a partial tile must fit in the problem's (dead) operand ring.
+  const int S = host_table[0].splits;
+  bool ck = cluster_splitk_enabled() && (S == 2 || S == 4 || S == 8) && grid % S == 0;
+  for (int i = 0; i < nprob && ck; ++i)
+    ck = host_table[i].splits == S && host_table[i].cta_begin % S == 0 &&
+         host_table[i].nstages * host_table[i].stage_bytes >= kGemmBM * host_table[i].bn * 4;
+  if (ck) {
+    t.cluster_k = 1;
+    return launch_k_cluster(fnd_gemm_kernel<0>, grid, kGemmThreads, smem, st, pdl, S, t, ctx, f);
+  }
   return launch_k(fnd_gemm_kernel<0>, grid, kGemmThreads, smem, st, pdl, t, ctx, f);
 }
 
