@@ -77,6 +77,28 @@ __device__ __forceinline__ void store_bf2(__nv_bfloat16* hi, __nv_bfloat16* lo, 
   }
 }
 
+// Four / eight consecutive elements: ONE 64-bit / 128-bit store per operand plane (idx a multiple of 4 / 8 elements).
+__device__ __forceinline__ void store_bf4(__nv_bfloat16* hi, __nv_bfloat16* lo, size_t idx, const float4& v) {
+  const uint32_t p0 = pack_bf16x2(v.x, v.y), p1 = pack_bf16x2(v.z, v.w);
+  *reinterpret_cast<uint2*>(hi + idx) = make_uint2(p0, p1);
+  if (lo) {
+    const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&p0), b = *reinterpret_cast<const __nv_bfloat162*>(&p1);
+    *reinterpret_cast<uint2*>(lo + idx) = make_uint2(pack_bf16x2(v.x - __low2float(a), v.y - __high2float(a)),
+                                                     pack_bf16x2(v.z - __low2float(b), v.w - __high2float(b)));
+  }
+}
+__device__ __forceinline__ void store_bf8(__nv_bfloat16* hi, __nv_bfloat16* lo, size_t idx, const float (&v)[8]) {
+  uint32_t ph[4], pl[4];
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    ph[t] = pack_bf16x2(v[2 * t], v[2 * t + 1]);
+    const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&ph[t]);
+    pl[t] = pack_bf16x2(v[2 * t] - __low2float(h2), v[2 * t + 1] - __high2float(h2));
+  }
+  *reinterpret_cast<uint4*>(hi + idx) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+  if (lo) *reinterpret_cast<uint4*>(lo + idx) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+}
+
 // ---------------------------------------------------------------------------------------------
 // prep: cast inputs to bf16 hi/lo, gather aux/labels, and alpha = softmax(gates)
 // ---------------------------------------------------------------------------------------------
@@ -119,10 +141,15 @@ __global__ void __launch_bounds__(kRowThreads) prep_kernel(PrepParams p) {
     for (int m = 0; m < p.nmod; ++m) {
       const float* xs = p.x[m] + static_cast<size_t>(src) * p.xpitch[m];
       const size_t obase = static_cast<size_t>(b) * p.dsum + p.xoff[m];
-      for (int c = threadIdx.x * 4; c < p.xdim[m]; c += kRowThreads * 4) {
-        const float4 v = ldg_f4(xs + c);
-        store_bf2(p.out_hi, p.out_lo, obase + c, v.x, v.y);
-        store_bf2(p.out_hi, p.out_lo, obase + c + 2, v.z, v.w);
+      if (((p.xdim[m] | p.xoff[m] | p.dsum | p.xpitch[m]) & 7) == 0 && (reinterpret_cast<uintptr_t>(xs) & 31) == 0) {
+        // 8 elements per thread: two 128-bit loads, one 128-bit store per plane
+        for (int c = threadIdx.x * 8; c < p.xdim[m]; c += kRowThreads * 8) {
+          float v[8];
+          ldg_f8(xs + c, v);
+          store_bf8(p.out_hi, p.out_lo, obase + c, v);
+        }
+      } else {
+        for (int c = threadIdx.x * 4; c < p.xdim[m]; c += kRowThreads * 4) store_bf4(p.out_hi, p.out_lo, obase + c, ldg_f4(xs + c));
       }
     }
     if (threadIdx.x == 0) {
@@ -690,8 +717,7 @@ __global__ void __launch_bounds__(256) head_kernel(HeadParams p) {
         float4 a = acc[i];
         a.x *= gelu_erf_grad(z.x) * mm[0]; a.y *= gelu_erf_grad(z.y) * mm[1];
         a.z *= gelu_erf_grad(z.z) * mm[2]; a.w *= gelu_erf_grad(z.w) * mm[3];
-        store_bf2(p.dz_hi, p.dz_lo, static_cast<size_t>(b) * H + j, a.x, a.y);
-        store_bf2(p.dz_hi, p.dz_lo, static_cast<size_t>(b) * H + j + 2, a.z, a.w);
+        store_bf4(p.dz_hi, p.dz_lo, static_cast<size_t>(b) * H + j, a);
       }
       __syncwarp();
       FND_HSTAMP(6);
@@ -754,12 +780,13 @@ __global__ void __launch_bounds__(256) gate_kernel(GateParams p) {
        i += static_cast<size_t>(gridDim.x) * blockDim.x * 8) {
     float mm[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f};
     if (dc.p > 0.f) dropout_mult8(dc, stream_key(p.state->rng, p.stream), i >> 3, mm);
+    const float4 d0 = ldg_f4(p.dy + i), d1 = ldg_f4(p.dy + i + 4), z0 = ldg_f4(p.z + i), z1 = ldg_f4(p.z + i + 4);
+    const float d[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+    const float z[8] = {z0.x, z0.y, z0.z, z0.w, z1.x, z1.y, z1.z, z1.w};
+    float o[8];
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const float4 d = ldg_f4(p.dy + i + 4 * h), z = ldg_f4(p.z + i + 4 * h);
-      store_bf2(p.out_hi, p.out_lo, i + 4 * h, d.x * gelu_erf_grad(z.x) * mm[4 * h], d.y * gelu_erf_grad(z.y) * mm[4 * h + 1]);
-      store_bf2(p.out_hi, p.out_lo, i + 4 * h + 2, d.z * gelu_erf_grad(z.z) * mm[4 * h + 2], d.w * gelu_erf_grad(z.w) * mm[4 * h + 3]);
-    }
+    for (int j = 0; j < 8; ++j) o[j] = d[j] * gelu_erf_grad(z[j]) * mm[j];
+    store_bf8(p.out_hi, p.out_lo, i, o);           // one 128-bit store per operand plane
   }
 }
 
