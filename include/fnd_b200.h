@@ -186,6 +186,11 @@ int fnd_profile_end(void* plan, void* stream, char* names, float* ms, int cap, i
 /* Debug aid: limit >= 0 makes every entry point issue only its first `limit` kernel launches (prefix timing of the
  * step, tools/prefix_probe.py); -1 restores normal operation. Results are incomplete while a limit is set. */
 int fnd_debug_set_launch_limit(void* plan, int limit);
+/* Test aid: 1 (default) = split-K launches whose problems share 2 / 4 / 8 splits run as thread-block clusters and exchange
+ * their partial tiles through distributed shared memory; 0 = through the L2 workspace (round-1 path). Affects launches
+ * issued AFTER the call (plans keep their tile / split choices); both exchanges sum in the same split order, so results are
+ * bit-identical. Returns the previous value. Call outside graph capture; captured graphs keep what they captured. */
+int fnd_debug_set_cluster_splitk(int on);
 /* Number of kernel launches one call of the named entry point issues ("train_step", "eval_step", ...). */
 int fnd_launch_count(const void* plan, const char* entry);
 /* Dropout keep-multipliers (0 or 1/(1-p)) that the NEXT training forward will use for a layer

@@ -481,3 +481,35 @@ def test_train_step_overlap_is_bit_identical(use_graph):
     (l0, p0, m0, v0), (l1, p1, m1, v1) = res
     assert l0 == l1
     assert torch.equal(p0, p1) and torch.equal(m0, m1) and torch.equal(v0, v1)
+
+
+@pytest.mark.parametrize("precision", ["bf16", "fp32"])
+def test_cluster_splitk_exchange_is_bit_identical(precision):
+    """Split-K partial tiles exchanged through distributed shared memory inside thread-block clusters (csrc/fnd_gemm.cuh) vs
+    through the L2 workspace: same plan (same tiles and splits), same fixed summation order -> parameters, Adam moments and
+    losses must be BIT-identical after several optimizer steps with dropout on."""
+    from ultrafnd_git_b200 import _lib
+    lib = _lib.load()
+    batch = O.make_batch(128, seed=33)
+    res = []
+    try:
+        for on in (1, 0):
+            lib.fnd_debug_set_cluster_splitk(1)           # plans are laid out with the cluster-era tile / split choices
+            torch.manual_seed(5)
+            f, c = CrossModalTransformer(precision=precision), DeepTruthClassifier(precision=precision)
+            f.train(); c.train()
+            st = FusedStep(f, c, 128, precision=precision, use_graph=False)
+            st.load_batch({k: v.cuda() for k, v in batch.items()})
+            lib.fnd_debug_set_cluster_splitk(on)          # ... and launched through one exchange or the other
+            losses = []
+            for _ in range(3):
+                st.train_step()
+                losses.append(st.plan.state()["loss"])
+            st.plan.check_error()
+            eng = st.engine
+            res.append((losses, eng.params.clone(), eng.adam_m.clone(), eng.adam_v.clone()))
+    finally:
+        lib.fnd_debug_set_cluster_splitk(1)
+    (l1, p1, m1, v1), (l0, p0, m0, v0) = res
+    assert l1 == l0
+    assert torch.equal(p1, p0) and torch.equal(m1, m0) and torch.equal(v1, v0)

@@ -137,6 +137,7 @@ def _signatures() -> Dict[str, tuple]:
         "fnd_eval_step": (_c_int, [_c_void_p, P(FndInputs), _c_void_p]),
         "fnd_launch_count": (_c_int, [_c_void_p, ctypes.c_char_p]),
         "fnd_debug_set_launch_limit": (_c_int, [_c_void_p, _c_int]),
+        "fnd_debug_set_cluster_splitk": (_c_int, [_c_int]),
         "fnd_dp_bind": (_c_int, [_c_void_p, _c_int, _c_int, P(ctypes.c_ulonglong), ll, ll, ll, ll, ll, ll, _c_int, ctypes.c_ulonglong, ll,
                                  _c_void_p, ll, _c_void_p, ll]),
         "fnd_dp_stage_bytes": (ll, [_c_void_p, _c_int, _c_int]),

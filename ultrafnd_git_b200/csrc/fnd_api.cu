@@ -1160,6 +1160,12 @@ int fnd_eval_step(void* plan, const fnd_inputs* in, void* stream) {
   return run_head<true, false, false>(P, h, st);
 }
 
+int fnd_debug_set_cluster_splitk(int on) {
+  const int old = cluster_splitk_flag();
+  cluster_splitk_flag() = on ? 1 : 0;
+  return old;
+}
+
 int fnd_debug_set_launch_limit(void* plan, int limit) {
   Plan* PP = as_plan(plan);
   if (!PP) return -1;

@@ -65,14 +65,17 @@ inline cudaError_t launch_k_cluster(void (*kern)(KArgs...), int grid, int block,
   cfg.numAttrs = (pdl && pdl_enabled()) ? 2 : 1;
   return cudaLaunchKernelEx(&cfg, kern, KArgs(std::forward<Args>(args))...);
 }
-inline bool cluster_splitk_enabled() {
+// FND_CLUSTER_SPLITK=0 keeps the L2-workspace exchange (and the round-1 tile / split choices); fnd_debug_set_cluster_splitk
+// flips the LAUNCH-time choice only, so that a test can run the same plan through both exchanges.
+inline int& cluster_splitk_flag() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("FND_CLUSTER_SPLITK");
     v = (e && e[0] == '0') ? 0 : 1;
   }
-  return v != 0;
+  return v;
 }
+inline bool cluster_splitk_enabled() { return cluster_splitk_flag() != 0; }
 
 // Fills one problem; returns 0 or a negative error. `cta_begin` is assigned by the caller (finish_table).
 inline int fill_problem(GemmProblem& p, const Operand& A, const Operand& B, int M, int N, int K, int bn, int splits,
