@@ -97,6 +97,12 @@ int fnd_set_hyper(void* plan, float lr, float beta1, float beta2, float eps, flo
 int fnd_set_lr(void* plan, float lr, void* stream);
 int fnd_set_seed(void* plan, unsigned long long seed, void* stream);
 int fnd_set_loss_scale(void* plan, float scale, void* stream);   /* d(mean loss)/d(row loss); default 1/batch */
+/* Per-step loss without a copy: `host_mapped` = pinned, device-accessible HOST memory of `ring` floats (cudaHostAlloc /
+ * torch pin_memory under unified addressing). Every fnd_train_step / fnd_train_fwd_bwd then ALSO stores its mean loss
+ * (forensic_trainer.py:287, the value loss.item() would return at :301) into host_mapped[steps_taken % ring] from the CTA
+ * that computes it — a 4-byte device-to-host store instead of a stream-ordered D2H memcpy between two steps. Readable on
+ * the host once the step has completed (event / stream synchronisation). NULL switches it off. Bound plans only. */
+int fnd_set_loss_mirror(void* plan, float* host_mapped, int ring, void* stream);
 /* Rebuild the bf16 operand copies from the fp32 master parameters (after load_state_dict or an external
  * optimizer step). fnd_clip_adamw_step keeps them current by itself. */
 int fnd_refresh_shadows(void* plan, void* stream);

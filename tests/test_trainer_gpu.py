@@ -183,3 +183,27 @@ def test_epochs_match_reference_trainer():
     for k, v in sm.items():
         if f"test.{k}" in g.files and np.isscalar(v):
             assert abs(float(v) - float(g[f"test.{k}"])) <= 0.02 + 1e-3 * abs(float(g[f"test.{k}"]))
+
+
+def test_loss_mirror_delivers_every_steps_loss_to_pinned_host_memory():
+    """fnd_set_loss_mirror: the step stores its mean loss (forensic_trainer.py:287 / :301 loss.item()) into a pinned host ring,
+    slot = optimizer steps taken so far; it must equal DevState.loss of that step bit for bit, also from a CUDA graph and
+    after the ring wraps."""
+    import torch
+    from oracle import fnd_oracle as O
+    from ultrafnd_git_b200.fused import FusedStep
+    from ultrafnd_git_b200.modules import CrossModalTransformer, DeepTruthClassifier
+    torch.manual_seed(9)
+    f, c = CrossModalTransformer(precision="bf16"), DeepTruthClassifier(precision="bf16")
+    f.train(); c.train()
+    st = FusedStep(f, c, 32, precision="bf16", use_graph=True)
+    st.load_batch({k: v.cuda() for k, v in O.make_batch(32, seed=2).items()})
+    ring = st.enable_loss_mirror(4)
+    seen = []
+    for i in range(7):                                    # wraps the 4-slot ring
+        st.train_step()
+        s = st.plan.state()                               # synchronises
+        assert s["step"] == i + 1
+        seen.append(s["loss"])
+        assert float(ring[i % 4]) == s["loss"], (i, float(ring[i % 4]), s["loss"])
+    assert len(set(seen)) > 1

@@ -255,7 +255,7 @@ static int build_tables(Plan& P) {
           nullptr, P.G("fusion.attn_tv.evidence_proj.0.weight"), 0, 1.0f);
     }
     if (clf && fus) {   // fused step only: mean loss (the stand-alone finalize launches compute it in their last CTA)
-      job(T, kJobLossMean, B, 1, 1, P.buf<float>("loss_row"), nullptr, nullptr, nullptr, nullptr, 0, 1.0f);
+      job(T, kJobLossMean, B, 1, 1, P.buf<float>("loss_row"), nullptr, nullptr, nullptr, P.loss_mirror, P.loss_mirror ? P.loss_ring : 0, 1.0f);
       T.host.back().cta_count = 1;
       T.host.back().want_norm = 0;
     }
@@ -692,6 +692,24 @@ int fnd_set_seed(void* plan, unsigned long long seed, void* stream) {
 int fnd_set_loss_scale(void* plan, float scale, void* stream) {
   FND_PLAN(plan);
   return write_state(P, offsetof(DevState, loss_scale), &scale, sizeof(scale), st);
+}
+int fnd_set_loss_mirror(void* plan, float* host_mapped, int ring, void* stream) {
+  FND_PLAN(plan);
+  if (host_mapped && ring <= 0) return -1;
+  P.loss_mirror = host_mapped;
+  P.loss_ring = host_mapped ? ring : 0;
+  bool found = false;
+  for (auto& j : P.fin_all.host)
+    if (j.type == kJobLossMean) {
+      j.dst = host_mapped;
+      j.dst_pitch = host_mapped ? ring : 0;
+      found = true;
+    }
+  if (!found) return -2;
+  // the job table lives in device memory and is read at run time: already-captured graphs see the new pointer too
+  FND_CUDA_OK(cudaMemcpyAsync(P.fin_all.dev, P.fin_all.host.data(), P.fin_all.host.size() * sizeof(FinJob), cudaMemcpyHostToDevice, st));
+  FND_CUDA_OK(cudaStreamSynchronize(st));
+  return 0;
 }
 int fnd_refresh_shadows(void* plan, void* stream) {
   FND_PLAN(plan);

@@ -216,6 +216,8 @@ struct Plan {
   GemmTable dg_p1, dg_p0_fused, dg_p0_split, dg_f1, dg_f0, dg_qkv;
   GemmTable wg_all, wg_clf, wg_fus, wg_early, wg_rest;
   DpRoute dp_route;                 // fused-push routing table (filled by fnd_dp_bind)
+  float* loss_mirror = nullptr;     // fnd_set_loss_mirror: pinned device-mapped host ring the loss job also writes (kept over re-binds)
+  int loss_ring = 0;
   bool joined_side = false;         // fnd_train_step_overlap forked / joined the side stream in the step being enqueued
   bool dp_fused_now = false;        // the step being enqueued uses the fused push (set by train_fwd_bwd_impl, read by dp_tail)
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;   // data-parallel overlap: side-stream fork / join (early push)

@@ -948,7 +948,17 @@ __device__ __forceinline__ void finalize_cta(const FinParams& p, int cta, int nc
       if (threadIdx.x < o) dred[threadIdx.x] += dred[threadIdx.x + o];
       __syncthreads();
     }
-    if (threadIdx.x == 0) p.state->loss = static_cast<float>(dred[0] * static_cast<double>(p.state->loss_scale));
+    if (threadIdx.x == 0) {
+      const float loss = static_cast<float>(dred[0] * static_cast<double>(p.state->loss_scale));
+      p.state->loss = loss;
+      // optional mirror in pinned, device-mapped HOST memory (fnd_set_loss_mirror): the step's loss reaches the host as ONE
+      // 4-byte store from this CTA instead of a stream-ordered D2H copy between two steps (measured: that copy held the next
+      // step's first kernel back by ~15 us). Slot = optimizer steps taken so far, modulo the ring.
+      if (J.dst && J.dst_pitch > 0) {
+        *reinterpret_cast<volatile float*>(J.dst + (p.state->step % J.dst_pitch)) = loss;
+        __threadfence_system();
+      }
+    }
     __syncthreads();
   } else if (J.type == kJobSoftmaxBwd) {
     // dgate[j] = alpha[j] * (draw[j] - sum_j' alpha[j'] draw[j'])       (softmax backward of deep_truth_classifier.py:64)

@@ -276,6 +276,16 @@ class FusedStep:
         """Device view of DevState.loss (mean loss of the last training step)."""
         return self.plan.buffer("state", torch.float32, (22,))[13:14]
 
+    def enable_loss_mirror(self, ring: int = 4096) -> torch.Tensor:
+        """Per-step losses without a D2H copy: returns a pinned host tensor of `ring` floats; every later training step stores
+        its mean loss into slot (optimizer steps taken so far) % ring straight from the device (fnd_set_loss_mirror). Read it
+        after the step has completed (stream / event synchronisation) — the host-side counterpart of the reference's
+        ``loss.item()`` (forensic_trainer.py:301) without stalling the stream between two steps."""
+        self._loss_mirror = torch.zeros(int(ring), dtype=torch.float32).pin_memory()
+        check(self.engine.lib.fnd_set_loss_mirror(self.plan.handle, self._loss_mirror.data_ptr(), int(ring), self.engine.stream_ptr()),
+              "fnd_set_loss_mirror")
+        return self._loss_mirror
+
     def mark_params_updated(self) -> None:
         """The library's AdamW updates the arena (and the shadows) behind torch's back; keep the modules' shadow
         bookkeeping consistent so a later module-level forward does not refresh needlessly."""
