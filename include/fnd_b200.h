@@ -103,6 +103,12 @@ int fnd_set_loss_scale(void* plan, float scale, void* stream);   /* d(mean loss)
  * that computes it — a 4-byte device-to-host store instead of a stream-ordered D2H memcpy between two steps. Readable on
  * the host once the step has completed (event / stream synchronisation). NULL switches it off. Bound plans only. */
 int fnd_set_loss_mirror(void* plan, float* host_mapped, int ring, void* stream);
+/* Epoch bookkeeping (ForensicTrainer._epoch_loop, forensic_trainer.py:301-313: y, p1, row losses and the three forensic
+ * scalars of every batch): appends the first k rows of the LAST step's results ("loss_row", "probs"[:,1], the gathered labels,
+ * "rowstat"[:, :3]) at row `offset` of caller-owned device buffers, and `batch_no` into bid — one stream-ordered launch
+ * instead of five indexing ops per step; any destination may be NULL. forensic3 is [*, 3] row-major. */
+int fnd_collect_rows(void* plan, int k, long long offset, long long batch_no, float* loss_rows, float* p1, long long* ys,
+                     long long* bid, float* forensic3, void* stream);
 /* Rebuild the bf16 operand copies from the fp32 master parameters (after load_state_dict or an external
  * optimizer step). fnd_clip_adamw_step keeps them current by itself. */
 int fnd_refresh_shadows(void* plan, void* stream);

@@ -125,6 +125,8 @@ def _signatures() -> Dict[str, tuple]:
         "fnd_set_seed": (_c_int, [_c_void_p, ctypes.c_ulonglong, _c_void_p]),
         "fnd_set_loss_scale": (_c_int, [_c_void_p, _c_float, _c_void_p]),
         "fnd_set_loss_mirror": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_void_p]),
+        "fnd_collect_rows": (_c_int, [_c_void_p, _c_int, ctypes.c_longlong, ctypes.c_longlong, _c_void_p, _c_void_p, _c_void_p,
+                                      _c_void_p, _c_void_p, _c_void_p]),
         "fnd_refresh_shadows": (_c_int, [_c_void_p, _c_void_p]),
         "fnd_fusion_forward": (_c_int, [_c_void_p, P(FndInputs), _c_int, _c_void_p]),
         "fnd_classifier_forward": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_void_p]),

@@ -711,6 +711,17 @@ int fnd_set_loss_mirror(void* plan, float* host_mapped, int ring, void* stream) 
   FND_CUDA_OK(cudaStreamSynchronize(st));
   return 0;
 }
+int fnd_collect_rows(void* plan, int k, long long offset, long long batch_no, float* loss_rows, float* p1, long long* ys,
+                     long long* bid, float* forensic3, void* stream) {
+  FND_PLAN(plan);
+  if (k <= 0) return 0;
+  if (k > P.B || offset < 0) return -1;
+  P.pdl_next = false;
+  collect_rows_kernel<<<ceil_div(k, 256), 256, 0, st>>>(P.buf<float>("loss_row"), P.buf<float>("probs"), P.buf<long long>("labels"),
+                                                       P.buf<float>("rowstat"), k, offset, batch_no, loss_rows, p1, ys, bid, forensic3);
+  FND_CUDA_OK(cudaGetLastError());
+  return 0;
+}
 int fnd_refresh_shadows(void* plan, void* stream) {
   FND_PLAN(plan);
   AdamWParams a = adamw_params(P);

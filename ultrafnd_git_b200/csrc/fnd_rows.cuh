@@ -727,6 +727,29 @@ __global__ void __launch_bounds__(256) head_kernel(HeadParams p) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Epoch bookkeeping of the drop-in trainer (forensic_trainer.py:301-313 collects y / p1 / row losses / the three forensic
+// scalars of every batch with five host round trips): ONE launch appends a step's rows to the epoch buffers on the device.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) collect_rows_kernel(const float* __restrict__ loss_row, const float* __restrict__ probs,
+                                                           const long long* __restrict__ labels, const float* __restrict__ rowstat,
+                                                           int k, long long off, long long batch_no, float* __restrict__ loss_dst,
+                                                           float* __restrict__ p1_dst, long long* __restrict__ y_dst,
+                                                           long long* __restrict__ bid_dst, float* __restrict__ forensic_dst) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= k) return;
+  const long long o = off + i;
+  if (loss_dst) loss_dst[o] = loss_row[i];
+  if (p1_dst) p1_dst[o] = probs[2 * i + 1];
+  if (y_dst) y_dst[o] = labels[i];
+  if (bid_dst) bid_dst[o] = batch_no;
+  if (forensic_dst) {
+    forensic_dst[3 * o] = rowstat[16 * i];
+    forensic_dst[3 * o + 1] = rowstat[16 * i + 1];
+    forensic_dst[3 * o + 2] = rowstat[16 * i + 2];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Tiny Linear(H, 2): y = x W^T + b, one warp per row (fusion.classifier, cross_modal_transformer.py:130,198)
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) rowlinear2_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,

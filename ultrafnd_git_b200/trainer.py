@@ -29,6 +29,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from ._lib import check
 from .fused import DeviceCache, FusedStep, FEATURE_KEYS
 from .gcn import SimpleGCN, build_gnn_embeddings
 from .metrics import aggregate_epoch_metrics, pretty_print
@@ -336,11 +337,9 @@ class ForensicTrainer:
                 st.eval_step(from_cache=True)
             if k == 0:
                 continue
-            loss_rows[done:done + k] = st.loss_rows()
-            p1[done:done + k] = st.probs()[:, 1]
-            ys[done:done + k] = self.dcache.labels[local]
-            bid[done:done + k] = bno
-            forensic[done:done + k] = st.plan.buffer("rowstat", torch.float32, (k, 16))[:, :3]
+            # one launch appends this step's rows (row losses, p1, the labels the step gathered, forensic scalars, batch number)
+            check(st.engine.lib.fnd_collect_rows(st.plan.handle, k, done, bno, loss_rows.data_ptr(), p1.data_ptr(), ys.data_ptr(),
+                                                 bid.data_ptr(), forensic.data_ptr(), st.engine.stream_ptr()), "fnd_collect_rows")
             done += k
         if is_train and self._last_step is not None:
             self._last_step.mark_params_updated()
