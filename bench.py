@@ -456,16 +456,43 @@ def run_b200_arm(args):
     idx_pool = torch.stack([torch.arange(i * B, (i + 1) * B) for i in range(pool)]).to(dev)
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
 
+    # Row indices of step i+1 are staged into the OTHER of two index buffers by a side stream while the graph of step i runs:
+    # a 1 KB device-to-device copy enqueued in front of every graph launch delayed the step's first kernel like any other
+    # stream-ordered copy does (the end-to-end leg's 4-byte loss copy measured ~15 us).
+    idx_stream = torch.cuda.Stream(dev)
+    idx_ready = [torch.cuda.Event() for _ in range(2)]
+    idx_free = [torch.cuda.Event() for _ in range(2)]
+    main_stream = torch.cuda.current_stream(dev)
+    for e in idx_free:
+        e.record(main_stream)
+
+    def stage_indices(j):
+        s = j % 2
+        with torch.cuda.stream(idx_stream):
+            idx_stream.wait_event(idx_free[s])             # the graph that last read this buffer has been enqueued and finished
+            step.gather_set(s).copy_(idx_pool[j % pool], non_blocking=True)
+            idx_ready[s].record(idx_stream)
+
+    staged = {"next": None}
+
     def one_step(i):
-        step.static_gather.copy_(idx_pool[i % pool], non_blocking=True)
-        if world == 1:
-            step.train_step(from_cache=True)
-        elif dp_mode == "peer":
-            step.train_step_dp(from_cache=True)
-        else:
+        if world > 1 and dp_mode != "peer":
+            step.static_gather.copy_(idx_pool[i % pool], non_blocking=True)
             step.train_fwd_bwd(from_cache=True)
             dist.all_reduce(eng.grads)
             step.optimizer_step(norm_from_slots=False)
+            return
+        s = i % 2
+        if staged["next"] != i:                            # first step of a run (or a gap in the sequence)
+            stage_indices(i)
+        main_stream.wait_event(idx_ready[s])
+        if world == 1:
+            step.train_step(from_cache=True, input_set=s)
+        else:
+            step.train_step_dp(from_cache=True, input_set=s)
+        idx_free[s].record(main_stream)
+        stage_indices(i + 1)
+        staged["next"] = i + 1
 
     def barrier():
         if world > 1:

@@ -102,6 +102,8 @@ class FusedStep:
         self.static_in = torch.zeros(batch, self.in_pitch, dtype=torch.float32, device=dev)
         self.static_labels = torch.zeros(batch, dtype=torch.int64, device=dev)
         self.static_gather = torch.zeros(batch, dtype=torch.int64, device=dev)
+        # second index buffer: the row indices of step i+1 are staged (side stream) while the graph of step i reads the other
+        self.alt_gather = torch.zeros(batch, dtype=torch.int64, device=dev)
         self._inp_static = self._make_static_inputs()
         # A second input set for double-buffered host feeding: the H2D copy of batch i+1 lands in one set while the
         # graph of batch i reads the other (no device-to-device staging copy on the critical path).
@@ -109,6 +111,7 @@ class FusedStep:
         self.alt_labels = torch.zeros_like(self.static_labels)
         self._inp_alt = self._make_static_inputs(self.alt_in, self.alt_labels)
         self._inp_cache: Optional[FndInputs] = None
+        self._inp_cache_alt: Optional[FndInputs] = None
         self._cache: Optional[DeviceCache] = None
         self.engine.refresh_shadows(self.engine.param_version())
 
@@ -126,6 +129,10 @@ class FusedStep:
         inp.labels = labels.data_ptr()
         inp.gather = None
         return inp
+
+    def gather_set(self, which: int) -> torch.Tensor:
+        """Row-index buffer (int64 [B]) read by the cache-fed graphs of input set 0 / 1."""
+        return self.static_gather if which == 0 else self.alt_gather
 
     def input_set(self, which: int):
         """(inputs, labels) device buffers of input set 0 / 1 (layout of host_staging())."""
@@ -158,6 +165,7 @@ class FusedStep:
     def attach_cache(self, cache: DeviceCache) -> None:
         self._cache = cache
         self._inp_cache = cache.inputs(self.static_gather)
+        self._inp_cache_alt = cache.inputs(self.alt_gather)
         self._graphs.clear()
 
     # ------------------------------------------------------------------ launches
@@ -184,7 +192,10 @@ class FusedStep:
         check(fn(h, ctypes.byref(inp), self.engine.stream_ptr()), "fnd_" + entry)
 
     def _launch(self, entry: str, from_cache: bool, input_set: int = 0) -> None:
-        inp = self._inp_cache if from_cache else (self._inp_static if input_set == 0 else self._inp_alt)
+        if from_cache:
+            inp = self._inp_cache if input_set == 0 else self._inp_cache_alt
+        else:
+            inp = self._inp_static if input_set == 0 else self._inp_alt
         if inp is None:
             raise RuntimeError("attach_cache() first")
         if entry != "train_step_dp":
@@ -192,7 +203,7 @@ class FusedStep:
         if not self.use_graph:
             self._run(entry, inp)
             return
-        key = entry + ("/cache" if from_cache else ("/static" if input_set == 0 else "/alt"))
+        key = entry + (("/cache" if input_set == 0 else "/cache1") if from_cache else ("/static" if input_set == 0 else "/alt"))
         g = self._graphs.get(key)
         if g is None:
             # warm-up on a side stream (first launches set function attributes), then capture
