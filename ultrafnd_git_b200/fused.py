@@ -235,9 +235,9 @@ class FusedStep:
         self.engine._dp_pending = self.dp_defer
         self.plan.bump_all()
 
-    def train_fwd_bwd(self, from_cache: bool = False) -> None:
+    def train_fwd_bwd(self, from_cache: bool = False, input_set: int = 0) -> None:
         """Forward + loss + backward only (gradients left in the arena for an all-reduce)."""
-        self._launch("train_fwd_bwd", from_cache)
+        self._launch("train_fwd_bwd", from_cache, input_set)
         self.plan.bump_all()
 
     def dp_optimizer_step(self) -> None:
@@ -262,8 +262,8 @@ class FusedStep:
         check(self.engine.lib.fnd_clip_adamw_step(self.plan.handle, int(norm_from_slots), self.engine.stream_ptr()),
               "fnd_clip_adamw_step")
 
-    def eval_step(self, from_cache: bool = False) -> None:
-        self._launch("eval_step", from_cache)
+    def eval_step(self, from_cache: bool = False, input_set: int = 0) -> None:
+        self._launch("eval_step", from_cache, input_set)
         self.plan.bump_all()
 
     # ------------------------------------------------------------------ results (zero-copy views of the workspace)
