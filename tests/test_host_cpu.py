@@ -232,3 +232,37 @@ def test_sequence_frontend_host_logic_and_no_cpu_fallback():
         SequenceTrainer(fe)
     with pytest.raises(NotImplementedError):
         SequenceFrontEnd(100, 2)                                           # head dimension must be 64
+
+
+def test_shipped_library_contains_blackwell_native_sass():
+    """The built libfnd_b200.so really is sm_100a tensor-core code (runs without a GPU: cuobjdump only): tcgen05.mma in the
+    latency GEMM, the cta_group::2 forms in the CTA-pair projection GEMM, cluster barriers for the distributed-shared-memory
+    split-K exchange, TMA loads, and no legacy mma.sync (HMMA) anywhere."""
+    import re
+    import shutil
+    import subprocess
+    from ultrafnd_git_b200 import _lib
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    _lib.build(force=False)
+    sass = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    per = {}
+    cur = None
+    for line in sass.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            cur = m.group(1)
+            per[cur] = []
+        elif cur is not None and "/*" in line:
+            per[cur].append(line)
+
+    def count(kernel_substr, pattern):
+        return sum(len(re.findall(pattern, "\n".join(v))) for k, v in per.items() if kernel_substr in k)
+
+    assert count("fnd_gemm_kernel", r"\bUTCHMMA\b") > 0 and count("fnd_gemm_kernel", r"\bUTMALDG") > 0
+    assert count("fnd_gemm_kernelILi0", r"\bUCGABAR_") > 0                     # cluster split-K (general variant only)
+    assert count("seq_gemm2_kernel", r"\bUTCHMMA\.2CTA") > 0
+    assert count("seq_gemm2_kernel", r"\bUTCBAR\.2CTA\.MULTICAST") > 0
+    assert count("seq_gemm2_kernel", r"\bUTMALDG\.2D\.2CTA") > 0
+    assert count("seq_attn_fwd_kernel", r"\bUTCHMMA\b") > 0 and count("seq_attn_fwd_kernel", r"\bMUFU\.EX2") > 0
+    assert count("", r"\bHMMA\b") == 0
